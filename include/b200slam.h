@@ -1,0 +1,154 @@
+/* b200slam.h - C ABI of libb200slam.so: the B200-native (sm_100a) ALIKED + LightGlue
+ * frontend that stands behind SimpleSLAM's `slam/core/features_utils.py`.
+ *
+ * The reference has no FFI layer: its seam is the Python adapter
+ * `/root/reference/slam/core/features_utils.py`, which constructs and calls the
+ * un-vendored `lightglue` package.  Each entry point below names the reference call it
+ * replaces; INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative B2S_E* code; the message is
+ *    available from b2s_last_error() (thread local).  Nothing throws or aborts.
+ *  - "_dev" pointers are device pointers on the handle's device; the caller owns all I/O
+ *    buffers; work is enqueued on `stream` (a cudaStream_t passed as void*); the
+ *    library owns weights and workspaces.  Functions whose name ends in `_host` take host
+ *    pointers, copy in/out and synchronise before returning.
+ *  - a handle is bound to one device and is not thread-safe (one handle per device+stream).
+ *  - there is NO CPU fallback: without a CUDA device every create call fails.
+ */
+#ifndef B200SLAM_H_
+#define B200SLAM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_VERSION 100
+
+enum {
+  B2S_OK = 0,
+  B2S_EINVAL = -1,   /* bad argument / malformed weight blob */
+  B2S_ECUDA = -2,    /* CUDA runtime error (message has the cudaError string) */
+  B2S_ENOMEM = -3,
+  B2S_ENODEV = -4,   /* no usable sm_100 device */
+  B2S_ESIZE = -5     /* input larger than the handle supports */
+};
+
+enum { B2S_FP32 = 0, B2S_BF16 = 1 };
+enum { B2S_IMG_BGR_U8_HWC = 0, B2S_IMG_RGB_F32_CHW = 1 };
+
+typedef struct b2s_aliked b2s_aliked;
+typedef struct b2s_lg b2s_lg;
+
+/* replaces the keyword arguments of `ALIKED(max_num_keypoints=...)`, features_utils.py:25,
+ * plus upstream's default_conf (model_name, detection_threshold, nms_radius, resize). */
+typedef struct {
+  int model;            /* 0 = aliked-n16 (M=16), 1 = aliked-n32 (M=32) */
+  int max_kp;           /* n_limit; <=0 means upstream's 20000 */
+  float det_thresh;     /* 0.2 */
+  int nms_radius;       /* 2 (only 2 is supported) */
+  int resize_long;      /* 1024; <=0 disables resizing */
+  int precision;        /* B2S_FP32 | B2S_BF16 */
+} b2s_aliked_cfg;
+
+/* replaces `LightGlue(features='aliked')`, features_utils.py:26, plus upstream's default_conf. */
+typedef struct {
+  int n_layers;         /* 9 */
+  int heads;            /* 4 */
+  int dim;              /* 256 */
+  int in_dim;           /* 128 */
+  float depth_conf;     /* 0.95; <=0 disables early exit */
+  float width_conf;     /* 0.99; <=0 disables point pruning */
+  float filter_thresh;  /* 0.1 */
+  int pruning_min_kpts; /* prune a side only while it has more points than this; -1 = the
+                           reference's CPU setting (always), 1536 = its CUDA+flash setting */
+  int precision;        /* B2S_FP32 | B2S_BF16 */
+  int max_kp;           /* initial workspace size per image (grows on demand) */
+} b2s_lg_cfg;
+
+int b2s_version(void);
+const char* b2s_last_error(void);
+int b2s_device_count(void);
+
+void b2s_aliked_default_cfg(b2s_aliked_cfg* cfg);
+void b2s_lg_default_cfg(b2s_lg_cfg* cfg);
+
+/* weights: flat "B2SW" blob of fp32 tensors named as in the upstream state dict
+ * (layout in opencv-simpleslam_b200/weights.py::pack_state). */
+int b2s_aliked_create(const b2s_aliked_cfg* cfg, const void* weights, size_t nbytes, int device,
+                      b2s_aliked** out);
+void b2s_aliked_destroy(b2s_aliked* h);
+
+/* replaces `detector.extract(t0)` (features_utils.py:94) and, for B2S_IMG_BGR_U8_HWC,
+ * also `_bgr_to_tensor` (features_utils.py:219-222).
+ *   img_dev    : device image; u8 BGR HWC with `row_stride` bytes per row, or f32 RGB CHW
+ *                planar in [0,1] (row_stride ignored)
+ *   kpts_dev   : [max_kp,2] f32 keypoints in ORIGINAL-image pixels (x,y)
+ *   desc_dev   : [max_kp,128] f32 unit-norm descriptors
+ *   scores_dev : [max_kp] f32 upstream "keypoint_scores" (nullable)
+ *   n_out_dev  : device int32, number of valid rows  */
+int b2s_aliked_extract(b2s_aliked* h, const void* img_dev, int img_format, int H, int W,
+                       int row_stride, void* stream, float* kpts_dev, float* desc_dev,
+                       float* scores_dev, int32_t* n_out_dev);
+
+/* same, host buffers; copies in/out, synchronises, returns the count in *n_out. */
+int b2s_aliked_extract_host(b2s_aliked* h, const void* img_host, int img_format, int H, int W,
+                            int row_stride, float* kpts_host, float* desc_host,
+                            float* scores_host, int32_t* n_out);
+
+int b2s_lightglue_create(const b2s_lg_cfg* cfg, const void* weights, size_t nbytes, int device,
+                         b2s_lg** out);
+void b2s_lg_destroy(b2s_lg* h);
+
+/* replaces `matcher({'image0':{...}, 'image1':{...}})` (features_utils.py:157-161, :237).
+ *   k0/k1 : [m,2]/[n,2] f32 keypoints (pixels); d0/d1 : [m,128]/[n,128] f32 descriptors
+ *   size0/size1 : HOST pointers to (W,H) or NULL -> upstream's bounding-extent normalisation
+ *                 (NULL is what the reference's split path does, features_utils.py:158-161)
+ *   matches_dev  : [min(m,n),2] int32 (i in image0, j in image1), ascending i
+ *   mscores_dev  : [min(m,n)] f32
+ *   n_matches_dev: device int32
+ *   optional (nullable): matches0_dev [m] / matches1_dev [n] int32 (-1 = unmatched),
+ *   ms0_dev [m] / ms1_dev [n] f32, prune0_dev [m] / prune1_dev [n] int32.
+ *   stop_layer (host, nullable) receives the number of layers executed (upstream 'stop').
+ * The call synchronises `stream` internally where upstream needs a host decision
+ * (early exit / pruning) unless those are disabled in the cfg. */
+int b2s_lightglue_match(b2s_lg* h, const float* k0_dev, const float* d0_dev, int m,
+                        const float* k1_dev, const float* d1_dev, int n, const float* size0,
+                        const float* size1, void* stream, int32_t* matches_dev,
+                        float* mscores_dev, int32_t* n_matches_dev, int32_t* stop_layer,
+                        int32_t* matches0_dev, int32_t* matches1_dev, float* ms0_dev,
+                        float* ms1_dev, int32_t* prune0_dev, int32_t* prune1_dev);
+
+int b2s_lightglue_match_host(b2s_lg* h, const float* k0, const float* d0, int m, const float* k1,
+                             const float* d1, int n, const float* size0, const float* size1,
+                             int32_t* matches, float* mscores, int32_t* n_matches,
+                             int32_t* stop_layer, int32_t* matches0, int32_t* matches1,
+                             float* ms0, float* ms1, int32_t* prune0, int32_t* prune1);
+
+/* Batched matching of P independent pairs (keyframe-window all-pairs, BASELINE config 3).
+ * Keypoints/descriptors of F frames are packed; frame f owns rows [cu[f], cu[f+1]).
+ * pair p matches frame pair_i[p] against pair_j[p]; outputs for pair p start at row
+ * p*stride of matches_dev/mscores_dev, counts in n_matches_dev[p]. Host arrays: cu,
+ * pair_i, pair_j. */
+int b2s_lightglue_match_batch(b2s_lg* h, const float* kpts_dev, const float* desc_dev,
+                              const int32_t* cu, int n_frames, const int32_t* pair_i,
+                              const int32_t* pair_j, int n_pairs, void* stream, int stride,
+                              int32_t* matches_dev, float* mscores_dev, int32_t* n_matches_dev);
+
+/* Test hooks: copy a named intermediate of the most recent call to the host (fp32).
+ * Returns the number of floats available in *n (and copies min(*n, cap)). */
+int b2s_aliked_debug_get(b2s_aliked* h, const char* name, float* out, size_t cap, size_t* n);
+int b2s_lg_set_debug(b2s_lg* h, int on);
+int b2s_lg_debug_get(b2s_lg* h, const char* name, float* out, size_t cap, size_t* n);
+
+/* Number of CUDA kernels this library launched on behalf of the handle so far. */
+long long b2s_aliked_launch_count(const b2s_aliked* h);
+long long b2s_lg_launch_count(const b2s_lg* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SLAM_H_ */

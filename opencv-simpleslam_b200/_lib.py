@@ -1,0 +1,70 @@
+"""ctypes binding of libb200slam.so (include/b200slam.h).  There is no CPU fallback: if the
+shared library has not been built (`python -c "import __graft_entry__ as g; g.build()"` or
+`make -C opencv-simpleslam_b200/csrc`) importing this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200slam.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing - build the CUDA library first (make -C {_HERE}/csrc). "
+        "b200slam has no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+
+class AlikedCfg(C.Structure):
+    _fields_ = [("model", C.c_int), ("max_kp", C.c_int), ("det_thresh", C.c_float),
+                ("nms_radius", C.c_int), ("resize_long", C.c_int), ("precision", C.c_int)]
+
+
+class LgCfg(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("heads", C.c_int), ("dim", C.c_int), ("in_dim", C.c_int),
+                ("depth_conf", C.c_float), ("width_conf", C.c_float), ("filter_thresh", C.c_float),
+                ("pruning_min_kpts", C.c_int), ("precision", C.c_int), ("max_kp", C.c_int)]
+
+
+FP32, BF16 = 0, 1
+IMG_BGR_U8_HWC, IMG_RGB_F32_CHW = 0, 1
+vp, i32p, f32p = C.c_void_p, C.c_void_p, C.c_void_p   # raw addresses (device or host)
+
+SIGNATURES = {
+    "b2s_version": (C.c_int, []),
+    "b2s_last_error": (C.c_char_p, []),
+    "b2s_device_count": (C.c_int, []),
+    "b2s_aliked_default_cfg": (None, [C.POINTER(AlikedCfg)]),
+    "b2s_lg_default_cfg": (None, [C.POINTER(LgCfg)]),
+    "b2s_aliked_create": (C.c_int, [C.POINTER(AlikedCfg), vp, C.c_size_t, C.c_int, C.POINTER(vp)]),
+    "b2s_aliked_destroy": (None, [vp]),
+    "b2s_aliked_extract": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, f32p, f32p, f32p, i32p]),
+    "b2s_aliked_extract_host": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, i32p]),
+    "b2s_lightglue_create": (C.c_int, [C.POINTER(LgCfg), vp, C.c_size_t, C.c_int, C.POINTER(vp)]),
+    "b2s_lg_destroy": (None, [vp]),
+    "b2s_lightglue_match": (C.c_int, [vp, f32p, f32p, C.c_int, f32p, f32p, C.c_int, f32p, f32p, vp,
+                                      i32p, f32p, i32p, i32p, i32p, i32p, f32p, f32p, i32p, i32p]),
+    "b2s_lightglue_match_host": (C.c_int, [vp, f32p, f32p, C.c_int, f32p, f32p, C.c_int, f32p, f32p,
+                                           i32p, f32p, i32p, i32p, i32p, i32p, f32p, f32p, i32p, i32p]),
+    "b2s_lightglue_match_batch": (C.c_int, [vp, f32p, f32p, i32p, C.c_int, i32p, i32p, C.c_int, vp, C.c_int,
+                                            i32p, f32p, i32p]),
+    "b2s_aliked_debug_get": (C.c_int, [vp, C.c_char_p, f32p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "b2s_lg_set_debug": (C.c_int, [vp, C.c_int]),
+    "b2s_lg_debug_get": (C.c_int, [vp, C.c_char_p, f32p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "b2s_aliked_launch_count": (C.c_longlong, [vp]),
+    "b2s_lg_launch_count": (C.c_longlong, [vp]),
+}
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)   # AttributeError here == header/library mismatch
+    _fn.restype, _fn.argtypes = _res, _args
+
+
+class B2SError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise B2SError(f"{what} failed ({rc}): {lib.b2s_last_error().decode(errors='replace')}")

@@ -1,0 +1,459 @@
+// aliked.cu - host orchestration of the ALIKED extractor behind b2s_aliked_*.
+// Replaces `detector.extract(t0)` (+ `_bgr_to_tensor`) at
+// /root/reference/slam/core/features_utils.py:94,219-222; arithmetic spec: SURVEY.md A.1/A.2.
+#include "aliked_kernels.cuh"
+#include "gemm_simt.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+using namespace b2s;
+
+struct DcnBlockW {   // ResBlock with deformable convs (block3 / block4)
+  int cin, cout;
+  float *off1_w, *off1_b, *reg1_w, *reg1_b;   // conv1: offset conv [18][9*cin], regular [cout][9*cin] (BN1 folded)
+  float *off2_w, *off2_b, *reg2_w, *reg2_b;   // conv2: [18][9*cout], [cout][9*cout] (BN2 folded)
+  float *ds_w, *ds_b;                         // downsample [cout][cin] + bias
+};
+
+struct b2s_aliked {
+  b2s_aliked_cfg cfg;
+  int device = 0, M = 16, n_limit = 0;
+  DeviceArena warena, wsarena, hostarena;
+  // weights
+  float *b1c1_w, *b1c1_b, *b1c2_w, *b1c2_b;            // block1 [cin][9][16]
+  float *b2c1_w, *b2c1_b, *b2c2_w, *b2c2_b, *b2ds_w, *b2ds_b;
+  DcnBlockW b3, b4;
+  float *agg_w[4];                                      // conv1..4 [32][ci]
+  float *sh0, *sh2, *sh4, *sh6;                         // score head
+  float *so0_w, *so0_b, *so2_w, *so2_b, *sf_w, *aggT;   // desc head
+  // workspace
+  int wsHp = 0, wsWp = 0;
+  float *img_pad, *resized, *t1a, *x1, *r2, *t2a, *x2, *x3in, *col3, *off3, *t3a, *r3, *x3, *x4in, *col4, *off4, *t4a, *r4, *x4;
+  float *x2a, *x3a, *x4a, *s8, *feat, *score, *nms, *cand_sc, *sel_sc, *thr, *kp_norm, *disp, *sampled;
+  float *Apatch, *toff1, *offs, *S, *F, *descraw;
+  int *cand_idx, *sel_idx, *dk;
+  int cand_cap = 0;
+  // last-call geometry (for debug taps)
+  int Hr = 0, Wr = 0, Hp = 0, Wp = 0;
+  // host API staging
+  size_t himg_bytes = 0; void* himg = nullptr;
+  float *hkp = nullptr, *hdesc = nullptr, *hscores = nullptr; int32_t* hn = nullptr;
+  long long launches = 0;
+};
+
+extern "C" void b2s_aliked_default_cfg(b2s_aliked_cfg* c) {
+  c->model = 0; c->max_kp = 2048; c->det_thresh = 0.2f; c->nms_radius = 2; c->resize_long = 1024; c->precision = B2S_FP32;
+}
+
+namespace {
+
+struct BnFold { std::vector<float> scale, shift; };
+
+int bn_fold(const WeightBlob& wb, const std::string& name, int c, BnFold* out) {
+  const TensorView *g = wb.get(name + ".weight", c), *b = wb.get(name + ".bias", c);
+  const TensorView *m = wb.get(name + ".running_mean", c), *v = wb.get(name + ".running_var", c);
+  if (!g || !b || !m || !v) return B2S_EINVAL;
+  out->scale.resize(c); out->shift.resize(c);
+  for (int i = 0; i < c; ++i) {
+    const float s = g->data[i] / std::sqrt(v->data[i] + 1e-5f);
+    out->scale[i] = s; out->shift[i] = b->data[i] - m->data[i] * s;
+  }
+  return 0;
+}
+
+// [cout][cin][3][3] (*scale[cout]) -> direct-conv layout [cin][9][cout]
+int upload_conv_direct(b2s_aliked* h, const WeightBlob& wb, const std::string& name, int cout, int cin, const BnFold& bn, float** w, float** b) {
+  const TensorView* t = wb.get(name + ".weight", (size_t)cout * cin * 9);
+  if (!t) return B2S_EINVAL;
+  std::vector<float> o((size_t)cin * 9 * cout);
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int k = 0; k < 9; ++k) o[((size_t)ci * 9 + k) * cout + co] = t->data[((size_t)co * cin + ci) * 9 + k] * bn.scale[co];
+  B2S_TRY(h->warena.upload(w, o));
+  return h->warena.upload(b, bn.shift);
+}
+
+// [cout][cin][3][3] (*scale) -> GEMM layout [cout][tap*cin + ci]
+int upload_conv_gemm(b2s_aliked* h, const WeightBlob& wb, const std::string& name, int cout, int cin, const float* scale, float** w) {
+  const TensorView* t = wb.get(name + ".weight", (size_t)cout * cin * 9);
+  if (!t) return B2S_EINVAL;
+  std::vector<float> o((size_t)cout * 9 * cin);
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int k = 0; k < 9; ++k)
+        o[(size_t)co * 9 * cin + (size_t)k * cin + ci] = t->data[((size_t)co * cin + ci) * 9 + k] * (scale ? scale[co] : 1.f);
+  return h->warena.upload(w, o);
+}
+
+int upload_plain(b2s_aliked* h, const WeightBlob& wb, const std::string& name, size_t numel, float** w) {
+  const TensorView* t = wb.get(name, numel);
+  if (!t) return B2S_EINVAL;
+  std::vector<float> o(t->data, t->data + numel);
+  return h->warena.upload(w, o);
+}
+
+int upload_dcn_block(b2s_aliked* h, const WeightBlob& wb, const std::string& blk, int cin, int cout, DcnBlockW* d) {
+  d->cin = cin; d->cout = cout;
+  BnFold bn1, bn2;
+  B2S_TRY(bn_fold(wb, blk + ".bn1", cout, &bn1));
+  B2S_TRY(bn_fold(wb, blk + ".bn2", cout, &bn2));
+  B2S_TRY(upload_conv_gemm(h, wb, blk + ".conv1.offset_conv", 18, cin, nullptr, &d->off1_w));
+  B2S_TRY(upload_plain(h, wb, blk + ".conv1.offset_conv.bias", 18, &d->off1_b));
+  B2S_TRY(upload_conv_gemm(h, wb, blk + ".conv1.regular_conv", cout, cin, bn1.scale.data(), &d->reg1_w));
+  B2S_TRY(h->warena.upload(&d->reg1_b, bn1.shift));
+  B2S_TRY(upload_conv_gemm(h, wb, blk + ".conv2.offset_conv", 18, cout, nullptr, &d->off2_w));
+  B2S_TRY(upload_plain(h, wb, blk + ".conv2.offset_conv.bias", 18, &d->off2_b));
+  B2S_TRY(upload_conv_gemm(h, wb, blk + ".conv2.regular_conv", cout, cout, bn2.scale.data(), &d->reg2_w));
+  B2S_TRY(h->warena.upload(&d->reg2_b, bn2.shift));
+  B2S_TRY(upload_plain(h, wb, blk + ".downsample.weight", (size_t)cout * cin, &d->ds_w));
+  B2S_TRY(upload_plain(h, wb, blk + ".downsample.bias", cout, &d->ds_b));
+  return 0;
+}
+
+int load_weights(b2s_aliked* h, const WeightBlob& wb) {
+  const int M = h->M;
+  BnFold bn;
+  B2S_TRY(bn_fold(wb, "block1.bn1", 16, &bn));
+  B2S_TRY(upload_conv_direct(h, wb, "block1.conv1", 16, 3, bn, &h->b1c1_w, &h->b1c1_b));
+  B2S_TRY(bn_fold(wb, "block1.bn2", 16, &bn));
+  B2S_TRY(upload_conv_direct(h, wb, "block1.conv2", 16, 16, bn, &h->b1c2_w, &h->b1c2_b));
+  B2S_TRY(bn_fold(wb, "block2.bn1", 32, &bn));
+  B2S_TRY(upload_conv_direct(h, wb, "block2.conv1", 32, 16, bn, &h->b2c1_w, &h->b2c1_b));
+  B2S_TRY(bn_fold(wb, "block2.bn2", 32, &bn));
+  B2S_TRY(upload_conv_direct(h, wb, "block2.conv2", 32, 32, bn, &h->b2c2_w, &h->b2c2_b));
+  B2S_TRY(upload_plain(h, wb, "block2.downsample.weight", 32 * 16, &h->b2ds_w));
+  B2S_TRY(upload_plain(h, wb, "block2.downsample.bias", 32, &h->b2ds_b));
+  B2S_TRY(upload_dcn_block(h, wb, "block3", 32, 64, &h->b3));
+  B2S_TRY(upload_dcn_block(h, wb, "block4", 64, 128, &h->b4));
+  const int ci[4] = {16, 32, 64, 128};
+  for (int i = 0; i < 4; ++i) B2S_TRY(upload_plain(h, wb, "conv" + std::to_string(i + 1) + ".weight", (size_t)32 * ci[i], &h->agg_w[i]));
+  B2S_TRY(upload_plain(h, wb, "score_head.0.weight", 8 * 128, &h->sh0));
+  B2S_TRY(upload_plain(h, wb, "score_head.2.weight", 4 * 8 * 9, &h->sh2));
+  B2S_TRY(upload_plain(h, wb, "score_head.4.weight", 4 * 4 * 9, &h->sh4));
+  B2S_TRY(upload_plain(h, wb, "score_head.6.weight", 4 * 9, &h->sh6));
+  B2S_TRY(upload_conv_gemm(h, wb, "desc_head.offset_conv.0", 2 * M, 128, nullptr, &h->so0_w));
+  B2S_TRY(upload_plain(h, wb, "desc_head.offset_conv.0.bias", 2 * M, &h->so0_b));
+  B2S_TRY(upload_plain(h, wb, "desc_head.offset_conv.2.weight", (size_t)4 * M * M, &h->so2_w));
+  B2S_TRY(upload_plain(h, wb, "desc_head.offset_conv.2.bias", 2 * M, &h->so2_b));
+  B2S_TRY(upload_plain(h, wb, "desc_head.sf_conv.weight", 128 * 128, &h->sf_w));
+  // agg_weights [M][c][d] -> [d][p*128 + c]   (einsum 'ncp,pcd->nd' as one GEMM over K = M*128)
+  const TensorView* ag = wb.get("desc_head.agg_weights", (size_t)M * 128 * 128);
+  if (!ag) return B2S_EINVAL;
+  std::vector<float> at((size_t)128 * M * 128);
+  for (int p = 0; p < M; ++p)
+    for (int c = 0; c < 128; ++c)
+      for (int d = 0; d < 128; ++d) at[(size_t)d * M * 128 + (size_t)p * 128 + c] = ag->data[((size_t)p * 128 + c) * 128 + d];
+  return h->warena.upload(&h->aggT, at);
+}
+
+int alloc_ws(b2s_aliked* h, int Hp, int Wp) {
+  h->wsarena.release();
+  h->wsHp = h->wsWp = 0;
+  const size_t P = (size_t)Hp * Wp, P2 = P / 4, P3 = P / 64, P4 = P / 1024;
+  const size_t K = (size_t)h->n_limit, M = (size_t)h->M;
+  DeviceArena& a = h->wsarena;
+  B2S_TRY(a.alloc(&h->img_pad, 3 * P)); B2S_TRY(a.alloc(&h->resized, 3 * P));
+  B2S_TRY(a.alloc(&h->t1a, 16 * P)); B2S_TRY(a.alloc(&h->x1, 16 * P));
+  B2S_TRY(a.alloc(&h->r2, 32 * P2)); B2S_TRY(a.alloc(&h->t2a, 32 * P2)); B2S_TRY(a.alloc(&h->x2, 32 * P2));
+  B2S_TRY(a.alloc(&h->x3in, 32 * P3)); B2S_TRY(a.alloc(&h->col3, 576 * P3)); B2S_TRY(a.alloc(&h->off3, 18 * P3));
+  B2S_TRY(a.alloc(&h->t3a, 64 * P3)); B2S_TRY(a.alloc(&h->r3, 64 * P3)); B2S_TRY(a.alloc(&h->x3, 64 * P3));
+  B2S_TRY(a.alloc(&h->x4in, 64 * P4)); B2S_TRY(a.alloc(&h->col4, 1152 * P4)); B2S_TRY(a.alloc(&h->off4, 18 * P4));
+  B2S_TRY(a.alloc(&h->t4a, 128 * P4)); B2S_TRY(a.alloc(&h->r4, 128 * P4)); B2S_TRY(a.alloc(&h->x4, 128 * P4));
+  B2S_TRY(a.alloc(&h->x2a, 32 * P2)); B2S_TRY(a.alloc(&h->x3a, 32 * P3)); B2S_TRY(a.alloc(&h->x4a, 32 * P4));
+  B2S_TRY(a.alloc(&h->s8, 8 * P)); B2S_TRY(a.alloc(&h->feat, 128 * P));
+  B2S_TRY(a.alloc(&h->score, P)); B2S_TRY(a.alloc(&h->nms, P));
+  B2S_TRY(a.alloc(&h->cand_idx, P)); B2S_TRY(a.alloc(&h->cand_sc, P));
+  h->cand_cap = (int)P;
+  B2S_TRY(a.alloc(&h->sel_idx, K)); B2S_TRY(a.alloc(&h->sel_sc, K));
+  B2S_TRY(a.alloc(&h->dk, (size_t)8)); B2S_TRY(a.alloc(&h->thr, (size_t)1));
+  B2S_TRY(a.alloc(&h->kp_norm, 2 * K)); B2S_TRY(a.alloc(&h->disp, K)); B2S_TRY(a.alloc(&h->sampled, K));
+  B2S_TRY(a.alloc(&h->Apatch, 1152 * K)); B2S_TRY(a.alloc(&h->toff1, 2 * M * K)); B2S_TRY(a.alloc(&h->offs, 2 * M * K));
+  B2S_TRY(a.alloc(&h->S, M * 128 * K)); B2S_TRY(a.alloc(&h->F, M * 128 * K)); B2S_TRY(a.alloc(&h->descraw, 128 * K));
+  h->wsHp = Hp; h->wsWp = Wp;
+  return 0;
+}
+
+// one DCN ResBlock on HWC maps; in [P][cin] -> out [P][cout]
+int run_dcn_block(b2s_aliked* h, cudaStream_t st, const DcnBlockW& w, const float* in, int Hh, int Ww, float* col, float* off,
+                  float* ta, float* res, float* out) {
+  const int P = Hh * Ww;
+  const float clampv = (float)std::max(Hh, Ww) / 4.0f;
+  auto gemm = [&](const float* A, int K, const float* W, int N, const float* bias, float* C, const float* residual, int act, float clamp) {
+    GemmParams g;
+    g.A1 = A; g.lda1 = K; g.K1 = K; g.W = W; g.ldw = K; g.K = K; g.M = P; g.N = N; g.C = C; g.ldc = N;
+    g.bias = bias; g.residual = residual; g.ldr = N; g.act = act; g.clamp = clamp;
+    return gemm_simt(g, st, &h->launches);
+  };
+  const int jobs = P * 9;
+  // conv1: offsets (regular im2col) -> deformable im2col -> GEMM (+BN1) + SELU
+  k_dcn_im2col<<<cdiv(jobs, 8), 256, 0, st>>>(in, w.cin, Hh, Ww, nullptr, col);
+  ++h->launches; B2S_LAUNCH_CHECK();
+  B2S_TRY(gemm(col, 9 * w.cin, w.off1_w, 18, w.off1_b, off, nullptr, ACT_NONE, clampv));
+  k_dcn_im2col<<<cdiv(jobs, 8), 256, 0, st>>>(in, w.cin, Hh, Ww, off, col);
+  ++h->launches; B2S_LAUNCH_CHECK();
+  B2S_TRY(gemm(col, 9 * w.cin, w.reg1_w, w.cout, w.reg1_b, ta, nullptr, ACT_SELU, 0.f));
+  // downsample(x) -> residual
+  B2S_TRY(gemm(in, w.cin, w.ds_w, w.cout, w.ds_b, res, nullptr, ACT_NONE, 0.f));
+  // conv2 on ta
+  k_dcn_im2col<<<cdiv(jobs, 8), 256, 0, st>>>(ta, w.cout, Hh, Ww, nullptr, col);
+  ++h->launches; B2S_LAUNCH_CHECK();
+  B2S_TRY(gemm(col, 9 * w.cout, w.off2_w, 18, w.off2_b, off, nullptr, ACT_NONE, clampv));
+  k_dcn_im2col<<<cdiv(jobs, 8), 256, 0, st>>>(ta, w.cout, Hh, Ww, off, col);
+  ++h->launches; B2S_LAUNCH_CHECK();
+  return gemm(col, 9 * w.cout, w.reg2_w, w.cout, w.reg2_b, out, res, ACT_SELU, 0.f);
+}
+
+}  // namespace
+
+extern "C" int b2s_aliked_create(const b2s_aliked_cfg* cfg, const void* weights, size_t nbytes, int device, b2s_aliked** out) {
+  if (!cfg || !weights || !out) { set_error("b2s_aliked_create: null argument"); return B2S_EINVAL; }
+  if (cfg->nms_radius != 2 || (cfg->model != 0 && cfg->model != 1) || cfg->precision != B2S_FP32) {
+    set_error("b2s_aliked_create: unsupported cfg (nms_radius must be 2, model 0|1, precision fp32)");
+    return B2S_EINVAL;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    set_error("b2s_aliked_create: CUDA device %d not available (%d devices) - there is no CPU fallback", device, ndev);
+    return B2S_ENODEV;
+  }
+  B2S_CUDA(cudaSetDevice(device));
+  WeightBlob wb;
+  B2S_TRY(wb.parse(weights, nbytes));
+  b2s_aliked* h = new b2s_aliked();
+  h->cfg = *cfg; h->device = device;
+  h->M = cfg->model == 1 ? 32 : 16;
+  h->n_limit = cfg->max_kp > 0 ? cfg->max_kp : 20000;
+  int rc = load_weights(h, wb);
+  if (rc) { delete h; return rc; }
+  *out = h;
+  return 0;
+}
+
+extern "C" void b2s_aliked_destroy(b2s_aliked* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  delete h;
+}
+
+extern "C" long long b2s_aliked_launch_count(const b2s_aliked* h) { return h ? h->launches : 0; }
+
+extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H, int W, int row_stride, void* stream,
+                                  float* kpts, float* desc, float* scores, int32_t* n_out) {
+  if (!h || !img || !kpts || !desc || !n_out || H < 8 || W < 8 || (fmt != B2S_IMG_BGR_U8_HWC && fmt != B2S_IMG_RGB_F32_CHW)) {
+    set_error("b2s_aliked_extract: bad argument (H=%d W=%d fmt=%d)", H, W, fmt);
+    return B2S_EINVAL;
+  }
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  // ---- geometry: kornia resize(side='long') then InputPadder(32) ----
+  int Hr = H, Wr = W;
+  if (h->cfg.resize_long > 0) {
+    const double ar = (double)W / (double)H;
+    if (ar >= 1.0) { Hr = (int)((double)h->cfg.resize_long / ar); Wr = h->cfg.resize_long; }
+    else { Hr = h->cfg.resize_long; Wr = (int)((double)h->cfg.resize_long * ar); }
+  }
+  if (Hr < 8 || Wr < 8) { set_error("b2s_aliked_extract: resized image %dx%d too small", Hr, Wr); return B2S_ESIZE; }
+  PreParams pp;
+  pp.img = img; pp.fmt = fmt; pp.H = H; pp.W = W; pp.stride = row_stride > 0 ? row_stride : 3 * W;
+  pp.Hr = Hr; pp.Wr = Wr;
+  pp.do_resize = (Hr != H || Wr != W);
+  pp.do_blur = 0; pp.ky = pp.kx = 1;
+  if (pp.do_resize) {
+    const double fy = (double)H / Hr, fx = (double)W / Wr;
+    if (std::max(fy, fx) > 1.0) {
+      const double sy = std::max((fy - 1.0) / 2.0, 0.001), sx = std::max((fx - 1.0) / 2.0, 0.001);
+      int ky = (int)std::max(2.0 * 2 * sy, 3.0), kx = (int)std::max(2.0 * 2 * sx, 3.0);
+      if (ky % 2 == 0) ++ky;
+      if (kx % 2 == 0) ++kx;
+      if (ky > 15 || kx > 15) { set_error("b2s_aliked_extract: downscale factor too large (blur kernel %dx%d > 15)", ky, kx); return B2S_ESIZE; }
+      pp.do_blur = 1; pp.ky = ky; pp.kx = kx;
+      auto mk = [](int ks, double sigma, float* g) {
+        const float denom = (float)(2.0 * sigma * sigma);
+        float s = 0.f;
+        for (int i = 0; i < ks; ++i) { const float x = (float)(i - ks / 2); g[i] = std::exp(-(x * x) / denom); s += g[i]; }
+        for (int i = 0; i < ks; ++i) g[i] /= s;
+      };
+      mk(ky, sy, pp.gy); mk(kx, sx, pp.gx);
+    }
+  }
+  pp.scale_h = (float)H / (float)Hr; pp.scale_w = (float)W / (float)Wr;
+  const int pad_h = (((Hr / 32) + 1) * 32 - Hr) % 32, pad_w = (((Wr / 32) + 1) * 32 - Wr) % 32;
+  const int Hp = Hr + pad_h, Wp = Wr + pad_w;
+  pp.Hp = Hp; pp.Wp = Wp; pp.pad_t = pad_h / 2; pp.pad_l = pad_w / 2;
+  if ((size_t)Hp * Wp > (size_t)h->wsHp * h->wsWp) {
+    B2S_CUDA(cudaStreamSynchronize(st));
+    B2S_TRY(alloc_ws(h, Hp, Wp));
+  }
+  h->Hr = Hr; h->Wr = Wr; h->Hp = Hp; h->Wp = Wp;
+  pp.out = h->img_pad; pp.resized = h->resized;
+  k_preprocess<<<dim3(cdiv(Wp, 256), Hp), 256, 0, st>>>(pp);
+  ++h->launches; B2S_LAUNCH_CHECK();
+
+  // ---- block1 (full res) ----
+  {
+    dim3 g(cdiv(Wp, 32), cdiv(Hp, 16));
+    k_conv3x3<3, 16, false><<<g, dim3(16, 8, 1), 0, st>>>(h->img_pad, Hp, Wp, h->b1c1_w, h->b1c1_b, nullptr, h->t1a, 1);
+    k_conv3x3<16, 16, false><<<g, dim3(16, 8, 1), 0, st>>>(h->t1a, Hp, Wp, h->b1c2_w, h->b1c2_b, nullptr, h->x1, 1);
+    h->launches += 2; B2S_LAUNCH_CHECK();
+  }
+  // ---- block2 (1/2 res): pool2 fused into conv1's load and into the 1x1 downsample ----
+  const int H2 = Hp / 2, W2 = Wp / 2;
+  {
+    dim3 g(cdiv(W2, 32), cdiv(H2, 16));
+    k_pool2_conv1x1<16, 32><<<cdiv(H2 * W2, 64), 256, 0, st>>>(h->x1, H2, W2, h->b2ds_w, h->b2ds_b, h->r2);
+    k_conv3x3<16, 32, true><<<g, dim3(16, 8, 2), 0, st>>>(h->x1, H2, W2, h->b2c1_w, h->b2c1_b, nullptr, h->t2a, 1);
+    k_conv3x3<32, 32, false><<<g, dim3(16, 8, 2), 0, st>>>(h->t2a, H2, W2, h->b2c2_w, h->b2c2_b, h->r2, h->x2, 1);
+    h->launches += 3; B2S_LAUNCH_CHECK();
+  }
+  // ---- block3 (1/8) and block4 (1/32): DCN via im2col + GEMM, HWC ----
+  const int H3 = H2 / 4, W3 = W2 / 4, H4 = H3 / 4, W4 = W3 / 4;
+  k_pool4_chw_to_hwc<<<cdiv(H3 * W3, 8), 256, 0, st>>>(h->x2, 32, H3, W3, h->x3in);
+  ++h->launches; B2S_LAUNCH_CHECK();
+  B2S_TRY(run_dcn_block(h, st, h->b3, h->x3in, H3, W3, h->col3, h->off3, h->t3a, h->r3, h->x3));
+  k_pool4_hwc<<<cdiv(H4 * W4, 8), 256, 0, st>>>(h->x3, 64, H4, W4, h->x4in);
+  ++h->launches; B2S_LAUNCH_CHECK();
+  B2S_TRY(run_dcn_block(h, st, h->b4, h->x4in, H4, W4, h->col4, h->off4, h->t4a, h->r4, h->x4));
+  // ---- aggregation convs at native resolution ----
+  k_conv1x1_chw_to_hwc32<32><<<cdiv(H2 * W2, 64), 256, 0, st>>>(h->x2, (size_t)H2 * W2, h->agg_w[1], h->x2a);
+  ++h->launches; B2S_LAUNCH_CHECK();
+  {
+    GemmParams g;
+    g.A1 = h->x3; g.lda1 = 64; g.K1 = 64; g.W = h->agg_w[2]; g.ldw = 64; g.K = 64; g.M = H3 * W3; g.N = 32; g.C = h->x3a; g.ldc = 32; g.act = ACT_SELU;
+    B2S_TRY(gemm_simt(g, st, &h->launches));
+    g.A1 = h->x4; g.lda1 = 128; g.K1 = 128; g.W = h->agg_w[3]; g.ldw = 128; g.K = 128; g.M = H4 * W4; g.C = h->x4a;
+    B2S_TRY(gemm_simt(g, st, &h->launches));
+  }
+  // ---- fused upsample + concat + normalise + score head ----
+  {
+    AggParams ap;
+    ap.x1 = h->x1; ap.Hp = Hp; ap.Wp = Wp;
+    ap.xa[0] = h->x2a; ap.xa[1] = h->x3a; ap.xa[2] = h->x4a;
+    const int hk[3] = {H2, H3, H4}, wk[3] = {W2, W3, W4};
+    for (int l = 0; l < 3; ++l) {
+      ap.Hk[l] = hk[l]; ap.Wk[l] = wk[l];
+      ap.sh[l] = Hp > 1 ? (float)(hk[l] - 1) / (float)(Hp - 1) : 0.f;
+      ap.sw[l] = Wp > 1 ? (float)(wk[l] - 1) / (float)(Wp - 1) : 0.f;
+    }
+    ap.W1 = h->agg_w[0]; ap.Ws0 = h->sh0; ap.s8 = h->s8; ap.feat = h->feat;
+    ap.Hr = Hr; ap.Wr = Wr; ap.pad_t = pp.pad_t; ap.pad_l = pp.pad_l;
+    k_aliked_agg<<<dim3(cdiv(Wp, 32), Hp), 256, 0, st>>>(ap);
+    ScoreParams sp;
+    sp.s8 = h->s8; sp.Hp = Hp; sp.Wp = Wp; sp.w2 = h->sh2; sp.w4 = h->sh4; sp.w6 = h->sh6;
+    sp.score = h->score; sp.Hr = Hr; sp.Wr = Wr; sp.pad_t = pp.pad_t; sp.pad_l = pp.pad_l;
+    k_aliked_score<<<dim3(cdiv(Wp, 32), cdiv(Hp, 8)), 256, 0, st>>>(sp);
+    h->launches += 2; B2S_LAUNCH_CHECK();
+  }
+  // ---- DKD ----
+  {
+    B2S_CUDA(cudaMemsetAsync(h->dk, 0, 8 * sizeof(int), st));
+    B2S_CUDA(cudaMemcpyAsync(h->thr, &h->cfg.det_thresh, sizeof(float), cudaMemcpyHostToDevice, st));
+    k_dkd_nms<<<dim3(cdiv(Wr, NMS_T), cdiv(Hr, NMS_T)), 256, 0, st>>>(h->score, Hr, Wr, h->nms, h->thr, h->dk, h->cand_idx, h->cand_sc, h->cand_cap);
+    k_dkd_fallback<<<1, 1024, 0, st>>>(h->score, h->nms, Hr * Wr, h->thr, h->dk, h->cand_idx, h->cand_sc, h->cand_cap);
+    k_dkd_select<<<1, 1024, 0, st>>>(h->cand_sc, h->cand_cap, h->n_limit, h->dk);
+    k_dkd_compact<<<cdiv(h->cand_cap, 256), 256, 0, st>>>(h->cand_idx, h->cand_sc, h->dk, h->sel_idx, h->sel_sc);
+    RefineParams rp;
+    rp.dk = h->dk; rp.sel_idx = h->sel_idx; rp.sel_sc = h->sel_sc; rp.score = h->score; rp.H = Hr; rp.W = Wr;
+    rp.scale_x = (float)((double)Wr / (double)W); rp.scale_y = (float)((double)Hr / (double)H);
+    rp.kp_norm = h->kp_norm; rp.kp_out = kpts; rp.disp = h->disp; rp.sampled = h->sampled; rp.n_out = n_out;
+    k_dkd_refine<<<cdiv(h->n_limit, 256), 256, 0, st>>>(rp);
+    h->launches += 5; B2S_LAUNCH_CHECK();
+    // upstream puts DKD's 2nd return value (dispersity) under "keypoint_scores" 
+    if (scores) B2S_CUDA(cudaMemcpyAsync(scores, h->disp, (size_t)h->n_limit * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  // ---- SDDH ----
+  {
+    const int K = h->n_limit, M = h->M;
+    const float clampv = (float)std::max(Hr, Wr) / 4.0f;
+    k_sddh_patch<<<cdiv(K * 9, 8), 256, 0, st>>>(h->feat, Hr, Wr, h->kp_norm, n_out, h->Apatch);
+    ++h->launches; B2S_LAUNCH_CHECK();
+    GemmParams g;
+    g.A1 = h->Apatch; g.lda1 = 1152; g.K1 = 1152; g.W = h->so0_w; g.ldw = 1152; g.K = 1152; g.M = K; g.N = 2 * M;
+    g.C = h->toff1; g.ldc = 2 * M; g.bias = h->so0_b; g.act = ACT_SELU; g.m_dev = n_out; g.m_mult = 1;
+    B2S_TRY(gemm_simt(g, st, &h->launches));
+    g = GemmParams();
+    g.A1 = h->toff1; g.lda1 = 2 * M; g.K1 = 2 * M; g.W = h->so2_w; g.ldw = 2 * M; g.K = 2 * M; g.M = K; g.N = 2 * M;
+    g.C = h->offs; g.ldc = 2 * M; g.bias = h->so2_b; g.clamp = clampv; g.m_dev = n_out; g.m_mult = 1;
+    B2S_TRY(gemm_simt(g, st, &h->launches));
+    k_sddh_sample<<<cdiv(K * M, 8), 256, 0, st>>>(h->feat, Hr, Wr, h->kp_norm, h->offs, M, n_out, h->S);
+    ++h->launches; B2S_LAUNCH_CHECK();
+    g = GemmParams();
+    g.A1 = h->S; g.lda1 = 128; g.K1 = 128; g.W = h->sf_w; g.ldw = 128; g.K = 128; g.M = K * M; g.N = 128;
+    g.C = h->F; g.ldc = 128; g.act = ACT_SELU; g.m_dev = n_out; g.m_mult = M;
+    B2S_TRY(gemm_simt(g, st, &h->launches));
+    g = GemmParams();
+    g.A1 = h->F; g.lda1 = M * 128; g.K1 = M * 128; g.W = h->aggT; g.ldw = M * 128; g.K = M * 128; g.M = K; g.N = 128;
+    g.C = h->descraw; g.ldc = 128; g.m_dev = n_out; g.m_mult = 1;
+    B2S_TRY(gemm_simt(g, st, &h->launches));
+    k_desc_normalize<<<cdiv(K, 8), 256, 0, st>>>(h->descraw, n_out, desc);
+    ++h->launches; B2S_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int b2s_aliked_extract_host(b2s_aliked* h, const void* img, int fmt, int H, int W, int row_stride,
+                                       float* kpts, float* desc, float* scores, int32_t* n_out) {
+  if (!h || !img || !kpts || !desc || !n_out) { set_error("b2s_aliked_extract_host: null argument"); return B2S_EINVAL; }
+  B2S_CUDA(cudaSetDevice(h->device));
+  const size_t bytes = fmt == B2S_IMG_BGR_U8_HWC ? (size_t)(row_stride > 0 ? row_stride : 3 * W) * H : (size_t)3 * H * W * sizeof(float);
+  if (bytes > h->himg_bytes || !h->hkp) {
+    h->hostarena.release();
+    h->himg_bytes = 0;
+    uint8_t* b = nullptr;
+    B2S_TRY(h->hostarena.alloc(&b, bytes));
+    h->himg = b;
+    B2S_TRY(h->hostarena.alloc(&h->hkp, (size_t)h->n_limit * 2));
+    B2S_TRY(h->hostarena.alloc(&h->hdesc, (size_t)h->n_limit * 128));
+    B2S_TRY(h->hostarena.alloc(&h->hscores, (size_t)h->n_limit));
+    B2S_TRY(h->hostarena.alloc(&h->hn, (size_t)1));
+    h->himg_bytes = bytes;
+  }
+  cudaStream_t st = 0;
+  B2S_CUDA(cudaMemcpyAsync(h->himg, img, bytes, cudaMemcpyHostToDevice, st));
+  B2S_TRY(b2s_aliked_extract(h, h->himg, fmt, H, W, row_stride, st, h->hkp, h->hdesc, h->hscores, h->hn));
+  int32_t n = 0;
+  B2S_CUDA(cudaMemcpyAsync(&n, h->hn, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaStreamSynchronize(st));
+  *n_out = n;
+  if (n > 0) {
+    B2S_CUDA(cudaMemcpyAsync(kpts, h->hkp, (size_t)n * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B2S_CUDA(cudaMemcpyAsync(desc, h->hdesc, (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (scores) B2S_CUDA(cudaMemcpyAsync(scores, h->hscores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+extern "C" int b2s_aliked_debug_get(b2s_aliked* h, const char* name, float* out, size_t cap, size_t* nout) {
+  if (!h || !name || !nout) return B2S_EINVAL;
+  B2S_CUDA(cudaSetDevice(h->device));
+  B2S_CUDA(cudaDeviceSynchronize());
+  const size_t P = (size_t)h->Hp * h->Wp, Pr = (size_t)h->Hr * h->Wr;
+  const std::string s(name);
+  const float* src = nullptr; size_t cnt = 0;
+  if (s == "geometry") {
+    const float g[4] = {(float)h->Hr, (float)h->Wr, (float)h->Hp, (float)h->Wp};
+    *nout = 4;
+    std::memcpy(out, g, std::min<size_t>(cap, 4) * sizeof(float));
+    return 0;
+  }
+  if (s == "padded") { src = h->img_pad; cnt = 3 * P; }            // CHW
+  else if (s == "resized") { src = h->resized; cnt = 3 * Pr; }     // CHW
+  else if (s == "x1") { src = h->x1; cnt = 16 * P; }               // CHW
+  else if (s == "x2") { src = h->x2; cnt = 32 * P / 4; }           // CHW
+  else if (s == "x3") { src = h->x3; cnt = 64 * P / 64; }          // HWC
+  else if (s == "x4") { src = h->x4; cnt = 128 * P / 1024; }       // HWC
+  else if (s == "score_map") { src = h->score; cnt = Pr; }
+  else if (s == "nms") { src = h->nms; cnt = Pr; }
+  else if (s == "feature_map") { src = h->feat; cnt = 128 * Pr; }  // HWC
+  else if (s == "kp_norm") { src = h->kp_norm; cnt = (size_t)h->n_limit * 2; }
+  else if (s == "sampled_score") { src = h->sampled; cnt = (size_t)h->n_limit; }
+  else if (s == "sddh_offset") { src = h->offs; cnt = (size_t)h->n_limit * 2 * h->M; }
+  else if (s == "desc_raw") { src = h->descraw; cnt = (size_t)h->n_limit * 128; }
+  else { set_error("unknown debug tensor %s", name); return B2S_EINVAL; }
+  if (!src) { set_error("debug tensor %s not available before the first extract", name); return B2S_EINVAL; }
+  *nout = cnt;
+  const size_t c = std::min(cnt, cap);
+  if (c) B2S_CUDA(cudaMemcpy(out, src, c * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}

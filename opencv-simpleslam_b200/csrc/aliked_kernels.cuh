@@ -1,0 +1,764 @@
+// aliked_kernels.cuh - ALIKED extractor stages (fp32): preprocess (K0), direct 3x3 convs for
+// the full/half resolution blocks (K1/K2), pooling + deformable im2col for the DCN blocks
+// (K3/K4, contracted by gemm_simt), fused aggregation/normalise/score-head (K5), DKD
+// NMS/top-k/soft-argmax (K6) and SDDH gathers (K7).  Upstream spec: SURVEY.md Appendix A.1/A.2.
+#pragma once
+#include "common.cuh"
+
+namespace b2s {
+
+// ---------------------------------------------------------------------------------------
+// K0: BGR u8 HWC (or RGB f32 CHW) -> [gaussian blur] -> bilinear resize -> replicate pad
+// out: planar RGB f32 [3][Hp][Wp].  One thread per padded pixel.
+// ---------------------------------------------------------------------------------------
+struct PreParams {
+  const void* img; int fmt; int H, W, stride;
+  int Hr, Wr, Hp, Wp, pad_t, pad_l;
+  int do_resize, do_blur, ky, kx;
+  float gy[15], gx[15];
+  float scale_h, scale_w;
+  float* out;
+  float* resized;   // optional tap: [3][Hr][Wr]
+};
+
+__device__ __forceinline__ float pre_src(const PreParams& p, int c, int y, int x) {
+  if (p.fmt == B2S_IMG_BGR_U8_HWC) {
+    const uint8_t* b = static_cast<const uint8_t*>(p.img);
+    return __fdiv_rn((float)b[(size_t)y * p.stride + x * 3 + (2 - c)], 255.0f);
+  }
+  const float* f = static_cast<const float*>(p.img);
+  return f[((size_t)c * p.H + y) * p.W + x];
+}
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return min(max(i, 0), n - 1);
+}
+__device__ __forceinline__ float pre_blur(const PreParams& p, int c, int y, int x) {
+  if (!p.do_blur) return pre_src(p, c, y, x);
+  const int ry = p.ky / 2, rx = p.kx / 2;
+  float acc = 0.f;
+  for (int i = 0; i < p.ky; ++i) {
+    const int yy = reflect_idx(y + i - ry, p.H);
+    float row = 0.f;
+    for (int j = 0; j < p.kx; ++j) row += p.gx[j] * pre_src(p, c, yy, reflect_idx(x + j - rx, p.W));
+    acc += p.gy[i] * row;
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(256) k_preprocess(PreParams p) {
+  const int xp = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yp = blockIdx.y;
+  if (xp >= p.Wp) return;
+  const int yr = min(max(yp - p.pad_t, 0), p.Hr - 1);
+  const int xr = min(max(xp - p.pad_l, 0), p.Wr - 1);
+  float v[3];
+  if (!p.do_resize) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = pre_src(p, c, yr, xr);
+  } else {
+    // torch upsample_bilinear2d, align_corners=False: src = scale*(dst+0.5)-0.5 clamped at 0
+    float fy = p.scale_h * ((float)yr + 0.5f) - 0.5f; if (fy < 0.f) fy = 0.f;
+    float fx = p.scale_w * ((float)xr + 0.5f) - 0.5f; if (fx < 0.f) fx = 0.f;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < p.H - 1 ? 1 : 0), x1 = x0 + (x0 < p.W - 1 ? 1 : 0);
+    const float ly1 = fy - (float)y0, ly0 = 1.f - ly1, lx1 = fx - (float)x0, lx0 = 1.f - lx1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float p00 = pre_blur(p, c, y0, x0), p01 = pre_blur(p, c, y0, x1);
+      const float p10 = pre_blur(p, c, y1, x0), p11 = pre_blur(p, c, y1, x1);
+      v[c] = ly0 * (lx0 * p00 + lx1 * p01) + ly1 * (lx0 * p10 + lx1 * p11);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) p.out[((size_t)c * p.Hp + yp) * p.Wp + xp] = v[c];
+  if (p.resized && yp - p.pad_t == yr && xp - p.pad_l == xr) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p.resized[((size_t)c * p.Hr + yr) * p.Wr + xr] = v[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K1/K2: direct 3x3 conv (pad 1), planar CHW, BN folded into w/bias, optional 2x2 average
+// pooling fused into the input load, optional residual, SELU.
+// block = (16, 8, COUT/16): thread -> 2x2 pixels x 16 output channels; tile 32 x 16 pixels.
+// weights: [CIN][9][COUT]
+// ---------------------------------------------------------------------------------------
+template <int CIN, int COUT, bool POOL2>
+__global__ void __launch_bounds__(128 * (COUT / 16)) k_conv3x3(const float* __restrict__ in, int H, int W,
+                                                               const float* __restrict__ w, const float* __restrict__ bias,
+                                                               const float* __restrict__ residual, float* __restrict__ out,
+                                                               int act) {
+  constexpr int CC = CIN < 8 ? CIN : 8;
+  constexpr int TH = 16, TW = 32, RS = TW + 4;
+  __shared__ __align__(16) float tin[CC][TH + 2][RS];
+  __shared__ __align__(16) float tw[CC][9][COUT];
+  const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
+  const int tid = (tz * 8 + ty) * 16 + tx;
+  constexpr int NT = 128 * (COUT / 16);
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int Hs = POOL2 ? H * 2 : H, Ws = POOL2 ? W * 2 : W;  // source dims
+  float acc[4][16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+
+  for (int c0 = 0; c0 < CIN; c0 += CC) {
+    __syncthreads();
+    for (int e = tid; e < CC * (TH + 2) * (TW + 2); e += NT) {
+      const int c = e / ((TH + 2) * (TW + 2));
+      const int r = (e / (TW + 2)) % (TH + 2), q = e % (TW + 2);
+      const int gy = y0 + r - 1, gx = x0 + q - 1;
+      float v = 0.f;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        if (POOL2) {
+          const float* s = in + ((size_t)(c0 + c) * Hs + 2 * gy) * Ws + 2 * gx;
+          v = (((s[0] + s[1]) + s[Ws]) + s[Ws + 1]) * 0.25f;
+        } else {
+          v = in[((size_t)(c0 + c) * H + gy) * W + gx];
+        }
+      }
+      tin[c][r][q] = v;
+    }
+    for (int e = tid; e < CC * 9 * COUT; e += NT) (&tw[0][0][0])[e] = w[(size_t)c0 * 9 * COUT + e];
+    __syncthreads();
+#pragma unroll 1
+    for (int c = 0; c < CC; ++c) {
+      float win[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float2 a = *reinterpret_cast<const float2*>(&tin[c][2 * ty + r][2 * tx]);
+        const float2 b = *reinterpret_cast<const float2*>(&tin[c][2 * ty + r][2 * tx + 2]);
+        win[r][0] = a.x; win[r][1] = a.y; win[r][2] = b.x; win[r][3] = b.y;
+      }
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4* wp = reinterpret_cast<const float4*>(&tw[c][ky * 3 + kx][tz * 16]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 wv = wp[q];
+            const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int py = 0; py < 2; ++py)
+#pragma unroll
+              for (int px = 0; px < 2; ++px) {
+                const float iv = win[py + ky][px + kx];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) acc[py * 2 + px][q * 4 + o] = fmaf(iv, ww[o], acc[py * 2 + px][q * 4 + o]);
+              }
+          }
+        }
+    }
+  }
+#pragma unroll
+  for (int py = 0; py < 2; ++py) {
+    const int gy = y0 + 2 * ty + py;
+    if (gy >= H) continue;
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+      const int co = tz * 16 + o;
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const int gx = x0 + 2 * tx + px;
+        if (gx >= W) continue;
+        float v = acc[py * 2 + px][o] + bias[co];
+        const size_t idx = ((size_t)co * H + gy) * W + gx;
+        if (residual) v += residual[idx];
+        if (act == 1) v = selu_f(v);
+        out[idx] = v;
+      }
+    }
+  }
+}
+
+// block2.downsample: 2x2 avg-pool + 1x1 conv (CIN -> COUT) + bias, planar CHW -> planar CHW.
+// block 256: 64 pixels x 4 output groups.
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256) k_pool2_conv1x1(const float* __restrict__ in, int H, int W /*pooled dims*/,
+                                                       const float* __restrict__ w /*[COUT][CIN]*/,
+                                                       const float* __restrict__ bias, float* __restrict__ out) {
+  __shared__ float xs[CIN][64];
+  __shared__ float ws[COUT][CIN + 1];
+  const int tid = threadIdx.x;
+  const size_t npix = (size_t)H * W;
+  const size_t p0 = (size_t)blockIdx.x * 64;
+  for (int e = tid; e < COUT * CIN; e += 256) ws[e / CIN][e % CIN] = w[e];
+  for (int e = tid; e < CIN * 64; e += 256) {
+    const int c = e / 64, q = e % 64;
+    const size_t pp = p0 + q;
+    float v = 0.f;
+    if (pp < npix) {
+      const int y = (int)(pp / W), x = (int)(pp % W);
+      const float* s = in + ((size_t)c * (2 * H) + 2 * y) * (2 * W) + 2 * x;
+      v = (((s[0] + s[1]) + s[2 * W]) + s[2 * W + 1]) * 0.25f;
+    }
+    xs[c][q] = v;
+  }
+  __syncthreads();
+  const int q = tid & 63, og = tid >> 6;
+  const size_t pp = p0 + q;
+  if (pp >= npix) return;
+  constexpr int OG = COUT / 4;
+#pragma unroll 4
+  for (int o = og * OG; o < (og + 1) * OG; ++o) {
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) a = fmaf(ws[o][c], xs[c][q], a);
+    out[(size_t)o * npix + pp] = a + bias[o];
+  }
+}
+
+// 4x4 average pooling, planar CHW [C][4H][4W] -> HWC [H*W][C].  warp per output pixel.
+__global__ void __launch_bounds__(256) k_pool4_chw_to_hwc(const float* __restrict__ in, int C, int H, int W, float* __restrict__ out) {
+  const int pix = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pix >= H * W) return;
+  const int lane = threadIdx.x & 31;
+  const int y = pix / W, x = pix % W;
+  for (int c = lane; c < C; c += 32) {
+    const float* s = in + ((size_t)c * (4 * H) + 4 * y) * (4 * W) + 4 * x;
+    float a = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 4; ++dy) {
+      const float4 v = *reinterpret_cast<const float4*>(s + (size_t)dy * 4 * W);
+      a += v.x; a += v.y; a += v.z; a += v.w;
+    }
+    out[(size_t)pix * C + c] = a * (1.f / 16.f);
+  }
+}
+// 4x4 average pooling HWC -> HWC.
+__global__ void __launch_bounds__(256) k_pool4_hwc(const float* __restrict__ in, int C, int H, int W, float* __restrict__ out) {
+  const int pix = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pix >= H * W) return;
+  const int lane = threadIdx.x & 31;
+  const int y = pix / W, x = pix % W;
+  for (int c = lane; c < C; c += 32) {
+    float a = 0.f;
+    for (int dy = 0; dy < 4; ++dy)
+      for (int dx = 0; dx < 4; ++dx) a += in[((size_t)(4 * y + dy) * (4 * W) + 4 * x + dx) * C + c];
+    out[(size_t)pix * C + c] = a * (1.f / 16.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3/K4: (deformable) im2col on HWC input.  col[pix][tap*C + c].  warp per (pixel, tap).
+// offsets (nullable -> regular conv): [pix][18] with (2k, 2k+1) = (dy, dx) of tap k=ky*3+kx,
+// bilinear with zeros outside - the torchvision deform_conv2d kernel semantics.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dcn_im2col(const float* __restrict__ in, int C, int H, int W,
+                                                    const float* __restrict__ offs, float* __restrict__ col) {
+  const int job = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (job >= H * W * 9) return;
+  const int lane = threadIdx.x & 31;
+  const int pix = job / 9, tap = job % 9;
+  const int py = pix / W, px = pix % W;
+  float* dst = col + (size_t)pix * 9 * C + (size_t)tap * C;
+  float hy = (float)(py - 1 + tap / 3), wx = (float)(px - 1 + tap % 3);
+  if (offs) { hy += offs[(size_t)pix * 18 + 2 * tap]; wx += offs[(size_t)pix * 18 + 2 * tap + 1]; }
+  if (hy <= -1.f || hy >= (float)H || wx <= -1.f || wx >= (float)W) {
+    for (int c = lane; c < C; c += 32) dst[c] = 0.f;
+    return;
+  }
+  const int hl = (int)floorf(hy), wl = (int)floorf(wx);
+  const int hh = hl + 1, wh = wl + 1;
+  const float lh = hy - (float)hl, lw = wx - (float)wl, uh = 1.f - lh, uw = 1.f - lw;
+  const bool v1 = hl >= 0 && wl >= 0, v2 = hl >= 0 && wh <= W - 1, v3 = hh <= H - 1 && wl >= 0, v4 = hh <= H - 1 && wh <= W - 1;
+  const float w1 = uh * uw, w2 = uh * lw, w3 = lh * uw, w4 = lh * lw;
+  for (int c = lane; c < C; c += 32) {
+    const float a = v1 ? in[((size_t)hl * W + wl) * C + c] : 0.f;
+    const float b = v2 ? in[((size_t)hl * W + wh) * C + c] : 0.f;
+    const float d = v3 ? in[((size_t)hh * W + wl) * C + c] : 0.f;
+    const float e = v4 ? in[((size_t)hh * W + wh) * C + c] : 0.f;
+    dst[c] = w1 * a + w2 * b + w3 * d + w4 * e;
+  }
+}
+
+// 1x1 conv (CIN -> 32, no bias) + SELU, planar CHW -> HWC.  block 256 = 64 pixels x 4 groups.
+template <int CIN>
+__global__ void __launch_bounds__(256) k_conv1x1_chw_to_hwc32(const float* __restrict__ in, size_t npix,
+                                                              const float* __restrict__ w /*[32][CIN]*/, float* __restrict__ out) {
+  __shared__ float xs[CIN][64];
+  __shared__ float ws[32][CIN + 1];
+  const int tid = threadIdx.x;
+  const size_t p0 = (size_t)blockIdx.x * 64;
+  for (int e = tid; e < 32 * CIN; e += 256) ws[e / CIN][e % CIN] = w[e];
+  for (int e = tid; e < CIN * 64; e += 256) {
+    const int c = e / 64, q = e % 64;
+    xs[c][q] = (p0 + q < npix) ? in[(size_t)c * npix + p0 + q] : 0.f;
+  }
+  __syncthreads();
+  const int q = tid & 63, og = tid >> 6;
+  if (p0 + q >= npix) return;
+  float r[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) a = fmaf(ws[og * 8 + o][c], xs[c][q], a);
+    r[o] = selu_f(a);
+  }
+  float4* d = reinterpret_cast<float4*>(out + (p0 + q) * 32 + og * 8);
+  d[0] = make_float4(r[0], r[1], r[2], r[3]);
+  d[1] = make_float4(r[4], r[5], r[6], r[7]);
+}
+
+// ---------------------------------------------------------------------------------------
+// K5a: fused aggregation.  Per full-resolution (padded) pixel: f = cat[selu(W1 x1),
+// up2(x2a), up8(x3a), up32(x4a)] (bilinear, align_corners=True) ; s8 = selu(Ws0 f) ;
+// feature = f / max(|f|,1e-12) written HWC for the UNPADDED region only.
+// CTA = 8 warps x 4 pixels = 32 consecutive pixels of a row; lane = channel within group.
+// ---------------------------------------------------------------------------------------
+struct AggParams {
+  const float* x1; int Hp, Wp;            // CHW [16][Hp][Wp]
+  const float* xa[3]; int Hk[3], Wk[3];   // HWC [Hk*Wk][32] (levels 1/2, 1/8, 1/32)
+  float sh[3], sw[3];                     // (in-1)/(out-1)
+  const float* W1;                        // [32][16]
+  const float* Ws0;                       // [8][128]
+  float* s8;                              // CHW [8][Hp][Wp]
+  float* feat;                            // HWC [Hr*Wr][128]
+  int Hr, Wr, pad_t, pad_l;
+};
+
+__global__ void __launch_bounds__(256) k_aliked_agg(AggParams p) {
+  __shared__ float xs[16][32];
+  const int y = blockIdx.y, xb = blockIdx.x * 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < 16 * 32; e += 256) {
+    const int c = e >> 5, q = e & 31;
+    xs[c][q] = (xb + q < p.Wp) ? p.x1[((size_t)c * p.Hp + y) * p.Wp + xb + q] : 0.f;
+  }
+  float w1[16], ws0[8][4];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) w1[k] = p.W1[lane * 16 + k];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) ws0[j][g] = p.Ws0[j * 128 + g * 32 + lane];
+  __syncthreads();
+  float ly1[3], ly0[3]; int yy0[3], yy1[3];
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const float fy = p.sh[l] * (float)y;
+    yy0[l] = (int)fy; yy1[l] = yy0[l] + (yy0[l] < p.Hk[l] - 1 ? 1 : 0);
+    ly1[l] = fy - (float)yy0[l]; ly0[l] = 1.f - ly1[l];
+  }
+  for (int q = warp * 4; q < warp * 4 + 4; ++q) {
+    const int x = xb + q;
+    if (x >= p.Wp) break;
+    float f[4];
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a = fmaf(w1[k], xs[k][q], a);
+    f[0] = selu_f(a);
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      const float fx = p.sw[l] * (float)x;
+      const int x0 = (int)fx, x1 = x0 + (x0 < p.Wk[l] - 1 ? 1 : 0);
+      const float lx1 = fx - (float)x0, lx0 = 1.f - lx1;
+      const float* b = p.xa[l];
+      const float p00 = b[((size_t)yy0[l] * p.Wk[l] + x0) * 32 + lane], p01 = b[((size_t)yy0[l] * p.Wk[l] + x1) * 32 + lane];
+      const float p10 = b[((size_t)yy1[l] * p.Wk[l] + x0) * 32 + lane], p11 = b[((size_t)yy1[l] * p.Wk[l] + x1) * 32 + lane];
+      f[l + 1] = ly0[l] * (lx0 * p00 + lx1 * p01) + ly1[l] * (lx0 * p10 + lx1 * p11);
+    }
+    const float ssq = warp_sum(f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3]);
+    float mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = warp_sum(ws0[j][0] * f[0] + ws0[j][1] * f[1] + ws0[j][2] * f[2] + ws0[j][3] * f[3]);
+      if (lane == j) mine = s;
+    }
+    if (lane < 8) p.s8[((size_t)lane * p.Hp + y) * p.Wp + x] = selu_f(mine);
+    const int yu = y - p.pad_t, xu = x - p.pad_l;
+    if (yu >= 0 && yu < p.Hr && xu >= 0 && xu < p.Wr) {
+      const float denom = fmaxf(sqrtf(ssq), 1e-12f);
+      float* d = p.feat + ((size_t)yu * p.Wr + xu) * 128 + lane;
+      d[0] = f[0] / denom; d[32] = f[1] / denom; d[64] = f[2] / denom; d[96] = f[3] / denom;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K5b: score-head tail: conv3x3(8->4)+SELU, conv3x3(4->4)+SELU, conv3x3(4->1), sigmoid, all
+// zero-padded at the PADDED image border; writes the unpadded score map [Hr][Wr].
+// tile 32x8, halo 3, block 256.  w2 [4][8][9], w4 [4][4][9], w6 [4][9].
+// ---------------------------------------------------------------------------------------
+struct ScoreParams {
+  const float* s8; int Hp, Wp; const float* w2; const float* w4; const float* w6;
+  float* score; int Hr, Wr, pad_t, pad_l;
+};
+
+__global__ void __launch_bounds__(256) k_aliked_score(ScoreParams p) {
+  constexpr int TW = 32, TH = 8;
+  __shared__ float t0[8][TH + 6][TW + 6];
+  __shared__ float t1[4][TH + 4][TW + 4];
+  __shared__ float t2[4][TH + 2][TW + 2];
+  __shared__ float w2[4 * 8 * 9], w4[4 * 4 * 9], w6[4 * 9];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  for (int e = tid; e < 288; e += 256) w2[e] = p.w2[e];
+  if (tid < 144) w4[tid] = p.w4[tid];
+  if (tid < 36) w6[tid] = p.w6[tid];
+  for (int e = tid; e < 8 * (TH + 6) * (TW + 6); e += 256) {
+    const int c = e / ((TH + 6) * (TW + 6)), r = (e / (TW + 6)) % (TH + 6), q = e % (TW + 6);
+    const int gy = y0 + r - 3, gx = x0 + q - 3;
+    t0[c][r][q] = (gy >= 0 && gy < p.Hp && gx >= 0 && gx < p.Wp) ? p.s8[((size_t)c * p.Hp + gy) * p.Wp + gx] : 0.f;
+  }
+  __syncthreads();
+  for (int e = tid; e < (TH + 4) * (TW + 4); e += 256) {
+    const int r = e / (TW + 4), q = e % (TW + 4);
+    const int gy = y0 + r - 2, gx = x0 + q - 2;
+    const bool in = gy >= 0 && gy < p.Hp && gx >= 0 && gx < p.Wp;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    if (in) {
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const float v = t0[c][r + k / 3][q + k % 3];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) a[o] = fmaf(w2[(o * 8 + c) * 9 + k], v, a[o]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) t1[o][r][q] = in ? selu_f(a[o]) : 0.f;
+  }
+  __syncthreads();
+  for (int e = tid; e < (TH + 2) * (TW + 2); e += 256) {
+    const int r = e / (TW + 2), q = e % (TW + 2);
+    const int gy = y0 + r - 1, gx = x0 + q - 1;
+    const bool in = gy >= 0 && gy < p.Hp && gx >= 0 && gx < p.Wp;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    if (in) {
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const float v = t1[c][r + k / 3][q + k % 3];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) a[o] = fmaf(w4[(o * 4 + c) * 9 + k], v, a[o]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) t2[o][r][q] = in ? selu_f(a[o]) : 0.f;
+  }
+  __syncthreads();
+  {
+    const int r = tid / TW, q = tid % TW;
+    const int gy = y0 + r, gx = x0 + q;
+    const int yu = gy - p.pad_t, xu = gx - p.pad_l;
+    if (gy < p.Hp && gx < p.Wp && yu >= 0 && yu < p.Hr && xu >= 0 && xu < p.Wr) {
+      float a = 0.f;
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) a = fmaf(w6[c * 9 + k], t2[c][r + k / 3][q + k % 3], a);
+      p.score[(size_t)yu * p.Wr + xu] = sigmoid_f(a);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K6a: simple_nms (radius 2, two suppression rounds) + border zeroing + threshold.
+// tile 32x32 with a 10-pixel halo in shared memory.  Pixels outside the image never win a
+// max (torch max_pool2d pads with -inf).  Appends (index, score) of every survivor
+// > *thr to the candidate list (arbitrary order; ranking is fixed later).
+// dk layout (ints): [0]=n_candidates [1]=T(key) [2]=n_ties_to_take [3]=truncated [4]=n_selected
+//                   [5]=fallback flag ; thr is a float in device memory.
+// ---------------------------------------------------------------------------------------
+constexpr int NMS_T = 32, NMS_H = 10, NMS_S = NMS_T + 2 * NMS_H;  // 52
+
+__global__ void __launch_bounds__(256) k_dkd_nms(const float* __restrict__ score, int H, int W, float* __restrict__ nms,
+                                                 const float* __restrict__ thr, int* __restrict__ dk,
+                                                 int* __restrict__ cand_idx, float* __restrict__ cand_sc, int cand_cap) {
+  __shared__ float S[NMS_S][NMS_S + 1];
+  __shared__ float SS[NMS_S][NMS_S + 1];
+  __shared__ unsigned char M[NMS_S][NMS_S + 4], SUP[NMS_S][NMS_S + 4];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * NMS_T - NMS_H, y0 = blockIdx.y * NMS_T - NMS_H;
+  for (int e = tid; e < NMS_S * NMS_S; e += 256) {
+    const int r = e / NMS_S, q = e % NMS_S;
+    const int gy = y0 + r, gx = x0 + q;
+    S[r][q] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? score[(size_t)gy * W + gx] : -INFINITY;
+    M[r][q] = 0; SUP[r][q] = 0;
+  }
+  __syncthreads();
+  // max_mask = S == mp(S) on the region with margin 2
+  for (int e = tid; e < (NMS_S - 4) * (NMS_S - 4); e += 256) {
+    const int r = 2 + e / (NMS_S - 4), q = 2 + e % (NMS_S - 4);
+    const float c = S[r][q];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+      for (int dx = -2; dx <= 2; ++dx) mx = fmaxf(mx, S[r + dy][q + dx]);
+    M[r][q] = (c == mx && c != -INFINITY) ? 1 : 0;
+  }
+  __syncthreads();
+  int lo = 2;
+  for (int it = 0; it < 2; ++it) {
+    // supp = mp(max_mask) > 0 on margin lo+2
+    const int a = lo + 2, na = NMS_S - 2 * a;
+    for (int e = tid; e < na * na; e += 256) {
+      const int r = a + e / na, q = a + e % na;
+      int s = 0;
+#pragma unroll
+      for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+        for (int dx = -2; dx <= 2; ++dx) s |= M[r + dy][q + dx];
+      SUP[r][q] = (unsigned char)s;
+      SS[r][q] = (S[r][q] == -INFINITY) ? -INFINITY : (s ? 0.f : S[r][q]);
+    }
+    __syncthreads();
+    // new_max = SS == mp(SS) on margin lo+4 ; M |= new_max & ~supp
+    const int b = lo + 4, nb = NMS_S - 2 * b;
+    for (int e = tid; e < nb * nb; e += 256) {
+      const int r = b + e / nb, q = b + e % nb;
+      const float c = SS[r][q];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+        for (int dx = -2; dx <= 2; ++dx) mx = fmaxf(mx, SS[r + dy][q + dx]);
+      if (c == mx && c != -INFINITY && !SUP[r][q]) M[r][q] = 1;
+    }
+    __syncthreads();
+    lo = b;
+  }
+  const float th = *thr;
+  for (int e = tid; e < NMS_T * NMS_T; e += 256) {
+    const int r = NMS_H + e / NMS_T, q = NMS_H + e % NMS_T;
+    const int gy = y0 + r, gx = x0 + q;
+    if (gy >= H || gx >= W) continue;
+    float v = M[r][q] ? S[r][q] : 0.f;
+    if (gy < 2 || gx < 2 || gy >= H - 2 || gx >= W - 2) v = 0.f;
+    nms[(size_t)gy * W + gx] = v;
+    if (v > th) {
+      const int slot = atomicAdd(&dk[0], 1);
+      if (slot < cand_cap) { cand_idx[slot] = gy * W + gx; cand_sc[slot] = v; }
+    }
+  }
+}
+
+// K6a': upstream fallback - when nothing passes the threshold use the mean score instead.
+__global__ void __launch_bounds__(1024) k_dkd_fallback(const float* __restrict__ score, const float* __restrict__ nms,
+                                                       int n, float* thr, int* dk, int* cand_idx, float* cand_sc, int cand_cap) {
+  if (dk[0] != 0) return;
+  __shared__ float red[32];
+  __shared__ float mean_s;
+  float a = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) a += score[i];
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 32; ++i) t += red[i];
+    mean_s = t / (float)n;
+    *thr = mean_s; dk[5] = 1;
+  }
+  __syncthreads();
+  const float th = mean_s;
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    const float v = nms[i];
+    if (v > th) {
+      const int slot = atomicAdd(&dk[0], 1);
+      if (slot < cand_cap) { cand_idx[slot] = i; cand_sc[slot] = v; }
+    }
+  }
+}
+
+// K6b: radix select of the n_limit-th largest score key (single CTA).
+__global__ void __launch_bounds__(1024) k_dkd_select(const float* __restrict__ cand_sc, int cand_cap, int n_limit, int* dk) {
+  __shared__ int hist[256];
+  __shared__ unsigned prefix_s;
+  __shared__ int krem_s;
+  const int C = min(dk[0], cand_cap);
+  if (threadIdx.x == 0) { dk[0] = C; dk[4] = 0; }
+  if (C <= n_limit) {
+    if (threadIdx.x == 0) { dk[1] = 0; dk[2] = 0; dk[3] = 0; }
+    return;
+  }
+  if (threadIdx.x == 0) { prefix_s = 0u; krem_s = n_limit; }
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned prefix = prefix_s;
+    const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = threadIdx.x; i < C; i += 1024) {
+      const unsigned key = __float_as_uint(cand_sc[i]);
+      if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int k = krem_s, d = 255, above = 0;
+      for (; d >= 0; --d) {
+        if (above + hist[d] >= k) break;
+        above += hist[d];
+      }
+      krem_s = k - above;
+      prefix_s = prefix | ((unsigned)d << shift);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { dk[1] = (int)prefix_s; dk[2] = krem_s; dk[3] = 1; }
+}
+
+// K6c: gather the selected candidates (key > T, plus the first dk[2] ties by raster index).
+__global__ void __launch_bounds__(256) k_dkd_compact(const int* __restrict__ cand_idx, const float* __restrict__ cand_sc,
+                                                     int* dk, int* __restrict__ sel_idx, float* __restrict__ sel_sc) {
+  const int C = dk[0];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C) return;
+  const unsigned T = (unsigned)dk[1];
+  const unsigned key = __float_as_uint(cand_sc[i]);
+  bool take = false;
+  if (!dk[3]) take = true;
+  else if (key > T) take = true;
+  else if (key == T) {
+    const int me = cand_idx[i];
+    int rank = 0;
+    for (int j = 0; j < C; ++j)
+      if (__float_as_uint(cand_sc[j]) == T && cand_idx[j] < me) ++rank;
+    take = rank < dk[2];
+  }
+  if (take) {
+    const int slot = atomicAdd(&dk[4], 1);
+    sel_idx[slot] = cand_idx[i]; sel_sc[slot] = cand_sc[i];
+  }
+}
+
+// K6d: rank (score desc, raster idx asc when truncated; raster idx asc otherwise), 5x5
+// soft-argmax refinement (T=0.1), dispersity, bilinear score sample, coordinate transforms.
+struct RefineParams {
+  const int* dk; const int* sel_idx; const float* sel_sc; const float* score; int H, W;
+  float scale_x, scale_y;      // resized/original (W'/W, H'/H)
+  float* kp_norm;              // [K,2] in [-1,1] (DKD output, SDDH input)
+  float* kp_out;               // [K,2] original-image pixels
+  float* disp; float* sampled; // [K]
+  int32_t* n_out;
+};
+
+__global__ void __launch_bounds__(256) k_dkd_refine(RefineParams p) {
+  const int K = p.dk[4];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e == 0) *p.n_out = K;
+  if (e >= K) return;
+  const int idx = p.sel_idx[e];
+  const float sc = p.sel_sc[e];
+  const bool trunc = p.dk[3] != 0;
+  int rank = 0;
+  for (int j = 0; j < K; ++j) {
+    const int oi = p.sel_idx[j];
+    if (trunc) {
+      const float os = p.sel_sc[j];
+      rank += (os > sc || (os == sc && oi < idx)) ? 1 : 0;
+    } else {
+      rank += (oi < idx) ? 1 : 0;
+    }
+  }
+  const int W = p.W, H = p.H;
+  const int xi = idx % W, yi = idx / W;
+  float patch[25], mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 25; ++k) {
+    const int yy = yi + k / 5 - 2, xx = xi + k % 5 - 2;
+    patch[k] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? p.score[(size_t)yy * W + xx] : 0.f;
+    mx = fmaxf(mx, patch[k]);
+  }
+  float sum = 0.f, rx = 0.f, ry = 0.f;
+#pragma unroll
+  for (int k = 0; k < 25; ++k) {
+    patch[k] = expf((patch[k] - mx) / 0.1f);
+    sum += patch[k];
+    rx += patch[k] * (float)(k % 5 - 2);
+    ry += patch[k] * (float)(k / 5 - 2);
+  }
+  rx /= sum; ry /= sum;
+  float dsp = 0.f;
+#pragma unroll
+  for (int k = 0; k < 25; ++k) {
+    const float dx = ((float)(k % 5 - 2) - rx) / 2.f, dy = ((float)(k / 5 - 2) - ry) / 2.f;
+    const float nr = sqrtf(dx * dx + dy * dy);
+    dsp += patch[k] * (nr * nr);
+  }
+  dsp /= sum;
+  const float whx = (float)(W - 1), why = (float)(H - 1);
+  const float nx = ((float)xi + rx) / whx * 2.f - 1.f, ny = ((float)yi + ry) / why * 2.f - 1.f;
+  // grid_sample(score, (nx,ny)), bilinear, align_corners=True, zeros padding
+  const float gx = ((nx + 1.f) / 2.f) * whx, gy = ((ny + 1.f) / 2.f) * why;
+  const float fx0 = floorf(gx), fy0 = floorf(gy);
+  const int ix0 = (int)fx0, iy0 = (int)fy0, ix1 = ix0 + 1, iy1 = iy0 + 1;
+  const float wnw = ((float)ix1 - gx) * ((float)iy1 - gy), wne = (gx - (float)ix0) * ((float)iy1 - gy);
+  const float wsw = ((float)ix1 - gx) * (gy - (float)iy0), wse = (gx - (float)ix0) * (gy - (float)iy0);
+  auto at = [&](int yy, int xx) { return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? p.score[(size_t)yy * W + xx] : 0.f; };
+  const float smp = at(iy0, ix0) * wnw + at(iy0, ix1) * wne + at(iy1, ix0) * wsw + at(iy1, ix1) * wse;
+  p.kp_norm[2 * rank] = nx; p.kp_norm[2 * rank + 1] = ny;
+  // ALIKED.forward: wh*(kp+1)/2 ; Extractor.extract: (kp+0.5)/scales - 0.5
+  const float px = whx * (nx + 1.f) / 2.0f, py = why * (ny + 1.f) / 2.0f;
+  p.kp_out[2 * rank] = (px + 0.5f) / p.scale_x - 0.5f;
+  p.kp_out[2 * rank + 1] = (py + 0.5f) / p.scale_y - 0.5f;
+  p.disp[rank] = dsp; p.sampled[rank] = smp;
+}
+
+// ---------------------------------------------------------------------------------------
+// K7 gathers.  Feature map is HWC [H*W][128].
+// (a) 3x3 patch rows for the offset conv: A[n][tap*128 + c]; warp per (keypoint, tap)
+// (b) M deformable samples per keypoint: S[n*M + m][c]; warp per sample
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sddh_patch(const float* __restrict__ feat, int H, int W, const float* __restrict__ kp_norm,
+                                                    const int32_t* __restrict__ n_dev, float* __restrict__ A) {
+  const int job = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int n = job / 9, tap = job % 9;
+  if (n >= *n_dev) return;
+  const int lane = threadIdx.x & 31;
+  const float kx = (kp_norm[2 * n] / 2.f + 0.5f) * (float)(W - 1), ky = (kp_norm[2 * n + 1] / 2.f + 0.5f) * (float)(H - 1);
+  const int cx = (int)kx, cy = (int)ky;                      // .long() truncation
+  int ox = (int)((float)cx - 0.5f), oy = (int)((float)cy - 0.5f);  // (c - ps/2 + 1).long()
+  ox = min(max(ox, 0), W - 4); oy = min(max(oy, 0), H - 4);
+  const int yy = oy + tap / 3, xx = ox + tap % 3;
+  const float4 v = *reinterpret_cast<const float4*>(feat + ((size_t)yy * W + xx) * 128 + lane * 4);
+  *reinterpret_cast<float4*>(A + (size_t)n * 1152 + tap * 128 + lane * 4) = v;
+}
+
+__global__ void __launch_bounds__(256) k_sddh_sample(const float* __restrict__ feat, int H, int W, const float* __restrict__ kp_norm,
+                                                     const float* __restrict__ offs /*[n][M][2]*/, int M,
+                                                     const int32_t* __restrict__ n_dev, float* __restrict__ S) {
+  const int job = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int n = job / M;
+  if (n >= *n_dev) return;
+  const int lane = threadIdx.x & 31;
+  const float whx = (float)(W - 1), why = (float)(H - 1);
+  const float kx = (kp_norm[2 * n] / 2.f + 0.5f) * whx, ky = (kp_norm[2 * n + 1] / 2.f + 0.5f) * why;
+  const float posx = kx + offs[(size_t)job * 2], posy = ky + offs[(size_t)job * 2 + 1];
+  const float nx = 2.0f * posx / whx - 1.f, ny = 2.0f * posy / why - 1.f;
+  const float gx = ((nx + 1.f) / 2.f) * whx, gy = ((ny + 1.f) / 2.f) * why;
+  const float fx0 = floorf(gx), fy0 = floorf(gy);
+  const int ix0 = (int)fx0, iy0 = (int)fy0, ix1 = ix0 + 1, iy1 = iy0 + 1;
+  const float wnw = ((float)ix1 - gx) * ((float)iy1 - gy), wne = (gx - (float)ix0) * ((float)iy1 - gy);
+  const float wsw = ((float)ix1 - gx) * (gy - (float)iy0), wse = (gx - (float)ix0) * (gy - (float)iy0);
+  auto ld = [&](int yy, int xx) {
+    return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? *reinterpret_cast<const float4*>(feat + ((size_t)yy * W + xx) * 128 + lane * 4)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  const float4 a = ld(iy0, ix0), b = ld(iy0, ix1), c = ld(iy1, ix0), d = ld(iy1, ix1);
+  float4 o;
+  o.x = a.x * wnw + b.x * wne + c.x * wsw + d.x * wse;
+  o.y = a.y * wnw + b.y * wne + c.y * wsw + d.y * wse;
+  o.z = a.z * wnw + b.z * wne + c.z * wsw + d.z * wse;
+  o.w = a.w * wnw + b.w * wne + c.w * wsw + d.w * wse;
+  *reinterpret_cast<float4*>(S + (size_t)job * 128 + lane * 4) = o;
+}
+
+// F.normalize(desc, dim=1) (eps 1e-12).  warp per row of 128.
+__global__ void __launch_bounds__(256) k_desc_normalize(const float* __restrict__ raw, const int32_t* __restrict__ n_dev, float* __restrict__ out) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= *n_dev) return;
+  const int lane = threadIdx.x & 31;
+  const float4 v = *reinterpret_cast<const float4*>(raw + (size_t)n * 128 + lane * 4);
+  const float ssq = warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+  const float d = fmaxf(sqrtf(ssq), 1e-12f);
+  *reinterpret_cast<float4*>(out + (size_t)n * 128 + lane * 4) = make_float4(v.x / d, v.y / d, v.z / d, v.w / d);
+}
+
+}  // namespace b2s

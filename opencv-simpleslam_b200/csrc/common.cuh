@@ -1,0 +1,112 @@
+// common.cuh - shared host/device helpers for libb200slam (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200slam.h"
+
+namespace b2s {
+
+void set_error(const char* fmt, ...);
+
+#define B2S_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      b2s::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return B2S_ECUDA;                                                                  \
+    }                                                                                    \
+  } while (0)
+
+#define B2S_TRY(expr)          \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != 0) return _r;    \
+  } while (0)
+
+#define B2S_LAUNCH_CHECK()                                                               \
+  do {                                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      b2s::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return B2S_ECUDA;                                                                  \
+    }                                                                                    \
+  } while (0)
+
+// ---- weight blob ("B2SW", see weights.py::pack_state) -----------------------------------
+struct TensorView {
+  const float* data = nullptr;  // host pointer into the blob
+  int ndim = 0;
+  int dims[4] = {1, 1, 1, 1};
+  size_t numel() const { return (size_t)dims[0] * dims[1] * dims[2] * dims[3]; }
+};
+
+struct WeightBlob {
+  std::map<std::string, TensorView> t;
+  int parse(const void* blob, size_t nbytes);
+  // returns nullptr (and sets the error) when missing or when numel mismatches (expect>0)
+  const TensorView* get(const std::string& name, size_t expect_numel = 0) const;
+};
+
+// ---- device memory owned by a handle ----------------------------------------------------
+struct DeviceArena {
+  std::vector<void*> ptrs;
+  ~DeviceArena() { release(); }
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+  }
+  template <typename T>
+  int alloc(T** out, size_t count) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes) -> %s", count * sizeof(T), cudaGetErrorString(e));
+      return B2S_ENOMEM;
+    }
+    ptrs.push_back(p);
+    *out = (T*)p;
+    return 0;
+  }
+  template <typename T>
+  int upload(T** out, const std::vector<T>& host) {
+    B2S_TRY(alloc(out, host.size()));
+    B2S_CUDA(cudaMemcpy(*out, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+  }
+};
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- device helpers -----------------------------------------------------------------------
+__device__ __forceinline__ float selu_f(float x) {
+  // torch SELU: scale * (max(0,x) + min(0, alpha*(exp(x)-1)))
+  const float alpha = 1.6732632423543772848170429916717f;
+  const float scale = 1.0507009873554804934193349852946f;
+  return x > 0.f ? scale * x : scale * (alpha * expm1f(x));
+}
+__device__ __forceinline__ float gelu_erf_f(float x) {
+  return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float logsigmoid_f(float x) {
+  // torch: min(0,x) - log1p(exp(-|x|))
+  return fminf(0.f, x) - log1pf(expf(-fabsf(x)));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace b2s

@@ -1,0 +1,525 @@
+// lightglue_kernels.cuh - bandwidth/latency-bound stages of the LightGlue matcher (fp32):
+// keypoint normalisation + learnable Fourier encoding, flash-style attention (FFMA),
+// LayerNorm+GELU, token-confidence / matchability heads, point-pruning compaction, dual
+// log-softmax assignment, mutual-NN filter.  Upstream spec: SURVEY.md Appendix A.3.
+#pragma once
+#include "common.cuh"
+
+namespace b2s {
+
+// ---------------------------------------------------------------------------------------
+// K9: normalize_keypoints + posenc.  grid = 2 (one CTA per image), block = 256.
+// upstream: size = 1 + max - min (when no image_size); shift = size/2; scale = max(size)/2;
+//           kn = (k - shift)/scale ; proj = Wr kn ; emb = (cos proj, sin proj)
+// ---------------------------------------------------------------------------------------
+struct PosencParams {
+  const float* kp[2]; int n[2]; int base[2];
+  int has_size[2]; float size[2][2];
+  const float* Wr;           // [32,2]
+  float* kn;                 // [rows,2]
+  float* cosb; float* sinb;  // [rows,32]
+  int* ind;                  // [rows]  identity index map
+  int* prune[2];             // per image [n] (nullable) -> 1
+};
+
+__global__ void __launch_bounds__(256) k_lg_posenc(PosencParams p) {
+  const int s = blockIdx.x;
+  const int n = p.n[s];
+  const float* kp = p.kp[s];
+  __shared__ float red[4][8];
+  __shared__ float sh_shift[2], sh_scale;
+  float sx, sy;
+  if (p.has_size[s]) {
+    sx = p.size[s][0]; sy = p.size[s][1];
+  } else {
+    float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float x = kp[2 * i], y = kp[2 * i + 1];
+      mnx = fminf(mnx, x); mxx = fmaxf(mxx, x); mny = fminf(mny, y); mxy = fmaxf(mxy, y);
+    }
+    mnx = -warp_max(-mnx); mny = -warp_max(-mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { red[0][w] = mnx; red[1][w] = mny; red[2][w] = mxx; red[3][w] = mxy; }
+    __syncthreads();
+    mnx = red[0][0]; mny = red[1][0]; mxx = red[2][0]; mxy = red[3][0];
+    for (int i = 1; i < 8; ++i) {
+      mnx = fminf(mnx, red[0][i]); mny = fminf(mny, red[1][i]);
+      mxx = fmaxf(mxx, red[2][i]); mxy = fmaxf(mxy, red[3][i]);
+    }
+    sx = 1.f + mxx - mnx; sy = 1.f + mxy - mny;
+  }
+  if (threadIdx.x == 0) {
+    sh_shift[0] = sx / 2.f; sh_shift[1] = sy / 2.f; sh_scale = fmaxf(sx, sy) / 2.f;
+  }
+  __syncthreads();
+  const float shx = sh_shift[0], shy = sh_shift[1], sc = sh_scale;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = p.base[s] + i;
+    const float x = (kp[2 * i] - shx) / sc, y = (kp[2 * i + 1] - shy) / sc;
+    p.kn[2 * r] = x; p.kn[2 * r + 1] = y;
+    p.ind[r] = i;
+    if (p.prune[s]) p.prune[s][i] = 1;
+#pragma unroll 4
+    for (int f = 0; f < 32; ++f) {
+      const float pr = p.Wr[2 * f] * x + p.Wr[2 * f + 1] * y;
+      p.cosb[(size_t)r * 32 + f] = cosf(pr);
+      p.sinb[(size_t)r * 32 + f] = sinf(pr);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K11/K12 attention core (fp32 FFMA, online softmax).  O = softmax(Q K^T * scale) V
+// grid = (ceil(max nq / 64), heads, nprob), block = 256, dyn smem = 4 * 64 * 68 * 4 B.
+// Thread (ty,tx) of a 16x16 grid owns S[ty*4..+4][tx*4..+4] and O[ty*4..+4][tx*4..+4].
+// ---------------------------------------------------------------------------------------
+struct AttnProb { const float* Q; const float* K; const float* V; float* O; int nq, nk; };
+struct AttnParams { AttnProb prob[2]; int ldq, ldk, ldv, ldo; float scale; };
+
+constexpr int ATT_B = 64, ATT_D = 64, ATT_LD = 68;
+constexpr int ATT_SMEM = 4 * ATT_B * ATT_LD * (int)sizeof(float);
+
+__global__ void __launch_bounds__(256) k_attn_fp32(AttnParams p) {
+  extern __shared__ __align__(16) float att_smem[];
+  float (*Qs)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem);                       // [d][q]
+  float (*Ks)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem + ATT_B * ATT_LD);      // [d][k]
+  float (*Vs)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem + 2 * ATT_B * ATT_LD);  // [k][d]
+  float (*Ps)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem + 3 * ATT_B * ATT_LD);  // [k][q]
+
+  const AttnProb pr = p.prob[blockIdx.z];
+  const int q0 = blockIdx.x * ATT_B;
+  if (q0 >= pr.nq) return;
+  const int hoff = blockIdx.y * ATT_D;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+
+  // Q tile -> Qs[d][q]
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int f = tid + i * 256, r = f >> 4, dq = f & 15;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < pr.nq) v = *reinterpret_cast<const float4*>(pr.Q + (size_t)(q0 + r) * p.ldq + hoff + dq * 4);
+    Qs[dq * 4 + 0][r] = v.x; Qs[dq * 4 + 1][r] = v.y; Qs[dq * 4 + 2][r] = v.z; Qs[dq * 4 + 3][r] = v.w;
+  }
+
+  float o[4][4], mrow[4], lrow[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    mrow[i] = -INFINITY; lrow[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  }
+
+  for (int k0 = 0; k0 < pr.nk; k0 += ATT_B) {
+    __syncthreads();  // previous P.V done (and Q stores visible on the first pass)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = tid + i * 256, r = f >> 4, dq = f & 15;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (k0 + r < pr.nk) {
+        kv = *reinterpret_cast<const float4*>(pr.K + (size_t)(k0 + r) * p.ldk + hoff + dq * 4);
+        vv = *reinterpret_cast<const float4*>(pr.V + (size_t)(k0 + r) * p.ldv + hoff + dq * 4);
+      }
+      Ks[dq * 4 + 0][r] = kv.x; Ks[dq * 4 + 1][r] = kv.y; Ks[dq * 4 + 2][r] = kv.z; Ks[dq * 4 + 3][r] = kv.w;
+      *reinterpret_cast<float4*>(&Vs[r][dq * 4]) = vv;
+    }
+    __syncthreads();
+
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < ATT_D; ++d) {
+      const float4 a = *reinterpret_cast<const float4*>(&Qs[d][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Ks[d][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] = fmaf(av[i], bv[j], s[i][j]);
+    }
+    // online softmax
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[i][j] = (k0 + tx * 4 + j < pr.nk) ? s[i][j] * p.scale : -INFINITY;
+        mx = fmaxf(mx, s[i][j]);
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      const float mnew = fmaxf(mrow[i], mx);
+      const float corr = expf(mrow[i] - mnew);
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[i][j] = expf(s[i][j] - mnew); sum += s[i][j]; }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+      lrow[i] = lrow[i] * corr + sum;
+      mrow[i] = mnew;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[i][j] *= corr;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(&Ps[tx * 4 + j][ty * 4]) = make_float4(s[0][j], s[1][j], s[2][j], s[3][j]);
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < ATT_B; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&Ps[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Vs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[i][j] = fmaf(av[i], bv[j], o[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = q0 + ty * 4 + i;
+    if (r >= pr.nq) continue;
+    const float inv = pr.nk > 0 ? 1.f / lrow[i] : 0.f;
+    *reinterpret_cast<float4*>(pr.O + (size_t)r * p.ldo + hoff + tx * 4) =
+        make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// FFN middle: LayerNorm(512, eps 1e-5, affine) + GELU(erf), in place.  One warp per row.
+// ---------------------------------------------------------------------------------------
+struct RowSeg { int base[2]; int rows[2]; };
+
+__global__ void __launch_bounds__(256) k_ln_gelu_512(float* h, RowSeg seg, const float* gamma, const float* beta) {
+  const int s = blockIdx.y;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= seg.rows[s]) return;
+  const int lane = threadIdx.x & 31;
+  float* x = h + (size_t)(seg.base[s] + row) * 512;
+  float4 v[4];
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    v[t] = *reinterpret_cast<const float4*>(x + t * 128 + lane * 4);
+    sum += (v[t].x + v[t].y) + (v[t].z + v[t].w);
+  }
+  const float mean = warp_sum(sum) * (1.f / 512.f);
+  float sq = 0.f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float a = v[t].x - mean, b = v[t].y - mean, c = v[t].z - mean, d = v[t].w - mean;
+    sq += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(sq) * (1.f / 512.f) + 1e-5f);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int c = t * 128 + lane * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 b = *reinterpret_cast<const float4*>(beta + c);
+    float4 o;
+    o.x = gelu_erf_f((v[t].x - mean) * rstd * g.x + b.x);
+    o.y = gelu_erf_f((v[t].y - mean) * rstd * g.y + b.y);
+    o.z = gelu_erf_f((v[t].z - mean) * rstd * g.z + b.z);
+    o.w = gelu_erf_f((v[t].w - mean) * rstd * g.w + b.w);
+    *reinterpret_cast<float4*>(x + c) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K13: per-row heads.  tok = sigmoid(wt.x + bt); mat = sigmoid(wm.x + bm).  One warp/row.
+// ctrl[0] accumulates #(tok < thr) over both images (upstream check_if_stop).
+// keep[row] = (mat > 1 - width_conf) | (tok <= thr)        (upstream get_pruning_mask)
+// Also used (mode z) to produce logsigmoid(z) for the assignment.
+// ---------------------------------------------------------------------------------------
+struct HeadParams {
+  const float* x; RowSeg seg;
+  const float* wt; float bt; const float* wm; float bm;
+  float thr; float keep_thr; int use_tok; int use_match;
+  float* tok; int* keep; int* ctrl;
+  float* ls_pos;   // if set: write logsigmoid(wm.x+bm) and nothing else
+};
+
+__global__ void __launch_bounds__(256) k_lg_heads(HeadParams p) {
+  const int s = blockIdx.y;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= p.seg.rows[s]) return;
+  const int lane = threadIdx.x & 31;
+  const int r = p.seg.base[s] + row;
+  const float* x = p.x + (size_t)r * 256;
+  const float4 a = *reinterpret_cast<const float4*>(x + lane * 4);
+  const float4 b = *reinterpret_cast<const float4*>(x + 128 + lane * 4);
+  float dt = 0.f, dm = 0.f;
+  if (p.use_tok) {
+    const float4 w0 = *reinterpret_cast<const float4*>(p.wt + lane * 4);
+    const float4 w1 = *reinterpret_cast<const float4*>(p.wt + 128 + lane * 4);
+    dt = a.x * w0.x + a.y * w0.y + a.z * w0.z + a.w * w0.w + b.x * w1.x + b.y * w1.y + b.z * w1.z + b.w * w1.w;
+    dt = warp_sum(dt);
+  }
+  if (p.use_match || p.ls_pos) {
+    const float4 w0 = *reinterpret_cast<const float4*>(p.wm + lane * 4);
+    const float4 w1 = *reinterpret_cast<const float4*>(p.wm + 128 + lane * 4);
+    dm = a.x * w0.x + a.y * w0.y + a.z * w0.z + a.w * w0.w + b.x * w1.x + b.y * w1.y + b.z * w1.z + b.w * w1.w;
+    dm = warp_sum(dm);
+  }
+  if (lane != 0) return;
+  if (p.ls_pos) { p.ls_pos[r] = logsigmoid_f(dm + p.bm); return; }
+  bool keep = false;
+  if (p.use_match) keep = sigmoid_f(dm + p.bm) > p.keep_thr;
+  if (p.use_tok) {
+    const float t = sigmoid_f(dt + p.bt);
+    p.tok[r] = t;
+    if (t < p.thr) atomicAdd(&p.ctrl[0], 1);
+    keep = keep || (t <= p.thr);
+  }
+  p.keep[r] = keep ? 1 : 0;
+}
+
+// ctrl layout: [0]=#unconfident  [1]=stop flag  [2]=count0  [3]=count1  [4]=n_matches
+__global__ void k_lg_decide(int* ctrl, int num_points, float depth_conf, int do_stop) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int stop = 0;
+    if (do_stop) {
+      const float ratio = 1.0f - (float)ctrl[0] / (float)num_points;
+      stop = ratio > depth_conf ? 1 : 0;
+    }
+    ctrl[1] = stop;
+    ctrl[0] = 0;
+  }
+}
+
+// order-preserving compaction map.  grid = 2, block = 1024.  srcmap[base + dst] = src.
+// A side that must not be pruned (stop fired / below the pruning threshold) gets the identity.
+struct ScanParams { const int* keep; int* srcmap; int* ctrl; int base[2]; int rows[2]; int can_prune[2]; };
+
+__global__ void __launch_bounds__(1024) k_lg_prune_scan(ScanParams p) {
+  const int s = blockIdx.x;
+  const int n = p.rows[s], base = p.base[s];
+  const bool prune = p.can_prune[s] && (p.ctrl[1] == 0);
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int i0 = 0; i0 < n; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    const int k = (i < n) ? (prune ? p.keep[base + i] : 1) : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, k);
+    const int inwarp = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) wsum[w] = __popc(bal);
+    __syncthreads();
+    int off = carry;
+    for (int j = 0; j < w; ++j) off += wsum[j];
+    if (k) p.srcmap[base + off + inwarp] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int j = 0; j < 32; ++j) t += wsum[j];
+      carry += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) p.ctrl[2 + s] = carry;
+}
+
+// gather rows into the other ping-pong buffers.  grid = (ceil(maxrows/8), 2), block 256 (warp/row)
+struct GatherParams {
+  const int* srcmap; const int* ctrl; int base[2]; int rows[2];
+  const float* x_in; float* x_out; const float* cos_in; float* cos_out; const float* sin_in; float* sin_out;
+  const int* ind_in; int* ind_out; int* prune[2]; int can_prune[2];
+};
+
+__global__ void __launch_bounds__(256) k_lg_gather(GatherParams p) {
+  const int s = blockIdx.y;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= p.ctrl[2 + s]) return;
+  const int lane = threadIdx.x & 31;
+  const int src = p.base[s] + p.srcmap[p.base[s] + j], dst = p.base[s] + j;
+  const float4* xi = reinterpret_cast<const float4*>(p.x_in + (size_t)src * 256);
+  float4* xo = reinterpret_cast<float4*>(p.x_out + (size_t)dst * 256);
+  xo[lane] = xi[lane]; xo[lane + 32] = xi[lane + 32];
+  p.cos_out[(size_t)dst * 32 + lane] = p.cos_in[(size_t)src * 32 + lane];
+  p.sin_out[(size_t)dst * 32 + lane] = p.sin_in[(size_t)src * 32 + lane];
+  if (lane == 0) {
+    const int orig = p.ind_in[src];
+    p.ind_out[dst] = orig;
+    if (p.prune[s] && p.can_prune[s] && p.ctrl[1] == 0) p.prune[s][orig] += 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K14: dual log-softmax statistics over the materialised similarity sim[m,n] (ld).
+// row pass: one warp per row -> rmax[i], rlog[i] = log(sum exp(sim - rmax)).
+// col pass: CTA = 32 columns x 32 row-lanes -> cmax[j], clog[j].
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_lg_row_lse(const float* sim, int ld, int m, int n, float* rmax, float* rlog) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= m) return;
+  const int lane = threadIdx.x & 31;
+  const float* r = sim + (size_t)i * ld;
+  float mx = -INFINITY;
+  for (int j = lane; j < n; j += 32) mx = fmaxf(mx, r[j]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < n; j += 32) sum += expf(r[j] - mx);
+  sum = warp_sum(sum);
+  if (lane == 0) { rmax[i] = mx; rlog[i] = logf(sum); }
+}
+
+__global__ void __launch_bounds__(1024) k_lg_col_lse(const float* sim, int ld, int m, int n, float* cmax, float* clog) {
+  __shared__ float smx[32][33], ssm[32][33];
+  const int tx = threadIdx.x & 31, tyy = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  float mx = -INFINITY, sum = 0.f;
+  if (j < n) {
+    for (int i = tyy; i < m; i += 32) mx = fmaxf(mx, sim[(size_t)i * ld + j]);
+  }
+  smx[tyy][tx] = mx;
+  __syncthreads();
+  float cm = -INFINITY;
+  for (int t = 0; t < 32; ++t) cm = fmaxf(cm, smx[t][tx]);
+  if (j < n) {
+    for (int i = tyy; i < m; i += 32) sum += expf(sim[(size_t)i * ld + j] - cm);
+  }
+  ssm[tyy][tx] = sum;
+  __syncthreads();
+  if (tyy == 0 && j < n) {
+    float t = 0.f;
+    for (int q = 0; q < 32; ++q) t += ssm[q][tx];
+    cmax[j] = cm; clog[j] = logf(t);
+  }
+}
+
+// assignment value, in upstream's association order:
+//   scores = (log_softmax_row + log_softmax_col) + (logsigmoid(z0) + logsigmoid(z1))
+__device__ __forceinline__ float assign_val(float s, float rm, float rl, float cm, float cl, float l0, float l1) {
+  return (((s - rm) - rl) + ((s - cm) - cl)) + (l0 + l1);
+}
+
+// K15a: row-wise max/argmax (first index on ties).  One warp per row.
+__global__ void __launch_bounds__(256) k_lg_row_argmax(const float* sim, int ld, int m, int n, const float* rmax,
+                                                       const float* rlog, const float* cmax, const float* clog,
+                                                       const float* ls0, const float* ls1, float* max0, int* m0) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= m) return;
+  const int lane = threadIdx.x & 31;
+  const float* r = sim + (size_t)i * ld;
+  const float rm = rmax[i], rl = rlog[i], l0 = ls0[i];
+  float best = -INFINITY; int bj = 0x7fffffff;
+  for (int j = lane; j < n; j += 32) {
+    const float v = assign_val(r[j], rm, rl, cmax[j], clog[j], l0, ls1[j]);
+    if (v > best) { best = v; bj = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+    if (ob > best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+  }
+  if (lane == 0) { max0[i] = best; m0[i] = bj == 0x7fffffff ? 0 : bj; }
+}
+
+// K15b: column-wise argmax.  CTA = 32 columns x 32 row-lanes.
+__global__ void __launch_bounds__(1024) k_lg_col_argmax(const float* sim, int ld, int m, int n, const float* rmax,
+                                                        const float* rlog, const float* cmax, const float* clog,
+                                                        const float* ls0, const float* ls1, int* m1) {
+  __shared__ float sv[32][33];
+  __shared__ int si[32][33];
+  const int tx = threadIdx.x & 31, tyy = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  float best = -INFINITY; int bi = 0x7fffffff;
+  if (j < n) {
+    const float cm = cmax[j], cl = clog[j], l1 = ls1[j];
+    for (int i = tyy; i < m; i += 32) {
+      const float v = assign_val(sim[(size_t)i * ld + j], rmax[i], rlog[i], cm, cl, ls0[i], l1);
+      if (v > best) { best = v; bi = i; }
+    }
+  }
+  sv[tyy][tx] = best; si[tyy][tx] = bi;
+  __syncthreads();
+  if (tyy == 0 && j < n) {
+    for (int t = 1; t < 32; ++t) {
+      const float ob = sv[t][tx]; const int oi = si[t][tx];
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    m1[j] = bi == 0x7fffffff ? 0 : bi;
+  }
+}
+
+// K15c: upstream filter_matches + match list.  Single CTA of 1024 threads.
+struct FilterParams {
+  int m, n; float th;
+  const float* max0; const int* m0; const int* m1;
+  const int* ind0; const int* ind1;          // pruned-index -> original index
+  int32_t* matches; float* mscores; int32_t* n_matches;   // compact outputs
+  int32_t* matches0; int32_t* matches1; float* ms0; float* ms1;  // full-size (nullable)
+};
+
+__global__ void __launch_bounds__(1024) k_lg_filter(FilterParams p) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int i0 = 0; i0 < p.m; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    int valid = 0, j = 0; float sc = 0.f;
+    if (i < p.m) {
+      j = p.m0[i];
+      const bool mutual = (p.m1[j] == i);
+      sc = mutual ? expf(p.max0[i]) : 0.f;
+      valid = mutual && (sc > p.th);
+      const int oi = p.ind0[i];
+      if (p.ms0) p.ms0[oi] = sc;
+      if (p.matches0) p.matches0[oi] = valid ? p.ind1[j] : -1;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, valid);
+    const int inwarp = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) wsum[w] = __popc(bal);
+    __syncthreads();
+    int off = carry;
+    for (int q = 0; q < w; ++q) off += wsum[q];
+    if (valid) {
+      p.matches[2 * (off + inwarp)] = p.ind0[i];
+      p.matches[2 * (off + inwarp) + 1] = p.ind1[j];
+      p.mscores[off + inwarp] = sc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int q = 0; q < 32; ++q) t += wsum[q];
+      carry += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *p.n_matches = carry;
+  // side 1: mscores1 = mutual1 ? mscores0[m1] : 0 ; valid1 = mutual1 & valid0[m1]
+  if (p.matches1 || p.ms1) {
+    for (int j = threadIdx.x; j < p.n; j += 1024) {
+      const int i = p.m1[j];
+      const bool mutual1 = (p.m0[i] == j);
+      float sc = 0.f; bool valid1 = false;
+      if (mutual1) {
+        const bool mutual0 = true;  // m0[i]==j and m1[j]==i
+        sc = mutual0 ? expf(p.max0[i]) : 0.f;
+        valid1 = sc > p.th;
+      }
+      const int oj = p.ind1[j];
+      if (p.ms1) p.ms1[oj] = sc;
+      if (p.matches1) p.matches1[oj] = valid1 ? p.ind0[i] : -1;
+    }
+  }
+}
+
+// fill helpers
+__global__ void k_fill_i32(int32_t* p, int n, int32_t v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void k_fill_f32(float* p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace b2s

@@ -1,0 +1,21 @@
+// lightglue_tc.cuh - bf16 tcgen05/TMEM path of the LightGlue layer (interface).
+#pragma once
+#include "common.cuh"
+
+namespace b2s {
+
+struct LgTensorCore;
+struct LgTcLayerSrc {   // fp32 device weights of one layer (self block then cross block)
+  const float *wqkv, *bqkv, *wo, *bo, *w1, *b1, *lng, *lnb, *w2, *b2;
+  const float *cwqkv, *cbqkv, *cwo, *cbo, *cw1, *cb1, *clng, *clnb, *cw2, *cb2;
+};
+
+int lgtc_create(LgTensorCore** out, size_t n_layers);
+int lgtc_set_layer(LgTensorCore* tc, int layer, const LgTcLayerSrc& src);
+int lgtc_alloc_ws(LgTensorCore* tc, int cap);
+// one full transformer layer (self + cross) in place on x [2*cap,256] fp32 master copy
+int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int layer, float* x, const float* cosb, const float* sinb, int cap,
+               int m, int n, long long* launches);
+void lgtc_destroy(LgTensorCore* tc);
+
+}  // namespace b2s

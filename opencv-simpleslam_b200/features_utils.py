@@ -1,0 +1,163 @@
+"""Drop-in replacement for `/root/reference/slam/core/features_utils.py`: same function names,
+signatures and return types, so `main_revamped.py`, `keyframe_utils.select_keyframe`
+(:153), `triangulation_utils.triangulate_between_kfs_2view` (:131), `pnp_utils` and
+`two_view_bootstrap` run unchanged.  The LightGlue branch runs on libb200slam.so (sm_100a
+CUDA); the OpenCV (ORB/SIFT/AKAZE + BF/FLANN) branch is plain cv2 as in the reference.
+
+Differences from the reference that are invisible to callers:
+  * the u8 BGR frame is uploaded as is (1.4 MB instead of a 5.6 MB float image) and the
+    BGR->RGB, /255 conversion happens inside the preprocess kernel;
+  * keypoints come back as one [N,2] array and are turned into cv2.KeyPoint objects with
+    cv2.KeyPoint_convert (no 2N device->host scalar syncs, features_utils.py:61-63);
+  * matching is one C-ABI call on host buffers (b2s_lightglue_match_host).
+"""
+from __future__ import annotations
+
+from typing import List
+
+import cv2
+import numpy as np
+import torch
+
+from .frontend import ALIKED, LightGlue, rbd  # noqa: F401  (re-exported like the reference's imports)
+
+
+# --------------------------------------------------------------------------- #
+#  Initialisation helpers                       (features_utils.py:18-55)
+# --------------------------------------------------------------------------- #
+def init_feature_pipeline(args):
+    """Instantiate detector & matcher according to CLI arguments. Returns (detector, matcher)."""
+    if args.use_lightglue:
+        if not torch.cuda.is_available():
+            raise RuntimeError("b200slam: the LightGlue branch needs a CUDA device (no CPU fallback)")
+        detector = ALIKED(max_num_keypoints=int(getattr(args, "max_features", 4000))).eval().to("cuda")
+        matcher = LightGlue(features="aliked",
+                            precision=str(getattr(args, "lg_precision", "fp32"))).eval().to("cuda")
+    else:
+        detector = _get_opencv_detector(args.detector, max_features=int(getattr(args, "max_features", 6000)))
+        matcher = _get_opencv_matcher(args.matcher, args.detector)
+    return detector, matcher
+
+
+def _get_opencv_detector(detector_type, max_features=6000):
+    makers = {"orb": lambda: cv2.ORB_create(max_features),
+              "sift": lambda: cv2.SIFT_create(nfeatures=max_features),
+              "akaze": lambda: cv2.AKAZE_create()}
+    if detector_type not in makers:
+        raise ValueError(f"Unsupported detector: {detector_type}")
+    return makers[detector_type]()
+
+
+def _get_opencv_matcher(matcher_type, detector_type):
+    if matcher_type == "flann":
+        return cv2.FlannBasedMatcher(dict(algorithm=1, trees=5), dict(checks=50))
+    norm = cv2.NORM_HAMMING if detector_type in ("orb", "akaze") else cv2.NORM_L2
+    return cv2.BFMatcher(norm, crossCheck=True)
+
+
+# --------------------------------------------------------------------------- #
+#  Conversions                                  (features_utils.py:61-83)
+# --------------------------------------------------------------------------- #
+def _convert_lg_kps_to_opencv(kp0) -> List[cv2.KeyPoint]:
+    pts = kp0.detach().cpu().numpy() if isinstance(kp0, torch.Tensor) else np.asarray(kp0)
+    pts = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 2)
+    if len(pts) == 0:
+        return []
+    # == [cv2.KeyPoint(float(x), float(y), 1) for x, y in kp0] (size 1, angle -1, response 0)
+    return list(cv2.KeyPoint_convert(pts, size=1.0, response=0.0, octave=0, class_id=-1))
+
+
+def _kps_to_array(cv_kp) -> np.ndarray:
+    if len(cv_kp) == 0:
+        return np.empty((0, 2), np.float32)
+    return np.ascontiguousarray(cv2.KeyPoint_convert(list(cv_kp)), dtype=np.float32).reshape(-1, 2)
+
+
+def _convert_opencv_to_lg_kps(cv_kp) -> torch.Tensor:
+    return torch.from_numpy(_kps_to_array(cv_kp))
+
+
+def _convert_lg_matches_to_opencv(matches_raw) -> List[cv2.DMatch]:
+    pairs = matches_raw.cpu().numpy() if isinstance(matches_raw, torch.Tensor) else np.asarray(matches_raw)
+    return [cv2.DMatch(int(i), int(j), 0, 0.0) for i, j in pairs.tolist()]
+
+
+# --------------------------------------------------------------------------- #
+#  Extraction / matching                        (features_utils.py:85-171)
+# --------------------------------------------------------------------------- #
+def feature_extractor(args, img: np.ndarray, detector):
+    """Extract features from one BGR frame -> (list[cv2.KeyPoint], np.float32 [N,128])."""
+    if args.use_lightglue:
+        kps, des0, _ = detector.extract_host(img)
+        kp0 = _convert_lg_kps_to_opencv(kps)
+        des0 = des0.astype(np.float32, copy=True)
+        des0 /= (np.linalg.norm(des0, axis=1, keepdims=True) + 1e-8).astype(np.float32)   # features_utils.py:100
+        return kp0, des0
+    kp0, des0 = detector.detectAndCompute(img, None)
+    if des0 is None:
+        return [], []
+    return kp0, des0
+
+
+def feature_matcher(args, kp0, kp1, des0, des1, matcher):
+    """Match two frames -> list[cv2.DMatch] (queryIdx -> kp0, trainIdx -> kp1, ascending queryIdx)."""
+    if (des0 is None or des1 is None or kp0 is None or kp1 is None
+            or len(kp0) == 0 or len(kp1) == 0 or len(des0) == 0 or len(des1) == 0):
+        return []
+    if args.use_lightglue:
+        d0 = des0.detach().cpu().numpy() if isinstance(des0, torch.Tensor) else des0
+        d1 = des1.detach().cpu().numpy() if isinstance(des1, torch.Tensor) else des1
+        # no image_size: upstream then normalises by the keypoint extent (features_utils.py:158-161)
+        raw = matcher.match_host(_kps_to_array(kp0), d0, _kps_to_array(kp1), d1)
+        thr = float(getattr(args, "min_conf", 0.7))
+        keep = raw["scores"] > np.float32(thr)
+        return _convert_lg_matches_to_opencv(raw["matches"][keep])
+    matches = matcher.match(des0, des1)
+    return sorted(matches, key=lambda m: m.distance)
+
+
+def filter_matches_ransac(kp1, kp2, matches, thresh=1.0):
+    """Drop outliers with a fundamental-matrix RANSAC (features_utils.py:185-200; CPU, cv2)."""
+    if len(matches) < 8:
+        return matches
+    pts1 = np.float32([kp1[m.queryIdx].pt for m in matches])
+    pts2 = np.float32([kp2[m.trainIdx].pt for m in matches])
+    _, mask = cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC, thresh, 0.99)
+    if mask is None:
+        return []
+    mask = mask.ravel().astype(bool)
+    return [m for m, ok in zip(matches, mask) if ok]
+
+
+# --------------------------------------------------------------------------- #
+#  One-shot convenience path                    (features_utils.py:209-255)
+# --------------------------------------------------------------------------- #
+def _opencv_detect_and_match(img1, img2, detector, matcher):
+    kp1, des1 = detector.detectAndCompute(img1, None)
+    kp2, des2 = detector.detectAndCompute(img2, None)
+    if des1 is None or des2 is None:
+        return [], [], [], [], []
+    return kp1, kp2, des1, des2, sorted(matcher.match(des1, des2), key=lambda m: m.distance)
+
+
+def _bgr_to_tensor(image):
+    img_rgb = cv2.cvtColor(image, cv2.COLOR_BGR2RGB).astype(np.float32) / 255.0
+    return torch.from_numpy(img_rgb).permute(2, 0, 1).unsqueeze(0).cuda()
+
+
+def _convert_lightglue_to_opencv(kp0, kp1, matches):
+    return _convert_lg_kps_to_opencv(kp0), _convert_lg_kps_to_opencv(kp1), _convert_lg_matches_to_opencv(matches)
+
+
+def _lightglue_detect_and_match(img1, img2, extractor, matcher):
+    f0, f1 = extractor.extract_bgr(img1), extractor.extract_bgr(img2)
+    matches = rbd(matcher({"image0": f0, "image1": f1}))   # with image_size, no min_conf (as the reference)
+    f0, f1 = rbd(f0), rbd(f1)
+    cv_kp0, cv_kp1, cv_matches = _convert_lightglue_to_opencv(f0["keypoints"], f1["keypoints"], matches["matches"])
+    return cv_kp0, cv_kp1, f0["descriptors"], f1["descriptors"], cv_matches
+
+
+def detect_and_match(img1, img2, detector, matcher, args):
+    if args.use_lightglue:
+        return _lightglue_detect_and_match(img1, img2, detector, matcher)
+    return _opencv_detect_and_match(img1, img2, detector, matcher)

@@ -1,0 +1,303 @@
+"""Drop-in objects for `lightglue.ALIKED`, `lightglue.LightGlue` and `lightglue.utils.rbd`
+as used by `/root/reference/slam/core/features_utils.py:8-9,25-26,94-95,157-162`.
+Host code is Python/PyTorch (device memory, streams); all arithmetic runs in libb200slam.so
+(hand-written sm_100a kernels) through the C ABI in include/b200slam.h."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, weights as _weights
+from ._lib import lib, check
+
+
+def rbd(data: dict) -> dict:
+    """lightglue.utils.rbd: strip the batch dimension (features_utils.py:95,162,240-241)."""
+    return {k: v[0] if isinstance(v, (torch.Tensor, np.ndarray, list)) else v for k, v in data.items()}
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("b200slam needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if dev.type != "cuda":
+        raise RuntimeError(f"b200slam runs on CUDA only, got device {dev}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+class _Module:
+    """The little bit of nn.Module surface the reference touches: eval(), to(), parameters()."""
+    _handle = None
+
+    def eval(self):
+        return self
+
+    def train(self, mode=False):
+        return self
+
+    def to(self, device=None, *a, **k):
+        dev = None
+        if isinstance(device, (str, torch.device)):
+            dev = torch.device(device)
+        if dev is not None and dev.type == "cpu":
+            raise RuntimeError("b200slam runs on CUDA only (no CPU fallback)")
+        if dev is not None and dev.type == "cuda":
+            idx = dev.index if dev.index is not None else torch.cuda.current_device()
+            if idx != self.device.index:
+                self._create(torch.device("cuda", idx))
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", device) if isinstance(device, int) else (device or "cuda"))
+
+    def parameters(self):
+        # features_utils.py:131 reads next(matcher.parameters()).device
+        yield self._param
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+
+class ALIKED(_Module):
+    """lightglue.ALIKED replacement (features_utils.py:25: `ALIKED(max_num_keypoints=...)`)."""
+
+    def __init__(self, model_name="aliked-n16", max_num_keypoints=-1, detection_threshold=0.2, nms_radius=2,
+                 resize=1024, weights=None, device=None, seed=0, **_ignored):
+        if model_name not in _weights.ALIKED_CFGS:
+            raise ValueError(f"unsupported ALIKED model {model_name}")
+        self.model_name, self.max_num_keypoints = model_name, int(max_num_keypoints)
+        self.detection_threshold, self.nms_radius, self.resize = float(detection_threshold), int(nms_radius), resize
+        if weights is None:
+            weights, self.weight_source = _weights.load_aliked_state(model_name, seed)
+        else:
+            self.weight_source = "provided"
+        self._blob = _weights.pack_state(weights)
+        self.n_limit = self.max_num_keypoints if self.max_num_keypoints > 0 else 20000
+        self._create(_require_cuda(device))
+
+    def _create(self, dev):
+        self._destroy()
+        cfg = _lib.AlikedCfg()
+        lib.b2s_aliked_default_cfg(C.byref(cfg))
+        cfg.model = 1 if self.model_name == "aliked-n32" else 0
+        cfg.max_kp = self.max_num_keypoints
+        cfg.det_thresh = self.detection_threshold
+        cfg.nms_radius = self.nms_radius
+        cfg.resize_long = int(self.resize) if self.resize else 0
+        h = C.c_void_p()
+        check(lib.b2s_aliked_create(C.byref(cfg), self._blob, len(self._blob), dev.index, C.byref(h)), "b2s_aliked_create")
+        self._handle, self.device = h, dev
+        self._param = torch.empty(1, device=dev)
+        with torch.cuda.device(dev):
+            self._kp = torch.empty((self.n_limit, 2), dtype=torch.float32, device=dev)
+            self._desc = torch.empty((self.n_limit, 128), dtype=torch.float32, device=dev)
+            self._sc = torch.empty((self.n_limit,), dtype=torch.float32, device=dev)
+            self._n = torch.zeros((1,), dtype=torch.int32, device=dev)
+            self._n_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+
+    def _destroy(self):
+        if getattr(self, "_handle", None):
+            lib.b2s_aliked_destroy(self._handle)
+            self._handle = None
+
+    # -- device-resident entry: enqueue on the current stream, outputs stay on the GPU -------
+    def extract_device(self, img: torch.Tensor, fmt: int, H: int, W: int, row_stride: int = 0):
+        """img: CUDA tensor (u8 HWC BGR or f32 CHW RGB). Returns views (kpts, desc, scores, n_dev)
+        into handle-owned buffers, valid until the next call."""
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        check(lib.b2s_aliked_extract(self._handle, img.data_ptr(), fmt, H, W, row_stride, st, self._kp.data_ptr(),
+                                     self._desc.data_ptr(), self._sc.data_ptr(), self._n.data_ptr()), "b2s_aliked_extract")
+        return self._kp, self._desc, self._sc, self._n
+
+    def _finish(self, H, W):
+        self._n_host.copy_(self._n, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        n = int(self._n_host[0])
+        return {"keypoints": self._kp[:n].clone()[None], "descriptors": self._desc[:n].clone()[None],
+                "keypoint_scores": self._sc[:n].clone()[None],
+                "image_size": torch.tensor([[float(W), float(H)]], device=self.device)}
+
+    @torch.no_grad()
+    def extract(self, img: torch.Tensor, **conf) -> dict:
+        """upstream Extractor.extract: img f32 [1,3,H,W] or [3,H,W] RGB in [0,1] (features_utils.py:94)."""
+        if img.dim() == 3:
+            img = img[None]
+        assert img.dim() == 4 and img.shape[0] == 1, "batch size must be 1 (as upstream)"
+        if img.shape[1] == 1:
+            img = img.expand(-1, 3, -1, -1)
+        H, W = int(img.shape[-2]), int(img.shape[-1])
+        with torch.cuda.device(self.device):
+            t = img[0].to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            self.extract_device(t, _lib.IMG_RGB_F32_CHW, H, W)
+            return self._finish(H, W)
+
+    @torch.no_grad()
+    def extract_bgr(self, image: np.ndarray) -> dict:
+        """u8 BGR HxWx3 image straight from cv2 (fuses `_bgr_to_tensor`, features_utils.py:219-222)."""
+        if image.ndim != 3 or image.shape[2] != 3 or image.dtype != np.uint8:
+            raise ValueError("expected an HxWx3 uint8 BGR image")
+        H, W = image.shape[:2]
+        with torch.cuda.device(self.device):
+            t = torch.from_numpy(np.ascontiguousarray(image)).to(self.device, non_blocking=True)
+            self.extract_device(t, _lib.IMG_BGR_U8_HWC, H, W, 3 * W)
+            return self._finish(H, W)
+
+    def extract_host(self, image: np.ndarray):
+        """One C-ABI call with host buffers (b2s_aliked_extract_host): returns numpy (kpts, desc, scores)."""
+        H, W = image.shape[:2]
+        if image.dtype == np.uint8:
+            image = np.ascontiguousarray(image); fmt = _lib.IMG_BGR_U8_HWC; stride = 3 * W
+        else:
+            image = np.ascontiguousarray(image, dtype=np.float32); fmt = _lib.IMG_RGB_F32_CHW; stride = 0
+            H, W = image.shape[-2:]
+        kp = np.empty((self.n_limit, 2), np.float32)
+        de = np.empty((self.n_limit, 128), np.float32)
+        sc = np.empty((self.n_limit,), np.float32)
+        n = C.c_int32(0)
+        check(lib.b2s_aliked_extract_host(self._handle, image.ctypes.data, fmt, H, W, stride, kp.ctypes.data,
+                                          de.ctypes.data, sc.ctypes.data, C.addressof(n)), "b2s_aliked_extract_host")
+        return kp[:n.value], de[:n.value], sc[:n.value]
+
+    def debug(self, name: str) -> np.ndarray:
+        n = C.c_size_t(0)
+        check(lib.b2s_aliked_debug_get(self._handle, name.encode(), None, 0, C.byref(n)), "debug_get")
+        out = np.empty((n.value,), np.float32)
+        check(lib.b2s_aliked_debug_get(self._handle, name.encode(), out.ctypes.data, n.value, C.byref(n)), "debug_get")
+        return out
+
+    @property
+    def launches(self) -> int:
+        return int(lib.b2s_aliked_launch_count(self._handle))
+
+
+class LightGlue(_Module):
+    """lightglue.LightGlue replacement (features_utils.py:26: `LightGlue(features='aliked')`)."""
+
+    def __init__(self, features="aliked", depth_confidence=0.95, width_confidence=0.99, filter_threshold=0.1,
+                 weights=None, device=None, seed=0, precision="fp32", pruning_threshold=-1, max_kp=2048, **_ignored):
+        if features != "aliked":
+            raise ValueError("only features='aliked' is supported")
+        self.depth_confidence, self.width_confidence = float(depth_confidence), float(width_confidence)
+        self.filter_threshold, self.pruning_threshold = float(filter_threshold), int(pruning_threshold)
+        self.precision, self.max_kp = precision, int(max_kp)
+        if weights is None:
+            weights, self.weight_source = _weights.load_lightglue_state(seed)
+        else:
+            self.weight_source = "provided"
+        self.n_layers = 1 + max(int(k.split(".")[1]) for k in weights if k.startswith("transformers."))
+        self._blob = _weights.pack_state(weights)
+        self._create(_require_cuda(device))
+
+    def _create(self, dev):
+        self._destroy()
+        cfg = _lib.LgCfg()
+        lib.b2s_lg_default_cfg(C.byref(cfg))
+        cfg.n_layers = self.n_layers
+        cfg.depth_conf, cfg.width_conf, cfg.filter_thresh = self.depth_confidence, self.width_confidence, self.filter_threshold
+        cfg.pruning_min_kpts = self.pruning_threshold
+        cfg.precision = _lib.BF16 if self.precision == "bf16" else _lib.FP32
+        cfg.max_kp = self.max_kp
+        h = C.c_void_p()
+        check(lib.b2s_lightglue_create(C.byref(cfg), self._blob, len(self._blob), dev.index, C.byref(h)), "b2s_lightglue_create")
+        self._handle, self.device = h, dev
+        self._param = torch.empty(1, device=dev)
+
+    def _destroy(self):
+        if getattr(self, "_handle", None):
+            lib.b2s_lg_destroy(self._handle)
+            self._handle = None
+
+    def match_device(self, k0, d0, k1, d1, size0=None, size1=None, full=True):
+        """CUDA f32 tensors k [m,2], d [m,128]; enqueues on the current stream.  Returns a dict of
+        device tensors (+ 'stop'); 'n' is a device int32 count for matches/scores."""
+        m, n = int(k0.shape[0]), int(k1.shape[0])
+        dev = self.device
+        k = max(min(m, n), 1)
+        out = {"matches": torch.empty((k, 2), dtype=torch.int32, device=dev),
+               "scores": torch.empty((k,), dtype=torch.float32, device=dev),
+               "n": torch.zeros((1,), dtype=torch.int32, device=dev)}
+        ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
+        if full:
+            out.update(matches0=torch.empty((m,), dtype=torch.int32, device=dev), matches1=torch.empty((n,), dtype=torch.int32, device=dev),
+                       matching_scores0=torch.empty((m,), dtype=torch.float32, device=dev),
+                       matching_scores1=torch.empty((n,), dtype=torch.float32, device=dev),
+                       prune0=torch.empty((m,), dtype=torch.int32, device=dev), prune1=torch.empty((n,), dtype=torch.int32, device=dev))
+        s0 = (C.c_float * 2)(*[float(v) for v in size0]) if size0 is not None else None
+        s1 = (C.c_float * 2)(*[float(v) for v in size1]) if size1 is not None else None
+        stop = C.c_int32(0)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        check(lib.b2s_lightglue_match(
+            self._handle, k0.data_ptr(), d0.data_ptr(), m, k1.data_ptr(), d1.data_ptr(), n,
+            C.cast(s0, C.c_void_p) if s0 is not None else None, C.cast(s1, C.c_void_p) if s1 is not None else None, st,
+            out["matches"].data_ptr(), out["scores"].data_ptr(), out["n"].data_ptr(), C.addressof(stop),
+            ptr(out.get("matches0")), ptr(out.get("matches1")), ptr(out.get("matching_scores0")),
+            ptr(out.get("matching_scores1")), ptr(out.get("prune0")), ptr(out.get("prune1"))), "b2s_lightglue_match")
+        out["stop"] = stop.value
+        return out
+
+    @torch.no_grad()
+    def __call__(self, data: dict) -> dict:
+        """upstream LightGlue.forward contract (features_utils.py:157-161, :237)."""
+        d0, d1 = data["image0"], data["image1"]
+        with torch.cuda.device(self.device):
+            prep = lambda t: t.to(self.device, dtype=torch.float32).contiguous()   # noqa: E731
+            k0, k1 = prep(d0["keypoints"]), prep(d1["keypoints"])
+            e0, e1 = prep(d0["descriptors"]), prep(d1["descriptors"])
+            assert k0.dim() == 3 and k0.shape[0] == 1, "batch size must be 1"
+            sz = []
+            for d in (d0, d1):
+                s = d.get("image_size")
+                sz.append(None if s is None else [float(v) for v in torch.as_tensor(s).reshape(-1)[:2].tolist()])
+            r = self.match_device(k0[0], e0[0], k1[0], e1[0], sz[0], sz[1], full=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            nm = int(r["n"].item())
+            return {"matches0": r["matches0"].long()[None], "matches1": r["matches1"].long()[None],
+                    "matching_scores0": r["matching_scores0"][None], "matching_scores1": r["matching_scores1"][None],
+                    "stop": r["stop"], "matches": [r["matches"][:nm].long()], "scores": [r["scores"][:nm]],
+                    "prune0": r["prune0"].long()[None], "prune1": r["prune1"].long()[None]}
+
+    forward = __call__
+
+    def match_host(self, k0, d0, k1, d1, size0=None, size1=None, full=False):
+        """One C-ABI call with host (numpy f32) buffers: b2s_lightglue_match_host."""
+        k0 = np.ascontiguousarray(k0, np.float32); k1 = np.ascontiguousarray(k1, np.float32)
+        d0 = np.ascontiguousarray(d0, np.float32); d1 = np.ascontiguousarray(d1, np.float32)
+        m, n = len(k0), len(k1)
+        k = max(min(m, n), 1)
+        matches = np.empty((k, 2), np.int32); scores = np.empty((k,), np.float32)
+        nm, stop = C.c_int32(0), C.c_int32(0)
+        extra = {}
+        if full:
+            extra = dict(matches0=np.empty(m, np.int32), matches1=np.empty(n, np.int32), matching_scores0=np.empty(m, np.float32),
+                         matching_scores1=np.empty(n, np.float32), prune0=np.empty(m, np.int32), prune1=np.empty(n, np.int32))
+        p = lambda a: a.ctypes.data if a is not None else None   # noqa: E731
+        s0 = np.asarray(size0, np.float32) if size0 is not None else None
+        s1 = np.asarray(size1, np.float32) if size1 is not None else None
+        check(lib.b2s_lightglue_match_host(
+            self._handle, p(k0), p(d0), m, p(k1), p(d1), n, p(s0), p(s1), p(matches), p(scores), C.addressof(nm),
+            C.addressof(stop), p(extra.get("matches0")), p(extra.get("matches1")), p(extra.get("matching_scores0")),
+            p(extra.get("matching_scores1")), p(extra.get("prune0")), p(extra.get("prune1"))), "b2s_lightglue_match_host")
+        out = {"matches": matches[:nm.value], "scores": scores[:nm.value], "stop": stop.value}
+        out.update(extra)
+        return out
+
+    def set_debug(self, on=True):
+        check(lib.b2s_lg_set_debug(self._handle, 1 if on else 0), "b2s_lg_set_debug")
+
+    def debug(self, name: str) -> np.ndarray:
+        n = C.c_size_t(0)
+        check(lib.b2s_lg_debug_get(self._handle, name.encode(), None, 0, C.byref(n)), "debug_get")
+        out = np.empty((max(n.value, 1),), np.float32)
+        check(lib.b2s_lg_debug_get(self._handle, name.encode(), out.ctypes.data, n.value, C.byref(n)), "debug_get")
+        return out[:n.value]
+
+    @property
+    def launches(self) -> int:
+        return int(lib.b2s_lg_launch_count(self._handle))
