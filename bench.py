@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py - ALIKED+LightGlue frame-pairs/sec on synthetic KITTI-shaped frames (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16]
+
+A "step" is PAIRS_PER_STEP frame-pairs of the steady-state stream (BASELINE config 2: extract
+frame t, match (t-1, t)) = 1 ALIKED extraction + 1 LightGlue match per unit, 1241x376, 2048 kp.
+
+  value : device-resident throughput - u8 frames already in HBM, keypoints/descriptors stay on the
+          device between extraction and matching (b2s_aliked_extract / b2s_lightglue_match), timed
+          with CUDA events per step on the launching stream, L2 flushed between steps.
+  e2e   : the same metric through the drop-in API (features_utils.feature_extractor +
+          feature_matcher) with HOST numpy buffers: H2D of the frame, D2H of keypoints/descriptors,
+          H2D of both frames' features for the match, D2H of the matches; lists of
+          cv2.KeyPoint/cv2.DMatch built. Wall clock bracketed by synchronisation.
+  roofline : dominant kernel (attention) timed live with CUDA events inside the library
+          (b2s_lg_profile) during the timed steps.
+  cpu_baseline : the CPU oracle (port of the reference's lightglue path) through the same API on
+          the host cores, bounded sample.  --impl reference runs only that arm.
+Multi-GPU (torchrun): every rank streams its own contiguous chunk of frames (halo frame
+re-extracted locally, no data-path collective) -> weak scaling; time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, NKP = 376, 1241, 2048
+PAIRS_PER_STEP = 8
+METRIC = "ALIKED+LightGlue frame-pairs/sec @1241x376, 2048 kp"
+
+
+def lg_flops(m, n, L=9):
+    """F_LG with the cross similarity counted once per layer."""
+    return (2 * (m + n) * 128 * 256 + L * ((m + n) * 2_490_368 + 1024 * (m * m + n * n) + 1536 * m * n)
+            + 2 * (m + n) * 256 ** 2 + 2 * m * n * 256)
+
+
+def aliked_flops(px=320 * 1024, n=NKP, M=16):
+    return 20018.75 * px + n * (2 * 128 * 9 * 2 * M + 2 * (2 * M) ** 2 + 4 * M * 128 ** 2)
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_arm(steps, warmup, n_pairs_per_step=1):
+    """The reference's CPU path (oracle port; `lightglue` itself is not installable here) through
+    feature_extractor/feature_matcher, all host threads.  Returns (pairs/s, ms_per_step, meta)."""
+    import oracle  # noqa: F401  (test infrastructure; allowed here as the cpu baseline only)
+    from oracle import features_utils as ofu
+    from b200slam import weights, synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    args = SimpleNamespace(use_lightglue=True, max_features=NKP, min_conf=0.7)
+    sa, src_a = weights.load_aliked_state()
+    sl, src_l = weights.load_lightglue_state()
+    det, mat = ofu.init_feature_pipeline(args, sa, sl)
+    frames = [synth.frame(t, H, W) for t in range((warmup + steps) * n_pairs_per_step + 1)]
+    prev = ofu.feature_extractor(args, frames[0], det)
+    times, nm, t_idx = [], [], 1
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        for _ in range(n_pairs_per_step):
+            cur = ofu.feature_extractor(args, frames[t_idx], det)
+            ms = ofu.feature_matcher(args, prev[0], cur[0], prev[1], cur[1], mat)
+            prev = cur
+            t_idx += 1
+            nm.append(len(ms))
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    ms_per_step = 1e3 * float(np.mean(times))
+    meta = {"kind": "port", "cores": torch.get_num_threads(),
+            "sample": f"{steps * n_pairs_per_step} frame-pairs after {warmup * n_pairs_per_step} warm-up, CPU oracle via feature_extractor+feature_matcher",
+            "weights": f"{src_a} / {src_l}", "mean_matches": float(np.mean(nm)), "torch": torch.__version__}
+    return n_pairs_per_step * 1e3 / ms_per_step, ms_per_step, meta
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    v, ms, meta = cpu_reference_arm(args.steps, args.warmup, 1)
+    meta["value"] = v
+    meta["unit"] = "frame-pairs/s"
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "frame-pairs/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "kitti_stream_1241x376_2048kp (BASELINE config 2)", "pairs_per_step": 1},
+                      "cpu_baseline": meta,
+                      "e2e": {"value": v, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_ours(args):
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - b200slam has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from b200slam import features_utils as fu, synth, frontend, weights, _lib
+
+    ns = SimpleNamespace(use_lightglue=True, max_features=NKP, min_conf=0.7, lg_precision=args.precision)
+    sa, src_a = weights.load_aliked_state()
+    sl, src_l = weights.load_lightglue_state()
+    det = frontend.ALIKED(max_num_keypoints=NKP, weights=sa, device=dev)
+    mat = frontend.LightGlue(weights=sl, device=dev, precision=args.precision, max_kp=NKP)
+
+    K, Wm, P = args.steps, args.warmup, PAIRS_PER_STEP
+    n_frames = (K + Wm) * P + 1
+    t_base = rank * n_frames            # each rank owns its own contiguous chunk of the stream
+    pool = 64                            # distinct frames kept in HBM (re-used cyclically)
+    frames_np = [synth.frame(t_base + t, H, W) for t in range(min(n_frames, pool))]
+    frames_dev = [torch.from_numpy(f).to(dev) for f in frames_np]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    kp_buf = [torch.empty((NKP, 2), device=dev), torch.empty((NKP, 2), device=dev)]
+    de_buf = [torch.empty((NKP, 128), device=dev), torch.empty((NKP, 128), device=dev)]
+    n_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    counts = [0, 0]
+    match_counts = []
+
+    def extract_into(slot, t):
+        kp, de, _, n = det.extract_device(frames_dev[t % len(frames_dev)], _lib.IMG_BGR_U8_HWC, H, W, 3 * W)
+        kp_buf[slot].copy_(kp, non_blocking=True)
+        de_buf[slot].copy_(de, non_blocking=True)
+        n_host.copy_(n, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the keypoint count sizes the matcher's launch
+        counts[slot] = int(n_host[0])
+
+    def device_step(t0):
+        res = None
+        for i in range(P):
+            t = t0 + i
+            cur, prv = t & 1, (t - 1) & 1
+            extract_into(cur, t)
+            res = mat.match_device(kp_buf[prv][:counts[prv]], de_buf[prv][:counts[prv]],
+                                   kp_buf[cur][:counts[cur]], de_buf[cur][:counts[cur]], full=False)
+        return res
+
+    extract_into(0, 0)
+    for s in range(Wm):
+        device_step(1 + s * P)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = det.launches + mat.launches
+    mat.profile(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = []
+    wall0 = time.perf_counter()
+    for s in range(K):
+        flush.fill_(s & 0xFF)                       # L2 flush between timed iterations (untimed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = device_step(1 + (Wm + s) * P)
+        e1.record()
+        evs.append((e0, e1))
+        match_counts.append(res["n"])
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    launches = det.launches + mat.launches - l0
+    attn_ms, attn_n = mat.profile_read(0)
+    gemm_ms, gemm_n = mat.profile_read(1)
+    mat.profile(False)
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+    mean_matches = float(np.mean([int(c.item()) for c in match_counts]))
+
+    # ---- e2e through the drop-in API with host buffers -------------------------------------
+    e2e_pairs = max(4, min(K * P, 24))
+    prev = fu.feature_extractor(ns, frames_np[0], det)
+    for t in range(1, 3):   # warm-up
+        cur = fu.feature_extractor(ns, frames_np[t % len(frames_np)], det)
+        fu.feature_matcher(ns, prev[0], cur[0], prev[1], cur[1], mat)
+        prev = cur
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for t in range(3, 3 + e2e_pairs):
+        cur = fu.feature_extractor(ns, frames_np[t % len(frames_np)], det)
+        ms = fu.feature_matcher(ns, prev[0], cur[0], prev[1], cur[1], mat)
+        h2d += H * W * 3 + (len(prev[0]) + len(cur[0])) * (2 + 128) * 4
+        d2h += len(cur[0]) * (2 + 128 + 1) * 4 + 4 + min(len(prev[0]), len(cur[0])) * 12 + 4
+        prev = cur
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_matches = len(ms)
+
+    t_total = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+    total_ms_max, e2e_s_max = float(t_total[0]), float(t_total[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * K * P / (total_ms_max / 1e3)
+    e2e_value = world * e2e_pairs / e2e_s_max
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s"
+    # dominant kernel: attention. Algorithmic flops per launch (two problems per launch:
+    # self = both images, cross = both directions): 2 * 4*N*N*64*... = QK^T + PV over 4 heads
+    # SURVEY 8d counting: self launch = 1024*(M^2+N^2), cross launch = 1536*M*N (similarity once)
+    attn_flops_per_launch = (1024 * 2 * NKP * NKP + 1536 * NKP * NKP) / 2
+    attn_avg_ms = attn_ms / max(attn_n, 1)
+    achieved = attn_flops_per_launch / (attn_avg_ms * 1e-3) / 1e12 if attn_n else None
+    out = {
+        "metric": METRIC, "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "config": {"workload": "kitti_stream_1241x376_2048kp (BASELINE config 2)", "pairs_per_step": P,
+                   "unit_of_work": "1 ALIKED-n16 extract + 1 LightGlue match (9 layers, adaptive depth/width on)",
+                   "l2": "flushed between steps (256 MiB write)", "weights": f"{src_a} / {src_l}",
+                   "mean_matches_per_pair": mean_matches, "precision": args.precision},
+        "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "h2d_bytes_per_step": int(h2d / e2e_pairs * P),
+                "d2h_bytes_per_step": int(d2h / e2e_pairs * P), "pairs_timed": e2e_pairs,
+                "api": "features_utils.feature_extractor + feature_matcher (host numpy in, cv2 lists out)",
+                "matches_last_pair": e2e_matches},
+        "roofline": {"bound": "tensor", "kernel": "k_attn_fp32" if args.precision == "fp32" else "attention (bf16 path)",
+                     "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                     "frac": (achieved / tensor_peak) if achieved else None, "traffic": None,
+                     "peak_source": peak_src, "launches_timed": int(attn_n), "avg_launch_ms": attn_avg_ms,
+                     "share_of_step": attn_ms / total_ms if total_ms else None,
+                     "gemm_share_of_step": gemm_ms / total_ms if total_ms else None,
+                     "whole_pair_tflops": (lg_flops(NKP, NKP) + aliked_flops()) * K * P / (total_ms * 1e-3) / 1e12},
+        "clocks": clocks,
+        "wall_s_timed_region": wall,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, ms_cpu, meta = cpu_reference_arm(steps=3, warmup=1)
+        meta.update(value=v, unit="frame-pairs/s")
+        out["cpu_baseline"] = meta
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("B2S_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -144,6 +144,13 @@ int b2s_aliked_debug_get(b2s_aliked* h, const char* name, float* out, size_t cap
 int b2s_lg_set_debug(b2s_lg* h, int on);
 int b2s_lg_debug_get(b2s_lg* h, const char* name, float* out, size_t cap, size_t* n);
 
+/* Per-kernel-class timing with CUDA events recorded on the launching stream (used by bench.py
+ * for roofline.achieved).  cls: 0 = attention kernel, 1 = GEMM kernels.  profile_read
+ * synchronises on the recorded events, returns the summed kernel time (ms) and the number of
+ * launches, and clears the records. */
+int b2s_lg_profile(b2s_lg* h, int on);
+int b2s_lg_profile_read(b2s_lg* h, int cls, double* ms, long long* n_launches);
+
 /* Number of CUDA kernels this library launched on behalf of the handle so far. */
 long long b2s_aliked_launch_count(const b2s_aliked* h);
 long long b2s_lg_launch_count(const b2s_lg* h);

@@ -83,6 +83,36 @@ struct DeviceArena {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// ---- per-kernel-class CUDA-event timing (bench.py's roofline.achieved is measured with it) --
+enum ProfClass { PROF_ATTN = 0, PROF_GEMM = 1, PROF_NCLASS = 2 };
+struct KernelProf {
+  bool on = false;
+  std::vector<cudaEvent_t> ev[PROF_NCLASS];
+  size_t used[PROF_NCLASS] = {0, 0};
+  ~KernelProf() {
+    for (auto& v : ev) for (cudaEvent_t e : v) cudaEventDestroy(e);
+  }
+  void mark(int cls, cudaStream_t st) {   // call before and after a launch
+    if (!on) return;
+    if (used[cls] == ev[cls].size()) { cudaEvent_t e; cudaEventCreate(&e); ev[cls].push_back(e); }
+    cudaEventRecord(ev[cls][used[cls]++], st);
+  }
+  // sums (stop - start) over the recorded pairs, then forgets them
+  int read(int cls, double* ms, long long* n) {
+    double tot = 0.0; long long cnt = 0;
+    for (size_t i = 0; i + 1 < used[cls]; i += 2) {
+      float t = 0.f;
+      cudaError_t e = cudaEventSynchronize(ev[cls][i + 1]);
+      if (e == cudaSuccess) e = cudaEventElapsedTime(&t, ev[cls][i], ev[cls][i + 1]);
+      if (e != cudaSuccess) { set_error("profile read: %s", cudaGetErrorString(e)); return B2S_ECUDA; }
+      tot += t; ++cnt;
+    }
+    used[cls] = 0;
+    *ms = tot; *n = cnt;
+    return 0;
+  }
+};
+
 // ---- device helpers -----------------------------------------------------------------------
 __device__ __forceinline__ float selu_f(float x) {
   // torch SELU: scale * (max(0,x) + min(0, alpha*(exp(x)-1)))

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256, (BM >= 128 ? 2 : 3)) k_gemm_simt(GemmPara
 }
 
 // Host launcher: picks the tile that best fills 148 SMs.
-inline int gemm_simt(const GemmParams& p, cudaStream_t st, long long* launches) {
+inline int gemm_simt(const GemmParams& p, cudaStream_t st, long long* launches, KernelProf* prof = nullptr) {
   if (p.K % 16 != 0 || (p.K1 % 16) != 0) {
     set_error("gemm_simt: K=%d / K1=%d must be multiples of 16", p.K, p.K1);
     return B2S_EINVAL;
@@ -183,6 +183,7 @@ inline int gemm_simt(const GemmParams& p, cudaStream_t st, long long* launches) 
   int maxrows = q.M;
   if (q.nseg > 1) maxrows = q.seg_rows[0] > q.seg_rows[1] ? q.seg_rows[0] : q.seg_rows[1];
   if (maxrows <= 0 || q.N <= 0) return 0;
+  if (prof) prof->mark(PROF_GEMM, st);
   const long long big = (long long)cdiv(maxrows, 128) * cdiv(q.N, 128) * q.nseg;
   if (big >= 148 && q.N >= 128) {
     dim3 g(cdiv(q.N, 128), cdiv(maxrows, 128), q.nseg);
@@ -191,6 +192,7 @@ inline int gemm_simt(const GemmParams& p, cudaStream_t st, long long* launches) 
     dim3 g(cdiv(q.N, 64), cdiv(maxrows, 64), q.nseg);
     k_gemm_simt<64, 64><<<g, 256, 0, st>>>(q);
   }
+  if (prof) prof->mark(PROF_GEMM, st);
   if (launches) ++*launches;
   B2S_LAUNCH_CHECK();
   return 0;

@@ -42,6 +42,7 @@ struct b2s_lg {
   float* dbg_layers = nullptr;  // [n_layers][2*cap][256]
   int dbg_m[16], dbg_n[16], dbg_nlayers = 0, dbg_simm = 0, dbg_simn = 0;
   long long launches = 0;
+  KernelProf prof;
   LgTensorCore* tc = nullptr;   // bf16 tcgen05 path (precision == B2S_BF16)
 };
 
@@ -208,6 +209,19 @@ extern "C" void b2s_lg_destroy(b2s_lg* h) {
 
 extern "C" long long b2s_lg_launch_count(const b2s_lg* h) { return h ? h->launches : 0; }
 
+extern "C" int b2s_lg_profile(b2s_lg* h, int on) {
+  if (!h) return B2S_EINVAL;
+  h->prof.on = on != 0;
+  for (int c = 0; c < PROF_NCLASS; ++c) h->prof.used[c] = 0;
+  return 0;
+}
+
+extern "C" int b2s_lg_profile_read(b2s_lg* h, int cls, double* ms, long long* n) {
+  if (!h || !ms || !n || cls < 0 || cls >= PROF_NCLASS) return B2S_EINVAL;
+  B2S_CUDA(cudaSetDevice(h->device));
+  return h->prof.read(cls, ms, n);
+}
+
 extern "C" int b2s_lg_set_debug(b2s_lg* h, int on) {
   if (!h) return B2S_EINVAL;
   B2S_CUDA(cudaSetDevice(h->device));
@@ -224,13 +238,15 @@ static int lg_linear(b2s_lg* h, cudaStream_t st, const float* A1, int lda1, int 
   g.W = W; g.ldw = K; g.C = C; g.ldc = ldc; g.N = N; g.K = K;
   g.nseg = 2; g.seg_base[0] = 0; g.seg_base[1] = h->cap; g.seg_rows[0] = m; g.seg_rows[1] = n;
   g.bias = bias; g.alpha = alpha; g.residual = residual; g.ldr = ldr;
-  return gemm_simt(g, st, &h->launches);
+  return gemm_simt(g, st, &h->launches, &h->prof);
 }
 
 static int lg_attention(b2s_lg* h, cudaStream_t st, const AttnParams& ap, int maxq) {
   if (maxq <= 0) return 0;
   dim3 grid(cdiv(maxq, ATT_B), 4, 2);
+  h->prof.mark(PROF_ATTN, st);
   k_attn_fp32<<<grid, 256, ATT_SMEM, st>>>(ap);
+  h->prof.mark(PROF_ATTN, st);
   ++h->launches;
   B2S_LAUNCH_CHECK();
   return 0;
@@ -258,7 +274,7 @@ static int lg_layer_fp32(b2s_lg* h, cudaStream_t st, int li, int cur, int m, int
     g.A1 = x; g.lda1 = 256; g.K1 = 256; g.W = l.wqkv; g.ldw = 256; g.C = h->qkv; g.ldc = 768; g.N = 768; g.K = 256;
     g.nseg = 2; g.seg_base[0] = 0; g.seg_base[1] = cap; g.seg_rows[0] = m; g.seg_rows[1] = n;
     g.bias = l.bqkv; g.rot_cols = 512; g.rot_cos = h->cosb[cur]; g.rot_sin = h->sinb[cur];
-    B2S_TRY(gemm_simt(g, st, &h->launches));
+    B2S_TRY(gemm_simt(g, st, &h->launches, &h->prof));
   }
   AttnParams ap;
   ap.ldq = ap.ldk = ap.ldv = 768; ap.ldo = 256; ap.scale = 0.125f;
@@ -368,7 +384,8 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
     HeadParams hp;
     hp.x = h->x[cur]; hp.seg = {{0, cap}, {mc, nc}};
     hp.wt = l.wtok; hp.bt = l.btok; hp.wm = l.wmatch; hp.bm = l.bmatch;
-    hp.thr = h->thr[i]; hp.keep_thr = (float)(1.0 - (double)h->cfg.width_conf);
+    hp.thr = h->thr[i]; // upstream: scores > (1 - width_confidence) with a python double; undo the float rounding of the cfg
+    hp.keep_thr = (float)(1.0 - std::round((double)h->cfg.width_conf * 1e6) / 1e6);
     hp.use_tok = do_stop; hp.use_match = (can0 || can1);
     hp.tok = h->tok; hp.keep = h->keep; hp.ctrl = h->ctrl; hp.ls_pos = nullptr;
     dim3 hg(cdiv(std::max(mc, nc), 8), 2);

@@ -288,6 +288,15 @@ class LightGlue(_Module):
         out.update(extra)
         return out
 
+    def profile(self, on=True):
+        check(lib.b2s_lg_profile(self._handle, 1 if on else 0), "b2s_lg_profile")
+
+    def profile_read(self, cls: int):
+        """(summed kernel ms, launches) of class 0 = attention, 1 = GEMM since the last read."""
+        ms, n = C.c_double(0), C.c_longlong(0)
+        check(lib.b2s_lg_profile_read(self._handle, cls, C.byref(ms), C.byref(n)), "b2s_lg_profile_read")
+        return ms.value, n.value
+
     def set_debug(self, on=True):
         check(lib.b2s_lg_set_debug(self._handle, 1 if on else 0), "b2s_lg_set_debug")
 

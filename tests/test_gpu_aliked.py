@@ -1,0 +1,105 @@
+"""GPU parity: ALIKED extractor (C-ABI b2s_aliked_extract[_host]) vs the CPU oracle.
+Bar: identical keypoint index sets; dense maps / descriptors within 1e-3 relative (measured ~1e-6);
+NMS bit-exact on identical input."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from b200slam import weights, synth
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(model="aliked-n16", max_kp=2048):
+    from b200slam import frontend
+    sd = weights.synthetic_aliked_state(model)
+    ora = oracle.ALIKED(model_name=model, max_num_keypoints=max_kp).eval()
+    ora.load_state_dict(sd, strict=True)
+    ora.record_taps = True
+    return ora, frontend.ALIKED(model_name=model, max_num_keypoints=max_kp, weights=sd)
+
+
+def _pix_index(det, n, Hr, Wr):
+    kn = det.debug("kp_norm").reshape(-1, 2)[:n]
+    # integer NMS location = round(refined - residual) is not recoverable exactly; use floor(x+0.5) of the
+    # refined position, which stays inside the 5x5 soft-argmax support centre +-0.5 for peaked maxima
+    return kn
+
+
+CASES = {"kitti_2048": (376, 1241, 2048, "aliked-n16"), "vga_upscale_1024": (480, 640, 1024, "aliked-n16"),
+         "small_512": (240, 320, 512, "aliked-n16"), "n32_1080p_4096": (1080, 1920, 4096, "aliked-n32")}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_extract_parity(name):
+    H, W, max_kp, model = CASES[name]
+    ora, det = _pair(model, max_kp)
+    img = synth.frame(3, H, W)
+    fo = ora.extract(oracle.bgr_to_tensor(img))
+    kp, de, sc = det.extract_host(img)                       # C-ABI, host buffers
+    Hr, Wr, Hp, Wp = [int(v) for v in det.debug("geometry")]
+    T = ora.taps
+    assert (Hr, Wr) == tuple(T["score_map"].shape[-2:])
+    # stage taps (tolerance 1e-3 relative to the tensor's max; observed ~1e-6)
+    assert rel_err(det.debug("resized").reshape(3, Hr, Wr), T["resized"][0].numpy()) < 1e-5
+    assert rel_err(det.debug("x1").reshape(16, Hp, Wp), T["x1"][0].numpy()) < 1e-4
+    assert rel_err(det.debug("x2").reshape(32, Hp // 2, Wp // 2), T["x2"][0].numpy()) < 1e-4
+    assert rel_err(det.debug("x3").reshape(Hp // 8, Wp // 8, 64).transpose(2, 0, 1), T["x3"][0].numpy()) < 1e-4
+    assert rel_err(det.debug("x4").reshape(Hp // 32, Wp // 32, 128).transpose(2, 0, 1), T["x4"][0].numpy()) < 1e-4
+    assert rel_err(det.debug("score_map").reshape(Hr, Wr), T["score_map"][0, 0].numpy()) < 1e-4
+    assert rel_err(det.debug("feature_map").reshape(Hr, Wr, 128).transpose(2, 0, 1), T["feature_map"][0].numpy()) < 1e-4
+    # NMS kernel is bit-exact against the oracle NMS of the same (GPU) score map
+    sg = torch.from_numpy(det.debug("score_map").reshape(1, 1, Hr, Wr).copy())
+    nms = oracle.simple_nms(sg, 2)[0, 0].numpy().copy()
+    nms[:2] = 0; nms[-2:] = 0; nms[:, :2] = 0; nms[:, -2:] = 0
+    assert np.array_equal(nms, det.debug("nms").reshape(Hr, Wr))
+    # identical keypoint sets (compare positions; order may swap between near-tied scores)
+    ko = fo["keypoints"][0].numpy()
+    assert len(kp) == len(ko)
+    key = lambda a: np.rint(a * 16).astype(np.int64)   # 1/16 px grid (positions agree to ~1e-4 px)
+    so = {tuple(r): i for i, r in enumerate(key(ko).tolist())}
+    idx = np.array([so.get(tuple(r), -1) for r in key(kp).tolist()])
+    assert (idx >= 0).all(), f"{(idx < 0).sum()} GPU keypoints not in the oracle set"
+    assert len(set(idx.tolist())) == len(ko)
+    assert np.abs(kp - ko[idx]).max() < 1e-2
+    # descriptors / scores of the same keypoints: 1e-3 relative
+    assert rel_err(de, fo["descriptors"][0].numpy()[idx]) < 1e-3
+    assert np.abs(np.linalg.norm(de, axis=1) - 1).max() < 1e-5
+    assert rel_err(sc, fo["keypoint_scores"][0].numpy()[idx]) < 1e-3
+    assert (idx == np.arange(len(idx))).mean() > 0.98          # order: score-descending like upstream
+
+
+def test_float_chw_entry_equals_u8_entry_and_contract():
+    """detector.extract(tensor) (features_utils.py:94) vs the fused u8 BGR entry; dict contract."""
+    ora, det = _pair(max_kp=600)
+    img = synth.frame(5, 200, 300)
+    f_u8 = det.extract_bgr(img)
+    f_f32 = det.extract(oracle.bgr_to_tensor(img))            # CPU tensor in, moved by the shim
+    assert set(f_f32) == {"keypoints", "descriptors", "keypoint_scores", "image_size"}
+    assert f_f32["keypoints"].shape == f_u8["keypoints"].shape and f_f32["keypoints"].shape[0] == 1
+    assert torch.equal(f_f32["keypoints"], f_u8["keypoints"]) and torch.equal(f_f32["descriptors"], f_u8["descriptors"])
+    assert f_f32["image_size"].tolist() == [[300.0, 200.0]]
+    assert det.eval() is det and det.to("cuda") is det and next(det.parameters()).is_cuda
+
+
+def test_untruncated_raster_order():
+    """fewer candidates than n_limit -> upstream keeps raster (nonzero) order."""
+    ora, det = _pair(max_kp=-1)
+    img = synth.frame(7, 120, 160)
+    fo = ora.extract(oracle.bgr_to_tensor(img))
+    kp, de, _ = det.extract_host(img)
+    ko = fo["keypoints"][0].numpy()
+    assert len(kp) == len(ko) and len(kp) < 20000
+    assert np.abs(kp - ko).max() < 1e-2, "raster order must match exactly when nothing is truncated"
+    assert rel_err(de, fo["descriptors"][0].numpy()) < 1e-3
+
+
+def test_degenerate_images_do_not_crash():
+    _, det = _pair(max_kp=256)
+    for img in (np.zeros((64, 48, 3), np.uint8), np.full((100, 333, 3), 255, np.uint8)):
+        kp, de, sc = det.extract_host(img)
+        assert len(kp) <= 256 and np.isfinite(kp).all() and np.isfinite(de).all()
+    with pytest.raises(Exception):
+        det.extract_host(np.zeros((4, 4, 3), np.uint8))     # too small: error code, not a crash
