@@ -1,0 +1,162 @@
+// gemm_tc.cuh - bf16 tcgen05/TMEM GEMM fed by TMA, fp32 accumulation, fused epilogues.
+//   C[M,N] = epi( [A1 | A2][M,K] * W[N,K]^T + bias )      (both operands K-major, 128B swizzle)
+// One 128 x BN output tile per CTA, BK = 64 (one 128-byte swizzle atom per row), 4-stage
+// TMA->smem ring, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected
+// lane issues tcgen05.mma, accumulator in TMEM), warps 2..5 = epilogue (tcgen05.ld: thread ==
+// accumulator row, so row-wise epilogues - rotary pairs, residual - are thread-local).
+// Row space: two segments (image0 / image1 of a pair) at fixed bases of a [2*cap, ld] buffer.
+#pragma once
+#include "tc_common.cuh"
+
+namespace b2s {
+
+enum TcEpi { TC_EPI_BF16 = 0, TC_EPI_ROTARY_BF16 = 1, TC_EPI_F32 = 2, TC_EPI_RESID_F32_BF16 = 3 };
+
+struct TcGemmParams {
+  int K, K1, N;                     // K total, K1 = columns served by map A1 (K1 == K when single source)
+  int seg_base[2], seg_rows[2];     // row segments; tiles_m[z] = ceil(seg_rows[z]/128)
+  int tiles0;                       // number of M tiles in segment 0
+  const float* bias;                // [N]
+  int epi;
+  __nv_bfloat16* out_bf16; int ld_bf16;     // TC_EPI_BF16 / ROTARY / RESID (bf16 copy)
+  float* out_f32; int ld_f32;               // TC_EPI_F32 (plain) / RESID (in-place residual stream)
+  const float* rot_cos; const float* rot_sin; int rot_cols;   // [rows,32] tables
+};
+
+template <int BN>
+struct TcGemmCfg {
+  static constexpr int BM = 128, BK = 64, STAGES = 4;
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int THREADS = 192;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtensorMap mapA1,
+                                                 const __grid_constant__ CUtensorMap mapA2,
+                                                 const __grid_constant__ CUtensorMap mapW, TcGemmParams p) {
+  using Cfg = TcGemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + Cfg::STAGES;  // [STAGES]
+  uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.y, n0 = blockIdx.x * BN;
+  const int seg = tile_m >= p.tiles0 ? 1 : 0;
+  const int row0 = p.seg_base[seg] + (tile_m - (seg ? p.tiles0 : 0)) * Cfg::BM;       // global row of the tile
+  const int rows_live = p.seg_rows[seg] - (tile_m - (seg ? p.tiles0 : 0)) * Cfg::BM;  // live rows in this tile
+  const int nkb = p.K / Cfg::BK;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&mapA1); tc::tma_prefetch_desc(&mapA2); tc::tma_prefetch_desc(&mapW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+    tc::mbar_init(tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (tc::elect_one()) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % Cfg::STAGES, ph = (kb / Cfg::STAGES) & 1;
+        tc::mbar_wait(&empty[s], ph ^ 1);
+        tc::mbar_expect_tx(&full[s], Cfg::A_BYTES + Cfg::B_BYTES);
+        const int k0 = kb * Cfg::BK;
+        if (k0 < p.K1) tc::tma_load_2d(sA + s * Cfg::A_BYTES, &mapA1, &full[s], k0, row0);
+        else tc::tma_load_2d(sA + s * Cfg::A_BYTES, &mapA2, &full[s], k0 - p.K1, row0);
+        tc::tma_load_2d(sB + s * Cfg::B_BYTES, &mapW, &full[s], k0, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::idesc_bf16(128, BN, 0, 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % Cfg::STAGES, ph = (kb / Cfg::STAGES) & 1;
+        tc::mbar_wait(&full[s], ph);
+        tc::tc_fence_after();
+        const uint32_t a0 = tc::smem_u32(sA + s * Cfg::A_BYTES), b0 = tc::smem_u32(sB + s * Cfg::B_BYTES);
+#pragma unroll
+        for (int k = 0; k < Cfg::BK / 16; ++k) {
+          const uint64_t ad = tc::smem_desc_sw128(a0 + k * 32, 16, 1024);
+          const uint64_t bd = tc::smem_desc_sw128(b0 + k * 32, 16, 1024);
+          tc::umma_bf16(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+        }
+        tc::umma_commit(&empty[s]);                 // frees the smem stage when these MMAs retire
+        if (kb == nkb - 1) tc::umma_commit(tmem_full);
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;                 // accumulator row handled by this thread
+    tc::mbar_wait(tmem_full, 0);
+    tc::tc_fence_after();
+    const bool live = r < rows_live;
+    const size_t grow = (size_t)(row0 + r);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + c0, v);
+      tc::tmem_ld_wait();
+      const int gc = n0 + c0;
+      if (!live || gc >= p.N) continue;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + gc + j) : 0.f);
+      if (p.epi == TC_EPI_ROTARY_BF16 && gc < p.rot_cols) {
+        const int f0 = (gc & 63) >> 1;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float cs = p.rot_cos[grow * 32 + f0 + (j >> 1)], sn = p.rot_sin[grow * 32 + f0 + (j >> 1)];
+          const float a = f[j], b = f[j + 1];
+          f[j] = a * cs - b * sn; f[j + 1] = b * cs + a * sn;
+        }
+      }
+      if (p.epi == TC_EPI_F32) {
+        float4* d = reinterpret_cast<float4*>(p.out_f32 + grow * p.ld_f32 + gc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        continue;
+      }
+      if (p.epi == TC_EPI_RESID_F32_BF16) {
+        float4* d = reinterpret_cast<float4*>(p.out_f32 + grow * p.ld_f32 + gc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 x = d[j];
+          x.x += f[4 * j]; x.y += f[4 * j + 1]; x.z += f[4 * j + 2]; x.w += f[4 * j + 3];
+          d[j] = x;
+          f[4 * j] = x.x; f[4 * j + 1] = x.y; f[4 * j + 2] = x.z; f[4 * j + 3] = x.w;
+        }
+      }
+      uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + grow * p.ld_bf16 + gc);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]), h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]), h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+        o[j] = u;
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_base, BN);
+}
+
+}  // namespace b2s
