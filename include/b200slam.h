@@ -151,6 +151,12 @@ int b2s_lg_debug_get(b2s_lg* h, const char* name, float* out, size_t cap, size_t
 int b2s_lg_profile(b2s_lg* h, int on);
 int b2s_lg_profile_read(b2s_lg* h, int cls, double* ms, long long* n_launches);
 
+/* Unit-test entry points for the tcgen05 kernels (host buffers, operands rounded to bf16):
+ *   b2s_test_gemm_tc : C[M,N] = A[M,K] W[N,K]^T + bias  (fp32 out; N, K multiples of 64)
+ *   b2s_test_attn_tc : ctx[nq,256] = softmax(q k^T / 8) v per head (4 heads x 64) */
+int b2s_test_gemm_tc(const float* A, const float* W, const float* bias, int M, int N, int K, float* C);
+int b2s_test_attn_tc(const float* q, const float* k, const float* v, int nq, int nk, float* ctx);
+
 /* Number of CUDA kernels this library launched on behalf of the handle so far. */
 long long b2s_aliked_launch_count(const b2s_aliked* h);
 long long b2s_lg_launch_count(const b2s_lg* h);

@@ -1,0 +1,212 @@
+// attn_tc.cuh - flash-style attention on tcgen05/TMEM (bf16 operands, fp32 accumulate/softmax).
+//   O = softmax(Q K^T * scale) V,  head_dim 64, 128-query tile per CTA, 128-key tiles.
+// Warp roles (192 threads): warp 0 = TMA producer (Q once, K/V double-buffered), warp 1 = MMA
+// issuer (S_j = Q K_j^T into TMEM S[j&1]; PV_j = P_j V_j into TMEM O[j&1]), warps 2..5 =
+// softmax (thread == query row: tcgen05.ld S, online max/sum in registers, P -> smem bf16 in
+// the 128B-swizzled K-major layout the MMA reads, running output kept in registers and
+// rescaled when PV_j is read back).  Issue order S0,S1,PV0,S2,PV1,... overlaps the tensor
+// pipe with the MUFU-bound softmax.
+// grid = (ceil(max nq/128), heads, nprob).  TMEM: S 2x128 + O 2x64 columns (512 allocated).
+#pragma once
+#include "tc_common.cuh"
+
+namespace b2s {
+
+struct AttnTcProb { int q_row, k_row, nq, nk; };   // row bases inside the [2*cap, ld] bf16 buffer
+struct AttnTcParams {
+  AttnTcProb prob[2];
+  int qcol, kcol, vcol;            // column offsets of Q / K / V (head h adds h*64)
+  float scale_log2e;               // softmax scale * log2(e)
+  __nv_bfloat16* out; int ldo;     // ctx [2*cap, 256] bf16, rows aligned with q_row
+};
+
+constexpr int ATC_BQ = 128, ATC_BK = 128, ATC_D = 64;
+constexpr int ATC_TILE = 128 * 64 * 2;               // 16 KB: one [128 x 64] bf16 tile
+constexpr int ATC_SMEM = ATC_TILE /*Q*/ + 2 * ATC_TILE /*K*/ + 2 * ATC_TILE /*V*/ + 2 * 2 * ATC_TILE /*P*/ + 1024 + 256;
+
+__global__ void __launch_bounds__(192, 1) k_attn_tc(const __grid_constant__ CUtensorMap mapQKV, AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATC_TILE;            // [2]
+  uint8_t* sV = sK + 2 * ATC_TILE;        // [2]
+  uint8_t* sP = sV + 2 * ATC_TILE;        // [2][2 blocks of 64 keys]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATC_TILE);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;   uint64_t* k_empty = bars + 3;
+  uint64_t* v_full = bars + 5;   uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 9;   uint64_t* p_full = bars + 11;  uint64_t* o_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const AttnTcProb pr = p.prob[blockIdx.z];
+  const int q0 = blockIdx.x * ATC_BQ;
+  if (q0 >= pr.nq) return;                               // uniform per CTA
+  const int h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = (pr.nk + ATC_BK - 1) / ATC_BK;
+
+  if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&mapQKV);
+  if (warp == 1 && lane == 0) {
+    tc::mbar_init(q_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&k_full[b], 1); tc::mbar_init(&k_empty[b], 1);
+      tc::mbar_init(&v_full[b], 1); tc::mbar_init(&v_empty[b], 1);
+      tc::mbar_init(&s_full[b], 1); tc::mbar_init(&p_full[b], 128); tc::mbar_init(&o_full[b], 1);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 256;    // S[b] = tS + 128 b ; O[b] = tO + 64 b
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      tc::mbar_expect_tx(q_full, ATC_TILE);
+      tc::tma_load_2d(sQ, &mapQKV, q_full, p.qcol + h * 64, pr.q_row + q0);
+      for (int j = 0; j < nt; ++j) {
+        const int b = j & 1, ph = (j >> 1) & 1;
+        tc::mbar_wait(&k_empty[b], ph ^ 1);
+        tc::mbar_expect_tx(&k_full[b], ATC_TILE);
+        tc::tma_load_2d(sK + b * ATC_TILE, &mapQKV, &k_full[b], p.kcol + h * 64, pr.k_row + j * ATC_BK);
+        tc::mbar_wait(&v_empty[b], ph ^ 1);
+        tc::mbar_expect_tx(&v_full[b], ATC_TILE);
+        tc::tma_load_2d(sV + b * ATC_TILE, &mapQKV, &v_full[b], p.vcol + h * 64, pr.k_row + j * ATC_BK);
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc_s = tc::idesc_bf16(128, 128, 0, 0);   // S: A = Q (K-major), B = K tile (K-major)
+      constexpr uint32_t idesc_o = tc::idesc_bf16(128, 64, 0, 1);    // PV: A = P (K-major), B = V (MN-major)
+      const uint32_t q_addr = tc::smem_u32(sQ);
+      auto issue_pv = [&](int i) {
+        const int b = i & 1, ph = (i >> 1) & 1;
+        tc::mbar_wait(&p_full[b], ph);
+        tc::mbar_wait(&v_full[b], ph);
+        tc::tc_fence_after();
+        const uint32_t p_addr = tc::smem_u32(sP + b * 2 * ATC_TILE), v_addr = tc::smem_u32(sV + b * ATC_TILE);
+#pragma unroll
+        for (int kk = 0; kk < ATC_BK / 16; ++kk) {
+          // P: two [128 x 64] K-major blocks; V: [128 keys x 64 d], MN-major, 16 keys = 2 swizzle atoms = 2048 B
+          const uint64_t ad = tc::smem_desc_sw128(p_addr + (kk >> 2) * ATC_TILE + (kk & 3) * 32, 16, 1024);
+          const uint64_t bd = tc::smem_desc_sw128(v_addr + kk * 2048, 16, 1024);
+          tc::umma_bf16(tO + b * 64, ad, bd, idesc_o, kk ? 1u : 0u);
+        }
+        tc::umma_commit(&o_full[b]);
+        tc::umma_commit(&v_empty[b]);
+      };
+      tc::mbar_wait(q_full, 0);
+      for (int j = 0; j < nt; ++j) {
+        const int b = j & 1, ph = (j >> 1) & 1;
+        tc::mbar_wait(&k_full[b], ph);
+        tc::tc_fence_after();
+        const uint32_t k_addr = tc::smem_u32(sK + b * ATC_TILE);
+#pragma unroll
+        for (int k = 0; k < ATC_D / 16; ++k) {
+          const uint64_t ad = tc::smem_desc_sw128(q_addr + k * 32, 16, 1024);
+          const uint64_t bd = tc::smem_desc_sw128(k_addr + k * 32, 16, 1024);
+          tc::umma_bf16(tS + b * 128, ad, bd, idesc_s, k ? 1u : 0u);
+        }
+        tc::umma_commit(&s_full[b]);
+        tc::umma_commit(&k_empty[b]);
+        if (j >= 1) issue_pv(j - 1);
+      }
+      issue_pv(nt - 1);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;                       // query row of this thread
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    float o[ATC_D];
+#pragma unroll
+    for (int d = 0; d < ATC_D; ++d) o[d] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, corr_prev = 0.f;
+    auto consume = [&](int i, float corr) {
+      const int b = i & 1, ph = (i >> 1) & 1;
+      tc::mbar_wait(&o_full[b], ph);
+      tc::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tc::tmem_ld32(tO + b * 64 + lane_addr + c * 32, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) o[c * 32 + t] = fmaf(o[c * 32 + t], corr, __uint_as_float(v[t]));
+      }
+    };
+    for (int j = 0; j < nt; ++j) {
+      const int b = j & 1, ph = (j >> 1) & 1;
+      tc::mbar_wait(&s_full[b], ph);
+      tc::tc_fence_after();
+      const int kbase = j * ATC_BK;
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tc::tmem_ld32(tS + b * 128 + lane_addr + c * 32, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const float s = (kbase + c * 32 + t < pr.nk) ? __uint_as_float(v[t]) * p.scale_log2e : -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float corr = exp2f(m_run - m_new);
+      // pass 2: P = exp2(s - m_new) -> bf16 -> swizzled smem; row sum (of the bf16-rounded values the MMA sees)
+      float sum = 0.f;
+      uint8_t* prow = sP + b * 2 * ATC_TILE + r * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tc::tmem_ld32(tS + b * 128 + lane_addr + c * 32, v);
+        tc::tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int t = 0; t < 32; t += 2) {
+          const float s0 = (kbase + c * 32 + t < pr.nk) ? __uint_as_float(v[t]) * p.scale_log2e : -INFINITY;
+          const float s1 = (kbase + c * 32 + t + 1 < pr.nk) ? __uint_as_float(v[t + 1]) * p.scale_log2e : -INFINITY;
+          const __nv_bfloat162 hb = __floats2bfloat162_rn(exp2f(s0 - m_new), exp2f(s1 - m_new));
+          sum += __low2float(hb) + __high2float(hb);
+          pk[t >> 1] = *reinterpret_cast<const uint32_t*>(&hb);
+        }
+        // 32 keys = 64 B = four 16-byte chunks of block (c >> 1), chunk index ((c & 1) * 4 + q) ^ (r & 7)
+        uint8_t* blk = prow + (c >> 1) * ATC_TILE;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (((c & 1) * 4 + q) ^ (r & 7));
+          *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+      }
+      l_run = l_run * corr + sum;
+      m_run = m_new;
+      tc::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc::tc_fence_before();            // order our tcgen05.ld of S before the MMA that overwrites it
+      tc::mbar_arrive(&p_full[b]);
+      if (j >= 1) consume(j - 1, corr_prev);
+      corr_prev = corr;
+    }
+    consume(nt - 1, corr_prev);
+    if (q0 + r < pr.nq) {
+      const float inv = 1.f / l_run;
+      uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)(pr.q_row + q0 + r) * p.ldo + h * 64);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(o[8 * q] * inv, o[8 * q + 1] * inv), bb = __floats2bfloat162_rn(o[8 * q + 2] * inv, o[8 * q + 3] * inv);
+        __nv_bfloat162 c = __floats2bfloat162_rn(o[8 * q + 4] * inv, o[8 * q + 5] * inv), d = __floats2bfloat162_rn(o[8 * q + 6] * inv, o[8 * q + 7] * inv);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&bb);
+        u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+        dst[q] = u;
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace b2s

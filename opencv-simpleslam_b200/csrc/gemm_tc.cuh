@@ -25,7 +25,7 @@ struct TcGemmParams {
 
 template <int BN>
 struct TcGemmCfg {
-  static constexpr int BM = 128, BK = 64, STAGES = 4;
+  static constexpr int BM = 128, BK = 64, STAGES = 3;
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
   static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int THREADS = 192;

@@ -54,7 +54,7 @@ static int upload_t(b2s_lg* h, const WeightBlob& wb, const std::string& name, si
 }
 
 static int lg_alloc_ws(b2s_lg* h, int cap) {
-  cap = (cap + 63) / 64 * 64;
+  cap = (cap + 127) / 128 * 128;
   h->wsarena.release();
   h->cap = 0;
   const size_t R = (size_t)2 * cap;

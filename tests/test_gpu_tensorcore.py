@@ -1,0 +1,62 @@
+"""GPU: unit tests of the tcgen05/TMEM kernels (bf16 operands, fp32 accumulation) and the bf16
+LightGlue path.  Tolerances: GEMM/attention vs a torch fp32 reference on the SAME bf16-rounded
+operands: 2e-3 relative to the output scale; bf16 matcher vs fp32 oracle: match-set agreement
+>= 99% (BASELINE.json north_star)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from b200slam import weights
+from helpers import noisy_copy_pair, match_set
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 128, 256), (200, 256, 256), (4096, 768, 256), (1000, 512, 512), (333, 256, 512)])
+def test_gemm_tc(M, N, K):
+    from b200slam import _lib
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g); W = torch.randn(N, K, generator=g) / K ** 0.5; b = torch.randn(N, generator=g)
+    out = np.empty((M, N), np.float32)
+    _lib.check(_lib.lib.b2s_test_gemm_tc(A.numpy().ctypes.data, W.numpy().ctypes.data, b.numpy().ctypes.data, M, N, K, out.ctypes.data), "gemm_tc")
+    ref = (_bf16(A) @ _bf16(W).T + b).numpy()
+    err = np.abs(out - ref).max() / np.abs(ref).max()
+    assert err < 2e-3, f"rel err {err}"
+
+
+@pytest.mark.parametrize("nq,nk", [(128, 128), (128, 256), (300, 200), (2048, 2048), (1, 77), (129, 1)])
+def test_attn_tc(nq, nk):
+    from b200slam import _lib
+    g = torch.Generator().manual_seed(nq * 7 + nk)
+    q = torch.randn(nq, 256, generator=g); k = torch.randn(nk, 256, generator=g); v = torch.randn(nk, 256, generator=g)
+    out = np.empty((nq, 256), np.float32)
+    _lib.check(_lib.lib.b2s_test_attn_tc(q.numpy().ctypes.data, k.numpy().ctypes.data, v.numpy().ctypes.data, nq, nk, out.ctypes.data), "attn_tc")
+    sp = lambda t: _bf16(t).view(-1, 4, 64).transpose(0, 1)   # noqa: E731
+    ref = torch.nn.functional.scaled_dot_product_attention(sp(q)[None], sp(k)[None], sp(v)[None])[0].transpose(0, 1).reshape(nq, 256).numpy()
+    err = np.abs(out - ref).max() / np.abs(ref).max()
+    assert err < 2e-2, f"rel err {err}"      # P and the output are rounded to bf16 (2^-8)
+
+
+@pytest.mark.parametrize("m,n", [(2048, 2048), (700, 512)])
+def test_bf16_matcher_agreement_with_fp32_oracle(m, n):
+    from b200slam import frontend
+    sd = weights.synthetic_lightglue_state(seed=0)
+    ora = oracle.LightGlue().eval(); ora.load_state_dict(sd, strict=False); ora.record_taps = True
+    mat = frontend.LightGlue(weights=sd, precision="bf16", max_kp=max(m, n))
+    mat.set_debug(True)
+    k0, d0, k1, d1, _ = noisy_copy_pair(m, n, seed=5)
+    ro = ora({"image0": {"keypoints": k0[None], "descriptors": d0[None]}, "image1": {"keypoints": k1[None], "descriptors": d1[None]}})
+    rg = mat.match_host(k0.numpy(), d0.numpy(), k1.numpy(), d1.numpy())
+    for i, (a, b) in enumerate(ora.taps["layers"]):
+        e = np.abs(mat.debug(f"layer{i}_0").reshape(-1, 256) - a[0].numpy()).max() / np.abs(a[0].numpy()).max()
+        assert e < 5e-2, f"layer {i}: rel err {e}"
+    so, sg = match_set(ro["matches"][0]), match_set(rg["matches"])
+    agree = len(so & sg) / max(len(so | sg), 1)
+    assert len(so) > 300 and agree >= 0.99, f"match-set agreement {agree:.4f} ({len(so)} vs {len(sg)})"
