@@ -350,7 +350,7 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
     B2S_CUDA(cudaMemcpyAsync(h->thr, &h->cfg.det_thresh, sizeof(float), cudaMemcpyHostToDevice, st));
     k_dkd_nms<<<dim3(cdiv(Wr, NMS_T), cdiv(Hr, NMS_T)), 256, 0, st>>>(h->score, Hr, Wr, h->nms, h->thr, h->dk, h->cand_idx, h->cand_sc, h->cand_cap);
     k_dkd_fallback<<<1, 1024, 0, st>>>(h->score, h->nms, Hr * Wr, h->thr, h->dk, h->cand_idx, h->cand_sc, h->cand_cap);
-    k_dkd_select<<<1, 1024, 0, st>>>(h->cand_sc, h->cand_cap, h->n_limit, h->dk);
+    k_dkd_select<<<1, 1024, 0, st>>>(h->cand_sc, h->cand_idx, h->cand_cap, h->n_limit, h->dk);
     k_dkd_compact<<<cdiv(h->cand_cap, 256), 256, 0, st>>>(h->cand_idx, h->cand_sc, h->dk, h->sel_idx, h->sel_sc);
     RefineParams rp;
     rp.dk = h->dk; rp.sel_idx = h->sel_idx; rp.sel_sc = h->sel_sc; rp.score = h->score; rp.H = Hr; rp.W = Wr;

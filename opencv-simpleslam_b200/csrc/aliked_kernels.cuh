@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(256) k_aliked_score(ScoreParams p) {
 // max (torch max_pool2d pads with -inf).  Appends (index, score) of every survivor
 // > *thr to the candidate list (arbitrary order; ranking is fixed later).
 // dk layout (ints): [0]=n_candidates [1]=T(key) [2]=n_ties_to_take [3]=truncated [4]=n_selected
-//                   [5]=fallback flag ; thr is a float in device memory.
+//                   [5]=fallback flag [6]=largest raster index taken among ties at T ; thr is a float in device memory.
 // ---------------------------------------------------------------------------------------
 constexpr int NMS_T = 32, NMS_H = 10, NMS_S = NMS_T + 2 * NMS_H;  // 52
 
@@ -568,14 +568,15 @@ __global__ void __launch_bounds__(1024) k_dkd_fallback(const float* __restrict__
 }
 
 // K6b: radix select of the n_limit-th largest score key (single CTA).
-__global__ void __launch_bounds__(1024) k_dkd_select(const float* __restrict__ cand_sc, int cand_cap, int n_limit, int* dk) {
+__global__ void __launch_bounds__(1024) k_dkd_select(const float* __restrict__ cand_sc, const int* __restrict__ cand_idx, int cand_cap,
+                                                      int n_limit, int* dk) {
   __shared__ int hist[256];
   __shared__ unsigned prefix_s;
   __shared__ int krem_s;
   const int C = min(dk[0], cand_cap);
   if (threadIdx.x == 0) { dk[0] = C; dk[4] = 0; }
   if (C <= n_limit) {
-    if (threadIdx.x == 0) { dk[1] = 0; dk[2] = 0; dk[3] = 0; }
+    if (threadIdx.x == 0) { dk[1] = 0; dk[2] = 0; dk[3] = 0; dk[6] = 0x7fffffff; }
     return;
   }
   if (threadIdx.x == 0) { prefix_s = 0u; krem_s = n_limit; }
@@ -601,7 +602,49 @@ __global__ void __launch_bounds__(1024) k_dkd_select(const float* __restrict__ c
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { dk[1] = (int)prefix_s; dk[2] = krem_s; dk[3] = 1; }
+  // ties at the cut: take the krem_s smallest raster indices among key == T.  Usually exactly
+  // krem_s candidates tie (then everything with key == T is taken); otherwise select the
+  // krem_s-th smallest index with a second radix select restricted to the tied candidates.
+  const unsigned T = prefix_s;
+  const int need = krem_s;
+  __syncthreads();
+  if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int i = threadIdx.x; i < C; i += 1024) mine += (__float_as_uint(cand_sc[i]) == T) ? 1 : 0;
+  if (mine) atomicAdd(&hist[0], mine);
+  __syncthreads();
+  const int n_ties = hist[0];
+  __syncthreads();
+  if (n_ties == need) {
+    if (threadIdx.x == 0) { dk[1] = (int)T; dk[2] = need; dk[3] = 1; dk[6] = 0x7fffffff; }
+    return;
+  }
+  if (threadIdx.x == 0) { prefix_s = 0u; krem_s = need; }
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned prefix = prefix_s;
+    const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = threadIdx.x; i < C; i += 1024) {
+      if (__float_as_uint(cand_sc[i]) != T) continue;
+      const unsigned key = (unsigned)cand_idx[i];
+      if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int k = krem_s, d = 0, below = 0;
+      for (; d < 256; ++d) {
+        if (below + hist[d] >= k) break;
+        below += hist[d];
+      }
+      krem_s = k - below;
+      prefix_s = prefix | ((unsigned)d << shift);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { dk[1] = (int)T; dk[2] = need; dk[3] = 1; dk[6] = (int)prefix_s; }
 }
 
 // K6c: gather the selected candidates (key > T, plus the first dk[2] ties by raster index).
@@ -615,13 +658,7 @@ __global__ void __launch_bounds__(256) k_dkd_compact(const int* __restrict__ can
   bool take = false;
   if (!dk[3]) take = true;
   else if (key > T) take = true;
-  else if (key == T) {
-    const int me = cand_idx[i];
-    int rank = 0;
-    for (int j = 0; j < C; ++j)
-      if (__float_as_uint(cand_sc[j]) == T && cand_idx[j] < me) ++rank;
-    take = rank < dk[2];
-  }
+  else if (key == T) take = cand_idx[i] <= dk[6];   // tie cut found by k_dkd_select
   if (take) {
     const int slot = atomicAdd(&dk[4], 1);
     sel_idx[slot] = cand_idx[i]; sel_sc[slot] = cand_sc[i];
