@@ -337,7 +337,7 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
     }
     ap.W1 = h->agg_w[0]; ap.Ws0 = h->sh0; ap.s8 = h->s8; ap.feat = h->feat;
     ap.Hr = Hr; ap.Wr = Wr; ap.pad_t = pp.pad_t; ap.pad_l = pp.pad_l;
-    k_aliked_agg<<<dim3(cdiv(Wp, 32), Hp), 256, 0, st>>>(ap);
+    k_aliked_agg<<<dim3(cdiv(Wp, 128), Hp), 128, 0, st>>>(ap);
     ScoreParams sp;
     sp.s8 = h->s8; sp.Hp = Hp; sp.Wp = Wp; sp.w2 = h->sh2; sp.w4 = h->sh4; sp.w6 = h->sh6;
     sp.score = h->score; sp.Hr = Hr; sp.Wr = Wr; sp.pad_t = pp.pad_t; sp.pad_l = pp.pad_l;

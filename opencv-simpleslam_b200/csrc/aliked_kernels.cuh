@@ -322,61 +322,76 @@ struct AggParams {
   int Hr, Wr, pad_t, pad_l;
 };
 
-__global__ void __launch_bounds__(256) k_aliked_agg(AggParams p) {
-  __shared__ float xs[16][32];
-  const int y = blockIdx.y, xb = blockIdx.x * 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int e = tid; e < 16 * 32; e += 256) {
-    const int c = e >> 5, q = e & 31;
-    xs[c][q] = (xb + q < p.Wp) ? p.x1[((size_t)c * p.Hp + y) * p.Wp + xb + q] : 0.f;
-  }
-  float w1[16], ws0[8][4];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) w1[k] = p.W1[lane * 16 + k];
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-#pragma unroll
-    for (int g = 0; g < 4; ++g) ws0[j][g] = p.Ws0[j * 128 + g * 32 + lane];
+__global__ void __launch_bounds__(128) k_aliked_agg(AggParams p) {
+  // one thread per padded pixel (128 consecutive pixels of a row per CTA): the whole 128-channel
+  // vector lives in registers, so the norm and the 128->8 score projection need no shuffles.
+  __shared__ __align__(16) float sW1[32 * 16];
+  __shared__ __align__(16) float sWs[8 * 128];
+  for (int e = threadIdx.x; e < 32 * 16; e += 128) sW1[e] = p.W1[e];
+  for (int e = threadIdx.x; e < 8 * 128; e += 128) sWs[e] = p.Ws0[e];
   __syncthreads();
-  float ly1[3], ly0[3]; int yy0[3], yy1[3];
+  const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
+  if (x >= p.Wp) return;
+  float f[128];
+  {
+    float xin[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) xin[k] = p.x1[((size_t)k * p.Hp + y) * p.Wp + x];
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+      const float4* w = reinterpret_cast<const float4*>(sW1 + o * 16);
+      float a = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 wv = w[q];
+        a = fmaf(wv.x, xin[4 * q], a); a = fmaf(wv.y, xin[4 * q + 1], a);
+        a = fmaf(wv.z, xin[4 * q + 2], a); a = fmaf(wv.w, xin[4 * q + 3], a);
+      }
+      f[o] = selu_f(a);
+    }
+  }
 #pragma unroll
   for (int l = 0; l < 3; ++l) {
-    const float fy = p.sh[l] * (float)y;
-    yy0[l] = (int)fy; yy1[l] = yy0[l] + (yy0[l] < p.Hk[l] - 1 ? 1 : 0);
-    ly1[l] = fy - (float)yy0[l]; ly0[l] = 1.f - ly1[l];
-  }
-  for (int q = warp * 4; q < warp * 4 + 4; ++q) {
-    const int x = xb + q;
-    if (x >= p.Wp) break;
-    float f[4];
-    float a = 0.f;
+    const float fy = p.sh[l] * (float)y, fx = p.sw[l] * (float)x;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < p.Hk[l] - 1 ? 1 : 0), x1 = x0 + (x0 < p.Wk[l] - 1 ? 1 : 0);
+    const float ly1 = fy - (float)y0, ly0 = 1.f - ly1, lx1 = fx - (float)x0, lx0 = 1.f - lx1;
+    const float4* r00 = reinterpret_cast<const float4*>(p.xa[l] + ((size_t)y0 * p.Wk[l] + x0) * 32);
+    const float4* r01 = reinterpret_cast<const float4*>(p.xa[l] + ((size_t)y0 * p.Wk[l] + x1) * 32);
+    const float4* r10 = reinterpret_cast<const float4*>(p.xa[l] + ((size_t)y1 * p.Wk[l] + x0) * 32);
+    const float4* r11 = reinterpret_cast<const float4*>(p.xa[l] + ((size_t)y1 * p.Wk[l] + x1) * 32);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) a = fmaf(w1[k], xs[k][q], a);
-    f[0] = selu_f(a);
-#pragma unroll
-    for (int l = 0; l < 3; ++l) {
-      const float fx = p.sw[l] * (float)x;
-      const int x0 = (int)fx, x1 = x0 + (x0 < p.Wk[l] - 1 ? 1 : 0);
-      const float lx1 = fx - (float)x0, lx0 = 1.f - lx1;
-      const float* b = p.xa[l];
-      const float p00 = b[((size_t)yy0[l] * p.Wk[l] + x0) * 32 + lane], p01 = b[((size_t)yy0[l] * p.Wk[l] + x1) * 32 + lane];
-      const float p10 = b[((size_t)yy1[l] * p.Wk[l] + x0) * 32 + lane], p11 = b[((size_t)yy1[l] * p.Wk[l] + x1) * 32 + lane];
-      f[l + 1] = ly0[l] * (lx0 * p00 + lx1 * p01) + ly1[l] * (lx0 * p10 + lx1 * p11);
+    for (int q = 0; q < 8; ++q) {
+      const float4 a = __ldg(r00 + q), b = __ldg(r01 + q), c = __ldg(r10 + q), d = __ldg(r11 + q);
+      float* o = f + 32 * (l + 1) + 4 * q;
+      o[0] = ly0 * (lx0 * a.x + lx1 * b.x) + ly1 * (lx0 * c.x + lx1 * d.x);
+      o[1] = ly0 * (lx0 * a.y + lx1 * b.y) + ly1 * (lx0 * c.y + lx1 * d.y);
+      o[2] = ly0 * (lx0 * a.z + lx1 * b.z) + ly1 * (lx0 * c.z + lx1 * d.z);
+      o[3] = ly0 * (lx0 * a.w + lx1 * b.w) + ly1 * (lx0 * c.w + lx1 * d.w);
     }
-    const float ssq = warp_sum(f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3]);
-    float mine = 0.f;
+  }
+  float ssq = 0.f, s8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s8[j] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 128; c += 4) {
+    ssq = fmaf(f[c], f[c], ssq); ssq = fmaf(f[c + 1], f[c + 1], ssq);
+    ssq = fmaf(f[c + 2], f[c + 2], ssq); ssq = fmaf(f[c + 3], f[c + 3], ssq);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float s = warp_sum(ws0[j][0] * f[0] + ws0[j][1] * f[1] + ws0[j][2] * f[2] + ws0[j][3] * f[3]);
-      if (lane == j) mine = s;
+      const float4 wv = *reinterpret_cast<const float4*>(sWs + j * 128 + c);
+      s8[j] = fmaf(wv.x, f[c], s8[j]); s8[j] = fmaf(wv.y, f[c + 1], s8[j]);
+      s8[j] = fmaf(wv.z, f[c + 2], s8[j]); s8[j] = fmaf(wv.w, f[c + 3], s8[j]);
     }
-    if (lane < 8) p.s8[((size_t)lane * p.Hp + y) * p.Wp + x] = selu_f(mine);
-    const int yu = y - p.pad_t, xu = x - p.pad_l;
-    if (yu >= 0 && yu < p.Hr && xu >= 0 && xu < p.Wr) {
-      const float denom = fmaxf(sqrtf(ssq), 1e-12f);
-      float* d = p.feat + ((size_t)yu * p.Wr + xu) * 128 + lane;
-      d[0] = f[0] / denom; d[32] = f[1] / denom; d[64] = f[2] / denom; d[96] = f[3] / denom;
-    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) p.s8[((size_t)j * p.Hp + y) * p.Wp + x] = selu_f(s8[j]);
+  const int yu = y - p.pad_t, xu = x - p.pad_l;
+  if (yu >= 0 && yu < p.Hr && xu >= 0 && xu < p.Wr) {
+    const float denom = fmaxf(sqrtf(ssq), 1e-12f);
+    float4* d = reinterpret_cast<float4*>(p.feat + ((size_t)yu * p.Wr + xu) * 128);
+#pragma unroll
+    for (int q = 0; q < 32; ++q) d[q] = make_float4(f[4 * q] / denom, f[4 * q + 1] / denom, f[4 * q + 2] / denom, f[4 * q + 3] / denom);
   }
 }
 

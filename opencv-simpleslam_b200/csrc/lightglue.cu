@@ -187,6 +187,7 @@ extern "C" int b2s_lightglue_create(const b2s_lg_cfg* cfg, const void* weights, 
   cudaFuncSetAttribute(k_attn_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
   if (cfg->precision == B2S_BF16) {
     if ((rc = lgtc_create(&h->tc, h->L.size()))) return fail(rc);
+    lgtc_set_prof(h->tc, &h->prof);
     for (size_t i = 0; i < h->L.size(); ++i) {
       const LgLayer& l = h->L[i];
       LgTcLayerSrc s = {l.wqkv, l.bqkv, l.wo, l.bo, l.w1, l.b1, l.lng, l.lnb, l.w2, l.b2,
@@ -352,7 +353,7 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
     pp.Wr = h->wr; pp.kn = h->kn; pp.cosb = h->cosb[0]; pp.sinb = h->sinb[0]; pp.ind = h->ind[0];
     pp.prune[0] = do_prune ? (prune0 ? prune0 : h->prune_scratch[0]) : nullptr;
     pp.prune[1] = do_prune ? (prune1 ? prune1 : h->prune_scratch[1]) : nullptr;
-    k_lg_posenc<<<2, 256, 0, st>>>(pp);
+    k_lg_posenc<<<dim3(cdiv(std::max(m, n), 64), 2), 256, 0, st>>>(pp);
     ++h->launches;
     B2S_LAUNCH_CHECK();
   }

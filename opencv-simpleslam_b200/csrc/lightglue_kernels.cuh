@@ -8,7 +8,7 @@
 namespace b2s {
 
 // ---------------------------------------------------------------------------------------
-// K9: normalize_keypoints + posenc.  grid = 2 (one CTA per image), block = 256.
+// K9: normalize_keypoints + posenc.  grid = (ceil(max n / 64), 2 images), block = 256.
 // upstream: size = 1 + max - min (when no image_size); shift = size/2; scale = max(size)/2;
 //           kn = (k - shift)/scale ; proj = Wr kn ; emb = (cos proj, sin proj)
 // ---------------------------------------------------------------------------------------
@@ -23,7 +23,7 @@ struct PosencParams {
 };
 
 __global__ void __launch_bounds__(256) k_lg_posenc(PosencParams p) {
-  const int s = blockIdx.x;
+  const int s = blockIdx.y;   // image; blockIdx.x = chunk of 64 points (every CTA re-derives the extent)
   const int n = p.n[s];
   const float* kp = p.kp[s];
   __shared__ float red[4][8];
@@ -53,18 +53,20 @@ __global__ void __launch_bounds__(256) k_lg_posenc(PosencParams p) {
   }
   __syncthreads();
   const float shx = sh_shift[0], shy = sh_shift[1], sc = sh_scale;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  // warp per point, lane = Fourier frequency: coalesced [row,32] cos/sin writes
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float w0 = p.Wr[2 * lane], w1 = p.Wr[2 * lane + 1];
+  for (int i = blockIdx.x * 64 + warp; i < min(n, blockIdx.x * 64 + 64); i += 8) {
     const int r = p.base[s] + i;
     const float x = (kp[2 * i] - shx) / sc, y = (kp[2 * i + 1] - shy) / sc;
-    p.kn[2 * r] = x; p.kn[2 * r + 1] = y;
-    p.ind[r] = i;
-    if (p.prune[s]) p.prune[s][i] = 1;
-#pragma unroll 4
-    for (int f = 0; f < 32; ++f) {
-      const float pr = p.Wr[2 * f] * x + p.Wr[2 * f + 1] * y;
-      p.cosb[(size_t)r * 32 + f] = cosf(pr);
-      p.sinb[(size_t)r * 32 + f] = sinf(pr);
+    if (lane == 0) {
+      p.kn[2 * r] = x; p.kn[2 * r + 1] = y;
+      p.ind[r] = i;
+      if (p.prune[s]) p.prune[s][i] = 1;
     }
+    const float pr = w0 * x + w1 * y;
+    p.cosb[(size_t)r * 32 + lane] = cosf(pr);
+    p.sinb[(size_t)r * 32 + lane] = sinf(pr);
   }
 }
 

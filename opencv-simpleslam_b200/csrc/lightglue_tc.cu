@@ -106,6 +106,7 @@ struct LgTensorCore {
   float* h1f = nullptr;
   CUtensorMap m_xb, m_ctxb, m_msgb, m_h1b, m_qkv768, m_qkv512;
   const float* last_x = nullptr;   // fp32 buffer xb was derived from (pruning switches buffers)
+  KernelProf* prof = nullptr;
 };
 
 static int make_linear(LgTensorCore* tc, const float* w_dev, const float* bias, int N, int K, TcLinear* out) {
@@ -165,6 +166,7 @@ int lgtc_alloc_ws(LgTensorCore* tc, int cap) {
 }
 
 void lgtc_destroy(LgTensorCore* tc) { delete tc; }
+void lgtc_set_prof(LgTensorCore* tc, KernelProf* prof) { tc->prof = prof; }
 
 static int tc_gemm(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& a1, const CUtensorMap& a2, int K1, const TcLinear& w,
                    TcGemmParams p, int m, int n, long long* launches) {
@@ -174,8 +176,10 @@ static int tc_gemm(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& a1, con
   const int tiles = p.tiles0 + cdiv(n, 128);
   if (tiles <= 0) return 0;
   dim3 grid(w.N / w.BN, tiles);
+  if (tc->prof) tc->prof->mark(PROF_GEMM, st);
   if (w.BN == 64) k_gemm_tc<64><<<grid, 192, TcGemmCfg<64>::SMEM, st>>>(a1, a2, w.map, p);
   else k_gemm_tc<128><<<grid, 192, TcGemmCfg<128>::SMEM, st>>>(a1, a2, w.map, p);
+  if (tc->prof) tc->prof->mark(PROF_GEMM, st);
   if (launches) ++*launches;
   B2S_LAUNCH_CHECK();
   return 0;
@@ -187,7 +191,9 @@ static int tc_attention(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& ma
   ap.scale_log2e = 0.125f * 1.4426950408889634f;
   ap.out = tc->ctxb; ap.ldo = 256;
   dim3 grid(cdiv(maxq, ATC_BQ), 4, 2);
+  if (tc->prof) tc->prof->mark(PROF_ATTN, st);
   k_attn_tc<<<grid, 192, ATC_SMEM, st>>>(map, ap);
+  if (tc->prof) tc->prof->mark(PROF_ATTN, st);
   if (launches) ++*launches;
   B2S_LAUNCH_CHECK();
   return 0;

@@ -17,5 +17,6 @@ int lgtc_alloc_ws(LgTensorCore* tc, int cap);
 int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int layer, float* x, const float* cosb, const float* sinb, int cap,
                int m, int n, long long* launches);
 void lgtc_destroy(LgTensorCore* tc);
+void lgtc_set_prof(LgTensorCore* tc, KernelProf* prof);
 
 }  // namespace b2s
