@@ -1,11 +1,13 @@
 // attn_tc.cuh - flash-style attention on tcgen05/TMEM (bf16 operands, fp32 accumulate/softmax).
 //   O = softmax(Q K^T * scale) V,  head_dim 64, 128-query tile per CTA, 128-key tiles.
-// Warp roles (192 threads): warp 0 = TMA producer (Q once, K/V double-buffered), warp 1 = MMA
-// issuer (S_j = Q K_j^T into TMEM S[j&1]; PV_j = P_j V_j into TMEM O[j&1]), warps 2..5 =
-// softmax (thread == query row: tcgen05.ld S, online max/sum in registers, P -> smem bf16 in
-// the 128B-swizzled K-major layout the MMA reads, running output kept in registers and
-// rescaled when PV_j is read back).  Issue order S0,S1,PV0,S2,PV1,... overlaps the tensor
-// pipe with the MUFU-bound softmax.
+// Warp roles (320 threads): warp 0 = TMA producer (Q once, K/V double-buffered), warp 1 = MMA
+// issuer (S_j = Q K_j^T into TMEM S[j&1]; PV_j = P_j V_j into TMEM O[j&1]), warps 2..5 and
+// 6..9 = two softmax groups: group g owns the key tiles with j & 1 == g (its own S / P / O
+// buffers and its own running max / sum / output in registers), so two tiles are in flight on
+// the CUDA cores (2 warps per scheduler) while the tensor pipe works on the next S / PV; the
+// two partial results are merged once at the end (log-sum-exp merge through shared memory).
+// Softmax thread == query row: tcgen05.ld S, P -> bf16 -> 128B-swizzled K-major smem tile that
+// the PV MMA reads; V is consumed MN-major straight from its row-major [key][d] tile.
 // grid = (ceil(max nq/128), heads, nprob).  TMEM: S 2x128 + O 2x64 columns (512 allocated).
 #pragma once
 #include "tc_common.cuh"
@@ -23,14 +25,70 @@ struct AttnTcParams {
 constexpr int ATC_BQ = 128, ATC_BK = 128, ATC_D = 64;
 constexpr int ATC_TILE = 128 * 64 * 2;               // 16 KB: one [128 x 64] bf16 tile
 constexpr int ATC_SMEM = ATC_TILE /*Q*/ + 2 * ATC_TILE /*K*/ + 2 * ATC_TILE /*V*/ + 2 * 2 * ATC_TILE /*P*/ + 1024 + 256;
+constexpr int ATC_THREADS = 320;
 
-__global__ void __launch_bounds__(192, 1) k_attn_tc(const __grid_constant__ CUtensorMap mapQKV, AttnTcParams p) {
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// one key tile of the online softmax for one query row. MASK: tile is partial (keys >= limit masked)
+template <bool MASK>
+__device__ __forceinline__ void atc_softmax_tile(uint32_t s_addr, uint8_t* prow, int r, int limit, float scale,
+                                                 float& m_run, float& l_run, float& corr_out) {
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tc::tmem_ld32(s_addr + c * 32, v);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      const float s = __uint_as_float(v[t]);
+      if (!MASK || c * 32 + t < limit) mx = fmaxf(mx, s);
+    }
+  }
+  const float m_new = fmaxf(m_run, mx * scale);
+  corr_out = ex2_approx(m_run - m_new);
+  float sum = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tc::tmem_ld32(s_addr + c * 32, v);
+    tc::tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int t = 0; t < 32; t += 2) {
+      float p0 = ex2_approx(fmaf(__uint_as_float(v[t]), scale, -m_new));
+      float p1 = ex2_approx(fmaf(__uint_as_float(v[t + 1]), scale, -m_new));
+      if (MASK) {
+        if (c * 32 + t >= limit) p0 = 0.f;
+        if (c * 32 + t + 1 >= limit) p1 = 0.f;
+      }
+      const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+      sum += __low2float(hb) + __high2float(hb);     // sum what the MMA will actually see
+      pk[t >> 1] = *reinterpret_cast<const uint32_t*>(&hb);
+    }
+    // 32 keys = 64 B = four 16-byte chunks of block (c >> 1); chunk ((c & 1) * 4 + q) ^ (r & 7)
+    uint8_t* blk = prow + (c >> 1) * ATC_TILE;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int chunk = (((c & 1) * 4 + q) ^ (r & 7));
+      *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
+  }
+  l_run = l_run * corr_out + sum;
+  m_run = m_new;
+}
+
+__global__ void __launch_bounds__(ATC_THREADS, 1) k_attn_tc(const __grid_constant__ CUtensorMap mapQKV, AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + ATC_TILE;            // [2]
   uint8_t* sV = sK + 2 * ATC_TILE;        // [2]
-  uint8_t* sP = sV + 2 * ATC_TILE;        // [2][2 blocks of 64 keys]
+  uint8_t* sP = sV + 2 * ATC_TILE;        // [2][2 blocks of 64 keys]; reused for the final merge
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATC_TILE);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;   uint64_t* k_empty = bars + 3;
@@ -116,87 +174,62 @@ __global__ void __launch_bounds__(192, 1) k_attn_tc(const __grid_constant__ CUte
       issue_pv(nt - 1);
     }
   } else {
+    // ===== softmax groups: g = 0 (warps 2..5) takes even key tiles, g = 1 (warps 6..9) odd ones =====
+    const int g = (warp - 2) >> 2;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;                       // query row of this thread
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     float o[ATC_D];
 #pragma unroll
     for (int d = 0; d < ATC_D; ++d) o[d] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, corr_prev = 0.f;
-    auto consume = [&](int i, float corr) {
-      const int b = i & 1, ph = (i >> 1) & 1;
-      tc::mbar_wait(&o_full[b], ph);
+    float m_run = -INFINITY, l_run = 0.f;
+    uint8_t* prow = sP + g * 2 * ATC_TILE + r * 128;
+    for (int j = g; j < nt; j += 2) {
+      const int ph = (j >> 1) & 1;
+      tc::mbar_wait(&s_full[g], ph);
+      tc::tc_fence_after();
+      const int limit = pr.nk - j * ATC_BK;
+      float corr;
+      if (limit >= ATC_BK) atc_softmax_tile<false>(tS + g * 128 + lane_addr, prow, r, limit, p.scale_log2e, m_run, l_run, corr);
+      else atc_softmax_tile<true>(tS + g * 128 + lane_addr, prow, r, limit, p.scale_log2e, m_run, l_run, corr);
+      tc::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc::tc_fence_before();            // order our tcgen05.ld of S before the MMA that overwrites it
+      tc::mbar_arrive(&p_full[g]);
+      tc::mbar_wait(&o_full[g], ph);
       tc::tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tc::tmem_ld32(tO + b * 64 + lane_addr + c * 32, v);
+        tc::tmem_ld32(tO + g * 64 + lane_addr + c * 32, v);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int t = 0; t < 32; ++t) o[c * 32 + t] = fmaf(o[c * 32 + t], corr, __uint_as_float(v[t]));
       }
-    };
-    for (int j = 0; j < nt; ++j) {
-      const int b = j & 1, ph = (j >> 1) & 1;
-      tc::mbar_wait(&s_full[b], ph);
-      tc::tc_fence_after();
-      const int kbase = j * ATC_BK;
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tc::tmem_ld32(tS + b * 128 + lane_addr + c * 32, v);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const float s = (kbase + c * 32 + t < pr.nk) ? __uint_as_float(v[t]) * p.scale_log2e : -INFINITY;
-          mx = fmaxf(mx, s);
-        }
-      }
-      const float m_new = fmaxf(m_run, mx);
-      const float corr = exp2f(m_run - m_new);
-      // pass 2: P = exp2(s - m_new) -> bf16 -> swizzled smem; row sum (of the bf16-rounded values the MMA sees)
-      float sum = 0.f;
-      uint8_t* prow = sP + b * 2 * ATC_TILE + r * 128;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tc::tmem_ld32(tS + b * 128 + lane_addr + c * 32, v);
-        tc::tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int t = 0; t < 32; t += 2) {
-          const float s0 = (kbase + c * 32 + t < pr.nk) ? __uint_as_float(v[t]) * p.scale_log2e : -INFINITY;
-          const float s1 = (kbase + c * 32 + t + 1 < pr.nk) ? __uint_as_float(v[t + 1]) * p.scale_log2e : -INFINITY;
-          const __nv_bfloat162 hb = __floats2bfloat162_rn(exp2f(s0 - m_new), exp2f(s1 - m_new));
-          sum += __low2float(hb) + __high2float(hb);
-          pk[t >> 1] = *reinterpret_cast<const uint32_t*>(&hb);
-        }
-        // 32 keys = 64 B = four 16-byte chunks of block (c >> 1), chunk index ((c & 1) * 4 + q) ^ (r & 7)
-        uint8_t* blk = prow + (c >> 1) * ATC_TILE;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = (((c & 1) * 4 + q) ^ (r & 7));
-          *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
-      }
-      l_run = l_run * corr + sum;
-      m_run = m_new;
-      tc::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc::tc_fence_before();            // order our tcgen05.ld of S before the MMA that overwrites it
-      tc::mbar_arrive(&p_full[b]);
-      if (j >= 1) consume(j - 1, corr_prev);
-      corr_prev = corr;
+      tc::tc_fence_before();            // our tcgen05.ld of O[g] precedes the next PV into it (via p_full)
     }
-    consume(nt - 1, corr_prev);
-    if (q0 + r < pr.nq) {
-      const float inv = 1.f / l_run;
+    // ---- merge the two groups' partial softmax states (all MMAs that read sP have completed) ----
+    float* mrg = reinterpret_cast<float*>(sP);            // [66][128] floats: O^T (64 rows), m, l
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (g == 1) {
+#pragma unroll
+      for (int d = 0; d < ATC_D; ++d) mrg[d * 128 + r] = o[d];
+      mrg[64 * 128 + r] = m_run; mrg[65 * 128 + r] = l_run;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (g == 0 && q0 + r < pr.nq) {
+      const float m_b = mrg[64 * 128 + r], l_b = mrg[65 * 128 + r];
+      const float m = fmaxf(m_run, m_b);
+      const float ca = ex2_approx(m_run - m), cb = (m_b == -INFINITY) ? 0.f : ex2_approx(m_b - m);
+      const float inv = 1.f / (l_run * ca + l_b * cb);
+      const float fa = ca * inv, fb = cb * inv;
       uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)(pr.q_row + q0 + r) * p.ldo + h * 64);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        __nv_bfloat162 a = __floats2bfloat162_rn(o[8 * q] * inv, o[8 * q + 1] * inv), bb = __floats2bfloat162_rn(o[8 * q + 2] * inv, o[8 * q + 3] * inv);
-        __nv_bfloat162 c = __floats2bfloat162_rn(o[8 * q + 4] * inv, o[8 * q + 5] * inv), d = __floats2bfloat162_rn(o[8 * q + 6] * inv, o[8 * q + 7] * inv);
+        float e[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) e[t] = o[8 * q + t] * fa + mrg[(8 * q + t) * 128 + r] * fb;
+        __nv_bfloat162 a = __floats2bfloat162_rn(e[0], e[1]), bb = __floats2bfloat162_rn(e[2], e[3]);
+        __nv_bfloat162 c = __floats2bfloat162_rn(e[4], e[5]), d = __floats2bfloat162_rn(e[6], e[7]);
         uint4 u;
         u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&bb);
         u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);

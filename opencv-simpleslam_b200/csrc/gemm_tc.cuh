@@ -115,15 +115,29 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
       const int gc = n0 + c0;
       if (!live || gc >= p.N) continue;
       float f[32];
+      {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + gc);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + gc + j) : 0.f);
+        for (int q = 0; q < 8; ++q) {
+          const float4 bv = __ldg(b4 + q);
+          f[4 * q] = __uint_as_float(v[4 * q]) + bv.x; f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bv.y;
+          f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bv.z; f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bv.w;
+        }
+      }
       if (p.epi == TC_EPI_ROTARY_BF16 && gc < p.rot_cols) {
-        const int f0 = (gc & 63) >> 1;
+        const int f0 = (gc & 63) >> 1;   // 0 or 16: this chunk's 16 (cos,sin) pairs are contiguous
+        const float4* c4 = reinterpret_cast<const float4*>(p.rot_cos + grow * 32 + f0);
+        const float4* s4 = reinterpret_cast<const float4*>(p.rot_sin + grow * 32 + f0);
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float cs = p.rot_cos[grow * 32 + f0 + (j >> 1)], sn = p.rot_sin[grow * 32 + f0 + (j >> 1)];
-          const float a = f[j], b = f[j + 1];
-          f[j] = a * cs - b * sn; f[j + 1] = b * cs + a * sn;
+        for (int q = 0; q < 4; ++q) {
+          const float4 cv = __ldg(c4 + q), sv = __ldg(s4 + q);
+          const float cs[4] = {cv.x, cv.y, cv.z, cv.w}, sn[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = 8 * q + 2 * e;
+            const float a = f[j], b = f[j + 1];
+            f[j] = a * cs[e] - b * sn[e]; f[j + 1] = b * cs[e] + a * sn[e];
+          }
         }
       }
       if (p.epi == TC_EPI_F32) {

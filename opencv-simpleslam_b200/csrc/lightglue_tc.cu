@@ -192,7 +192,7 @@ static int tc_attention(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& ma
   ap.out = tc->ctxb; ap.ldo = 256;
   dim3 grid(cdiv(maxq, ATC_BQ), 4, 2);
   if (tc->prof) tc->prof->mark(PROF_ATTN, st);
-  k_attn_tc<<<grid, 192, ATC_SMEM, st>>>(map, ap);
+  k_attn_tc<<<grid, ATC_THREADS, ATC_SMEM, st>>>(map, ap);
   if (tc->prof) tc->prof->mark(PROF_ATTN, st);
   if (launches) ++*launches;
   B2S_LAUNCH_CHECK();
@@ -310,7 +310,7 @@ extern "C" int b2s_test_attn_tc(const float* q, const float* k, const float* v, 
   AttnTcParams ap = {};
   ap.qcol = 0; ap.kcol = 256; ap.vcol = 512; ap.prob[0] = {0, 0, nq, nk}; ap.prob[1] = {0, 0, 0, 0};
   ap.scale_log2e = 0.125f * 1.4426950408889634f; ap.out = dctx; ap.ldo = 256;
-  k_attn_tc<<<dim3(cdiv(nq, 128), 4, 1), 192, ATC_SMEM>>>(map, ap);
+  k_attn_tc<<<dim3(cdiv(nq, 128), 4, 1), ATC_THREADS, ATC_SMEM>>>(map, ap);
   B2S_LAUNCH_CHECK();
   B2S_CUDA(cudaDeviceSynchronize());
   std::vector<__nv_bfloat16> out((size_t)nq * 256);
