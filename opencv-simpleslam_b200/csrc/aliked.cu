@@ -32,6 +32,7 @@ struct b2s_aliked {
   float *img_pad, *resized, *t1a, *x1, *r2, *t2a, *x2, *x3in, *col3, *off3, *t3a, *r3, *x3, *x4in, *col4, *off4, *t4a, *r4, *x4;
   float *x2a, *x3a, *x4a, *s8, *feat, *score, *nms, *cand_sc, *sel_sc, *thr, *kp_norm, *disp, *sampled;
   float *Apatch, *toff1, *offs, *S, *F, *descraw;
+  float* skws = nullptr; size_t skws_floats = 0;        // split-K partial sums
   int *cand_idx, *sel_idx, *dk;
   int cand_cap = 0;
   // last-call geometry (for debug taps)
@@ -47,6 +48,12 @@ extern "C" void b2s_aliked_default_cfg(b2s_aliked_cfg* c) {
 }
 
 namespace {
+
+// GEMM with the handle's split-K workspace attached (small-M/N problems of the DCN / SDDH stages)
+int agemm(b2s_aliked* h, GemmParams& g, cudaStream_t st) {
+  g.splitk_ws = h->skws; g.splitk_ws_floats = h->skws_floats;
+  return gemm_simt(g, st, &h->launches);
+}
 
 struct BnFold { std::vector<float> scale, shift; };
 
@@ -168,6 +175,8 @@ int alloc_ws(b2s_aliked* h, int Hp, int Wp) {
   B2S_TRY(a.alloc(&h->sel_idx, K)); B2S_TRY(a.alloc(&h->sel_sc, K));
   B2S_TRY(a.alloc(&h->dk, (size_t)8)); B2S_TRY(a.alloc(&h->thr, (size_t)1));
   B2S_TRY(a.alloc(&h->kp_norm, 2 * K)); B2S_TRY(a.alloc(&h->disp, K)); B2S_TRY(a.alloc(&h->sampled, K));
+  h->skws_floats = std::max<size_t>((size_t)8 * K * 128, (size_t)8 * P3 * 64);
+  B2S_TRY(a.alloc(&h->skws, h->skws_floats));
   B2S_TRY(a.alloc(&h->Apatch, 1152 * K)); B2S_TRY(a.alloc(&h->toff1, 2 * M * K)); B2S_TRY(a.alloc(&h->offs, 2 * M * K));
   B2S_TRY(a.alloc(&h->S, M * 128 * K)); B2S_TRY(a.alloc(&h->F, M * 128 * K)); B2S_TRY(a.alloc(&h->descraw, 128 * K));
   h->wsHp = Hp; h->wsWp = Wp;
@@ -183,7 +192,7 @@ int run_dcn_block(b2s_aliked* h, cudaStream_t st, const DcnBlockW& w, const floa
     GemmParams g;
     g.A1 = A; g.lda1 = K; g.K1 = K; g.W = W; g.ldw = K; g.K = K; g.M = P; g.N = N; g.C = C; g.ldc = N;
     g.bias = bias; g.residual = residual; g.ldr = N; g.act = act; g.clamp = clamp;
-    return gemm_simt(g, st, &h->launches);
+    return agemm(h, g, st);
   };
   const int jobs = P * 9;
   // conv1: offsets (regular im2col) -> deformable im2col -> GEMM (+BN1) + SELU
@@ -320,9 +329,9 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
   {
     GemmParams g;
     g.A1 = h->x3; g.lda1 = 64; g.K1 = 64; g.W = h->agg_w[2]; g.ldw = 64; g.K = 64; g.M = H3 * W3; g.N = 32; g.C = h->x3a; g.ldc = 32; g.act = ACT_SELU;
-    B2S_TRY(gemm_simt(g, st, &h->launches));
+    B2S_TRY(agemm(h, g, st));
     g.A1 = h->x4; g.lda1 = 128; g.K1 = 128; g.W = h->agg_w[3]; g.ldw = 128; g.K = 128; g.M = H4 * W4; g.C = h->x4a;
-    B2S_TRY(gemm_simt(g, st, &h->launches));
+    B2S_TRY(agemm(h, g, st));
   }
   // ---- fused upsample + concat + normalise + score head ----
   {
@@ -370,21 +379,21 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
     GemmParams g;
     g.A1 = h->Apatch; g.lda1 = 1152; g.K1 = 1152; g.W = h->so0_w; g.ldw = 1152; g.K = 1152; g.M = K; g.N = 2 * M;
     g.C = h->toff1; g.ldc = 2 * M; g.bias = h->so0_b; g.act = ACT_SELU; g.m_dev = n_out; g.m_mult = 1;
-    B2S_TRY(gemm_simt(g, st, &h->launches));
+    B2S_TRY(agemm(h, g, st));
     g = GemmParams();
     g.A1 = h->toff1; g.lda1 = 2 * M; g.K1 = 2 * M; g.W = h->so2_w; g.ldw = 2 * M; g.K = 2 * M; g.M = K; g.N = 2 * M;
     g.C = h->offs; g.ldc = 2 * M; g.bias = h->so2_b; g.clamp = clampv; g.m_dev = n_out; g.m_mult = 1;
-    B2S_TRY(gemm_simt(g, st, &h->launches));
+    B2S_TRY(agemm(h, g, st));
     k_sddh_sample<<<cdiv(K * M, 8), 256, 0, st>>>(h->feat, Hr, Wr, h->kp_norm, h->offs, M, n_out, h->S);
     ++h->launches; B2S_LAUNCH_CHECK();
     g = GemmParams();
     g.A1 = h->S; g.lda1 = 128; g.K1 = 128; g.W = h->sf_w; g.ldw = 128; g.K = 128; g.M = K * M; g.N = 128;
     g.C = h->F; g.ldc = 128; g.act = ACT_SELU; g.m_dev = n_out; g.m_mult = M;
-    B2S_TRY(gemm_simt(g, st, &h->launches));
+    B2S_TRY(agemm(h, g, st));
     g = GemmParams();
     g.A1 = h->F; g.lda1 = M * 128; g.K1 = M * 128; g.W = h->aggT; g.ldw = M * 128; g.K = M * 128; g.M = K; g.N = 128;
     g.C = h->descraw; g.ldc = 128; g.m_dev = n_out; g.m_mult = 1;
-    B2S_TRY(gemm_simt(g, st, &h->launches));
+    B2S_TRY(agemm(h, g, st));
     k_desc_normalize<<<cdiv(K, 8), 256, 0, st>>>(h->descraw, n_out, desc);
     ++h->launches; B2S_LAUNCH_CHECK();
   }

@@ -33,53 +33,61 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// one key tile of the online softmax for one query row. MASK: tile is partial (keys >= limit masked)
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// pass 1 of a key tile: row maximum of the raw scores (keys >= limit masked when MASK)
 template <bool MASK>
-__device__ __forceinline__ void atc_softmax_tile(uint32_t s_addr, uint8_t* prow, int r, int limit, float scale,
-                                                 float& m_run, float& l_run, float& corr_out) {
+__device__ __forceinline__ float atc_row_max(uint32_t s_addr, int limit) {
   float mx = -INFINITY;
-#pragma unroll 1
+  uint32_t v[2][32];
+  tc::tmem_ld32(s_addr, v[0]);
+#pragma unroll
   for (int c = 0; c < 4; ++c) {
-    uint32_t v[32];
-    tc::tmem_ld32(s_addr + c * 32, v);
     tc::tmem_ld_wait();
+    if (c < 3) tc::tmem_ld32(s_addr + (c + 1) * 32, v[(c + 1) & 1]);   // next chunk in flight while this one is reduced
 #pragma unroll
     for (int t = 0; t < 32; ++t) {
-      const float s = __uint_as_float(v[t]);
+      const float s = __uint_as_float(v[c & 1][t]);
       if (!MASK || c * 32 + t < limit) mx = fmaxf(mx, s);
     }
   }
-  const float m_new = fmaxf(m_run, mx * scale);
-  corr_out = ex2_approx(m_run - m_new);
+  return mx;
+}
+
+// pass 2: P = 2^(s*scale - m) -> bf16 -> swizzled K-major smem tile; returns the row sum
+template <bool MASK>
+__device__ __forceinline__ float atc_write_p(uint32_t s_addr, uint32_t prow_addr, int r, int limit, float scale, float m_new) {
   float sum = 0.f;
-#pragma unroll 1
+  uint32_t v[2][32];
+  tc::tmem_ld32(s_addr, v[0]);
+#pragma unroll
   for (int c = 0; c < 4; ++c) {
-    uint32_t v[32];
-    tc::tmem_ld32(s_addr + c * 32, v);
     tc::tmem_ld_wait();
+    if (c < 3) tc::tmem_ld32(s_addr + (c + 1) * 32, v[(c + 1) & 1]);
     uint32_t pk[16];
 #pragma unroll
     for (int t = 0; t < 32; t += 2) {
-      float p0 = ex2_approx(fmaf(__uint_as_float(v[t]), scale, -m_new));
-      float p1 = ex2_approx(fmaf(__uint_as_float(v[t + 1]), scale, -m_new));
+      float p0 = ex2_approx(fmaf(__uint_as_float(v[c & 1][t]), scale, -m_new));
+      float p1 = ex2_approx(fmaf(__uint_as_float(v[c & 1][t + 1]), scale, -m_new));
       if (MASK) {
         if (c * 32 + t >= limit) p0 = 0.f;
         if (c * 32 + t + 1 >= limit) p1 = 0.f;
       }
+      sum += p0 + p1;
       const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-      sum += __low2float(hb) + __high2float(hb);     // sum what the MMA will actually see
       pk[t >> 1] = *reinterpret_cast<const uint32_t*>(&hb);
     }
     // 32 keys = 64 B = four 16-byte chunks of block (c >> 1); chunk ((c & 1) * 4 + q) ^ (r & 7)
-    uint8_t* blk = prow + (c >> 1) * ATC_TILE;
+    const uint32_t blk = prow_addr + (c >> 1) * ATC_TILE;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int chunk = (((c & 1) * 4 + q) ^ (r & 7));
-      *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      st_shared_v4(blk + chunk * 16, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
     }
   }
-  l_run = l_run * corr_out + sum;
-  m_run = m_new;
+  return sum;
 }
 
 __global__ void __launch_bounds__(ATC_THREADS, 1) k_attn_tc(const __grid_constant__ CUtensorMap mapQKV, AttnTcParams p) {
@@ -139,9 +147,22 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) k_attn_tc(const __grid_constan
       constexpr uint32_t idesc_s = tc::idesc_bf16(128, 128, 0, 0);   // S: A = Q (K-major), B = K tile (K-major)
       constexpr uint32_t idesc_o = tc::idesc_bf16(128, 64, 0, 1);    // PV: A = P (K-major), B = V (MN-major)
       const uint32_t q_addr = tc::smem_u32(sQ);
+      auto issue_s = [&](int j) {
+        const int b = j & 1, ph = (j >> 1) & 1;
+        tc::mbar_wait(&k_full[b], ph);
+        tc::tc_fence_after();
+        const uint32_t k_addr = tc::smem_u32(sK + b * ATC_TILE);
+#pragma unroll
+        for (int k = 0; k < ATC_D / 16; ++k) {
+          const uint64_t ad = tc::smem_desc_sw128(q_addr + k * 32, 16, 1024);
+          const uint64_t bd = tc::smem_desc_sw128(k_addr + k * 32, 16, 1024);
+          tc::umma_bf16(tS + b * 128, ad, bd, idesc_s, k ? 1u : 0u);
+        }
+        tc::umma_commit(&s_full[b]);
+        tc::umma_commit(&k_empty[b]);
+      };
       auto issue_pv = [&](int i) {
         const int b = i & 1, ph = (i >> 1) & 1;
-        tc::mbar_wait(&p_full[b], ph);
         tc::mbar_wait(&v_full[b], ph);
         tc::tc_fence_after();
         const uint32_t p_addr = tc::smem_u32(sP + b * 2 * ATC_TILE), v_addr = tc::smem_u32(sV + b * ATC_TILE);
@@ -156,22 +177,14 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) k_attn_tc(const __grid_constan
         tc::umma_commit(&v_empty[b]);
       };
       tc::mbar_wait(q_full, 0);
+      issue_s(0);
+      if (nt > 1) issue_s(1);
       for (int j = 0; j < nt; ++j) {
-        const int b = j & 1, ph = (j >> 1) & 1;
-        tc::mbar_wait(&k_full[b], ph);
-        tc::tc_fence_after();
-        const uint32_t k_addr = tc::smem_u32(sK + b * ATC_TILE);
-#pragma unroll
-        for (int k = 0; k < ATC_D / 16; ++k) {
-          const uint64_t ad = tc::smem_desc_sw128(q_addr + k * 32, 16, 1024);
-          const uint64_t bd = tc::smem_desc_sw128(k_addr + k * 32, 16, 1024);
-          tc::umma_bf16(tS + b * 128, ad, bd, idesc_s, k ? 1u : 0u);
-        }
-        tc::umma_commit(&s_full[b]);
-        tc::umma_commit(&k_empty[b]);
-        if (j >= 1) issue_pv(j - 1);
+        // p_full(j): group (j&1) has finished reading S[j&1] and has written P[j&1]
+        tc::mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        if (j + 2 < nt) issue_s(j + 2);     // next score tile of that group first: it is on the group's critical path
+        issue_pv(j);
       }
-      issue_pv(nt - 1);
     }
   } else {
     // ===== softmax groups: g = 0 (warps 2..5) takes even key tiles, g = 1 (warps 6..9) odd ones =====
@@ -183,30 +196,40 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) k_attn_tc(const __grid_constan
 #pragma unroll
     for (int d = 0; d < ATC_D; ++d) o[d] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
-    uint8_t* prow = sP + g * 2 * ATC_TILE + r * 128;
+    const uint32_t prow_addr = tc::smem_u32(sP + g * 2 * ATC_TILE + r * 128);
+    const uint32_t s_addr = tS + g * 128 + lane_addr, o_addr = tO + g * 64 + lane_addr;
+    float corr_prev = 0.f;
+    auto consume = [&](int jprev, float corr) {     // O = O * corr + PV(jprev)
+      tc::mbar_wait(&o_full[g], (jprev >> 1) & 1);
+      tc::tc_fence_after();
+      uint32_t v[2][32];
+      tc::tmem_ld32(o_addr, v[0]);
+      tc::tmem_ld32(o_addr + 32, v[1]);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int t = 0; t < 64; ++t) o[t] = fmaf(o[t], corr, __uint_as_float(v[t >> 5][t & 31]));
+    };
     for (int j = g; j < nt; j += 2) {
-      const int ph = (j >> 1) & 1;
-      tc::mbar_wait(&s_full[g], ph);
+      tc::mbar_wait(&s_full[g], (j >> 1) & 1);
       tc::tc_fence_after();
       const int limit = pr.nk - j * ATC_BK;
-      float corr;
-      if (limit >= ATC_BK) atc_softmax_tile<false>(tS + g * 128 + lane_addr, prow, r, limit, p.scale_log2e, m_run, l_run, corr);
-      else atc_softmax_tile<true>(tS + g * 128 + lane_addr, prow, r, limit, p.scale_log2e, m_run, l_run, corr);
+      const bool full = limit >= ATC_BK;
+      const float mx = full ? atc_row_max<false>(s_addr, limit) : atc_row_max<true>(s_addr, limit);
+      const float m_new = fmaxf(m_run, mx * p.scale_log2e);
+      const float corr = ex2_approx(m_run - m_new);
+      // PV of this group's previous tile: once it is read back, P[g] and O[g] are free again
+      if (j >= 2) consume(j - 2, corr_prev);
+      const float sum = full ? atc_write_p<false>(s_addr, prow_addr, r, limit, p.scale_log2e, m_new)
+                             : atc_write_p<true>(s_addr, prow_addr, r, limit, p.scale_log2e, m_new);
+      l_run = l_run * corr + sum;
+      m_run = m_new;
+      corr_prev = corr;
       tc::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc::tc_fence_before();            // order our tcgen05.ld of S before the MMA that overwrites it
+      tc::tc_fence_before();            // order our tcgen05.ld of S / O before the MMAs that overwrite them
       tc::mbar_arrive(&p_full[g]);
-      tc::mbar_wait(&o_full[g], ph);
-      tc::tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tc::tmem_ld32(tO + g * 64 + lane_addr + c * 32, v);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int t = 0; t < 32; ++t) o[c * 32 + t] = fmaf(o[c * 32 + t], corr, __uint_as_float(v[t]));
-      }
-      tc::tc_fence_before();            // our tcgen05.ld of O[g] precedes the next PV into it (via p_full)
     }
+    if (nt > g) consume(((nt - 1 - g) & ~1) + g, corr_prev);   // this group's last tile
+    tc::tc_fence_before();
     // ---- merge the two groups' partial softmax states (all MMAs that read sP have completed) ----
     float* mrg = reinterpret_cast<float*>(sP);            // [66][128] floats: O^T (64 rows), m, l
     asm volatile("bar.sync 1, 256;" ::: "memory");

@@ -10,6 +10,7 @@
 // Tile: BM x BN x 16, 256 threads, (BM/16)x(BN/16) register micro-tile split in two halves
 // per dimension so shared-memory float4 reads are conflict free.
 #pragma once
+#include <algorithm>
 #include "common.cuh"
 
 namespace b2s {
@@ -38,6 +39,11 @@ struct GemmParams {
   int rot_cols = 0;
   const float* rot_cos = nullptr;
   const float* rot_sin = nullptr;
+  // deterministic split-K for small-M/N problems (single segment only): blockIdx.z = K slice,
+  // raw partial sums go to splitk_ws [splitk][M][N] and k_gemm_splitk_epilogue reduces them
+  // in a fixed order (no atomics -> bitwise reproducible) before applying the epilogue.
+  float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;
+  int splitk = 1;
 };
 
 template <int BM, int BN>
@@ -49,7 +55,7 @@ __global__ void __launch_bounds__(256, (BM >= 128 ? 2 : 3)) k_gemm_simt(GemmPara
   __shared__ __align__(16) float As[2][BK][BM + PAD];
   __shared__ __align__(16) float Ws[2][BK][BN + PAD];
 
-  const int z = blockIdx.z;
+  const int z = p.splitk > 1 ? 0 : blockIdx.z;
   int rows = p.nseg > 1 ? p.seg_rows[z] : p.M;
   const int base = p.nseg > 1 ? p.seg_base[z] : 0;
   if (p.m_dev) rows = min(rows, *p.m_dev * p.m_mult);
@@ -109,11 +115,18 @@ __global__ void __launch_bounds__(256, (BM >= 128 ? 2 : 3)) k_gemm_simt(GemmPara
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  const int nk = p.K / BK;
-  load_tiles(0);
-  store_tiles(0);
+  int kt_begin = 0, nk = p.K / BK;
+  if (p.splitk > 1) {
+    const int per = (nk + p.splitk - 1) / p.splitk;
+    kt_begin = blockIdx.z * per;
+    nk = min(nk, kt_begin + per);
+  }
+  if (kt_begin < nk) {
+    load_tiles(kt_begin * BK);
+    store_tiles(kt_begin & 1);
+  }
   __syncthreads();
-  for (int kt = 0; kt < nk; ++kt) {
+  for (int kt = kt_begin; kt < nk; ++kt) {
     const int buf = kt & 1;
     if (kt + 1 < nk) load_tiles((kt + 1) * BK);
 #pragma unroll
@@ -149,6 +162,10 @@ __global__ void __launch_bounds__(256, (BM >= 128 ? 2 : 3)) k_gemm_simt(GemmPara
       const int c = n0 + (j / HN) * (BN / 2) + tx * HN + (j % HN);
       if (c >= p.N) continue;
       float v = acc[i][j];
+      if (p.splitk > 1) {   // raw partial sum; epilogue applied after the ordered reduction
+        p.splitk_ws[((size_t)blockIdx.z * p.M + r) * p.N + c] = v;
+        continue;
+      }
       if (p.bias) v += p.bias[c];
       v *= p.alpha;
       if (c < p.rot_cols) {
@@ -172,6 +189,24 @@ __global__ void __launch_bounds__(256, (BM >= 128 ? 2 : 3)) k_gemm_simt(GemmPara
   }
 }
 
+// ordered reduction of the split-K partials + the usual epilogue (bias, alpha, residual, act, clamp)
+static __global__ void __launch_bounds__(256) k_gemm_splitk_epilogue(GemmParams p) {
+  int rows = p.M;
+  if (p.m_dev) rows = min(rows, *p.m_dev * p.m_mult);
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)rows * p.N) return;
+  const int r = (int)(e / p.N), c = (int)(e % p.N);
+  float v = 0.f;
+  for (int z = 0; z < p.splitk; ++z) v += p.splitk_ws[((size_t)z * p.M + r) * p.N + c];
+  if (p.bias) v += p.bias[c];
+  v *= p.alpha;
+  if (p.residual) v += p.residual[(size_t)r * p.ldr + c];
+  if (p.act == ACT_SELU) v = selu_f(v);
+  else if (p.act == ACT_GELU) v = gelu_erf_f(v);
+  if (p.clamp > 0.f) v = fminf(fmaxf(v, -p.clamp), p.clamp);
+  p.C[(size_t)r * p.ldc + c] = v;
+}
+
 // Host launcher: picks the tile that best fills 148 SMs.
 inline int gemm_simt(const GemmParams& p, cudaStream_t st, long long* launches, KernelProf* prof = nullptr) {
   if (p.K % 16 != 0 || (p.K1 % 16) != 0) {
@@ -185,6 +220,23 @@ inline int gemm_simt(const GemmParams& p, cudaStream_t st, long long* launches, 
   if (maxrows <= 0 || q.N <= 0) return 0;
   if (prof) prof->mark(PROF_GEMM, st);
   const long long big = (long long)cdiv(maxrows, 128) * cdiv(q.N, 128) * q.nseg;
+  const long long small = (long long)cdiv(maxrows, 64) * cdiv(q.N, 64);
+  q.splitk = 1;
+  if (q.nseg == 1 && q.splitk_ws && q.rot_cols == 0 && small < 100 && q.K >= 256) {
+    int sk = (int)std::min<long long>((148 * 2 + small - 1) / small, q.K / 64);   // >= 4 k-tiles of 16 per slice
+    while (sk > 1 && (size_t)sk * q.M * q.N > q.splitk_ws_floats) --sk;
+    if (sk > 1) {
+      q.splitk = sk;
+      dim3 g(cdiv(q.N, 64), cdiv(maxrows, 64), sk);
+      k_gemm_simt<64, 64><<<g, 256, 0, st>>>(q);
+      const size_t total = (size_t)maxrows * q.N;
+      k_gemm_splitk_epilogue<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(q);
+      if (prof) prof->mark(PROF_GEMM, st);
+      if (launches) *launches += 2;
+      B2S_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   if (big >= 148 && q.N >= 128) {
     dim3 g(cdiv(q.N, 128), cdiv(maxrows, 128), q.nseg);
     k_gemm_simt<128, 128><<<g, 256, 0, st>>>(q);
