@@ -21,10 +21,12 @@ struct PreParams {
   float* resized;   // optional tap: [3][Hr][Wr]
 };
 
+__shared__ float pre_lut[256];   // u8 -> float(u8)/255 (filled by k_preprocess; replaces 100+ divisions per pixel)
+
 __device__ __forceinline__ float pre_src(const PreParams& p, int c, int y, int x) {
   if (p.fmt == B2S_IMG_BGR_U8_HWC) {
     const uint8_t* b = static_cast<const uint8_t*>(p.img);
-    return __fdiv_rn((float)b[(size_t)y * p.stride + x * 3 + (2 - c)], 255.0f);
+    return pre_lut[b[(size_t)y * p.stride + x * 3 + (2 - c)]];     // == (float)u8 / 255.0f, exactly rounded
   }
   const float* f = static_cast<const float*>(p.img);
   return f[((size_t)c * p.H + y) * p.W + x];
@@ -48,6 +50,8 @@ __device__ __forceinline__ float pre_blur(const PreParams& p, int c, int y, int 
 }
 
 __global__ void __launch_bounds__(256) k_preprocess(PreParams p) {
+  pre_lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);   // blockDim.x == 256
+  __syncthreads();
   const int xp = blockIdx.x * blockDim.x + threadIdx.x;
   const int yp = blockIdx.y;
   if (xp >= p.Wp) return;
@@ -695,20 +699,29 @@ __global__ void __launch_bounds__(256) k_dkd_refine(RefineParams p) {
   const int K = p.dk[4];
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e == 0) *p.n_out = K;
-  if (e >= K) return;
-  const int idx = p.sel_idx[e];
-  const float sc = p.sel_sc[e];
+  if (blockIdx.x * blockDim.x >= K) return;            // uniform per CTA
+  __shared__ int t_idx[256];
+  __shared__ float t_sc[256];
+  const bool live = e < K;
+  const int idx = live ? p.sel_idx[e] : 0;
+  const float sc = live ? p.sel_sc[e] : 0.f;
   const bool trunc = p.dk[3] != 0;
   int rank = 0;
-  for (int j = 0; j < K; ++j) {
-    const int oi = p.sel_idx[j];
+  for (int j0 = 0; j0 < K; j0 += 256) {               // the selected list streams through shared memory
+    __syncthreads();
+    if (j0 + threadIdx.x < K) { t_idx[threadIdx.x] = p.sel_idx[j0 + threadIdx.x]; t_sc[threadIdx.x] = p.sel_sc[j0 + threadIdx.x]; }
+    __syncthreads();
+    const int lim = min(256, K - j0);
     if (trunc) {
-      const float os = p.sel_sc[j];
-      rank += (os > sc || (os == sc && oi < idx)) ? 1 : 0;
+      for (int j = 0; j < lim; ++j) {
+        const float os = t_sc[j];
+        rank += (os > sc || (os == sc && t_idx[j] < idx)) ? 1 : 0;
+      }
     } else {
-      rank += (oi < idx) ? 1 : 0;
+      for (int j = 0; j < lim; ++j) rank += (t_idx[j] < idx) ? 1 : 0;
     }
   }
+  if (!live) return;
   const int W = p.W, H = p.H;
   const int xi = idx % W, yi = idx / W;
   float patch[25], mx = -INFINITY;

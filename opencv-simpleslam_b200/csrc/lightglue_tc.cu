@@ -118,6 +118,38 @@ static int make_linear(LgTensorCore* tc, const float* w_dev, const float* bias, 
   return make_tmap_bf16_2d(&out->map, out->w, K, N, (uint64_t)K * 2, 64, out->BN);
 }
 
+// FFN first layer with the attention output projection folded in (exact in real arithmetic):
+//   ffn.0([x | out_proj(ctx)]) = x W1x^T + ctx (W1m Wo)^T + (b1 + W1m bo)
+// so the block needs no separate out_proj GEMM and `msg` is never rounded to bf16.
+static int make_folded_ffn1(LgTensorCore* tc, const float* w1_dev, const float* b1_dev, const float* wo_dev, const float* bo_dev,
+                            TcLinear* out) {
+  std::vector<float> w1(512 * 512), b1(512), wo(256 * 256), bo(256);
+  B2S_CUDA(cudaMemcpy(w1.data(), w1_dev, w1.size() * 4, cudaMemcpyDeviceToHost));
+  B2S_CUDA(cudaMemcpy(b1.data(), b1_dev, b1.size() * 4, cudaMemcpyDeviceToHost));
+  B2S_CUDA(cudaMemcpy(wo.data(), wo_dev, wo.size() * 4, cudaMemcpyDeviceToHost));
+  B2S_CUDA(cudaMemcpy(bo.data(), bo_dev, bo.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<float> wf(512 * 512), bf(512);
+  for (int o = 0; o < 512; ++o) {
+    const float* w1m = &w1[(size_t)o * 512 + 256];
+    double bacc = b1[o];
+    for (int j = 0; j < 256; ++j) bacc += (double)w1m[j] * bo[j];
+    bf[o] = (float)bacc;
+    for (int k = 0; k < 256; ++k) wf[(size_t)o * 512 + k] = w1[(size_t)o * 512 + k];
+    double acc[256];
+    for (int k = 0; k < 256; ++k) acc[k] = 0.0;
+    for (int j = 0; j < 256; ++j) {
+      const double a = w1m[j];
+      const float* wr = &wo[(size_t)j * 256];
+      for (int k = 0; k < 256; ++k) acc[k] += a * wr[k];
+    }
+    for (int k = 0; k < 256; ++k) wf[(size_t)o * 512 + 256 + k] = (float)acc[k];
+  }
+  float *wf_dev, *bf_dev;
+  B2S_TRY(tc->warena.upload(&wf_dev, wf));
+  B2S_TRY(tc->warena.upload(&bf_dev, bf));
+  return make_linear(tc, wf_dev, bf_dev, 512, 512, out);
+}
+
 int lgtc_create(LgTensorCore** out, size_t n_layers) {
   LgTensorCore* tc = new LgTensorCore();
   tc->L.resize(n_layers);
@@ -131,12 +163,10 @@ int lgtc_create(LgTensorCore** out, size_t n_layers) {
 int lgtc_set_layer(LgTensorCore* tc, int li, const LgTcLayerSrc& s) {
   TcLayer& l = tc->L[li];
   B2S_TRY(make_linear(tc, s.wqkv, s.bqkv, 768, 256, &l.qkv));
-  B2S_TRY(make_linear(tc, s.wo, s.bo, 256, 256, &l.wo));
-  B2S_TRY(make_linear(tc, s.w1, s.b1, 512, 512, &l.w1));
+  B2S_TRY(make_folded_ffn1(tc, s.w1, s.b1, s.wo, s.bo, &l.w1));
   B2S_TRY(make_linear(tc, s.w2, s.b2, 256, 512, &l.w2));
   B2S_TRY(make_linear(tc, s.cwqkv, s.cbqkv, 512, 256, &l.cqkv));
-  B2S_TRY(make_linear(tc, s.cwo, s.cbo, 256, 256, &l.cwo));
-  B2S_TRY(make_linear(tc, s.cw1, s.cb1, 512, 512, &l.cw1));
+  B2S_TRY(make_folded_ffn1(tc, s.cw1, s.cb1, s.cwo, s.cbo, &l.cw1));
   B2S_TRY(make_linear(tc, s.cw2, s.cb2, 256, 512, &l.cw2));
   l.lng = s.lng; l.lnb = s.lnb; l.clng = s.clng; l.clnb = s.clnb;
   B2S_CUDA(cudaDeviceSynchronize());
@@ -203,7 +233,7 @@ static int tc_ffn(LgTensorCore* tc, cudaStream_t st, float* x, const TcLinear& w
                   int m, int n, long long* launches) {
   TcGemmParams p = {};
   p.epi = TC_EPI_F32; p.out_f32 = tc->h1f; p.ld_f32 = 512;
-  B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_msgb, 256, w1, p, m, n, launches));          // [x | msg] W1^T + b1
+  B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_ctxb, 256, w1, p, m, n, launches));          // [x | ctx] W1'^T + b1' (out_proj folded)
   dim3 g(cdiv(std::max(m, n), 8), 2);
   k_ln_gelu_512_bf16<<<g, 256, 0, st>>>(tc->h1f, tc->h1b, 0, m, tc->cap, n, lng, lnb);
   if (launches) ++*launches;
@@ -232,8 +262,6 @@ int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int li, float* x, const float*
   ap.qcol = 0; ap.kcol = 256; ap.vcol = 512;
   ap.prob[0] = {0, 0, m, m}; ap.prob[1] = {cap, cap, n, n};
   B2S_TRY(tc_attention(tc, st, tc->m_qkv768, ap, launches));
-  p = TcGemmParams(); p.epi = TC_EPI_BF16; p.out_bf16 = tc->msgb; p.ld_bf16 = 256;
-  B2S_TRY(tc_gemm(tc, st, tc->m_ctxb, tc->m_ctxb, 256, l.wo, p, m, n, launches));
   B2S_TRY(tc_ffn(tc, st, x, l.w1, l.lng, l.lnb, l.w2, m, n, launches));
   // ---- cross block ----
   p = TcGemmParams(); p.epi = TC_EPI_BF16; p.out_bf16 = tc->qkvb; p.ld_bf16 = 512;
@@ -242,8 +270,6 @@ int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int li, float* x, const float*
   ap.qcol = 0; ap.kcol = 0; ap.vcol = 256;
   ap.prob[0] = {0, cap, m, n}; ap.prob[1] = {cap, 0, n, m};
   B2S_TRY(tc_attention(tc, st, tc->m_qkv512, ap, launches));
-  p = TcGemmParams(); p.epi = TC_EPI_BF16; p.out_bf16 = tc->msgb; p.ld_bf16 = 256;
-  B2S_TRY(tc_gemm(tc, st, tc->m_ctxb, tc->m_ctxb, 256, l.cwo, p, m, n, launches));
   return tc_ffn(tc, st, x, l.cw1, l.clng, l.clnb, l.cw2, m, n, launches);
 }
 
