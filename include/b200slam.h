@@ -112,13 +112,15 @@ void b2s_lg_destroy(b2s_lg* h);
  *   n_matches_dev: device int32
  *   optional (nullable): matches0_dev [m] / matches1_dev [n] int32 (-1 = unmatched),
  *   ms0_dev [m] / ms1_dev [n] f32, prune0_dev [m] / prune1_dev [n] int32.
- *   stop_layer (host, nullable) receives the number of layers executed (upstream 'stop').
- * The call synchronises `stream` internally where upstream needs a host decision
- * (early exit / pruning) unless those are disabled in the cfg. */
+ *   stop_layer_dev (device int32, nullable) receives the number of layers executed (upstream 'stop').
+ * The whole match is enqueued on `stream` without any host synchronisation: the decisions upstream
+ * takes on the host after every layer (early exit, point pruning) are taken on the device, and the
+ * kernels of layers behind an exit return at once.  (A stream sync happens only when the workspace
+ * has to grow because max(m,n) exceeds the handle's capacity.) */
 int b2s_lightglue_match(b2s_lg* h, const float* k0_dev, const float* d0_dev, int m,
                         const float* k1_dev, const float* d1_dev, int n, const float* size0,
                         const float* size1, void* stream, int32_t* matches_dev,
-                        float* mscores_dev, int32_t* n_matches_dev, int32_t* stop_layer,
+                        float* mscores_dev, int32_t* n_matches_dev, int32_t* stop_layer_dev,
                         int32_t* matches0_dev, int32_t* matches1_dev, float* ms0_dev,
                         float* ms1_dev, int32_t* prune0_dev, int32_t* prune1_dev);
 
@@ -156,6 +158,8 @@ int b2s_lg_profile_read(b2s_lg* h, int cls, double* ms, long long* n_launches);
  *   b2s_test_attn_tc : ctx[nq,256] = softmax(q k^T / 8) v per head (4 heads x 64) */
 int b2s_test_gemm_tc(const float* A, const float* W, const float* bias, int M, int N, int K, float* C);
 int b2s_test_attn_tc(const float* q, const float* k, const float* v, int nq, int nk, float* ctx);
+/* device-only timing of one self-block attention launch (2 problems x 4 heads, nq x nk), mean ms per launch */
+int b2s_bench_attn_tc(int nq, int nk, int iters, float* ms_out);
 
 /* Number of CUDA kernels this library launched on behalf of the handle so far. */
 long long b2s_aliked_launch_count(const b2s_aliked* h);

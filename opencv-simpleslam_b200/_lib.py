@@ -57,6 +57,7 @@ SIGNATURES = {
     "b2s_lg_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "b2s_test_gemm_tc": (C.c_int, [f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, f32p]),
     "b2s_test_attn_tc": (C.c_int, [f32p, f32p, f32p, C.c_int, C.c_int, f32p]),
+    "b2s_bench_attn_tc": (C.c_int, [C.c_int, C.c_int, C.c_int, f32p]),
     "b2s_aliked_launch_count": (C.c_longlong, [vp]),
     "b2s_lg_launch_count": (C.c_longlong, [vp]),
 }

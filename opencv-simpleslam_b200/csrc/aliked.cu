@@ -196,19 +196,19 @@ int run_dcn_block(b2s_aliked* h, cudaStream_t st, const DcnBlockW& w, const floa
   };
   const int jobs = P * 9;
   // conv1: offsets (regular im2col) -> deformable im2col -> GEMM (+BN1) + SELU
-  k_dcn_im2col<<<cdiv(jobs, 8), 256, 0, st>>>(in, w.cin, Hh, Ww, nullptr, col);
+  launch_k(k_dcn_im2col, cdiv(jobs, 8), 256, 0, st, in, w.cin, Hh, Ww, nullptr, col);
   ++h->launches; B2S_LAUNCH_CHECK();
   B2S_TRY(gemm(col, 9 * w.cin, w.off1_w, 18, w.off1_b, off, nullptr, ACT_NONE, clampv));
-  k_dcn_im2col<<<cdiv(jobs, 8), 256, 0, st>>>(in, w.cin, Hh, Ww, off, col);
+  launch_k(k_dcn_im2col, cdiv(jobs, 8), 256, 0, st, in, w.cin, Hh, Ww, off, col);
   ++h->launches; B2S_LAUNCH_CHECK();
   B2S_TRY(gemm(col, 9 * w.cin, w.reg1_w, w.cout, w.reg1_b, ta, nullptr, ACT_SELU, 0.f));
   // downsample(x) -> residual
   B2S_TRY(gemm(in, w.cin, w.ds_w, w.cout, w.ds_b, res, nullptr, ACT_NONE, 0.f));
   // conv2 on ta
-  k_dcn_im2col<<<cdiv(jobs, 8), 256, 0, st>>>(ta, w.cout, Hh, Ww, nullptr, col);
+  launch_k(k_dcn_im2col, cdiv(jobs, 8), 256, 0, st, ta, w.cout, Hh, Ww, nullptr, col);
   ++h->launches; B2S_LAUNCH_CHECK();
   B2S_TRY(gemm(col, 9 * w.cout, w.off2_w, 18, w.off2_b, off, nullptr, ACT_NONE, clampv));
-  k_dcn_im2col<<<cdiv(jobs, 8), 256, 0, st>>>(ta, w.cout, Hh, Ww, off, col);
+  launch_k(k_dcn_im2col, cdiv(jobs, 8), 256, 0, st, ta, w.cout, Hh, Ww, off, col);
   ++h->launches; B2S_LAUNCH_CHECK();
   return gemm(col, 9 * w.cout, w.reg2_w, w.cout, w.reg2_b, out, res, ACT_SELU, 0.f);
 }
@@ -296,35 +296,35 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
   }
   h->Hr = Hr; h->Wr = Wr; h->Hp = Hp; h->Wp = Wp;
   pp.out = h->img_pad; pp.resized = h->resized;
-  k_preprocess<<<dim3(cdiv(Wp, 256), Hp), 256, 0, st>>>(pp);
+  launch_k(k_preprocess, dim3(cdiv(Wp, 256), Hp), 256, 0, st, pp);
   ++h->launches; B2S_LAUNCH_CHECK();
 
   // ---- block1 (full res) ----
   {
     dim3 g(cdiv(Wp, 32), cdiv(Hp, 16));
-    k_conv3x3<3, 16, false><<<g, dim3(16, 8, 1), 0, st>>>(h->img_pad, Hp, Wp, h->b1c1_w, h->b1c1_b, nullptr, h->t1a, 1);
-    k_conv3x3<16, 16, false><<<g, dim3(16, 8, 1), 0, st>>>(h->t1a, Hp, Wp, h->b1c2_w, h->b1c2_b, nullptr, h->x1, 1);
+    launch_k(k_conv3x3<3, 16, false>, g, dim3(16, 8, 1), 0, st, h->img_pad, Hp, Wp, h->b1c1_w, h->b1c1_b, nullptr, h->t1a, 1);
+    launch_k(k_conv3x3<16, 16, false>, g, dim3(16, 8, 1), 0, st, h->t1a, Hp, Wp, h->b1c2_w, h->b1c2_b, nullptr, h->x1, 1);
     h->launches += 2; B2S_LAUNCH_CHECK();
   }
   // ---- block2 (1/2 res): pool2 fused into conv1's load and into the 1x1 downsample ----
   const int H2 = Hp / 2, W2 = Wp / 2;
   {
     dim3 g(cdiv(W2, 32), cdiv(H2, 16));
-    k_pool2_conv1x1<16, 32><<<cdiv(H2 * W2, 64), 256, 0, st>>>(h->x1, H2, W2, h->b2ds_w, h->b2ds_b, h->r2);
-    k_conv3x3<16, 32, true><<<g, dim3(16, 8, 2), 0, st>>>(h->x1, H2, W2, h->b2c1_w, h->b2c1_b, nullptr, h->t2a, 1);
-    k_conv3x3<32, 32, false><<<g, dim3(16, 8, 2), 0, st>>>(h->t2a, H2, W2, h->b2c2_w, h->b2c2_b, h->r2, h->x2, 1);
+    launch_k(k_pool2_conv1x1<16, 32>, cdiv(H2 * W2, 64), 256, 0, st, h->x1, H2, W2, h->b2ds_w, h->b2ds_b, h->r2);
+    launch_k(k_conv3x3<16, 32, true>, g, dim3(16, 8, 2), 0, st, h->x1, H2, W2, h->b2c1_w, h->b2c1_b, nullptr, h->t2a, 1);
+    launch_k(k_conv3x3<32, 32, false>, g, dim3(16, 8, 2), 0, st, h->t2a, H2, W2, h->b2c2_w, h->b2c2_b, h->r2, h->x2, 1);
     h->launches += 3; B2S_LAUNCH_CHECK();
   }
   // ---- block3 (1/8) and block4 (1/32): DCN via im2col + GEMM, HWC ----
   const int H3 = H2 / 4, W3 = W2 / 4, H4 = H3 / 4, W4 = W3 / 4;
-  k_pool4_chw_to_hwc<<<cdiv(H3 * W3, 8), 256, 0, st>>>(h->x2, 32, H3, W3, h->x3in);
+  launch_k(k_pool4_chw_to_hwc, cdiv(H3 * W3, 8), 256, 0, st, h->x2, 32, H3, W3, h->x3in);
   ++h->launches; B2S_LAUNCH_CHECK();
   B2S_TRY(run_dcn_block(h, st, h->b3, h->x3in, H3, W3, h->col3, h->off3, h->t3a, h->r3, h->x3));
-  k_pool4_hwc<<<cdiv(H4 * W4, 8), 256, 0, st>>>(h->x3, 64, H4, W4, h->x4in);
+  launch_k(k_pool4_hwc, cdiv(H4 * W4, 8), 256, 0, st, h->x3, 64, H4, W4, h->x4in);
   ++h->launches; B2S_LAUNCH_CHECK();
   B2S_TRY(run_dcn_block(h, st, h->b4, h->x4in, H4, W4, h->col4, h->off4, h->t4a, h->r4, h->x4));
   // ---- aggregation convs at native resolution ----
-  k_conv1x1_chw_to_hwc32<32><<<cdiv(H2 * W2, 64), 256, 0, st>>>(h->x2, (size_t)H2 * W2, h->agg_w[1], h->x2a);
+  launch_k(k_conv1x1_chw_to_hwc32<32>, cdiv(H2 * W2, 64), 256, 0, st, h->x2, (size_t)H2 * W2, h->agg_w[1], h->x2a);
   ++h->launches; B2S_LAUNCH_CHECK();
   {
     GemmParams g;
@@ -346,26 +346,26 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
     }
     ap.W1 = h->agg_w[0]; ap.Ws0 = h->sh0; ap.s8 = h->s8; ap.feat = h->feat;
     ap.Hr = Hr; ap.Wr = Wr; ap.pad_t = pp.pad_t; ap.pad_l = pp.pad_l;
-    k_aliked_agg<<<dim3(cdiv(Wp, 128), Hp), 128, 0, st>>>(ap);
+    launch_k(k_aliked_agg, dim3(cdiv(Wp, 128), Hp), 128, 0, st, ap);
     ScoreParams sp;
     sp.s8 = h->s8; sp.Hp = Hp; sp.Wp = Wp; sp.w2 = h->sh2; sp.w4 = h->sh4; sp.w6 = h->sh6;
     sp.score = h->score; sp.Hr = Hr; sp.Wr = Wr; sp.pad_t = pp.pad_t; sp.pad_l = pp.pad_l;
-    k_aliked_score<<<dim3(cdiv(Wp, 32), cdiv(Hp, 8)), 256, 0, st>>>(sp);
+    launch_k(k_aliked_score, dim3(cdiv(Wp, 32), cdiv(Hp, 8)), 256, 0, st, sp);
     h->launches += 2; B2S_LAUNCH_CHECK();
   }
   // ---- DKD ----
   {
     B2S_CUDA(cudaMemsetAsync(h->dk, 0, 8 * sizeof(int), st));
     B2S_CUDA(cudaMemcpyAsync(h->thr, &h->cfg.det_thresh, sizeof(float), cudaMemcpyHostToDevice, st));
-    k_dkd_nms<<<dim3(cdiv(Wr, NMS_T), cdiv(Hr, NMS_T)), 256, 0, st>>>(h->score, Hr, Wr, h->nms, h->thr, h->dk, h->cand_idx, h->cand_sc, h->cand_cap);
-    k_dkd_fallback<<<1, 1024, 0, st>>>(h->score, h->nms, Hr * Wr, h->thr, h->dk, h->cand_idx, h->cand_sc, h->cand_cap);
-    k_dkd_select<<<1, 1024, 0, st>>>(h->cand_sc, h->cand_idx, h->cand_cap, h->n_limit, h->dk);
-    k_dkd_compact<<<cdiv(h->cand_cap, 256), 256, 0, st>>>(h->cand_idx, h->cand_sc, h->dk, h->sel_idx, h->sel_sc);
+    launch_k(k_dkd_nms, dim3(cdiv(Wr, NMS_T), cdiv(Hr, NMS_T)), 256, 0, st, h->score, Hr, Wr, h->nms, h->thr, h->dk, h->cand_idx, h->cand_sc, h->cand_cap);
+    launch_k(k_dkd_fallback, 1, 1024, 0, st, h->score, h->nms, Hr * Wr, h->thr, h->dk, h->cand_idx, h->cand_sc, h->cand_cap);
+    launch_k(k_dkd_select, 1, 1024, 0, st, h->cand_sc, h->cand_idx, h->cand_cap, h->n_limit, h->dk);
+    launch_k(k_dkd_compact, cdiv(h->cand_cap, 256), 256, 0, st, h->cand_idx, h->cand_sc, h->dk, h->sel_idx, h->sel_sc);
     RefineParams rp;
     rp.dk = h->dk; rp.sel_idx = h->sel_idx; rp.sel_sc = h->sel_sc; rp.score = h->score; rp.H = Hr; rp.W = Wr;
     rp.scale_x = (float)((double)Wr / (double)W); rp.scale_y = (float)((double)Hr / (double)H);
     rp.kp_norm = h->kp_norm; rp.kp_out = kpts; rp.disp = h->disp; rp.sampled = h->sampled; rp.n_out = n_out;
-    k_dkd_refine<<<cdiv(h->n_limit, 256), 256, 0, st>>>(rp);
+    launch_k(k_dkd_refine, cdiv(h->n_limit, RF_KP), 256, 0, st, rp);
     h->launches += 5; B2S_LAUNCH_CHECK();
     // upstream puts DKD's 2nd return value (dispersity) under "keypoint_scores" 
     if (scores) B2S_CUDA(cudaMemcpyAsync(scores, h->disp, (size_t)h->n_limit * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -374,7 +374,7 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
   {
     const int K = h->n_limit, M = h->M;
     const float clampv = (float)std::max(Hr, Wr) / 4.0f;
-    k_sddh_patch<<<cdiv(K * 9, 8), 256, 0, st>>>(h->feat, Hr, Wr, h->kp_norm, n_out, h->Apatch);
+    launch_k(k_sddh_patch, cdiv(K * 9, 8), 256, 0, st, h->feat, Hr, Wr, h->kp_norm, n_out, h->Apatch);
     ++h->launches; B2S_LAUNCH_CHECK();
     GemmParams g;
     g.A1 = h->Apatch; g.lda1 = 1152; g.K1 = 1152; g.W = h->so0_w; g.ldw = 1152; g.K = 1152; g.M = K; g.N = 2 * M;
@@ -384,7 +384,7 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
     g.A1 = h->toff1; g.lda1 = 2 * M; g.K1 = 2 * M; g.W = h->so2_w; g.ldw = 2 * M; g.K = 2 * M; g.M = K; g.N = 2 * M;
     g.C = h->offs; g.ldc = 2 * M; g.bias = h->so2_b; g.clamp = clampv; g.m_dev = n_out; g.m_mult = 1;
     B2S_TRY(agemm(h, g, st));
-    k_sddh_sample<<<cdiv(K * M, 8), 256, 0, st>>>(h->feat, Hr, Wr, h->kp_norm, h->offs, M, n_out, h->S);
+    launch_k(k_sddh_sample, cdiv(K * M, 8), 256, 0, st, h->feat, Hr, Wr, h->kp_norm, h->offs, M, n_out, h->S);
     ++h->launches; B2S_LAUNCH_CHECK();
     g = GemmParams();
     g.A1 = h->S; g.lda1 = 128; g.K1 = 128; g.W = h->sf_w; g.ldw = 128; g.K = 128; g.M = K * M; g.N = 128;
@@ -394,7 +394,7 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
     g.A1 = h->F; g.lda1 = M * 128; g.K1 = M * 128; g.W = h->aggT; g.ldw = M * 128; g.K = M * 128; g.M = K; g.N = 128;
     g.C = h->descraw; g.ldc = 128; g.m_dev = n_out; g.m_mult = 1;
     B2S_TRY(agemm(h, g, st));
-    k_desc_normalize<<<cdiv(K, 8), 256, 0, st>>>(h->descraw, n_out, desc);
+    launch_k(k_desc_normalize, cdiv(K, 8), 256, 0, st, h->descraw, n_out, desc);
     ++h->launches; B2S_LAUNCH_CHECK();
   }
   return 0;

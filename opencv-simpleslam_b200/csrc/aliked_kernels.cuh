@@ -50,6 +50,7 @@ __device__ __forceinline__ float pre_blur(const PreParams& p, int c, int y, int 
 }
 
 __global__ void __launch_bounds__(256) k_preprocess(PreParams p) {
+  pdl_wait();
   pre_lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);   // blockDim.x == 256
   __syncthreads();
   const int xp = blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(128 * (COUT / 16)) k_conv3x3(const float* __re
                                                                const float* __restrict__ w, const float* __restrict__ bias,
                                                                const float* __restrict__ residual, float* __restrict__ out,
                                                                int act) {
+  pdl_wait();
   constexpr int CC = CIN < 8 ? CIN : 8;
   constexpr int TH = 16, TW = 32, RS = TW + 4;
   __shared__ __align__(16) float tin[CC][TH + 2][RS];
@@ -185,6 +187,7 @@ template <int CIN, int COUT>
 __global__ void __launch_bounds__(256) k_pool2_conv1x1(const float* __restrict__ in, int H, int W /*pooled dims*/,
                                                        const float* __restrict__ w /*[COUT][CIN]*/,
                                                        const float* __restrict__ bias, float* __restrict__ out) {
+  pdl_wait();
   __shared__ float xs[CIN][64];
   __shared__ float ws[COUT][CIN + 1];
   const int tid = threadIdx.x;
@@ -218,6 +221,7 @@ __global__ void __launch_bounds__(256) k_pool2_conv1x1(const float* __restrict__
 
 // 4x4 average pooling, planar CHW [C][4H][4W] -> HWC [H*W][C].  warp per output pixel.
 __global__ void __launch_bounds__(256) k_pool4_chw_to_hwc(const float* __restrict__ in, int C, int H, int W, float* __restrict__ out) {
+  pdl_wait();
   const int pix = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (pix >= H * W) return;
   const int lane = threadIdx.x & 31;
@@ -235,6 +239,7 @@ __global__ void __launch_bounds__(256) k_pool4_chw_to_hwc(const float* __restric
 }
 // 4x4 average pooling HWC -> HWC.
 __global__ void __launch_bounds__(256) k_pool4_hwc(const float* __restrict__ in, int C, int H, int W, float* __restrict__ out) {
+  pdl_wait();
   const int pix = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (pix >= H * W) return;
   const int lane = threadIdx.x & 31;
@@ -254,6 +259,7 @@ __global__ void __launch_bounds__(256) k_pool4_hwc(const float* __restrict__ in,
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_dcn_im2col(const float* __restrict__ in, int C, int H, int W,
                                                     const float* __restrict__ offs, float* __restrict__ col) {
+  pdl_wait();
   const int job = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (job >= H * W * 9) return;
   const int lane = threadIdx.x & 31;
@@ -284,6 +290,7 @@ __global__ void __launch_bounds__(256) k_dcn_im2col(const float* __restrict__ in
 template <int CIN>
 __global__ void __launch_bounds__(256) k_conv1x1_chw_to_hwc32(const float* __restrict__ in, size_t npix,
                                                               const float* __restrict__ w /*[32][CIN]*/, float* __restrict__ out) {
+  pdl_wait();
   __shared__ float xs[CIN][64];
   __shared__ float ws[32][CIN + 1];
   const int tid = threadIdx.x;
@@ -327,6 +334,7 @@ struct AggParams {
 };
 
 __global__ void __launch_bounds__(128) k_aliked_agg(AggParams p) {
+  pdl_wait();
   // one thread per padded pixel (128 consecutive pixels of a row per CTA): the whole 128-channel
   // vector lives in registers, so the norm and the 128->8 score projection need no shuffles.
   __shared__ __align__(16) float sW1[32 * 16];
@@ -410,6 +418,7 @@ struct ScoreParams {
 };
 
 __global__ void __launch_bounds__(256) k_aliked_score(ScoreParams p) {
+  pdl_wait();
   constexpr int TW = 32, TH = 8;
   __shared__ float t0[8][TH + 6][TW + 6];
   __shared__ float t1[4][TH + 4][TW + 4];
@@ -489,6 +498,7 @@ constexpr int NMS_T = 32, NMS_H = 10, NMS_S = NMS_T + 2 * NMS_H;  // 52
 __global__ void __launch_bounds__(256) k_dkd_nms(const float* __restrict__ score, int H, int W, float* __restrict__ nms,
                                                  const float* __restrict__ thr, int* __restrict__ dk,
                                                  int* __restrict__ cand_idx, float* __restrict__ cand_sc, int cand_cap) {
+  pdl_wait();
   __shared__ float S[NMS_S][NMS_S + 1];
   __shared__ float SS[NMS_S][NMS_S + 1];
   __shared__ unsigned char M[NMS_S][NMS_S + 4], SUP[NMS_S][NMS_S + 4];
@@ -561,6 +571,7 @@ __global__ void __launch_bounds__(256) k_dkd_nms(const float* __restrict__ score
 // K6a': upstream fallback - when nothing passes the threshold use the mean score instead.
 __global__ void __launch_bounds__(1024) k_dkd_fallback(const float* __restrict__ score, const float* __restrict__ nms,
                                                        int n, float* thr, int* dk, int* cand_idx, float* cand_sc, int cand_cap) {
+  pdl_wait();
   if (dk[0] != 0) return;
   __shared__ float red[32];
   __shared__ float mean_s;
@@ -589,6 +600,7 @@ __global__ void __launch_bounds__(1024) k_dkd_fallback(const float* __restrict__
 // K6b: radix select of the n_limit-th largest score key (single CTA).
 __global__ void __launch_bounds__(1024) k_dkd_select(const float* __restrict__ cand_sc, const int* __restrict__ cand_idx, int cand_cap,
                                                       int n_limit, int* dk) {
+  pdl_wait();
   __shared__ int hist[256];
   __shared__ unsigned prefix_s;
   __shared__ int krem_s;
@@ -669,6 +681,7 @@ __global__ void __launch_bounds__(1024) k_dkd_select(const float* __restrict__ c
 // K6c: gather the selected candidates (key > T, plus the first dk[2] ties by raster index).
 __global__ void __launch_bounds__(256) k_dkd_compact(const int* __restrict__ cand_idx, const float* __restrict__ cand_sc,
                                                      int* dk, int* __restrict__ sel_idx, float* __restrict__ sel_sc) {
+  pdl_wait();
   const int C = dk[0];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C) return;
@@ -695,32 +708,38 @@ struct RefineParams {
   int32_t* n_out;
 };
 
+constexpr int RF_KP = 32;     // keypoints per CTA: 8 threads rank one keypoint, one of them refines it
 __global__ void __launch_bounds__(256) k_dkd_refine(RefineParams p) {
+  pdl_wait();
   const int K = p.dk[4];
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e == 0) *p.n_out = K;
-  if (blockIdx.x * blockDim.x >= K) return;            // uniform per CTA
-  __shared__ int t_idx[256];
-  __shared__ float t_sc[256];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.n_out = K;
+  if (blockIdx.x * RF_KP >= K) return;                 // uniform per CTA
+  __shared__ int t_idx[1024];
+  __shared__ float t_sc[1024];
+  const int e = blockIdx.x * RF_KP + (threadIdx.x >> 3), sub = threadIdx.x & 7;
   const bool live = e < K;
   const int idx = live ? p.sel_idx[e] : 0;
   const float sc = live ? p.sel_sc[e] : 0.f;
   const bool trunc = p.dk[3] != 0;
   int rank = 0;
-  for (int j0 = 0; j0 < K; j0 += 256) {               // the selected list streams through shared memory
+  for (int j0 = 0; j0 < K; j0 += 1024) {               // the selected list streams through shared memory
     __syncthreads();
-    if (j0 + threadIdx.x < K) { t_idx[threadIdx.x] = p.sel_idx[j0 + threadIdx.x]; t_sc[threadIdx.x] = p.sel_sc[j0 + threadIdx.x]; }
+    for (int j = threadIdx.x; j < 1024 && j0 + j < K; j += 256) { t_idx[j] = p.sel_idx[j0 + j]; t_sc[j] = p.sel_sc[j0 + j]; }
     __syncthreads();
-    const int lim = min(256, K - j0);
+    const int lim = min(1024, K - j0);
     if (trunc) {
-      for (int j = 0; j < lim; ++j) {
+      for (int j = sub; j < lim; j += 8) {
         const float os = t_sc[j];
         rank += (os > sc || (os == sc && t_idx[j] < idx)) ? 1 : 0;
       }
     } else {
-      for (int j = 0; j < lim; ++j) rank += (t_idx[j] < idx) ? 1 : 0;
+      for (int j = sub; j < lim; j += 8) rank += (t_idx[j] < idx) ? 1 : 0;
     }
   }
+  rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+  rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+  rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+  if (sub != 0) return;
   if (!live) return;
   const int W = p.W, H = p.H;
   const int xi = idx % W, yi = idx / W;
@@ -773,6 +792,7 @@ __global__ void __launch_bounds__(256) k_dkd_refine(RefineParams p) {
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_sddh_patch(const float* __restrict__ feat, int H, int W, const float* __restrict__ kp_norm,
                                                     const int32_t* __restrict__ n_dev, float* __restrict__ A) {
+  pdl_wait();
   const int job = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int n = job / 9, tap = job % 9;
   if (n >= *n_dev) return;
@@ -789,6 +809,7 @@ __global__ void __launch_bounds__(256) k_sddh_patch(const float* __restrict__ fe
 __global__ void __launch_bounds__(256) k_sddh_sample(const float* __restrict__ feat, int H, int W, const float* __restrict__ kp_norm,
                                                      const float* __restrict__ offs /*[n][M][2]*/, int M,
                                                      const int32_t* __restrict__ n_dev, float* __restrict__ S) {
+  pdl_wait();
   const int job = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int n = job / M;
   if (n >= *n_dev) return;
@@ -817,6 +838,7 @@ __global__ void __launch_bounds__(256) k_sddh_sample(const float* __restrict__ f
 
 // F.normalize(desc, dim=1) (eps 1e-12).  warp per row of 128.
 __global__ void __launch_bounds__(256) k_desc_normalize(const float* __restrict__ raw, const int32_t* __restrict__ n_dev, float* __restrict__ out) {
+  pdl_wait();
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (n >= *n_dev) return;
   const int lane = threadIdx.x & 31;

@@ -1,4 +1,5 @@
 // api.cu - error reporting, weight-blob parsing and misc C-ABI entry points of libb200slam.
+#include <cstdlib>
 #include "common.cuh"
 
 #include <cstdarg>
@@ -6,6 +7,11 @@
 namespace b2s {
 
 static thread_local char g_err[1024] = "";
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = std::getenv("B2S_NO_PDL"); return !(e && e[0] == '1'); }();
+  return on;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

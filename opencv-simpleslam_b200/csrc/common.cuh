@@ -83,6 +83,31 @@ struct DeviceArena {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// Every kernel of the library is launched with programmatic stream serialization: it may become
+// resident (and run its prologue: barrier init, TMEM allocation, descriptor prefetch, weight
+// staging) while the previous kernel of the stream is still draining.  Device side: pdl_trigger()
+// lets the NEXT kernel start launching, pdl_wait() blocks until the PREVIOUS kernel has completed
+// and its memory is visible - it must precede the first access to any buffer another kernel writes
+// or reads (activations, workspaces, counters); constant weights may be read before it.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();   // B2S_NO_PDL=1 in the environment turns the launch attribute off (debugging)
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through B2S_LAUNCH_CHECK()
+}
+#endif
+
 // ---- per-kernel-class CUDA-event timing (bench.py's roofline.achieved is measured with it) --
 enum ProfClass { PROF_ATTN = 0, PROF_GEMM = 1, PROF_NCLASS = 2 };
 struct KernelProf {

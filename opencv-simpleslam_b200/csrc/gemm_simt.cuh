@@ -44,10 +44,33 @@ struct GemmParams {
   // in a fixed order (no atomics -> bitwise reproducible) before applying the epilogue.
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;
   int splitk = 1;
+  // LightGlue device-resident control (lightglue_kernels.cuh, LGC_*): sizes / early exit without host syncs
+  //   lg_mode 1: transformer-layer GEMM - exit when stopped or a side is empty; seg_rows[z] = ctrl[2 + z]
+  //   lg_mode 2: assignment projection - seg_rows from ctrl, runs after a stop too; W / bias of layer
+  //              ctrl[6] from w_tab / b_tab; A1 := A1_alt when that layer lives in the odd buffer
+  //   lg_mode 3: similarity - M = ctrl[2], N = ctrl[3]
+  const int* lg_ctrl = nullptr; int lg_mode = 0;
+  const float* const* w_tab = nullptr; const float* const* b_tab = nullptr; const float* A1_alt = nullptr;
 };
 
 template <int BM, int BN>
 __global__ void __launch_bounds__(256, (BM >= 128 ? 2 : 3)) k_gemm_simt(GemmParams p) {
+  pdl_wait();
+  if (p.lg_ctrl) {
+    const int* c = p.lg_ctrl;
+    if (c[2] <= 0 || c[3] <= 0) return;
+    if (p.lg_mode == 1) {
+      if (c[1]) return;
+      p.seg_rows[0] = c[2]; p.seg_rows[1] = c[3];
+    } else if (p.lg_mode == 2) {
+      p.seg_rows[0] = c[2]; p.seg_rows[1] = c[3];
+      const int last = c[6];
+      p.W = p.w_tab[last]; p.bias = p.b_tab[last];
+      if (p.A1_alt && (last & 1)) p.A1 = p.A1_alt;
+    } else {
+      p.M = c[2]; p.N = c[3];
+    }
+  }
   constexpr int BK = 16;
   constexpr int TM = BM / 16, TN = BN / 16;   // micro tile (8 or 4)
   constexpr int HM = TM / 2, HN = TN / 2;     // half tiles
@@ -191,6 +214,7 @@ __global__ void __launch_bounds__(256, (BM >= 128 ? 2 : 3)) k_gemm_simt(GemmPara
 
 // ordered reduction of the split-K partials + the usual epilogue (bias, alpha, residual, act, clamp)
 static __global__ void __launch_bounds__(256) k_gemm_splitk_epilogue(GemmParams p) {
+  pdl_wait();
   int rows = p.M;
   if (p.m_dev) rows = min(rows, *p.m_dev * p.m_mult);
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -228,9 +252,9 @@ inline int gemm_simt(const GemmParams& p, cudaStream_t st, long long* launches, 
     if (sk > 1) {
       q.splitk = sk;
       dim3 g(cdiv(q.N, 64), cdiv(maxrows, 64), sk);
-      k_gemm_simt<64, 64><<<g, 256, 0, st>>>(q);
+      launch_k(k_gemm_simt<64, 64>, g, 256, 0, st, q);
       const size_t total = (size_t)maxrows * q.N;
-      k_gemm_splitk_epilogue<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(q);
+      launch_k(k_gemm_splitk_epilogue, (unsigned)((total + 255) / 256), 256, 0, st, q);
       if (prof) prof->mark(PROF_GEMM, st);
       if (launches) *launches += 2;
       B2S_LAUNCH_CHECK();
@@ -239,10 +263,10 @@ inline int gemm_simt(const GemmParams& p, cudaStream_t st, long long* launches, 
   }
   if (big >= 148 && q.N >= 128) {
     dim3 g(cdiv(q.N, 128), cdiv(maxrows, 128), q.nseg);
-    k_gemm_simt<128, 128><<<g, 256, 0, st>>>(q);
+    launch_k(k_gemm_simt<128, 128>, g, 256, 0, st, q);
   } else {
     dim3 g(cdiv(q.N, 64), cdiv(maxrows, 64), q.nseg);
-    k_gemm_simt<64, 64><<<g, 256, 0, st>>>(q);
+    launch_k(k_gemm_simt<64, 64>, g, 256, 0, st, q);
   }
   if (prof) prof->mark(PROF_GEMM, st);
   if (launches) ++*launches;

@@ -21,6 +21,7 @@ struct TcGemmParams {
   __nv_bfloat16* out_bf16; int ld_bf16;     // TC_EPI_BF16 / ROTARY / RESID (bf16 copy)
   float* out_f32; int ld_f32;               // TC_EPI_F32 (plain) / RESID (in-place residual stream)
   const float* rot_cos; const float* rot_sin; int rot_cols;   // [rows,32] tables
+  const int* ctrl;                  // LightGlue device state (nullable): live rows = ctrl[2 + seg]; exit when stopped
 };
 
 template <int BN>
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
   const int tile_m = blockIdx.y, n0 = blockIdx.x * BN;
   const int seg = tile_m >= p.tiles0 ? 1 : 0;
   const int row0 = p.seg_base[seg] + (tile_m - (seg ? p.tiles0 : 0)) * Cfg::BM;       // global row of the tile
-  const int rows_live = p.seg_rows[seg] - (tile_m - (seg ? p.tiles0 : 0)) * Cfg::BM;  // live rows in this tile
+  int rows_live = p.seg_rows[seg] - (tile_m - (seg ? p.tiles0 : 0)) * Cfg::BM;        // live rows in this tile
   const int nkb = p.K / Cfg::BK;
 
   if (warp == 0 && lane == 0) {
@@ -62,12 +63,20 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc(tmem_slot, BN);
+  pdl_trigger();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();            // everything above overlaps the previous kernel's tail; operands are touched only below
+  if (p.ctrl) {          // device-resident sizes: pruning shrinks the segments, an early exit empties the layer
+    const bool on = !p.ctrl[1] && p.ctrl[2] > 0 && p.ctrl[3] > 0;
+    rows_live = on ? p.ctrl[2 + seg] - (tile_m - (seg ? p.tiles0 : 0)) * Cfg::BM : 0;
+  }
 
-  if (warp == 0) {
+  if (rows_live <= 0) {
+    // nothing to do for this tile (uniform per CTA)
+  } else if (warp == 0) {
     // ===== TMA producer =====
     if (tc::elect_one()) {
       for (int kb = 0; kb < nkb; ++kb) {

@@ -30,6 +30,8 @@ struct b2s_lg {
   float *qkv = nullptr, *ctx = nullptr, *msg = nullptr, *h1 = nullptr, *tok = nullptr, *sim = nullptr;
   float *rmax = nullptr, *rlog = nullptr, *cmax = nullptr, *clog = nullptr, *ls = nullptr, *max0 = nullptr;
   int *ind[2] = {nullptr, nullptr}, *keep = nullptr, *srcmap = nullptr, *m0 = nullptr, *m1 = nullptr, *ctrl = nullptr;
+  const float** wfinal_tab = nullptr; const float** bfinal_tab = nullptr; const float** wmatch_tab = nullptr;  // device tables [L]
+  float* bmatch_tab = nullptr;
   int *prune_scratch[2] = {nullptr, nullptr};
   int* h_ctrl = nullptr;  // pinned
   // host-API staging
@@ -82,10 +84,10 @@ static int lg_alloc_ws(b2s_lg* h, int cap) {
   B2S_TRY(h->wsarena.alloc(&h->srcmap, R));
   B2S_TRY(h->wsarena.alloc(&h->m0, (size_t)cap));
   B2S_TRY(h->wsarena.alloc(&h->m1, (size_t)cap));
-  B2S_TRY(h->wsarena.alloc(&h->ctrl, (size_t)8));
+  B2S_TRY(h->wsarena.alloc(&h->ctrl, (size_t)LGC_INTS));
   h->dbg_layers = nullptr;
   if (h->debug) B2S_TRY(h->wsarena.alloc(&h->dbg_layers, (size_t)h->cfg.n_layers * R * 256));
-  B2S_CUDA(cudaMemset(h->ctrl, 0, 8 * sizeof(int)));
+  B2S_CUDA(cudaMemset(h->ctrl, 0, LGC_INTS * sizeof(int)));
   if (h->tc) B2S_TRY(lgtc_alloc_ws(h->tc, cap));
   h->cap = cap;
   return 0;
@@ -183,7 +185,13 @@ extern "C" int b2s_lightglue_create(const b2s_lg_cfg* cfg, const void* weights, 
     double th = 0.8 + 0.1 * std::exp(-4.0 * i / cfg->n_layers);
     h->thr.push_back((float)std::min(1.0, std::max(0.0, th)));
   }
-  if (cudaMallocHost((void**)&h->h_ctrl, 8 * sizeof(int)) != cudaSuccess) { set_error("cudaMallocHost failed"); return fail(B2S_ENOMEM); }
+  {
+    std::vector<const float*> wf, bf, wm; std::vector<float> bm;
+    for (const LgLayer& l : h->L) { wf.push_back(l.wfinal); bf.push_back(l.bfinal); wm.push_back(l.wmatch); bm.push_back(l.bmatch); }
+    if ((rc = h->warena.upload(&h->wfinal_tab, wf)) || (rc = h->warena.upload(&h->bfinal_tab, bf)) ||
+        (rc = h->warena.upload(&h->wmatch_tab, wm)) || (rc = h->warena.upload(&h->bmatch_tab, bm))) return fail(rc);
+  }
+  if (cudaMallocHost((void**)&h->h_ctrl, LGC_INTS * sizeof(int)) != cudaSuccess) { set_error("cudaMallocHost failed"); return fail(B2S_ENOMEM); }
   cudaFuncSetAttribute(k_attn_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
   if (cfg->precision == B2S_BF16) {
     if ((rc = lgtc_create(&h->tc, h->L.size()))) return fail(rc);
@@ -230,7 +238,7 @@ extern "C" int b2s_lg_set_debug(b2s_lg* h, int on) {
   return lg_alloc_ws(h, h->cap);
 }
 
-// one Linear over both images' live rows
+// one Linear over both images' live rows (m, n = upper bounds; live counts come from h->ctrl)
 static int lg_linear(b2s_lg* h, cudaStream_t st, const float* A1, int lda1, int K1, const float* A2, int lda2,
                      const float* W, int K, int N, const float* bias, float* C, int ldc, int m, int n,
                      const float* residual, int ldr, float alpha = 1.f) {
@@ -239,14 +247,16 @@ static int lg_linear(b2s_lg* h, cudaStream_t st, const float* A1, int lda1, int 
   g.W = W; g.ldw = K; g.C = C; g.ldc = ldc; g.N = N; g.K = K;
   g.nseg = 2; g.seg_base[0] = 0; g.seg_base[1] = h->cap; g.seg_rows[0] = m; g.seg_rows[1] = n;
   g.bias = bias; g.alpha = alpha; g.residual = residual; g.ldr = ldr;
+  g.lg_ctrl = h->ctrl; g.lg_mode = 1;
   return gemm_simt(g, st, &h->launches, &h->prof);
 }
 
-static int lg_attention(b2s_lg* h, cudaStream_t st, const AttnParams& ap, int maxq) {
+static int lg_attention(b2s_lg* h, cudaStream_t st, AttnParams ap, int cross, int maxq) {
   if (maxq <= 0) return 0;
+  ap.ctrl = h->ctrl; ap.cross = cross;
   dim3 grid(cdiv(maxq, ATT_B), 4, 2);
   h->prof.mark(PROF_ATTN, st);
-  k_attn_fp32<<<grid, 256, ATT_SMEM, st>>>(ap);
+  launch_k(k_attn_fp32, grid, 256, ATT_SMEM, st, ap);
   h->prof.mark(PROF_ATTN, st);
   ++h->launches;
   B2S_LAUNCH_CHECK();
@@ -259,7 +269,7 @@ static int lg_ffn(b2s_lg* h, cudaStream_t st, float* x, const float* msg, const 
   B2S_TRY(lg_linear(h, st, x, 256, 256, msg, 256, w1, 512, 512, b1, h->h1, 512, m, n, nullptr, 0));
   RowSeg seg = {{0, h->cap}, {m, n}};
   dim3 grid(cdiv(std::max(m, n), 8), 2);
-  k_ln_gelu_512<<<grid, 256, 0, st>>>(h->h1, seg, lng, lnb);
+  launch_k(k_ln_gelu_512, grid, 256, 0, st, h->h1, seg, lng, lnb, (const int*)h->ctrl);
   ++h->launches;
   B2S_LAUNCH_CHECK();
   return lg_linear(h, st, h->h1, 512, 512, nullptr, 0, w2, 512, 256, b2, x, 256, m, n, x, 256);
@@ -275,6 +285,7 @@ static int lg_layer_fp32(b2s_lg* h, cudaStream_t st, int li, int cur, int m, int
     g.A1 = x; g.lda1 = 256; g.K1 = 256; g.W = l.wqkv; g.ldw = 256; g.C = h->qkv; g.ldc = 768; g.N = 768; g.K = 256;
     g.nseg = 2; g.seg_base[0] = 0; g.seg_base[1] = cap; g.seg_rows[0] = m; g.seg_rows[1] = n;
     g.bias = l.bqkv; g.rot_cols = 512; g.rot_cos = h->cosb[cur]; g.rot_sin = h->sinb[cur];
+    g.lg_ctrl = h->ctrl; g.lg_mode = 1;
     B2S_TRY(gemm_simt(g, st, &h->launches, &h->prof));
   }
   AttnParams ap;
@@ -282,7 +293,7 @@ static int lg_layer_fp32(b2s_lg* h, cudaStream_t st, int li, int cur, int m, int
   ap.prob[0] = {h->qkv, h->qkv + 256, h->qkv + 512, h->ctx, m, m};
   ap.prob[1] = {h->qkv + (size_t)cap * 768, h->qkv + (size_t)cap * 768 + 256, h->qkv + (size_t)cap * 768 + 512,
                 h->ctx + (size_t)cap * 256, n, n};
-  B2S_TRY(lg_attention(h, st, ap, std::max(m, n)));
+  B2S_TRY(lg_attention(h, st, ap, 0, std::max(m, n)));
   B2S_TRY(lg_linear(h, st, h->ctx, 256, 256, nullptr, 0, l.wo, 256, 256, l.bo, h->msg, 256, m, n, nullptr, 0));
   B2S_TRY(lg_ffn(h, st, x, h->msg, l.w1, l.b1, l.lng, l.lnb, l.w2, l.b2, m, n));
   // ---- cross block ----
@@ -291,7 +302,7 @@ static int lg_layer_fp32(b2s_lg* h, cudaStream_t st, int li, int cur, int m, int
   float* q0 = h->qkv; float* q1 = h->qkv + (size_t)cap * 512;
   ap.prob[0] = {q0, q1, q1 + 256, h->ctx, m, n};
   ap.prob[1] = {q1, q0, q0 + 256, h->ctx + (size_t)cap * 256, n, m};
-  B2S_TRY(lg_attention(h, st, ap, std::max(m, n)));
+  B2S_TRY(lg_attention(h, st, ap, 1, std::max(m, n)));
   B2S_TRY(lg_linear(h, st, h->ctx, 256, 256, nullptr, 0, l.cwo, 256, 256, l.cbo, h->msg, 256, m, n, nullptr, 0));
   B2S_TRY(lg_ffn(h, st, x, h->msg, l.cw1, l.cb1, l.clng, l.clnb, l.cw2, l.cb2, m, n));
   return 0;
@@ -299,19 +310,22 @@ static int lg_layer_fp32(b2s_lg* h, cudaStream_t st, int li, int cur, int m, int
 
 static int fill_i32(b2s_lg* h, cudaStream_t st, int32_t* p, int n, int32_t v) {
   if (!p || n <= 0) return 0;
-  k_fill_i32<<<cdiv(n, 256), 256, 0, st>>>(p, n, v);
+  launch_k(k_fill_i32, cdiv(n, 256), 256, 0, st, p, n, v);
   ++h->launches;
   B2S_LAUNCH_CHECK();
   return 0;
 }
 static int fill_f32(b2s_lg* h, cudaStream_t st, float* p, int n, float v) {
   if (!p || n <= 0) return 0;
-  k_fill_f32<<<cdiv(n, 256), 256, 0, st>>>(p, n, v);
+  launch_k(k_fill_f32, cdiv(n, 256), 256, 0, st, p, n, v);
   ++h->launches;
   B2S_LAUNCH_CHECK();
   return 0;
 }
 
+// The whole match is enqueued without a single host synchronisation: the adaptive-depth exit test
+// and the adaptive-width pruning (upstream decides both on the host after every layer) are taken
+// on the device; kernels of layers behind an exit find the stop flag set and return at once.
 extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, int m, const float* k1,
                                    const float* d1, int n, const float* size0, const float* size1, void* stream,
                                    int32_t* matches, float* mscores, int32_t* n_matches, int32_t* stop_layer,
@@ -335,7 +349,7 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
   if (m == 0 || n == 0) {
     B2S_CUDA(cudaMemsetAsync(n_matches, 0, sizeof(int32_t), st));
     if (do_prune) { B2S_TRY(fill_i32(h, st, prune0, m, 1)); B2S_TRY(fill_i32(h, st, prune1, n, 1)); }
-    if (stop_layer) *stop_layer = 1;
+    B2S_TRY(fill_i32(h, st, stop_layer, 1, 1));
     return 0;
   }
   if (std::max(m, n) > h->cap) {
@@ -343,7 +357,8 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
     B2S_TRY(lg_alloc_ws(h, std::max(m, n)));
   }
   const int cap = h->cap;
-  int cur = 0;
+  int* pr0 = do_prune ? (prune0 ? prune0 : h->prune_scratch[0]) : nullptr;
+  int* pr1 = do_prune ? (prune1 ? prune1 : h->prune_scratch[1]) : nullptr;
   {
     PosencParams pp;
     pp.kp[0] = k0; pp.kp[1] = k1; pp.n[0] = m; pp.n[1] = n; pp.base[0] = 0; pp.base[1] = cap;
@@ -351,14 +366,12 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
     pp.size[0][0] = size0 ? size0[0] : 0.f; pp.size[0][1] = size0 ? size0[1] : 0.f;
     pp.size[1][0] = size1 ? size1[0] : 0.f; pp.size[1][1] = size1 ? size1[1] : 0.f;
     pp.Wr = h->wr; pp.kn = h->kn; pp.cosb = h->cosb[0]; pp.sinb = h->sinb[0]; pp.ind = h->ind[0];
-    pp.prune[0] = do_prune ? (prune0 ? prune0 : h->prune_scratch[0]) : nullptr;
-    pp.prune[1] = do_prune ? (prune1 ? prune1 : h->prune_scratch[1]) : nullptr;
-    k_lg_posenc<<<dim3(cdiv(std::max(m, n), 64), 2), 256, 0, st>>>(pp);
+    pp.prune[0] = pr0; pp.prune[1] = pr1;
+    pp.ctrl = h->ctrl; pp.last_init = (do_stop || do_prune) ? 0 : L - 1;
+    launch_k(k_lg_posenc, dim3(cdiv(std::max(m, n), 64), 2), 256, 0, st, pp);
     ++h->launches;
     B2S_LAUNCH_CHECK();
   }
-  int* pr0 = do_prune ? (prune0 ? prune0 : h->prune_scratch[0]) : nullptr;
-  int* pr1 = do_prune ? (prune1 ? prune1 : h->prune_scratch[1]) : nullptr;
   // input projection (two sources -> rows 0.. and cap..)
   for (int s = 0; s < 2; ++s) {
     GemmParams g;
@@ -366,75 +379,72 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
     g.C = h->x[0] + (size_t)(s ? cap : 0) * 256; g.ldc = 256; g.M = s ? n : m; g.bias = h->in_b;
     B2S_TRY(gemm_simt(g, st, &h->launches));
   }
-  int mc = m, nc = n, last = 0;
   h->dbg_nlayers = 0;
+  // with pruning enabled layer i lives in ping-pong buffer i & 1 (the gather after layer i moves the
+  // survivors across); without it everything stays in buffer 0
+  auto buf_of = [&](int i) { return do_prune ? (i & 1) : 0; };
   for (int i = 0; i < L; ++i) {
-    last = i;
-    if (h->tc) B2S_TRY(lgtc_layer(h->tc, st, i, h->x[cur], h->cosb[cur], h->sinb[cur], cap, mc, nc, &h->launches));
-    else B2S_TRY(lg_layer_fp32(h, st, i, cur, mc, nc));
-    if (h->debug && h->dbg_layers) {
+    const int cur = buf_of(i);
+    if (h->tc) B2S_TRY(lgtc_layer(h->tc, st, i, h->x[cur], h->cosb[cur], h->sinb[cur], cap, m, n, h->ctrl, i == 0, &h->launches));
+    else B2S_TRY(lg_layer_fp32(h, st, i, cur, m, n));
+    if (h->debug && h->dbg_layers) {   // debug only: snapshot the layer output and its live sizes (host sync)
       B2S_CUDA(cudaMemcpyAsync(h->dbg_layers + (size_t)i * 2 * cap * 256, h->x[cur], (size_t)2 * cap * 256 * sizeof(float),
                                cudaMemcpyDeviceToDevice, st));
-      h->dbg_m[i] = mc; h->dbg_n[i] = nc; h->dbg_nlayers = i + 1;
+      B2S_CUDA(cudaMemcpyAsync(h->h_ctrl, h->ctrl, LGC_INTS * sizeof(int), cudaMemcpyDeviceToHost, st));
+      B2S_CUDA(cudaStreamSynchronize(st));
+      if (!h->h_ctrl[LGC_STOP] && h->h_ctrl[LGC_M] > 0 && h->h_ctrl[LGC_N] > 0) {
+        h->dbg_m[i] = h->h_ctrl[LGC_M]; h->dbg_n[i] = h->h_ctrl[LGC_N]; h->dbg_nlayers = i + 1;
+      }
     }
-    if (i == L - 1) break;
-    const bool can0 = do_prune && mc > h->cfg.pruning_min_kpts;
-    const bool can1 = do_prune && nc > h->cfg.pruning_min_kpts;
-    if (!do_stop && !can0 && !can1) continue;
+    if (i == L - 1 || (!do_stop && !do_prune)) continue;
     const LgLayer& l = h->L[i];
-    HeadParams hp;
-    hp.x = h->x[cur]; hp.seg = {{0, cap}, {mc, nc}};
+    HeadParams hp = {};
+    hp.x = h->x[cur]; hp.seg = {{0, cap}, {m, n}};
     hp.wt = l.wtok; hp.bt = l.btok; hp.wm = l.wmatch; hp.bm = l.bmatch;
     hp.thr = h->thr[i]; // upstream: scores > (1 - width_confidence) with a python double; undo the float rounding of the cfg
     hp.keep_thr = (float)(1.0 - std::round((double)h->cfg.width_conf * 1e6) / 1e6);
-    hp.use_tok = do_stop; hp.use_match = (can0 || can1);
-    hp.tok = h->tok; hp.keep = h->keep; hp.ctrl = h->ctrl; hp.ls_pos = nullptr;
-    dim3 hg(cdiv(std::max(mc, nc), 8), 2);
-    k_lg_heads<<<hg, 256, 0, st>>>(hp);
-    k_lg_decide<<<1, 32, 0, st>>>(h->ctrl, m + n, h->cfg.depth_conf, do_stop ? 1 : 0);
+    hp.use_tok = do_stop; hp.use_match = do_prune;
+    hp.tok = h->tok; hp.keep = h->keep; hp.ctrl = h->ctrl; hp.layer = i; hp.ls_pos = nullptr;
+    dim3 hg(cdiv(std::max(m, n), 8), 2);
+    launch_k(k_lg_heads, hg, 256, 0, st, hp);
+    ScanParams sp;
+    sp.keep = h->keep; sp.srcmap = h->srcmap; sp.ctrl = h->ctrl; sp.base[0] = 0; sp.base[1] = cap;
+    sp.layer = i; sp.num_points = m + n; sp.do_stop = do_stop ? 1 : 0; sp.do_prune = do_prune ? 1 : 0;
+    sp.pruning_min_kpts = h->cfg.pruning_min_kpts; sp.depth_conf = h->cfg.depth_conf;
+    launch_k(k_lg_prune_scan, 2, 1024, 0, st, sp);
     h->launches += 2;
     B2S_LAUNCH_CHECK();
-    if (can0 || can1) {
-      ScanParams sp;
-      sp.keep = h->keep; sp.srcmap = h->srcmap; sp.ctrl = h->ctrl;
-      sp.base[0] = 0; sp.base[1] = cap; sp.rows[0] = mc; sp.rows[1] = nc; sp.can_prune[0] = can0; sp.can_prune[1] = can1;
-      k_lg_prune_scan<<<2, 1024, 0, st>>>(sp);
+    if (do_prune) {
+      const int nxt = cur ^ 1;
       GatherParams gp;
-      gp.srcmap = h->srcmap; gp.ctrl = h->ctrl; gp.base[0] = 0; gp.base[1] = cap; gp.rows[0] = mc; gp.rows[1] = nc;
-      gp.x_in = h->x[cur]; gp.x_out = h->x[cur ^ 1]; gp.cos_in = h->cosb[cur]; gp.cos_out = h->cosb[cur ^ 1];
-      gp.sin_in = h->sinb[cur]; gp.sin_out = h->sinb[cur ^ 1]; gp.ind_in = h->ind[cur]; gp.ind_out = h->ind[cur ^ 1];
-      gp.prune[0] = pr0; gp.prune[1] = pr1; gp.can_prune[0] = can0; gp.can_prune[1] = can1;
-      dim3 gg(cdiv(std::max(mc, nc), 8), 2);
-      k_lg_gather<<<gg, 256, 0, st>>>(gp);
-      h->launches += 2;
+      gp.srcmap = h->srcmap; gp.ctrl = h->ctrl; gp.base[0] = 0; gp.base[1] = cap;
+      gp.x_in = h->x[cur]; gp.x_out = h->x[nxt]; gp.cos_in = h->cosb[cur]; gp.cos_out = h->cosb[nxt];
+      gp.sin_in = h->sinb[cur]; gp.sin_out = h->sinb[nxt]; gp.ind_in = h->ind[cur]; gp.ind_out = h->ind[nxt];
+      gp.prune[0] = pr0; gp.prune[1] = pr1;
+      gp.xb_out = h->tc ? lgtc_xb(h->tc) : nullptr;
+      launch_k(k_lg_gather, dim3(cdiv(std::max(m, n), 8), 2), 256, 0, st, gp);
+      ++h->launches;
       B2S_LAUNCH_CHECK();
     }
-    // upstream takes these decisions on the host too (check_if_stop / shape change)
-    B2S_CUDA(cudaMemcpyAsync(h->h_ctrl, h->ctrl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    B2S_CUDA(cudaStreamSynchronize(st));
-    if (h->h_ctrl[1]) break;  // early exit: keep this layer's (unpruned) state
-    if (can0 || can1) {
-      cur ^= 1;
-      mc = h->h_ctrl[2]; nc = h->h_ctrl[3];
-      if (mc == 0 || nc == 0) break;
-    }
   }
-  if (stop_layer) *stop_layer = last + 1;
-  if (mc == 0 || nc == 0) {
-    B2S_CUDA(cudaMemsetAsync(n_matches, 0, sizeof(int32_t), st));
-    return 0;
-  }
-  // ---- assignment with the last executed layer's heads (K14/K15) ----
-  const LgLayer& l = h->L[last];
+  // ---- assignment with the last executed layer's heads (K14/K15); that layer index, its buffer and the
+  //      live sizes are device-side values ----
   float* md = h->qkv;  // [2*cap, 256]
-  B2S_TRY(lg_linear(h, st, h->x[cur], 256, 256, nullptr, 0, l.wfinal, 256, 256, l.bfinal, md, 256, mc, nc, nullptr, 0, 0.25f));
   {
-    HeadParams hp;
-    hp.x = h->x[cur]; hp.seg = {{0, cap}, {mc, nc}};
-    hp.wt = nullptr; hp.bt = 0.f; hp.wm = l.wmatch; hp.bm = l.bmatch; hp.thr = 0.f; hp.keep_thr = 0.f;
-    hp.use_tok = 0; hp.use_match = 0; hp.tok = nullptr; hp.keep = nullptr; hp.ctrl = nullptr; hp.ls_pos = h->ls;
-    dim3 hg(cdiv(std::max(mc, nc), 8), 2);
-    k_lg_heads<<<hg, 256, 0, st>>>(hp);
+    GemmParams g;
+    g.A1 = h->x[0]; g.lda1 = 256; g.K1 = 256; g.A1_alt = do_prune ? h->x[1] : nullptr;
+    g.W = h->L[L - 1].wfinal; g.ldw = 256; g.K = 256; g.N = 256; g.bias = h->L[L - 1].bfinal; g.alpha = 0.25f;
+    g.C = md; g.ldc = 256;
+    g.nseg = 2; g.seg_base[0] = 0; g.seg_base[1] = cap; g.seg_rows[0] = m; g.seg_rows[1] = n;
+    g.lg_ctrl = h->ctrl; g.lg_mode = 2; g.w_tab = h->wfinal_tab; g.b_tab = h->bfinal_tab;
+    B2S_TRY(gemm_simt(g, st, &h->launches, &h->prof));
+  }
+  {
+    HeadParams hp = {};
+    hp.x = h->x[0]; hp.x_alt = do_prune ? h->x[1] : nullptr; hp.seg = {{0, cap}, {m, n}};
+    hp.wm_tab = h->wmatch_tab; hp.bm_tab = h->bmatch_tab; hp.ctrl = h->ctrl; hp.ls_pos = h->ls;
+    dim3 hg(cdiv(std::max(m, n), 8), 2);
+    launch_k(k_lg_heads, hg, 256, 0, st, hp);
     ++h->launches;
     B2S_LAUNCH_CHECK();
   }
@@ -442,22 +452,29 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
   {
     GemmParams g;
     g.A1 = md; g.lda1 = 256; g.K1 = 256; g.W = md + (size_t)cap * 256; g.ldw = 256; g.K = 256;
-    g.M = mc; g.N = nc; g.C = h->sim; g.ldc = ld;
+    g.M = m; g.N = n; g.C = h->sim; g.ldc = ld;
+    g.lg_ctrl = h->ctrl; g.lg_mode = 3;
     B2S_TRY(gemm_simt(g, st, &h->launches));
   }
-  h->dbg_simm = mc; h->dbg_simn = nc;
-  k_lg_row_lse<<<cdiv(mc, 8), 256, 0, st>>>(h->sim, ld, mc, nc, h->rmax, h->rlog);
-  k_lg_col_lse<<<cdiv(nc, 32), 1024, 0, st>>>(h->sim, ld, mc, nc, h->cmax, h->clog);
-  k_lg_row_argmax<<<cdiv(mc, 8), 256, 0, st>>>(h->sim, ld, mc, nc, h->rmax, h->rlog, h->cmax, h->clog, h->ls, h->ls + cap, h->max0, h->m0);
-  k_lg_col_argmax<<<cdiv(nc, 32), 1024, 0, st>>>(h->sim, ld, mc, nc, h->rmax, h->rlog, h->cmax, h->clog, h->ls, h->ls + cap, h->m1);
-  FilterParams fp;
-  fp.m = mc; fp.n = nc; fp.th = h->cfg.filter_thresh; fp.max0 = h->max0; fp.m0 = h->m0; fp.m1 = h->m1;
-  fp.ind0 = h->ind[cur]; fp.ind1 = h->ind[cur] + cap;
+  const int* ctrl = h->ctrl;
+  launch_k(k_lg_row_lse, cdiv(m, 8), 256, 0, st, h->sim, ld, ctrl, h->rmax, h->rlog);
+  launch_k(k_lg_col_lse, cdiv(n, 32), 1024, 0, st, h->sim, ld, ctrl, h->cmax, h->clog);
+  launch_k(k_lg_row_argmax, cdiv(m, 8), 256, 0, st, h->sim, ld, ctrl, h->rmax, h->rlog, h->cmax, h->clog, h->ls, h->ls + cap, h->max0, h->m0);
+  launch_k(k_lg_col_argmax, cdiv(n, 32), 1024, 0, st, h->sim, ld, ctrl, h->rmax, h->rlog, h->cmax, h->clog, h->ls, h->ls + cap, h->m1);
+  FilterParams fp = {};
+  fp.th = h->cfg.filter_thresh; fp.max0 = h->max0; fp.m0 = h->m0; fp.m1 = h->m1;
+  fp.ctrl = h->ctrl; fp.cap = cap; fp.stop_layer = stop_layer;
+  fp.ind0 = h->ind[0]; fp.ind1 = h->ind[0] + cap; fp.ind_alt = do_prune ? h->ind[1] : nullptr;
   fp.matches = matches; fp.mscores = mscores; fp.n_matches = n_matches;
   fp.matches0 = matches0; fp.matches1 = matches1; fp.ms0 = ms0; fp.ms1 = ms1;
-  k_lg_filter<<<1, 1024, 0, st>>>(fp);
+  launch_k(k_lg_filter, 1, 1024, 0, st, fp);
   h->launches += 5;
   B2S_LAUNCH_CHECK();
+  if (h->debug) {
+    B2S_CUDA(cudaMemcpyAsync(h->h_ctrl, h->ctrl, LGC_INTS * sizeof(int), cudaMemcpyDeviceToHost, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    h->dbg_simm = h->h_ctrl[LGC_M]; h->dbg_simn = h->h_ctrl[LGC_N];
+  }
   return 0;
 }
 
@@ -498,12 +515,13 @@ extern "C" int b2s_lightglue_match_host(b2s_lg* h, const float* k0, const float*
     B2S_CUDA(cudaMemcpyAsync(h->hd[1], d1, (size_t)n * 128 * sizeof(float), cudaMemcpyHostToDevice, st));
   }
   B2S_TRY(b2s_lightglue_match(h, h->hk[0], h->hd[0], m, h->hk[1], h->hd[1], n, size0, size1, st, h->hmatches,
-                              h->hmscores, h->hnm, stop_layer, h->hm[0], h->hm[1], h->hms[0], h->hms[1],
+                              h->hmscores, h->hnm, h->hnm + 1, h->hm[0], h->hm[1], h->hms[0], h->hms[1],
                               h->hprune[0], h->hprune[1]));
-  int32_t nm = 0;
-  B2S_CUDA(cudaMemcpyAsync(&nm, h->hnm, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  B2S_CUDA(cudaMemcpyAsync(h->h_ctrl, h->hnm, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));   // pinned: n_matches, stop
   B2S_CUDA(cudaStreamSynchronize(st));
+  const int32_t nm = h->h_ctrl[0];
   *n_matches = nm;
+  if (stop_layer) *stop_layer = h->h_ctrl[1];
   if (nm > 0) {
     if (matches) B2S_CUDA(cudaMemcpyAsync(matches, h->hmatches, (size_t)nm * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (mscores) B2S_CUDA(cudaMemcpyAsync(mscores, h->hmscores, (size_t)nm * sizeof(float), cudaMemcpyDeviceToHost, st));

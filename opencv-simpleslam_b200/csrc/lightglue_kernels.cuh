@@ -3,9 +3,17 @@
 // LayerNorm+GELU, token-confidence / matchability heads, point-pruning compaction, dual
 // log-softmax assignment, mutual-NN filter.  Upstream spec: SURVEY.md Appendix A.3.
 #pragma once
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace b2s {
+
+// Device-resident matcher state (ints): adaptive depth / width decisions never visit the host.
+//   [LGC_STOP] early-exit flag (sticky)   [LGC_M],[LGC_N] live points of image 0 / 1
+//   [LGC_CAN0],[LGC_CAN1] this layer's prune-eligibility per side   [LGC_LAST] last executed layer
+//   [LGC_UNCONF + i] #(token confidence < thr_i) after layer i
+enum { LGC_STOP = 1, LGC_M = 2, LGC_N = 3, LGC_CAN0 = 4, LGC_CAN1 = 5, LGC_LAST = 6, LGC_UNCONF = 8, LGC_INTS = 32 };
+__device__ __forceinline__ bool lg_active(const int* c) { return !c[LGC_STOP] && c[LGC_M] > 0 && c[LGC_N] > 0; }
 
 // ---------------------------------------------------------------------------------------
 // K9: normalize_keypoints + posenc.  grid = (ceil(max n / 64), 2 images), block = 256.
@@ -20,12 +28,18 @@ struct PosencParams {
   float* cosb; float* sinb;  // [rows,32]
   int* ind;                  // [rows]  identity index map
   int* prune[2];             // per image [n] (nullable) -> 1
+  int* ctrl; int last_init;  // device state, reset here (last_init = L-1 when depth/width adaptivity is off)
 };
 
 __global__ void __launch_bounds__(256) k_lg_posenc(PosencParams p) {
+  pdl_wait();
   const int s = blockIdx.y;   // image; blockIdx.x = chunk of 64 points (every CTA re-derives the extent)
   const int n = p.n[s];
   const float* kp = p.kp[s];
+  if (blockIdx.x == 0 && s == 0 && threadIdx.x < LGC_INTS) {
+    const int t = threadIdx.x;
+    p.ctrl[t] = t == LGC_M ? p.n[0] : t == LGC_N ? p.n[1] : t == LGC_LAST ? p.last_init : 0;
+  }
   __shared__ float red[4][8];
   __shared__ float sh_shift[2], sh_scale;
   float sx, sy;
@@ -76,19 +90,25 @@ __global__ void __launch_bounds__(256) k_lg_posenc(PosencParams p) {
 // Thread (ty,tx) of a 16x16 grid owns S[ty*4..+4][tx*4..+4] and O[ty*4..+4][tx*4..+4].
 // ---------------------------------------------------------------------------------------
 struct AttnProb { const float* Q; const float* K; const float* V; float* O; int nq, nk; };
-struct AttnParams { AttnProb prob[2]; int ldq, ldk, ldv, ldo; float scale; };
+struct AttnParams { AttnProb prob[2]; int ldq, ldk, ldv, ldo; float scale; const int* ctrl; int cross; };
 
 constexpr int ATT_B = 64, ATT_D = 64, ATT_LD = 68;
 constexpr int ATT_SMEM = 4 * ATT_B * ATT_LD * (int)sizeof(float);
 
 __global__ void __launch_bounds__(256) k_attn_fp32(AttnParams p) {
+  pdl_wait();
   extern __shared__ __align__(16) float att_smem[];
   float (*Qs)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem);                       // [d][q]
   float (*Ks)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem + ATT_B * ATT_LD);      // [d][k]
   float (*Vs)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem + 2 * ATT_B * ATT_LD);  // [k][d]
   float (*Ps)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem + 3 * ATT_B * ATT_LD);  // [k][q]
 
-  const AttnProb pr = p.prob[blockIdx.z];
+  AttnProb pr = p.prob[blockIdx.z];
+  if (p.ctrl) {             // live sizes come from the device state (pruning / early exit)
+    if (!lg_active(p.ctrl)) return;
+    pr.nq = p.ctrl[LGC_M + blockIdx.z];
+    pr.nk = p.ctrl[LGC_M + (p.cross ? 1 - blockIdx.z : blockIdx.z)];
+  }
   const int q0 = blockIdx.x * ATT_B;
   if (q0 >= pr.nq) return;
   const int hoff = blockIdx.y * ATT_D;
@@ -194,9 +214,11 @@ __global__ void __launch_bounds__(256) k_attn_fp32(AttnParams p) {
 // ---------------------------------------------------------------------------------------
 struct RowSeg { int base[2]; int rows[2]; };
 
-__global__ void __launch_bounds__(256) k_ln_gelu_512(float* h, RowSeg seg, const float* gamma, const float* beta) {
+__global__ void __launch_bounds__(256) k_ln_gelu_512(float* h, RowSeg seg, const float* gamma, const float* beta, const int* ctrl) {
+  pdl_wait();
   const int s = blockIdx.y;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (ctrl) { if (!lg_active(ctrl)) return; seg.rows[s] = ctrl[LGC_M + s]; }
   if (row >= seg.rows[s]) return;
   const int lane = threadIdx.x & 31;
   float* x = h + (size_t)(seg.base[s] + row) * 512;
@@ -239,13 +261,26 @@ struct HeadParams {
   const float* x; RowSeg seg;
   const float* wt; float bt; const float* wm; float bm;
   float thr; float keep_thr; int use_tok; int use_match;
-  float* tok; int* keep; int* ctrl;
-  float* ls_pos;   // if set: write logsigmoid(wm.x+bm) and nothing else
+  float* tok; int* keep; int* ctrl; int layer;
+  float* ls_pos;   // if set (assignment mode): write logsigmoid(wm.x+bm) and nothing else; the
+                   // matchability head of layer ctrl[LGC_LAST] comes from wm_tab / bm_tab and the
+                   // state from x_alt when that layer lives in the odd ping-pong buffer
+  const float* const* wm_tab; const float* bm_tab; const float* x_alt;
 };
 
 __global__ void __launch_bounds__(256) k_lg_heads(HeadParams p) {
+  pdl_wait();
   const int s = blockIdx.y;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (p.ls_pos) {
+    if (p.ctrl[LGC_M] <= 0 || p.ctrl[LGC_N] <= 0) return;
+    const int last = p.ctrl[LGC_LAST];
+    p.wm = p.wm_tab[last]; p.bm = p.bm_tab[last];
+    if (p.x_alt && (last & 1)) p.x = p.x_alt;
+  } else if (!lg_active(p.ctrl)) {
+    return;
+  }
+  p.seg.rows[s] = p.ctrl[LGC_M + s];
   if (row >= p.seg.rows[s]) return;
   const int lane = threadIdx.x & 31;
   const int r = p.seg.base[s] + row;
@@ -272,33 +307,40 @@ __global__ void __launch_bounds__(256) k_lg_heads(HeadParams p) {
   if (p.use_tok) {
     const float t = sigmoid_f(dt + p.bt);
     p.tok[r] = t;
-    if (t < p.thr) atomicAdd(&p.ctrl[0], 1);
+    if (t < p.thr) atomicAdd(&p.ctrl[LGC_UNCONF + p.layer], 1);
     keep = keep || (t <= p.thr);
   }
   p.keep[r] = keep ? 1 : 0;
 }
 
-// ctrl layout: [0]=#unconfident  [1]=stop flag  [2]=count0  [3]=count1  [4]=n_matches
-__global__ void k_lg_decide(int* ctrl, int num_points, float depth_conf, int do_stop) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    int stop = 0;
-    if (do_stop) {
-      const float ratio = 1.0f - (float)ctrl[0] / (float)num_points;
-      stop = ratio > depth_conf ? 1 : 0;
-    }
-    ctrl[1] = stop;
-    ctrl[0] = 0;
-  }
-}
-
-// order-preserving compaction map.  grid = 2, block = 1024.  srcmap[base + dst] = src.
-// A side that must not be pruned (stop fired / below the pruning threshold) gets the identity.
-struct ScanParams { const int* keep; int* srcmap; int* ctrl; int base[2]; int rows[2]; int can_prune[2]; };
+// After layer i: early-exit test (upstream check_if_stop) and the order-preserving compaction map of
+// the points that survive pruning (upstream get_pruning_mask).  grid = 2 (one CTA per image), block = 1024.
+//   stop  <=> 1 - #unconfident / (m + n) > depth_conf, m + n = ORIGINAL counts (pruned points count as confident)
+//   srcmap[base + dst] = src.  A side that is not eligible (count <= pruning_min_kpts) keeps every point.
+// On stop nothing else is written: the state stays in this layer's buffer and LGC_LAST stays i.
+struct ScanParams {
+  const int* keep; int* srcmap; int* ctrl; int base[2];
+  int layer, num_points, do_stop, do_prune, pruning_min_kpts; float depth_conf;
+};
 
 __global__ void __launch_bounds__(1024) k_lg_prune_scan(ScanParams p) {
+  pdl_wait();
   const int s = blockIdx.x;
-  const int n = p.rows[s], base = p.base[s];
-  const bool prune = p.can_prune[s] && (p.ctrl[1] == 0);
+  __shared__ int sh_go, sh_n;
+  if (threadIdx.x == 0) {
+    int go = lg_active(p.ctrl) ? 1 : 0;
+    if (go && p.do_stop) {
+      const float ratio = 1.0f - (float)p.ctrl[LGC_UNCONF + p.layer] / (float)p.num_points;
+      if (ratio > p.depth_conf) { go = 0; if (s == 0) p.ctrl[LGC_STOP] = 1; }
+    }
+    sh_go = go; sh_n = p.ctrl[LGC_M + s];
+  }
+  __syncthreads();
+  if (!sh_go) return;
+  if (s == 0 && threadIdx.x == 0) p.ctrl[LGC_LAST] = p.layer + 1;
+  if (!p.do_prune) return;
+  const int n = sh_n, base = p.base[s];
+  const bool prune = n > p.pruning_min_kpts;
   __shared__ int wsum[32];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -322,31 +364,45 @@ __global__ void __launch_bounds__(1024) k_lg_prune_scan(ScanParams p) {
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) p.ctrl[2 + s] = carry;
+  if (threadIdx.x == 0) { p.ctrl[LGC_M + s] = carry; p.ctrl[LGC_CAN0 + s] = prune ? 1 : 0; }
 }
 
-// gather rows into the other ping-pong buffers.  grid = (ceil(maxrows/8), 2), block 256 (warp/row)
+// gather the surviving rows into the other ping-pong buffers (layer i lives in buffer i & 1 when
+// pruning is enabled).  grid = (ceil(maxrows/8), 2), block 256 (warp per row).  Optionally also
+// writes the bf16 copy of the residual stream that the tensor-core path feeds to TMA.
 struct GatherParams {
-  const int* srcmap; const int* ctrl; int base[2]; int rows[2];
+  const int* srcmap; const int* ctrl; int base[2];
   const float* x_in; float* x_out; const float* cos_in; float* cos_out; const float* sin_in; float* sin_out;
-  const int* ind_in; int* ind_out; int* prune[2]; int can_prune[2];
+  const int* ind_in; int* ind_out; int* prune[2];
+  __nv_bfloat16* xb_out;
 };
 
 __global__ void __launch_bounds__(256) k_lg_gather(GatherParams p) {
+  pdl_wait();
+  if (p.ctrl[LGC_STOP]) return;          // exit fired in this layer's scan: keep the unpruned state where it is
   const int s = blockIdx.y;
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (j >= p.ctrl[2 + s]) return;
+  if (j >= p.ctrl[LGC_M + s]) return;
   const int lane = threadIdx.x & 31;
   const int src = p.base[s] + p.srcmap[p.base[s] + j], dst = p.base[s] + j;
   const float4* xi = reinterpret_cast<const float4*>(p.x_in + (size_t)src * 256);
   float4* xo = reinterpret_cast<float4*>(p.x_out + (size_t)dst * 256);
-  xo[lane] = xi[lane]; xo[lane + 32] = xi[lane + 32];
+  const float4 a = xi[2 * lane], b = xi[2 * lane + 1];
+  xo[2 * lane] = a; xo[2 * lane + 1] = b;
+  if (p.xb_out) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(p.xb_out + (size_t)dst * 256 + lane * 8) = u;
+  }
   p.cos_out[(size_t)dst * 32 + lane] = p.cos_in[(size_t)src * 32 + lane];
   p.sin_out[(size_t)dst * 32 + lane] = p.sin_in[(size_t)src * 32 + lane];
   if (lane == 0) {
     const int orig = p.ind_in[src];
     p.ind_out[dst] = orig;
-    if (p.prune[s] && p.can_prune[s] && p.ctrl[1] == 0) p.prune[s][orig] += 1;
+    if (p.prune[s] && p.ctrl[LGC_CAN0 + s]) p.prune[s][orig] += 1;
   }
 }
 
@@ -355,7 +411,9 @@ __global__ void __launch_bounds__(256) k_lg_gather(GatherParams p) {
 // row pass: one warp per row -> rmax[i], rlog[i] = log(sum exp(sim - rmax)).
 // col pass: CTA = 32 columns x 32 row-lanes -> cmax[j], clog[j].
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_lg_row_lse(const float* sim, int ld, int m, int n, float* rmax, float* rlog) {
+__global__ void __launch_bounds__(256) k_lg_row_lse(const float* sim, int ld, const int* ctrl, float* rmax, float* rlog) {
+  pdl_wait();
+  const int m = ctrl[LGC_M], n = ctrl[LGC_N];
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= m) return;
   const int lane = threadIdx.x & 31;
@@ -369,7 +427,9 @@ __global__ void __launch_bounds__(256) k_lg_row_lse(const float* sim, int ld, in
   if (lane == 0) { rmax[i] = mx; rlog[i] = logf(sum); }
 }
 
-__global__ void __launch_bounds__(1024) k_lg_col_lse(const float* sim, int ld, int m, int n, float* cmax, float* clog) {
+__global__ void __launch_bounds__(1024) k_lg_col_lse(const float* sim, int ld, const int* ctrl, float* cmax, float* clog) {
+  pdl_wait();
+  const int m = ctrl[LGC_M], n = ctrl[LGC_N];
   __shared__ float smx[32][33], ssm[32][33];
   const int tx = threadIdx.x & 31, tyy = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + tx;
@@ -400,9 +460,11 @@ __device__ __forceinline__ float assign_val(float s, float rm, float rl, float c
 }
 
 // K15a: row-wise max/argmax (first index on ties).  One warp per row.
-__global__ void __launch_bounds__(256) k_lg_row_argmax(const float* sim, int ld, int m, int n, const float* rmax,
+__global__ void __launch_bounds__(256) k_lg_row_argmax(const float* sim, int ld, const int* ctrl, const float* rmax,
                                                        const float* rlog, const float* cmax, const float* clog,
                                                        const float* ls0, const float* ls1, float* max0, int* m0) {
+  pdl_wait();
+  const int m = ctrl[LGC_M], n = ctrl[LGC_N];
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= m) return;
   const int lane = threadIdx.x & 31;
@@ -423,9 +485,11 @@ __global__ void __launch_bounds__(256) k_lg_row_argmax(const float* sim, int ld,
 }
 
 // K15b: column-wise argmax.  CTA = 32 columns x 32 row-lanes.
-__global__ void __launch_bounds__(1024) k_lg_col_argmax(const float* sim, int ld, int m, int n, const float* rmax,
+__global__ void __launch_bounds__(1024) k_lg_col_argmax(const float* sim, int ld, const int* ctrl, const float* rmax,
                                                         const float* rlog, const float* cmax, const float* clog,
                                                         const float* ls0, const float* ls1, int* m1) {
+  pdl_wait();
+  const int m = ctrl[LGC_M], n = ctrl[LGC_N];
   __shared__ float sv[32][33];
   __shared__ int si[32][33];
   const int tx = threadIdx.x & 31, tyy = threadIdx.x >> 5;
@@ -451,14 +515,28 @@ __global__ void __launch_bounds__(1024) k_lg_col_argmax(const float* sim, int ld
 
 // K15c: upstream filter_matches + match list.  Single CTA of 1024 threads.
 struct FilterParams {
-  int m, n; float th;
+  int m, n; float th;                        // m, n are read from ctrl on the device
+  const int* ctrl; int cap; int32_t* stop_layer;   // stop_layer (device, nullable) = executed layers
   const float* max0; const int* m0; const int* m1;
-  const int* ind0; const int* ind1;          // pruned-index -> original index
+  const int* ind0; const int* ind1;          // pruned-index -> original index (image 1 at + cap)
+  const int* ind_alt;                        // same for the odd ping-pong buffer (nullptr: no pruning)
   int32_t* matches; float* mscores; int32_t* n_matches;   // compact outputs
   int32_t* matches0; int32_t* matches1; float* ms0; float* ms1;  // full-size (nullable)
 };
 
 __global__ void __launch_bounds__(1024) k_lg_filter(FilterParams p) {
+  pdl_wait();
+  p.m = p.ctrl[LGC_M]; p.n = p.ctrl[LGC_N];
+  {
+    const int last = p.ctrl[LGC_LAST];
+    if (p.ind_alt && (last & 1)) { p.ind0 = p.ind_alt; p.ind1 = p.ind_alt + p.cap; }
+    // upstream: stop = i + 1 of the last layer entered; a side pruned to zero breaks out before the next layer
+    if (threadIdx.x == 0 && p.stop_layer) *p.stop_layer = (p.m > 0 && p.n > 0) ? last + 1 : last;
+    if (p.m <= 0 || p.n <= 0) {
+      if (threadIdx.x == 0) *p.n_matches = 0;
+      return;
+    }
+  }
   __shared__ int wsum[32];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -516,10 +594,12 @@ __global__ void __launch_bounds__(1024) k_lg_filter(FilterParams p) {
 
 // fill helpers
 __global__ void k_fill_i32(int32_t* p, int n, int32_t v) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
 __global__ void k_fill_f32(float* p, int n, float v) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }

@@ -45,7 +45,9 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t inner, uint64
 
 // ---- glue kernels -------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_f32_to_bf16_rows(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int ld,
-                                                          int base0, int rows0, int base1, int rows1) {
+                                                          int base0, int rows0, int base1, int rows1, const int* __restrict__ ctrl) {
+  pdl_wait();
+  if (ctrl) { rows0 = ctrl[2]; rows1 = ctrl[3]; }
   // one warp per row of 256
   const int s = blockIdx.y;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -64,7 +66,13 @@ __global__ void __launch_bounds__(256) k_f32_to_bf16_rows(const float* __restric
 // LayerNorm(512) + GELU(erf): fp32 in -> bf16 out.  One warp per row.
 __global__ void __launch_bounds__(256) k_ln_gelu_512_bf16(const float* __restrict__ h, __nv_bfloat16* __restrict__ y,
                                                           int base0, int rows0, int base1, int rows1,
-                                                          const float* __restrict__ gamma, const float* __restrict__ beta) {
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const int* __restrict__ ctrl) {
+  pdl_wait();
+  if (ctrl) {
+    if (ctrl[1] || ctrl[2] <= 0 || ctrl[3] <= 0) return;
+    rows0 = ctrl[2]; rows1 = ctrl[3];
+  }
   const int s = blockIdx.y;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (s ? rows1 : rows0)) return;
@@ -119,7 +127,7 @@ struct LgTensorCore {
   __nv_bfloat16 *xb = nullptr, *qkvb = nullptr, *ctxb = nullptr, *msgb = nullptr, *h1b = nullptr;
   float* h1f = nullptr;
   CUtensorMap m_xb, m_ctxb, m_msgb, m_h1b, m_qkv768, m_qkv512;
-  const float* last_x = nullptr;   // fp32 buffer xb was derived from (pruning switches buffers)
+  const int* ctrl = nullptr;       // LightGlue device state (sizes / early exit), set per match
   KernelProf* prof = nullptr;
 };
 
@@ -189,7 +197,7 @@ int lgtc_set_layer(LgTensorCore* tc, int li, const LgTcLayerSrc& s) {
 
 int lgtc_alloc_ws(LgTensorCore* tc, int cap) {
   tc->wsarena.release();
-  tc->cap = 0; tc->last_x = nullptr;
+  tc->cap = 0;
   if (cap % 128) { set_error("lgtc_alloc_ws: cap %d must be a multiple of 128", cap); return B2S_EINVAL; }
   const size_t R = (size_t)2 * cap;
   B2S_TRY(tc->wsarena.alloc(&tc->xb, R * 256)); B2S_TRY(tc->wsarena.alloc(&tc->qkvb, R * 768));
@@ -214,15 +222,15 @@ void lgtc_set_prof(LgTensorCore* tc, KernelProf* prof) { tc->prof = prof; }
 
 static int tc_gemm(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& a1, const CUtensorMap& a2, int K1, const TcLinear& w,
                    TcGemmParams p, int m, int n, long long* launches) {
-  p.K = w.K; p.K1 = K1; p.N = w.N; p.bias = w.bias;
+  p.K = w.K; p.K1 = K1; p.N = w.N; p.bias = w.bias; p.ctrl = tc->ctrl;
   p.seg_base[0] = 0; p.seg_base[1] = tc->cap; p.seg_rows[0] = m; p.seg_rows[1] = n;
   p.tiles0 = cdiv(m, 128);
   const int tiles = p.tiles0 + cdiv(n, 128);
   if (tiles <= 0) return 0;
   dim3 grid(w.N / w.BN, tiles);
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
-  if (w.BN == 64) k_gemm_tc<64><<<grid, 192, TcGemmCfg<64>::SMEM, st>>>(a1, a2, w.map, p);
-  else k_gemm_tc<128><<<grid, 192, TcGemmCfg<128>::SMEM, st>>>(a1, a2, w.map, p);
+  if (w.BN == 64) launch_k(k_gemm_tc<64>, grid, 192, TcGemmCfg<64>::SMEM, st, a1, a2, w.map, p);
+  else launch_k(k_gemm_tc<128>, grid, 192, TcGemmCfg<128>::SMEM, st, a1, a2, w.map, p);
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
   if (launches) ++*launches;
   B2S_LAUNCH_CHECK();
@@ -233,10 +241,10 @@ static int tc_attention(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& ma
   const int maxq = std::max(ap.prob[0].nq, ap.prob[1].nq);
   if (maxq <= 0) return 0;
   ap.scale_log2e = 0.125f * 1.4426950408889634f;
-  ap.out = tc->ctxb; ap.ldo = 256;
+  ap.out = tc->ctxb; ap.ldo = 256; ap.ctrl = tc->ctrl;
   dim3 grid(cdiv(maxq, ATC_BQ), 4, 2);
   if (tc->prof) tc->prof->mark(PROF_ATTN, st);
-  k_attn_tc<<<grid, ATC_THREADS, ATC_SMEM, st>>>(map, ap);
+  launch_k(k_attn_tc, grid, ATC_THREADS, ATC_SMEM, st, map, ap);
   if (tc->prof) tc->prof->mark(PROF_ATTN, st);
   if (launches) ++*launches;
   B2S_LAUNCH_CHECK();
@@ -249,7 +257,7 @@ static int tc_ffn(LgTensorCore* tc, cudaStream_t st, float* x, const TcLinear& w
   p.epi = TC_EPI_F32; p.out_f32 = tc->h1f; p.ld_f32 = 512;
   B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_ctxb, 256, w1, p, m, n, launches));          // [x | ctx] W1'^T + b1' (out_proj folded)
   dim3 g(cdiv(std::max(m, n), 8), 2);
-  k_ln_gelu_512_bf16<<<g, 256, 0, st>>>(tc->h1f, tc->h1b, 0, m, tc->cap, n, lng, lnb);
+  launch_k(k_ln_gelu_512_bf16, g, 256, 0, st, tc->h1f, tc->h1b, 0, m, tc->cap, n, lng, lnb, tc->ctrl);
   if (launches) ++*launches;
   B2S_LAUNCH_CHECK();
   p = TcGemmParams();
@@ -257,23 +265,29 @@ static int tc_ffn(LgTensorCore* tc, cudaStream_t st, float* x, const TcLinear& w
   return tc_gemm(tc, st, tc->m_h1b, tc->m_h1b, 512, w2, p, m, n, launches);              // x += h W2^T + b2 ; xb = bf16(x)
 }
 
+__nv_bfloat16* lgtc_xb(LgTensorCore* tc) { return tc->xb; }
+
+// One transformer layer.  m, n are upper bounds of the live point counts (they size the grids); the
+// live counts and the early-exit flag are read from `ctrl` on the device.  `x` is the fp32 residual
+// stream of this layer; its bf16 copy xb is maintained by the FFN epilogues / the pruning gather
+// (derive_xb: re-derive it from x first - layer 0, right after the input projection).
 int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int li, float* x, const float* cosb, const float* sinb, int cap, int m, int n,
-               long long* launches) {
+               const int* ctrl, bool derive_xb, long long* launches) {
   if (cap != tc->cap) { set_error("lgtc_layer: workspace capacity mismatch"); return B2S_EINVAL; }
   const TcLayer& l = tc->L[li];
-  if (tc->last_x != x || li == 0) {   // (re)derive the bf16 copy of the residual stream
+  tc->ctrl = ctrl;
+  if (derive_xb) {
     dim3 g(cdiv(std::max(m, n), 8), 2);
-    k_f32_to_bf16_rows<<<g, 256, 0, st>>>(x, tc->xb, 256, 0, m, cap, n);
+    launch_k(k_f32_to_bf16_rows, g, 256, 0, st, x, tc->xb, 256, 0, m, cap, n, ctrl);
     if (launches) ++*launches;
     B2S_LAUNCH_CHECK();
-    tc->last_x = x;
   }
   TcGemmParams p = {};
   // ---- self block ----
   p.epi = TC_EPI_ROTARY_BF16; p.out_bf16 = tc->qkvb; p.ld_bf16 = 768; p.rot_cos = cosb; p.rot_sin = sinb; p.rot_cols = 512;
   B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_xb, 256, l.qkv, p, m, n, launches));
   AttnTcParams ap = {};
-  ap.qcol = 0; ap.kcol = 256; ap.vcol = 512;
+  ap.qcol = 0; ap.kcol = 256; ap.vcol = 512; ap.cross = 0;
   ap.prob[0] = {0, 0, m, m}; ap.prob[1] = {cap, cap, n, n};
   B2S_TRY(tc_attention(tc, st, tc->m_qkv768, ap, launches));
   B2S_TRY(tc_ffn(tc, st, x, l.w1, l.lng, l.lnb, l.w2, m, n, launches));
@@ -281,7 +295,7 @@ int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int li, float* x, const float*
   p = TcGemmParams(); p.epi = TC_EPI_BF16; p.out_bf16 = tc->qkvb; p.ld_bf16 = 512;
   B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_xb, 256, l.cqkv, p, m, n, launches));
   ap = AttnTcParams();
-  ap.qcol = 0; ap.kcol = 0; ap.vcol = 256;
+  ap.qcol = 0; ap.kcol = 0; ap.vcol = 256; ap.cross = 1;
   ap.prob[0] = {0, cap, m, n}; ap.prob[1] = {cap, 0, n, m};
   B2S_TRY(tc_attention(tc, st, tc->m_qkv512, ap, launches));
   return tc_ffn(tc, st, x, l.cw1, l.clng, l.clnb, l.cw2, m, n, launches);
@@ -356,5 +370,40 @@ extern "C" int b2s_test_attn_tc(const float* q, const float* k, const float* v, 
   std::vector<__nv_bfloat16> out((size_t)nq * 256);
   B2S_CUDA(cudaMemcpy(out.data(), dctx, out.size() * 2, cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < out.size(); ++i) ctx[i] = __bfloat162float(out[i]);
+  return 0;
+}
+
+// Device-only timing of the attention kernel on random bf16 data: one launch = what a LightGlue
+// self block issues (2 problems x 4 heads, nq queries x nk keys each).  ms_out = mean per launch.
+extern "C" int b2s_bench_attn_tc(int nq, int nk, int iters, float* ms_out) {
+  if (nq <= 0 || nk <= 0 || iters <= 0 || !ms_out) { set_error("b2s_bench_attn_tc: bad argument"); return B2S_EINVAL; }
+  DeviceArena ar;
+  const int cap = cdiv(std::max(nq, nk), 128) * 128;
+  const size_t R = (size_t)2 * cap;
+  std::vector<__nv_bfloat16> buf(R * 768);
+  uint32_t s = 12345u;
+  for (auto& b : buf) { s = s * 1664525u + 1013904223u; b = __float2bfloat16_rn(((s >> 8) & 0xFFFF) / 32768.f - 1.f); }
+  __nv_bfloat16 *dq, *dctx;
+  B2S_TRY(ar.alloc(&dq, buf.size())); B2S_TRY(ar.alloc(&dctx, R * 256));
+  B2S_CUDA(cudaMemcpy(dq, buf.data(), buf.size() * 2, cudaMemcpyHostToDevice));
+  CUtensorMap map;
+  B2S_TRY(make_tmap_bf16_2d(&map, dq, 768, R, 1536, 64, 128));
+  cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
+  AttnTcParams ap = {};
+  ap.qcol = 0; ap.kcol = 256; ap.vcol = 512; ap.prob[0] = {0, 0, nq, nk}; ap.prob[1] = {cap, cap, nq, nk};
+  ap.scale_log2e = 0.125f * 1.4426950408889634f; ap.out = dctx; ap.ldo = 256;
+  cudaEvent_t e0, e1;
+  B2S_CUDA(cudaEventCreate(&e0)); B2S_CUDA(cudaEventCreate(&e1));
+  const dim3 grid(cdiv(nq, 128), 4, 2);
+  for (int i = 0; i < 3; ++i) k_attn_tc<<<grid, ATC_THREADS, ATC_SMEM>>>(map, ap);
+  B2S_CUDA(cudaEventRecord(e0));
+  for (int i = 0; i < iters; ++i) k_attn_tc<<<grid, ATC_THREADS, ATC_SMEM>>>(map, ap);
+  B2S_CUDA(cudaEventRecord(e1));
+  B2S_LAUNCH_CHECK();
+  B2S_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  B2S_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_out = ms / iters;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return 0;
 }

@@ -1,5 +1,6 @@
 // lightglue_tc.cuh - bf16 tcgen05/TMEM path of the LightGlue layer (interface).
 #pragma once
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace b2s {
@@ -13,9 +14,11 @@ struct LgTcLayerSrc {   // fp32 device weights of one layer (self block then cro
 int lgtc_create(LgTensorCore** out, size_t n_layers);
 int lgtc_set_layer(LgTensorCore* tc, int layer, const LgTcLayerSrc& src);
 int lgtc_alloc_ws(LgTensorCore* tc, int cap);
-// one full transformer layer (self + cross) in place on x [2*cap,256] fp32 master copy
+// one full transformer layer (self + cross) in place on x [2*cap,256] fp32 master copy; m, n bound the
+// live counts (grid sizes), the live counts / early-exit flag come from the device state `ctrl`
 int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int layer, float* x, const float* cosb, const float* sinb, int cap,
-               int m, int n, long long* launches);
+               int m, int n, const int* ctrl, bool derive_xb, long long* launches);
+__nv_bfloat16* lgtc_xb(LgTensorCore* tc);   // bf16 copy of the residual stream (the pruning gather refreshes it)
 void lgtc_destroy(LgTensorCore* tc);
 void lgtc_set_prof(LgTensorCore* tc, KernelProf* prof);
 

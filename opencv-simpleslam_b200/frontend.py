@@ -215,14 +215,16 @@ class LightGlue(_Module):
             self._handle = None
 
     def match_device(self, k0, d0, k1, d1, size0=None, size1=None, full=True):
-        """CUDA f32 tensors k [m,2], d [m,128]; enqueues on the current stream.  Returns a dict of
-        device tensors (+ 'stop'); 'n' is a device int32 count for matches/scores."""
+        """CUDA f32 tensors k [m,2], d [m,128]; enqueues on the current stream WITHOUT any host
+        synchronisation (early exit / pruning are decided on the device).  Returns a dict of device
+        tensors; 'n' (valid rows of matches/scores) and 'stop' (executed layers) are device int32."""
         m, n = int(k0.shape[0]), int(k1.shape[0])
         dev = self.device
         k = max(min(m, n), 1)
         out = {"matches": torch.empty((k, 2), dtype=torch.int32, device=dev),
                "scores": torch.empty((k,), dtype=torch.float32, device=dev),
-               "n": torch.zeros((1,), dtype=torch.int32, device=dev)}
+               "n": torch.zeros((1,), dtype=torch.int32, device=dev),
+               "stop": torch.zeros((1,), dtype=torch.int32, device=dev)}
         ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
         if full:
             out.update(matches0=torch.empty((m,), dtype=torch.int32, device=dev), matches1=torch.empty((n,), dtype=torch.int32, device=dev),
@@ -231,15 +233,13 @@ class LightGlue(_Module):
                        prune0=torch.empty((m,), dtype=torch.int32, device=dev), prune1=torch.empty((n,), dtype=torch.int32, device=dev))
         s0 = (C.c_float * 2)(*[float(v) for v in size0]) if size0 is not None else None
         s1 = (C.c_float * 2)(*[float(v) for v in size1]) if size1 is not None else None
-        stop = C.c_int32(0)
         st = torch.cuda.current_stream(dev).cuda_stream
         check(lib.b2s_lightglue_match(
             self._handle, k0.data_ptr(), d0.data_ptr(), m, k1.data_ptr(), d1.data_ptr(), n,
             C.cast(s0, C.c_void_p) if s0 is not None else None, C.cast(s1, C.c_void_p) if s1 is not None else None, st,
-            out["matches"].data_ptr(), out["scores"].data_ptr(), out["n"].data_ptr(), C.addressof(stop),
+            out["matches"].data_ptr(), out["scores"].data_ptr(), out["n"].data_ptr(), out["stop"].data_ptr(),
             ptr(out.get("matches0")), ptr(out.get("matches1")), ptr(out.get("matching_scores0")),
             ptr(out.get("matching_scores1")), ptr(out.get("prune0")), ptr(out.get("prune1"))), "b2s_lightglue_match")
-        out["stop"] = stop.value
         return out
 
     @torch.no_grad()
@@ -260,7 +260,7 @@ class LightGlue(_Module):
             nm = int(r["n"].item())
             return {"matches0": r["matches0"].long()[None], "matches1": r["matches1"].long()[None],
                     "matching_scores0": r["matching_scores0"][None], "matching_scores1": r["matching_scores1"][None],
-                    "stop": r["stop"], "matches": [r["matches"][:nm].long()], "scores": [r["scores"][:nm]],
+                    "stop": int(r["stop"].item()), "matches": [r["matches"][:nm].long()], "scores": [r["scores"][:nm]],
                     "prune0": r["prune0"].long()[None], "prune1": r["prune1"].long()[None]}
 
     forward = __call__
