@@ -299,7 +299,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(d2h / e2e_pairs * P), "pairs_timed": e2e_pairs,
                 "api": "features_utils.feature_extractor + feature_matcher (host numpy in, cv2 lists out)",
                 "matches_last_pair": e2e_matches},
-        "roofline": {"bound": "tensor", "kernel": "k_attn_fp32" if args.precision == "fp32" else "attention (bf16 path)",
+        "roofline": {"bound": "tensor", "kernel": {"fp32": "k_attn_tc3 (fp32 on bf16x3 planes, tcgen05)", "bf16": "k_attn_tc (bf16, tcgen05)", "fp32_simt": "k_attn_fp32 (CUDA cores)"}[args.precision],
                      "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                      "frac": (achieved / tensor_peak) if achieved else None, "traffic": None,
                      "peak_source": peak_src, "launches_timed": int(attn_n), "avg_launch_ms": attn_avg_ms,
@@ -324,7 +324,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("B2S_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("B2S_PRECISION", "fp32"), choices=["fp32", "bf16", "fp32_simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

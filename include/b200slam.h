@@ -37,7 +37,13 @@ enum {
   B2S_ESIZE = -5     /* input larger than the handle supports */
 };
 
-enum { B2S_FP32 = 0, B2S_BF16 = 1 };
+/* Arithmetic of the LightGlue transformer layers.
+ *   B2S_FP32      fp32-faithful on the tensor cores: every fp32 operand is carried as three bf16
+ *                 planes and each contraction issues the six significant cross products into an fp32
+ *                 TMEM accumulator (results agree with an fp32 FMA path to rounding level);
+ *   B2S_BF16      operands rounded once to bf16 (fastest; >= 99 % match-set agreement);
+ *   B2S_FP32_SIMT the same fp32 arithmetic on the CUDA cores (cross-check of the B2S_FP32 path). */
+enum { B2S_FP32 = 0, B2S_BF16 = 1, B2S_FP32_SIMT = 2 };
 enum { B2S_IMG_BGR_U8_HWC = 0, B2S_IMG_RGB_F32_CHW = 1 };
 
 typedef struct b2s_aliked b2s_aliked;
@@ -153,13 +159,17 @@ int b2s_lg_debug_get(b2s_lg* h, const char* name, float* out, size_t cap, size_t
 int b2s_lg_profile(b2s_lg* h, int on);
 int b2s_lg_profile_read(b2s_lg* h, int cls, double* ms, long long* n_launches);
 
-/* Unit-test entry points for the tcgen05 kernels (host buffers, operands rounded to bf16):
- *   b2s_test_gemm_tc : C[M,N] = A[M,K] W[N,K]^T + bias  (fp32 out; N, K multiples of 64)
- *   b2s_test_attn_tc : ctx[nq,256] = softmax(q k^T / 8) v per head (4 heads x 64) */
+/* Unit-test entry points for the tcgen05 kernels (host buffers).  The plain names round the
+ * operands to bf16; the "3" variants carry them as three bf16 planes (fp32-faithful):
+ *   b2s_test_gemm_tc* : C[M,N] = A[M,K] W[N,K]^T + bias  (fp32 out; N, K multiples of 64)
+ *   b2s_test_attn_tc* : ctx[nq,256] = softmax(q k^T / 8) v per head (4 heads x 64) */
 int b2s_test_gemm_tc(const float* A, const float* W, const float* bias, int M, int N, int K, float* C);
 int b2s_test_attn_tc(const float* q, const float* k, const float* v, int nq, int nk, float* ctx);
+int b2s_test_gemm_tc3(const float* A, const float* W, const float* bias, int M, int N, int K, float* C);
+int b2s_test_attn_tc3(const float* q, const float* k, const float* v, int nq, int nk, float* ctx);
 /* device-only timing of one self-block attention launch (2 problems x 4 heads, nq x nk), mean ms per launch */
 int b2s_bench_attn_tc(int nq, int nk, int iters, float* ms_out);
+int b2s_bench_attn_tc3(int nq, int nk, int iters, float* ms_out);
 
 /* Number of CUDA kernels this library launched on behalf of the handle so far. */
 long long b2s_aliked_launch_count(const b2s_aliked* h);

@@ -28,7 +28,8 @@ class LgCfg(C.Structure):
                 ("pruning_min_kpts", C.c_int), ("precision", C.c_int), ("max_kp", C.c_int)]
 
 
-FP32, BF16 = 0, 1
+FP32, BF16, FP32_SIMT = 0, 1, 2
+PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp32_simt": FP32_SIMT}
 IMG_BGR_U8_HWC, IMG_RGB_F32_CHW = 0, 1
 vp, i32p, f32p = C.c_void_p, C.c_void_p, C.c_void_p   # raw addresses (device or host)
 
@@ -58,6 +59,9 @@ SIGNATURES = {
     "b2s_test_gemm_tc": (C.c_int, [f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, f32p]),
     "b2s_test_attn_tc": (C.c_int, [f32p, f32p, f32p, C.c_int, C.c_int, f32p]),
     "b2s_bench_attn_tc": (C.c_int, [C.c_int, C.c_int, C.c_int, f32p]),
+    "b2s_test_gemm_tc3": (C.c_int, [f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, f32p]),
+    "b2s_test_attn_tc3": (C.c_int, [f32p, f32p, f32p, C.c_int, C.c_int, f32p]),
+    "b2s_bench_attn_tc3": (C.c_int, [C.c_int, C.c_int, C.c_int, f32p]),
     "b2s_aliked_launch_count": (C.c_longlong, [vp]),
     "b2s_lg_launch_count": (C.c_longlong, [vp]),
 }

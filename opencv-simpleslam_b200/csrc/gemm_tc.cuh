@@ -1,9 +1,15 @@
-// gemm_tc.cuh - bf16 tcgen05/TMEM GEMM fed by TMA, fp32 accumulation, fused epilogues.
+// gemm_tc.cuh - tcgen05/TMEM GEMM fed by TMA, fp32 accumulation, fused epilogues.
 //   C[M,N] = epi( [A1 | A2][M,K] * W[N,K]^T + bias )      (both operands K-major, 128B swizzle)
-// One 128 x BN output tile per CTA, BK = 64 (one 128-byte swizzle atom per row), 4-stage
-// TMA->smem ring, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected
-// lane issues tcgen05.mma, accumulator in TMEM), warps 2..5 = epilogue (tcgen05.ld: thread ==
-// accumulator row, so row-wise epilogues - rotary pairs, residual - are thread-local).
+// Operands are bf16 PLANES (tc_common.cuh): NP = 1 is the plain bf16 path; NP = 3 carries fp32
+// values as three bf16 planes and issues the six cross products a_i w_j (i + j <= 2) per k-step,
+// which reproduces the fp32 product to fp32 rounding level on the tensor pipe ("fp32 on bf16x3").
+// Plane p of an activation buffer lives `plane_rows` rows below plane 0 (same tensor map);
+// plane p of a weight lives K columns to the right ([N, NP*K]).
+// One 128 x BN output tile per CTA, BK = 64 (one 128-byte swizzle atom per row), TMA->smem ring
+// (a stage holds all NP planes of both operands), warp-specialised: warp 0 = TMA producer,
+// warp 1 = MMA issuer (one elected lane issues tcgen05.mma, accumulator in TMEM), warps 2..5 =
+// epilogue (tcgen05.ld: thread == accumulator row, so row-wise epilogues - rotary pairs, residual,
+// plane splitting - are thread-local).
 // Row space: two segments (image0 / image1 of a pair) at fixed bases of a [2*cap, ld] buffer.
 #pragma once
 #include "tc_common.cuh"
@@ -16,36 +22,41 @@ struct TcGemmParams {
   int K, K1, N;                     // K total, K1 = columns served by map A1 (K1 == K when single source)
   int seg_base[2], seg_rows[2];     // row segments; tiles_m[z] = ceil(seg_rows[z]/128)
   int tiles0;                       // number of M tiles in segment 0
+  int plane_rows;                   // rows between consecutive operand planes of A1 / A2 (NP > 1)
   const float* bias;                // [N]
   int epi;
-  __nv_bfloat16* out_bf16; int ld_bf16;     // TC_EPI_BF16 / ROTARY / RESID (bf16 copy)
+  __nv_bfloat16* out_bf16; int ld_bf16;     // TC_EPI_BF16 / ROTARY / RESID (bf16 copy); plane p at + p * out_plane
+  size_t out_plane;                         // elements between output planes
   float* out_f32; int ld_f32;               // TC_EPI_F32 (plain) / RESID (in-place residual stream)
   const float* rot_cos; const float* rot_sin; int rot_cols;   // [rows,32] tables
   const int* ctrl;                  // LightGlue device state (nullable): live rows = ctrl[2 + seg]; exit when stopped
 };
 
-template <int BN>
+template <int BN, int NP>
 struct TcGemmCfg {
-  static constexpr int BM = 128, BK = 64, STAGES = 3;
-  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;       // one plane
+  static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = NP == 1 ? 3 : (BN == 128 ? 2 : 3);
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
   static constexpr int THREADS = 192;
 };
 
-template <int BN>
+template <int BN, int NP>
 __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtensorMap mapA1,
                                                  const __grid_constant__ CUtensorMap mapA2,
                                                  const __grid_constant__ CUtensorMap mapW, TcGemmParams p) {
-  using Cfg = TcGemmCfg<BN>;
+  using Cfg = TcGemmCfg<BN, NP>;
+  using Terms = tc::PlaneTerms<NP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+  // stage s: A planes at s*STAGE_BYTES + p*A_BYTES, W planes behind them
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + Cfg::STAGES;  // [STAGES]
   uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_m = blockIdx.y, n0 = blockIdx.x * BN;
@@ -63,6 +74,10 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc(tmem_slot, BN);
+  if (warp >= 2) {                       // bias is a constant weight: staged before the dependency wait
+    const int t = threadIdx.x - 64;
+    if (t < BN) s_bias[t] = __ldg(p.bias + n0 + t);
+  }
   pdl_trigger();
   tc::tc_fence_before();
   __syncthreads();
@@ -82,11 +97,15 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % Cfg::STAGES, ph = (kb / Cfg::STAGES) & 1;
         tc::mbar_wait(&empty[s], ph ^ 1);
-        tc::mbar_expect_tx(&full[s], Cfg::A_BYTES + Cfg::B_BYTES);
+        tc::mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
         const int k0 = kb * Cfg::BK;
-        if (k0 < p.K1) tc::tma_load_2d(sA + s * Cfg::A_BYTES, &mapA1, &full[s], k0, row0);
-        else tc::tma_load_2d(sA + s * Cfg::A_BYTES, &mapA2, &full[s], k0 - p.K1, row0);
-        tc::tma_load_2d(sB + s * Cfg::B_BYTES, &mapW, &full[s], k0, n0);
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl) {
+          if (k0 < p.K1) tc::tma_load_2d(st + pl * Cfg::A_BYTES, &mapA1, &full[s], k0, row0 + pl * p.plane_rows);
+          else tc::tma_load_2d(st + pl * Cfg::A_BYTES, &mapA2, &full[s], k0 - p.K1, row0 + pl * p.plane_rows);
+          tc::tma_load_2d(st + NP * Cfg::A_BYTES + pl * Cfg::B_BYTES, &mapW, &full[s], pl * p.K + k0, n0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -97,12 +116,15 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
         const int s = kb % Cfg::STAGES, ph = (kb / Cfg::STAGES) & 1;
         tc::mbar_wait(&full[s], ph);
         tc::tc_fence_after();
-        const uint32_t a0 = tc::smem_u32(sA + s * Cfg::A_BYTES), b0 = tc::smem_u32(sB + s * Cfg::B_BYTES);
+        const uint32_t a0 = tc::smem_u32(smem + s * Cfg::STAGE_BYTES), b0 = a0 + NP * Cfg::A_BYTES;
 #pragma unroll
-        for (int k = 0; k < Cfg::BK / 16; ++k) {
-          const uint64_t ad = tc::smem_desc_sw128(a0 + k * 32, 16, 1024);
-          const uint64_t bd = tc::smem_desc_sw128(b0 + k * 32, 16, 1024);
-          tc::umma_bf16(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+        for (int t = 0; t < Terms::N; ++t) {
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / 16; ++k) {
+            const uint64_t ad = tc::smem_desc_sw128(a0 + Terms::a(t) * Cfg::A_BYTES + k * 32, 16, 1024);
+            const uint64_t bd = tc::smem_desc_sw128(b0 + Terms::b(t) * Cfg::B_BYTES + k * 32, 16, 1024);
+            tc::umma_bf16(tmem_base, ad, bd, idesc, (kb | t | k) ? 1u : 0u);
+          }
         }
         tc::umma_commit(&empty[s]);                 // frees the smem stage when these MMAs retire
         if (kb == nkb - 1) tc::umma_commit(tmem_full);
@@ -112,10 +134,10 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
     // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
     const int quad = warp & 3;
     const int r = quad * 32 + lane;                 // accumulator row handled by this thread
-    tc::mbar_wait(tmem_full, 0);
-    tc::tc_fence_after();
     const bool live = r < rows_live;
     const size_t grow = (size_t)(row0 + r);
+    tc::mbar_wait(tmem_full, 0);
+    tc::tc_fence_after();
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
@@ -125,10 +147,10 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
       if (!live || gc >= p.N) continue;
       float f[32];
       {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + gc);
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 bv = __ldg(b4 + q);
+          const float4 bv = b4[q];
           f[4 * q] = __uint_as_float(v[4 * q]) + bv.x; f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bv.y;
           f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bv.z; f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bv.w;
         }
@@ -145,7 +167,9 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
           for (int e = 0; e < 4; ++e) {
             const int j = 8 * q + 2 * e;
             const float a = f[j], b = f[j + 1];
-            f[j] = a * cs[e] - b * sn[e]; f[j + 1] = b * cs[e] + a * sn[e];
+            // torch: t * cos + rotate_half(t) * sin, two rounded products then one add (no contraction)
+            f[j] = __fadd_rn(__fmul_rn(a, cs[e]), __fmul_rn(-b, sn[e]));
+            f[j + 1] = __fadd_rn(__fmul_rn(b, cs[e]), __fmul_rn(a, sn[e]));
           }
         }
       }
@@ -165,15 +189,19 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
           f[4 * j] = x.x; f[4 * j + 1] = x.y; f[4 * j + 2] = x.z; f[4 * j + 3] = x.w;
         }
       }
-      uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + grow * p.ld_bf16 + gc);
+      uint32_t w[NP][16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]), h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]), h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-        uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-        o[j] = u;
+      for (int j = 0; j < 16; ++j) {
+        uint32_t pw[NP];
+        tc::pack_planes2<NP>(f[2 * j], f[2 * j + 1], pw);
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl) w[pl][j] = pw[pl];
+      }
+#pragma unroll
+      for (int pl = 0; pl < NP; ++pl) {
+        uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + pl * p.out_plane + grow * p.ld_bf16 + gc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = make_uint4(w[pl][4 * j], w[pl][4 * j + 1], w[pl][4 * j + 2], w[pl][4 * j + 3]);
       }
     }
   }

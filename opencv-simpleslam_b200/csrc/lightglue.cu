@@ -101,6 +101,10 @@ extern "C" void b2s_lg_default_cfg(b2s_lg_cfg* c) {
 
 extern "C" int b2s_lightglue_create(const b2s_lg_cfg* cfg, const void* weights, size_t nbytes, int device, b2s_lg** out) {
   if (!cfg || !weights || !out) { set_error("b2s_lightglue_create: null argument"); return B2S_EINVAL; }
+  if (cfg->precision != B2S_FP32 && cfg->precision != B2S_BF16 && cfg->precision != B2S_FP32_SIMT) {
+    set_error("b2s_lightglue_create: unknown precision %d", cfg->precision);
+    return B2S_EINVAL;
+  }
   if (cfg->dim != 256 || cfg->heads != 4 || cfg->in_dim != 128 || cfg->n_layers < 1 || cfg->n_layers > 16) {
     set_error("b2s_lightglue_create: only dim=256, heads=4, in_dim=128, 1..16 layers are supported");
     return B2S_EINVAL;
@@ -193,8 +197,8 @@ extern "C" int b2s_lightglue_create(const b2s_lg_cfg* cfg, const void* weights, 
   }
   if (cudaMallocHost((void**)&h->h_ctrl, LGC_INTS * sizeof(int)) != cudaSuccess) { set_error("cudaMallocHost failed"); return fail(B2S_ENOMEM); }
   cudaFuncSetAttribute(k_attn_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-  if (cfg->precision == B2S_BF16) {
-    if ((rc = lgtc_create(&h->tc, h->L.size()))) return fail(rc);
+  if (cfg->precision != B2S_FP32_SIMT) {   // tensor-core paths: bf16 operands, or fp32 carried as three bf16 planes
+    if ((rc = lgtc_create(&h->tc, h->L.size(), cfg->precision == B2S_BF16 ? 1 : 3))) return fail(rc);
     lgtc_set_prof(h->tc, &h->prof);
     for (size_t i = 0; i < h->L.size(); ++i) {
       const LgLayer& l = h->L[i];
@@ -422,6 +426,7 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
       gp.sin_in = h->sinb[cur]; gp.sin_out = h->sinb[nxt]; gp.ind_in = h->ind[cur]; gp.ind_out = h->ind[nxt];
       gp.prune[0] = pr0; gp.prune[1] = pr1;
       gp.xb_out = h->tc ? lgtc_xb(h->tc) : nullptr;
+      gp.xb_planes = h->tc ? lgtc_planes(h->tc) : 0; gp.xb_plane = (size_t)2 * cap * 256;
       launch_k(k_lg_gather, dim3(cdiv(std::max(m, n), 8), 2), 256, 0, st, gp);
       ++h->launches;
       B2S_LAUNCH_CHECK();

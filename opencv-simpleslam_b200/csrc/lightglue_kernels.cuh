@@ -374,7 +374,7 @@ struct GatherParams {
   const int* srcmap; const int* ctrl; int base[2];
   const float* x_in; float* x_out; const float* cos_in; float* cos_out; const float* sin_in; float* sin_out;
   const int* ind_in; int* ind_out; int* prune[2];
-  __nv_bfloat16* xb_out;
+  __nv_bfloat16* xb_out; int xb_planes; size_t xb_plane;   // bf16 plane copy of x (tensor-core paths)
 };
 
 __global__ void __launch_bounds__(256) k_lg_gather(GatherParams p) {
@@ -390,12 +390,17 @@ __global__ void __launch_bounds__(256) k_lg_gather(GatherParams p) {
   const float4 a = xi[2 * lane], b = xi[2 * lane + 1];
   xo[2 * lane] = a; xo[2 * lane + 1] = b;
   if (p.xb_out) {
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
-    __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
-    uint4 u;
-    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-    *reinterpret_cast<uint4*>(p.xb_out + (size_t)dst * 256 + lane * 8) = u;
+    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    for (int pl = 0; pl < p.xb_planes; ++pl) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 hb = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        w[j] = *reinterpret_cast<const uint32_t*>(&hb);
+        f[2 * j] -= __uint_as_float(w[j] << 16); f[2 * j + 1] -= __uint_as_float(w[j] & 0xFFFF0000u);
+      }
+      *reinterpret_cast<uint4*>(p.xb_out + pl * p.xb_plane + (size_t)dst * 256 + lane * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
   }
   p.cos_out[(size_t)dst * 32 + lane] = p.cos_in[(size_t)src * 32 + lane];
   p.sin_out[(size_t)dst * 32 + lane] = p.sin_in[(size_t)src * 32 + lane];

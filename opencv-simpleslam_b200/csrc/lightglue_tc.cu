@@ -3,6 +3,7 @@
 // bandwidth-bound glue (fp32->bf16, LayerNorm+GELU).  The residual stream stays fp32.
 #include "lightglue_tc.cuh"
 #include "attn_tc.cuh"
+#include "attn_tc3.cuh"
 #include "gemm_tc.cuh"
 
 #include <algorithm>
@@ -44,7 +45,23 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t inner, uint64
 }
 
 // ---- glue kernels -------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_f32_to_bf16_rows(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int ld,
+// store 8 consecutive values of one row as NP bf16 planes (plane p at y + p * plane)
+template <int NP>
+__device__ __forceinline__ void store_planes8(__nv_bfloat16* y, size_t plane, const float (&f)[8]) {
+  uint32_t w[NP][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t pw[NP];
+    tc::pack_planes2<NP>(f[2 * j], f[2 * j + 1], pw);
+#pragma unroll
+    for (int pl = 0; pl < NP; ++pl) w[pl][j] = pw[pl];
+  }
+#pragma unroll
+  for (int pl = 0; pl < NP; ++pl) *reinterpret_cast<uint4*>(y + pl * plane) = make_uint4(w[pl][0], w[pl][1], w[pl][2], w[pl][3]);
+}
+
+template <int NP>
+__global__ void __launch_bounds__(256) k_f32_to_bf16_rows(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int ld, size_t plane,
                                                           int base0, int rows0, int base1, int rows1, const int* __restrict__ ctrl) {
   pdl_wait();
   if (ctrl) { rows0 = ctrl[2]; rows1 = ctrl[3]; }
@@ -55,16 +72,13 @@ __global__ void __launch_bounds__(256) k_f32_to_bf16_rows(const float* __restric
   const int lane = threadIdx.x & 31;
   const size_t off = (size_t)((s ? base1 : base0) + row) * ld + lane * 8;
   const float4 a = *reinterpret_cast<const float4*>(x + off), b = *reinterpret_cast<const float4*>(x + off + 4);
-  __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
-  __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
-  uint4 u;
-  u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-  u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-  *reinterpret_cast<uint4*>(y + off) = u;
+  const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  store_planes8<NP>(y + off, plane, f);
 }
 
-// LayerNorm(512) + GELU(erf): fp32 in -> bf16 out.  One warp per row.
-__global__ void __launch_bounds__(256) k_ln_gelu_512_bf16(const float* __restrict__ h, __nv_bfloat16* __restrict__ y,
+// LayerNorm(512) + GELU(erf): fp32 in -> NP bf16 planes out.  One warp per row.
+template <int NP>
+__global__ void __launch_bounds__(256) k_ln_gelu_512_bf16(const float* __restrict__ h, __nv_bfloat16* __restrict__ y, size_t plane,
                                                           int base0, int rows0, int base1, int rows1,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const int* __restrict__ ctrl) {
@@ -78,11 +92,11 @@ __global__ void __launch_bounds__(256) k_ln_gelu_512_bf16(const float* __restric
   if (row >= (s ? rows1 : rows0)) return;
   const int lane = threadIdx.x & 31;
   const size_t roff = (size_t)((s ? base1 : base0) + row) * 512;
-  float4 v[4];
+  float4 v[4];   // columns lane*8 + t*256 + {0..3} and +4: two chunks of 8 consecutive values per lane
   float sum = 0.f;
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    v[t] = *reinterpret_cast<const float4*>(h + roff + t * 128 + lane * 4);
+    v[t] = *reinterpret_cast<const float4*>(h + roff + (t >> 1) * 256 + lane * 8 + (t & 1) * 4);
     sum += (v[t].x + v[t].y) + (v[t].z + v[t].w);
   }
   const float mean = warp_sum(sum) * (1.f / 512.f);
@@ -94,55 +108,69 @@ __global__ void __launch_bounds__(256) k_ln_gelu_512_bf16(const float* __restric
   }
   const float rstd = rsqrtf(warp_sum(sq) * (1.f / 512.f) + 1e-5f);
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const int c = t * 128 + lane * 4;
-    const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(gelu_erf_f((v[t].x - mean) * rstd * g.x + b.x), gelu_erf_f((v[t].y - mean) * rstd * g.y + b.y));
-    __nv_bfloat162 h1 = __floats2bfloat162_rn(gelu_erf_f((v[t].z - mean) * rstd * g.z + b.z), gelu_erf_f((v[t].w - mean) * rstd * g.w + b.w));
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(y + roff + c) = u;
+  for (int u = 0; u < 2; ++u) {
+    const int c = u * 256 + lane * 8;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c + e * 4), b = *reinterpret_cast<const float4*>(beta + c + e * 4);
+      const float4 x = v[2 * u + e];
+      f[4 * e] = gelu_erf_f((x.x - mean) * rstd * g.x + b.x); f[4 * e + 1] = gelu_erf_f((x.y - mean) * rstd * g.y + b.y);
+      f[4 * e + 2] = gelu_erf_f((x.z - mean) * rstd * g.z + b.z); f[4 * e + 3] = gelu_erf_f((x.w - mean) * rstd * g.w + b.w);
+    }
+    store_planes8<NP>(y + roff + c, plane, f);
   }
 }
 
-__global__ void k_f32_to_bf16_flat(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n) {
+// fp32 weight [N,K] -> NP bf16 planes side by side: out[n][p*K + k]
+__global__ void k_weight_planes(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int N, int K, int np) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = __float2bfloat16_rn(x[i]);
+  if (i >= (size_t)N * K) return;
+  const int n = (int)(i / K), k = (int)(i % K);
+  float r = w[i];
+  for (int p = 0; p < np; ++p) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(r);
+    out[(size_t)n * np * K + (size_t)p * K + k] = b;
+    r -= __bfloat162float(b);
+  }
 }
 
 // ---- state --------------------------------------------------------------------------------
-struct TcLinear {            // bf16 weight [N,K] + its tensor map (box {64, BN})
+struct TcLinear {            // bf16 weight planes [N, NP*K] + their tensor map (box {64, BN})
   __nv_bfloat16* w = nullptr; const float* bias = nullptr; int N = 0, K = 0, BN = 0;
   CUtensorMap map;
 };
 struct TcLayer {
-  TcLinear qkv, wo, w1, w2, cqkv, cwo, cw1, cw2;
+  TcLinear qkv, w1, w2, cqkv, cw1, cw2;
   const float *lng, *lnb, *clng, *clnb;
 };
 
 struct LgTensorCore {
   DeviceArena warena, wsarena;
   std::vector<TcLayer> L;
+  int np = 1;                      // operand planes: 1 = bf16, 3 = fp32 carried as bf16x3
   int cap = 0;
-  __nv_bfloat16 *xb = nullptr, *qkvb = nullptr, *ctxb = nullptr, *msgb = nullptr, *h1b = nullptr;
+  // activation planes: [np][2*cap][C] bf16
+  __nv_bfloat16 *xb = nullptr, *qkvb = nullptr, *ctxb = nullptr, *h1b = nullptr;
   float* h1f = nullptr;
-  CUtensorMap m_xb, m_ctxb, m_msgb, m_h1b, m_qkv768, m_qkv512;
+  CUtensorMap m_xb, m_ctxb, m_h1b, m_qkv768, m_qkv512;     // box {64, 128}: GEMM A operands, attention Q
+  CUtensorMap m_kv768, m_kv512;                            // box {64, 64}: attention K / V tiles (np == 3)
   const int* ctrl = nullptr;       // LightGlue device state (sizes / early exit), set per match
   KernelProf* prof = nullptr;
 };
 
 static int make_linear(LgTensorCore* tc, const float* w_dev, const float* bias, int N, int K, TcLinear* out) {
   out->N = N; out->K = K; out->bias = bias; out->BN = N <= 256 ? 64 : 128;
-  B2S_TRY(tc->warena.alloc(&out->w, (size_t)N * K));
   const size_t n = (size_t)N * K;
-  k_f32_to_bf16_flat<<<(unsigned)((n + 255) / 256), 256>>>(w_dev, out->w, n);
+  B2S_TRY(tc->warena.alloc(&out->w, n * tc->np));
+  k_weight_planes<<<(unsigned)((n + 255) / 256), 256>>>(w_dev, out->w, N, K, tc->np);
   B2S_LAUNCH_CHECK();
-  return make_tmap_bf16_2d(&out->map, out->w, K, N, (uint64_t)K * 2, 64, out->BN);
+  return make_tmap_bf16_2d(&out->map, out->w, (uint64_t)tc->np * K, N, (uint64_t)tc->np * K * 2, 64, out->BN);
 }
 
 // FFN first layer with the attention output projection folded in (exact in real arithmetic):
 //   ffn.0([x | out_proj(ctx)]) = x W1x^T + ctx (W1m Wo)^T + (b1 + W1m bo)
-// so the block needs no separate out_proj GEMM and `msg` is never rounded to bf16.
+// so the block needs no separate out_proj GEMM and `msg` is never materialised.
 static int make_folded_ffn1(LgTensorCore* tc, const float* w1_dev, const float* b1_dev, const float* wo_dev, const float* bo_dev,
                             TcLinear* out) {
   std::vector<float> w1(512 * 512), b1(512), wo(256 * 256), bo(256);
@@ -172,12 +200,22 @@ static int make_folded_ffn1(LgTensorCore* tc, const float* w1_dev, const float* 
   return make_linear(tc, wf_dev, bf_dev, 512, 512, out);
 }
 
-int lgtc_create(LgTensorCore** out, size_t n_layers) {
-  LgTensorCore* tc = new LgTensorCore();
-  tc->L.resize(n_layers);
-  cudaFuncSetAttribute(k_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGemmCfg<64>::SMEM);
-  cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGemmCfg<128>::SMEM);
+template <int BN, int NP>
+static void gemm_attr() {
+  cudaFuncSetAttribute(k_gemm_tc<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGemmCfg<BN, NP>::SMEM);
+}
+static void tc_kernel_attrs() {
+  gemm_attr<64, 1>(); gemm_attr<128, 1>(); gemm_attr<64, 3>(); gemm_attr<128, 3>();
   cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
+  cudaFuncSetAttribute(k_attn_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM);
+}
+
+int lgtc_create(LgTensorCore** out, size_t n_layers, int planes) {
+  if (planes != 1 && planes != 3) { set_error("lgtc_create: planes must be 1 or 3"); return B2S_EINVAL; }
+  LgTensorCore* tc = new LgTensorCore();
+  tc->np = planes;
+  tc->L.resize(n_layers);
+  tc_kernel_attrs();
   *out = tc;
   return 0;
 }
@@ -199,20 +237,21 @@ int lgtc_alloc_ws(LgTensorCore* tc, int cap) {
   tc->wsarena.release();
   tc->cap = 0;
   if (cap % 128) { set_error("lgtc_alloc_ws: cap %d must be a multiple of 128", cap); return B2S_EINVAL; }
-  const size_t R = (size_t)2 * cap;
-  B2S_TRY(tc->wsarena.alloc(&tc->xb, R * 256)); B2S_TRY(tc->wsarena.alloc(&tc->qkvb, R * 768));
-  B2S_TRY(tc->wsarena.alloc(&tc->ctxb, R * 256)); B2S_TRY(tc->wsarena.alloc(&tc->msgb, R * 256));
-  B2S_TRY(tc->wsarena.alloc(&tc->h1b, R * 512)); B2S_TRY(tc->wsarena.alloc(&tc->h1f, R * 512));
+  const size_t R = (size_t)2 * cap, P = (size_t)tc->np;
+  B2S_TRY(tc->wsarena.alloc(&tc->xb, P * R * 256)); B2S_TRY(tc->wsarena.alloc(&tc->qkvb, P * R * 768));
+  B2S_TRY(tc->wsarena.alloc(&tc->ctxb, P * R * 256));
+  B2S_TRY(tc->wsarena.alloc(&tc->h1b, P * R * 512)); B2S_TRY(tc->wsarena.alloc(&tc->h1f, R * 512));
   // dead rows between the live counts and the tile boundary are read by TMA: keep them finite
-  B2S_CUDA(cudaMemset(tc->xb, 0, R * 256 * 2)); B2S_CUDA(cudaMemset(tc->qkvb, 0, R * 768 * 2));
-  B2S_CUDA(cudaMemset(tc->ctxb, 0, R * 256 * 2)); B2S_CUDA(cudaMemset(tc->msgb, 0, R * 256 * 2));
-  B2S_CUDA(cudaMemset(tc->h1b, 0, R * 512 * 2)); B2S_CUDA(cudaMemset(tc->h1f, 0, R * 512 * 4));
-  B2S_TRY(make_tmap_bf16_2d(&tc->m_xb, tc->xb, 256, R, 512, 64, 128));
-  B2S_TRY(make_tmap_bf16_2d(&tc->m_ctxb, tc->ctxb, 256, R, 512, 64, 128));
-  B2S_TRY(make_tmap_bf16_2d(&tc->m_msgb, tc->msgb, 256, R, 512, 64, 128));
-  B2S_TRY(make_tmap_bf16_2d(&tc->m_h1b, tc->h1b, 512, R, 1024, 64, 128));
-  B2S_TRY(make_tmap_bf16_2d(&tc->m_qkv768, tc->qkvb, 768, R, 1536, 64, 128));
-  B2S_TRY(make_tmap_bf16_2d(&tc->m_qkv512, tc->qkvb, 512, R, 1024, 64, 128));
+  B2S_CUDA(cudaMemset(tc->xb, 0, P * R * 256 * 2)); B2S_CUDA(cudaMemset(tc->qkvb, 0, P * R * 768 * 2));
+  B2S_CUDA(cudaMemset(tc->ctxb, 0, P * R * 256 * 2));
+  B2S_CUDA(cudaMemset(tc->h1b, 0, P * R * 512 * 2)); B2S_CUDA(cudaMemset(tc->h1f, 0, R * 512 * 4));
+  B2S_TRY(make_tmap_bf16_2d(&tc->m_xb, tc->xb, 256, P * R, 512, 64, 128));
+  B2S_TRY(make_tmap_bf16_2d(&tc->m_ctxb, tc->ctxb, 256, P * R, 512, 64, 128));
+  B2S_TRY(make_tmap_bf16_2d(&tc->m_h1b, tc->h1b, 512, P * R, 1024, 64, 128));
+  B2S_TRY(make_tmap_bf16_2d(&tc->m_qkv768, tc->qkvb, 768, P * R, 1536, 64, 128));
+  B2S_TRY(make_tmap_bf16_2d(&tc->m_qkv512, tc->qkvb, 512, P * R, 1024, 64, 128));
+  B2S_TRY(make_tmap_bf16_2d(&tc->m_kv768, tc->qkvb, 768, P * R, 1536, 64, 64));
+  B2S_TRY(make_tmap_bf16_2d(&tc->m_kv512, tc->qkvb, 512, P * R, 1024, 64, 64));
   tc->cap = cap;
   return 0;
 }
@@ -225,26 +264,46 @@ static int tc_gemm(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& a1, con
   p.K = w.K; p.K1 = K1; p.N = w.N; p.bias = w.bias; p.ctrl = tc->ctrl;
   p.seg_base[0] = 0; p.seg_base[1] = tc->cap; p.seg_rows[0] = m; p.seg_rows[1] = n;
   p.tiles0 = cdiv(m, 128);
+  p.plane_rows = 2 * tc->cap;
+  p.out_plane = (size_t)2 * tc->cap * p.ld_bf16;
   const int tiles = p.tiles0 + cdiv(n, 128);
   if (tiles <= 0) return 0;
   dim3 grid(w.N / w.BN, tiles);
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
-  if (w.BN == 64) launch_k(k_gemm_tc<64>, grid, 192, TcGemmCfg<64>::SMEM, st, a1, a2, w.map, p);
-  else launch_k(k_gemm_tc<128>, grid, 192, TcGemmCfg<128>::SMEM, st, a1, a2, w.map, p);
+  if (tc->np == 1) {
+    if (w.BN == 64) launch_k(k_gemm_tc<64, 1>, grid, 192, TcGemmCfg<64, 1>::SMEM, st, a1, a2, w.map, p);
+    else launch_k(k_gemm_tc<128, 1>, grid, 192, TcGemmCfg<128, 1>::SMEM, st, a1, a2, w.map, p);
+  } else {
+    if (w.BN == 64) launch_k(k_gemm_tc<64, 3>, grid, 192, TcGemmCfg<64, 3>::SMEM, st, a1, a2, w.map, p);
+    else launch_k(k_gemm_tc<128, 3>, grid, 192, TcGemmCfg<128, 3>::SMEM, st, a1, a2, w.map, p);
+  }
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
   if (launches) ++*launches;
   B2S_LAUNCH_CHECK();
   return 0;
 }
 
-static int tc_attention(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& map, AttnTcParams ap, long long* launches) {
-  const int maxq = std::max(ap.prob[0].nq, ap.prob[1].nq);
+// one attention launch over the q/k/v planes in qkvb viewed with row length ld (768 self, 512 cross)
+static int tc_attention(LgTensorCore* tc, cudaStream_t st, int ld, const AttnTcProb (&prob)[2], int qcol, int kcol, int vcol, int cross,
+                        long long* launches) {
+  const int maxq = std::max(prob[0].nq, prob[1].nq);
   if (maxq <= 0) return 0;
-  ap.scale_log2e = 0.125f * 1.4426950408889634f;
-  ap.out = tc->ctxb; ap.ldo = 256; ap.ctrl = tc->ctrl;
+  const float scale_log2e = 0.125f * 1.4426950408889634f;
   dim3 grid(cdiv(maxq, ATC_BQ), 4, 2);
   if (tc->prof) tc->prof->mark(PROF_ATTN, st);
-  launch_k(k_attn_tc, grid, ATC_THREADS, ATC_SMEM, st, map, ap);
+  if (tc->np == 1) {
+    AttnTcParams ap = {};
+    ap.prob[0] = prob[0]; ap.prob[1] = prob[1]; ap.qcol = qcol; ap.kcol = kcol; ap.vcol = vcol; ap.cross = cross;
+    ap.scale_log2e = scale_log2e; ap.out = tc->ctxb; ap.ldo = 256; ap.ctrl = tc->ctrl;
+    launch_k(k_attn_tc, grid, ATC_THREADS, ATC_SMEM, st, ld == 768 ? tc->m_qkv768 : tc->m_qkv512, ap);
+  } else {
+    Attn3Params ap = {};
+    ap.prob[0] = prob[0]; ap.prob[1] = prob[1]; ap.qcol = qcol; ap.kcol = kcol; ap.vcol = vcol; ap.cross = cross;
+    ap.plane_rows = 2 * tc->cap;
+    ap.scale_log2e = scale_log2e; ap.out = tc->ctxb; ap.ldo = 256; ap.out_plane = (size_t)2 * tc->cap * 256; ap.ctrl = tc->ctrl;
+    launch_k(k_attn_tc3, grid, A3_THREADS, A3_SMEM, st, ld == 768 ? tc->m_qkv768 : tc->m_qkv512,
+             ld == 768 ? tc->m_kv768 : tc->m_kv512, ap);
+  }
   if (tc->prof) tc->prof->mark(PROF_ATTN, st);
   if (launches) ++*launches;
   B2S_LAUNCH_CHECK();
@@ -257,19 +316,22 @@ static int tc_ffn(LgTensorCore* tc, cudaStream_t st, float* x, const TcLinear& w
   p.epi = TC_EPI_F32; p.out_f32 = tc->h1f; p.ld_f32 = 512;
   B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_ctxb, 256, w1, p, m, n, launches));          // [x | ctx] W1'^T + b1' (out_proj folded)
   dim3 g(cdiv(std::max(m, n), 8), 2);
-  launch_k(k_ln_gelu_512_bf16, g, 256, 0, st, tc->h1f, tc->h1b, 0, m, tc->cap, n, lng, lnb, tc->ctrl);
+  const size_t hplane = (size_t)2 * tc->cap * 512;
+  if (tc->np == 1) launch_k(k_ln_gelu_512_bf16<1>, g, 256, 0, st, tc->h1f, tc->h1b, hplane, 0, m, tc->cap, n, lng, lnb, tc->ctrl);
+  else launch_k(k_ln_gelu_512_bf16<3>, g, 256, 0, st, tc->h1f, tc->h1b, hplane, 0, m, tc->cap, n, lng, lnb, tc->ctrl);
   if (launches) ++*launches;
   B2S_LAUNCH_CHECK();
   p = TcGemmParams();
   p.epi = TC_EPI_RESID_F32_BF16; p.out_f32 = x; p.ld_f32 = 256; p.out_bf16 = tc->xb; p.ld_bf16 = 256;
-  return tc_gemm(tc, st, tc->m_h1b, tc->m_h1b, 512, w2, p, m, n, launches);              // x += h W2^T + b2 ; xb = bf16(x)
+  return tc_gemm(tc, st, tc->m_h1b, tc->m_h1b, 512, w2, p, m, n, launches);              // x += h W2^T + b2 ; xb = planes(x)
 }
 
 __nv_bfloat16* lgtc_xb(LgTensorCore* tc) { return tc->xb; }
+int lgtc_planes(LgTensorCore* tc) { return tc->np; }
 
 // One transformer layer.  m, n are upper bounds of the live point counts (they size the grids); the
 // live counts and the early-exit flag are read from `ctrl` on the device.  `x` is the fp32 residual
-// stream of this layer; its bf16 copy xb is maintained by the FFN epilogues / the pruning gather
+// stream of this layer; its bf16 plane copy xb is maintained by the FFN epilogues / the pruning gather
 // (derive_xb: re-derive it from x first - layer 0, right after the input projection).
 int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int li, float* x, const float* cosb, const float* sinb, int cap, int m, int n,
                const int* ctrl, bool derive_xb, long long* launches) {
@@ -278,7 +340,9 @@ int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int li, float* x, const float*
   tc->ctrl = ctrl;
   if (derive_xb) {
     dim3 g(cdiv(std::max(m, n), 8), 2);
-    launch_k(k_f32_to_bf16_rows, g, 256, 0, st, x, tc->xb, 256, 0, m, cap, n, ctrl);
+    const size_t xplane = (size_t)2 * cap * 256;
+    if (tc->np == 1) launch_k(k_f32_to_bf16_rows<1>, g, 256, 0, st, x, tc->xb, 256, xplane, 0, m, cap, n, ctrl);
+    else launch_k(k_f32_to_bf16_rows<3>, g, 256, 0, st, x, tc->xb, 256, xplane, 0, m, cap, n, ctrl);
     if (launches) ++*launches;
     B2S_LAUNCH_CHECK();
   }
@@ -286,18 +350,18 @@ int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int li, float* x, const float*
   // ---- self block ----
   p.epi = TC_EPI_ROTARY_BF16; p.out_bf16 = tc->qkvb; p.ld_bf16 = 768; p.rot_cos = cosb; p.rot_sin = sinb; p.rot_cols = 512;
   B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_xb, 256, l.qkv, p, m, n, launches));
-  AttnTcParams ap = {};
-  ap.qcol = 0; ap.kcol = 256; ap.vcol = 512; ap.cross = 0;
-  ap.prob[0] = {0, 0, m, m}; ap.prob[1] = {cap, cap, n, n};
-  B2S_TRY(tc_attention(tc, st, tc->m_qkv768, ap, launches));
+  {
+    const AttnTcProb prob[2] = {{0, 0, m, m}, {cap, cap, n, n}};
+    B2S_TRY(tc_attention(tc, st, 768, prob, 0, 256, 512, 0, launches));
+  }
   B2S_TRY(tc_ffn(tc, st, x, l.w1, l.lng, l.lnb, l.w2, m, n, launches));
   // ---- cross block ----
   p = TcGemmParams(); p.epi = TC_EPI_BF16; p.out_bf16 = tc->qkvb; p.ld_bf16 = 512;
   B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_xb, 256, l.cqkv, p, m, n, launches));
-  ap = AttnTcParams();
-  ap.qcol = 0; ap.kcol = 0; ap.vcol = 256; ap.cross = 1;
-  ap.prob[0] = {0, cap, m, n}; ap.prob[1] = {cap, 0, n, m};
-  B2S_TRY(tc_attention(tc, st, tc->m_qkv512, ap, launches));
+  {
+    const AttnTcProb prob[2] = {{0, cap, m, n}, {cap, 0, n, m}};
+    B2S_TRY(tc_attention(tc, st, 512, prob, 0, 0, 256, 1, launches));
+  }
   return tc_ffn(tc, st, x, l.cw1, l.clng, l.clnb, l.cw2, m, n, launches);
 }
 
@@ -306,104 +370,152 @@ int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int li, float* x, const float*
 // ---- unit-test entry points (host buffers) --------------------------------------------------
 using namespace b2s;
 
-static std::vector<__nv_bfloat16> to_bf16(const float* x, size_t n) {
-  std::vector<__nv_bfloat16> v(n);
-  for (size_t i = 0; i < n; ++i) v[i] = __float2bfloat16_rn(x[i]);
+// host fp32 [rows, cols] -> np bf16 planes [np][rows_pad, cols] (zero padded)
+static std::vector<__nv_bfloat16> to_planes(const float* x, size_t rows, size_t cols, size_t rows_pad, int np) {
+  std::vector<__nv_bfloat16> v((size_t)np * rows_pad * cols, __float2bfloat16_rn(0.f));
+  for (size_t i = 0; i < rows; ++i)
+    for (size_t c = 0; c < cols; ++c) {
+      float r = x[i * cols + c];
+      for (int p = 0; p < np; ++p) {
+        const __nv_bfloat16 b = __float2bfloat16_rn(r);
+        v[((size_t)p * rows_pad + i) * cols + c] = b;
+        r -= __bfloat162float(b);
+      }
+    }
   return v;
 }
 
-// C[M,N] (fp32) = A[M,K] W[N,K]^T + bias, operands rounded to bf16.  M, N multiples of 64; K of 64.
-extern "C" int b2s_test_gemm_tc(const float* A, const float* W, const float* bias, int M, int N, int K, float* C) {
+// C[M,N] (fp32) = A[M,K] W[N,K]^T + bias.  planes = 1: operands rounded to bf16; planes = 3: fp32
+// operands carried as bf16x3.  N, K multiples of 64.
+static int test_gemm(const float* A, const float* W, const float* bias, int M, int N, int K, float* C, int np) {
   if (!A || !W || !C || M <= 0 || N % 64 || K % 64) { set_error("b2s_test_gemm_tc: bad shape"); return B2S_EINVAL; }
   DeviceArena ar;
   const int Mp = cdiv(M, 128) * 128;
-  __nv_bfloat16 *dA, *dW; float *dB, *dC;
-  std::vector<__nv_bfloat16> hA = to_bf16(A, (size_t)M * K), hW = to_bf16(W, (size_t)N * K);
-  B2S_TRY(ar.alloc(&dA, (size_t)Mp * K)); B2S_TRY(ar.alloc(&dW, (size_t)N * K)); B2S_TRY(ar.alloc(&dB, (size_t)N)); B2S_TRY(ar.alloc(&dC, (size_t)Mp * N));
-  B2S_CUDA(cudaMemset(dA, 0, (size_t)Mp * K * 2));
+  __nv_bfloat16 *dA, *dW; float *dB, *dC, *dWf;
+  std::vector<__nv_bfloat16> hA = to_planes(A, M, K, Mp, np);
+  B2S_TRY(ar.alloc(&dA, hA.size())); B2S_TRY(ar.alloc(&dW, (size_t)np * N * K)); B2S_TRY(ar.alloc(&dWf, (size_t)N * K));
+  B2S_TRY(ar.alloc(&dB, (size_t)N)); B2S_TRY(ar.alloc(&dC, (size_t)Mp * N));
   B2S_CUDA(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
-  B2S_CUDA(cudaMemcpy(dW, hW.data(), hW.size() * 2, cudaMemcpyHostToDevice));
+  B2S_CUDA(cudaMemcpy(dWf, W, (size_t)N * K * 4, cudaMemcpyHostToDevice));
+  k_weight_planes<<<(unsigned)(((size_t)N * K + 255) / 256), 256>>>(dWf, dW, N, K, np);
+  B2S_LAUNCH_CHECK();
   std::vector<float> zb(N, 0.f);
   B2S_CUDA(cudaMemcpy(dB, bias ? bias : zb.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
   const int BN = N % 128 == 0 && N > 256 ? 128 : 64;
   CUtensorMap ma, mw;
-  B2S_TRY(make_tmap_bf16_2d(&ma, dA, K, Mp, (uint64_t)K * 2, 64, 128));
-  B2S_TRY(make_tmap_bf16_2d(&mw, dW, K, N, (uint64_t)K * 2, 64, BN));
-  cudaFuncSetAttribute(k_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGemmCfg<64>::SMEM);
-  cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGemmCfg<128>::SMEM);
+  B2S_TRY(make_tmap_bf16_2d(&ma, dA, K, (uint64_t)np * Mp, (uint64_t)K * 2, 64, 128));
+  B2S_TRY(make_tmap_bf16_2d(&mw, dW, (uint64_t)np * K, N, (uint64_t)np * K * 2, 64, BN));
+  tc_kernel_attrs();
   TcGemmParams p = {};
-  p.K = K; p.K1 = K; p.N = N; p.bias = dB; p.epi = TC_EPI_F32; p.out_f32 = dC; p.ld_f32 = N;
+  p.K = K; p.K1 = K; p.N = N; p.bias = dB; p.epi = TC_EPI_F32; p.out_f32 = dC; p.ld_f32 = N; p.plane_rows = Mp;
   p.seg_base[0] = 0; p.seg_rows[0] = M; p.seg_base[1] = 0; p.seg_rows[1] = 0; p.tiles0 = cdiv(M, 128);
   dim3 grid(N / BN, p.tiles0);
-  if (BN == 64) k_gemm_tc<64><<<grid, 192, TcGemmCfg<64>::SMEM>>>(ma, ma, mw, p);
-  else k_gemm_tc<128><<<grid, 192, TcGemmCfg<128>::SMEM>>>(ma, ma, mw, p);
+  if (np == 1) {
+    if (BN == 64) k_gemm_tc<64, 1><<<grid, 192, TcGemmCfg<64, 1>::SMEM>>>(ma, ma, mw, p);
+    else k_gemm_tc<128, 1><<<grid, 192, TcGemmCfg<128, 1>::SMEM>>>(ma, ma, mw, p);
+  } else {
+    if (BN == 64) k_gemm_tc<64, 3><<<grid, 192, TcGemmCfg<64, 3>::SMEM>>>(ma, ma, mw, p);
+    else k_gemm_tc<128, 3><<<grid, 192, TcGemmCfg<128, 3>::SMEM>>>(ma, ma, mw, p);
+  }
   B2S_LAUNCH_CHECK();
   B2S_CUDA(cudaDeviceSynchronize());
   B2S_CUDA(cudaMemcpy(C, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
+extern "C" int b2s_test_gemm_tc(const float* A, const float* W, const float* bias, int M, int N, int K, float* C) {
+  return test_gemm(A, W, bias, M, N, K, C, 1);
+}
+extern "C" int b2s_test_gemm_tc3(const float* A, const float* W, const float* bias, int M, int N, int K, float* C) {
+  return test_gemm(A, W, bias, M, N, K, C, 3);
+}
 
-// ctx[nq,256] = per-head softmax(q k^T / 8) v, 4 heads of 64; operands rounded to bf16.
-extern "C" int b2s_test_attn_tc(const float* q, const float* k, const float* v, int nq, int nk, float* ctx) {
-  if (!q || !k || !v || !ctx || nq <= 0 || nk <= 0) { set_error("b2s_test_attn_tc: bad shape"); return B2S_EINVAL; }
+// uploads q | k | v as [np][R, 768] planes and launches one attention (z problems); ctx planes come back summed
+static int run_attn(int np, const std::vector<__nv_bfloat16>& buf, int R, const AttnTcProb (&prob)[2], int nz, int maxq, int iters,
+                    float* ms_out, float* ctx, int nq_out) {
   DeviceArena ar;
-  const int R = cdiv(std::max(nq, nk), 128) * 128;
-  std::vector<__nv_bfloat16> buf((size_t)R * 768, __float2bfloat16_rn(0.f));
-  for (int i = 0; i < nq; ++i) for (int c = 0; c < 256; ++c) buf[(size_t)i * 768 + c] = __float2bfloat16_rn(q[(size_t)i * 256 + c]);
-  for (int i = 0; i < nk; ++i) for (int c = 0; c < 256; ++c) {
-    buf[(size_t)i * 768 + 256 + c] = __float2bfloat16_rn(k[(size_t)i * 256 + c]);
-    buf[(size_t)i * 768 + 512 + c] = __float2bfloat16_rn(v[(size_t)i * 256 + c]);
-  }
   __nv_bfloat16 *dq, *dctx;
-  B2S_TRY(ar.alloc(&dq, buf.size())); B2S_TRY(ar.alloc(&dctx, (size_t)R * 256));
+  B2S_TRY(ar.alloc(&dq, buf.size())); B2S_TRY(ar.alloc(&dctx, (size_t)np * R * 256));
   B2S_CUDA(cudaMemcpy(dq, buf.data(), buf.size() * 2, cudaMemcpyHostToDevice));
-  B2S_CUDA(cudaMemset(dctx, 0, (size_t)R * 256 * 2));
-  CUtensorMap map;
-  B2S_TRY(make_tmap_bf16_2d(&map, dq, 768, R, 1536, 64, 128));
-  cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
-  AttnTcParams ap = {};
-  ap.qcol = 0; ap.kcol = 256; ap.vcol = 512; ap.prob[0] = {0, 0, nq, nk}; ap.prob[1] = {0, 0, 0, 0};
-  ap.scale_log2e = 0.125f * 1.4426950408889634f; ap.out = dctx; ap.ldo = 256;
-  k_attn_tc<<<dim3(cdiv(nq, 128), 4, 1), ATC_THREADS, ATC_SMEM>>>(map, ap);
+  B2S_CUDA(cudaMemset(dctx, 0, (size_t)np * R * 256 * 2));
+  CUtensorMap mq, mkv;
+  B2S_TRY(make_tmap_bf16_2d(&mq, dq, 768, (uint64_t)np * R, 1536, 64, 128));
+  B2S_TRY(make_tmap_bf16_2d(&mkv, dq, 768, (uint64_t)np * R, 1536, 64, 64));
+  tc_kernel_attrs();
+  const float sc = 0.125f * 1.4426950408889634f;
+  AttnTcParams a1 = {};
+  a1.qcol = 0; a1.kcol = 256; a1.vcol = 512; a1.prob[0] = prob[0]; a1.prob[1] = prob[1]; a1.scale_log2e = sc; a1.out = dctx; a1.ldo = 256;
+  Attn3Params a3 = {};
+  a3.qcol = 0; a3.kcol = 256; a3.vcol = 512; a3.prob[0] = prob[0]; a3.prob[1] = prob[1]; a3.scale_log2e = sc; a3.out = dctx; a3.ldo = 256;
+  a3.plane_rows = R; a3.out_plane = (size_t)R * 256;
+  const dim3 grid(cdiv(maxq, 128), 4, nz);
+  auto launch = [&]() {
+    if (np == 1) k_attn_tc<<<grid, ATC_THREADS, ATC_SMEM>>>(mq, a1);
+    else k_attn_tc3<<<grid, A3_THREADS, A3_SMEM>>>(mq, mkv, a3);
+  };
+  if (iters > 0) {
+    cudaEvent_t e0, e1;
+    B2S_CUDA(cudaEventCreate(&e0)); B2S_CUDA(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) launch();
+    B2S_CUDA(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i) launch();
+    B2S_CUDA(cudaEventRecord(e1));
+    B2S_LAUNCH_CHECK();
+    B2S_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    B2S_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = ms / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+  }
+  launch();
   B2S_LAUNCH_CHECK();
   B2S_CUDA(cudaDeviceSynchronize());
-  std::vector<__nv_bfloat16> out((size_t)nq * 256);
+  std::vector<__nv_bfloat16> out((size_t)np * R * 256);
   B2S_CUDA(cudaMemcpy(out.data(), dctx, out.size() * 2, cudaMemcpyDeviceToHost));
-  for (size_t i = 0; i < out.size(); ++i) ctx[i] = __bfloat162float(out[i]);
+  for (size_t i = 0; i < (size_t)nq_out * 256; ++i) {
+    float acc = 0.f;
+    for (int p = np - 1; p >= 0; --p) acc += __bfloat162float(out[(size_t)p * R * 256 + i]);
+    ctx[i] = acc;
+  }
   return 0;
 }
 
-// Device-only timing of the attention kernel on random bf16 data: one launch = what a LightGlue
-// self block issues (2 problems x 4 heads, nq queries x nk keys each).  ms_out = mean per launch.
-extern "C" int b2s_bench_attn_tc(int nq, int nk, int iters, float* ms_out) {
-  if (nq <= 0 || nk <= 0 || iters <= 0 || !ms_out) { set_error("b2s_bench_attn_tc: bad argument"); return B2S_EINVAL; }
-  DeviceArena ar;
-  const int cap = cdiv(std::max(nq, nk), 128) * 128;
-  const size_t R = (size_t)2 * cap;
-  std::vector<__nv_bfloat16> buf(R * 768);
-  uint32_t s = 12345u;
-  for (auto& b : buf) { s = s * 1664525u + 1013904223u; b = __float2bfloat16_rn(((s >> 8) & 0xFFFF) / 32768.f - 1.f); }
-  __nv_bfloat16 *dq, *dctx;
-  B2S_TRY(ar.alloc(&dq, buf.size())); B2S_TRY(ar.alloc(&dctx, R * 256));
-  B2S_CUDA(cudaMemcpy(dq, buf.data(), buf.size() * 2, cudaMemcpyHostToDevice));
-  CUtensorMap map;
-  B2S_TRY(make_tmap_bf16_2d(&map, dq, 768, R, 1536, 64, 128));
-  cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
-  AttnTcParams ap = {};
-  ap.qcol = 0; ap.kcol = 256; ap.vcol = 512; ap.prob[0] = {0, 0, nq, nk}; ap.prob[1] = {cap, cap, nq, nk};
-  ap.scale_log2e = 0.125f * 1.4426950408889634f; ap.out = dctx; ap.ldo = 256;
-  cudaEvent_t e0, e1;
-  B2S_CUDA(cudaEventCreate(&e0)); B2S_CUDA(cudaEventCreate(&e1));
-  const dim3 grid(cdiv(nq, 128), 4, 2);
-  for (int i = 0; i < 3; ++i) k_attn_tc<<<grid, ATC_THREADS, ATC_SMEM>>>(map, ap);
-  B2S_CUDA(cudaEventRecord(e0));
-  for (int i = 0; i < iters; ++i) k_attn_tc<<<grid, ATC_THREADS, ATC_SMEM>>>(map, ap);
-  B2S_CUDA(cudaEventRecord(e1));
-  B2S_LAUNCH_CHECK();
-  B2S_CUDA(cudaEventSynchronize(e1));
-  float ms = 0.f;
-  B2S_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-  *ms_out = ms / iters;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  return 0;
+// ctx[nq,256] = per-head softmax(q k^T / 8) v, 4 heads of 64.  planes = 1: operands rounded to bf16; 3: bf16x3.
+static int test_attn(const float* q, const float* k, const float* v, int nq, int nk, float* ctx, int np) {
+  if (!q || !k || !v || !ctx || nq <= 0 || nk <= 0) { set_error("b2s_test_attn_tc: bad shape"); return B2S_EINVAL; }
+  const int R = cdiv(std::max(nq, nk), 128) * 128;
+  std::vector<float> f((size_t)R * 768, 0.f);
+  for (int i = 0; i < nq; ++i) std::memcpy(&f[(size_t)i * 768], q + (size_t)i * 256, 256 * 4);
+  for (int i = 0; i < nk; ++i) {
+    std::memcpy(&f[(size_t)i * 768 + 256], k + (size_t)i * 256, 256 * 4);
+    std::memcpy(&f[(size_t)i * 768 + 512], v + (size_t)i * 256, 256 * 4);
+  }
+  std::vector<__nv_bfloat16> buf = to_planes(f.data(), R, 768, R, np);
+  const AttnTcProb prob[2] = {{0, 0, nq, nk}, {0, 0, 0, 0}};
+  return run_attn(np, buf, R, prob, 1, nq, 0, nullptr, ctx, nq);
 }
+extern "C" int b2s_test_attn_tc(const float* q, const float* k, const float* v, int nq, int nk, float* ctx) {
+  return test_attn(q, k, v, nq, nk, ctx, 1);
+}
+extern "C" int b2s_test_attn_tc3(const float* q, const float* k, const float* v, int nq, int nk, float* ctx) {
+  return test_attn(q, k, v, nq, nk, ctx, 3);
+}
+
+// Device-only timing of the attention kernel on random data: one launch = what a LightGlue self
+// block issues (2 problems x 4 heads, nq queries x nk keys each).  ms_out = mean per launch.
+static int bench_attn(int nq, int nk, int iters, float* ms_out, int np) {
+  if (nq <= 0 || nk <= 0 || iters <= 0 || !ms_out) { set_error("b2s_bench_attn_tc: bad argument"); return B2S_EINVAL; }
+  const int cap = cdiv(std::max(nq, nk), 128) * 128;
+  const int R = 2 * cap;
+  std::vector<__nv_bfloat16> buf((size_t)np * R * 768);
+  uint32_t s = 12345u;
+  for (size_t i = 0; i < buf.size(); ++i) {
+    s = s * 1664525u + 1013904223u;
+    const float scale = i < (size_t)R * 768 ? 1.f : (i < (size_t)2 * R * 768 ? 1.f / 256 : 1.f / 65536);   // lower planes are small
+    buf[i] = __float2bfloat16_rn((((s >> 8) & 0xFFFF) / 32768.f - 1.f) * scale);
+  }
+  const AttnTcProb prob[2] = {{0, 0, nq, nk}, {cap, cap, nq, nk}};
+  return run_attn(np, buf, R, prob, 2, nq, iters, ms_out, nullptr, 0);
+}
+extern "C" int b2s_bench_attn_tc(int nq, int nk, int iters, float* ms_out) { return bench_attn(nq, nk, iters, ms_out, 1); }
+extern "C" int b2s_bench_attn_tc3(int nq, int nk, int iters, float* ms_out) { return bench_attn(nq, nk, iters, ms_out, 3); }

@@ -1,4 +1,5 @@
-// lightglue_tc.cuh - bf16 tcgen05/TMEM path of the LightGlue layer (interface).
+// lightglue_tc.cuh - tcgen05/TMEM path of the LightGlue layer (interface): bf16 operands (planes = 1)
+// or fp32 carried as three bf16 planes (planes = 3, fp32-faithful).
 #pragma once
 #include <cuda_bf16.h>
 #include "common.cuh"
@@ -11,14 +12,15 @@ struct LgTcLayerSrc {   // fp32 device weights of one layer (self block then cro
   const float *cwqkv, *cbqkv, *cwo, *cbo, *cw1, *cb1, *clng, *clnb, *cw2, *cb2;
 };
 
-int lgtc_create(LgTensorCore** out, size_t n_layers);
+int lgtc_create(LgTensorCore** out, size_t n_layers, int planes);
 int lgtc_set_layer(LgTensorCore* tc, int layer, const LgTcLayerSrc& src);
 int lgtc_alloc_ws(LgTensorCore* tc, int cap);
 // one full transformer layer (self + cross) in place on x [2*cap,256] fp32 master copy; m, n bound the
 // live counts (grid sizes), the live counts / early-exit flag come from the device state `ctrl`
 int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int layer, float* x, const float* cosb, const float* sinb, int cap,
                int m, int n, const int* ctrl, bool derive_xb, long long* launches);
-__nv_bfloat16* lgtc_xb(LgTensorCore* tc);   // bf16 copy of the residual stream (the pruning gather refreshes it)
+__nv_bfloat16* lgtc_xb(LgTensorCore* tc);   // bf16 plane copy of the residual stream (the pruning gather refreshes it)
+int lgtc_planes(LgTensorCore* tc);
 void lgtc_destroy(LgTensorCore* tc);
 void lgtc_set_prof(LgTensorCore* tc, KernelProf* prof);
 

@@ -121,6 +121,35 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, 
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- fp32 carried as bf16 planes --------------------------------------------------------------
+// x = a0 + a1 + a2 exactly up to 24 significant bits (each a_i a bf16, a_{i+1} = bf16(residual)):
+// with six cross products a_i b_j (i + j <= 2) accumulated in fp32 the tensor core reproduces an
+// fp32 dot product to fp32 rounding level.  pack_planes2 splits two values and returns, per plane,
+// the packed bf16x2 word (first value in the low half).
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <int NP>
+__device__ __forceinline__ void pack_planes2(float a, float b, uint32_t (&w)[NP]) {
+  w[0] = pack_bf16x2(a, b);
+  if (NP > 1) {
+    a -= __uint_as_float(w[0] << 16); b -= __uint_as_float(w[0] & 0xFFFF0000u);
+    w[1] = pack_bf16x2(a, b);
+  }
+  if (NP > 2) {
+    a -= __uint_as_float(w[1] << 16); b -= __uint_as_float(w[1] & 0xFFFF0000u);
+    w[2] = pack_bf16x2(a, b);
+  }
+}
+// operand-plane pairs (a_i, b_j) of the split product, smallest contributions first
+template <int NP> struct PlaneTerms {
+  static constexpr int N = NP == 1 ? 1 : 6;
+  // NP == 3: (2,0) (1,1) (0,2) (1,0) (0,1) (0,0)
+  __host__ __device__ static constexpr int a(int t) { return NP == 1 ? 0 : (t == 0 ? 2 : (t == 1 || t == 3) ? 1 : 0); }
+  __host__ __device__ static constexpr int b(int t) { return NP == 1 ? 0 : (t == 2 ? 2 : (t == 1 || t == 4) ? 1 : 0); }
+};
+
 }  // namespace tc
 
 // host: 2-D bf16 tensor map, 128-byte swizzle. inner = contiguous extent (elements), box_inner must be 64.

@@ -186,6 +186,8 @@ class LightGlue(_Module):
             raise ValueError("only features='aliked' is supported")
         self.depth_confidence, self.width_confidence = float(depth_confidence), float(width_confidence)
         self.filter_threshold, self.pruning_threshold = float(filter_threshold), int(pruning_threshold)
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
         self.precision, self.max_kp = precision, int(max_kp)
         if weights is None:
             weights, self.weight_source = _weights.load_lightglue_state(seed)
@@ -202,7 +204,7 @@ class LightGlue(_Module):
         cfg.n_layers = self.n_layers
         cfg.depth_conf, cfg.width_conf, cfg.filter_thresh = self.depth_confidence, self.width_confidence, self.filter_threshold
         cfg.pruning_min_kpts = self.pruning_threshold
-        cfg.precision = _lib.BF16 if self.precision == "bf16" else _lib.FP32
+        cfg.precision = _lib.PRECISIONS[self.precision]
         cfg.max_kp = self.max_kp
         h = C.c_void_p()
         check(lib.b2s_lightglue_create(C.byref(cfg), self._blob, len(self._blob), dev.index, C.byref(h)), "b2s_lightglue_create")

@@ -27,7 +27,7 @@ CASES = {
 def _models(wkw, mkw, n_layers=9):
     from b200slam import frontend
     sd = weights.synthetic_lightglue_state(seed=0, n_layers=n_layers, **wkw)
-    ora = oracle.LightGlue(n_layers=n_layers, **mkw).eval()
+    ora = oracle.LightGlue(n_layers=n_layers, **{k: v for k, v in mkw.items() if k != "precision"}).eval()
     ora.load_state_dict(sd, strict=False)
     return ora, frontend.LightGlue(weights=sd, **mkw)
 
@@ -58,6 +58,18 @@ def test_match_parity_through_c_abi(name):
         assert rel_err(rg[k], ro[k][0].numpy()) < 1e-3, k
     if name.startswith("adaptive"):
         assert ro["prune0"][0].min() < ro["stop"], "pruning must actually happen in this case"
+
+
+@pytest.mark.parametrize("name", ["headline_2048", "adaptive_prune_and_stop"])
+def test_simt_cross_check_path(name):
+    """precision='fp32_simt' (CUDA-core fp32, the cross-check of the tensor-core fp32 path) meets the same bar."""
+    m, n, wkw, mkw = CASES[name]
+    ora, mat = _models(wkw, dict(mkw, precision="fp32_simt"))
+    k0, d0, k1, d1, _ = noisy_copy_pair(m, n, seed=1)
+    ro = _oracle_run(ora, k0, d0, k1, d1)
+    rg = mat.match_host(k0.numpy(), d0.numpy(), k1.numpy(), d1.numpy(), full=True)
+    assert np.array_equal(rg["matches"], ro["matches"][0].numpy()) and rg["stop"] == ro["stop"]
+    assert rel_err(rg["scores"], ro["scores"][0].numpy()) < 1e-3
 
 
 def test_layer_taps_and_similarity():

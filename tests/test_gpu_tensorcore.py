@@ -44,6 +44,35 @@ def test_attn_tc(nq, nk):
     assert err < 2e-2, f"rel err {err}"      # P and the output are rounded to bf16 (2^-8)
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (200, 256, 256), (4096, 768, 256), (1000, 512, 512), (333, 256, 512)])
+def test_gemm_tc3_is_fp32_faithful(M, N, K):
+    """fp32 operands carried as three bf16 planes, six cross products: error vs a float64 reference must be at the
+    level of an fp32 GEMM.  Tolerance 4e-6 of the output scale: the operand split itself is exact to 2^-26, what is
+    left is the tensor core's fp32 accumulator (it truncates after every k-step; 6 x K/16 steps)."""
+    from b200slam import _lib
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g); W = torch.randn(N, K, generator=g) / K ** 0.5; b = torch.randn(N, generator=g)
+    out = np.empty((M, N), np.float32)
+    _lib.check(_lib.lib.b2s_test_gemm_tc3(A.numpy().ctypes.data, W.numpy().ctypes.data, b.numpy().ctypes.data, M, N, K, out.ctypes.data), "gemm_tc3")
+    ref = (A.double() @ W.double().T + b.double()).numpy()
+    err = np.abs(out - ref).max() / np.abs(ref).max()
+    err32 = np.abs((A @ W.T + b).numpy() - ref).max() / np.abs(ref).max()
+    assert err < 4e-6, f"rel err {err} (torch fp32: {err32})"
+
+
+@pytest.mark.parametrize("nq,nk", [(128, 128), (128, 64), (300, 200), (2048, 2048), (1, 77), (129, 1), (640, 1000)])
+def test_attn_tc3_is_fp32_faithful(nq, nk):
+    from b200slam import _lib
+    g = torch.Generator().manual_seed(nq * 7 + nk)
+    q = 2 * torch.randn(nq, 256, generator=g); k = torch.randn(nk, 256, generator=g); v = torch.randn(nk, 256, generator=g)
+    out = np.empty((nq, 256), np.float32)
+    _lib.check(_lib.lib.b2s_test_attn_tc3(q.numpy().ctypes.data, k.numpy().ctypes.data, v.numpy().ctypes.data, nq, nk, out.ctypes.data), "attn_tc3")
+    sp = lambda t: t.double().view(-1, 4, 64).transpose(0, 1)   # noqa: E731
+    ref = torch.nn.functional.scaled_dot_product_attention(sp(q)[None], sp(k)[None], sp(v)[None])[0].transpose(0, 1).reshape(nq, 256).numpy()
+    err = np.abs(out - ref).max() / np.abs(ref).max()
+    assert err < 5e-6, f"rel err {err}"      # fp32 softmax with ex2.approx: a few fp32 ulps of the output scale
+
+
 @pytest.mark.parametrize("m,n", [(2048, 2048), (700, 512)])
 def test_bf16_matcher_agreement_with_fp32_oracle(m, n):
     from b200slam import frontend

@@ -10,6 +10,8 @@ def attn():
         _lib.check(_lib.lib.b2s_bench_attn_tc(nq, nk, 50, C.byref(ms)), "bench_attn")
         fl = 2 * 4 * 4.0 * nq * nk * 64          # executed: QK^T + PV, 4 heads, 2 problems
         print(f"attn_tc {nq}x{nk}: {ms.value*1e3:.2f} us/launch  {fl/ms.value/1e9:.1f} TFLOP/s executed", flush=True)
+        _lib.check(_lib.lib.b2s_bench_attn_tc3(nq, nk, 50, C.byref(ms)), "bench_attn3")
+        print(f"attn_tc3 {nq}x{nk}: {ms.value*1e3:.2f} us/launch  {fl/ms.value/1e9:.1f} TFLOP/s fp32-equivalent ({6*fl/ms.value/1e9:.1f} bf16 issued)", flush=True)
 
 if __name__ == "__main__":
     {"attn": attn}[sys.argv[1]]()
