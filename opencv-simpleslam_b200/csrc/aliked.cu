@@ -3,6 +3,7 @@
 // /root/reference/slam/core/features_utils.py:94,219-222; arithmetic spec: SURVEY.md A.1/A.2.
 #include "aliked_kernels.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -16,6 +17,10 @@ struct DcnBlockW {   // ResBlock with deformable convs (block3 / block4)
   float *ds_w, *ds_b;                         // downsample [cout][cin] + bias
 };
 
+struct TcWeight {     // fp32 weight [N][K] as three bf16 planes [N][3K] + tensor map (box {64, 64})
+  __nv_bfloat16* w = nullptr; CUtensorMap map; int N = 0, K = 0;
+};
+
 struct b2s_aliked {
   b2s_aliked_cfg cfg;
   int device = 0, M = 16, n_limit = 0;
@@ -27,13 +32,17 @@ struct b2s_aliked {
   float *agg_w[4];                                      // conv1..4 [32][ci]
   float *sh0, *sh2, *sh4, *sh6;                         // score head
   float *so0_w, *so0_b, *so2_w, *so2_b, *sf_w, *aggT;   // desc head
+  TcWeight tc_so0, tc_sf, tc_agg;                       // desc-head contractions on the tensor cores (fp32 as bf16x3)
   // workspace
   int wsHp = 0, wsWp = 0;
   float *img_pad, *resized, *t1a, *x1, *r2, *t2a, *x2, *x3in, *col3, *off3, *t3a, *r3, *x3, *x4in, *col4, *off4, *t4a, *r4, *x4;
-  float *x2a, *x3a, *x4a, *s8, *feat, *score, *nms, *cand_sc, *sel_sc, *thr, *kp_norm, *disp, *sampled;
-  float *Apatch, *toff1, *offs, *S, *F, *descraw;
+  float *x2a, *x3a, *x4a, *p8[3], *s8, *score, *nms, *cand_sc, *sel_sc, *thr, *kp_norm, *disp, *sampled;
+  float *toff1, *offs, *descraw;
+  __nv_bfloat16 *Apatch, *S, *F;                        // bf16x3 planes: [3][K][1152], [3][K*M][128], [3][K*M][128]
+  CUtensorMap m_Apatch, m_S, m_F;
   float* skws = nullptr; size_t skws_floats = 0;        // split-K partial sums
   int *cand_idx, *sel_idx, *dk;
+  FeatSrc fsrc = {};                                    // last call's on-demand feature source (SDDH, debug tap)
   int cand_cap = 0;
   // last-call geometry (for debug taps)
   int Hr = 0, Wr = 0, Hp = 0, Wp = 0;
@@ -151,7 +160,35 @@ int load_weights(b2s_aliked* h, const WeightBlob& wb) {
   for (int p = 0; p < M; ++p)
     for (int c = 0; c < 128; ++c)
       for (int d = 0; d < 128; ++d) at[(size_t)d * M * 128 + (size_t)p * 128 + c] = ag->data[((size_t)p * 128 + c) * 128 + d];
-  return h->warena.upload(&h->aggT, at);
+  B2S_TRY(h->warena.upload(&h->aggT, at));
+  auto mk = [&](const float* w_dev, int N, int K, TcWeight* out) -> int {
+    out->N = N; out->K = K;
+    const size_t n = (size_t)N * K;
+    B2S_TRY(h->warena.alloc(&out->w, 3 * n));
+    k_weight_planes<<<(unsigned)((n + 255) / 256), 256>>>(w_dev, out->w, N, K, 3);
+    B2S_LAUNCH_CHECK();
+    return make_tmap_bf16_2d(&out->map, out->w, (uint64_t)3 * K, N, (uint64_t)3 * K * 2, 64, 64);
+  };
+  B2S_TRY(mk(h->so0_w, 2 * M, 1152, &h->tc_so0));
+  B2S_TRY(mk(h->sf_w, 128, 128, &h->tc_sf));
+  B2S_TRY(mk(h->aggT, 128, M * 128, &h->tc_agg));
+  B2S_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+// C = act(A W^T + bias) on the tensor cores, fp32 operands as bf16x3 planes; rows = *n_dev * mult
+int tc_gemm(b2s_aliked* h, cudaStream_t st, const CUtensorMap& a, int plane_rows, const TcWeight& w, const float* bias, int act,
+            int rows_max, const int32_t* n_dev, int mult, float* out_f32, int ldc, __nv_bfloat16* out_planes, size_t out_plane) {
+  TcGemmParams p = {};
+  p.K = w.K; p.K1 = w.K; p.N = w.N; p.bias = bias; p.act = act;
+  p.seg_base[0] = 0; p.seg_rows[0] = rows_max; p.seg_base[1] = 0; p.seg_rows[1] = 0; p.tiles0 = cdiv(rows_max, 128);
+  p.plane_rows = plane_rows; p.m_dev = n_dev; p.m_mult = mult;
+  if (out_f32) { p.epi = TC_EPI_F32; p.out_f32 = out_f32; p.ld_f32 = ldc; }
+  else { p.epi = TC_EPI_BF16; p.out_bf16 = out_planes; p.ld_bf16 = ldc; p.out_plane = out_plane; }
+  launch_k(k_gemm_tc<64, 3>, dim3(cdiv(w.N, 64), p.tiles0), 192, TcGemmCfg<64, 3>::SMEM, st, a, a, w.map, p);
+  ++h->launches;
+  B2S_LAUNCH_CHECK();
+  return 0;
 }
 
 int alloc_ws(b2s_aliked* h, int Hp, int Wp) {
@@ -168,7 +205,8 @@ int alloc_ws(b2s_aliked* h, int Hp, int Wp) {
   B2S_TRY(a.alloc(&h->x4in, 64 * P4)); B2S_TRY(a.alloc(&h->col4, 1152 * P4)); B2S_TRY(a.alloc(&h->off4, 18 * P4));
   B2S_TRY(a.alloc(&h->t4a, 128 * P4)); B2S_TRY(a.alloc(&h->r4, 128 * P4)); B2S_TRY(a.alloc(&h->x4, 128 * P4));
   B2S_TRY(a.alloc(&h->x2a, 32 * P2)); B2S_TRY(a.alloc(&h->x3a, 32 * P3)); B2S_TRY(a.alloc(&h->x4a, 32 * P4));
-  B2S_TRY(a.alloc(&h->s8, 8 * P)); B2S_TRY(a.alloc(&h->feat, 128 * P));
+  B2S_TRY(a.alloc(&h->p8[0], 8 * P2)); B2S_TRY(a.alloc(&h->p8[1], 8 * P3)); B2S_TRY(a.alloc(&h->p8[2], 8 * P4));
+  B2S_TRY(a.alloc(&h->s8, 8 * P));
   B2S_TRY(a.alloc(&h->score, P)); B2S_TRY(a.alloc(&h->nms, P));
   B2S_TRY(a.alloc(&h->cand_idx, P)); B2S_TRY(a.alloc(&h->cand_sc, P));
   h->cand_cap = (int)P;
@@ -177,8 +215,14 @@ int alloc_ws(b2s_aliked* h, int Hp, int Wp) {
   B2S_TRY(a.alloc(&h->kp_norm, 2 * K)); B2S_TRY(a.alloc(&h->disp, K)); B2S_TRY(a.alloc(&h->sampled, K));
   h->skws_floats = std::max<size_t>((size_t)8 * K * 128, (size_t)8 * P3 * 64);
   B2S_TRY(a.alloc(&h->skws, h->skws_floats));
-  B2S_TRY(a.alloc(&h->Apatch, 1152 * K)); B2S_TRY(a.alloc(&h->toff1, 2 * M * K)); B2S_TRY(a.alloc(&h->offs, 2 * M * K));
-  B2S_TRY(a.alloc(&h->S, M * 128 * K)); B2S_TRY(a.alloc(&h->F, M * 128 * K)); B2S_TRY(a.alloc(&h->descraw, 128 * K));
+  B2S_TRY(a.alloc(&h->Apatch, 3 * 1152 * K)); B2S_TRY(a.alloc(&h->toff1, 2 * M * K)); B2S_TRY(a.alloc(&h->offs, 2 * M * K));
+  B2S_TRY(a.alloc(&h->S, 3 * M * 128 * K)); B2S_TRY(a.alloc(&h->F, 3 * M * 128 * K)); B2S_TRY(a.alloc(&h->descraw, 128 * K));
+  // rows past the keypoint count are read by TMA (never stored): keep them finite
+  B2S_CUDA(cudaMemset(h->Apatch, 0, 3 * 1152 * K * 2)); B2S_CUDA(cudaMemset(h->S, 0, 3 * M * 128 * K * 2));
+  B2S_CUDA(cudaMemset(h->F, 0, 3 * M * 128 * K * 2));
+  B2S_TRY(make_tmap_bf16_2d(&h->m_Apatch, h->Apatch, 1152, 3 * K, 1152 * 2, 64, 128));
+  B2S_TRY(make_tmap_bf16_2d(&h->m_S, h->S, 128, 3 * K * M, 128 * 2, 64, 128));
+  B2S_TRY(make_tmap_bf16_2d(&h->m_F, h->F, M * 128, 3 * K, M * 128 * 2, 64, 128));
   h->wsHp = Hp; h->wsWp = Wp;
   return 0;
 }
@@ -233,6 +277,7 @@ extern "C" int b2s_aliked_create(const b2s_aliked_cfg* cfg, const void* weights,
   h->cfg = *cfg; h->device = device;
   h->M = cfg->model == 1 ? 32 : 16;
   h->n_limit = cfg->max_kp > 0 ? cfg->max_kp : 20000;
+  cudaFuncSetAttribute(k_gemm_tc<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGemmCfg<64, 3>::SMEM);
   int rc = load_weights(h, wb);
   if (rc) { delete h; return rc; }
   *out = h;
@@ -333,25 +378,30 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
     g.A1 = h->x4; g.lda1 = 128; g.K1 = 128; g.W = h->agg_w[3]; g.ldw = 128; g.K = 128; g.M = H4 * W4; g.C = h->x4a;
     B2S_TRY(agemm(h, g, st));
   }
-  // ---- fused upsample + concat + normalise + score head ----
+  // ---- score head: level projections at native resolution, fused 1x1 stage, 3x3 tail ----
+  FeatSrc& fs = h->fsrc;
   {
-    AggParams ap;
-    ap.x1 = h->x1; ap.Hp = Hp; ap.Wp = Wp;
-    ap.xa[0] = h->x2a; ap.xa[1] = h->x3a; ap.xa[2] = h->x4a;
+    fs.x1 = h->x1; fs.Hp = Hp; fs.Wp = Wp;
+    fs.xa[0] = h->x2a; fs.xa[1] = h->x3a; fs.xa[2] = h->x4a;
     const int hk[3] = {H2, H3, H4}, wk[3] = {W2, W3, W4};
+    Proj8Params pj;
     for (int l = 0; l < 3; ++l) {
-      ap.Hk[l] = hk[l]; ap.Wk[l] = wk[l];
-      ap.sh[l] = Hp > 1 ? (float)(hk[l] - 1) / (float)(Hp - 1) : 0.f;
-      ap.sw[l] = Wp > 1 ? (float)(wk[l] - 1) / (float)(Wp - 1) : 0.f;
+      fs.Hk[l] = hk[l]; fs.Wk[l] = wk[l];
+      fs.sh[l] = Hp > 1 ? (float)(hk[l] - 1) / (float)(Hp - 1) : 0.f;
+      fs.sw[l] = Wp > 1 ? (float)(wk[l] - 1) / (float)(Wp - 1) : 0.f;
+      pj.xa[l] = fs.xa[l]; pj.out[l] = h->p8[l]; pj.npix[l] = hk[l] * wk[l];
     }
-    ap.W1 = h->agg_w[0]; ap.Ws0 = h->sh0; ap.s8 = h->s8; ap.feat = h->feat;
-    ap.Hr = Hr; ap.Wr = Wr; ap.pad_t = pp.pad_t; ap.pad_l = pp.pad_l;
-    launch_k(k_aliked_agg, dim3(cdiv(Wp, 128), Hp), 128, 0, st, ap);
+    fs.W1 = h->agg_w[0]; fs.Hr = Hr; fs.Wr = Wr; fs.pad_t = pp.pad_t; fs.pad_l = pp.pad_l;
+    pj.Ws0 = h->sh0;
+    launch_k(k_aliked_proj8, cdiv(pj.npix[0] + pj.npix[1] + pj.npix[2], 256), 256, 0, st, pj);
+    S8Params s8p;
+    s8p.src = fs; s8p.P[0] = h->p8[0]; s8p.P[1] = h->p8[1]; s8p.P[2] = h->p8[2]; s8p.Ws0 = h->sh0; s8p.s8 = h->s8;
+    launch_k(k_aliked_s8, dim3(cdiv(Wp, 128), Hp), 128, 0, st, s8p);
     ScoreParams sp;
     sp.s8 = h->s8; sp.Hp = Hp; sp.Wp = Wp; sp.w2 = h->sh2; sp.w4 = h->sh4; sp.w6 = h->sh6;
     sp.score = h->score; sp.Hr = Hr; sp.Wr = Wr; sp.pad_t = pp.pad_t; sp.pad_l = pp.pad_l;
     launch_k(k_aliked_score, dim3(cdiv(Wp, 32), cdiv(Hp, 8)), 256, 0, st, sp);
-    h->launches += 2; B2S_LAUNCH_CHECK();
+    h->launches += 3; B2S_LAUNCH_CHECK();
   }
   // ---- DKD ----
   {
@@ -370,30 +420,22 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
     // upstream puts DKD's 2nd return value (dispersity) under "keypoint_scores" 
     if (scores) B2S_CUDA(cudaMemcpyAsync(scores, h->disp, (size_t)h->n_limit * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
-  // ---- SDDH ----
+  // ---- SDDH: gathers evaluate the feature on demand and emit bf16x3 planes; the three large
+  //      contractions (offset conv K=1152, sf_conv, aggregation K=M*128) run on tcgen05 ----
   {
     const int K = h->n_limit, M = h->M;
     const float clampv = (float)std::max(Hr, Wr) / 4.0f;
-    launch_k(k_sddh_patch, cdiv(K * 9, 8), 256, 0, st, h->feat, Hr, Wr, h->kp_norm, n_out, h->Apatch);
+    launch_k(k_sddh_patch, cdiv(K * 9, 8), 256, 0, st, fs, h->kp_norm, n_out, h->Apatch, (size_t)K * 1152);
     ++h->launches; B2S_LAUNCH_CHECK();
+    B2S_TRY(tc_gemm(h, st, h->m_Apatch, K, h->tc_so0, h->so0_b, 1, K, n_out, 1, h->toff1, 2 * M, nullptr, 0));
     GemmParams g;
-    g.A1 = h->Apatch; g.lda1 = 1152; g.K1 = 1152; g.W = h->so0_w; g.ldw = 1152; g.K = 1152; g.M = K; g.N = 2 * M;
-    g.C = h->toff1; g.ldc = 2 * M; g.bias = h->so0_b; g.act = ACT_SELU; g.m_dev = n_out; g.m_mult = 1;
-    B2S_TRY(agemm(h, g, st));
-    g = GemmParams();
     g.A1 = h->toff1; g.lda1 = 2 * M; g.K1 = 2 * M; g.W = h->so2_w; g.ldw = 2 * M; g.K = 2 * M; g.M = K; g.N = 2 * M;
     g.C = h->offs; g.ldc = 2 * M; g.bias = h->so2_b; g.clamp = clampv; g.m_dev = n_out; g.m_mult = 1;
     B2S_TRY(agemm(h, g, st));
-    launch_k(k_sddh_sample, cdiv(K * M, 8), 256, 0, st, h->feat, Hr, Wr, h->kp_norm, h->offs, M, n_out, h->S);
+    launch_k(k_sddh_sample, cdiv(K * M, 8), 256, 0, st, fs, h->kp_norm, h->offs, M, n_out, h->S, (size_t)K * M * 128);
     ++h->launches; B2S_LAUNCH_CHECK();
-    g = GemmParams();
-    g.A1 = h->S; g.lda1 = 128; g.K1 = 128; g.W = h->sf_w; g.ldw = 128; g.K = 128; g.M = K * M; g.N = 128;
-    g.C = h->F; g.ldc = 128; g.act = ACT_SELU; g.m_dev = n_out; g.m_mult = M;
-    B2S_TRY(agemm(h, g, st));
-    g = GemmParams();
-    g.A1 = h->F; g.lda1 = M * 128; g.K1 = M * 128; g.W = h->aggT; g.ldw = M * 128; g.K = M * 128; g.M = K; g.N = 128;
-    g.C = h->descraw; g.ldc = 128; g.m_dev = n_out; g.m_mult = 1;
-    B2S_TRY(agemm(h, g, st));
+    B2S_TRY(tc_gemm(h, st, h->m_S, K * M, h->tc_sf, nullptr, 1, K * M, n_out, M, nullptr, 128, h->F, (size_t)K * M * 128));
+    B2S_TRY(tc_gemm(h, st, h->m_F, K, h->tc_agg, nullptr, 0, K, n_out, 1, h->descraw, 128, nullptr, 0));
     launch_k(k_desc_normalize, cdiv(K, 8), 256, 0, st, h->descraw, n_out, desc);
     ++h->launches; B2S_LAUNCH_CHECK();
   }
@@ -454,7 +496,18 @@ extern "C" int b2s_aliked_debug_get(b2s_aliked* h, const char* name, float* out,
   else if (s == "x4") { src = h->x4; cnt = 128 * P / 1024; }       // HWC
   else if (s == "score_map") { src = h->score; cnt = Pr; }
   else if (s == "nms") { src = h->nms; cnt = Pr; }
-  else if (s == "feature_map") { src = h->feat; cnt = 128 * Pr; }  // HWC
+  else if (s == "feature_map") {   // HWC; never materialised by the extractor: evaluated here from the last call's maps
+    *nout = 128 * Pr;
+    if (!h->fsrc.x1) { set_error("debug tensor %s not available before the first extract", name); return B2S_EINVAL; }
+    if (cap < 128 * Pr) return 0;
+    float* tmp = nullptr;
+    B2S_CUDA(cudaMalloc(&tmp, 128 * Pr * sizeof(float)));
+    k_aliked_featmap<<<cdiv((int)Pr, 8), 256>>>(h->fsrc, tmp);
+    cudaError_t e = cudaMemcpy(out, tmp, 128 * Pr * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    if (e != cudaSuccess) { set_error("feature_map tap: %s", cudaGetErrorString(e)); return B2S_ECUDA; }
+    return 0;
+  }
   else if (s == "kp_norm") { src = h->kp_norm; cnt = (size_t)h->n_limit * 2; }
   else if (s == "sampled_score") { src = h->sampled; cnt = (size_t)h->n_limit; }
   else if (s == "sddh_offset") { src = h->offs; cnt = (size_t)h->n_limit * 2 * h->M; }

@@ -3,6 +3,7 @@
 // (K3/K4, contracted by gemm_simt), fused aggregation/normalise/score-head (K5), DKD
 // NMS/top-k/soft-argmax (K6) and SDDH gathers (K7).  Upstream spec: SURVEY.md Appendix A.1/A.2.
 #pragma once
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace b2s {
@@ -317,94 +318,152 @@ __global__ void __launch_bounds__(256) k_conv1x1_chw_to_hwc32(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------
-// K5a: fused aggregation.  Per full-resolution (padded) pixel: f = cat[selu(W1 x1),
-// up2(x2a), up8(x3a), up32(x4a)] (bilinear, align_corners=True) ; s8 = selu(Ws0 f) ;
-// feature = f / max(|f|,1e-12) written HWC for the UNPADDED region only.
-// CTA = 8 warps x 4 pixels = 32 consecutive pixels of a row; lane = channel within group.
+// K5a: aggregation.  Upstream builds the full-resolution 128-channel map
+//   f = cat[selu(W1 x1), up2(x2a), up8(x3a), up32(x4a)]   (bilinear, align_corners=True)
+// normalises it and feeds (the un-normalised) f to the score head's 1x1 conv (128 -> 8).  The map is
+// 162 MB at KITTI size and only ~150 k of its 327 k pixels are ever sampled (SDDH), so it is never
+// materialised here:
+//  * k_aliked_proj8 projects the three low-resolution levels to the 8 score channels at THEIR
+//    resolution (the 1x1 conv commutes with the bilinear upsampling);
+//  * k_aliked_s8 computes s8 = selu(Ws0[:, :32] selu(W1 x1) + sum_l up(P_l)) per padded pixel;
+//  * feat_at() evaluates the normalised feature vector of one pixel on demand (warp-cooperative,
+//    lane l holds channels l, 32+l, 64+l, 96+l) for the SDDH gathers.
 // ---------------------------------------------------------------------------------------
-struct AggParams {
+struct FeatSrc {
   const float* x1; int Hp, Wp;            // CHW [16][Hp][Wp]
   const float* xa[3]; int Hk[3], Wk[3];   // HWC [Hk*Wk][32] (levels 1/2, 1/8, 1/32)
   float sh[3], sw[3];                     // (in-1)/(out-1)
   const float* W1;                        // [32][16]
-  const float* Ws0;                       // [8][128]
-  float* s8;                              // CHW [8][Hp][Wp]
-  float* feat;                            // HWC [Hr*Wr][128]
   int Hr, Wr, pad_t, pad_l;
 };
 
-__global__ void __launch_bounds__(128) k_aliked_agg(AggParams p) {
+struct BilinTap { int o00, o01, o10, o11; float ly0, ly1, lx0, lx1; };
+__device__ __forceinline__ BilinTap level_tap(const FeatSrc& s, int l, int y, int x) {
+  const float fy = s.sh[l] * (float)y, fx = s.sw[l] * (float)x;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < s.Hk[l] - 1 ? 1 : 0), x1 = x0 + (x0 < s.Wk[l] - 1 ? 1 : 0);
+  BilinTap t;
+  t.ly1 = fy - (float)y0; t.ly0 = 1.f - t.ly1; t.lx1 = fx - (float)x0; t.lx0 = 1.f - t.lx1;
+  t.o00 = y0 * s.Wk[l] + x0; t.o01 = y0 * s.Wk[l] + x1; t.o10 = y1 * s.Wk[l] + x0; t.o11 = y1 * s.Wk[l] + x1;
+  return t;
+}
+__device__ __forceinline__ float bilin(const BilinTap& t, float a, float b, float c, float d) {
+  return t.ly0 * (t.lx0 * a + t.lx1 * b) + t.ly1 * (t.lx0 * c + t.lx1 * d);
+}
+
+// normalised feature of UNPADDED pixel (yu, xu); w1 = row `lane` of W1.  Whole warp must call.
+__device__ __forceinline__ float4 feat_at(const FeatSrc& s, const float (&w1)[16], int yu, int xu, int lane) {
+  const int y = yu + s.pad_t, x = xu + s.pad_l;
+  const float xin = lane < 16 ? s.x1[((size_t)lane * s.Hp + y) * s.Wp + x] : 0.f;
+  float a = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a = fmaf(w1[k], __shfl_sync(0xffffffffu, xin, k), a);
+  float4 f;
+  f.x = selu_f(a);
+  float lv[3];
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const BilinTap t = level_tap(s, l, y, x);
+    const float* m = s.xa[l] + lane;
+    lv[l] = bilin(t, __ldg(m + (size_t)t.o00 * 32), __ldg(m + (size_t)t.o01 * 32), __ldg(m + (size_t)t.o10 * 32), __ldg(m + (size_t)t.o11 * 32));
+  }
+  f.y = lv[0]; f.z = lv[1]; f.w = lv[2];
+  const float ssq = warp_sum(fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, f.w * f.w))));
+  const float denom = fmaxf(sqrtf(ssq), 1e-12f);
+  return make_float4(f.x / denom, f.y / denom, f.z / denom, f.w / denom);
+}
+
+// P_l[pix][j] = sum_c Ws0[j][32 (l+1) + c] xa_l[pix][c] for the three low-resolution levels in one launch.
+struct Proj8Params { const float* xa[3]; float* out[3]; int npix[3]; const float* Ws0; };
+__global__ void __launch_bounds__(256) k_aliked_proj8(Proj8Params p) {
   pdl_wait();
-  // one thread per padded pixel (128 consecutive pixels of a row per CTA): the whole 128-channel
-  // vector lives in registers, so the norm and the 128->8 score projection need no shuffles.
-  __shared__ __align__(16) float sW1[32 * 16];
-  __shared__ __align__(16) float sWs[8 * 128];
-  for (int e = threadIdx.x; e < 32 * 16; e += 128) sW1[e] = p.W1[e];
-  for (int e = threadIdx.x; e < 8 * 128; e += 128) sWs[e] = p.Ws0[e];
+  __shared__ __align__(16) float sW[3][8][32];
+  for (int e = threadIdx.x; e < 3 * 8 * 32; e += 256) {
+    const int l = e / 256, j = (e / 32) % 8, c = e % 32;
+    sW[l][j][c] = p.Ws0[j * 128 + 32 * (l + 1) + c];
+  }
   __syncthreads();
+  int i = blockIdx.x * 256 + threadIdx.x, l = 0;
+  while (l < 3 && i >= p.npix[l]) { i -= p.npix[l]; ++l; }
+  if (l >= 3) return;
+  float f[32];
+  const float4* src = reinterpret_cast<const float4*>(p.xa[l] + (size_t)i * 32);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { const float4 v = src[q]; f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w; }
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) a = fmaf(sW[l][j][c], f[c], a);
+    o[j] = a;
+  }
+  float4* d = reinterpret_cast<float4*>(p.out[l] + (size_t)i * 8);
+  d[0] = make_float4(o[0], o[1], o[2], o[3]); d[1] = make_float4(o[4], o[5], o[6], o[7]);
+}
+
+struct S8Params {
+  FeatSrc src;
+  const float* P[3];                      // [Hk*Wk][8]
+  const float* Ws0;                       // [8][128]
+  float* s8;                              // CHW [8][Hp][Wp]
+};
+__global__ void __launch_bounds__(128) k_aliked_s8(S8Params p) {
+  pdl_wait();
+  __shared__ __align__(16) float sW1[32 * 16];
+  __shared__ __align__(16) float sWs[8 * 32];
+  for (int e = threadIdx.x; e < 32 * 16; e += 128) sW1[e] = p.src.W1[e];
+  for (int e = threadIdx.x; e < 8 * 32; e += 128) sWs[e] = p.Ws0[(e / 32) * 128 + (e % 32)];
+  __syncthreads();
+  const FeatSrc& s = p.src;
   const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
-  if (x >= p.Wp) return;
-  float f[128];
-  {
-    float xin[16];
+  if (x >= s.Wp) return;
+  float xin[16], acc[8];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) xin[k] = p.x1[((size_t)k * p.Hp + y) * p.Wp + x];
+  for (int k = 0; k < 16; ++k) xin[k] = s.x1[((size_t)k * s.Hp + y) * s.Wp + x];
 #pragma unroll
-    for (int o = 0; o < 32; ++o) {
-      const float4* w = reinterpret_cast<const float4*>(sW1 + o * 16);
-      float a = 0.f;
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 wv = w[q];
-        a = fmaf(wv.x, xin[4 * q], a); a = fmaf(wv.y, xin[4 * q + 1], a);
-        a = fmaf(wv.z, xin[4 * q + 2], a); a = fmaf(wv.w, xin[4 * q + 3], a);
-      }
-      f[o] = selu_f(a);
+  for (int o = 0; o < 32; ++o) {
+    const float4* w = reinterpret_cast<const float4*>(sW1 + o * 16);
+    float a = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 wv = w[q];
+      a = fmaf(wv.x, xin[4 * q], a); a = fmaf(wv.y, xin[4 * q + 1], a);
+      a = fmaf(wv.z, xin[4 * q + 2], a); a = fmaf(wv.w, xin[4 * q + 3], a);
     }
+    const float f = selu_f(a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(sWs[j * 32 + o], f, acc[j]);
   }
 #pragma unroll
   for (int l = 0; l < 3; ++l) {
-    const float fy = p.sh[l] * (float)y, fx = p.sw[l] * (float)x;
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = y0 + (y0 < p.Hk[l] - 1 ? 1 : 0), x1 = x0 + (x0 < p.Wk[l] - 1 ? 1 : 0);
-    const float ly1 = fy - (float)y0, ly0 = 1.f - ly1, lx1 = fx - (float)x0, lx0 = 1.f - lx1;
-    const float4* r00 = reinterpret_cast<const float4*>(p.xa[l] + ((size_t)y0 * p.Wk[l] + x0) * 32);
-    const float4* r01 = reinterpret_cast<const float4*>(p.xa[l] + ((size_t)y0 * p.Wk[l] + x1) * 32);
-    const float4* r10 = reinterpret_cast<const float4*>(p.xa[l] + ((size_t)y1 * p.Wk[l] + x0) * 32);
-    const float4* r11 = reinterpret_cast<const float4*>(p.xa[l] + ((size_t)y1 * p.Wk[l] + x1) * 32);
+    const BilinTap t = level_tap(s, l, y, x);
+    const float4* m = reinterpret_cast<const float4*>(p.P[l]);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 a = __ldg(r00 + q), b = __ldg(r01 + q), c = __ldg(r10 + q), d = __ldg(r11 + q);
-      float* o = f + 32 * (l + 1) + 4 * q;
-      o[0] = ly0 * (lx0 * a.x + lx1 * b.x) + ly1 * (lx0 * c.x + lx1 * d.x);
-      o[1] = ly0 * (lx0 * a.y + lx1 * b.y) + ly1 * (lx0 * c.y + lx1 * d.y);
-      o[2] = ly0 * (lx0 * a.z + lx1 * b.z) + ly1 * (lx0 * c.z + lx1 * d.z);
-      o[3] = ly0 * (lx0 * a.w + lx1 * b.w) + ly1 * (lx0 * c.w + lx1 * d.w);
-    }
-  }
-  float ssq = 0.f, s8[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) s8[j] = 0.f;
-#pragma unroll
-  for (int c = 0; c < 128; c += 4) {
-    ssq = fmaf(f[c], f[c], ssq); ssq = fmaf(f[c + 1], f[c + 1], ssq);
-    ssq = fmaf(f[c + 2], f[c + 2], ssq); ssq = fmaf(f[c + 3], f[c + 3], ssq);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 wv = *reinterpret_cast<const float4*>(sWs + j * 128 + c);
-      s8[j] = fmaf(wv.x, f[c], s8[j]); s8[j] = fmaf(wv.y, f[c + 1], s8[j]);
-      s8[j] = fmaf(wv.z, f[c + 2], s8[j]); s8[j] = fmaf(wv.w, f[c + 3], s8[j]);
+    for (int h = 0; h < 2; ++h) {
+      const float4 a = __ldg(m + (size_t)t.o00 * 2 + h), b = __ldg(m + (size_t)t.o01 * 2 + h);
+      const float4 c = __ldg(m + (size_t)t.o10 * 2 + h), d = __ldg(m + (size_t)t.o11 * 2 + h);
+      acc[4 * h] += bilin(t, a.x, b.x, c.x, d.x); acc[4 * h + 1] += bilin(t, a.y, b.y, c.y, d.y);
+      acc[4 * h + 2] += bilin(t, a.z, b.z, c.z, d.z); acc[4 * h + 3] += bilin(t, a.w, b.w, c.w, d.w);
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) p.s8[((size_t)j * p.Hp + y) * p.Wp + x] = selu_f(s8[j]);
-  const int yu = y - p.pad_t, xu = x - p.pad_l;
-  if (yu >= 0 && yu < p.Hr && xu >= 0 && xu < p.Wr) {
-    const float denom = fmaxf(sqrtf(ssq), 1e-12f);
-    float4* d = reinterpret_cast<float4*>(p.feat + ((size_t)yu * p.Wr + xu) * 128);
+  for (int j = 0; j < 8; ++j) p.s8[((size_t)j * s.Hp + y) * s.Wp + x] = selu_f(acc[j]);
+}
+
+// debug tap only: materialise the normalised feature map HWC [Hr*Wr][128].  warp per pixel.
+__global__ void __launch_bounds__(256) k_aliked_featmap(FeatSrc s, float* __restrict__ feat) {
+  const int pix = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pix >= s.Hr * s.Wr) return;
+  const int lane = threadIdx.x & 31;
+  float w1[16];
 #pragma unroll
-    for (int q = 0; q < 32; ++q) d[q] = make_float4(f[4 * q] / denom, f[4 * q + 1] / denom, f[4 * q + 2] / denom, f[4 * q + 3] / denom);
-  }
+  for (int k = 0; k < 16; ++k) w1[k] = s.W1[lane * 16 + k];
+  const float4 f = feat_at(s, w1, pix / s.Wr, pix % s.Wr, lane);
+  float* d = feat + (size_t)pix * 128 + lane;
+  d[0] = f.x; d[32] = f.y; d[64] = f.z; d[96] = f.w;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -786,34 +845,52 @@ __global__ void __launch_bounds__(256) k_dkd_refine(RefineParams p) {
 }
 
 // ---------------------------------------------------------------------------------------
-// K7 gathers.  Feature map is HWC [H*W][128].
+// K7 gathers.  The feature vector of a pixel is evaluated on demand (feat_at).
 // (a) 3x3 patch rows for the offset conv: A[n][tap*128 + c]; warp per (keypoint, tap)
 // (b) M deformable samples per keypoint: S[n*M + m][c]; warp per sample
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_sddh_patch(const float* __restrict__ feat, int H, int W, const float* __restrict__ kp_norm,
-                                                    const int32_t* __restrict__ n_dev, float* __restrict__ A) {
+// one fp32 value -> three bf16 planes (x = a0 + a1 + a2 to 24 bits; tensor-core operand format, tc_common.cuh)
+__device__ __forceinline__ void store_planes1(__nv_bfloat16* d, size_t plane, float x) {
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(x);
+    d[p * plane] = b;
+    x -= __bfloat162float(b);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sddh_patch(FeatSrc s, const float* __restrict__ kp_norm,
+                                                    const int32_t* __restrict__ n_dev, __nv_bfloat16* __restrict__ A, size_t plane) {
   pdl_wait();
   const int job = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int n = job / 9, tap = job % 9;
   if (n >= *n_dev) return;
   const int lane = threadIdx.x & 31;
+  const int H = s.Hr, W = s.Wr;
+  float w1[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) w1[k] = s.W1[lane * 16 + k];
   const float kx = (kp_norm[2 * n] / 2.f + 0.5f) * (float)(W - 1), ky = (kp_norm[2 * n + 1] / 2.f + 0.5f) * (float)(H - 1);
   const int cx = (int)kx, cy = (int)ky;                      // .long() truncation
   int ox = (int)((float)cx - 0.5f), oy = (int)((float)cy - 0.5f);  // (c - ps/2 + 1).long()
   ox = min(max(ox, 0), W - 4); oy = min(max(oy, 0), H - 4);
-  const int yy = oy + tap / 3, xx = ox + tap % 3;
-  const float4 v = *reinterpret_cast<const float4*>(feat + ((size_t)yy * W + xx) * 128 + lane * 4);
-  *reinterpret_cast<float4*>(A + (size_t)n * 1152 + tap * 128 + lane * 4) = v;
+  const float4 v = feat_at(s, w1, oy + tap / 3, ox + tap % 3, lane);
+  __nv_bfloat16* d = A + (size_t)n * 1152 + tap * 128 + lane;
+  store_planes1(d, plane, v.x); store_planes1(d + 32, plane, v.y); store_planes1(d + 64, plane, v.z); store_planes1(d + 96, plane, v.w);
 }
 
-__global__ void __launch_bounds__(256) k_sddh_sample(const float* __restrict__ feat, int H, int W, const float* __restrict__ kp_norm,
+__global__ void __launch_bounds__(256) k_sddh_sample(FeatSrc s, const float* __restrict__ kp_norm,
                                                      const float* __restrict__ offs /*[n][M][2]*/, int M,
-                                                     const int32_t* __restrict__ n_dev, float* __restrict__ S) {
+                                                     const int32_t* __restrict__ n_dev, __nv_bfloat16* __restrict__ S, size_t plane) {
   pdl_wait();
   const int job = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int n = job / M;
   if (n >= *n_dev) return;
   const int lane = threadIdx.x & 31;
+  const int H = s.Hr, W = s.Wr;
+  float w1[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) w1[k] = s.W1[lane * 16 + k];
   const float whx = (float)(W - 1), why = (float)(H - 1);
   const float kx = (kp_norm[2 * n] / 2.f + 0.5f) * whx, ky = (kp_norm[2 * n + 1] / 2.f + 0.5f) * why;
   const float posx = kx + offs[(size_t)job * 2], posy = ky + offs[(size_t)job * 2 + 1];
@@ -823,17 +900,15 @@ __global__ void __launch_bounds__(256) k_sddh_sample(const float* __restrict__ f
   const int ix0 = (int)fx0, iy0 = (int)fy0, ix1 = ix0 + 1, iy1 = iy0 + 1;
   const float wnw = ((float)ix1 - gx) * ((float)iy1 - gy), wne = (gx - (float)ix0) * ((float)iy1 - gy);
   const float wsw = ((float)ix1 - gx) * (gy - (float)iy0), wse = (gx - (float)ix0) * (gy - (float)iy0);
-  auto ld = [&](int yy, int xx) {
-    return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? *reinterpret_cast<const float4*>(feat + ((size_t)yy * W + xx) * 128 + lane * 4)
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+  auto ld = [&](int yy, int xx) {     // uniform across the warp: all lanes take the same branch
+    return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? feat_at(s, w1, yy, xx, lane) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
   const float4 a = ld(iy0, ix0), b = ld(iy0, ix1), c = ld(iy1, ix0), d = ld(iy1, ix1);
-  float4 o;
-  o.x = a.x * wnw + b.x * wne + c.x * wsw + d.x * wse;
-  o.y = a.y * wnw + b.y * wne + c.y * wsw + d.y * wse;
-  o.z = a.z * wnw + b.z * wne + c.z * wsw + d.z * wse;
-  o.w = a.w * wnw + b.w * wne + c.w * wsw + d.w * wse;
-  *reinterpret_cast<float4*>(S + (size_t)job * 128 + lane * 4) = o;
+  __nv_bfloat16* o = S + (size_t)job * 128 + lane;
+  store_planes1(o, plane, a.x * wnw + b.x * wne + c.x * wsw + d.x * wse);
+  store_planes1(o + 32, plane, a.y * wnw + b.y * wne + c.y * wsw + d.y * wse);
+  store_planes1(o + 64, plane, a.z * wnw + b.z * wne + c.z * wsw + d.z * wse);
+  store_planes1(o + 96, plane, a.w * wnw + b.w * wne + c.w * wsw + d.w * wse);
 }
 
 // F.normalize(desc, dim=1) (eps 1e-12).  warp per row of 128.

@@ -6,7 +6,10 @@
 // Same role split as attn_tc.cuh (two softmax groups on alternating key tiles, TMA warp, MMA warp,
 // lazy rescale with O kept in TMEM).  Differences: K and V tiles (3 planes x 8 KB) share ONE ring of
 // 3 slots filled in exactly the order the MMA warp consumes them (K0 K1 [K2 V0] [K3 V1] ...), P has
-// three planes per group, TMEM holds S 2x64 + O 2x64 columns.
+// three planes per group.  The tensor core truncates its fp32 accumulator after every k-step, so every
+// contraction keeps TWO TMEM accumulators - the main q0*k0 (p0*v0) term and the five correction terms - and
+// the per-tile P V result is added to the running output in fp32 REGISTERS (round-to-nearest) instead of
+// being accumulated across tiles by the MMA.  TMEM: S 2 groups x (main, corr) x 64 + O likewise = 512 columns.
 // grid = (ceil(max nq/128), heads, nprob).
 #pragma once
 #include "attn_tc.cuh"
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
     }
     tc::fence_barrier_init();
   }
-  if (warp == 10) tc::tmem_alloc(tmem_slot, 256);
+  if (warp == 10) tc::tmem_alloc(tmem_slot, 512);
   pdl_trigger();
   tc::tc_fence_before();
   __syncthreads();
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
   }
   const bool live = q0 < pr.nq;                          // uniform per CTA
   const int nt = live ? (pr.nk + A3_BK - 1) / A3_BK : 0;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;    // S[g] = tS + 64 g ; O[g] = tO + 64 g
+  const uint32_t tS = tmem_base, tO = tmem_base + 256;    // S[g] = tS + 128 g + {0 main, 64 corr} ; O[g] likewise
 
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -154,7 +157,8 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
           for (int k = 0; k < A3_D / 16; ++k) {
             const uint64_t ad = tc::smem_desc_sw128(q_addr + Terms::a(t) * A3_QPL + k * 32, 16, 1024);
             const uint64_t bd = tc::smem_desc_sw128(k_addr + Terms::b(t) * A3_KPL + k * 32, 16, 1024);
-            tc::umma_bf16(tS + g * 64, ad, bd, idesc_s, (t | k) ? 1u : 0u);
+            const bool main_term = t == Terms::N - 1;
+            tc::umma_bf16(tS + g * 128 + (main_term ? 0 : 64), ad, bd, idesc_s, main_term ? (k ? 1u : 0u) : ((t | k) ? 1u : 0u));
           }
         tc::umma_commit(&s_full[g]);
         tc::umma_commit(&r_empty[b]);
@@ -172,7 +176,8 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
             // P plane: [128 x 64] K-major; V plane: [64 keys x 64 d] MN-major, 16 keys = 2 swizzle atoms = 2048 B
             const uint64_t ad = tc::smem_desc_sw128(p_addr + Terms::a(t) * A3_PPL + kk * 32, 16, 1024);
             const uint64_t bd = tc::smem_desc_sw128(v_addr + Terms::b(t) * A3_KPL + kk * 2048, 16, 1024);
-            tc::umma_bf16(tO + g * 64, ad, bd, idesc_o, (j >= 2 || t || kk) ? 1u : 0u);   // O[g] accumulates over the group's tiles
+            const bool main_term = t == Terms::N - 1;      // per-tile result: both accumulators start afresh
+            tc::umma_bf16(tO + g * 128 + (main_term ? 0 : 64), ad, bd, idesc_o, main_term ? (kk ? 1u : 0u) : ((t | kk) ? 1u : 0u));
           }
         tc::umma_commit(&o_full[g]);
         tc::umma_commit(&r_empty[b]);
@@ -198,15 +203,35 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
     const int r = quad * 32 + lane;                       // query row of this thread
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     float m_used = -INFINITY, l_run = 0.f;
+    float o[A3_D];                                        // running output (fp32 registers)
+#pragma unroll
+    for (int d = 0; d < A3_D; ++d) o[d] = 0.f;
     const uint32_t prow_addr = tc::smem_u32(sP + g * A3_NP * A3_PPL + r * 128);
-    const uint32_t s_addr = tS + g * 64 + lane_addr, o_addr = tO + g * 64 + lane_addr;
+    const uint32_t s_addr = tS + g * 128 + lane_addr, o_addr = tO + g * 128 + lane_addr;
+    // o += (main + corr) of the PV result sitting in TMEM (exact fp32 adds)
+    auto add_pv = [&]() {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t a[32], b[32];
+        tc::tmem_ld32(o_addr + 32 * c, a); tc::tmem_ld32(o_addr + 64 + 32 * c, b);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[32 * c + e] += __uint_as_float(a[e]) + __uint_as_float(b[e]);
+      }
+    };
     int t = 0;                                            // index among this group's tiles
     for (int j = g; j < nt; j += 2, ++t) {
       tc::mbar_wait(&s_full[g], t & 1);
       tc::tc_fence_after();
       uint32_t s[2][32];
-      tc::tmem_ld32(s_addr, s[0]); tc::tmem_ld32(s_addr + 32, s[1]);
-      tc::tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t b[32];
+        tc::tmem_ld32(s_addr + 32 * c, s[c]); tc::tmem_ld32(s_addr + 64 + 32 * c, b);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) s[c][e] = __float_as_uint(__uint_as_float(s[c][e]) + __uint_as_float(b[e]));
+      }
       tc::tc_fence_before();
       tc::mbar_arrive(&s_free[g]);                        // S[g] is in registers: next QK^T of this group may overwrite it
       const int limit = pr.nk - j * A3_BK;
@@ -216,24 +241,18 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
       else mx = fmaxf(atc_chunk_max<true>(s[0], 0, limit), atc_chunk_max<true>(s[1], 1, limit));
       const float mxs = mx * p.scale_log2e;
       if (t == 0) {
-        m_used = mxs;                                     // first PV of the group overwrites O[g]: nothing to rescale
+        m_used = mxs;
       } else {
-        // PV of the group's previous tile must have retired before P[g] is rewritten / O[g] is touched
+        // PV of the group's previous tile must have retired before P[g] is rewritten; collect its result
         tc::mbar_wait(&o_full[g], (t - 1) & 1);
         tc::tc_fence_after();
-        if (__any_sync(0xffffffffu, mxs > m_used + ATC_LAZY)) {
+        add_pv();
+        if (__any_sync(0xffffffffu, mxs > m_used + ATC_LAZY)) {   // lazy: raise the reference max only beyond 2^8
           const float m_new = fmaxf(m_used, mxs);
           const float corr = ex2_approx(m_used - m_new);  // 1 for rows whose reference did not move
           l_run *= corr; m_used = m_new;
-          uint32_t o[2][32];
-          tc::tmem_ld32(o_addr, o[0]); tc::tmem_ld32(o_addr + 32, o[1]);
-          tc::tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int e = 0; e < 32; ++e) o[c][e] = __float_as_uint(__uint_as_float(o[c][e]) * corr);
-          tc::tmem_st32(o_addr, o[0]); tc::tmem_st32(o_addr + 32, o[1]);
-          tc::tmem_st_wait();
+          for (int d = 0; d < A3_D; ++d) o[d] *= corr;
         }
       }
       float sum;
@@ -243,22 +262,14 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
                  a3_write_p_chunk<true>(s[1], 1, prow_addr, r, limit, p.scale_log2e, m_used);
       l_run += sum;
       tc::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc::tc_fence_before();            // order our tcgen05.ld / st before the MMAs that follow the arrive
+      tc::tc_fence_before();            // order our tcgen05.ld before the MMAs that follow the arrive
       tc::mbar_arrive(&p_full[g]);
     }
-    // ---- this group's accumulator: O[g] after its last PV ----
-    float o[A3_D];
+    // ---- the group's last PV ----
     if (t > 0) {
       tc::mbar_wait(&o_full[g], (t - 1) & 1);
       tc::tc_fence_after();
-      uint32_t v[2][32];
-      tc::tmem_ld32(o_addr, v[0]); tc::tmem_ld32(o_addr + 32, v[1]);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int d = 0; d < A3_D; ++d) o[d] = __uint_as_float(v[d >> 5][d & 31]);
-    } else {
-#pragma unroll
-      for (int d = 0; d < A3_D; ++d) o[d] = 0.f;
+      add_pv();
     }
     const float m_run = m_used;
     tc::tc_fence_before();
@@ -297,7 +308,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 10) tc::tmem_dealloc(tmem_base, 256);
+  if (warp == 10) tc::tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace b2s

@@ -30,7 +30,22 @@ struct TcGemmParams {
   float* out_f32; int ld_f32;               // TC_EPI_F32 (plain) / RESID (in-place residual stream)
   const float* rot_cos; const float* rot_sin; int rot_cols;   // [rows,32] tables
   const int* ctrl;                  // LightGlue device state (nullable): live rows = ctrl[2 + seg]; exit when stopped
+  const int* m_dev; int m_mult;     // nullable: live rows of segment 0 = *m_dev * m_mult (ALIKED keypoint count)
+  int act;                          // 0 none, 1 SELU (after bias)
 };
+
+// fp32 weight [N,K] -> np bf16 planes side by side: out[n][p*K + k]
+static __global__ void k_weight_planes(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int N, int K, int np) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * K) return;
+  const int n = (int)(i / K), k = (int)(i % K);
+  float r = w[i];
+  for (int p = 0; p < np; ++p) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(r);
+    out[(size_t)n * np * K + (size_t)p * K + k] = b;
+    r -= __bfloat162float(b);
+  }
+}
 
 template <int BN, int NP>
 struct TcGemmCfg {
@@ -40,6 +55,13 @@ struct TcGemmCfg {
   static constexpr int STAGES = NP == 1 ? 3 : (BN == 128 ? 2 : 3);
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
   static constexpr int THREADS = 192;
+  // The tensor core truncates its fp32 accumulator after every k-step (measured: bias -4.4e-9 * K on positive
+  // data), which would cost the NP = 3 path its fp32 fidelity for long K.  So the accumulation is spread over
+  // NACC TMEM accumulators that the epilogue adds in fp32 registers (round-to-nearest): accumulator 0 takes the
+  // five correction terms (2^-8 of the magnitude, their truncation is negligible), accumulators 1.. take the
+  // main a0*w0 term round-robin by k-block.
+  static constexpr int NACC = NP == 1 ? 1 : 512 / BN;
+  static constexpr int TMEM_COLS = NACC * BN;
 };
 
 template <int BN, int NP>
@@ -73,10 +95,10 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
     tc::mbar_init(tmem_full, 1);
     tc::fence_barrier_init();
   }
-  if (warp == 2) tc::tmem_alloc(tmem_slot, BN);
+  if (warp == 2) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   if (warp >= 2) {                       // bias is a constant weight: staged before the dependency wait
     const int t = threadIdx.x - 64;
-    if (t < BN) s_bias[t] = __ldg(p.bias + n0 + t);
+    if (t < BN) s_bias[t] = (p.bias && n0 + t < p.N) ? __ldg(p.bias + n0 + t) : 0.f;
   }
   pdl_trigger();
   tc::tc_fence_before();
@@ -88,6 +110,7 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
     const bool on = !p.ctrl[1] && p.ctrl[2] > 0 && p.ctrl[3] > 0;
     rows_live = on ? p.ctrl[2 + seg] - (tile_m - (seg ? p.tiles0 : 0)) * Cfg::BM : 0;
   }
+  if (p.m_dev) rows_live = *p.m_dev * p.m_mult - tile_m * Cfg::BM;
 
   if (rows_live <= 0) {
     // nothing to do for this tile (uniform per CTA)
@@ -112,6 +135,7 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
     // ===== MMA issuer =====
     if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::idesc_bf16(128, BN, 0, 0);
+      uint32_t used = 0;                                  // accumulators already written (first MMA overwrites)
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % Cfg::STAGES, ph = (kb / Cfg::STAGES) & 1;
         tc::mbar_wait(&full[s], ph);
@@ -119,11 +143,13 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
         const uint32_t a0 = tc::smem_u32(smem + s * Cfg::STAGE_BYTES), b0 = a0 + NP * Cfg::A_BYTES;
 #pragma unroll
         for (int t = 0; t < Terms::N; ++t) {
+          const int acc = (Cfg::NACC == 1) ? 0 : (t == Terms::N - 1 ? 1 + kb % (Cfg::NACC - 1) : 0);
 #pragma unroll
           for (int k = 0; k < Cfg::BK / 16; ++k) {
             const uint64_t ad = tc::smem_desc_sw128(a0 + Terms::a(t) * Cfg::A_BYTES + k * 32, 16, 1024);
             const uint64_t bd = tc::smem_desc_sw128(b0 + Terms::b(t) * Cfg::B_BYTES + k * 32, 16, 1024);
-            tc::umma_bf16(tmem_base, ad, bd, idesc, (kb | t | k) ? 1u : 0u);
+            tc::umma_bf16(tmem_base + acc * BN, ad, bd, idesc, (used >> acc) & 1u);
+            used |= 1u << acc;
           }
         }
         tc::umma_commit(&empty[s]);                 // frees the smem stage when these MMAs retire
@@ -141,19 +167,45 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
-      tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + c0, v);
-      tc::tmem_ld_wait();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + c0;
+      float f[32];
+      if (Cfg::NACC == 1) {
+        tc::tmem_ld32(taddr, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      } else {
+        // main-term accumulators first (1 .. n_main), the correction accumulator last
+        const int n_main = nkb < Cfg::NACC - 1 ? nkb : Cfg::NACC - 1;
+        tc::tmem_ld32(taddr + BN, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+#pragma unroll 1
+        for (int a = 2; a <= n_main; ++a) {
+          tc::tmem_ld32(taddr + a * BN, v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+        }
+        tc::tmem_ld32(taddr, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+      }
       const int gc = n0 + c0;
       if (!live || gc >= p.N) continue;
-      float f[32];
       {
         const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 bv = b4[q];
-          f[4 * q] = __uint_as_float(v[4 * q]) + bv.x; f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bv.y;
-          f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bv.z; f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bv.w;
+          f[4 * q] += bv.x; f[4 * q + 1] += bv.y; f[4 * q + 2] += bv.z; f[4 * q + 3] += bv.w;
         }
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = selu_f(f[j]);
       }
       if (p.epi == TC_EPI_ROTARY_BF16 && gc < p.rot_cols) {
         const int f0 = (gc & 63) >> 1;   // 0 or 16: this chunk's 16 (cos,sin) pairs are contiguous
@@ -207,7 +259,7 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 2) tc::tmem_dealloc(tmem_base, BN);
+  if (warp == 2) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 }  // namespace b2s

@@ -122,19 +122,6 @@ __global__ void __launch_bounds__(256) k_ln_gelu_512_bf16(const float* __restric
   }
 }
 
-// fp32 weight [N,K] -> NP bf16 planes side by side: out[n][p*K + k]
-__global__ void k_weight_planes(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int N, int K, int np) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)N * K) return;
-  const int n = (int)(i / K), k = (int)(i % K);
-  float r = w[i];
-  for (int p = 0; p < np; ++p) {
-    const __nv_bfloat16 b = __float2bfloat16_rn(r);
-    out[(size_t)n * np * K + (size_t)p * K + k] = b;
-    r -= __bfloat162float(b);
-  }
-}
-
 // ---- state --------------------------------------------------------------------------------
 struct TcLinear {            // bf16 weight planes [N, NP*K] + their tensor map (box {64, BN})
   __nv_bfloat16* w = nullptr; const float* bias = nullptr; int N = 0, K = 0, BN = 0;

@@ -47,8 +47,9 @@ def test_attn_tc(nq, nk):
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (200, 256, 256), (4096, 768, 256), (1000, 512, 512), (333, 256, 512)])
 def test_gemm_tc3_is_fp32_faithful(M, N, K):
     """fp32 operands carried as three bf16 planes, six cross products: error vs a float64 reference must be at the
-    level of an fp32 GEMM.  Tolerance 4e-6 of the output scale: the operand split itself is exact to 2^-26, what is
-    left is the tensor core's fp32 accumulator (it truncates after every k-step; 6 x K/16 steps)."""
+    level of an fp32 GEMM: tolerance 1e-6 of the output scale and no worse than 2x torch's own fp32 matmul + 1e-7.
+    (The operand split is exact to 2^-26; the tensor core truncates its fp32 accumulator after every k-step, which
+    the kernel contains by spreading the accumulation over several TMEM accumulators summed in registers.)"""
     from b200slam import _lib
     g = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K, generator=g); W = torch.randn(N, K, generator=g) / K ** 0.5; b = torch.randn(N, generator=g)
@@ -57,7 +58,7 @@ def test_gemm_tc3_is_fp32_faithful(M, N, K):
     ref = (A.double() @ W.double().T + b.double()).numpy()
     err = np.abs(out - ref).max() / np.abs(ref).max()
     err32 = np.abs((A @ W.T + b).numpy() - ref).max() / np.abs(ref).max()
-    assert err < 4e-6, f"rel err {err} (torch fp32: {err32})"
+    assert err < 1e-6 and err < 2 * err32 + 1e-7, f"rel err {err} (torch fp32: {err32})"
 
 
 @pytest.mark.parametrize("nq,nk", [(128, 128), (128, 64), (300, 200), (2048, 2048), (1, 77), (129, 1), (640, 1000)])
