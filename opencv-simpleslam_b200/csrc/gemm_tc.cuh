@@ -30,6 +30,11 @@ struct TcGemmParams {
   float* out_f32; int ld_f32;               // TC_EPI_F32 (plain) / RESID (in-place residual stream)
   const float* rot_cos; const float* rot_sin; int rot_cols;   // [rows,32] tables
   const int* ctrl;                  // LightGlue device state (nullable): live rows = ctrl[2 + seg]; exit when stopped
+  int ctrl_mode;                    // 0/1 transformer layer (skipped after an early exit); 2 assignment head: runs after a stop
+                                    //   too, weight rows / bias of layer ctrl[6] (w_layer_rows apart); 3 similarity: M = ctrl[2],
+                                    //   N = ctrl[3], the B operand is an activation (planes w_plane_rows apart, first row w_row0)
+  int w_layer_rows, w_plane_rows, w_row0;
+  float alpha;                      // epilogue: (acc + bias) * alpha (0 means 1)
   const int* m_dev; int m_mult;     // nullable: live rows of segment 0 = *m_dev * m_mult (ALIKED keypoint count)
   int act;                          // 0 none, 1 SELU (after bias)
 };
@@ -106,9 +111,22 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();            // everything above overlaps the previous kernel's tail; operands are touched only below
+  int w_row = p.w_row0, n_live = p.N;
   if (p.ctrl) {          // device-resident sizes: pruning shrinks the segments, an early exit empties the layer
-    const bool on = !p.ctrl[1] && p.ctrl[2] > 0 && p.ctrl[3] > 0;
+    const bool sides = p.ctrl[2] > 0 && p.ctrl[3] > 0;
+    const bool on = sides && (p.ctrl_mode >= 2 || !p.ctrl[1]);
     rows_live = on ? p.ctrl[2 + seg] - (tile_m - (seg ? p.tiles0 : 0)) * Cfg::BM : 0;
+    if (p.ctrl_mode == 2) {
+      w_row += p.ctrl[6] * p.w_layer_rows;
+      if (warp >= 2) {               // the bias depends on the layer: restage it (epilogue warps only)
+        const int t = threadIdx.x - 64;
+        if (t < BN) s_bias[t] = __ldg(p.bias + w_row + n0 + t);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    } else if (p.ctrl_mode == 3) {
+      n_live = p.ctrl[3];
+      if (n0 >= n_live) rows_live = 0;
+    }
   }
   if (p.m_dev) rows_live = *p.m_dev * p.m_mult - tile_m * Cfg::BM;
 
@@ -127,7 +145,8 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
         for (int pl = 0; pl < NP; ++pl) {
           if (k0 < p.K1) tc::tma_load_2d(st + pl * Cfg::A_BYTES, &mapA1, &full[s], k0, row0 + pl * p.plane_rows);
           else tc::tma_load_2d(st + pl * Cfg::A_BYTES, &mapA2, &full[s], k0 - p.K1, row0 + pl * p.plane_rows);
-          tc::tma_load_2d(st + NP * Cfg::A_BYTES + pl * Cfg::B_BYTES, &mapW, &full[s], pl * p.K + k0, n0);
+          if (p.w_plane_rows) tc::tma_load_2d(st + NP * Cfg::A_BYTES + pl * Cfg::B_BYTES, &mapW, &full[s], k0, w_row + n0 + pl * p.w_plane_rows);
+          else tc::tma_load_2d(st + NP * Cfg::A_BYTES + pl * Cfg::B_BYTES, &mapW, &full[s], pl * p.K + k0, w_row + n0);
         }
       }
     }
@@ -202,6 +221,10 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
           const float4 bv = b4[q];
           f[4 * q] += bv.x; f[4 * q + 1] += bv.y; f[4 * q + 2] += bv.z; f[4 * q + 3] += bv.w;
         }
+      }
+      if (p.alpha != 0.f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
       }
       if (p.act == 1) {
 #pragma unroll

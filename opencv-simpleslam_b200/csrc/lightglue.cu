@@ -206,6 +206,9 @@ extern "C" int b2s_lightglue_create(const b2s_lg_cfg* cfg, const void* weights, 
                         l.cwqkv, l.cbqkv, l.cwo, l.cbo, l.cw1, l.cb1, l.clng, l.clnb, l.cw2, l.cb2};
       if ((rc = lgtc_set_layer(h->tc, (int)i, s))) return fail(rc);
     }
+    std::vector<const float*> wf, bf;
+    for (const LgLayer& l : h->L) { wf.push_back(l.wfinal); bf.push_back(l.bfinal); }
+    if ((rc = lgtc_set_final(h->tc, wf, bf))) return fail(rc);
   }
   if ((rc = lg_alloc_ws(h, cfg->max_kp > 0 ? cfg->max_kp : 2048))) return fail(rc);
   *out = h;
@@ -434,8 +437,8 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
   }
   // ---- assignment with the last executed layer's heads (K14/K15); that layer index, its buffer and the
   //      live sizes are device-side values ----
-  float* md = h->qkv;  // [2*cap, 256]
-  {
+  float* md = h->qkv;  // [2*cap, 256] (CUDA-core path)
+  if (!h->tc) {
     GemmParams g;
     g.A1 = h->x[0]; g.lda1 = 256; g.K1 = 256; g.A1_alt = do_prune ? h->x[1] : nullptr;
     g.W = h->L[L - 1].wfinal; g.ldw = 256; g.K = 256; g.N = 256; g.bias = h->L[L - 1].bfinal; g.alpha = 0.25f;
@@ -454,7 +457,9 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
     B2S_LAUNCH_CHECK();
   }
   const int ld = cap;
-  {
+  if (h->tc) {
+    B2S_TRY(lgtc_assignment(h->tc, st, h->x[0], do_prune ? h->x[1] : nullptr, cap, m, n, h->ctrl, h->sim, &h->launches));
+  } else {
     GemmParams g;
     g.A1 = md; g.lda1 = 256; g.K1 = 256; g.W = md + (size_t)cap * 256; g.ldw = 256; g.K = 256;
     g.M = m; g.N = n; g.C = h->sim; g.ldc = ld;

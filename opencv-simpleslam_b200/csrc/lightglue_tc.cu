@@ -61,10 +61,12 @@ __device__ __forceinline__ void store_planes8(__nv_bfloat16* y, size_t plane, co
 }
 
 template <int NP>
-__global__ void __launch_bounds__(256) k_f32_to_bf16_rows(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int ld, size_t plane,
+__global__ void __launch_bounds__(256) k_f32_to_bf16_rows(const float* __restrict__ x, const float* __restrict__ x_odd,
+                                                          __nv_bfloat16* __restrict__ y, int ld, size_t plane,
                                                           int base0, int rows0, int base1, int rows1, const int* __restrict__ ctrl) {
   pdl_wait();
   if (ctrl) { rows0 = ctrl[2]; rows1 = ctrl[3]; }
+  if (x_odd && (ctrl[6] & 1)) x = x_odd;     // the last executed layer lives in the odd ping-pong buffer
   // one warp per row of 256
   const int s = blockIdx.y;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -142,6 +144,11 @@ struct LgTensorCore {
   float* h1f = nullptr;
   CUtensorMap m_xb, m_ctxb, m_h1b, m_qkv768, m_qkv512;     // box {64, 128}: GEMM A operands, attention Q
   CUtensorMap m_kv768, m_kv512;                            // box {64, 64}: attention K / V tiles (np == 3)
+  // assignment head (always fp32-faithful, three planes): planes of the final x, of the projected descriptors md
+  __nv_bfloat16 *tx = nullptr, *md = nullptr;
+  CUtensorMap m_tx, m_md;
+  TcLinear wfinal;                 // all layers' final_proj stacked: [L*256, 3*256]
+  float* bfinal = nullptr;         // [L*256]
   const int* ctrl = nullptr;       // LightGlue device state (sizes / early exit), set per match
   KernelProf* prof = nullptr;
 };
@@ -239,6 +246,10 @@ int lgtc_alloc_ws(LgTensorCore* tc, int cap) {
   B2S_TRY(make_tmap_bf16_2d(&tc->m_qkv512, tc->qkvb, 512, P * R, 1024, 64, 128));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_kv768, tc->qkvb, 768, P * R, 1536, 64, 64));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_kv512, tc->qkvb, 512, P * R, 1024, 64, 64));
+  B2S_TRY(tc->wsarena.alloc(&tc->tx, 3 * R * 256)); B2S_TRY(tc->wsarena.alloc(&tc->md, 3 * R * 256));
+  B2S_CUDA(cudaMemset(tc->tx, 0, 3 * R * 256 * 2)); B2S_CUDA(cudaMemset(tc->md, 0, 3 * R * 256 * 2));
+  B2S_TRY(make_tmap_bf16_2d(&tc->m_tx, tc->tx, 256, 3 * R, 512, 64, 128));
+  B2S_TRY(make_tmap_bf16_2d(&tc->m_md, tc->md, 256, 3 * R, 512, 64, 128));
   tc->cap = cap;
   return 0;
 }
@@ -313,6 +324,54 @@ static int tc_ffn(LgTensorCore* tc, cudaStream_t st, float* x, const TcLinear& w
   return tc_gemm(tc, st, tc->m_h1b, tc->m_h1b, 512, w2, p, m, n, launches);              // x += h W2^T + b2 ; xb = planes(x)
 }
 
+// all layers' assignment projections (fp32 device pointers, [256,256] + [256] each) as one stacked bf16x3 weight
+int lgtc_set_final(LgTensorCore* tc, const std::vector<const float*>& w, const std::vector<const float*>& b) {
+  const size_t L = w.size();
+  float *wall, *ball;
+  B2S_TRY(tc->warena.alloc(&wall, L * 256 * 256)); B2S_TRY(tc->warena.alloc(&ball, L * 256));
+  for (size_t i = 0; i < L; ++i) {
+    B2S_CUDA(cudaMemcpy(wall + i * 256 * 256, w[i], 256 * 256 * 4, cudaMemcpyDeviceToDevice));
+    B2S_CUDA(cudaMemcpy(ball + i * 256, b[i], 256 * 4, cudaMemcpyDeviceToDevice));
+  }
+  tc->bfinal = ball;
+  TcLinear& o = tc->wfinal;
+  o.N = (int)L * 256; o.K = 256; o.bias = ball; o.BN = 64;
+  const size_t n = L * 256 * 256;
+  B2S_TRY(tc->warena.alloc(&o.w, 3 * n));
+  k_weight_planes<<<(unsigned)((n + 255) / 256), 256>>>(wall, o.w, o.N, 256, 3);
+  B2S_LAUNCH_CHECK();
+  B2S_CUDA(cudaDeviceSynchronize());
+  return make_tmap_bf16_2d(&o.map, o.w, 3 * 256, o.N, 3 * 256 * 2, 64, 64);
+}
+
+// Assignment head on the tensor cores (fp32 carried as bf16x3 whatever the layer precision):
+//   md = final_proj_last(x) / 256^(1/4) for both images, then sim = md0 md1^T  ([cap, cap] fp32, ld = cap).
+// x0 / x1: the two ping-pong residual buffers (x1 null when pruning is off); the last executed layer,
+// its buffer and the live sizes are read from ctrl on the device.
+int lgtc_assignment(LgTensorCore* tc, cudaStream_t st, const float* x0, const float* x1, int cap, int m, int n, const int* ctrl,
+                    float* sim, long long* launches) {
+  if (cap != tc->cap) { set_error("lgtc_assignment: workspace capacity mismatch"); return B2S_EINVAL; }
+  const size_t plane = (size_t)2 * cap * 256;
+  dim3 g(cdiv(std::max(m, n), 8), 2);
+  launch_k(k_f32_to_bf16_rows<3>, g, 256, 0, st, x0, x1, tc->tx, 256, plane, 0, m, cap, n, ctrl);
+  TcGemmParams p = {};
+  p.K = 256; p.K1 = 256; p.N = 256; p.bias = tc->bfinal; p.ctrl = ctrl; p.ctrl_mode = 2; p.w_layer_rows = 256; p.alpha = 0.25f;
+  p.seg_base[0] = 0; p.seg_base[1] = cap; p.seg_rows[0] = m; p.seg_rows[1] = n; p.tiles0 = cdiv(m, 128);
+  p.plane_rows = 2 * cap; p.epi = TC_EPI_BF16; p.out_bf16 = tc->md; p.ld_bf16 = 256; p.out_plane = plane;
+  if (tc->prof) tc->prof->mark(PROF_GEMM, st);
+  launch_k(k_gemm_tc<64, 3>, dim3(4, p.tiles0 + cdiv(n, 128)), 192, TcGemmCfg<64, 3>::SMEM, st, tc->m_tx, tc->m_tx, tc->wfinal.map, p);
+  p = TcGemmParams();
+  p.K = 256; p.K1 = 256; p.N = n; p.bias = nullptr; p.ctrl = ctrl; p.ctrl_mode = 3;
+  p.w_plane_rows = 2 * cap; p.w_row0 = cap;
+  p.seg_base[0] = 0; p.seg_base[1] = 0; p.seg_rows[0] = m; p.seg_rows[1] = 0; p.tiles0 = cdiv(m, 128);
+  p.plane_rows = 2 * cap; p.epi = TC_EPI_F32; p.out_f32 = sim; p.ld_f32 = cap;
+  launch_k(k_gemm_tc<128, 3>, dim3(cdiv(n, 128), p.tiles0), 192, TcGemmCfg<128, 3>::SMEM, st, tc->m_md, tc->m_md, tc->m_md, p);
+  if (tc->prof) tc->prof->mark(PROF_GEMM, st);
+  if (launches) *launches += 3;
+  B2S_LAUNCH_CHECK();
+  return 0;
+}
+
 __nv_bfloat16* lgtc_xb(LgTensorCore* tc) { return tc->xb; }
 int lgtc_planes(LgTensorCore* tc) { return tc->np; }
 
@@ -328,8 +387,8 @@ int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int li, float* x, const float*
   if (derive_xb) {
     dim3 g(cdiv(std::max(m, n), 8), 2);
     const size_t xplane = (size_t)2 * cap * 256;
-    if (tc->np == 1) launch_k(k_f32_to_bf16_rows<1>, g, 256, 0, st, x, tc->xb, 256, xplane, 0, m, cap, n, ctrl);
-    else launch_k(k_f32_to_bf16_rows<3>, g, 256, 0, st, x, tc->xb, 256, xplane, 0, m, cap, n, ctrl);
+    if (tc->np == 1) launch_k(k_f32_to_bf16_rows<1>, g, 256, 0, st, x, (const float*)nullptr, tc->xb, 256, xplane, 0, m, cap, n, ctrl);
+    else launch_k(k_f32_to_bf16_rows<3>, g, 256, 0, st, x, (const float*)nullptr, tc->xb, 256, xplane, 0, m, cap, n, ctrl);
     if (launches) ++*launches;
     B2S_LAUNCH_CHECK();
   }
