@@ -4,6 +4,7 @@
 #include "aliked_kernels.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "conv_tc.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -33,6 +34,9 @@ struct b2s_aliked {
   float *sh0, *sh2, *sh4, *sh6;                         // score head
   float *so0_w, *so0_b, *so2_w, *so2_b, *sf_w, *aggT;   // desc head
   TcWeight tc_so0, tc_sf, tc_agg;                       // desc-head contractions on the tensor cores (fp32 as bf16x3)
+  __nv_bfloat16 *b1c2_pl, *b2c1_pl, *b2c2_pl;           // conv weights as bf16x3 chunk planes (conv_tc.cuh)
+  __nv_bfloat16 *t1a_pl, *x1p_pl, *t2a_pl;              // activations as chunk planes: block1.conv1 out, pool2(x1), block2.conv1 out
+  CUtensorMap m_t1a, m_x1p, m_t2a; int mapHp = 0, mapWp = 0;
   // workspace
   int wsHp = 0, wsWp = 0;
   float *img_pad, *resized, *t1a, *x1, *r2, *t2a, *x2, *x3in, *col3, *off3, *t3a, *r3, *x3, *x4in, *col4, *off4, *t4a, *r4, *x4;
@@ -138,6 +142,33 @@ int load_weights(b2s_aliked* h, const WeightBlob& wb) {
   B2S_TRY(upload_conv_direct(h, wb, "block2.conv1", 32, 16, bn, &h->b2c1_w, &h->b2c1_b));
   B2S_TRY(bn_fold(wb, "block2.bn2", 32, &bn));
   B2S_TRY(upload_conv_direct(h, wb, "block2.conv2", 32, 32, bn, &h->b2c2_w, &h->b2c2_b));
+  {
+    auto mkconv = [&](const std::string& name, const std::string& bnname, int cout, int cin, __nv_bfloat16** out) -> int {
+      BnFold b;
+      B2S_TRY(bn_fold(wb, bnname, cout, &b));
+      const TensorView* t = wb.get(name + ".weight", (size_t)cout * cin * 9);
+      if (!t) return B2S_EINVAL;
+      const int nch = cin / 8;
+      const size_t plane = (size_t)9 * cin * cout;
+      std::vector<__nv_bfloat16> o(3 * plane);
+      for (int tap = 0; tap < 9; ++tap)
+        for (int cc = 0; cc < nch; ++cc)
+          for (int co = 0; co < cout; ++co)
+            for (int j = 0; j < 8; ++j) {
+              float r = t->data[((size_t)co * cin + cc * 8 + j) * 9 + tap] * b.scale[co];
+              const size_t idx = (((size_t)tap * nch + cc) * cout + co) * 8 + j;
+              for (int pl = 0; pl < 3; ++pl) {
+                const __nv_bfloat16 q = __float2bfloat16_rn(r);
+                o[pl * plane + idx] = q;
+                r -= __bfloat162float(q);
+              }
+            }
+      return h->warena.upload(out, o);
+    };
+    B2S_TRY(mkconv("block1.conv2", "block1.bn2", 16, 16, &h->b1c2_pl));
+    B2S_TRY(mkconv("block2.conv1", "block2.bn1", 32, 16, &h->b2c1_pl));
+    B2S_TRY(mkconv("block2.conv2", "block2.bn2", 32, 32, &h->b2c2_pl));
+  }
   B2S_TRY(upload_plain(h, wb, "block2.downsample.weight", 32 * 16, &h->b2ds_w));
   B2S_TRY(upload_plain(h, wb, "block2.downsample.bias", 32, &h->b2ds_b));
   B2S_TRY(upload_dcn_block(h, wb, "block3", 32, 64, &h->b3));
@@ -198,8 +229,10 @@ int alloc_ws(b2s_aliked* h, int Hp, int Wp) {
   const size_t K = (size_t)h->n_limit, M = (size_t)h->M;
   DeviceArena& a = h->wsarena;
   B2S_TRY(a.alloc(&h->img_pad, 3 * P)); B2S_TRY(a.alloc(&h->resized, 3 * P));
-  B2S_TRY(a.alloc(&h->t1a, 16 * P)); B2S_TRY(a.alloc(&h->x1, 16 * P));
-  B2S_TRY(a.alloc(&h->r2, 32 * P2)); B2S_TRY(a.alloc(&h->t2a, 32 * P2)); B2S_TRY(a.alloc(&h->x2, 32 * P2));
+  B2S_TRY(a.alloc(&h->t1a, (size_t)1)); B2S_TRY(a.alloc(&h->x1, 16 * P));
+  B2S_TRY(a.alloc(&h->t1a_pl, 3 * 16 * P)); B2S_TRY(a.alloc(&h->x1p_pl, 3 * 16 * P2)); B2S_TRY(a.alloc(&h->t2a_pl, 3 * 32 * P2));
+  h->mapHp = h->mapWp = 0;
+  B2S_TRY(a.alloc(&h->r2, 32 * P2)); B2S_TRY(a.alloc(&h->t2a, (size_t)1)); B2S_TRY(a.alloc(&h->x2, 32 * P2));
   B2S_TRY(a.alloc(&h->x3in, 32 * P3)); B2S_TRY(a.alloc(&h->col3, 576 * P3)); B2S_TRY(a.alloc(&h->off3, 18 * P3));
   B2S_TRY(a.alloc(&h->t3a, 64 * P3)); B2S_TRY(a.alloc(&h->r3, 64 * P3)); B2S_TRY(a.alloc(&h->x3, 64 * P3));
   B2S_TRY(a.alloc(&h->x4in, 64 * P4)); B2S_TRY(a.alloc(&h->col4, 1152 * P4)); B2S_TRY(a.alloc(&h->off4, 18 * P4));
@@ -278,6 +311,9 @@ extern "C" int b2s_aliked_create(const b2s_aliked_cfg* cfg, const void* weights,
   h->M = cfg->model == 1 ? 32 : 16;
   h->n_limit = cfg->max_kp > 0 ? cfg->max_kp : 20000;
   cudaFuncSetAttribute(k_gemm_tc<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGemmCfg<64, 3>::SMEM);
+  cudaFuncSetAttribute(k_conv3x3_tc<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<16, 16>::SMEM);
+  cudaFuncSetAttribute(k_conv3x3_tc<16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<16, 32>::SMEM);
+  cudaFuncSetAttribute(k_conv3x3_tc<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<32, 32>::SMEM);
   int rc = load_weights(h, wb);
   if (rc) { delete h; return rc; }
   *out = h;
@@ -344,21 +380,37 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
   launch_k(k_preprocess, dim3(cdiv(Wp, 256), Hp), 256, 0, st, pp);
   ++h->launches; B2S_LAUNCH_CHECK();
 
-  // ---- block1 (full res) ----
+  // ---- block1 (full res) and block2 (1/2 res) ----
+  // conv1 (3 -> 16, K = 27) stays on the CUDA cores and emits tensor-core operand planes; the three
+  // 16/32-channel convs are implicit GEMMs on tcgen05 (conv_tc.cuh).  pool2 is fused into block1.conv2's
+  // epilogue (planes for block2.conv1) and into the 1x1 downsample.
+  const int H2 = Hp / 2, W2 = Wp / 2;
+  if (h->mapHp != Hp || h->mapWp != Wp) {
+    auto mk = [&](CUtensorMap* m, const __nv_bfloat16* ptr, int Hh, int Ww, int nch) -> int {
+      const uint64_t dims[4] = {8, (uint64_t)Ww, (uint64_t)Hh, (uint64_t)3 * nch};
+      const uint64_t str[3] = {16, (uint64_t)Ww * 16, (uint64_t)Hh * Ww * 16};
+      const uint32_t box[4] = {8, 130, 6, (uint32_t)nch};
+      return make_tmap_bf16_4d(m, ptr, dims, str, box);
+    };
+    B2S_TRY(mk(&h->m_t1a, h->t1a_pl, Hp, Wp, 2));
+    B2S_TRY(mk(&h->m_x1p, h->x1p_pl, H2, W2, 2));
+    B2S_TRY(mk(&h->m_t2a, h->t2a_pl, H2, W2, 4));
+    h->mapHp = Hp; h->mapWp = Wp;
+  }
   {
     dim3 g(cdiv(Wp, 32), cdiv(Hp, 16));
-    launch_k(k_conv3x3<3, 16, false>, g, dim3(16, 8, 1), 0, st, h->img_pad, Hp, Wp, h->b1c1_w, h->b1c1_b, nullptr, h->t1a, 1);
-    launch_k(k_conv3x3<16, 16, false>, g, dim3(16, 8, 1), 0, st, h->t1a, Hp, Wp, h->b1c2_w, h->b1c2_b, nullptr, h->x1, 1);
-    h->launches += 2; B2S_LAUNCH_CHECK();
-  }
-  // ---- block2 (1/2 res): pool2 fused into conv1's load and into the 1x1 downsample ----
-  const int H2 = Hp / 2, W2 = Wp / 2;
-  {
-    dim3 g(cdiv(W2, 32), cdiv(H2, 16));
+    launch_k(k_conv3x3<3, 16, false>, g, dim3(16, 8, 1), 0, st, h->img_pad, Hp, Wp, h->b1c1_w, h->b1c1_b, nullptr, (float*)nullptr, 1, h->t1a_pl);
+    ConvTcParams cp = {};
+    cp.H = Hp; cp.W = Wp; cp.wplanes = h->b1c2_pl; cp.bias = h->b1c2_b; cp.out_chw = h->x1; cp.out_pooled = h->x1p_pl;
+    launch_k(k_conv3x3_tc<16, 16>, dim3(cdiv(Wp, 128), cdiv(Hp, 4)), 192, ConvTcCfg<16, 16>::SMEM, st, h->m_t1a, cp);
     launch_k(k_pool2_conv1x1<16, 32>, cdiv(H2 * W2, 64), 256, 0, st, h->x1, H2, W2, h->b2ds_w, h->b2ds_b, h->r2);
-    launch_k(k_conv3x3<16, 32, true>, g, dim3(16, 8, 2), 0, st, h->x1, H2, W2, h->b2c1_w, h->b2c1_b, nullptr, h->t2a, 1);
-    launch_k(k_conv3x3<32, 32, false>, g, dim3(16, 8, 2), 0, st, h->t2a, H2, W2, h->b2c2_w, h->b2c2_b, h->r2, h->x2, 1);
-    h->launches += 3; B2S_LAUNCH_CHECK();
+    cp = ConvTcParams();
+    cp.H = H2; cp.W = W2; cp.wplanes = h->b2c1_pl; cp.bias = h->b2c1_b; cp.out_planes = h->t2a_pl;
+    launch_k(k_conv3x3_tc<16, 32>, dim3(cdiv(W2, 128), cdiv(H2, 4)), 192, ConvTcCfg<16, 32>::SMEM, st, h->m_x1p, cp);
+    cp = ConvTcParams();
+    cp.H = H2; cp.W = W2; cp.wplanes = h->b2c2_pl; cp.bias = h->b2c2_b; cp.residual = h->r2; cp.out_chw = h->x2;
+    launch_k(k_conv3x3_tc<32, 32>, dim3(cdiv(W2, 128), cdiv(H2, 4)), 192, ConvTcCfg<32, 32>::SMEM, st, h->m_t2a, cp);
+    h->launches += 5; B2S_LAUNCH_CHECK();
   }
   // ---- block3 (1/8) and block4 (1/32): DCN via im2col + GEMM, HWC ----
   const int H3 = H2 / 4, W3 = W2 / 4, H4 = H3 / 4, W4 = W3 / 4;

@@ -95,7 +95,7 @@ template <int CIN, int COUT, bool POOL2>
 __global__ void __launch_bounds__(128 * (COUT / 16)) k_conv3x3(const float* __restrict__ in, int H, int W,
                                                                const float* __restrict__ w, const float* __restrict__ bias,
                                                                const float* __restrict__ residual, float* __restrict__ out,
-                                                               int act) {
+                                                               int act, __nv_bfloat16* __restrict__ out_planes) {
   pdl_wait();
   constexpr int CC = CIN < 8 ? CIN : 8;
   constexpr int TH = 16, TW = 32, RS = TW + 4;
@@ -160,6 +160,42 @@ __global__ void __launch_bounds__(128 * (COUT / 16)) k_conv3x3(const float* __re
           }
         }
     }
+  }
+  if (out_planes) {
+    // tensor-core operand format for the next conv (conv_tc.cuh): [plane][8-channel chunk][H][W][8] bf16
+    const size_t HW = (size_t)H * W, plane = (size_t)(COUT / 8) * HW * 8;
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const int gy = y0 + 2 * ty + py, gx = x0 + 2 * tx + px;
+        if (gy >= H || gx >= W) continue;
+        float v[16];
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+          v[o] = acc[py * 2 + px][o] + bias[tz * 16 + o];
+          if (act == 1) v[o] = selu_f(v[o]);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          __nv_bfloat16* d = out_planes + ((size_t)(tz * 2 + ch) * HW + (size_t)gy * W + gx) * 8;
+          float r[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = v[8 * ch + j];
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 hb = __floats2bfloat162_rn(r[2 * j], r[2 * j + 1]);
+              w[j] = *reinterpret_cast<const uint32_t*>(&hb);
+              r[2 * j] -= __uint_as_float(w[j] << 16); r[2 * j + 1] -= __uint_as_float(w[j] & 0xFFFF0000u);
+            }
+            *reinterpret_cast<uint4*>(d + pl * plane) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+    return;
   }
 #pragma unroll
   for (int py = 0; py < 2; ++py) {

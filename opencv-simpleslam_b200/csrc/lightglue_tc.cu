@@ -44,6 +44,34 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t inner, uint64
   return 0;
 }
 
+int make_tmap_bf16_4d(CUtensorMap* out, const void* gptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                      const uint32_t box[4]) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeTiled is not available from the installed driver");
+    return B2S_ECUDA;
+  }
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t st[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = reinterpret_cast<EncodeFn>(fn)(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(gptr), d, st, bx, es,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d) failed: CUresult %d (dims %llu %llu %llu %llu box %u %u %u %u)", (int)r,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)dims[3],
+              box[0], box[1], box[2], box[3]);
+    return B2S_ECUDA;
+  }
+  return 0;
+}
+
 // ---- glue kernels -------------------------------------------------------------------------
 // store 8 consecutive values of one row as NP bf16 planes (plane p at y + p * plane)
 template <int NP>

@@ -55,6 +55,19 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 4-D tile load (c0 innermost); out-of-bounds elements (negative or past the extent) arrive as zeros
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// contiguous global -> shared bulk copy (bytes multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // ---- TMEM -------------------------------------------------------------------------------
 // whole warp; writes the TMEM base address (lane<<16 | column) to *smem_slot
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
@@ -113,6 +126,12 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
 }
+// same, no swizzle ("interleave"): 8-row x 16-byte core matrices stored contiguously (128 B);
+// sbo = bytes between consecutive 8-row groups, lbo = bytes between the two 16-byte K chunks of one MMA
+__device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
 // instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
 //   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt  [15] A major  [16] B major (1 = MN-major)
 //   [17,23) N >> 3         [24,29) M >> 4
@@ -155,5 +174,8 @@ template <int NP> struct PlaneTerms {
 // host: 2-D bf16 tensor map, 128-byte swizzle. inner = contiguous extent (elements), box_inner must be 64.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t inner, uint64_t rows, uint64_t row_pitch_bytes,
                       uint32_t box_inner, uint32_t box_rows);
+// host: 4-D bf16 tensor map without swizzle. dims[0] is the contiguous extent; strides_bytes[i] is the pitch of dims[i+1].
+int make_tmap_bf16_4d(CUtensorMap* out, const void* gptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                      const uint32_t box[4]);
 
 }  // namespace b2s
