@@ -3,14 +3,19 @@
 // products a_i b_j (i + j <= 2), so S = Q K^T and O = P V are accumulated to fp32 rounding level
 // on the tensor pipe; the softmax itself runs in fp32 registers.
 //   O = softmax(Q K^T * scale) V,  head_dim 64, 128-query tile per CTA, 64-key tiles.
-// Same role split as attn_tc.cuh (two softmax groups on alternating key tiles, TMA warp, MMA warp,
-// lazy rescale with O kept in TMEM).  Differences: K and V tiles (3 planes x 8 KB) share ONE ring of
-// 3 slots filled in exactly the order the MMA warp consumes them (K0 K1 [K2 V0] [K3 V1] ...), P has
-// three planes per group.  The tensor core truncates its fp32 accumulator after every k-step, so every
-// contraction keeps TWO TMEM accumulators - the main q0*k0 (p0*v0) term and the five correction terms - and
-// the per-tile P V result is added to the running output in fp32 REGISTERS (round-to-nearest) instead of
-// being accumulated across tiles by the MMA.  TMEM: S 2 groups x (main, corr) x 64 + O likewise = 512 columns.
-// grid = (ceil(max nq/128), heads, nprob).
+// Same role split as attn_tc.cuh (two softmax groups on alternating key tiles, TMA warp, MMA warp, lazy
+// rescale).  Differences:
+//  * P never touches shared memory: the softmax threads write its three planes into TENSOR MEMORY
+//    (tcgen05.st, lane = query row, one column = two keys) and the P V MMAs take their A operand from
+//    there (TS form).  Shared memory then only feeds the B operands, which is what bounds this kernel
+//    (head_dim 64 means N = 64 MMAs: an A operand from shared memory would cost 2x the B traffic);
+//  * the tensor core truncates its fp32 accumulator after every k-step, so a tile's six terms are issued
+//    smallest first (the main a0*b0 term last: only its 4 k-steps round at full magnitude) and the per-tile
+//    P V result is added to the running output in fp32 REGISTERS instead of being accumulated across tiles;
+//  * the score MMAs are issued for PAIRS of key tiles (N = 128: tile 2i for group 0 and 2i+1 for group 1 land
+//    in adjacent TMEM columns), which halves the re-reads of Q from shared memory; K therefore arrives as
+//    128-key tiles (2-slot ring, 3 planes x 16 KB), V as 64-key tiles (3-slot ring, 3 planes x 8 KB).
+// TMEM (512 columns allocated): S[g] 64 | O[g] 64 | P[g] 3 x 32, g = 0, 1.   grid = (ceil(max nq/128), heads, nprob).
 #pragma once
 #include "attn_tc.cuh"
 
@@ -19,10 +24,11 @@ namespace b2s {
 constexpr int A3_BQ = 128, A3_BK = 64, A3_D = 64, A3_NP = 3, A3_SLOTS = 3;
 constexpr int A3_QPL = A3_BQ * A3_D * 2;             // 16 KB: one Q plane  [128 x 64] bf16
 constexpr int A3_KPL = A3_BK * A3_D * 2;             //  8 KB: one K / V plane [64 x 64] bf16
-constexpr int A3_SLOT = A3_NP * A3_KPL;              // 24 KB
-constexpr int A3_PPL = A3_BQ * A3_BK * 2;            // 16 KB: one P plane [128 x 64] bf16
-constexpr int A3_SMEM = A3_NP * A3_QPL + A3_SLOTS * A3_SLOT + 2 * A3_NP * A3_PPL + 1024 + 256;
+constexpr int A3_SLOT = A3_NP * A3_KPL;              // 24 KB: one V slot
+constexpr int A3_KSLOTS = 2, A3_KSLOT = A3_NP * A3_QPL;   // 48 KB: one K slot = a pair of key tiles
+constexpr int A3_SMEM = A3_NP * A3_QPL + A3_KSLOTS * A3_KSLOT + A3_SLOTS * A3_SLOT + 1024 + 256;
 constexpr int A3_THREADS = 384;
+static_assert(66 * 128 * 4 <= A3_KSLOTS * A3_KSLOT, "the final merge buffer aliases the K ring");
 
 struct Attn3Params {
   AttnTcProb prob[2];
@@ -33,10 +39,9 @@ struct Attn3Params {
   const int* ctrl; int cross;
 };
 
-// P chunk c (32 keys) of one row -> three swizzled K-major planes; returns the partial row sum (fp32 values)
+// P chunk c (32 keys) of one row -> three planes in tensor memory (16 columns each); returns the partial row sum
 template <bool MASK>
-__device__ __forceinline__ float a3_write_p_chunk(const uint32_t (&v)[32], int c, uint32_t prow_addr, int r, int limit, float scale,
-                                                  float m_used) {
+__device__ __forceinline__ float a3_write_p_chunk(const uint32_t (&v)[32], int c, uint32_t p_addr, int limit, float scale, float m_used) {
   float sum0 = 0.f, sum1 = 0.f;
   uint32_t pk[A3_NP][16];
 #pragma unroll
@@ -53,14 +58,8 @@ __device__ __forceinline__ float a3_write_p_chunk(const uint32_t (&v)[32], int c
 #pragma unroll
     for (int pl = 0; pl < A3_NP; ++pl) pk[pl][t >> 1] = w[pl];
   }
-  // 32 keys = 64 B = four 16-byte chunks: chunk (c * 4 + q) ^ (r & 7) of the 128-byte row
 #pragma unroll
-  for (int pl = 0; pl < A3_NP; ++pl)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int chunk = ((c * 4 + q) ^ (r & 7));
-      st_shared_v4(prow_addr + pl * A3_PPL + chunk * 16, pk[pl][4 * q], pk[pl][4 * q + 1], pk[pl][4 * q + 2], pk[pl][4 * q + 3]);
-    }
+  for (int pl = 0; pl < A3_NP; ++pl) tc::tmem_st16(p_addr + pl * 32 + c * 16, pk[pl]);
   return sum0 + sum1;
 }
 
@@ -69,12 +68,13 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                               // [3 planes]
-  uint8_t* sR = sQ + A3_NP * A3_QPL;                // ring [A3_SLOTS][3 planes]
-  uint8_t* sP = sR + A3_SLOTS * A3_SLOT;            // [2 groups][3 planes]; reused for the final merge
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * A3_NP * A3_PPL);
+  uint8_t* sK = sQ + A3_NP * A3_QPL;                // ring [A3_KSLOTS][3 planes][128 keys]; reused for the final merge
+  uint8_t* sV = sK + A3_KSLOTS * A3_KSLOT;          // ring [A3_SLOTS][3 planes][64 keys]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + A3_SLOTS * A3_SLOT);
   uint64_t* q_full = bars;
-  uint64_t* r_full = bars + 1;                 uint64_t* r_empty = r_full + A3_SLOTS;
-  uint64_t* s_full = r_empty + A3_SLOTS;       uint64_t* s_free = s_full + 2;
+  uint64_t* k_full = bars + 1;                 uint64_t* k_empty = k_full + A3_SLOTS;
+  uint64_t* v_full = k_empty + A3_SLOTS;       uint64_t* v_empty = v_full + A3_SLOTS;
+  uint64_t* s_full = v_empty + A3_SLOTS;       uint64_t* s_free = s_full + 2;
   uint64_t* p_full = s_free + 2;               uint64_t* o_full = p_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
@@ -87,7 +87,10 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
   if (warp == 8 && lane == 0) { tc::tma_prefetch_desc(&mapQ); tc::tma_prefetch_desc(&mapKV); }
   if (warp == 9 && lane == 0) {
     tc::mbar_init(q_full, 1);
-    for (int b = 0; b < A3_SLOTS; ++b) { tc::mbar_init(&r_full[b], 1); tc::mbar_init(&r_empty[b], 1); }
+    for (int b = 0; b < A3_SLOTS; ++b) {
+      tc::mbar_init(&k_full[b], 1); tc::mbar_init(&k_empty[b], 1);
+      tc::mbar_init(&v_full[b], 1); tc::mbar_init(&v_empty[b], 1);
+    }
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(&s_full[b], 1); tc::mbar_init(&s_free[b], 128);
       tc::mbar_init(&p_full[b], 128); tc::mbar_init(&o_full[b], 1);
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
   }
   const bool live = q0 < pr.nq;                          // uniform per CTA
   const int nt = live ? (pr.nk + A3_BK - 1) / A3_BK : 0;
-  const uint32_t tS = tmem_base, tO = tmem_base + 256;    // S[g] = tS + 128 g + {0 main, 64 corr} ; O[g] likewise
+  const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 256;   // S[g] + 64 g, O[g] + 64 g, P[g] + 96 g
 
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -121,78 +124,78 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
 #pragma unroll
       for (int pl = 0; pl < A3_NP; ++pl)
         tc::tma_load_2d(sQ + pl * A3_QPL, &mapQ, q_full, p.qcol + h * 64, pl * p.plane_rows + pr.q_row + q0);
-      int c = 0;                                           // ring position, in consumption order
-      auto load = [&](int col, int j) {
-        const int b = c % A3_SLOTS, ph = (c / A3_SLOTS) & 1;
-        tc::mbar_wait(&r_empty[b], ph ^ 1);
-        tc::mbar_expect_tx(&r_full[b], A3_SLOT);
+      for (int j = 0; j < nt; ++j) {
+        if ((j & 1) == 0) {                                  // K: one 128-key tile per pair of key tiles
+          const int jp = j >> 1, kb = jp % A3_KSLOTS, kph = (jp / A3_KSLOTS) & 1;
+          tc::mbar_wait(&k_empty[kb], kph ^ 1);
+          tc::mbar_expect_tx(&k_full[kb], A3_KSLOT);
+#pragma unroll
+          for (int pl = 0; pl < A3_NP; ++pl)
+            tc::tma_load_2d(sK + kb * A3_KSLOT + pl * A3_QPL, &mapQ, &k_full[kb], p.kcol + h * 64, pl * p.plane_rows + pr.k_row + j * A3_BK);
+        }
+        const int b = j % A3_SLOTS, ph = (j / A3_SLOTS) & 1;
+        tc::mbar_wait(&v_empty[b], ph ^ 1);
+        tc::mbar_expect_tx(&v_full[b], A3_SLOT);
 #pragma unroll
         for (int pl = 0; pl < A3_NP; ++pl)
-          tc::tma_load_2d(sR + b * A3_SLOT + pl * A3_KPL, &mapKV, &r_full[b], col + h * 64, pl * p.plane_rows + pr.k_row + j * A3_BK);
-        ++c;
-      };
-      load(p.kcol, 0);
-      if (nt > 1) load(p.kcol, 1);
-      for (int j = 0; j < nt; ++j) {
-        if (j + 2 < nt) load(p.kcol, j + 2);
-        load(p.vcol, j);
+          tc::tma_load_2d(sV + b * A3_SLOT + pl * A3_KPL, &mapKV, &v_full[b], p.vcol + h * 64, pl * p.plane_rows + pr.k_row + j * A3_BK);
       }
     }
   } else if (warp == 9) {
     if (tc::elect_one()) {
       using Terms = tc::PlaneTerms<A3_NP>;
-      constexpr uint32_t idesc_s = tc::idesc_bf16(128, 64, 0, 0);    // S: A = Q (K-major), B = K tile (K-major)
-      constexpr uint32_t idesc_o = tc::idesc_bf16(128, 64, 0, 1);    // PV: A = P (K-major), B = V (MN-major)
+      constexpr uint32_t idesc_s = tc::idesc_bf16(128, 128, 0, 0);   // S pair: A = Q (K-major), B = 128 keys (K-major)
+      constexpr uint32_t idesc_o = tc::idesc_bf16(128, 64, 0, 1);    // PV: A = P (tensor memory), B = V (MN-major)
       const uint32_t q_addr = tc::smem_u32(sQ);
-      int c = 0;
-      auto issue_s = [&](int j) {
-        const int b = c % A3_SLOTS, ph = (c / A3_SLOTS) & 1, g = j & 1;
-        ++c;
-        tc::mbar_wait(&r_full[b], ph);
+      auto issue_s_pair = [&](int jp) {                              // tiles 2jp (-> S[0]) and 2jp + 1 (-> S[1])
+        const int b = jp % A3_KSLOTS, ph = (jp / A3_KSLOTS) & 1;
+        tc::mbar_wait(&k_full[b], ph);
         tc::tc_fence_after();
-        const uint32_t k_addr = tc::smem_u32(sR + b * A3_SLOT);
+        const uint32_t k_addr = tc::smem_u32(sK + b * A3_KSLOT);
 #pragma unroll
         for (int t = 0; t < Terms::N; ++t)
 #pragma unroll
           for (int k = 0; k < A3_D / 16; ++k) {
             const uint64_t ad = tc::smem_desc_sw128(q_addr + Terms::a(t) * A3_QPL + k * 32, 16, 1024);
-            const uint64_t bd = tc::smem_desc_sw128(k_addr + Terms::b(t) * A3_KPL + k * 32, 16, 1024);
-            const bool main_term = t == Terms::N - 1;
-            tc::umma_bf16(tS + g * 128 + (main_term ? 0 : 64), ad, bd, idesc_s, main_term ? (k ? 1u : 0u) : ((t | k) ? 1u : 0u));
+            const uint64_t bd = tc::smem_desc_sw128(k_addr + Terms::b(t) * A3_QPL + k * 32, 16, 1024);
+            tc::umma_bf16(tS, ad, bd, idesc_s, (t | k) ? 1u : 0u);
           }
-        tc::umma_commit(&s_full[g]);
-        tc::umma_commit(&r_empty[b]);
+        tc::umma_commit(&s_full[0]);
+        tc::umma_commit(&s_full[1]);
+        tc::umma_commit(&k_empty[b]);
       };
       auto issue_pv = [&](int j) {
-        const int b = c % A3_SLOTS, ph = (c / A3_SLOTS) & 1, g = j & 1;
-        ++c;
-        tc::mbar_wait(&r_full[b], ph);
+        const int b = j % A3_SLOTS, ph = (j / A3_SLOTS) & 1, g = j & 1;
+        tc::mbar_wait(&v_full[b], ph);
         tc::tc_fence_after();
-        const uint32_t p_addr = tc::smem_u32(sP + g * A3_NP * A3_PPL), v_addr = tc::smem_u32(sR + b * A3_SLOT);
+        const uint32_t v_addr = tc::smem_u32(sV + b * A3_SLOT);
 #pragma unroll
         for (int t = 0; t < Terms::N; ++t)
 #pragma unroll
           for (int kk = 0; kk < A3_BK / 16; ++kk) {
-            // P plane: [128 x 64] K-major; V plane: [64 keys x 64 d] MN-major, 16 keys = 2 swizzle atoms = 2048 B
-            const uint64_t ad = tc::smem_desc_sw128(p_addr + Terms::a(t) * A3_PPL + kk * 32, 16, 1024);
+            // P plane: 32 columns (64 keys), 16 keys = 8 columns; V plane: [64 keys x 64 d] MN-major, 16 keys = 2048 B
             const uint64_t bd = tc::smem_desc_sw128(v_addr + Terms::b(t) * A3_KPL + kk * 2048, 16, 1024);
-            const bool main_term = t == Terms::N - 1;      // per-tile result: both accumulators start afresh
-            tc::umma_bf16(tO + g * 128 + (main_term ? 0 : 64), ad, bd, idesc_o, main_term ? (kk ? 1u : 0u) : ((t | kk) ? 1u : 0u));
+            tc::umma_bf16_ts(tO + g * 64, tP + g * 96 + Terms::a(t) * 32 + kk * 8, bd, idesc_o, (t | kk) ? 1u : 0u);   // fresh per tile
           }
         tc::umma_commit(&o_full[g]);
-        tc::umma_commit(&r_empty[b]);
+        tc::umma_commit(&v_empty[b]);
       };
       tc::mbar_wait(q_full, 0);
-      issue_s(0);
-      if (nt > 1) issue_s(1);
-      for (int j = 0; j < nt; ++j) {
-        const int g = j & 1, ph = (j >> 1) & 1;
-        if (j + 2 < nt) {                     // the group has S_j in registers: its next score tile can start
-          tc::mbar_wait(&s_free[g], ph);
-          issue_s(j + 2);
+      issue_s_pair(0);
+      const int npairs = (nt + 1) >> 1;
+      for (int jp = 0; jp < npairs; ++jp) {
+        const int ph = jp & 1;
+        if (jp + 1 < npairs) {                // both groups have their score tiles in registers: next pair can start
+          tc::mbar_wait(&s_free[0], ph);
+          tc::mbar_wait(&s_free[1], ph);
+          issue_s_pair(jp + 1);
         }
-        tc::mbar_wait(&p_full[g], ph);        // P_j written (and O[g] rescaled if the reference max moved)
-        issue_pv(j);
+        tc::mbar_wait(&p_full[0], ph);        // P of tile 2jp is in tensor memory
+        issue_pv(2 * jp);
+        if (2 * jp + 1 < nt) {
+          tc::mbar_wait(&p_full[1], ph);
+          issue_pv(2 * jp + 1);
+        }
       }
     }
   } else if (warp < 8) {
@@ -206,17 +209,16 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
     float o[A3_D];                                        // running output (fp32 registers)
 #pragma unroll
     for (int d = 0; d < A3_D; ++d) o[d] = 0.f;
-    const uint32_t prow_addr = tc::smem_u32(sP + g * A3_NP * A3_PPL + r * 128);
-    const uint32_t s_addr = tS + g * 128 + lane_addr, o_addr = tO + g * 128 + lane_addr;
-    // o += (main + corr) of the PV result sitting in TMEM (exact fp32 adds)
+    const uint32_t s_addr = tS + g * 64 + lane_addr, o_addr = tO + g * 64 + lane_addr, p_addr = tP + g * 96 + lane_addr;
+    // o += the P V result of one tile sitting in TMEM (exact fp32 adds)
     auto add_pv = [&]() {
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t a[32], b[32];
-        tc::tmem_ld32(o_addr + 32 * c, a); tc::tmem_ld32(o_addr + 64 + 32 * c, b);
+        uint32_t a[32];
+        tc::tmem_ld32(o_addr + 32 * c, a);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) o[32 * c + e] += __uint_as_float(a[e]) + __uint_as_float(b[e]);
+        for (int e = 0; e < 32; ++e) o[32 * c + e] += __uint_as_float(a[e]);
       }
     };
     int t = 0;                                            // index among this group's tiles
@@ -224,14 +226,8 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
       tc::mbar_wait(&s_full[g], t & 1);
       tc::tc_fence_after();
       uint32_t s[2][32];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t b[32];
-        tc::tmem_ld32(s_addr + 32 * c, s[c]); tc::tmem_ld32(s_addr + 64 + 32 * c, b);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) s[c][e] = __float_as_uint(__uint_as_float(s[c][e]) + __uint_as_float(b[e]));
-      }
+      tc::tmem_ld32(s_addr, s[0]); tc::tmem_ld32(s_addr + 32, s[1]);
+      tc::tmem_ld_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(&s_free[g]);                        // S[g] is in registers: next QK^T of this group may overwrite it
       const int limit = pr.nk - j * A3_BK;
@@ -256,13 +252,13 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
         }
       }
       float sum;
-      if (full) sum = a3_write_p_chunk<false>(s[0], 0, prow_addr, r, limit, p.scale_log2e, m_used) +
-                      a3_write_p_chunk<false>(s[1], 1, prow_addr, r, limit, p.scale_log2e, m_used);
-      else sum = a3_write_p_chunk<true>(s[0], 0, prow_addr, r, limit, p.scale_log2e, m_used) +
-                 a3_write_p_chunk<true>(s[1], 1, prow_addr, r, limit, p.scale_log2e, m_used);
+      if (full) sum = a3_write_p_chunk<false>(s[0], 0, p_addr, limit, p.scale_log2e, m_used) +
+                      a3_write_p_chunk<false>(s[1], 1, p_addr, limit, p.scale_log2e, m_used);
+      else sum = a3_write_p_chunk<true>(s[0], 0, p_addr, limit, p.scale_log2e, m_used) +
+                 a3_write_p_chunk<true>(s[1], 1, p_addr, limit, p.scale_log2e, m_used);
       l_run += sum;
-      tc::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc::tc_fence_before();            // order our tcgen05.ld before the MMAs that follow the arrive
+      tc::tmem_st_wait();               // P is in tensor memory
+      tc::tc_fence_before();            // order our tcgen05.ld / st before the MMAs that follow the arrive
       tc::mbar_arrive(&p_full[g]);
     }
     // ---- the group's last PV ----
@@ -273,8 +269,8 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
     }
     const float m_run = m_used;
     tc::tc_fence_before();
-    // ---- merge the two groups' partial softmax states (all MMAs that read sP have completed) ----
-    float* mrg = reinterpret_cast<float*>(sP);            // [66][128] floats: O^T (64 rows), m, l
+    // ---- merge the two groups' partial softmax states (every MMA and every TMA load has completed) ----
+    float* mrg = reinterpret_cast<float*>(sK);            // [66][128] floats: O^T (64 rows), m, l
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (g == 1) {
 #pragma unroll
