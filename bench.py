@@ -14,7 +14,8 @@ frame t, match (t-1, t)) = 1 ALIKED extraction + 1 LightGlue match per unit, 124
           H2D of both frames' features for the match, D2H of the matches; lists of
           cv2.KeyPoint/cv2.DMatch built. Wall clock bracketed by synchronisation.
   roofline : dominant kernel (attention) timed live with CUDA events inside the library
-          (b2s_lg_profile) during the timed steps.
+          (b2s_lg_profile) in a separate pass right after the timed steps (the event pairs would
+          perturb them); executed work is counted on the device.
   cpu_baseline : the CPU oracle (port of the reference's lightglue path) through the same API on
           the host cores, bounded sample.  --impl reference runs only that arm.
 Multi-GPU (torchrun): every rank streams its own contiguous chunk of frames (halo frame
@@ -74,7 +75,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.02)
 
     def stop(self):
         self._stop_evt.set()
@@ -158,86 +159,113 @@ def run_ours(args):
     frames_dev = [torch.from_numpy(f).to(dev) for f in frames_np]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    # Software pipeline over two CUDA streams: while LightGlue matches (t-1, t) on stream B, ALIKED
-    # already extracts frame t+1 on stream A (frames are independent; both stages leave SMs idle on
-    # their own).  3 feature slots: t-1 and t are being matched while t+1 is being written.
-    NS = 3
-    kp_buf = [torch.empty((NKP, 2), device=dev) for _ in range(NS)]
-    de_buf = [torch.empty((NKP, 128), device=dev) for _ in range(NS)]
-    n_host = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(NS)]
-    counts = [0] * NS
-    match_counts = []
-    s_ext, s_mat = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    ext_done = [torch.cuda.Event() for _ in range(NS)]
-    mat_done = torch.cuda.Event()
+    def device_run(matcher, steps, warm, sampler=None):
+        """Streams (warm + steps) * P frame pairs through extract + match with everything resident in HBM.
+        Software pipeline over two CUDA streams: while LightGlue matches (t-1, t) on stream B, ALIKED already
+        extracts frame t+1 on stream A.  3 feature slots: t-1 and t are being matched while t+1 is written.
+        Returns (per-step ms list, launches inside the timed steps, match counts, wall seconds)."""
+        NS = 3
+        kp_buf = [torch.empty((NKP, 2), device=dev) for _ in range(NS)]
+        de_buf = [torch.empty((NKP, 128), device=dev) for _ in range(NS)]
+        n_host = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(NS)]
+        counts = [0] * NS
+        s_ext, s_mat = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        ext_done = [torch.cuda.Event() for _ in range(NS)]
+        mat_done = torch.cuda.Event()
 
-    def enqueue_extract(t):
-        slot = t % NS
-        with torch.cuda.stream(s_ext):
-            s_ext.wait_event(mat_done)     # slot t%3 was last read by match(t-3, t-2): already enqueued before
-            kp, de, _, n = det.extract_device(frames_dev[t % len(frames_dev)], _lib.IMG_BGR_U8_HWC, H, W, 3 * W)
-            kp_buf[slot].copy_(kp, non_blocking=True)
-            de_buf[slot].copy_(de, non_blocking=True)
-            n_host[slot].copy_(n, non_blocking=True)
-            ext_done[slot].record(s_ext)
+        def enqueue_extract(t):
+            slot = t % NS
+            with torch.cuda.stream(s_ext):
+                s_ext.wait_event(mat_done)     # slot t%3 was last read by match(t-3, t-2): already enqueued before
+                kp, de, _, n = det.extract_device(frames_dev[t % len(frames_dev)], _lib.IMG_BGR_U8_HWC, H, W, 3 * W)
+                kp_buf[slot].copy_(kp, non_blocking=True)
+                de_buf[slot].copy_(de, non_blocking=True)
+                n_host[slot].copy_(n, non_blocking=True)
+                ext_done[slot].record(s_ext)
 
-    def finish_extract(t):
-        slot = t % NS
-        ext_done[slot].synchronize()       # the keypoint count sizes the matcher's launch
-        counts[slot] = int(n_host[slot][0])
+        def finish_extract(t):
+            slot = t % NS
+            ext_done[slot].synchronize()       # the keypoint count sizes the matcher's launch
+            counts[slot] = int(n_host[slot][0])
 
-    def device_step(t0):
-        """pairs (t-1, t) for t = t0 .. t0+P-1; frame t0 is already in flight, frame t0+P is left in flight."""
-        res = None
-        for i in range(P):
-            t = t0 + i
-            finish_extract(t)
-            enqueue_extract(t + 1)
-            cur, prv = t % NS, (t - 1) % NS
-            with torch.cuda.stream(s_mat):
-                s_mat.wait_event(ext_done[cur])
-                res = mat.match_device(kp_buf[prv][:counts[prv]], de_buf[prv][:counts[prv]],
-                                       kp_buf[cur][:counts[cur]], de_buf[cur][:counts[cur]], full=False)
-                mat_done.record(s_mat)
-        return res
+        def device_step(t0):
+            res = None
+            for i in range(P):
+                t = t0 + i
+                finish_extract(t)
+                enqueue_extract(t + 1)
+                cur, prv = t % NS, (t - 1) % NS
+                with torch.cuda.stream(s_mat):
+                    s_mat.wait_event(ext_done[cur])
+                    res = matcher.match_device(kp_buf[prv][:counts[prv]], de_buf[prv][:counts[prv]],
+                                               kp_buf[cur][:counts[cur]], de_buf[cur][:counts[cur]], full=False)
+                    mat_done.record(s_mat)
+            return res
 
-    def join_streams():
-        cur = torch.cuda.current_stream()
-        cur.wait_stream(s_ext); cur.wait_stream(s_mat)
+        def join_streams():
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(s_ext); cur.wait_stream(s_mat)
 
-    enqueue_extract(0); finish_extract(0); enqueue_extract(1)
-    for s in range(Wm):
-        device_step(1 + s * P)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    l0 = det.launches + mat.launches
-    mat.profile(True)
+        enqueue_extract(0); finish_extract(0); enqueue_extract(1)
+        for s in range(warm):
+            device_step(1 + s * P)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        l0 = det.launches + matcher.launches
+        if sampler is not None:
+            sampler.start()
+        evs, mcounts = [], []
+        wall0 = time.perf_counter()
+        for s in range(steps):
+            join_streams()
+            flush.fill_(s & 0xFF)                       # L2 flush between timed iterations (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            s_ext.wait_event(e0); s_mat.wait_event(e0)
+            res = device_step(1 + (warm + s) * P)
+            join_streams()
+            e1.record()
+            evs.append((e0, e1))
+            mcounts.append(res["n"])
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - wall0
+        launches = det.launches + matcher.launches - l0
+        return [a.elapsed_time(b) for a, b in evs], launches, [int(c.item()) for c in mcounts], wall
+
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    evs = []
-    wall0 = time.perf_counter()
-    for s in range(K):
-        join_streams()
-        flush.fill_(s & 0xFF)                       # L2 flush between timed iterations (untimed)
+    step_ms, launches, mcounts, wall = device_run(mat, K, Wm, sampler)
+    clocks = sampler.stop()
+    total_ms = float(sum(step_ms))
+    mean_matches = float(np.mean(mcounts))
+
+    # ---- per-kernel timing pass (outside the timed region: the event pairs around every attention / GEMM launch
+    #      would perturb it): single stream, the same frames, CUDA events on the launching stream inside the library
+    def kernel_pass(matcher, pairs=4):
+        feats = []
+        for t in range(pairs + 1):
+            kp, de, _, n = det.extract_device(frames_dev[t % len(frames_dev)], _lib.IMG_BGR_U8_HWC, H, W, 3 * W)
+            torch.cuda.synchronize()
+            k = int(n.item())
+            feats.append((kp[:k].clone(), de[:k].clone()))
+        for t in range(2):
+            matcher.match_device(feats[t][0], feats[t][1], feats[t + 1][0], feats[t + 1][1], full=False)
+        torch.cuda.synchronize()
+        matcher.profile(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        s_ext.wait_event(e0); s_mat.wait_event(e0)
-        res = device_step(1 + (Wm + s) * P)
-        join_streams()
+        for t in range(pairs):
+            matcher.match_device(feats[t][0], feats[t][1], feats[t + 1][0], feats[t + 1][1], full=False)
         e1.record()
-        evs.append((e0, e1))
-        match_counts.append(res["n"])
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
-    launches = det.launches + mat.launches - l0
-    attn_ms, attn_n = mat.profile_read(0)
-    gemm_ms, gemm_n = mat.profile_read(1)
-    mat.profile(False)
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = float(sum(step_ms))
-    mean_matches = float(np.mean([int(c.item()) for c in match_counts]))
+        torch.cuda.synchronize()
+        attn_ms, attn_n = matcher.profile_read(0)
+        gemm_ms, gemm_n = matcher.profile_read(1)
+        self_w, cross_w = matcher.profile_work()
+        matcher.profile(False)
+        return dict(attn_ms=attn_ms, attn_n=attn_n, gemm_ms=gemm_ms, gemm_n=gemm_n, self_w=self_w, cross_w=cross_w,
+                    match_ms=e0.elapsed_time(e1) / pairs, pairs=pairs)
+
+    kp_ = kernel_pass(mat)
 
     # ---- e2e through the drop-in API with host buffers -------------------------------------
     e2e_pairs = max(4, min(K * P, 24))
@@ -261,6 +289,16 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     e2e_matches = len(ms)
 
+    # ---- secondary: the bf16 matcher on the same stream (reported next to the fp32 headline) ----
+    other = None
+    if args.precision == "fp32" and not args.no_secondary:
+        mat16 = frontend.LightGlue(weights=sl, device=dev, precision="bf16", max_kp=NKP)
+        ms16, _, mc16, _ = device_run(mat16, max(2, K // 2), 2)
+        other = {"precision": "bf16", "value": world * len(ms16) * P / (float(sum(ms16)) / 1e3), "unit": "frame-pairs/s",
+                 "ms_per_step": float(np.mean(ms16)), "mean_matches_per_pair": float(np.mean(mc16)),
+                 "note": "operands rounded once to bf16 (>= 99 % match-set agreement, tests/test_gpu_tensorcore.py); this rank only"}
+        del mat16
+
     t_total = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
@@ -279,36 +317,60 @@ def run_ours(args):
         pass
     tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s"
-    # dominant kernel: attention. Algorithmic flops per launch (two problems per launch:
-    # self = both images, cross = both directions): 2 * 4*N*N*64*... = QK^T + PV over 4 heads
-    # SURVEY 8d counting: self launch = 1024*(M^2+N^2), cross launch = 1536*M*N (similarity once)
-    attn_flops_per_launch = (1024 * 2 * NKP * NKP + 1536 * NKP * NKP) / 2
-    attn_avg_ms = attn_ms / max(attn_n, 1)
-    achieved = attn_flops_per_launch / (attn_avg_ms * 1e-3) / 1e12 if attn_n else None
+    # dominant kernel: attention.  Work counted on the device (live sizes after pruning / early exit):
+    #   self_w = sum nq*nk over self problems, cross_w = same over cross problems (both directions).
+    # SURVEY 8d algorithmic FLOPs: self 1024 (M^2 + N^2) = 1024 self_w ; cross 1536 M N = 768 cross_w (similarity once);
+    # executed: 1024 (self_w + cross_w) (the kernel forms Q K^T for both directions); the fp32 path issues 6 bf16
+    # MMAs per product (three operand planes), the bf16 path 1.
+    attn_s = kp_["attn_ms"] * 1e-3
+    alg = 1024.0 * kp_["self_w"] + 768.0 * kp_["cross_w"]
+    executed = 1024.0 * (kp_["self_w"] + kp_["cross_w"])
+    issue_mult = {"fp32": 6, "bf16": 1, "fp32_simt": 0}[args.precision]
+    achieved = alg / attn_s / 1e12 if attn_s > 0 else None
+    ncu = {}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json"))).get(args.precision, {})
+    except Exception:
+        pass
     out = {
         "metric": METRIC, "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "dtype": "f32" if args.precision != "bf16" else "bf16", "data": "synthetic",
         "config": {"workload": "kitti_stream_1241x376_2048kp (BASELINE config 2)", "pairs_per_step": P,
                    "unit_of_work": "1 ALIKED-n16 extract + 1 LightGlue match (9 layers, adaptive depth/width on)",
                    "l2": "flushed between steps (256 MiB write)", "weights": f"{src_a} / {src_l}",
                    "pipeline": "2 CUDA streams: ALIKED extract(t+1) overlaps LightGlue match(t-1,t)",
-                   "mean_matches_per_pair": mean_matches, "precision": args.precision},
+                   "mean_matches_per_pair": mean_matches, "precision": args.precision,
+                   "arithmetic": {"fp32": "fp32-faithful on tcgen05: operands as three bf16 planes, six cross products, fp32 accumulate",
+                                  "bf16": "bf16 operands on tcgen05, fp32 accumulate", "fp32_simt": "fp32 FMA on CUDA cores"}[args.precision]},
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "h2d_bytes_per_step": int(h2d / e2e_pairs * P),
                 "d2h_bytes_per_step": int(d2h / e2e_pairs * P), "pairs_timed": e2e_pairs,
                 "api": "features_utils.feature_extractor + feature_matcher (host numpy in, cv2 lists out)",
                 "matches_last_pair": e2e_matches},
-        "roofline": {"bound": "tensor", "kernel": {"fp32": "k_attn_tc3 (fp32 on bf16x3 planes, tcgen05)", "bf16": "k_attn_tc (bf16, tcgen05)", "fp32_simt": "k_attn_fp32 (CUDA cores)"}[args.precision],
+        "roofline": {"bound": "tensor",
+                     "kernel": {"fp32": "k_attn_tc3 (fp32 on bf16x3 planes, tcgen05)", "bf16": "k_attn_tc (bf16, tcgen05)",
+                                "fp32_simt": "k_attn_fp32 (CUDA cores)"}[args.precision],
                      "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                     "frac": (achieved / tensor_peak) if achieved else None, "traffic": None,
-                     "peak_source": peak_src, "launches_timed": int(attn_n), "avg_launch_ms": attn_avg_ms,
-                     "share_of_step": attn_ms / total_ms if total_ms else None,
-                     "gemm_share_of_step": gemm_ms / total_ms if total_ms else None,
+                     "frac": (achieved / tensor_peak) if achieved else None,
+                     "traffic": ncu.get("dram_bytes_per_launch"),
+                     "peak_source": peak_src, "launches_timed": int(kp_["attn_n"]),
+                     "avg_launch_ms": kp_["attn_ms"] / max(kp_["attn_n"], 1),
+                     "algorithmic_flop_per_launch": alg / max(kp_["attn_n"], 1),
+                     "executed_tflops": executed / attn_s / 1e12 if attn_s > 0 else None,
+                     "mma_issued_tflops": issue_mult * executed / attn_s / 1e12 if attn_s > 0 else None,
+                     "mma_issued_frac_of_peak": issue_mult * executed / attn_s / 1e12 / tensor_peak if attn_s > 0 else None,
+                     "share_of_match": kp_["attn_ms"] / kp_["pairs"] / kp_["match_ms"],
+                     "gemm_share_of_match": kp_["gemm_ms"] / kp_["pairs"] / kp_["match_ms"],
+                     "match_ms_single_stream": kp_["match_ms"],
+                     "timing": "CUDA events around every attention launch on the launching stream, separate pass of "
+                               f"{kp_['pairs']} matches after the timed region; work counted on the device (live sizes)",
                      "whole_pair_tflops": (lg_flops(NKP, NKP) + aliked_flops()) * K * P / (total_ms * 1e-3) / 1e12},
         "clocks": clocks,
         "wall_s_timed_region": wall,
     }
+    if other:
+        out["other_precision"] = other
     if world == 1 and not args.no_cpu_baseline:
         v, ms_cpu, meta = cpu_reference_arm(steps=3, warmup=1)
         meta.update(value=v, unit="frame-pairs/s")
@@ -326,6 +388,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("B2S_PRECISION", "fp32"), choices=["fp32", "bf16", "fp32_simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the bf16 side measurement of the fp32 run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

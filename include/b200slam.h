@@ -158,6 +158,10 @@ int b2s_lg_debug_get(b2s_lg* h, const char* name, float* out, size_t cap, size_t
  * launches, and clears the records. */
 int b2s_lg_profile(b2s_lg* h, int on);
 int b2s_lg_profile_read(b2s_lg* h, int cls, double* ms, long long* n_launches);
+/* Executed attention work since b2s_lg_profile(h, 1): the sum of nq*nk over every live self-attention problem
+ * and over every live cross-attention problem (device-side counters: pruning / early exit are accounted for).
+ * Synchronises the device. */
+int b2s_lg_profile_work(b2s_lg* h, double* self_pairs, double* cross_pairs);
 
 /* Unit-test entry points for the tcgen05 kernels (host buffers).  The plain names round the
  * operands to bf16; the "3" variants carry them as three bf16 planes (fp32-faithful):

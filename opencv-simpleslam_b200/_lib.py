@@ -56,6 +56,7 @@ SIGNATURES = {
     "b2s_lg_debug_get": (C.c_int, [vp, C.c_char_p, f32p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b2s_lg_profile": (C.c_int, [vp, C.c_int]),
     "b2s_lg_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "b2s_lg_profile_work": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "b2s_test_gemm_tc": (C.c_int, [f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, f32p]),
     "b2s_test_attn_tc": (C.c_int, [f32p, f32p, f32p, C.c_int, C.c_int, f32p]),
     "b2s_bench_attn_tc": (C.c_int, [C.c_int, C.c_int, C.c_int, f32p]),

@@ -27,6 +27,7 @@ struct AttnTcParams {
   float scale_log2e;               // softmax scale * log2(e)
   __nv_bfloat16* out; int ldo;     // ctx [2*cap, 256] bf16, rows aligned with q_row
   const int* ctrl; int cross;      // LightGlue device state (nullable): nq / nk = ctrl[2 + z] (cross: nk = ctrl[3 - z])
+  unsigned long long* stats;       // nullable: stats[cross] += nq * nk of every live problem (executed work, for the roofline)
 };
 
 constexpr int ATC_BQ = 128, ATC_BK = 128, ATC_D = 64, ATC_KS = 3;
@@ -130,6 +131,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) k_attn_tc(const __grid_constan
   }
   const bool live = q0 < pr.nq;                          // uniform per CTA
   const int nt = live ? (pr.nk + ATC_BK - 1) / ATC_BK : 0;
+  if (p.stats && live && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+    atomicAdd(&p.stats[p.cross ? 1 : 0], (unsigned long long)pr.nq * (unsigned long long)pr.nk);
   const uint32_t tS = tmem_base, tO = tmem_base + 256;    // S[g] = tS + 128 g ; O[g] = tO + 64 g
 
   if (warp >= 8) {

@@ -37,6 +37,7 @@ struct Attn3Params {
   float scale_log2e;
   __nv_bfloat16* out; int ldo; size_t out_plane;   // ctx planes [3][2*cap, 256] bf16
   const int* ctrl; int cross;
+  unsigned long long* stats;       // nullable: stats[cross] += nq * nk of every live problem
 };
 
 // P chunk c (32 keys) of one row -> three planes in tensor memory (16 columns each); returns the partial row sum
@@ -111,6 +112,8 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
   }
   const bool live = q0 < pr.nq;                          // uniform per CTA
   const int nt = live ? (pr.nk + A3_BK - 1) / A3_BK : 0;
+  if (p.stats && live && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+    atomicAdd(&p.stats[p.cross ? 1 : 0], (unsigned long long)pr.nq * (unsigned long long)pr.nk);
   const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 256;   // S[g] + 64 g, O[g] + 64 g, P[g] + 96 g
 
   if (warp >= 8) {

@@ -45,6 +45,7 @@ struct b2s_lg {
   int dbg_m[16], dbg_n[16], dbg_nlayers = 0, dbg_simm = 0, dbg_simn = 0;
   long long launches = 0;
   KernelProf prof;
+  unsigned long long* stats = nullptr;   // device: [0] sum nq*nk over self-attention problems, [1] over cross-attention problems
   LgTensorCore* tc = nullptr;   // bf16 tcgen05 path (precision == B2S_BF16)
 };
 
@@ -195,11 +196,13 @@ extern "C" int b2s_lightglue_create(const b2s_lg_cfg* cfg, const void* weights, 
     if ((rc = h->warena.upload(&h->wfinal_tab, wf)) || (rc = h->warena.upload(&h->bfinal_tab, bf)) ||
         (rc = h->warena.upload(&h->wmatch_tab, wm)) || (rc = h->warena.upload(&h->bmatch_tab, bm))) return fail(rc);
   }
+  if ((rc = h->warena.alloc(&h->stats, (size_t)4))) return fail(rc);
+  cudaMemset(h->stats, 0, 4 * sizeof(unsigned long long));
   if (cudaMallocHost((void**)&h->h_ctrl, LGC_INTS * sizeof(int)) != cudaSuccess) { set_error("cudaMallocHost failed"); return fail(B2S_ENOMEM); }
   cudaFuncSetAttribute(k_attn_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
   if (cfg->precision != B2S_FP32_SIMT) {   // tensor-core paths: bf16 operands, or fp32 carried as three bf16 planes
     if ((rc = lgtc_create(&h->tc, h->L.size(), cfg->precision == B2S_BF16 ? 1 : 3))) return fail(rc);
-    lgtc_set_prof(h->tc, &h->prof);
+    lgtc_set_prof(h->tc, &h->prof, h->stats);
     for (size_t i = 0; i < h->L.size(); ++i) {
       const LgLayer& l = h->L[i];
       LgTcLayerSrc s = {l.wqkv, l.bqkv, l.wo, l.bo, l.w1, l.b1, l.lng, l.lnb, l.w2, l.b2,
@@ -229,6 +232,18 @@ extern "C" int b2s_lg_profile(b2s_lg* h, int on) {
   if (!h) return B2S_EINVAL;
   h->prof.on = on != 0;
   for (int c = 0; c < PROF_NCLASS; ++c) h->prof.used[c] = 0;
+  B2S_CUDA(cudaSetDevice(h->device));
+  B2S_CUDA(cudaMemset(h->stats, 0, 4 * sizeof(unsigned long long)));
+  return 0;
+}
+
+extern "C" int b2s_lg_profile_work(b2s_lg* h, double* self_pairs, double* cross_pairs) {
+  if (!h || !self_pairs || !cross_pairs) return B2S_EINVAL;
+  B2S_CUDA(cudaSetDevice(h->device));
+  unsigned long long v[2] = {0, 0};
+  B2S_CUDA(cudaDeviceSynchronize());
+  B2S_CUDA(cudaMemcpy(v, h->stats, sizeof(v), cudaMemcpyDeviceToHost));   // synchronises with the default stream
+  *self_pairs = (double)v[0]; *cross_pairs = (double)v[1];
   return 0;
 }
 
@@ -260,7 +275,7 @@ static int lg_linear(b2s_lg* h, cudaStream_t st, const float* A1, int lda1, int 
 
 static int lg_attention(b2s_lg* h, cudaStream_t st, AttnParams ap, int cross, int maxq) {
   if (maxq <= 0) return 0;
-  ap.ctrl = h->ctrl; ap.cross = cross;
+  ap.ctrl = h->ctrl; ap.cross = cross; ap.stats = h->prof.on ? h->stats : nullptr;
   dim3 grid(cdiv(maxq, ATT_B), 4, 2);
   h->prof.mark(PROF_ATTN, st);
   launch_k(k_attn_fp32, grid, 256, ATT_SMEM, st, ap);

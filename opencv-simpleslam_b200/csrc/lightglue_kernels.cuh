@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) k_lg_posenc(PosencParams p) {
 // Thread (ty,tx) of a 16x16 grid owns S[ty*4..+4][tx*4..+4] and O[ty*4..+4][tx*4..+4].
 // ---------------------------------------------------------------------------------------
 struct AttnProb { const float* Q; const float* K; const float* V; float* O; int nq, nk; };
-struct AttnParams { AttnProb prob[2]; int ldq, ldk, ldv, ldo; float scale; const int* ctrl; int cross; };
+struct AttnParams { AttnProb prob[2]; int ldq, ldk, ldv, ldo; float scale; const int* ctrl; int cross; unsigned long long* stats; };
 
 constexpr int ATT_B = 64, ATT_D = 64, ATT_LD = 68;
 constexpr int ATT_SMEM = 4 * ATT_B * ATT_LD * (int)sizeof(float);
@@ -111,6 +111,8 @@ __global__ void __launch_bounds__(256) k_attn_fp32(AttnParams p) {
   }
   const int q0 = blockIdx.x * ATT_B;
   if (q0 >= pr.nq) return;
+  if (p.stats && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+    atomicAdd(&p.stats[p.cross ? 1 : 0], (unsigned long long)pr.nq * (unsigned long long)pr.nk);
   const int hoff = blockIdx.y * ATT_D;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
 

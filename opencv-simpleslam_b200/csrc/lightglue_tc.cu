@@ -179,6 +179,7 @@ struct LgTensorCore {
   float* bfinal = nullptr;         // [L*256]
   const int* ctrl = nullptr;       // LightGlue device state (sizes / early exit), set per match
   KernelProf* prof = nullptr;
+  unsigned long long* stats = nullptr;   // executed attention work counters (owned by the matcher handle)
 };
 
 static int make_linear(LgTensorCore* tc, const float* w_dev, const float* bias, int N, int K, TcLinear* out) {
@@ -283,7 +284,7 @@ int lgtc_alloc_ws(LgTensorCore* tc, int cap) {
 }
 
 void lgtc_destroy(LgTensorCore* tc) { delete tc; }
-void lgtc_set_prof(LgTensorCore* tc, KernelProf* prof) { tc->prof = prof; }
+void lgtc_set_prof(LgTensorCore* tc, KernelProf* prof, unsigned long long* stats) { tc->prof = prof; tc->stats = stats; }
 
 static int tc_gemm(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& a1, const CUtensorMap& a2, int K1, const TcLinear& w,
                    TcGemmParams p, int m, int n, long long* launches) {
@@ -321,12 +322,14 @@ static int tc_attention(LgTensorCore* tc, cudaStream_t st, int ld, const AttnTcP
     AttnTcParams ap = {};
     ap.prob[0] = prob[0]; ap.prob[1] = prob[1]; ap.qcol = qcol; ap.kcol = kcol; ap.vcol = vcol; ap.cross = cross;
     ap.scale_log2e = scale_log2e; ap.out = tc->ctxb; ap.ldo = 256; ap.ctrl = tc->ctrl;
+    ap.stats = (tc->prof && tc->prof->on) ? tc->stats : nullptr;
     launch_k(k_attn_tc, grid, ATC_THREADS, ATC_SMEM, st, ld == 768 ? tc->m_qkv768 : tc->m_qkv512, ap);
   } else {
     Attn3Params ap = {};
     ap.prob[0] = prob[0]; ap.prob[1] = prob[1]; ap.qcol = qcol; ap.kcol = kcol; ap.vcol = vcol; ap.cross = cross;
     ap.plane_rows = 2 * tc->cap;
     ap.scale_log2e = scale_log2e; ap.out = tc->ctxb; ap.ldo = 256; ap.out_plane = (size_t)2 * tc->cap * 256; ap.ctrl = tc->ctrl;
+    ap.stats = (tc->prof && tc->prof->on) ? tc->stats : nullptr;
     launch_k(k_attn_tc3, grid, A3_THREADS, A3_SMEM, st, ld == 768 ? tc->m_qkv768 : tc->m_qkv512,
              ld == 768 ? tc->m_kv768 : tc->m_kv512, ap);
   }

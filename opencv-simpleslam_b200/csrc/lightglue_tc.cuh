@@ -27,6 +27,6 @@ int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int layer, float* x, const flo
 __nv_bfloat16* lgtc_xb(LgTensorCore* tc);   // bf16 plane copy of the residual stream (the pruning gather refreshes it)
 int lgtc_planes(LgTensorCore* tc);
 void lgtc_destroy(LgTensorCore* tc);
-void lgtc_set_prof(LgTensorCore* tc, KernelProf* prof);
+void lgtc_set_prof(LgTensorCore* tc, KernelProf* prof, unsigned long long* stats);
 
 }  // namespace b2s

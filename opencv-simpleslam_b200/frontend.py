@@ -299,6 +299,12 @@ class LightGlue(_Module):
         check(lib.b2s_lg_profile_read(self._handle, cls, C.byref(ms), C.byref(n)), "b2s_lg_profile_read")
         return ms.value, n.value
 
+    def profile_work(self):
+        """(sum nq*nk over executed self-attention problems, same for cross-attention) since profile(True)."""
+        a, b = C.c_double(0), C.c_double(0)
+        check(lib.b2s_lg_profile_work(self._handle, C.byref(a), C.byref(b)), "b2s_lg_profile_work")
+        return a.value, b.value
+
     def set_debug(self, on=True):
         check(lib.b2s_lg_set_debug(self._handle, 1 if on else 0), "b2s_lg_set_debug")
 
