@@ -11,15 +11,16 @@
 
 using namespace b2s;
 
+struct TcWeight {     // fp32 weight [N][K] as three bf16 planes [N][3K] + tensor map (box {64, 64})
+  __nv_bfloat16* w = nullptr; CUtensorMap map; int N = 0, K = 0;
+};
+
 struct DcnBlockW {   // ResBlock with deformable convs (block3 / block4)
   int cin, cout;
   float *off1_w, *off1_b, *reg1_w, *reg1_b;   // conv1: offset conv [18][9*cin], regular [cout][9*cin] (BN1 folded)
   float *off2_w, *off2_b, *reg2_w, *reg2_b;   // conv2: [18][9*cout], [cout][9*cout] (BN2 folded)
   float *ds_w, *ds_b;                         // downsample [cout][cin] + bias
-};
-
-struct TcWeight {     // fp32 weight [N][K] as three bf16 planes [N][3K] + tensor map (box {64, 64})
-  __nv_bfloat16* w = nullptr; CUtensorMap map; int N = 0, K = 0;
+  TcWeight reg1_tc, reg2_tc;                  // regular convs as tensor-core weights (block3)
 };
 
 struct b2s_aliked {
@@ -37,6 +38,8 @@ struct b2s_aliked {
   __nv_bfloat16 *b1c2_pl, *b2c1_pl, *b2c2_pl;           // conv weights as bf16x3 chunk planes (conv_tc.cuh)
   __nv_bfloat16 *t1a_pl, *x1p_pl, *t2a_pl;              // activations as chunk planes: block1.conv1 out, pool2(x1), block2.conv1 out
   CUtensorMap m_t1a, m_x1p, m_t2a; int mapHp = 0, mapWp = 0;
+  __nv_bfloat16* col3_pl;                               // block3 deformable im2col as bf16x3 planes [3][P3][<= 576]
+  CUtensorMap m_col3a, m_col3b;                         // views with row length 9*32 / 9*64
   // workspace
   int wsHp = 0, wsWp = 0;
   float *img_pad, *resized, *t1a, *x1, *r2, *t2a, *x2, *x3in, *col3, *off3, *t3a, *r3, *x3, *x4in, *col4, *off4, *t4a, *r4, *x4;
@@ -113,6 +116,26 @@ int upload_plain(b2s_aliked* h, const WeightBlob& wb, const std::string& name, s
   return h->warena.upload(w, o);
 }
 
+// fp32 device weight [N][K] -> bf16x3 planes [N][3*Kpad] (K zero-padded to a multiple of 64) + tensor map
+int make_tc_weight(b2s_aliked* h, const float* w_dev, int N, int K, TcWeight* out) {
+  const int Kpad = cdiv(K, 64) * 64;
+  out->N = N; out->K = Kpad;
+  const float* src = w_dev;
+  if (Kpad != K) {
+    float* padded;
+    B2S_TRY(h->warena.alloc(&padded, (size_t)N * Kpad));
+    B2S_CUDA(cudaMemset(padded, 0, (size_t)N * Kpad * sizeof(float)));
+    B2S_CUDA(cudaMemcpy2D(padded, (size_t)Kpad * sizeof(float), w_dev, (size_t)K * sizeof(float), (size_t)K * sizeof(float), N,
+                          cudaMemcpyDeviceToDevice));
+    src = padded;
+  }
+  const size_t n = (size_t)N * Kpad;
+  B2S_TRY(h->warena.alloc(&out->w, 3 * n));
+  k_weight_planes<<<(unsigned)((n + 255) / 256), 256>>>(src, out->w, N, Kpad, 3);
+  B2S_LAUNCH_CHECK();
+  return make_tmap_bf16_2d(&out->map, out->w, (uint64_t)3 * Kpad, N, (uint64_t)3 * Kpad * 2, 64, 64);
+}
+
 int upload_dcn_block(b2s_aliked* h, const WeightBlob& wb, const std::string& blk, int cin, int cout, DcnBlockW* d) {
   d->cin = cin; d->cout = cout;
   BnFold bn1, bn2;
@@ -128,6 +151,8 @@ int upload_dcn_block(b2s_aliked* h, const WeightBlob& wb, const std::string& blk
   B2S_TRY(h->warena.upload(&d->reg2_b, bn2.shift));
   B2S_TRY(upload_plain(h, wb, blk + ".downsample.weight", (size_t)cout * cin, &d->ds_w));
   B2S_TRY(upload_plain(h, wb, blk + ".downsample.bias", cout, &d->ds_b));
+  B2S_TRY(make_tc_weight(h, d->reg1_w, cout, 9 * cin, &d->reg1_tc));
+  B2S_TRY(make_tc_weight(h, d->reg2_w, cout, 9 * cout, &d->reg2_tc));
   return 0;
 }
 
@@ -192,25 +217,19 @@ int load_weights(b2s_aliked* h, const WeightBlob& wb) {
     for (int c = 0; c < 128; ++c)
       for (int d = 0; d < 128; ++d) at[(size_t)d * M * 128 + (size_t)p * 128 + c] = ag->data[((size_t)p * 128 + c) * 128 + d];
   B2S_TRY(h->warena.upload(&h->aggT, at));
-  auto mk = [&](const float* w_dev, int N, int K, TcWeight* out) -> int {
-    out->N = N; out->K = K;
-    const size_t n = (size_t)N * K;
-    B2S_TRY(h->warena.alloc(&out->w, 3 * n));
-    k_weight_planes<<<(unsigned)((n + 255) / 256), 256>>>(w_dev, out->w, N, K, 3);
-    B2S_LAUNCH_CHECK();
-    return make_tmap_bf16_2d(&out->map, out->w, (uint64_t)3 * K, N, (uint64_t)3 * K * 2, 64, 64);
-  };
-  B2S_TRY(mk(h->so0_w, 2 * M, 1152, &h->tc_so0));
-  B2S_TRY(mk(h->sf_w, 128, 128, &h->tc_sf));
-  B2S_TRY(mk(h->aggT, 128, M * 128, &h->tc_agg));
+  B2S_TRY(make_tc_weight(h, h->so0_w, 2 * M, 1152, &h->tc_so0));
+  B2S_TRY(make_tc_weight(h, h->sf_w, 128, 128, &h->tc_sf));
+  B2S_TRY(make_tc_weight(h, h->aggT, 128, M * 128, &h->tc_agg));
   B2S_CUDA(cudaDeviceSynchronize());
   return 0;
 }
 
 // C = act(A W^T + bias) on the tensor cores, fp32 operands as bf16x3 planes; rows = *n_dev * mult
 int tc_gemm(b2s_aliked* h, cudaStream_t st, const CUtensorMap& a, int plane_rows, const TcWeight& w, const float* bias, int act,
-            int rows_max, const int32_t* n_dev, int mult, float* out_f32, int ldc, __nv_bfloat16* out_planes, size_t out_plane) {
+            int rows_max, const int32_t* n_dev, int mult, float* out_f32, int ldc, __nv_bfloat16* out_planes, size_t out_plane,
+            const float* residual = nullptr) {
   TcGemmParams p = {};
+  p.residual = residual; p.ld_res = ldc;
   p.K = w.K; p.K1 = w.K; p.N = w.N; p.bias = bias; p.act = act;
   p.seg_base[0] = 0; p.seg_rows[0] = rows_max; p.seg_base[1] = 0; p.seg_rows[1] = 0; p.tiles0 = cdiv(rows_max, 128);
   p.plane_rows = plane_rows; p.m_dev = n_dev; p.m_mult = mult;
@@ -231,6 +250,8 @@ int alloc_ws(b2s_aliked* h, int Hp, int Wp) {
   B2S_TRY(a.alloc(&h->img_pad, 3 * P)); B2S_TRY(a.alloc(&h->resized, 3 * P));
   B2S_TRY(a.alloc(&h->t1a, (size_t)1)); B2S_TRY(a.alloc(&h->x1, 16 * P));
   B2S_TRY(a.alloc(&h->t1a_pl, 3 * 16 * P)); B2S_TRY(a.alloc(&h->x1p_pl, 3 * 16 * P2)); B2S_TRY(a.alloc(&h->t2a_pl, 3 * 32 * P2));
+  B2S_TRY(a.alloc(&h->col3_pl, 3 * 576 * P3));
+  B2S_CUDA(cudaMemset(h->col3_pl, 0, 3 * 576 * P3 * 2));
   h->mapHp = h->mapWp = 0;
   B2S_TRY(a.alloc(&h->r2, 32 * P2)); B2S_TRY(a.alloc(&h->t2a, (size_t)1)); B2S_TRY(a.alloc(&h->x2, 32 * P2));
   B2S_TRY(a.alloc(&h->x3in, 32 * P3)); B2S_TRY(a.alloc(&h->col3, 576 * P3)); B2S_TRY(a.alloc(&h->off3, 18 * P3));
@@ -260,34 +281,39 @@ int alloc_ws(b2s_aliked* h, int Hp, int Wp) {
   return 0;
 }
 
-// one DCN ResBlock on HWC maps; in [P][cin] -> out [P][cout]
-int run_dcn_block(b2s_aliked* h, cudaStream_t st, const DcnBlockW& w, const float* in, int Hh, int Ww, float* col, float* off,
-                  float* ta, float* res, float* out) {
+// one DCN ResBlock on HWC maps; in [P][cin] -> out [P][cout].  Per deformable conv: one fused kernel (offset conv +
+// deformable im2col) and one GEMM - on the tensor cores (bf16x3) for block3, on the CUDA cores with split-K for the
+// 320-pixel block4 (3 row tiles would leave the tensor-core kernel latency-bound over K = 1152).
+template <int CIN, int COUT>
+int run_dcn_block(b2s_aliked* h, cudaStream_t st, const DcnBlockW& w, const float* in, int Hh, int Ww, float* col, float* ta,
+                  float* res, float* out, bool use_tc) {
   const int P = Hh * Ww;
   const float clampv = (float)std::max(Hh, Ww) / 4.0f;
-  auto gemm = [&](const float* A, int K, const float* W, int N, const float* bias, float* C, const float* residual, int act, float clamp) {
+  auto gemm = [&](const float* A, int K, const float* W, int N, const float* bias, float* C, const float* residual, int act) {
     GemmParams g;
     g.A1 = A; g.lda1 = K; g.K1 = K; g.W = W; g.ldw = K; g.K = K; g.M = P; g.N = N; g.C = C; g.ldc = N;
-    g.bias = bias; g.residual = residual; g.ldr = N; g.act = act; g.clamp = clamp;
+    g.bias = bias; g.residual = residual; g.ldr = N; g.act = act;
     return agemm(h, g, st);
   };
-  const int jobs = P * 9;
-  // conv1: offsets (regular im2col) -> deformable im2col -> GEMM (+BN1) + SELU
-  launch_k(k_dcn_im2col, cdiv(jobs, 8), 256, 0, st, in, w.cin, Hh, Ww, nullptr, col);
+  const int ppw = P >= 2048 ? 4 : 1;
+  DcnColParams cp = {};
+  cp.H = Hh; cp.W = Ww; cp.clampv = clampv; cp.ppw = ppw;
+  if (use_tc) { cp.col_pl = h->col3_pl; cp.plane = (size_t)P * 9 * CIN; } else cp.col_f32 = col;
+  // conv1 (+BN1) + SELU
+  cp.in = in; cp.w_off = w.off1_w; cp.b_off = w.off1_b;
+  launch_k(k_dcn_offcol<CIN>, cdiv(P, 8 * ppw), 256, 18 * 9 * CIN * sizeof(float), st, cp);
   ++h->launches; B2S_LAUNCH_CHECK();
-  B2S_TRY(gemm(col, 9 * w.cin, w.off1_w, 18, w.off1_b, off, nullptr, ACT_NONE, clampv));
-  launch_k(k_dcn_im2col, cdiv(jobs, 8), 256, 0, st, in, w.cin, Hh, Ww, off, col);
-  ++h->launches; B2S_LAUNCH_CHECK();
-  B2S_TRY(gemm(col, 9 * w.cin, w.reg1_w, w.cout, w.reg1_b, ta, nullptr, ACT_SELU, 0.f));
+  if (use_tc) B2S_TRY(tc_gemm(h, st, CIN == 32 ? h->m_col3a : h->m_col3b, P, w.reg1_tc, w.reg1_b, 1, P, nullptr, 0, ta, COUT, nullptr, 0));
+  else B2S_TRY(gemm(col, 9 * CIN, w.reg1_w, COUT, w.reg1_b, ta, nullptr, ACT_SELU));
   // downsample(x) -> residual
-  B2S_TRY(gemm(in, w.cin, w.ds_w, w.cout, w.ds_b, res, nullptr, ACT_NONE, 0.f));
-  // conv2 on ta
-  launch_k(k_dcn_im2col, cdiv(jobs, 8), 256, 0, st, ta, w.cout, Hh, Ww, nullptr, col);
+  B2S_TRY(gemm(in, CIN, w.ds_w, COUT, w.ds_b, res, nullptr, ACT_NONE));
+  // conv2 (+BN2) + residual + SELU
+  cp.in = ta; cp.w_off = w.off2_w; cp.b_off = w.off2_b;
+  if (use_tc) cp.plane = (size_t)P * 9 * COUT;
+  launch_k(k_dcn_offcol<COUT>, cdiv(P, 8 * ppw), 256, 18 * 9 * COUT * sizeof(float), st, cp);
   ++h->launches; B2S_LAUNCH_CHECK();
-  B2S_TRY(gemm(col, 9 * w.cout, w.off2_w, 18, w.off2_b, off, nullptr, ACT_NONE, clampv));
-  launch_k(k_dcn_im2col, cdiv(jobs, 8), 256, 0, st, ta, w.cout, Hh, Ww, off, col);
-  ++h->launches; B2S_LAUNCH_CHECK();
-  return gemm(col, 9 * w.cout, w.reg2_w, w.cout, w.reg2_b, out, res, ACT_SELU, 0.f);
+  if (use_tc) return tc_gemm(h, st, COUT == 32 ? h->m_col3a : h->m_col3b, P, w.reg2_tc, w.reg2_b, 1, P, nullptr, 0, out, COUT, nullptr, 0, res);
+  return gemm(col, 9 * COUT, w.reg2_w, COUT, w.reg2_b, out, res, ACT_SELU);
 }
 
 }  // namespace
@@ -311,6 +337,8 @@ extern "C" int b2s_aliked_create(const b2s_aliked_cfg* cfg, const void* weights,
   h->M = cfg->model == 1 ? 32 : 16;
   h->n_limit = cfg->max_kp > 0 ? cfg->max_kp : 20000;
   cudaFuncSetAttribute(k_gemm_tc<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGemmCfg<64, 3>::SMEM);
+  cudaFuncSetAttribute(k_dcn_offcol<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 18 * 9 * 64 * (int)sizeof(float));
+  cudaFuncSetAttribute(k_dcn_offcol<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 18 * 9 * 128 * (int)sizeof(float));
   cudaFuncSetAttribute(k_conv3x3_tc<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<16, 16>::SMEM);
   cudaFuncSetAttribute(k_conv3x3_tc<16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<16, 32>::SMEM);
   cudaFuncSetAttribute(k_conv3x3_tc<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<32, 32>::SMEM);
@@ -395,6 +423,9 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
     B2S_TRY(mk(&h->m_t1a, h->t1a_pl, Hp, Wp, 2));
     B2S_TRY(mk(&h->m_x1p, h->x1p_pl, H2, W2, 2));
     B2S_TRY(mk(&h->m_t2a, h->t2a_pl, H2, W2, 4));
+    const uint64_t P3 = (uint64_t)(H2 / 4) * (W2 / 4);
+    B2S_TRY(make_tmap_bf16_2d(&h->m_col3a, h->col3_pl, 288, 3 * P3, 288 * 2, 64, 128));
+    B2S_TRY(make_tmap_bf16_2d(&h->m_col3b, h->col3_pl, 576, 3 * P3, 576 * 2, 64, 128));
     h->mapHp = Hp; h->mapWp = Wp;
   }
   {
@@ -416,10 +447,10 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
   const int H3 = H2 / 4, W3 = W2 / 4, H4 = H3 / 4, W4 = W3 / 4;
   launch_k(k_pool4_chw_to_hwc, cdiv(H3 * W3, 8), 256, 0, st, h->x2, 32, H3, W3, h->x3in);
   ++h->launches; B2S_LAUNCH_CHECK();
-  B2S_TRY(run_dcn_block(h, st, h->b3, h->x3in, H3, W3, h->col3, h->off3, h->t3a, h->r3, h->x3));
+  B2S_TRY((run_dcn_block<32, 64>(h, st, h->b3, h->x3in, H3, W3, h->col3, h->t3a, h->r3, h->x3, true)));
   launch_k(k_pool4_hwc, cdiv(H4 * W4, 8), 256, 0, st, h->x3, 64, H4, W4, h->x4in);
   ++h->launches; B2S_LAUNCH_CHECK();
-  B2S_TRY(run_dcn_block(h, st, h->b4, h->x4in, H4, W4, h->col4, h->off4, h->t4a, h->r4, h->x4));
+  B2S_TRY((run_dcn_block<64, 128>(h, st, h->b4, h->x4in, H4, W4, h->col4, h->t4a, h->r4, h->x4, false)));
   // ---- aggregation convs at native resolution ----
   launch_k(k_conv1x1_chw_to_hwc32<32>, cdiv(H2 * W2, 64), 256, 0, st, h->x2, (size_t)H2 * W2, h->agg_w[1], h->x2a);
   ++h->launches; B2S_LAUNCH_CHECK();

@@ -323,6 +323,92 @@ __global__ void __launch_bounds__(256) k_dcn_im2col(const float* __restrict__ in
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// K3/K4 fused: offset conv (regular 3x3, C -> 18, clamped) + deformable im2col in ONE kernel.
+// warp per pixel (PPW pixels per warp, 8 warps per CTA); the 18 x 9C offset weights sit in shared memory.
+// Output row col[pix][tap*C + c] either fp32 (CUDA-core GEMM) or three bf16 planes (tensor-core GEMM).
+// ---------------------------------------------------------------------------------------
+struct DcnColParams {
+  const float* in; int H, W;              // HWC [H*W][C]
+  const float* w_off; const float* b_off; // [18][9C], [18]
+  float clampv;
+  float* col_f32;                         // [P][9C] (nullable)
+  __nv_bfloat16* col_pl; size_t plane;    // [3][P][9C] planes (nullable), elements between planes
+  int ppw;                                // pixels per warp
+};
+
+template <int C>
+__global__ void __launch_bounds__(256) k_dcn_offcol(DcnColParams p) {
+  extern __shared__ __align__(16) float s_woff[];          // [18][9C]
+  for (int e = threadIdx.x; e < 18 * 9 * C; e += 256) s_woff[e] = p.w_off[e];   // constant weights: before the wait
+  pdl_wait();
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int H = p.H, W = p.W, P = H * W;
+  constexpr int CC = C / 32;
+  for (int q = 0; q < p.ppw; ++q) {
+    const int pix = (blockIdx.x * 8 + warp) * p.ppw + q;
+    if (pix >= P) return;                                  // warp-uniform
+    const int py = pix / W, px = pix % W;
+    // ---- offsets: 18 outputs, reduction over (tap, channel) split across lanes ----
+    float acc[18];
+#pragma unroll
+    for (int o = 0; o < 18; ++o) acc[o] = 0.f;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = py - 1 + tap / 3, xx = px - 1 + tap % 3;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;   // zero padding
+      const float* src = p.in + ((size_t)yy * W + xx) * C;
+#pragma unroll
+      for (int cc = 0; cc < CC; ++cc) {
+        const float v = src[cc * 32 + lane];
+        const float* wr = s_woff + tap * C + cc * 32 + lane;
+#pragma unroll
+        for (int o = 0; o < 18; ++o) acc[o] = fmaf(wr[o * 9 * C], v, acc[o]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 18; ++o) {
+      float v = warp_sum(acc[o]) + p.b_off[o];
+      acc[o] = fminf(fmaxf(v, -p.clampv), p.clampv);
+    }
+    // ---- deformable bilinear im2col (torchvision deform_conv2d semantics, zeros outside) ----
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float hy = (float)(py - 1 + tap / 3) + acc[2 * tap], wx = (float)(px - 1 + tap % 3) + acc[2 * tap + 1];
+      const size_t doff = (size_t)pix * 9 * C + (size_t)tap * C;
+      const bool outside = hy <= -1.f || hy >= (float)H || wx <= -1.f || wx >= (float)W;
+      const int hl = (int)floorf(hy), wl = (int)floorf(wx);
+      const int hh = hl + 1, wh = wl + 1;
+      const float lh = hy - (float)hl, lw = wx - (float)wl, uh = 1.f - lh, uw = 1.f - lw;
+      const bool v1 = hl >= 0 && wl >= 0, v2 = hl >= 0 && wh <= W - 1, v3 = hh <= H - 1 && wl >= 0, v4 = hh <= H - 1 && wh <= W - 1;
+      const float w1 = uh * uw, w2 = uh * lw, w3 = lh * uw, w4 = lh * lw;
+#pragma unroll
+      for (int cc = 0; cc < CC; ++cc) {
+        const int c = cc * 32 + lane;
+        float r = 0.f;
+        if (!outside) {
+          const float a = v1 ? p.in[((size_t)hl * W + wl) * C + c] : 0.f;
+          const float b = v2 ? p.in[((size_t)hl * W + wh) * C + c] : 0.f;
+          const float d = v3 ? p.in[((size_t)hh * W + wl) * C + c] : 0.f;
+          const float e = v4 ? p.in[((size_t)hh * W + wh) * C + c] : 0.f;
+          r = w1 * a + w2 * b + w3 * d + w4 * e;
+        }
+        if (p.col_f32) p.col_f32[doff + c] = r;
+        if (p.col_pl) {
+          __nv_bfloat16* d = p.col_pl + doff + c;
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl) {
+            const __nv_bfloat16 b = __float2bfloat16_rn(r);
+            d[pl * p.plane] = b;
+            r -= __bfloat162float(b);
+          }
+        }
+      }
+    }
+  }
+}
+
 // 1x1 conv (CIN -> 32, no bias) + SELU, planar CHW -> HWC.  block 256 = 64 pixels x 4 groups.
 template <int CIN>
 __global__ void __launch_bounds__(256) k_conv1x1_chw_to_hwc32(const float* __restrict__ in, size_t npix,

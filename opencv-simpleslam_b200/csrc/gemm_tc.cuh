@@ -36,7 +36,8 @@ struct TcGemmParams {
   int w_layer_rows, w_plane_rows, w_row0;
   float alpha;                      // epilogue: (acc + bias) * alpha (0 means 1)
   const int* m_dev; int m_mult;     // nullable: live rows of segment 0 = *m_dev * m_mult (ALIKED keypoint count)
-  int act;                          // 0 none, 1 SELU (after bias)
+  int act;                          // 0 none, 1 SELU (after bias / residual)
+  const float* residual; int ld_res; // nullable fp32 [rows, ld_res]: added after bias * alpha, before the activation
 };
 
 // fp32 weight [N,K] -> np bf16 planes side by side: out[n][p*K + k]
@@ -225,6 +226,14 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
       if (p.alpha != 0.f) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
+      }
+      if (p.residual) {
+        const float4* rs = reinterpret_cast<const float4*>(p.residual + grow * p.ld_res + gc);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 rv = rs[q];
+          f[4 * q] += rv.x; f[4 * q + 1] += rv.y; f[4 * q + 2] += rv.z; f[4 * q + 3] += rv.w;
+        }
       }
       if (p.act == 1) {
 #pragma unroll
