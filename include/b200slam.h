@@ -105,6 +105,21 @@ int b2s_aliked_extract_host(b2s_aliked* h, const void* img_host, int img_format,
                             int row_stride, float* kpts_host, float* desc_host,
                             float* scores_host, int32_t* n_out);
 
+/* same, and additionally applies the reference caller's re-normalisation `des0 /= (||des0||_2 + eps)`
+ * (features_utils.py:100) on the device when desc_renorm_eps > 0 (the reference uses 1e-8). */
+int b2s_aliked_extract_host_ex(b2s_aliked* h, const void* img_host, int img_format, int H, int W,
+                               int row_stride, float* kpts_host, float* desc_host,
+                               float* scores_host, int32_t* n_out, float desc_renorm_eps);
+
+/* Split form of b2s_aliked_extract_host_ex for callers that build per-keypoint host objects (cv2.KeyPoint lists,
+ * features_utils.py:61-63): _begin uploads the frame and enqueues the whole extraction; _keypoints blocks only until
+ * the detector has finished (the descriptor head is still running) and returns keypoints + count; _finish waits for
+ * the descriptors (n rows) and scores.  One extraction may be pending per handle. */
+int b2s_aliked_extract_host_begin(b2s_aliked* h, const void* img_host, int img_format, int H, int W,
+                                  int row_stride, float desc_renorm_eps);
+int b2s_aliked_extract_host_keypoints(b2s_aliked* h, float* kpts_host, int32_t* n_out);
+int b2s_aliked_extract_host_finish(b2s_aliked* h, float* desc_host, float* scores_host);
+
 int b2s_lightglue_create(const b2s_lg_cfg* cfg, const void* weights, size_t nbytes, int device,
                          b2s_lg** out);
 void b2s_lg_destroy(b2s_lg* h);

@@ -57,6 +57,9 @@ struct b2s_aliked {
   size_t himg_bytes = 0; void* himg = nullptr;
   float *hkp = nullptr, *hdesc = nullptr, *hscores = nullptr; int32_t* hn = nullptr;
   long long launches = 0;
+  float desc_renorm_eps = 0.f;                           // set per call by b2s_aliked_extract_host_ex
+  // split host API (begin / keypoints / finish): pinned staging for the early keypoint copy
+  float* pin_kp = nullptr; int32_t* pin_n = nullptr; cudaEvent_t ev_kp = nullptr; bool early_kp = false; bool pending = false;
 };
 
 extern "C" void b2s_aliked_default_cfg(b2s_aliked_cfg* c) {
@@ -351,6 +354,9 @@ extern "C" int b2s_aliked_create(const b2s_aliked_cfg* cfg, const void* weights,
 extern "C" void b2s_aliked_destroy(b2s_aliked* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->pin_kp) cudaFreeHost(h->pin_kp);
+  if (h->pin_n) cudaFreeHost(h->pin_n);
+  if (h->ev_kp) cudaEventDestroy(h->ev_kp);
   delete h;
 }
 
@@ -502,6 +508,11 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
     h->launches += 5; B2S_LAUNCH_CHECK();
     // upstream puts DKD's 2nd return value (dispersity) under "keypoint_scores" 
     if (scores) B2S_CUDA(cudaMemcpyAsync(scores, h->disp, (size_t)h->n_limit * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (h->early_kp) {   // split host API: keypoints are final here, the descriptor head still has to run
+      B2S_CUDA(cudaMemcpyAsync(h->pin_n, n_out, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      B2S_CUDA(cudaMemcpyAsync(h->pin_kp, kpts, (size_t)h->n_limit * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+      B2S_CUDA(cudaEventRecord(h->ev_kp, st));
+    }
   }
   // ---- SDDH: gathers evaluate the feature on demand and emit bf16x3 planes; the three large
   //      contractions (offset conv K=1152, sf_conv, aggregation K=M*128) run on tcgen05 ----
@@ -519,17 +530,16 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
     ++h->launches; B2S_LAUNCH_CHECK();
     B2S_TRY(tc_gemm(h, st, h->m_S, K * M, h->tc_sf, nullptr, 1, K * M, n_out, M, nullptr, 128, h->F, (size_t)K * M * 128));
     B2S_TRY(tc_gemm(h, st, h->m_F, K, h->tc_agg, nullptr, 0, K, n_out, 1, h->descraw, 128, nullptr, 0));
-    launch_k(k_desc_normalize, cdiv(K, 8), 256, 0, st, h->descraw, n_out, desc);
+    launch_k(k_desc_normalize, cdiv(K, 8), 256, 0, st, h->descraw, n_out, desc, h->desc_renorm_eps);
     ++h->launches; B2S_LAUNCH_CHECK();
   }
   return 0;
 }
 
-extern "C" int b2s_aliked_extract_host(b2s_aliked* h, const void* img, int fmt, int H, int W, int row_stride,
-                                       float* kpts, float* desc, float* scores, int32_t* n_out) {
-  if (!h || !img || !kpts || !desc || !n_out) { set_error("b2s_aliked_extract_host: null argument"); return B2S_EINVAL; }
-  B2S_CUDA(cudaSetDevice(h->device));
-  const size_t bytes = fmt == B2S_IMG_BGR_U8_HWC ? (size_t)(row_stride > 0 ? row_stride : 3 * W) * H : (size_t)3 * H * W * sizeof(float);
+extern "C" int b2s_aliked_extract_host_ex(b2s_aliked* h, const void* img, int fmt, int H, int W, int row_stride,
+                                          float* kpts, float* desc, float* scores, int32_t* n_out, float desc_renorm_eps);
+
+static int aliked_host_staging(b2s_aliked* h, size_t bytes) {
   if (bytes > h->himg_bytes || !h->hkp) {
     h->hostarena.release();
     h->himg_bytes = 0;
@@ -542,9 +552,75 @@ extern "C" int b2s_aliked_extract_host(b2s_aliked* h, const void* img, int fmt, 
     B2S_TRY(h->hostarena.alloc(&h->hn, (size_t)1));
     h->himg_bytes = bytes;
   }
+  return 0;
+}
+
+// Split form of b2s_aliked_extract_host_ex: begin enqueues the whole extraction and returns; keypoints blocks only
+// until the detector (DKD) has finished - the descriptor head is still running - so the caller can build its keypoint
+// objects meanwhile; finish waits for the descriptors.  One extraction may be pending per handle.
+extern "C" int b2s_aliked_extract_host_begin(b2s_aliked* h, const void* img, int fmt, int H, int W, int row_stride, float desc_renorm_eps) {
+  if (!h || !img) { set_error("b2s_aliked_extract_host_begin: null argument"); return B2S_EINVAL; }
+  if (h->pending) { set_error("b2s_aliked_extract_host_begin: an extraction is already pending on this handle"); return B2S_EINVAL; }
+  B2S_CUDA(cudaSetDevice(h->device));
+  const size_t bytes = fmt == B2S_IMG_BGR_U8_HWC ? (size_t)(row_stride > 0 ? row_stride : 3 * W) * H : (size_t)3 * H * W * sizeof(float);
+  B2S_TRY(aliked_host_staging(h, bytes));
+  if (!h->pin_kp) {
+    B2S_CUDA(cudaMallocHost((void**)&h->pin_kp, (size_t)h->n_limit * 2 * sizeof(float)));
+    B2S_CUDA(cudaMallocHost((void**)&h->pin_n, sizeof(int32_t)));
+    B2S_CUDA(cudaEventCreateWithFlags(&h->ev_kp, cudaEventDisableTiming));
+  }
   cudaStream_t st = 0;
   B2S_CUDA(cudaMemcpyAsync(h->himg, img, bytes, cudaMemcpyHostToDevice, st));
-  B2S_TRY(b2s_aliked_extract(h, h->himg, fmt, H, W, row_stride, st, h->hkp, h->hdesc, h->hscores, h->hn));
+  h->desc_renorm_eps = desc_renorm_eps; h->early_kp = true;
+  const int rc = b2s_aliked_extract(h, h->himg, fmt, H, W, row_stride, st, h->hkp, h->hdesc, h->hscores, h->hn);
+  h->desc_renorm_eps = 0.f; h->early_kp = false;
+  B2S_TRY(rc);
+  h->pending = true;
+  return 0;
+}
+
+extern "C" int b2s_aliked_extract_host_keypoints(b2s_aliked* h, float* kpts, int32_t* n_out) {
+  if (!h || !kpts || !n_out || !h->pending) { set_error("b2s_aliked_extract_host_keypoints: no pending extraction"); return B2S_EINVAL; }
+  B2S_CUDA(cudaSetDevice(h->device));
+  B2S_CUDA(cudaEventSynchronize(h->ev_kp));
+  const int32_t n = *h->pin_n;
+  *n_out = n;
+  if (n > 0) std::memcpy(kpts, h->pin_kp, (size_t)n * 2 * sizeof(float));
+  return 0;
+}
+
+extern "C" int b2s_aliked_extract_host_finish(b2s_aliked* h, float* desc, float* scores) {
+  if (!h || !desc || !h->pending) { set_error("b2s_aliked_extract_host_finish: no pending extraction"); return B2S_EINVAL; }
+  B2S_CUDA(cudaSetDevice(h->device));
+  h->pending = false;
+  cudaStream_t st = 0;
+  B2S_CUDA(cudaEventSynchronize(h->ev_kp));
+  const int32_t n = *h->pin_n;
+  if (n > 0) {
+    B2S_CUDA(cudaMemcpyAsync(desc, h->hdesc, (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (scores) B2S_CUDA(cudaMemcpyAsync(scores, h->hscores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  B2S_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int b2s_aliked_extract_host(b2s_aliked* h, const void* img, int fmt, int H, int W, int row_stride,
+                                       float* kpts, float* desc, float* scores, int32_t* n_out) {
+  return b2s_aliked_extract_host_ex(h, img, fmt, H, W, row_stride, kpts, desc, scores, n_out, 0.f);
+}
+
+extern "C" int b2s_aliked_extract_host_ex(b2s_aliked* h, const void* img, int fmt, int H, int W, int row_stride,
+                                          float* kpts, float* desc, float* scores, int32_t* n_out, float desc_renorm_eps) {
+  if (!h || !img || !kpts || !desc || !n_out) { set_error("b2s_aliked_extract_host: null argument"); return B2S_EINVAL; }
+  B2S_CUDA(cudaSetDevice(h->device));
+  const size_t bytes = fmt == B2S_IMG_BGR_U8_HWC ? (size_t)(row_stride > 0 ? row_stride : 3 * W) * H : (size_t)3 * H * W * sizeof(float);
+  B2S_TRY(aliked_host_staging(h, bytes));
+  cudaStream_t st = 0;
+  B2S_CUDA(cudaMemcpyAsync(h->himg, img, bytes, cudaMemcpyHostToDevice, st));
+  h->desc_renorm_eps = desc_renorm_eps;
+  const int rc_ext = b2s_aliked_extract(h, h->himg, fmt, H, W, row_stride, st, h->hkp, h->hdesc, h->hscores, h->hn);
+  h->desc_renorm_eps = 0.f;
+  B2S_TRY(rc_ext);
   int32_t n = 0;
   B2S_CUDA(cudaMemcpyAsync(&n, h->hn, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   B2S_CUDA(cudaStreamSynchronize(st));

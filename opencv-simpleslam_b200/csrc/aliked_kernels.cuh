@@ -70,11 +70,42 @@ __global__ void __launch_bounds__(256) k_preprocess(PreParams p) {
     const int y0 = (int)fy, x0 = (int)fx;
     const int y1 = y0 + (y0 < p.H - 1 ? 1 : 0), x1 = x0 + (x0 < p.W - 1 ? 1 : 0);
     const float ly1 = fy - (float)y0, ly0 = 1.f - ly1, lx1 = fx - (float)x0, lx0 = 1.f - lx1;
+    if (p.do_blur && p.ky == 3 && p.kx == 3) {
+      // 3x3 blur (every down-scale factor below 2.5): the four bilinear corners share a 4x4 source window; load it
+      // once and evaluate each corner with exactly pre_blur()'s arithmetic (same bits, 16 instead of 36 loads)
+      int ry[4], rx[4];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float p00 = pre_blur(p, c, y0, x0), p01 = pre_blur(p, c, y0, x1);
-      const float p10 = pre_blur(p, c, y1, x0), p11 = pre_blur(p, c, y1, x1);
-      v[c] = ly0 * (lx0 * p00 + lx1 * p01) + ly1 * (lx0 * p10 + lx1 * p11);
+      for (int i = 0; i < 4; ++i) { ry[i] = reflect_idx(y0 - 1 + i, p.H); rx[i] = reflect_idx(x0 - 1 + i, p.W); }
+      const bool dy = y1 != y0, dx = x1 != x0;       // at the last row / column the two corners coincide
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float w[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) w[i][j] = pre_src(p, c, ry[i], rx[j]);
+        auto corner = [&](int oy, int ox) {
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            float row = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) row += p.gx[j] * w[oy + i][ox + j];
+            acc += p.gy[i] * row;
+          }
+          return acc;
+        };
+        const float p00 = corner(0, 0), p01 = dx ? corner(0, 1) : p00;
+        const float p10 = dy ? corner(1, 0) : p00, p11 = dy ? (dx ? corner(1, 1) : p10) : p01;
+        v[c] = ly0 * (lx0 * p00 + lx1 * p01) + ly1 * (lx0 * p10 + lx1 * p11);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float p00 = pre_blur(p, c, y0, x0), p01 = pre_blur(p, c, y0, x1);
+        const float p10 = pre_blur(p, c, y1, x0), p11 = pre_blur(p, c, y1, x1);
+        v[c] = ly0 * (lx0 * p00 + lx1 * p01) + ly1 * (lx0 * p10 + lx1 * p11);
+      }
     }
   }
 #pragma unroll
@@ -469,8 +500,45 @@ __device__ __forceinline__ BilinTap level_tap(const FeatSrc& s, int l, int y, in
   t.o00 = y0 * s.Wk[l] + x0; t.o01 = y0 * s.Wk[l] + x1; t.o10 = y1 * s.Wk[l] + x0; t.o11 = y1 * s.Wk[l] + x1;
   return t;
 }
+// one axis of the align_corners=True upsampling: source index pair and weights of output coordinate v
+struct AxisTap { int i0, i1; float l0, l1; };
+__device__ __forceinline__ AxisTap axis_tap(float scale, int v, int n) {
+  const float f = scale * (float)v;
+  AxisTap t;
+  t.i0 = (int)f; t.i1 = t.i0 + (t.i0 < n - 1 ? 1 : 0);
+  t.l1 = f - (float)t.i0; t.l0 = 1.f - t.l1;
+  return t;
+}
+__device__ __forceinline__ BilinTap join_taps(const AxisTap& ty, const AxisTap& tx, int Wk) {
+  BilinTap t;
+  t.ly0 = ty.l0; t.ly1 = ty.l1; t.lx0 = tx.l0; t.lx1 = tx.l1;
+  t.o00 = ty.i0 * Wk + tx.i0; t.o01 = ty.i0 * Wk + tx.i1; t.o10 = ty.i1 * Wk + tx.i0; t.o11 = ty.i1 * Wk + tx.i1;
+  return t;
+}
 __device__ __forceinline__ float bilin(const BilinTap& t, float a, float b, float c, float d) {
   return t.ly0 * (t.lx0 * a + t.lx1 * b) + t.ly1 * (t.lx0 * c + t.lx1 * d);
+}
+
+// normalised feature of UNPADDED pixel (yu, xu) given the three levels' taps; w1 = row `lane` of W1.  Whole warp must call.
+__device__ __forceinline__ float4 feat_at_taps(const FeatSrc& s, const float (&w1)[16], int yu, int xu, int lane, const BilinTap (&tp)[3]) {
+  const int y = yu + s.pad_t, x = xu + s.pad_l;
+  const float xin = lane < 16 ? s.x1[((size_t)lane * s.Hp + y) * s.Wp + x] : 0.f;
+  float a = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a = fmaf(w1[k], __shfl_sync(0xffffffffu, xin, k), a);
+  float4 f;
+  f.x = selu_f(a);
+  float lv[3];
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const BilinTap& t = tp[l];
+    const float* m = s.xa[l] + lane;
+    lv[l] = bilin(t, __ldg(m + (size_t)t.o00 * 32), __ldg(m + (size_t)t.o01 * 32), __ldg(m + (size_t)t.o10 * 32), __ldg(m + (size_t)t.o11 * 32));
+  }
+  f.y = lv[0]; f.z = lv[1]; f.w = lv[2];
+  const float ssq = warp_sum(fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, f.w * f.w))));
+  const float denom = fmaxf(sqrtf(ssq), 1e-12f);
+  return make_float4(f.x / denom, f.y / denom, f.z / denom, f.w / denom);
 }
 
 // normalised feature of UNPADDED pixel (yu, xu); w1 = row `lane` of W1.  Whole warp must call.
@@ -1022,10 +1090,25 @@ __global__ void __launch_bounds__(256) k_sddh_sample(FeatSrc s, const float* __r
   const int ix0 = (int)fx0, iy0 = (int)fy0, ix1 = ix0 + 1, iy1 = iy0 + 1;
   const float wnw = ((float)ix1 - gx) * ((float)iy1 - gy), wne = (gx - (float)ix0) * ((float)iy1 - gy);
   const float wsw = ((float)ix1 - gx) * (gy - (float)iy0), wse = (gx - (float)ix0) * (gy - (float)iy0);
-  auto ld = [&](int yy, int xx) {     // uniform across the warp: all lanes take the same branch
-    return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? feat_at(s, w1, yy, xx, lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  // the four neighbours share their per-axis upsampling taps: two rows x two columns per level
+  AxisTap ty[2][3], tx[2][3];
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      ty[e][l] = axis_tap(s.sh[l], min(max(iy0 + e, 0), H - 1) + s.pad_t, s.Hk[l]);
+      tx[e][l] = axis_tap(s.sw[l], min(max(ix0 + e, 0), W - 1) + s.pad_l, s.Wk[l]);
+    }
+  }
+  auto ld = [&](int ey, int ex) {     // uniform across the warp: all lanes take the same branch
+    const int yy = iy0 + ey, xx = ix0 + ex;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
+    BilinTap tp[3];
+#pragma unroll
+    for (int l = 0; l < 3; ++l) tp[l] = join_taps(ty[ey][l], tx[ex][l], s.Wk[l]);
+    return feat_at_taps(s, w1, yy, xx, lane, tp);
   };
-  const float4 a = ld(iy0, ix0), b = ld(iy0, ix1), c = ld(iy1, ix0), d = ld(iy1, ix1);
+  const float4 a = ld(0, 0), b = ld(0, 1), c = ld(1, 0), d = ld(1, 1);
   __nv_bfloat16* o = S + (size_t)job * 128 + lane;
   store_planes1(o, plane, a.x * wnw + b.x * wne + c.x * wsw + d.x * wse);
   store_planes1(o + 32, plane, a.y * wnw + b.y * wne + c.y * wsw + d.y * wse);
@@ -1034,7 +1117,9 @@ __global__ void __launch_bounds__(256) k_sddh_sample(FeatSrc s, const float* __r
 }
 
 // F.normalize(desc, dim=1) (eps 1e-12).  warp per row of 128.
-__global__ void __launch_bounds__(256) k_desc_normalize(const float* __restrict__ raw, const int32_t* __restrict__ n_dev, float* __restrict__ out) {
+// renorm_eps > 0 additionally applies the caller-side step of features_utils.py:100, d / (||d||_2 + eps).
+__global__ void __launch_bounds__(256) k_desc_normalize(const float* __restrict__ raw, const int32_t* __restrict__ n_dev, float* __restrict__ out,
+                                                        float renorm_eps) {
   pdl_wait();
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (n >= *n_dev) return;
@@ -1042,7 +1127,12 @@ __global__ void __launch_bounds__(256) k_desc_normalize(const float* __restrict_
   const float4 v = *reinterpret_cast<const float4*>(raw + (size_t)n * 128 + lane * 4);
   const float ssq = warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
   const float d = fmaxf(sqrtf(ssq), 1e-12f);
-  *reinterpret_cast<float4*>(out + (size_t)n * 128 + lane * 4) = make_float4(v.x / d, v.y / d, v.z / d, v.w / d);
+  float4 o = make_float4(v.x / d, v.y / d, v.z / d, v.w / d);
+  if (renorm_eps > 0.f) {
+    const float d2 = sqrtf(warp_sum(o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w)) + renorm_eps;
+    o = make_float4(o.x / d2, o.y / d2, o.z / d2, o.w / d2);
+  }
+  *reinterpret_cast<float4*>(out + (size_t)n * 128 + lane * 4) = o;
 }
 
 }  // namespace b2s

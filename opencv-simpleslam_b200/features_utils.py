@@ -9,7 +9,8 @@ Differences from the reference that are invisible to callers:
     BGR->RGB, /255 conversion happens inside the preprocess kernel;
   * keypoints come back as one [N,2] array and are turned into cv2.KeyPoint objects with
     cv2.KeyPoint_convert (no 2N device->host scalar syncs, features_utils.py:61-63);
-  * matching is one C-ABI call on host buffers (b2s_lightglue_match_host).
+  * matching is one C-ABI call on host buffers (b2s_lightglue_match_host);
+  * the caller-side descriptor re-normalisation (features_utils.py:100) is fused into the extractor's last kernel.
 """
 from __future__ import annotations
 
@@ -97,12 +98,9 @@ def _convert_lg_matches_to_opencv(matches_raw) -> List[cv2.DMatch]:
 def feature_extractor(args, img: np.ndarray, detector):
     """Extract features from one BGR frame -> (list[cv2.KeyPoint], np.float32 [N,128])."""
     if args.use_lightglue:
-        kps, des0, _ = detector.extract_host(img)
-        kp0 = _convert_lg_kps_to_opencv(kps)
-        # features_utils.py:100  des0 /= (||des0||_2 + 1e-8), float32; des0 is a fresh array we own
-        nrm = np.sqrt(np.einsum("ij,ij->i", des0, des0))
-        nrm += np.float32(1e-8)
-        des0 /= nrm[:, None]
+        # features_utils.py:100  des0 /= (||des0||_2 + 1e-8) runs on the device, fused into the descriptor normalisation
+        # and the cv2.KeyPoint list is built while the descriptor head is still running on the GPU
+        kp0, des0, _ = detector.extract_host_split(img, _convert_lg_kps_to_opencv, desc_renorm_eps=1e-8)
         return kp0, des0
     kp0, des0 = detector.detectAndCompute(img, None)
     if des0 is None:

@@ -149,8 +149,9 @@ class ALIKED(_Module):
             self.extract_device(t, _lib.IMG_BGR_U8_HWC, H, W, 3 * W)
             return self._finish(H, W)
 
-    def extract_host(self, image: np.ndarray):
-        """One C-ABI call with host buffers (b2s_aliked_extract_host): returns numpy (kpts, desc, scores)."""
+    def extract_host(self, image: np.ndarray, desc_renorm_eps: float = 0.0):
+        """One C-ABI call with host buffers (b2s_aliked_extract_host_ex): returns numpy (kpts, desc, scores).
+        desc_renorm_eps > 0 fuses the reference caller's `des /= (||des|| + eps)` (features_utils.py:100)."""
         H, W = image.shape[:2]
         if image.dtype == np.uint8:
             image = np.ascontiguousarray(image); fmt = _lib.IMG_BGR_U8_HWC; stride = 3 * W
@@ -161,9 +162,32 @@ class ALIKED(_Module):
         de = np.empty((self.n_limit, 128), np.float32)
         sc = np.empty((self.n_limit,), np.float32)
         n = C.c_int32(0)
-        check(lib.b2s_aliked_extract_host(self._handle, image.ctypes.data, fmt, H, W, stride, kp.ctypes.data,
-                                          de.ctypes.data, sc.ctypes.data, C.addressof(n)), "b2s_aliked_extract_host")
+        check(lib.b2s_aliked_extract_host_ex(self._handle, image.ctypes.data, fmt, H, W, stride, kp.ctypes.data,
+                                             de.ctypes.data, sc.ctypes.data, C.addressof(n), float(desc_renorm_eps)),
+              "b2s_aliked_extract_host")
         return kp[:n.value], de[:n.value], sc[:n.value]
+
+    def extract_host_split(self, image: np.ndarray, on_keypoints, desc_renorm_eps: float = 0.0):
+        """extract_host in three C-ABI calls (begin / keypoints / finish): `on_keypoints(kpts)` runs on the host while
+        the descriptor head is still busy on the GPU.  Returns (on_keypoints' result, desc, scores)."""
+        H, W = image.shape[:2]
+        if image.dtype == np.uint8:
+            image = np.ascontiguousarray(image); fmt = _lib.IMG_BGR_U8_HWC; stride = 3 * W
+        else:
+            image = np.ascontiguousarray(image, dtype=np.float32); fmt = _lib.IMG_RGB_F32_CHW; stride = 0
+            H, W = image.shape[-2:]
+        check(lib.b2s_aliked_extract_host_begin(self._handle, image.ctypes.data, fmt, H, W, stride, float(desc_renorm_eps)),
+              "b2s_aliked_extract_host_begin")
+        kp = np.empty((self.n_limit, 2), np.float32)
+        n = C.c_int32(0)
+        try:
+            check(lib.b2s_aliked_extract_host_keypoints(self._handle, kp.ctypes.data, C.addressof(n)), "b2s_aliked_extract_host_keypoints")
+            res = on_keypoints(kp[:n.value])
+        finally:
+            de = np.empty((max(n.value, 1), 128), np.float32)
+            sc = np.empty((max(n.value, 1),), np.float32)
+            check(lib.b2s_aliked_extract_host_finish(self._handle, de.ctypes.data, sc.ctypes.data), "b2s_aliked_extract_host_finish")
+        return res, de[:n.value], sc[:n.value]
 
     def debug(self, name: str) -> np.ndarray:
         n = C.c_size_t(0)

@@ -86,3 +86,19 @@ def test_init_feature_pipeline_signature():
     det2, mat2 = fu.init_feature_pipeline(SimpleNamespace(use_lightglue=False, detector="orb", matcher="bf", max_features=500))
     kp, des = fu.feature_extractor(SimpleNamespace(use_lightglue=False), synth.frame(0, 240, 320), det2)
     assert len(kp) > 0 and des.dtype == np.uint8
+
+
+def test_split_host_extraction_equals_single_call(pipelines):
+    """b2s_aliked_extract_host_begin/_keypoints/_finish (keypoint objects built while the descriptor head runs) and
+    the fused re-normalisation of features_utils.py:100 give what the single call + numpy give."""
+    det = pipelines[3]
+    img = synth.frame(21, 376, 1241)
+    kp, de, sc = det.extract_host(img)
+    seen = {}
+    res, de2, sc2 = det.extract_host_split(img, lambda k: seen.setdefault("kp", k.copy()) is not None and len(k), desc_renorm_eps=1e-8)
+    assert res == len(kp) and np.array_equal(seen["kp"], kp) and np.array_equal(sc2, sc)
+    ref = de / (np.linalg.norm(de, axis=1, keepdims=True) + 1e-8).astype(np.float32)
+    assert np.abs(de2 - ref).max() < 1e-6
+    with pytest.raises(Exception):                      # nothing pending any more
+        det.extract_host_split.__self__ and __import__("b200slam")._lib.check(
+            __import__("b200slam")._lib.lib.b2s_aliked_extract_host_finish(det._handle, de2.ctypes.data, None), "finish")
