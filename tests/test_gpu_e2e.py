@@ -102,3 +102,18 @@ def test_split_host_extraction_equals_single_call(pipelines):
     with pytest.raises(Exception):                      # nothing pending any more
         det.extract_host_split.__self__ and __import__("b200slam")._lib.check(
             __import__("b200slam")._lib.lib.b2s_aliked_extract_host_finish(det._handle, de2.ctypes.data, None), "finish")
+
+
+def test_keyframe_window_all_pairs_single_gpu(pipelines):
+    """BASELINE config 3 shape (small): window.match_keyframe_window at world 1 equals pair-by-pair host matching."""
+    from b200slam import window
+    args, fu, ofu, det, mat = pipelines[:5]
+    frames_np = [synth.frame(8 * t, 240, 320) for t in range(4)]
+    frames = [torch.from_numpy(f).cuda() for f in frames_np]
+    res = window.match_keyframe_window(frames, det, mat, 240, 320)
+    torch.cuda.synchronize()
+    assert sorted(res) == [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
+    feats = [det.extract_host(f) for f in frames_np]
+    for (i, j), (m, s, n) in res.items():
+        ref = mat.match_host(feats[i][0], feats[i][1], feats[j][0], feats[j][1])
+        assert np.array_equal(m[: int(n)].cpu().numpy(), ref["matches"])
