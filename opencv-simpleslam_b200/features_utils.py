@@ -21,6 +21,7 @@ import cv2
 import numpy as np
 import torch
 
+from .containers import DMatchArray, KeyPointArray
 from .frontend import ALIKED, LightGlue, rbd  # noqa: F401  (re-exported like the reference's imports)
 
 
@@ -71,6 +72,8 @@ def _convert_lg_kps_to_opencv(kp0) -> List[cv2.KeyPoint]:
 
 
 def _kps_to_array(cv_kp) -> np.ndarray:
+    if isinstance(cv_kp, KeyPointArray):
+        return cv_kp.pts
     if len(cv_kp) == 0:
         return np.empty((0, 2), np.float32)
     return np.ascontiguousarray(cv2.KeyPoint_convert(list(cv_kp)), dtype=np.float32).reshape(-1, 2)
@@ -100,7 +103,8 @@ def feature_extractor(args, img: np.ndarray, detector):
     if args.use_lightglue:
         # features_utils.py:100  des0 /= (||des0||_2 + 1e-8) runs on the device, fused into the descriptor normalisation
         # and the cv2.KeyPoint list is built while the descriptor head is still running on the GPU
-        kp0, des0, _ = detector.extract_host_split(img, _convert_lg_kps_to_opencv, desc_renorm_eps=1e-8)
+        make = KeyPointArray if getattr(args, "array_native", False) else _convert_lg_kps_to_opencv   # opt-in: SURVEY 8f f2
+        kp0, des0, _ = detector.extract_host_split(img, make, desc_renorm_eps=1e-8)
         return kp0, des0
     kp0, des0 = detector.detectAndCompute(img, None)
     if des0 is None:
@@ -120,6 +124,8 @@ def feature_matcher(args, kp0, kp1, des0, des1, matcher):
         raw = matcher.match_host(_kps_to_array(kp0), d0, _kps_to_array(kp1), d1)
         thr = float(getattr(args, "min_conf", 0.7))
         keep = raw["scores"] > np.float32(thr)
+        if getattr(args, "array_native", False):
+            return DMatchArray(raw["matches"][keep])
         return _convert_lg_matches_to_opencv(raw["matches"][keep])
     matches = matcher.match(des0, des1)
     return sorted(matches, key=lambda m: m.distance)
@@ -129,6 +135,10 @@ def filter_matches_ransac(kp1, kp2, matches, thresh=1.0):
     """Drop outliers with a fundamental-matrix RANSAC (features_utils.py:185-200; CPU, cv2)."""
     if len(matches) < 8:
         return matches
+    if isinstance(matches, DMatchArray) and isinstance(kp1, KeyPointArray) and isinstance(kp2, KeyPointArray):
+        pts1, pts2 = kp1.pts[matches.queryIdx], kp2.pts[matches.trainIdx]
+        _, mask = cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC, thresh, 0.99)
+        return DMatchArray(matches.pairs[:0]) if mask is None else matches[mask.ravel().astype(bool)]
     pts1 = np.float32([kp1[m.queryIdx].pt for m in matches])
     pts2 = np.float32([kp2[m.trainIdx].pt for m in matches])
     _, mask = cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC, thresh, 0.99)

@@ -117,3 +117,17 @@ def test_keyframe_window_all_pairs_single_gpu(pipelines):
     for (i, j), (m, s, n) in res.items():
         ref = mat.match_host(feats[i][0], feats[i][1], feats[j][0], feats[j][1])
         assert np.array_equal(m[: int(n)].cpu().numpy(), ref["matches"])
+
+
+def test_array_native_path_equals_list_path(pipelines):
+    args, fu, ofu, det, mat = pipelines[:5]
+    a2 = SimpleNamespace(**vars(args), array_native=True)
+    i0, i1 = synth.frame(30, 376, 1241), synth.frame(31, 376, 1241)
+    l0, l1 = fu.feature_extractor(args, i0, det), fu.feature_extractor(args, i1, det)
+    n0, n1 = fu.feature_extractor(a2, i0, det), fu.feature_extractor(a2, i1, det)
+    assert [k.pt for k in l0[0]] == [k.pt for k in n0[0]] and np.array_equal(l0[1], n0[1])
+    ml = fu.feature_matcher(args, l0[0], l1[0], l0[1], l1[1], mat)
+    mn = fu.feature_matcher(a2, n0[0], n1[0], n0[1], n1[1], mat)
+    assert [(m.queryIdx, m.trainIdx) for m in ml] == [(m.queryIdx, m.trainIdx) for m in mn]
+    il, inn = fu.filter_matches_ransac(l0[0], l1[0], ml, 2.5), fu.filter_matches_ransac(n0[0], n1[0], mn, 2.5)
+    assert abs(len(il) - len(inn)) <= max(3, len(il) // 20)      # cv2 RANSAC on the same points (RNG state may differ)

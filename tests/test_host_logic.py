@@ -105,3 +105,22 @@ def test_reference_adapter_runs_unchanged_over_oracle_objects(aliked_state, ligh
         assert [(m.queryIdx, m.trainIdx) for m in mr] == [(m.queryIdx, m.trainIdx) for m in mo] and len(mr) > 10
     finally:
         sys.modules.pop("lightglue", None); sys.modules.pop("lightglue.utils", None)
+
+
+def test_array_native_containers_quack_like_cv2_lists():
+    """ndarray-backed sequences expose what the reference's consumers read (.pt / .queryIdx / .trainIdx)."""
+    import cv2
+    from b200slam.containers import DMatchArray, KeyPointArray
+    pts = np.random.default_rng(0).random((50, 2)).astype(np.float32) * 100
+    ka = KeyPointArray(pts)
+    cv = ka.to_cv()
+    assert len(ka) == 50 and isinstance(cv[0], cv2.KeyPoint)
+    for a, b in zip(ka, cv):
+        assert a.pt == b.pt and a.size == b.size and a.angle == b.angle and a.response == b.response
+    assert ka[7].pt == cv[7].pt and len(ka[10:20]) == 10 and ka[10:20][0].pt == cv[10].pt
+    pairs = np.stack([np.arange(20), np.arange(20)[::-1]], 1)
+    ma = DMatchArray(pairs)
+    mc = ma.to_cv()
+    assert [(m.queryIdx, m.trainIdx, m.imgIdx, m.distance) for m in ma] == [(m.queryIdx, m.trainIdx, m.imgIdx, m.distance) for m in mc]
+    assert np.float32([ka[m.queryIdx].pt for m in ma]).tolist() == ka.pts[ma.queryIdx].tolist()     # the reference's access pattern
+    assert len(ma[np.arange(20) % 2 == 0]) == 10
