@@ -161,6 +161,52 @@ int b2s_lightglue_match_batch(b2s_lg* h, const float* kpts_dev, const float* des
                               const int32_t* pair_j, int n_pairs, void* stream, int stride,
                               int32_t* matches_dev, float* mscores_dev, int32_t* n_matches_dev);
 
+/* ---------------------------------------------------------------------------------------------
+ * Rows behind the matcher: epipolar outlier rejection and frame ingest.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct b2s_fm b2s_fm;
+typedef struct b2s_remap b2s_remap;
+
+/* Fundamental-matrix RANSAC.  Replaces `cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC, thresh, 0.99)` inside
+ * `filter_matches_ransac` (features_utils.py:185-200; callers main_revamped.py:126, keyframe_utils.py:154,
+ * triangulation_utils.py:132).  n_hyp minimal 7-point samples are drawn (splitmix64 streams of `seed`), solved and
+ * scored in parallel with OpenCV's error (max of the two squared point-to-epipolar-line distances <= thresh^2); the
+ * model with the largest consensus wins (lowest sample index on ties).  OpenCV's sequential loop stops after at most
+ * 2000 samples; a fixed n_hyp >= 2000 therefore never looks at fewer hypotheses than cv2 would for the same data.
+ *   pts1_dev / pts2_dev : [*,2] f32 pixel coordinates; pairs_dev (nullable) [n,2] int32 selects row pairs[i][0] of
+ *                         pts1 and pairs[i][1] of pts2 (the matcher's `matches` output) - NULL means row i of both
+ *   mask_dev   : [n] u8, 1 = inlier           F_dev : [9] f64 row-major, unit Frobenius norm (x2^T F x1 = 0)
+ *   result_dev : [2] int32 = { inlier count, winning model index (sample*3 + root) or -1 if every sample was degenerate } */
+int b2s_fm_create(int device, int max_points, int max_hypotheses, b2s_fm** out);
+void b2s_fm_destroy(b2s_fm* h);
+int b2s_fm_ransac(b2s_fm* h, const float* pts1_dev, const float* pts2_dev, const int32_t* pairs_dev, int n,
+                  float thresh, int n_hyp, uint64_t seed, void* stream, uint8_t* mask_dev, double* F_dev,
+                  int32_t* result_dev);
+/* host buffers; copies in/out on the handle's own stream and synchronises */
+int b2s_fm_ransac_host(b2s_fm* h, const float* pts1, const float* pts2, int n, float thresh, int n_hyp,
+                       uint64_t seed, uint8_t* mask, double* F, int32_t* n_inliers, int32_t* model_index);
+/* test hook: candidate models (pixel coordinates, [3][9]), their number and consensus counts of one sample */
+int b2s_fm_debug_models(b2s_fm* h, int hyp, double* models27, int32_t* n_models, int32_t* counts3);
+long long b2s_fm_launch_count(const b2s_fm* h);
+
+/* Frame ingest.  Replaces `cv2.remap(img, mapx, mapy, cv2.INTER_LINEAR)` on u8 BGR frames with the maps of
+ * `cv2.initUndistortRectifyMap(..., cv2.CV_32FC1)` (main_revamped.py:313-315, :323-324).  Bit-exact with OpenCV's
+ * fixed-point bilinear remap (5 fractional coordinate bits, 15-bit weights, constant 0 border).  The maps are uploaded
+ * once at create; the undistorted frame can stay on the device and go straight into b2s_aliked_extract. */
+int b2s_remap_create(int device, const float* mapx_host, const float* mapy_host, int dst_h, int dst_w, int src_h,
+                     int src_w, b2s_remap** out);
+void b2s_remap_destroy(b2s_remap* h);
+int b2s_remap_bgr(b2s_remap* h, const uint8_t* src_dev, int src_stride, void* stream, uint8_t* dst_dev, int dst_stride);
+int b2s_remap_bgr_host(b2s_remap* h, const uint8_t* src, int src_stride, uint8_t* dst, int dst_stride);
+const uint8_t* b2s_remap_output_dev(const b2s_remap* h);
+void b2s_remap_dims(const b2s_remap* h, int* dst_h, int* dst_w, int* src_h, int* src_w);
+/* Attach (or detach with NULL) an ingest stage to an extractor: the *_host extraction entry points then take the raw
+ * distorted frame, undistort it on the device and extract from the result - the reference's
+ * `img = cv2.remap(img, mapx, mapy, INTER_LINEAR); feature_extractor(args, img, detector)` in one upload.  Keypoints are in
+ * undistorted-image pixels.  The remap handle is borrowed, not owned. */
+int b2s_aliked_set_undistort(b2s_aliked* h, b2s_remap* r);
+long long b2s_remap_launch_count(const b2s_remap* h);
+
 /* Test hooks: copy a named intermediate of the most recent call to the host (fp32).
  * Returns the number of floats available in *n (and copies min(*n, cap)). */
 int b2s_aliked_debug_get(b2s_aliked* h, const char* name, float* out, size_t cap, size_t* n);

@@ -69,6 +69,20 @@ SIGNATURES = {
     "b2s_bench_attn_tc3": (C.c_int, [C.c_int, C.c_int, C.c_int, f32p]),
     "b2s_aliked_launch_count": (C.c_longlong, [vp]),
     "b2s_lg_launch_count": (C.c_longlong, [vp]),
+    "b2s_fm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "b2s_fm_destroy": (None, [vp]),
+    "b2s_fm_ransac": (C.c_int, [vp, f32p, f32p, i32p, C.c_int, C.c_float, C.c_int, C.c_uint64, vp, vp, vp, i32p]),
+    "b2s_fm_ransac_host": (C.c_int, [vp, f32p, f32p, C.c_int, C.c_float, C.c_int, C.c_uint64, vp, vp, i32p, i32p]),
+    "b2s_fm_debug_models": (C.c_int, [vp, C.c_int, vp, i32p, i32p]),
+    "b2s_fm_launch_count": (C.c_longlong, [vp]),
+    "b2s_remap_create": (C.c_int, [C.c_int, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "b2s_remap_destroy": (None, [vp]),
+    "b2s_remap_bgr": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int]),
+    "b2s_remap_bgr_host": (C.c_int, [vp, vp, C.c_int, vp, C.c_int]),
+    "b2s_remap_output_dev": (vp, [vp]),
+    "b2s_remap_launch_count": (C.c_longlong, [vp]),
+    "b2s_remap_dims": (None, [vp, i32p, i32p, i32p, i32p]),
+    "b2s_aliked_set_undistort": (C.c_int, [vp, vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)   # AttributeError here == header/library mismatch

@@ -59,7 +59,7 @@ struct b2s_aliked {
   long long launches = 0;
   float desc_renorm_eps = 0.f;                           // set per call by b2s_aliked_extract_host_ex
   // split host API (begin / keypoints / finish): pinned staging for the early keypoint copy
-  float* pin_kp = nullptr; int32_t* pin_n = nullptr; cudaEvent_t ev_kp = nullptr; bool early_kp = false; bool pending = false;
+  float* pin_kp = nullptr; int32_t* pin_n = nullptr; cudaEvent_t ev_kp = nullptr; bool early_kp = false; bool pending = false;  b2s_remap* undist = nullptr;                           // optional ingest stage (b2s_aliked_set_undistort); borrowed
 };
 
 extern "C" void b2s_aliked_default_cfg(b2s_aliked_cfg* c) {
@@ -555,6 +555,30 @@ static int aliked_host_staging(b2s_aliked* h, size_t bytes) {
   return 0;
 }
 
+extern "C" int b2s_aliked_set_undistort(b2s_aliked* h, b2s_remap* r) {
+  if (!h) { set_error("b2s_aliked_set_undistort: null handle"); return B2S_EINVAL; }
+  if (h->pending) { set_error("b2s_aliked_set_undistort: an extraction is pending"); return B2S_EINVAL; }
+  h->undist = r;
+  return 0;
+}
+
+// host-API ingest: the uploaded frame goes through the attached cv2.remap stage (u8 BGR only) before K0
+static int aliked_ingest(b2s_aliked* h, int fmt, int* H, int* W, int* row_stride, cudaStream_t st, const void** img_dev) {
+  *img_dev = h->himg;
+  if (!h->undist) return 0;
+  int dh, dw, sh, sw;
+  b2s_remap_dims(h->undist, &dh, &dw, &sh, &sw);
+  if (fmt != B2S_IMG_BGR_U8_HWC || *H != sh || *W != sw) {
+    set_error("b2s_aliked: the attached undistortion stage expects %dx%d u8 BGR frames, got %dx%d fmt %d", sh, sw, *H, *W, fmt);
+    return B2S_EINVAL;
+  }
+  uint8_t* dst = const_cast<uint8_t*>(b2s_remap_output_dev(h->undist));
+  B2S_TRY(b2s_remap_bgr(h->undist, static_cast<const uint8_t*>(h->himg), *row_stride > 0 ? *row_stride : 3 * sw, st, dst, 3 * dw));
+  ++h->launches;
+  *img_dev = dst; *H = dh; *W = dw; *row_stride = 3 * dw;
+  return 0;
+}
+
 // Split form of b2s_aliked_extract_host_ex: begin enqueues the whole extraction and returns; keypoints blocks only
 // until the detector (DKD) has finished - the descriptor head is still running - so the caller can build its keypoint
 // objects meanwhile; finish waits for the descriptors.  One extraction may be pending per handle.
@@ -571,8 +595,10 @@ extern "C" int b2s_aliked_extract_host_begin(b2s_aliked* h, const void* img, int
   }
   cudaStream_t st = 0;
   B2S_CUDA(cudaMemcpyAsync(h->himg, img, bytes, cudaMemcpyHostToDevice, st));
+  const void* src = nullptr;
+  B2S_TRY(aliked_ingest(h, fmt, &H, &W, &row_stride, st, &src));
   h->desc_renorm_eps = desc_renorm_eps; h->early_kp = true;
-  const int rc = b2s_aliked_extract(h, h->himg, fmt, H, W, row_stride, st, h->hkp, h->hdesc, h->hscores, h->hn);
+  const int rc = b2s_aliked_extract(h, src, fmt, H, W, row_stride, st, h->hkp, h->hdesc, h->hscores, h->hn);
   h->desc_renorm_eps = 0.f; h->early_kp = false;
   B2S_TRY(rc);
   h->pending = true;
@@ -617,8 +643,10 @@ extern "C" int b2s_aliked_extract_host_ex(b2s_aliked* h, const void* img, int fm
   B2S_TRY(aliked_host_staging(h, bytes));
   cudaStream_t st = 0;
   B2S_CUDA(cudaMemcpyAsync(h->himg, img, bytes, cudaMemcpyHostToDevice, st));
+  const void* src = nullptr;
+  B2S_TRY(aliked_ingest(h, fmt, &H, &W, &row_stride, st, &src));
   h->desc_renorm_eps = desc_renorm_eps;
-  const int rc_ext = b2s_aliked_extract(h, h->himg, fmt, H, W, row_stride, st, h->hkp, h->hdesc, h->hscores, h->hn);
+  const int rc_ext = b2s_aliked_extract(h, src, fmt, H, W, row_stride, st, h->hkp, h->hdesc, h->hscores, h->hn);
   h->desc_renorm_eps = 0.f;
   B2S_TRY(rc_ext);
   int32_t n = 0;

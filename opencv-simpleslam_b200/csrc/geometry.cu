@@ -1,0 +1,230 @@
+// geometry.cu - host orchestration behind b2s_fm_* (fundamental-matrix RANSAC, replaces the cv2.findFundamentalMat
+// call of `filter_matches_ransac`, /root/reference/slam/core/features_utils.py:185-200) and b2s_remap_* (cv2.remap of
+// the undistortion maps, /root/reference/slam/monocular/main_revamped.py:313-324).
+#include "geometry_kernels.cuh"
+
+#include <cmath>
+
+using namespace b2s;
+
+struct b2s_fm {
+  int device = 0, max_pts = 0, max_hyp = 0;
+  DeviceArena arena;
+  float4* xy = nullptr; double* norm = nullptr; double* models = nullptr; int32_t *nmodels = nullptr, *counts = nullptr;
+  // host API staging (device copies of the caller's host arrays + pinned result block)
+  float *d_pts1 = nullptr, *d_pts2 = nullptr; uint8_t* d_mask = nullptr; double* d_F = nullptr; int32_t* d_res = nullptr;
+  uint8_t* h_pin = nullptr;    // pinned: [max_pts] mask | 9 doubles | 2 int32
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+};
+
+extern "C" int b2s_fm_create(int device, int max_points, int max_hypotheses, b2s_fm** out) {
+  if (!out || max_points < 8 || max_hypotheses < 1) { set_error("b2s_fm_create: bad arguments"); return B2S_EINVAL; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    set_error("b2s_fm_create: no CUDA device %d (there is no CPU fallback)", device);
+    return B2S_ENODEV;
+  }
+  B2S_CUDA(cudaSetDevice(device));
+  b2s_fm* h = new b2s_fm();
+  h->device = device; h->max_pts = max_points; h->max_hyp = max_hypotheses;
+  int rc = 0;
+  auto A = [&](int r) { if (rc == 0) rc = r; };
+  A(h->arena.alloc(&h->xy, (size_t)max_points));
+  A(h->arena.alloc(&h->norm, 6));
+  A(h->arena.alloc(&h->models, (size_t)max_hypotheses * 27));
+  A(h->arena.alloc(&h->nmodels, (size_t)max_hypotheses));
+  A(h->arena.alloc(&h->counts, (size_t)max_hypotheses * 3));
+  A(h->arena.alloc(&h->d_pts1, (size_t)max_points * 2));
+  A(h->arena.alloc(&h->d_pts2, (size_t)max_points * 2));
+  A(h->arena.alloc(&h->d_mask, (size_t)max_points));
+  A(h->arena.alloc(&h->d_F, 9));
+  A(h->arena.alloc(&h->d_res, 2));
+  if (rc == 0 && cudaMallocHost((void**)&h->h_pin, (size_t)max_points + 128) != cudaSuccess) { set_error("b2s_fm_create: pinned alloc failed"); rc = B2S_ENOMEM; }
+  if (rc == 0 && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("b2s_fm_create: stream"); rc = B2S_ECUDA; }
+  if (rc != 0) { if (h->h_pin) cudaFreeHost(h->h_pin); delete h; return rc; }
+  *out = h;
+  return 0;
+}
+
+extern "C" void b2s_fm_destroy(b2s_fm* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  delete h;
+}
+
+extern "C" long long b2s_fm_launch_count(const b2s_fm* h) { return h ? h->launches : 0; }
+
+extern "C" int b2s_fm_ransac(b2s_fm* h, const float* pts1_dev, const float* pts2_dev, const int32_t* pairs_dev, int n,
+                             float thresh, int n_hyp, uint64_t seed, void* stream, uint8_t* mask_dev, double* F_dev,
+                             int32_t* result_dev) {
+  if (!h || !pts1_dev || !pts2_dev || !mask_dev || !F_dev || !result_dev) { set_error("b2s_fm_ransac: null argument"); return B2S_EINVAL; }
+  if (n < 7) { set_error("b2s_fm_ransac: need at least 7 correspondences, got %d", n); return B2S_EINVAL; }
+  if (n > h->max_pts || n_hyp > h->max_hyp || n_hyp < 1) { set_error("b2s_fm_ransac: n=%d / n_hyp=%d exceed the handle (%d / %d)", n, n_hyp, h->max_pts, h->max_hyp); return B2S_ESIZE; }
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  FmParams p;
+  p.pts1 = pts1_dev; p.pts2 = pts2_dev; p.pairs = pairs_dev; p.n = n; p.n_hyp = n_hyp; p.seed = seed;
+  p.thresh2 = (double)thresh * (double)thresh;
+  p.xy = h->xy; p.norm = h->norm; p.models = h->models; p.nmodels = h->nmodels; p.counts = h->counts;
+  p.mask = mask_dev; p.F = F_dev; p.result = result_dev;
+  launch_k(k_fm_prepare, dim3(1), dim3(256), 0, st, p);
+  launch_k(k_fm_hypotheses, dim3(cdiv(n_hyp, 64)), dim3(64), 0, st, p);
+  launch_k(k_fm_score, dim3(n_hyp), dim3(128), 0, st, p);
+  launch_k(k_fm_select, dim3(1), dim3(256), 0, st, p);
+  h->launches += 4;
+  B2S_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b2s_fm_ransac_host(b2s_fm* h, const float* pts1, const float* pts2, int n, float thresh, int n_hyp,
+                                  uint64_t seed, uint8_t* mask, double* F, int32_t* n_inliers, int32_t* model_index) {
+  if (!h || !pts1 || !pts2 || !mask) { set_error("b2s_fm_ransac_host: null argument"); return B2S_EINVAL; }
+  if (n > h->max_pts) { set_error("b2s_fm_ransac_host: n=%d exceeds the handle (%d)", n, h->max_pts); return B2S_ESIZE; }
+  B2S_CUDA(cudaSetDevice(h->device));
+  B2S_CUDA(cudaMemcpyAsync(h->d_pts1, pts1, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  B2S_CUDA(cudaMemcpyAsync(h->d_pts2, pts2, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  B2S_TRY(b2s_fm_ransac(h, h->d_pts1, h->d_pts2, nullptr, n, thresh, n_hyp, seed, h->stream, h->d_mask, h->d_F, h->d_res));
+  uint8_t* pm = h->h_pin;                                           // pinned: mask | 9 doubles | 2 int32
+  const size_t off = ((size_t)h->max_pts + 15) & ~(size_t)15;
+  double* hF = reinterpret_cast<double*>(pm + off);
+  int32_t* hres = reinterpret_cast<int32_t*>(pm + off + 9 * sizeof(double));
+  B2S_CUDA(cudaMemcpyAsync(pm, h->d_mask, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  B2S_CUDA(cudaMemcpyAsync(hF, h->d_F, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  B2S_CUDA(cudaMemcpyAsync(hres, h->d_res, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  B2S_CUDA(cudaStreamSynchronize(h->stream));
+  std::memcpy(mask, pm, (size_t)n);
+  if (F) std::memcpy(F, hF, 9 * sizeof(double));
+  if (n_inliers) *n_inliers = hres[0];
+  if (model_index) *model_index = hres[1];
+  return 0;
+}
+
+// test hook: the de-normalised candidate models of hypothesis `hyp` of the most recent call (host copy)
+extern "C" int b2s_fm_debug_models(b2s_fm* h, int hyp, double* models27, int32_t* n_models, int32_t* counts3) {
+  if (!h || hyp < 0 || hyp >= h->max_hyp) { set_error("b2s_fm_debug_models: bad hypothesis index"); return B2S_EINVAL; }
+  B2S_CUDA(cudaSetDevice(h->device));
+  B2S_CUDA(cudaDeviceSynchronize());
+  if (models27) B2S_CUDA(cudaMemcpy(models27, h->models + (size_t)hyp * 27, 27 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (n_models) B2S_CUDA(cudaMemcpy(n_models, h->nmodels + hyp, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (counts3) B2S_CUDA(cudaMemcpy(counts3, h->counts + (size_t)hyp * 3, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// remap
+// ---------------------------------------------------------------------------------------------------------------
+struct b2s_remap {
+  int device = 0, sH = 0, sW = 0, dH = 0, dW = 0;
+  DeviceArena arena;
+  float *mapx = nullptr, *mapy = nullptr; int16_t* wtab = nullptr;
+  uint8_t *src = nullptr, *dst = nullptr;     // staging for the host API / output frame (dstride = 3*dW)
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+};
+
+namespace {
+// OpenCV's initInterTab2D(INTER_LINEAR, fixpt): 32x32 sub-pixel positions, four float weights each, rounded to 15-bit
+// integers whose sum is forced to 32768 by adjusting the largest (sum too big) or smallest (too small) entry.
+void build_weight_table(std::vector<int16_t>& t) {
+  t.resize(1024 * 4);
+  for (int i = 0; i < 32; ++i)
+    for (int j = 0; j < 32; ++j) {
+      const float vy[2] = {1.f - (float)i * (1.f / 32.f), (float)i * (1.f / 32.f)};
+      const float vx[2] = {1.f - (float)j * (1.f / 32.f), (float)j * (1.f / 32.f)};
+      int it[4], sum = 0;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          const float v = vy[a] * vx[b];
+          long r = std::lrintf(v * 32768.f);
+          if (r > 32767) r = 32767;
+          if (r < -32768) r = -32768;
+          it[a * 2 + b] = (int)r; sum += (int)r;
+        }
+      if (sum != 32768) {
+        const int d = 32768 - sum;
+        int k = 0;
+        for (int q = 1; q < 4; ++q)
+          if (d < 0 ? it[q] > it[k] : it[q] < it[k]) k = q;
+        it[k] += d;
+      }
+      for (int q = 0; q < 4; ++q) t[(i * 32 + j) * 4 + q] = (int16_t)it[q];
+    }
+}
+}  // namespace
+
+extern "C" int b2s_remap_create(int device, const float* mapx_host, const float* mapy_host, int dst_h, int dst_w, int src_h,
+                                int src_w, b2s_remap** out) {
+  if (!out || !mapx_host || !mapy_host || dst_h < 1 || dst_w < 1 || src_h < 1 || src_w < 1) { set_error("b2s_remap_create: bad arguments"); return B2S_EINVAL; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    set_error("b2s_remap_create: no CUDA device %d (there is no CPU fallback)", device);
+    return B2S_ENODEV;
+  }
+  B2S_CUDA(cudaSetDevice(device));
+  b2s_remap* h = new b2s_remap();
+  h->device = device; h->sH = src_h; h->sW = src_w; h->dH = dst_h; h->dW = dst_w;
+  std::vector<int16_t> tab;
+  build_weight_table(tab);
+  int rc = 0;
+  auto A = [&](int r) { if (rc == 0) rc = r; };
+  A(h->arena.alloc(&h->mapx, (size_t)dst_h * dst_w));
+  A(h->arena.alloc(&h->mapy, (size_t)dst_h * dst_w));
+  A(h->arena.upload(&h->wtab, tab));
+  A(h->arena.alloc(&h->src, (size_t)src_h * src_w * 3));
+  A(h->arena.alloc(&h->dst, (size_t)dst_h * dst_w * 3));
+  if (rc == 0 && cudaMemcpy(h->mapx, mapx_host, (size_t)dst_h * dst_w * 4, cudaMemcpyHostToDevice) != cudaSuccess) rc = B2S_ECUDA;
+  if (rc == 0 && cudaMemcpy(h->mapy, mapy_host, (size_t)dst_h * dst_w * 4, cudaMemcpyHostToDevice) != cudaSuccess) rc = B2S_ECUDA;
+  if (rc == 0 && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) rc = B2S_ECUDA;
+  if (rc != 0) { if (rc == B2S_ECUDA) set_error("b2s_remap_create: %s", cudaGetErrorString(cudaGetLastError())); delete h; return rc; }
+  *out = h;
+  return 0;
+}
+
+extern "C" void b2s_remap_destroy(b2s_remap* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" void b2s_remap_dims(const b2s_remap* h, int* dst_h, int* dst_w, int* src_h, int* src_w) {
+  if (dst_h) *dst_h = h ? h->dH : 0;
+  if (dst_w) *dst_w = h ? h->dW : 0;
+  if (src_h) *src_h = h ? h->sH : 0;
+  if (src_w) *src_w = h ? h->sW : 0;
+}
+
+extern "C" long long b2s_remap_launch_count(const b2s_remap* h) { return h ? h->launches : 0; }
+
+extern "C" int b2s_remap_bgr(b2s_remap* h, const uint8_t* src_dev, int src_stride, void* stream, uint8_t* dst_dev, int dst_stride) {
+  if (!h || !src_dev || !dst_dev) { set_error("b2s_remap_bgr: null argument"); return B2S_EINVAL; }
+  if (src_stride < 3 * h->sW || dst_stride < 3 * h->dW) { set_error("b2s_remap_bgr: stride smaller than a row"); return B2S_EINVAL; }
+  B2S_CUDA(cudaSetDevice(h->device));
+  RemapParams p;
+  p.src = src_dev; p.sH = h->sH; p.sW = h->sW; p.sstride = src_stride;
+  p.mapx = h->mapx; p.mapy = h->mapy; p.dH = h->dH; p.dW = h->dW; p.wtab = h->wtab; p.dst = dst_dev; p.dstride = dst_stride;
+  launch_k(k_remap_bgr_u8, dim3(cdiv(h->dW, 256), h->dH), dim3(256), 0, (cudaStream_t)stream, p);
+  h->launches += 1;
+  B2S_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b2s_remap_bgr_host(b2s_remap* h, const uint8_t* src, int src_stride, uint8_t* dst, int dst_stride) {
+  if (!h || !src || !dst) { set_error("b2s_remap_bgr_host: null argument"); return B2S_EINVAL; }
+  if (src_stride < 3 * h->sW || dst_stride < 3 * h->dW) { set_error("b2s_remap_bgr_host: stride smaller than a row"); return B2S_EINVAL; }
+  B2S_CUDA(cudaSetDevice(h->device));
+  B2S_CUDA(cudaMemcpy2DAsync(h->src, (size_t)3 * h->sW, src, (size_t)src_stride, (size_t)3 * h->sW, h->sH, cudaMemcpyHostToDevice, h->stream));
+  B2S_TRY(b2s_remap_bgr(h, h->src, 3 * h->sW, h->stream, h->dst, 3 * h->dW));
+  B2S_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_stride, h->dst, (size_t)3 * h->dW, (size_t)3 * h->dW, h->dH, cudaMemcpyDeviceToHost, h->stream));
+  B2S_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// the handle's own undistorted device frame ([dst_h][dst_w][3] u8, packed) - what b2s_aliked_extract consumes when the
+// frame never has to come back to the host
+extern "C" const uint8_t* b2s_remap_output_dev(const b2s_remap* h) { return h ? h->dst : nullptr; }

@@ -21,6 +21,7 @@ import cv2
 import numpy as np
 import torch
 
+from . import geometry as _geometry
 from .containers import DMatchArray, KeyPointArray
 from .frontend import ALIKED, LightGlue, rbd  # noqa: F401  (re-exported like the reference's imports)
 
@@ -131,17 +132,40 @@ def feature_matcher(args, kp0, kp1, des0, des1, matcher):
     return sorted(matches, key=lambda m: m.distance)
 
 
+def _match_points(kp1, kp2, matches):
+    """The two [K,2] float32 coordinate arrays `np.float32([kp[m.idx].pt for m in matches])` (features_utils.py:191-192)."""
+    if isinstance(matches, DMatchArray):
+        qi, ti = matches.queryIdx, matches.trainIdx
+    else:
+        qi = np.fromiter((m.queryIdx for m in matches), np.intp, len(matches))
+        ti = np.fromiter((m.trainIdx for m in matches), np.intp, len(matches))
+    return _kps_to_array(kp1)[qi], _kps_to_array(kp2)[ti]
+
+
 def filter_matches_ransac(kp1, kp2, matches, thresh=1.0):
-    """Drop outliers with a fundamental-matrix RANSAC (features_utils.py:185-200; CPU, cv2)."""
+    """Drop outliers with a fundamental-matrix RANSAC (features_utils.py:185-200).  The reference's
+    `cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC, thresh, 0.99)` is replaced by the parallel 7-point RANSAC of
+    libb200slam.so (geometry.FundamentalRansac: 2048 samples scored at once, same error measure and threshold)."""
     if len(matches) < 8:
         return matches
-    if isinstance(matches, DMatchArray) and isinstance(kp1, KeyPointArray) and isinstance(kp2, KeyPointArray):
-        pts1, pts2 = kp1.pts[matches.queryIdx], kp2.pts[matches.trainIdx]
-        _, mask = cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC, thresh, 0.99)
+    pts1, pts2 = _match_points(kp1, kp2, matches)
+    _, mask = _geometry.find_fundamental_mat(pts1, pts2, thresh)
+    if isinstance(matches, DMatchArray):
         return DMatchArray(matches.pairs[:0]) if mask is None else matches[mask.ravel().astype(bool)]
-    pts1 = np.float32([kp1[m.queryIdx].pt for m in matches])
-    pts2 = np.float32([kp2[m.trainIdx].pt for m in matches])
+    if mask is None:
+        return []
+    mask = mask.ravel().astype(bool)
+    return [m for m, ok in zip(matches, mask) if ok]
+
+
+def filter_matches_ransac_cv2(kp1, kp2, matches, thresh=1.0):
+    """The reference's own body (cv2.findFundamentalMat on the host) - kept for side-by-side comparisons in tests / tools."""
+    if len(matches) < 8:
+        return matches
+    pts1, pts2 = _match_points(kp1, kp2, matches)
     _, mask = cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC, thresh, 0.99)
+    if isinstance(matches, DMatchArray):
+        return DMatchArray(matches.pairs[:0]) if mask is None else matches[mask.ravel().astype(bool)]
     if mask is None:
         return []
     mask = mask.ravel().astype(bool)

@@ -94,6 +94,7 @@ class ALIKED(_Module):
         h = C.c_void_p()
         check(lib.b2s_aliked_create(C.byref(cfg), self._blob, len(self._blob), dev.index, C.byref(h)), "b2s_aliked_create")
         self._handle, self.device = h, dev
+        self._undistorter = None
         self._param = torch.empty(1, device=dev)
         with torch.cuda.device(dev):
             self._kp = torch.empty((self.n_limit, 2), dtype=torch.float32, device=dev)
@@ -106,6 +107,17 @@ class ALIKED(_Module):
         if getattr(self, "_handle", None):
             lib.b2s_aliked_destroy(self._handle)
             self._handle = None
+
+    def set_undistort(self, undistorter=None):
+        """Attach a `geometry.FrameUndistorter` (or None): `extract_host*` / `feature_extractor` then take the RAW frame
+        and run the reference's `cv2.remap(img, mapx, mapy, INTER_LINEAR)` (main_revamped.py:323-324) on the device in
+        front of the extractor - one upload, no host round trip.  Keypoints are in undistorted-image pixels."""
+        if undistorter is not None and undistorter.device_index != self.device.index:
+            raise ValueError("the undistorter lives on another device")
+        check(lib.b2s_aliked_set_undistort(self._handle, undistorter._handle if undistorter is not None else None),
+              "b2s_aliked_set_undistort")
+        self._undistorter = undistorter            # keep the borrowed handle alive
+        return self
 
     # -- device-resident entry: enqueue on the current stream, outputs stay on the GPU -------
     def extract_device(self, img: torch.Tensor, fmt: int, H: int, W: int, row_stride: int = 0):

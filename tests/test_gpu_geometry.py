@@ -1,0 +1,173 @@
+"""GPU: the rows behind the matcher through the C ABI - fundamental-matrix RANSAC against the numpy
+restatement (same seed: same winning sample, same mask), against cv2.findFundamentalMat (the reference's call,
+features_utils.py:193-194) and against ground truth; cv2.remap bit-exactness; ingest fused in front of the extractor."""
+from types import SimpleNamespace
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ransac():
+    from b200slam.geometry import FundamentalRansac
+    return FundamentalRansac(max_points=4096, n_hyp=2048, seed=0)
+
+
+def _same_model(Fa, Fb, tol=1e-7):
+    Fa, Fb = Fa / np.linalg.norm(Fa), Fb / np.linalg.norm(Fb)
+    return min(np.abs(Fa - Fb).max(), np.abs(Fa + Fb).max()) < tol
+
+
+@pytest.mark.parametrize("n,frac,noise,seed", [(800, 0.3, 0.3, 1), (64, 0.2, 0.2, 3), (2048, 0.5, 0.5, 2)])
+def test_ransac_matches_restatement(ransac, n, frac, noise, seed):
+    """Same samples, same candidate models, same winner and mask as oracle/geometry.py (float64 both sides)."""
+    from b200slam.geometry import FundamentalRansac
+    p1, p2, _ = G.two_view_scene(n, frac, noise, seed)
+    H = 96
+    r = FundamentalRansac(max_points=4096, n_hyp=H, seed=7)
+    F, mask = r.run_host(p1, p2, 1.0)
+    Fo, mo, cnt_o, h_o = G.fm_ransac(p1, p2, 1.0, H, seed=7)
+    # per-sample candidate sets (the solver): every oracle model appears among the device's and vice versa
+    for h in (0, 1, 2, 17, H - 1):
+        dm, dc = r.debug_models(h)
+        om = G.hypothesis_models(p1, p2, 7, h)
+        assert len(dm) == len(om)
+        for Fm, c in zip(dm, dc):
+            assert any(_same_model(Fm, Fq) for Fq in om)
+            err = G.fm_error(Fm, p1, p2)
+            assert abs(int((err <= 1.0).sum()) - int(c)) <= int((np.abs(err - 1.0) < 1e-9).sum())
+    assert r.last_model_index // 3 == h_o and r.last_count == cnt_o
+    assert _same_model(F, Fo)
+    border = np.abs(G.fm_error(Fo, p1, p2) - 1.0) < 1e-9
+    assert (mask.ravel() == mo)[~border].all() and int(mask.sum()) == r.last_count
+
+
+@pytest.mark.parametrize("n,frac,noise,seed", [(800, 0.3, 0.15, 1), (1500, 0.5, 0.3, 2), (300, 0.6, 0.2, 5), (2048, 0.2, 0.1, 8)])
+def test_ransac_against_cv2_and_ground_truth(ransac, n, frac, noise, seed):
+    p1, p2, gt = G.two_view_scene(n, frac, noise, seed)
+    F, mask = ransac.run_host(p1, p2, 1.0)
+    m = mask.ravel().astype(bool)
+    _, mc = cv2.findFundamentalMat(p1, p2, cv2.FM_RANSAC, 1.0, 0.99)
+    mc = mc.ravel().astype(bool)
+    assert mask.shape == (n, 1) and mask.dtype == np.uint8 and F.shape == (3, 3)
+    assert m.sum() >= 0.98 * mc.sum(), "consensus smaller than cv2's"
+    assert (m & gt).sum() >= 0.97 * m.sum(), "false inliers"
+    assert (m & gt).sum() >= (mc & gt).sum() - 0.02 * gt.sum(), "recall below cv2's"
+    # properties of the returned model: rank 2, every flagged pair within the threshold, nothing else
+    err = G.fm_error(F, p1, p2)
+    assert abs(np.linalg.det(F / np.linalg.norm(F))) < 1e-9
+    assert (err[m] <= 1.0 + 1e-9).all() and (err[~m] > 1.0 - 1e-9).all()
+
+
+def test_ransac_low_noise_overlap_with_cv2(ransac):
+    p1, p2, gt = G.two_view_scene(1200, 0.3, 0.05, 4)
+    _, mask = ransac.run_host(p1, p2, 1.0)
+    _, mc = cv2.findFundamentalMat(p1, p2, cv2.FM_RANSAC, 1.0, 0.99)
+    m, mc = mask.ravel().astype(bool), mc.ravel().astype(bool)
+    assert (m & mc).sum() / (m | mc).sum() >= 0.97
+    assert (m == gt).mean() >= 0.99
+
+
+def test_ransac_device_resident_pairs(ransac):
+    """pairs_dev indirection (the matcher's device `matches` feed RANSAC without a host round trip)."""
+    p1, p2, _ = G.two_view_scene(700, 0.3, 0.2, 9)
+    rng = np.random.default_rng(0)
+    perm1, perm2 = rng.permutation(900), rng.permutation(900)
+    k0 = np.zeros((900, 2), np.float32); k1 = np.zeros((900, 2), np.float32)
+    k0[perm1[:700]] = p1; k1[perm2[:700]] = p2
+    pairs = np.stack([perm1[:700], perm2[:700]], axis=1).astype(np.int32)
+    mask_d, F_d, res_d = ransac.run_device(torch.from_numpy(k0).cuda(), torch.from_numpy(k1).cuda(),
+                                           torch.from_numpy(pairs).cuda(), 700, 1.0)
+    torch.cuda.synchronize()
+    F, mask = ransac.run_host(p1, p2, 1.0)
+    assert np.array_equal(mask_d.cpu().numpy(), mask.ravel()) and int(res_d[0]) == int(mask.sum())
+    assert np.allclose(F_d.cpu().numpy().reshape(3, 3), F, atol=0, rtol=0)
+
+
+def test_ransac_edge_cases(ransac):
+    from b200slam import features_utils as fu
+    kps = [cv2.KeyPoint(float(3 * i), float(i % 11), 1) for i in range(30)]
+    ms = [cv2.DMatch(i, i, 0.0) for i in range(30)]
+    assert fu.filter_matches_ransac(kps, kps, ms[:7], 1.0) == ms[:7]          # < 8: unchanged (reference :188-189)
+    assert ransac.run_host(np.zeros((5, 2), np.float32), np.zeros((5, 2), np.float32)) == (None, None)
+    # every correspondence identical -> every sample degenerate -> no model -> reference returns [] (mask is None)
+    same = [cv2.KeyPoint(5.0, 5.0, 1)] * 30
+    assert fu.filter_matches_ransac(same, same, ms, 1.0) == []
+    # pure translation of a planar grid is consistent with many F: whatever is returned must satisfy its own mask
+    out = fu.filter_matches_ransac(kps, kps, ms, 1.0)
+    assert isinstance(out, list) and all(isinstance(m, cv2.DMatch) for m in out)
+    # growth beyond the handle's capacity
+    p1, p2, _ = G.two_view_scene(5000, 0.1, 0.1, 12)
+    F, mask = ransac.run_host(p1, p2, 1.0)
+    assert mask.sum() >= 0.85 * 4500 and ransac.max_points >= 5000
+
+
+def test_filter_matches_ransac_drop_in(ransac):
+    """Same signature / return type as the reference; array-native containers keep their type."""
+    from b200slam import features_utils as fu
+    from b200slam.containers import DMatchArray, KeyPointArray
+    p1, p2, gt = G.two_view_scene(600, 0.3, 0.15, 21)
+    kp1 = [cv2.KeyPoint(float(x), float(y), 1) for x, y in p1]
+    kp2 = [cv2.KeyPoint(float(x), float(y), 1) for x, y in p2]
+    ms = [cv2.DMatch(i, i, 0.0) for i in range(600)]
+    out = fu.filter_matches_ransac(kp1, kp2, ms, 1.0)
+    ref = fu.filter_matches_ransac_cv2(kp1, kp2, ms, 1.0)
+    assert isinstance(out, list) and isinstance(out[0], cv2.DMatch)
+    so, sr = {m.queryIdx for m in out}, {m.queryIdx for m in ref}
+    assert len(so) >= 0.98 * len(sr) and len(so & sr) / len(so | sr) >= 0.9
+    assert np.mean([gt[i] for i in so]) >= 0.97
+    out_a = fu.filter_matches_ransac(KeyPointArray(p1), KeyPointArray(p2), DMatchArray(np.stack([np.arange(600)] * 2, 1)), 1.0)
+    assert isinstance(out_a, DMatchArray) and set(out_a.queryIdx.tolist()) == so
+
+
+def _kitti_maps(W=1241, H=376):
+    K = np.array([[718.856, 0, 607.19], [0, 718.856, 185.2], [0, 0, 1.0]])
+    D = np.array([-0.28, 0.07, 0.0002, 0.0001, 0.0])
+    nK, _ = cv2.getOptimalNewCameraMatrix(K, D, (W, H), alpha=0, newImgSize=(W, H))
+    return cv2.initUndistortRectifyMap(K, D, None, nK, (W, H), cv2.CV_32FC1)
+
+
+def test_remap_bit_exact_with_cv2():
+    from b200slam import synth
+    from b200slam.geometry import FrameUndistorter
+    img = synth.frame(3, 376, 1241)
+    mx, my = _kitti_maps()
+    und = FrameUndistorter(mx, my)
+    out = und.remap(img)
+    assert np.array_equal(out, cv2.remap(img, mx, my, cv2.INTER_LINEAR))
+    assert np.array_equal(out, G.remap_bgr_u8(img, mx, my))
+    assert np.array_equal(und.remap_to_device(img).cpu().numpy(), out)
+    # arbitrary maps with out-of-image taps, destination size != source size
+    rng = np.random.default_rng(1)
+    noise = rng.integers(0, 256, (200, 333, 3), dtype=np.uint8)
+    mx2 = rng.random((97, 131), dtype=np.float32) * (333 + 40) - 20
+    my2 = rng.random((97, 131), dtype=np.float32) * (200 + 40) - 20
+    mx2[0, :8] = [-1.0, -0.5, 0.0, 0.015625, 332, 332.5, 333, 5.5]
+    my2[0, :8] = [-1.0, -0.5, 0.0, 0.015625, 199, 199.5, 200, 7.484375]
+    und2 = FrameUndistorter(mx2, my2, src_shape=(200, 333))
+    assert np.array_equal(und2.remap(noise), cv2.remap(noise, mx2, my2, cv2.INTER_LINEAR))
+    with pytest.raises(ValueError):
+        und2.remap(img)
+
+
+def test_ingest_fused_in_front_of_the_extractor(aliked_state):
+    """feature_extractor(raw frame) with an attached undistorter == feature_extractor(cv2.remap(raw frame))."""
+    from b200slam import features_utils as fu, frontend, synth
+    from b200slam.geometry import FrameUndistorter
+    args = SimpleNamespace(use_lightglue=True, max_features=1024)
+    det = frontend.ALIKED(max_num_keypoints=1024, weights=aliked_state)
+    img = synth.frame(5, 376, 1241)
+    mx, my = _kitti_maps()
+    kp_ref, de_ref = fu.feature_extractor(args, cv2.remap(img, mx, my, cv2.INTER_LINEAR), det)
+    det.set_undistort(FrameUndistorter(mx, my))
+    kp, de = fu.feature_extractor(args, img, det)
+    det.set_undistort(None)
+    assert [k.pt for k in kp] == [k.pt for k in kp_ref] and np.array_equal(de, de_ref)
+    kp2, _ = fu.feature_extractor(args, img, det)                  # detached again: the raw frame gives other keypoints
+    assert [k.pt for k in kp2] != [k.pt for k in kp_ref]

@@ -1,0 +1,104 @@
+"""CPU: pins of oracle/geometry.py against the reference's own implementation (OpenCV, which the reference calls at
+slam/monocular/main_revamped.py:313-324 and slam/core/features_utils.py:193-194) and host-side checks of the library
+boundary for the rows behind the matcher."""
+import ctypes as C
+import re
+
+import cv2
+import numpy as np
+
+from oracle import geometry as G
+
+
+def _kitti_maps(W=1241, H=376):
+    K = np.array([[718.856, 0, 607.19], [0, 718.856, 185.2], [0, 0, 1.0]])
+    D = np.array([-0.28, 0.07, 0.0002, 0.0001, 0.0])
+    nK, _ = cv2.getOptimalNewCameraMatrix(K, D, (W, H), alpha=0, newImgSize=(W, H))
+    return cv2.initUndistortRectifyMap(K, D, None, nK, (W, H), cv2.CV_32FC1)
+
+
+def test_remap_restatement_is_bit_exact_with_cv2():
+    rng = np.random.default_rng(0)
+    H, W = 376, 1241
+    src = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    mx, my = _kitti_maps(W, H)
+    assert np.array_equal(cv2.remap(src, mx, my, cv2.INTER_LINEAR), G.remap_bgr_u8(src, mx, my))
+    # arbitrary maps incl. out-of-image taps on every border and exact integer / half positions
+    mx2 = rng.random((97, 131), dtype=np.float32) * (W + 40) - 20
+    my2 = rng.random((97, 131), dtype=np.float32) * (H + 40) - 20
+    mx2[0, :8] = [-1.0, -0.5, 0.0, 0.015625, W - 1, W - 0.5, W, 5.5]
+    my2[0, :8] = [-1.0, -0.5, 0.0, 0.015625, H - 1, H - 0.5, H, 7.484375]
+    assert np.array_equal(cv2.remap(src, mx2, my2, cv2.INTER_LINEAR), G.remap_bgr_u8(src, mx2, my2))
+
+
+def test_remap_weight_table_sums():
+    t = G.remap_weight_table().astype(np.int64)
+    assert t.shape == (1024, 4) and (t.sum(axis=1) == 32768).all() and t[0].tolist() == [32767, 1, 0, 0]   # int16 saturation, as OpenCV
+
+
+def test_seven_point_models_satisfy_their_sample():
+    p1, p2, _ = G.two_view_scene(200, 0.0, 0.0, seed=3)
+    for h in range(20):
+        idx = G.sample_indices(11, h, len(p1))
+        assert len(set(idx)) == 7 and all(0 <= i < len(p1) for i in idx)
+        models = G.hypothesis_models(p1, p2, 11, h)
+        assert 1 <= len(models) <= 3
+        for F in models:
+            assert abs(np.linalg.det(F)) < 1e-9 and abs(np.linalg.norm(F) - 1) < 1e-12
+            assert G.fm_error(F, p1[idx], p2[idx]).max() < 1e-6      # the seven pairs lie on their epipolar lines
+
+
+def test_fm_error_matches_opencv_definition():
+    """computeError of OpenCV's FM estimator, checked through cv2 itself: every point cv2 flags as inlier has
+    error <= thresh^2 under cv2's own F and every other point has a larger one."""
+    p1, p2, _ = G.two_view_scene(600, 0.35, 0.2, seed=5)
+    F, mask = cv2.findFundamentalMat(p1, p2, cv2.FM_RANSAC, 1.0, 0.99)
+    err = G.fm_error(F, p1, p2)
+    m = mask.ravel().astype(bool)
+    border = np.abs(err - 1.0) < 1e-3                  # cv2 evaluates in float32
+    assert ((err <= 1.0) == m)[~border].all()
+
+
+def test_ransac_restatement_against_cv2_and_ground_truth():
+    for n, frac, noise, seed in [(800, 0.3, 0.15, 1), (400, 0.5, 0.2, 2)]:
+        p1, p2, gt = G.two_view_scene(n, frac, noise, seed)
+        F, mask, cnt, h = G.fm_ransac(p1, p2, 1.0, 192, seed=0)
+        m = mask.astype(bool)
+        _, mc = cv2.findFundamentalMat(p1, p2, cv2.FM_RANSAC, 1.0, 0.99)
+        mc = mc.ravel().astype(bool)
+        assert cnt == m.sum() and cnt >= 0.95 * mc.sum()
+        assert (m & gt).sum() >= 0.97 * m.sum()                        # precision against the true inliers
+        assert (m & mc).sum() / (m | mc).sum() >= 0.85                 # overlap with cv2's consensus set
+        assert h >= 0 and abs(np.linalg.det(F)) < 1e-9
+
+
+def test_header_declares_what_the_library_exports():
+    import b200slam._lib as L
+    hdr = open(L._HERE + "/../include/b200slam.h").read()
+    names = set(re.findall(r"\b(b2s_[a-z0-9_]+)\s*\(", hdr))
+    for name in sorted(names):
+        assert hasattr(L.lib, name), f"{name} declared in include/b200slam.h but not exported"
+    for name in ("b2s_fm_create", "b2s_fm_ransac", "b2s_fm_ransac_host", "b2s_remap_create", "b2s_remap_bgr",
+                 "b2s_remap_bgr_host", "b2s_aliked_set_undistort"):
+        assert name in names and name in L.SIGNATURES
+
+
+def test_geometry_handles_fail_loudly_without_a_device():
+    import torch
+    import b200slam._lib as L
+    if torch.cuda.is_available():
+        return
+    h = C.c_void_p()
+    assert L.lib.b2s_fm_create(0, 1024, 256, C.byref(h)) == -4            # B2S_ENODEV
+    assert b"no CPU fallback" in L.lib.b2s_last_error()
+    mx = np.zeros((4, 4), np.float32)
+    assert L.lib.b2s_remap_create(0, mx.ctypes.data, mx.ctypes.data, 4, 4, 4, 4, C.byref(h)) == -4
+    from b200slam import features_utils as fu
+    kps = [cv2.KeyPoint(float(i), float(i % 7), 1) for i in range(20)]
+    ms = [cv2.DMatch(i, i, 0.0) for i in range(20)]
+    assert fu.filter_matches_ransac(kps, kps, ms[:5], 1.0) == ms[:5]      # < 8 matches: returned unchanged (reference :188-189)
+    try:
+        fu.filter_matches_ransac(kps, kps, ms, 1.0)
+        raise AssertionError("expected a RuntimeError without CUDA")
+    except RuntimeError as e:
+        assert "no CPU fallback" in str(e)
