@@ -207,6 +207,27 @@ void b2s_remap_dims(const b2s_remap* h, int* dst_h, int* dst_w, int* src_h, int*
 int b2s_aliked_set_undistort(b2s_aliked* h, b2s_remap* r);
 long long b2s_remap_launch_count(const b2s_remap* h);
 
+/* Projected-landmark window matching.  Replaces the body of `reproject_and_match_2d3d` (pnp_utils.py:224-304, called
+ * once per tracked frame at main_revamped.py:460): project every map point with T_cw, keep those in front of the camera
+ * and inside the image, collect the keypoints within radius_px of the projection (the reference's cKDTree ball query),
+ * score each by the smallest descriptor distance to the point's most recent (<= max_obs, the reference checks 6)
+ * observations, and give every point - in map order, as the reference's loop does - its best keypoint not taken by
+ * an earlier point, if that distance is <= max_dist.
+ *   Xw_dev [P,3] f64 | mp_desc_dev [rows,max_obs,128] f32 | mp_nobs_dev [rows] i32 (0: point skipped, as when the
+ *   reference finds no descriptor) | mp_row_dev (nullable) [P] i32: table row of point i (NULL: row i) | K_host [9] f64 row-major | Tcw_host [16] f64 row-major | kps_dev [N,2] f32 | des_dev [N,128] f32
+ *   distance = L2 between float descriptors (what the reference computes whatever `use_cosine` says: its
+ *   _best_mp_distance_to_cur_desc always passes metric="auto", pnp_utils.py:121)
+ *   kp_of_point_dev [P] i32: matched keypoint index or -1 | uv_dev (nullable) [P,2] f32 projections
+ *   flags_dev (nullable) i32: bit 0 set if a window held more keypoints than the handle's cand_cap (result then unreliable) */
+typedef struct b2s_reproj b2s_reproj;
+int b2s_reproj_create(int device, int max_points, int max_kps, int cand_cap, b2s_reproj** out);
+void b2s_reproj_destroy(b2s_reproj* h);
+int b2s_reproj_match(b2s_reproj* h, const double* Xw_dev, const float* mp_desc_dev, const int32_t* mp_nobs_dev,
+                     const int32_t* mp_row_dev, int P, int max_obs, const double* K_host, const double* Tcw_host, const float* kps_dev,
+                     const float* des_dev, int N, int img_w, int img_h, double radius_px, double max_dist,
+                     void* stream, int32_t* kp_of_point_dev, float* uv_dev, int32_t* flags_dev);
+long long b2s_reproj_launch_count(const b2s_reproj* h);
+
 /* Test hooks: copy a named intermediate of the most recent call to the host (fp32).
  * Returns the number of floats available in *n (and copies min(*n, cap)). */
 int b2s_aliked_debug_get(b2s_aliked* h, const char* name, float* out, size_t cap, size_t* n);

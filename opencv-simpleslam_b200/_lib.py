@@ -81,6 +81,11 @@ SIGNATURES = {
     "b2s_remap_bgr_host": (C.c_int, [vp, vp, C.c_int, vp, C.c_int]),
     "b2s_remap_output_dev": (vp, [vp]),
     "b2s_remap_launch_count": (C.c_longlong, [vp]),
+    "b2s_reproj_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "b2s_reproj_destroy": (None, [vp]),
+    "b2s_reproj_match": (C.c_int, [vp, vp, f32p, i32p, i32p, C.c_int, C.c_int, vp, vp, f32p, f32p, C.c_int, C.c_int, C.c_int,
+                                   C.c_double, C.c_double, vp, i32p, f32p, i32p]),
+    "b2s_reproj_launch_count": (C.c_longlong, [vp]),
     "b2s_remap_dims": (None, [vp, i32p, i32p, i32p, i32p]),
     "b2s_aliked_set_undistort": (C.c_int, [vp, vp]),
 }

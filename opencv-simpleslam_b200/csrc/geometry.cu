@@ -228,3 +228,85 @@ extern "C" int b2s_remap_bgr_host(b2s_remap* h, const uint8_t* src, int src_stri
 // the handle's own undistorted device frame ([dst_h][dst_w][3] u8, packed) - what b2s_aliked_extract consumes when the
 // frame never has to come back to the host
 extern "C" const uint8_t* b2s_remap_output_dev(const b2s_remap* h) { return h ? h->dst : nullptr; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// reproject_and_match_2d3d
+// ---------------------------------------------------------------------------------------------------------------
+struct b2s_reproj {
+  int device = 0, max_pts = 0, max_kps = 0, cap = 0;
+  DeviceArena arena;
+  int32_t *cand_kp = nullptr, *count = nullptr, *pos = nullptr, *flags = nullptr; float *cand_d = nullptr, *uv = nullptr;
+  long long launches = 0;
+};
+
+extern "C" int b2s_reproj_create(int device, int max_points, int max_kps, int cand_cap, b2s_reproj** out) {
+  if (!out || max_points < 1 || max_kps < 1 || cand_cap < 1 || cand_cap > REPROJ_MAXCAP || max_kps > 12000) {
+    set_error("b2s_reproj_create: bad arguments (cand_cap <= %d, max_kps <= 12000)", REPROJ_MAXCAP);
+    return B2S_EINVAL;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    set_error("b2s_reproj_create: no CUDA device %d (there is no CPU fallback)", device);
+    return B2S_ENODEV;
+  }
+  B2S_CUDA(cudaSetDevice(device));
+  b2s_reproj* h = new b2s_reproj();
+  h->device = device; h->max_pts = max_points; h->max_kps = max_kps; h->cap = cand_cap;
+  int rc = 0;
+  auto A = [&](int r) { if (rc == 0) rc = r; };
+  A(h->arena.alloc(&h->cand_kp, (size_t)max_points * cand_cap));
+  A(h->arena.alloc(&h->cand_d, (size_t)max_points * cand_cap));
+  A(h->arena.alloc(&h->count, (size_t)max_points));
+  A(h->arena.alloc(&h->pos, (size_t)max_points));
+  A(h->arena.alloc(&h->uv, (size_t)max_points * 2));
+  A(h->arena.alloc(&h->flags, 1));
+  if (rc == 0 && max_kps * sizeof(int) > 48 * 1024 &&
+      cudaFuncSetAttribute(k_reproj_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, max_kps * (int)sizeof(int)) != cudaSuccess) {
+    set_error("b2s_reproj_create: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = B2S_ECUDA;
+  }
+  if (rc != 0) { delete h; return rc; }
+  *out = h;
+  return 0;
+}
+
+extern "C" void b2s_reproj_destroy(b2s_reproj* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  delete h;
+}
+
+extern "C" long long b2s_reproj_launch_count(const b2s_reproj* h) { return h ? h->launches : 0; }
+
+extern "C" int b2s_reproj_match(b2s_reproj* h, const double* Xw_dev, const float* mp_desc_dev, const int32_t* mp_nobs_dev,
+                                const int32_t* mp_row_dev, int P, int max_obs, const double* K_host, const double* Tcw_host, const float* kps_dev,
+                                const float* des_dev, int N, int img_w, int img_h, double radius_px, double max_dist,
+                                void* stream, int32_t* kp_of_point_dev, float* uv_dev, int32_t* flags_dev) {
+  if (!h || !Xw_dev || !mp_desc_dev || !mp_nobs_dev || !K_host || !Tcw_host || !kps_dev || !des_dev || !kp_of_point_dev) {
+    set_error("b2s_reproj_match: null argument");
+    return B2S_EINVAL;
+  }
+  if (P < 1 || N < 1 || max_obs < 1) { set_error("b2s_reproj_match: bad sizes (P=%d N=%d max_obs=%d)", P, N, max_obs); return B2S_EINVAL; }
+  if (P > h->max_pts || N > h->max_kps) { set_error("b2s_reproj_match: P=%d / N=%d exceed the handle (%d / %d)", P, N, h->max_pts, h->max_kps); return B2S_ESIZE; }
+  B2S_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  ReprojParams p;
+  p.Xw = Xw_dev; p.mp_desc = mp_desc_dev; p.mp_nobs = mp_nobs_dev; p.mp_row = mp_row_dev; p.P = P; p.max_obs = max_obs;
+  for (int i = 0; i < 9; ++i) p.K[i] = K_host[i];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) p.R[3 * r + c] = Tcw_host[4 * r + c];
+    p.t[r] = Tcw_host[4 * r + 3];
+  }
+  p.kps = kps_dev; p.des = des_dev; p.N = N; p.cap = h->cap;
+  p.img_w = (float)img_w; p.img_h = (float)img_h;
+  p.radius2 = radius_px * radius_px; p.thr = max_dist;
+  p.cand_kp = h->cand_kp; p.cand_d = h->cand_d; p.count = h->count; p.pos = h->pos;
+  p.uv = uv_dev ? uv_dev : h->uv; p.out_kp = kp_of_point_dev; p.flags = flags_dev ? flags_dev : h->flags;
+  B2S_CUDA(cudaMemsetAsync(p.flags, 0, sizeof(int32_t), st));
+  launch_k(k_reproj_candidates, dim3(cdiv(P, REPROJ_WARPS)), dim3(32 * REPROJ_WARPS), 0, st, p);
+  launch_k(k_reproj_assign, dim3(1), dim3(1024), (size_t)N * sizeof(int), st, p);
+  h->launches += 2;
+  B2S_LAUNCH_CHECK();
+  return 0;
+}

@@ -361,6 +361,134 @@ __global__ void __launch_bounds__(256) k_remap_bgr_u8(RemapParams p) {
     d[c] = (uint8_t)max(0, min(255, v));
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// reproject_and_match_2d3d (pnp_utils.py:224-304): for every map point, project with the predicted pose, collect the
+// keypoints within radius_px of the projection, and score each by the smallest descriptor distance to the point's
+// last (<= 6) observations.  The reference then walks the points in order and gives each its best not-yet-used
+// keypoint if that distance is within the threshold; k_reproj_assign reproduces that order-dependent greedy result
+// with a parallel fixpoint (a claim is lost only to a smaller point index, exactly the points processed earlier).
+// ---------------------------------------------------------------------------------------------------------------
+struct ReprojParams {
+  const double* Xw;          // [P,3] world positions
+  const float* mp_desc;      // [P,max_obs,128] descriptors of the most recent observations (oldest first)
+  const int32_t* mp_nobs;    // [P] usable descriptors (0: the reference skips the point)
+  const int32_t* mp_row;     // nullable [P]: descriptors / counts of point i live in table row mp_row[i] (else row i)
+  int P, max_obs;
+  double K[9], R[9], t[3];   // intrinsics, T_cw rotation / translation
+  const float* kps;          // [N,2]
+  const float* des;          // [N,128]
+  int N, cap;
+  float img_w, img_h;
+  double radius2, thr;
+  int32_t* cand_kp;          // [P,cap] keypoint indices, ascending distance
+  float* cand_d;             // [P,cap]
+  int32_t* count;            // [P]
+  int32_t* pos;              // [P] scratch of the assignment fixpoint
+  float* uv;                 // [P,2] projections (float32 like the reference's uv_all), (-1,-1) behind the camera
+  int32_t* out_kp;           // [P] assigned keypoint or -1
+  int32_t* flags;            // [0] != 0: some point had more than `cap` keypoints in its window
+};
+
+constexpr int REPROJ_WARPS = 8, REPROJ_MAXCAP = 64;
+
+__global__ void __launch_bounds__(32 * REPROJ_WARPS) k_reproj_candidates(ReprojParams p) {
+  pdl_wait();
+  __shared__ int s_kp[REPROJ_WARPS][REPROJ_MAXCAP];
+  __shared__ float s_d[REPROJ_WARPS][REPROJ_MAXCAP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pt = blockIdx.x * REPROJ_WARPS + warp;
+  if (pt >= p.P) return;
+  const double X = p.Xw[3 * pt], Y = p.Xw[3 * pt + 1], Z = p.Xw[3 * pt + 2];
+  const double xc = X * p.R[0] + Y * p.R[1] + Z * p.R[2] + p.t[0];
+  const double yc = X * p.R[3] + Y * p.R[4] + Z * p.R[5] + p.t[1];
+  const double zc = X * p.R[6] + Y * p.R[7] + Z * p.R[8] + p.t[2];
+  float u = -1.f, v = -1.f;
+  if (zc > 1e-8) {
+    const double xn = xc / zc, yn = yc / zc, zn = zc / zc;
+    u = (float)(p.K[0] * xn + p.K[1] * yn + p.K[2] * zn);
+    v = (float)(p.K[3] * xn + p.K[4] * yn + p.K[5] * zn);
+  }
+  if (lane == 0) { p.uv[2 * pt] = u; p.uv[2 * pt + 1] = v; }
+  const int row = p.mp_row ? p.mp_row[pt] : pt;
+  const int nobs = p.mp_nobs[row];
+  const bool live = zc > 0.0 && u >= 0.f && u < p.img_w && v >= 0.f && v < p.img_h && nobs > 0;
+  if (!live) { if (lane == 0) p.count[pt] = 0; return; }
+  const float* mpd = p.mp_desc + (size_t)row * p.max_obs * 128;
+  int cnt = 0;
+  for (int base = 0; base < p.N; base += 32) {
+    const int i = base + lane;
+    bool in = false;
+    if (i < p.N) {
+      const double dx = (double)p.kps[2 * i] - (double)u, dy = (double)p.kps[2 * i + 1] - (double)v;
+      in = dx * dx + dy * dy <= p.radius2;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, in);
+    while (m) {
+      const int j = base + __ffs(m) - 1;
+      m &= m - 1;
+      const float4 b = reinterpret_cast<const float4*>(p.des + (size_t)j * 128)[lane];
+      float best = INFINITY;
+      for (int o = 0; o < nobs; ++o) {
+        const float4 a = reinterpret_cast<const float4*>(mpd + (size_t)o * 128)[lane];
+        const float e0 = a.x - b.x, e1 = a.y - b.y, e2 = a.z - b.z, e3 = a.w - b.w;
+        const float d = sqrtf(warp_sum(fmaf(e3, e3, fmaf(e2, e2, fmaf(e1, e1, e0 * e0)))));
+        best = fminf(best, d);
+      }
+      if (cnt < p.cap && lane == 0) { s_kp[warp][cnt] = j; s_d[warp][cnt] = best; }
+      ++cnt;
+    }
+  }
+  __syncwarp();
+  if (cnt > p.cap) { if (lane == 0) atomicOr(p.flags, 1); cnt = p.cap; }
+  // rank sort by (distance, keypoint index); the list is already ascending in the index
+  for (int e = lane; e < cnt; e += 32) {
+    const float d = s_d[warp][e];
+    int rank = 0;
+    for (int q = 0; q < cnt; ++q) {
+      const float dq = s_d[warp][q];
+      rank += (dq < d || (dq == d && q < e)) ? 1 : 0;
+    }
+    p.cand_kp[(size_t)pt * p.cap + rank] = s_kp[warp][e];
+    p.cand_d[(size_t)pt * p.cap + rank] = d;
+  }
+  if (lane == 0) p.count[pt] = cnt;
+}
+
+// one CTA; dynamic smem: owner[N]
+__global__ void __launch_bounds__(1024) k_reproj_assign(ReprojParams p) {
+  pdl_wait();
+  extern __shared__ int owner[];
+  __shared__ int changed;
+  const int tid = threadIdx.x;
+  for (int q = tid; q < p.P; q += 1024) p.pos[q] = 0;
+  for (;;) {   // every round but the last advances at least one point; total advances <= sum(count)
+    for (int i = tid; i < p.N; i += 1024) owner[i] = 0x7fffffff;
+    if (tid == 0) changed = 0;
+    __syncthreads();
+    for (int q = tid; q < p.P; q += 1024) {
+      const int ps = p.pos[q];
+      if (ps < p.count[q] && (double)p.cand_d[(size_t)q * p.cap + ps] <= p.thr) atomicMin(&owner[p.cand_kp[(size_t)q * p.cap + ps]], q);
+    }
+    __syncthreads();
+    for (int q = tid; q < p.P; q += 1024) {
+      const int ps = p.pos[q];
+      if (ps < p.count[q] && (double)p.cand_d[(size_t)q * p.cap + ps] <= p.thr && owner[p.cand_kp[(size_t)q * p.cap + ps]] != q) {
+        p.pos[q] = ps + 1;
+        changed = 1;
+      }
+    }
+    __syncthreads();
+    const int c = changed;
+    __syncthreads();
+    if (!c) break;
+  }
+  for (int q = tid; q < p.P; q += 1024) {
+    const int ps = p.pos[q];
+    const bool ok = ps < p.count[q] && (double)p.cand_d[(size_t)q * p.cap + ps] <= p.thr;
+    p.out_kp[q] = ok ? p.cand_kp[(size_t)q * p.cap + ps] : -1;
+  }
+}
 #endif  // __CUDACC__
 
 }  // namespace b2s

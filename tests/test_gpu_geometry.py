@@ -171,3 +171,75 @@ def test_ingest_fused_in_front_of_the_extractor(aliked_state):
     assert [k.pt for k in kp] == [k.pt for k in kp_ref] and np.array_equal(de, de_ref)
     kp2, _ = fu.feature_extractor(args, img, det)                  # detached again: the raw frame gives other keypoints
     assert [k.pt for k in kp2] != [k.pt for k in kp_ref]
+
+
+# ---- reproject_and_match_2d3d (pnp_utils.py:224-304) -------------------------------------------------------------
+def _golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "pnp_reproj.npz"))
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_reproject_and_match_against_reference_fixture(case):
+    """Identical landmark ids / keypoint indices / coordinates as the reference's own function (committed fixture)
+    and as the numpy restatement on the same seeded scene."""
+    from b200slam import pnp_utils as P
+    from oracle import pnp as O
+    g = _golden()
+    n_points, n_kps, seed, radius, max_l2, cosine = g[f"c{case}_cfg"].tolist()
+    wm, K, Tcw, kps, des = O.tracking_scene(int(n_points), int(n_kps), int(seed))
+    r = P.reproject_and_match_2d3d(wm, K, Tcw, kps, des, 1241, 376, radius_px=radius, max_l2=max_l2, use_cosine=bool(cosine))
+    assert isinstance(r, P.Matches2D3D) and r.pts3d.dtype == np.float32 and r.pts2d.dtype == np.float32
+    assert r.mp_ids == g[f"c{case}_mp_ids"].tolist()
+    assert r.kp_indices == g[f"c{case}_kp_indices"].tolist()
+    assert np.array_equal(r.pts3d, g[f"c{case}_pts3d"]) and np.array_equal(r.pts2d, g[f"c{case}_pts2d"])
+
+
+def test_reproject_and_match_map_updates_and_edge_cases():
+    import cv2 as _cv2
+    from b200slam import pnp_utils as P
+    from oracle import pnp as O
+    wm, K, Tcw, kps, des = O.tracking_scene(800, 1024, 11)
+    m = P.ReprojectionMatcher(max_points=256, max_kps=256)         # both capacities must grow
+    a = m.match(wm, K, Tcw, kps, des, 1241, 376, 12.0, 0.8)
+    o = O.reproject_and_match_2d3d(wm, K, Tcw, kps, des, 1241, 376, 12.0, 0.8)
+    assert a.mp_ids == o.mp_ids and a.kp_indices == o.kp_indices and len(a.mp_ids) > 100
+    # the map changes between frames: new observations, culled and new landmarks, moved positions (after BA)
+    rng = np.random.default_rng(0)
+    ids = list(wm.points)
+    for pid in ids[::7]:
+        del wm.points[pid]
+    for pid in ids[1::5]:
+        if pid in wm.points:
+            d = rng.normal(size=128).astype(np.float32); d /= np.linalg.norm(d)
+            wm.points[pid].observations.append((99, 0, d))
+    for pid in ids[2::9]:
+        if pid in wm.points:
+            wm.points[pid].position = wm.points[pid].position + rng.normal(0, 0.05, 3)
+    for k in range(40):
+        src = wm.points[ids[3 + 7 * k + 1]] if ids[3 + 7 * k + 1] in wm.points else None
+        if src is not None:
+            wm.points[900000 + k] = O._MP(900000 + k, src.position + 0.01, list(src.observations))
+    b = m.match(wm, K, Tcw, kps, des, 1241, 376, 12.0, 0.8)
+    o2 = O.reproject_and_match_2d3d(wm, K, Tcw, kps, des, 1241, 376, 12.0, 0.8)
+    assert b.mp_ids == o2.mp_ids and b.kp_indices == o2.kp_indices and b.mp_ids != a.mp_ids
+    # cv2.KeyPoint list input, as the tracking loop passes it (main_revamped.py:460)
+    kp_list = [_cv2.KeyPoint(float(x), float(y), 1) for x, y in kps]
+    c = P.reproject_and_match_2d3d(wm, K, Tcw, kp_list, des, 1241, 376, radius_px=12.0)
+    assert c.mp_ids == o2.mp_ids and c.kp_indices == o2.kp_indices
+    # empties (pnp_utils.py:239-247)
+    e = P.reproject_and_match_2d3d(wm, K, Tcw, kp_list, des[:0], 1241, 376)
+    assert e.pts3d.shape == (0, 3) and e.pts2d.shape == (0, 2) and e.kp_indices == [] and e.mp_ids == []
+    assert P.reproject_and_match_2d3d(O._Map(), K, Tcw, kp_list, des, 1241, 376).mp_ids == []
+    assert P.reproject_and_match_2d3d(wm, K, Tcw, [], des, 1241, 376).mp_ids == []
+    # camera looking away: nothing projects into the image
+    Tb = Tcw.copy(); Tb[:3, :3] = Tcw[:3, :3] @ np.diag([-1.0, 1.0, -1.0]); Tb[:3, 3] = [0, 0, -200.0]
+    assert P.reproject_and_match_2d3d(wm, K, Tb, kps, des, 1241, 376).mp_ids == O.reproject_and_match_2d3d(wm, K, Tb, kps, des, 1241, 376).mp_ids
+    # a window holding more keypoints than the candidate capacity is reported, not silently truncated
+    wm2, K2, T2, kps2, des2 = O.tracking_scene(300, 512, 5)
+    usable = [p for p in wm2.points.values() if p.observations and p.observations[-1][2] is not None]
+    uv, _ = O.project_points(K2, T2, np.asarray([p.position for p in usable]))
+    vis = uv[(uv[:, 0] > 50) & (uv[:, 0] < 1100) & (uv[:, 1] > 50) & (uv[:, 1] < 300)][0]
+    kps2[:200] = vis + rng.normal(0, 0.5, (200, 2)).astype(np.float32)
+    with pytest.raises(RuntimeError):
+        P.reproject_and_match_2d3d(wm2, K2, T2, kps2, des2, 1241, 376, radius_px=12.0)

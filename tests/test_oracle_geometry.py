@@ -102,3 +102,18 @@ def test_geometry_handles_fail_loudly_without_a_device():
         raise AssertionError("expected a RuntimeError without CUDA")
     except RuntimeError as e:
         assert "no CPU fallback" in str(e)
+
+
+def test_pnp_restatement_matches_reference_fixture():
+    """oracle/pnp.py against tests/golden/pnp_reproj.npz = outputs of the reference's own reproject_and_match_2d3d
+    (generated by tests/golden/make_golden_pnp.py from /root/reference/slam/core/pnp_utils.py)."""
+    import os
+    from oracle import pnp as O
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pnp_reproj.npz"))
+    for c in range(4):
+        n_points, n_kps, seed, radius, max_l2, cosine = g[f"c{c}_cfg"].tolist()
+        wm, K, Tcw, kps, des = O.tracking_scene(int(n_points), int(n_kps), int(seed))
+        r = O.reproject_and_match_2d3d(wm, K, Tcw, kps, des, 1241, 376, radius_px=radius, max_l2=max_l2, use_cosine=bool(cosine))
+        assert len(r.mp_ids) >= 100
+        assert r.mp_ids == g[f"c{c}_mp_ids"].tolist() and r.kp_indices == g[f"c{c}_kp_indices"].tolist()
+        assert np.array_equal(r.pts3d, g[f"c{c}_pts3d"]) and np.array_equal(r.pts2d, g[f"c{c}_pts2d"])
