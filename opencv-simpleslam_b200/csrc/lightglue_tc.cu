@@ -2,6 +2,7 @@
 // tcgen05/TMEM GEMMs (gemm_tc.cuh) + tcgen05 flash attention (attn_tc.cuh) + small
 // bandwidth-bound glue (fp32->bf16, LayerNorm+GELU).  The residual stream stays fp32.
 #include "lightglue_tc.cuh"
+#include <cstdlib>
 #include "attn_tc.cuh"
 #include "attn_tc3.cuh"
 #include "gemm_tc.cuh"
@@ -172,6 +173,7 @@ struct LgTensorCore {
   float* h1f = nullptr;
   CUtensorMap m_xb, m_ctxb, m_h1b, m_qkv768, m_qkv512;     // box {64, 128}: GEMM A operands, attention Q
   CUtensorMap m_kv768, m_kv512;                            // box {64, 64}: attention K / V tiles (np == 3)
+  CUtensorMap m_xb32, m_ctxb32, m_h1b32;                   // box {64, 32}: A operands of the cluster-multicast GEMMs
   // assignment head (always fp32-faithful, three planes): planes of the final x, of the projected descriptors md
   __nv_bfloat16 *tx = nullptr, *md = nullptr;
   CUtensorMap m_tx, m_md;
@@ -227,8 +229,18 @@ template <int BN, int NP>
 static void gemm_attr() {
   cudaFuncSetAttribute(k_gemm_tc<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGemmCfg<BN, NP>::SMEM);
 }
+template <int BN, int NP, int CL>
+static void gemm_attr_cl() {
+  cudaFuncSetAttribute(k_gemm_tc<BN, NP, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGemmCfg<BN, NP>::SMEM);
+}
+static bool gemm_cluster_enabled() {
+  static const bool on = [] { const char* e = std::getenv("B2S_NO_CLUSTER"); return !(e && e[0] == '1'); }();
+  return on;
+}
 static void tc_kernel_attrs() {
   gemm_attr<64, 1>(); gemm_attr<128, 1>(); gemm_attr<64, 3>(); gemm_attr<128, 3>();
+  gemm_attr_cl<64, 1, 4>(); gemm_attr_cl<128, 1, 4>(); gemm_attr_cl<128, 1, 2>();
+  gemm_attr_cl<64, 3, 4>(); gemm_attr_cl<128, 3, 4>(); gemm_attr_cl<128, 3, 2>();
   cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
   cudaFuncSetAttribute(k_attn_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM);
 }
@@ -271,6 +283,9 @@ int lgtc_alloc_ws(LgTensorCore* tc, int cap) {
   B2S_TRY(make_tmap_bf16_2d(&tc->m_xb, tc->xb, 256, P * R, 512, 64, 128));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_ctxb, tc->ctxb, 256, P * R, 512, 64, 128));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_h1b, tc->h1b, 512, P * R, 1024, 64, 128));
+  B2S_TRY(make_tmap_bf16_2d(&tc->m_xb32, tc->xb, 256, P * R, 512, 64, 32));
+  B2S_TRY(make_tmap_bf16_2d(&tc->m_ctxb32, tc->ctxb, 256, P * R, 512, 64, 32));
+  B2S_TRY(make_tmap_bf16_2d(&tc->m_h1b32, tc->h1b, 512, P * R, 1024, 64, 32));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_qkv768, tc->qkvb, 768, P * R, 1536, 64, 128));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_qkv512, tc->qkvb, 512, P * R, 1024, 64, 128));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_kv768, tc->qkvb, 768, P * R, 1536, 64, 64));
@@ -297,12 +312,30 @@ static int tc_gemm(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& a1, con
   if (tiles <= 0) return 0;
   dim3 grid(w.N / w.BN, tiles);
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
+  // cluster-multicast variant: the column tiles of a row tile share the A operand (32-row-box views of the same buffers)
+  auto a32 = [&](const CUtensorMap& m) -> const CUtensorMap* {
+    return &m == &tc->m_xb ? &tc->m_xb32 : &m == &tc->m_ctxb ? &tc->m_ctxb32 : &m == &tc->m_h1b ? &tc->m_h1b32 : nullptr;
+  };
+  const CUtensorMap *c1 = a32(a1), *c2 = a32(a2);
+  const int cl = (gemm_cluster_enabled() && c1 && c2) ? (grid.x % 4 == 0 ? 4 : (grid.x % 2 == 0 && w.BN == 128 ? 2 : 1)) : 1;
   if (tc->np == 1) {
-    if (w.BN == 64) launch_k(k_gemm_tc<64, 1>, grid, 192, TcGemmCfg<64, 1>::SMEM, st, a1, a2, w.map, p);
-    else launch_k(k_gemm_tc<128, 1>, grid, 192, TcGemmCfg<128, 1>::SMEM, st, a1, a2, w.map, p);
+    if (w.BN == 64) {
+      if (cl == 4) launch_k_cluster(k_gemm_tc<64, 1, 4>, grid, 192, TcGemmCfg<64, 1>::SMEM, st, 4, *c1, *c2, w.map, p);
+      else launch_k(k_gemm_tc<64, 1>, grid, 192, TcGemmCfg<64, 1>::SMEM, st, a1, a2, w.map, p);
+    } else {
+      if (cl == 4) launch_k_cluster(k_gemm_tc<128, 1, 4>, grid, 192, TcGemmCfg<128, 1>::SMEM, st, 4, *c1, *c2, w.map, p);
+      else if (cl == 2) launch_k_cluster(k_gemm_tc<128, 1, 2>, grid, 192, TcGemmCfg<128, 1>::SMEM, st, 2, *c1, *c2, w.map, p);
+      else launch_k(k_gemm_tc<128, 1>, grid, 192, TcGemmCfg<128, 1>::SMEM, st, a1, a2, w.map, p);
+    }
   } else {
-    if (w.BN == 64) launch_k(k_gemm_tc<64, 3>, grid, 192, TcGemmCfg<64, 3>::SMEM, st, a1, a2, w.map, p);
-    else launch_k(k_gemm_tc<128, 3>, grid, 192, TcGemmCfg<128, 3>::SMEM, st, a1, a2, w.map, p);
+    if (w.BN == 64) {
+      if (cl == 4) launch_k_cluster(k_gemm_tc<64, 3, 4>, grid, 192, TcGemmCfg<64, 3>::SMEM, st, 4, *c1, *c2, w.map, p);
+      else launch_k(k_gemm_tc<64, 3>, grid, 192, TcGemmCfg<64, 3>::SMEM, st, a1, a2, w.map, p);
+    } else {
+      if (cl == 4) launch_k_cluster(k_gemm_tc<128, 3, 4>, grid, 192, TcGemmCfg<128, 3>::SMEM, st, 4, *c1, *c2, w.map, p);
+      else if (cl == 2) launch_k_cluster(k_gemm_tc<128, 3, 2>, grid, 192, TcGemmCfg<128, 3>::SMEM, st, 2, *c1, *c2, w.map, p);
+      else launch_k(k_gemm_tc<128, 3>, grid, 192, TcGemmCfg<128, 3>::SMEM, st, a1, a2, w.map, p);
+    }
   }
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
   if (launches) ++*launches;

@@ -32,6 +32,16 @@ class Matches2D3D:     # pnp_utils.py:51-56
     mp_ids: List[int]          # matched map point ids
 
 
+def _kp_coords(kps) -> np.ndarray:
+    """list[cv2.KeyPoint] / KeyPointArray / ndarray (N,>=2) -> float32 (N,2)   (pnp_utils.py:65-76)"""
+    if isinstance(kps, np.ndarray):
+        if kps.size == 0:
+            return np.empty((0, 2), np.float32)
+        assert kps.ndim == 2 and kps.shape[1] >= 2, "kps must be (N,2)"
+        return np.ascontiguousarray(kps[:, :2], dtype=np.float32)
+    return _kps_to_array(kps)
+
+
 def _empty() -> Matches2D3D:
     return Matches2D3D(np.zeros((0, 3), np.float32), np.zeros((0, 2), np.float32), [], [])
 
@@ -139,7 +149,7 @@ class ReprojectionMatcher:
             return MapDescriptorMirror(self.device_index)
 
     def match(self, world_map, K, Tcw_pred, kps_cur, des_cur, img_w, img_h, radius_px=12.0, max_l2=0.8) -> Matches2D3D:
-        pts2d_cur = _kps_to_array(kps_cur)
+        pts2d_cur = _kp_coords(kps_cur)
         N, P = len(pts2d_cur), len(world_map.points)
         if N == 0 or P == 0:
             return _empty()
