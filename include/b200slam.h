@@ -257,6 +257,10 @@ int b2s_test_attn_tc3(const float* q, const float* k, const float* v, int nq, in
 int b2s_bench_attn_tc(int nq, int nk, int iters, float* ms_out);
 int b2s_bench_attn_tc3(int nq, int nk, int iters, float* ms_out);
 
+/* device-only timing of one bf16x3 layer-GEMM shape, `iters` launches back to back (PDL), clusters of `cl` CTAs sharing
+ * the A tile (1 = none); ts_out (nullable) receives 6 globaltimer stamps (ns, relative) per CTA of one extra launch */
+int b2s_bench_gemm_tc3(int M, int N, int K, int cl, int iters, float* ms_out, long long* ts_out, int* n_cta_out);
+
 /* Number of CUDA kernels this library launched on behalf of the handle so far. */
 long long b2s_aliked_launch_count(const b2s_aliked* h);
 long long b2s_lg_launch_count(const b2s_lg* h);

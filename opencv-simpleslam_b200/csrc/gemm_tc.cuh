@@ -38,6 +38,7 @@ struct TcGemmParams {
   const int* m_dev; int m_mult;     // nullable: live rows of segment 0 = *m_dev * m_mult (ALIKED keypoint count)
   int act;                          // 0 none, 1 SELU (after bias / residual)
   const float* residual; int ld_res; // nullable fp32 [rows, ld_res]: added after bias * alpha, before the activation
+  unsigned long long* ts;            // nullable profiling hook: per CTA 6 globaltimer stamps (b2s_bench_gemm_tc3)
 };
 
 // fp32 weight [N,K] -> np bf16 planes side by side: out[n][p*K + k]
@@ -60,7 +61,10 @@ struct TcGemmCfg {
   static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
   static constexpr int STAGES = NP == 1 ? 3 : (BN == 128 ? 2 : 3);
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
-  static constexpr int THREADS = 192;
+  // warps 0 / 1 = TMA / MMA; EPI_WARPS epilogue warps: four per TMEM lane quadrant, each owning every fourth 32-column
+  // chunk (one warp per scheduler cannot hide its own instruction latency: the thread==row epilogue is latency bound)
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   // The tensor core truncates its fp32 accumulator after every k-step (measured: bias -4.4e-9 * K on positive
   // data), which would cost the NP = 3 path its fp32 fidelity for long K.  So the accumulation is spread over
   // NACC TMEM accumulators that the epilogue adds in fp32 registers (round-to-nearest): accumulator 0 takes the
@@ -75,7 +79,7 @@ struct TcGemmCfg {
 // same smem offset of all CL CTAs, so the L2 -> SM operand traffic per CTA drops from A + W to A/CL + W.  A stage is
 // released to the producers of ALL CTAs (multicast tcgen05.commit, empty barriers count CL arrivals).
 template <int BN, int NP, int CL = 1>
-__global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtensorMap mapA1,
+__global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __grid_constant__ CUtensorMap mapA1,
                                                  const __grid_constant__ CUtensorMap mapA2,
                                                  const __grid_constant__ CUtensorMap mapW, TcGemmParams p) {
   using Cfg = TcGemmCfg<BN, NP>;
@@ -92,6 +96,10 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_m = blockIdx.y, n0 = blockIdx.x * BN;
+  auto stamp = [&](int slot) {
+    if (p.ts) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.ts[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 6 + slot] = t; }
+  };
+  if (threadIdx.x == 0) stamp(0);                    // CTA start
   const int seg = tile_m >= p.tiles0 ? 1 : 0;
   const int row0 = p.seg_base[seg] + (tile_m - (seg ? p.tiles0 : 0)) * Cfg::BM;       // global row of the tile
   int rows_live = p.seg_rows[seg] - (tile_m - (seg ? p.tiles0 : 0)) * Cfg::BM;        // live rows in this tile
@@ -119,6 +127,7 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
   const uint32_t crank = CL > 1 ? tc::cluster_ctarank() : 0;
   constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1);
   pdl_wait();            // everything above overlaps the previous kernel's tail; operands are touched only below
+  if (threadIdx.x == 0) stamp(1);                    // dependencies resolved
   int w_row = p.w_row0, n_live = p.N;
   if (p.ctrl) {          // device-resident sizes: pruning shrinks the segments, an early exit empties the layer
     const bool sides = p.ctrl[2] > 0 && p.ctrl[3] > 0;
@@ -129,7 +138,7 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
       if (warp >= 2) {               // the bias depends on the layer: restage it (epilogue warps only)
         const int t = threadIdx.x - 64;
         if (t < BN) s_bias[t] = __ldg(p.bias + w_row + n0 + t);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * Cfg::EPI_WARPS) : "memory");
       }
     } else if (p.ctrl_mode == 3) {
       n_live = p.ctrl[3];
@@ -181,6 +190,7 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
         const int s = kb % Cfg::STAGES, ph = (kb / Cfg::STAGES) & 1;
         tc::mbar_wait(&full[s], ph);
         tc::tc_fence_after();
+        if (kb == 0) stamp(2);                       // first operand stage landed
         const uint32_t a0 = tc::smem_u32(smem + s * Cfg::STAGE_BYTES), b0 = a0 + NP * Cfg::A_BYTES;
 #pragma unroll
         for (int t = 0; t < Terms::N; ++t) {
@@ -199,15 +209,35 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
       }
     }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
-    const int quad = warp & 3;
+    // ===== epilogue: a warp may touch the TMEM lane quadrant (warp % 4); the column chunks are dealt round-robin to the
+    //       EPI_WARPS / 4 warps of a quadrant =====
+    const int quad = warp & 3, cgrp = (warp - 2) >> 2;   // chunks c0 = cgrp*32, step EPI_WARPS/4*32
     const int r = quad * 32 + lane;                 // accumulator row handled by this thread
     const bool live = r < rows_live;
     const size_t grow = (size_t)(row0 + r);
     tc::mbar_wait(tmem_full, 0);
     tc::tc_fence_after();
+    if (threadIdx.x == 64) stamp(3);                 // accumulators complete
+    // Output staging (the operand stages are idle now: every MMA has retired and every TMA write has landed).
+    // thread == row makes each store instruction touch 32 different lines and the LSU serialises them; instead a warp
+    // parks its 32 x 32 chunk in shared memory (16-byte slots XOR-swizzled by row: conflict-free both ways) and writes
+    // it back row-contiguously (4 rows x 128 B or 8 rows x 64 B per instruction).
+    uint8_t* stg = smem + (warp - 2) * 4096;
+    float* sf = reinterpret_cast<float*>(stg);                      // fp32 tile [32 rows][32]
+    uint32_t* sp = reinterpret_cast<uint32_t*>(stg);                // or one bf16 plane tile [32 rows][16 words]
+    const int rows_q = rows_live - quad * 32;                       // live rows of this warp's quadrant
+    const size_t qrow0 = (size_t)row0 + quad * 32;
+    uint4* myrow = reinterpret_cast<uint4*>(sf + lane * 32);
+    auto store_f32_tile = [&](int gc) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int R = it * 4 + (lane >> 3), sl = lane & 7;
+        const uint4 v = reinterpret_cast<const uint4*>(sf + R * 32)[sl ^ (R & 7)];
+        if (R < rows_q) *reinterpret_cast<uint4*>(p.out_f32 + (qrow0 + R) * p.ld_f32 + gc + sl * 4) = v;
+      }
+    };
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = cgrp * 32; c0 < BN; c0 += 8 * Cfg::EPI_WARPS) {
       uint32_t v[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + c0;
       float f[32];
@@ -236,7 +266,7 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
         for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
       }
       const int gc = n0 + c0;
-      if (!live || gc >= p.N) continue;
+      if (gc >= p.N) continue;                       // uniform per warp
       {
         const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
@@ -249,7 +279,7 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
       }
-      if (p.residual) {
+      if (p.residual && live) {
         const float4* rs = reinterpret_cast<const float4*>(p.residual + grow * p.ld_res + gc);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -261,7 +291,7 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = selu_f(f[j]);
       }
-      if (p.epi == TC_EPI_ROTARY_BF16 && gc < p.rot_cols) {
+      if (p.epi == TC_EPI_ROTARY_BF16 && gc < p.rot_cols && live) {
         const int f0 = (gc & 63) >> 1;   // 0 or 16: this chunk's 16 (cos,sin) pairs are contiguous
         const float4* c4 = reinterpret_cast<const float4*>(p.rot_cos + grow * 32 + f0);
         const float4* s4 = reinterpret_cast<const float4*>(p.rot_sin + grow * 32 + f0);
@@ -280,40 +310,63 @@ __global__ void __launch_bounds__(192) k_gemm_tc(const __grid_constant__ CUtenso
         }
       }
       if (p.epi == TC_EPI_F32) {
-        float4* d = reinterpret_cast<float4*>(p.out_f32 + grow * p.ld_f32 + gc);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        for (int q = 0; q < 8; ++q)
+          myrow[q ^ (lane & 7)] = make_uint4(__float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]), __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3]));
+        __syncwarp();
+        store_f32_tile(gc);
+        __syncwarp();
         continue;
       }
       if (p.epi == TC_EPI_RESID_F32_BF16) {
-        float4* d = reinterpret_cast<float4*>(p.out_f32 + grow * p.ld_f32 + gc);
+        // x (fp32 residual stream, updated in place): row-contiguous load into the staging tile, add, write back
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 x = d[j];
-          x.x += f[4 * j]; x.y += f[4 * j + 1]; x.z += f[4 * j + 2]; x.w += f[4 * j + 3];
-          d[j] = x;
-          f[4 * j] = x.x; f[4 * j + 1] = x.y; f[4 * j + 2] = x.z; f[4 * j + 3] = x.w;
+        for (int it = 0; it < 8; ++it) {
+          const int R = it * 4 + (lane >> 3), sl = lane & 7;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (R < rows_q) v = *reinterpret_cast<const uint4*>(p.out_f32 + (qrow0 + R) * p.ld_f32 + gc + sl * 4);
+          reinterpret_cast<uint4*>(sf + R * 32)[sl ^ (R & 7)] = v;
         }
-      }
-      uint32_t w[NP][16];
+        __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        uint32_t pw[NP];
-        tc::pack_planes2<NP>(f[2 * j], f[2 * j + 1], pw);
-#pragma unroll
-        for (int pl = 0; pl < NP; ++pl) w[pl][j] = pw[pl];
+        for (int q = 0; q < 8; ++q) {
+          const uint4 xv = myrow[q ^ (lane & 7)];
+          f[4 * q] += __uint_as_float(xv.x); f[4 * q + 1] += __uint_as_float(xv.y);
+          f[4 * q + 2] += __uint_as_float(xv.z); f[4 * q + 3] += __uint_as_float(xv.w);
+          myrow[q ^ (lane & 7)] = make_uint4(__float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]), __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3]));
+        }
+        __syncwarp();
+        store_f32_tile(gc);
+        __syncwarp();
       }
+      // operand planes, one at a time: plane p = bf16(residual), residual -= plane p  (== tc::pack_planes2)
 #pragma unroll
       for (int pl = 0; pl < NP; ++pl) {
-        uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + pl * p.out_plane + grow * p.ld_bf16 + gc);
+        uint32_t w[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = make_uint4(w[pl][4 * j], w[pl][4 * j + 1], w[pl][4 * j + 2], w[pl][4 * j + 3]);
+        for (int j = 0; j < 16; ++j) {
+          w[j] = tc::pack_bf16x2(f[2 * j], f[2 * j + 1]);
+          if (pl + 1 < NP) { f[2 * j] -= __uint_as_float(w[j] << 16); f[2 * j + 1] -= __uint_as_float(w[j] & 0xFFFF0000u); }
+        }
+        uint4* prow = reinterpret_cast<uint4*>(sp + lane * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) prow[j ^ ((lane >> 1) & 3)] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int R = it * 8 + (lane >> 2), sl = lane & 3;
+          const uint4 v = reinterpret_cast<const uint4*>(sp + R * 16)[sl ^ ((R >> 1) & 3)];
+          if (R < rows_q) *reinterpret_cast<uint4*>(p.out_bf16 + pl * p.out_plane + (qrow0 + R) * p.ld_bf16 + gc + sl * 8) = v;
+        }
+        __syncwarp();
       }
     }
   }
+  if (threadIdx.x == 64) stamp(4);                   // epilogue of warp 2 done
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 2) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (threadIdx.x == 0) stamp(5);                    // CTA end
 }
 
 }  // namespace b2s

@@ -320,21 +320,21 @@ static int tc_gemm(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& a1, con
   const int cl = (gemm_cluster_enabled() && c1 && c2) ? (grid.x % 4 == 0 ? 4 : (grid.x % 2 == 0 && w.BN == 128 ? 2 : 1)) : 1;
   if (tc->np == 1) {
     if (w.BN == 64) {
-      if (cl == 4) launch_k_cluster(k_gemm_tc<64, 1, 4>, grid, 192, TcGemmCfg<64, 1>::SMEM, st, 4, *c1, *c2, w.map, p);
-      else launch_k(k_gemm_tc<64, 1>, grid, 192, TcGemmCfg<64, 1>::SMEM, st, a1, a2, w.map, p);
+      if (cl == 4) launch_k_cluster(k_gemm_tc<64, 1, 4>, grid, TcGemmCfg<64, 1>::THREADS, TcGemmCfg<64, 1>::SMEM, st, 4, *c1, *c2, w.map, p);
+      else launch_k(k_gemm_tc<64, 1>, grid, TcGemmCfg<64, 1>::THREADS, TcGemmCfg<64, 1>::SMEM, st, a1, a2, w.map, p);
     } else {
-      if (cl == 4) launch_k_cluster(k_gemm_tc<128, 1, 4>, grid, 192, TcGemmCfg<128, 1>::SMEM, st, 4, *c1, *c2, w.map, p);
-      else if (cl == 2) launch_k_cluster(k_gemm_tc<128, 1, 2>, grid, 192, TcGemmCfg<128, 1>::SMEM, st, 2, *c1, *c2, w.map, p);
-      else launch_k(k_gemm_tc<128, 1>, grid, 192, TcGemmCfg<128, 1>::SMEM, st, a1, a2, w.map, p);
+      if (cl == 4) launch_k_cluster(k_gemm_tc<128, 1, 4>, grid, TcGemmCfg<128, 1>::THREADS, TcGemmCfg<128, 1>::SMEM, st, 4, *c1, *c2, w.map, p);
+      else if (cl == 2) launch_k_cluster(k_gemm_tc<128, 1, 2>, grid, TcGemmCfg<128, 1>::THREADS, TcGemmCfg<128, 1>::SMEM, st, 2, *c1, *c2, w.map, p);
+      else launch_k(k_gemm_tc<128, 1>, grid, TcGemmCfg<128, 1>::THREADS, TcGemmCfg<128, 1>::SMEM, st, a1, a2, w.map, p);
     }
   } else {
     if (w.BN == 64) {
-      if (cl == 4) launch_k_cluster(k_gemm_tc<64, 3, 4>, grid, 192, TcGemmCfg<64, 3>::SMEM, st, 4, *c1, *c2, w.map, p);
-      else launch_k(k_gemm_tc<64, 3>, grid, 192, TcGemmCfg<64, 3>::SMEM, st, a1, a2, w.map, p);
+      if (cl == 4) launch_k_cluster(k_gemm_tc<64, 3, 4>, grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, 4, *c1, *c2, w.map, p);
+      else launch_k(k_gemm_tc<64, 3>, grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, a1, a2, w.map, p);
     } else {
-      if (cl == 4) launch_k_cluster(k_gemm_tc<128, 3, 4>, grid, 192, TcGemmCfg<128, 3>::SMEM, st, 4, *c1, *c2, w.map, p);
-      else if (cl == 2) launch_k_cluster(k_gemm_tc<128, 3, 2>, grid, 192, TcGemmCfg<128, 3>::SMEM, st, 2, *c1, *c2, w.map, p);
-      else launch_k(k_gemm_tc<128, 3>, grid, 192, TcGemmCfg<128, 3>::SMEM, st, a1, a2, w.map, p);
+      if (cl == 4) launch_k_cluster(k_gemm_tc<128, 3, 4>, grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, 4, *c1, *c2, w.map, p);
+      else if (cl == 2) launch_k_cluster(k_gemm_tc<128, 3, 2>, grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, 2, *c1, *c2, w.map, p);
+      else launch_k(k_gemm_tc<128, 3>, grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, a1, a2, w.map, p);
     }
   }
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
@@ -423,13 +423,13 @@ int lgtc_assignment(LgTensorCore* tc, cudaStream_t st, const float* x0, const fl
   p.seg_base[0] = 0; p.seg_base[1] = cap; p.seg_rows[0] = m; p.seg_rows[1] = n; p.tiles0 = cdiv(m, 128);
   p.plane_rows = 2 * cap; p.epi = TC_EPI_BF16; p.out_bf16 = tc->md; p.ld_bf16 = 256; p.out_plane = plane;
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
-  launch_k(k_gemm_tc<64, 3>, dim3(4, p.tiles0 + cdiv(n, 128)), 192, TcGemmCfg<64, 3>::SMEM, st, tc->m_tx, tc->m_tx, tc->wfinal.map, p);
+  launch_k(k_gemm_tc<64, 3>, dim3(4, p.tiles0 + cdiv(n, 128)), TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, tc->m_tx, tc->m_tx, tc->wfinal.map, p);
   p = TcGemmParams();
   p.K = 256; p.K1 = 256; p.N = n; p.bias = nullptr; p.ctrl = ctrl; p.ctrl_mode = 3;
   p.w_plane_rows = 2 * cap; p.w_row0 = cap;
   p.seg_base[0] = 0; p.seg_base[1] = 0; p.seg_rows[0] = m; p.seg_rows[1] = 0; p.tiles0 = cdiv(m, 128);
   p.plane_rows = 2 * cap; p.epi = TC_EPI_F32; p.out_f32 = sim; p.ld_f32 = cap;
-  launch_k(k_gemm_tc<128, 3>, dim3(cdiv(n, 128), p.tiles0), 192, TcGemmCfg<128, 3>::SMEM, st, tc->m_md, tc->m_md, tc->m_md, p);
+  launch_k(k_gemm_tc<128, 3>, dim3(cdiv(n, 128), p.tiles0), TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, tc->m_md, tc->m_md, tc->m_md, p);
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
   if (launches) *launches += 3;
   B2S_LAUNCH_CHECK();
@@ -521,11 +521,11 @@ static int test_gemm(const float* A, const float* W, const float* bias, int M, i
   p.seg_base[0] = 0; p.seg_rows[0] = M; p.seg_base[1] = 0; p.seg_rows[1] = 0; p.tiles0 = cdiv(M, 128);
   dim3 grid(N / BN, p.tiles0);
   if (np == 1) {
-    if (BN == 64) k_gemm_tc<64, 1><<<grid, 192, TcGemmCfg<64, 1>::SMEM>>>(ma, ma, mw, p);
-    else k_gemm_tc<128, 1><<<grid, 192, TcGemmCfg<128, 1>::SMEM>>>(ma, ma, mw, p);
+    if (BN == 64) k_gemm_tc<64, 1><<<grid, TcGemmCfg<64, 1>::THREADS, TcGemmCfg<64, 1>::SMEM>>>(ma, ma, mw, p);
+    else k_gemm_tc<128, 1><<<grid, TcGemmCfg<128, 1>::THREADS, TcGemmCfg<128, 1>::SMEM>>>(ma, ma, mw, p);
   } else {
-    if (BN == 64) k_gemm_tc<64, 3><<<grid, 192, TcGemmCfg<64, 3>::SMEM>>>(ma, ma, mw, p);
-    else k_gemm_tc<128, 3><<<grid, 192, TcGemmCfg<128, 3>::SMEM>>>(ma, ma, mw, p);
+    if (BN == 64) k_gemm_tc<64, 3><<<grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM>>>(ma, ma, mw, p);
+    else k_gemm_tc<128, 3><<<grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM>>>(ma, ma, mw, p);
   }
   B2S_LAUNCH_CHECK();
   B2S_CUDA(cudaDeviceSynchronize());
@@ -537,6 +537,75 @@ extern "C" int b2s_test_gemm_tc(const float* A, const float* W, const float* bia
 }
 extern "C" int b2s_test_gemm_tc3(const float* A, const float* W, const float* bias, int M, int N, int K, float* C) {
   return test_gemm(A, W, bias, M, N, K, C, 3);
+}
+
+// Device-only timing of one layer GEMM shape (bf16x3 planes in, planes out like the QKV / FFN epilogues), `iters` launches
+// back to back on one stream with programmatic dependent launch, optionally as clusters of `cl` CTAs sharing A.
+// ts_out (nullable, host, [tiles*6]): globaltimer stamps of the last launch's CTAs relative to its earliest CTA start:
+// start, dependencies resolved, first stage landed, accumulators complete, epilogue done, end (ns).
+extern "C" int b2s_bench_gemm_tc3(int M, int N, int K, int cl, int iters, float* ms_out, long long* ts_out, int* n_cta_out) {
+  if (M <= 0 || N % 64 || K % 64 || iters <= 0 || !ms_out) { set_error("b2s_bench_gemm_tc3: bad argument"); return B2S_EINVAL; }
+  const int np = 3;
+  DeviceArena ar;
+  const int Mp = cdiv(M, 128) * 128;
+  const int BN = N <= 256 ? 64 : 128;
+  __nv_bfloat16 *dA, *dW, *dO; float* dB; unsigned long long* dts;
+  const size_t nA = (size_t)np * Mp * K, nW = (size_t)np * N * K, nO = (size_t)np * Mp * N;
+  B2S_TRY(ar.alloc(&dA, nA)); B2S_TRY(ar.alloc(&dW, nW)); B2S_TRY(ar.alloc(&dO, nO)); B2S_TRY(ar.alloc(&dB, (size_t)N));
+  std::vector<__nv_bfloat16> h(std::max(nA, nW));
+  uint32_t sd = 777u;
+  for (size_t i = 0; i < h.size(); ++i) { sd = sd * 1664525u + 1013904223u; h[i] = __float2bfloat16_rn(((sd >> 8) & 0xFFFF) / 32768.f - 1.f); }
+  B2S_CUDA(cudaMemcpy(dA, h.data(), nA * 2, cudaMemcpyHostToDevice));
+  B2S_CUDA(cudaMemcpy(dW, h.data(), nW * 2, cudaMemcpyHostToDevice));
+  B2S_CUDA(cudaMemset(dB, 0, (size_t)N * 4));
+  const dim3 grid(N / BN, Mp / 128);
+  const size_t ncta = (size_t)grid.x * grid.y;
+  B2S_TRY(ar.alloc(&dts, ncta * 6));
+  CUtensorMap ma, ma32, mw;
+  B2S_TRY(make_tmap_bf16_2d(&ma, dA, K, (uint64_t)np * Mp, (uint64_t)K * 2, 64, 128));
+  B2S_TRY(make_tmap_bf16_2d(&ma32, dA, K, (uint64_t)np * Mp, (uint64_t)K * 2, 64, 32));
+  B2S_TRY(make_tmap_bf16_2d(&mw, dW, (uint64_t)np * K, N, (uint64_t)np * K * 2, 64, BN));
+  tc_kernel_attrs();
+  TcGemmParams p = {};
+  p.K = K; p.K1 = K; p.N = N; p.bias = dB; p.epi = TC_EPI_BF16; p.out_bf16 = dO; p.ld_bf16 = N; p.out_plane = (size_t)Mp * N; p.plane_rows = Mp;
+  p.seg_base[0] = 0; p.seg_rows[0] = M; p.seg_base[1] = 0; p.seg_rows[1] = 0; p.tiles0 = Mp / 128;
+  cudaStream_t st;
+  B2S_CUDA(cudaStreamCreate(&st));
+  auto launch = [&](unsigned long long* ts) {
+    TcGemmParams q = p; q.ts = ts;
+    if (BN == 64) {
+      if (cl == 4) launch_k_cluster(k_gemm_tc<64, 3, 4>, grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, 4, ma32, ma32, mw, q);
+      else launch_k(k_gemm_tc<64, 3>, grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, ma, ma, mw, q);
+    } else {
+      if (cl == 4) launch_k_cluster(k_gemm_tc<128, 3, 4>, grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, 4, ma32, ma32, mw, q);
+      else if (cl == 2) launch_k_cluster(k_gemm_tc<128, 3, 2>, grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, 2, ma32, ma32, mw, q);
+      else launch_k(k_gemm_tc<128, 3>, grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, ma, ma, mw, q);
+    }
+  };
+  cudaEvent_t e0, e1;
+  B2S_CUDA(cudaEventCreate(&e0)); B2S_CUDA(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) launch(nullptr);
+  B2S_CUDA(cudaEventRecord(e0, st));
+  for (int i = 0; i < iters; ++i) launch(nullptr);
+  B2S_CUDA(cudaEventRecord(e1, st));
+  B2S_LAUNCH_CHECK();
+  B2S_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  B2S_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_out = ms / iters;
+  if (ts_out) {
+    for (int i = 0; i < 4; ++i) launch(i == 3 ? dts : nullptr);
+    B2S_LAUNCH_CHECK();
+    B2S_CUDA(cudaStreamSynchronize(st));
+    std::vector<unsigned long long> hts(ncta * 6);
+    B2S_CUDA(cudaMemcpy(hts.data(), dts, hts.size() * 8, cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (size_t c = 0; c < ncta; ++c) t0 = std::min(t0, hts[c * 6]);
+    for (size_t i = 0; i < hts.size(); ++i) ts_out[i] = (long long)(hts[i] - t0);
+  }
+  if (n_cta_out) *n_cta_out = (int)ncta;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
+  return 0;
 }
 
 // uploads q | k | v as [np][R, 768] planes and launches one attention (z problems); ctx planes come back summed
