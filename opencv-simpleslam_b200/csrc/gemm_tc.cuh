@@ -59,7 +59,7 @@ struct TcGemmCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;       // one plane
   static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = NP == 1 ? 3 : (BN == 128 ? 2 : 3);
+  static constexpr int STAGES = NP == 1 ? 3 : (BN >= 96 ? 2 : 3);
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
   // warps 0 / 1 = TMA / MMA; EPI_WARPS epilogue warps: four per TMEM lane quadrant, each owning every fourth 32-column
   // chunk (one warp per scheduler cannot hide its own instruction latency: the thread==row epilogue is latency bound)
@@ -71,7 +71,7 @@ struct TcGemmCfg {
   // five correction terms (2^-8 of the magnitude, their truncation is negligible), accumulators 1.. take the
   // main a0*w0 term round-robin by k-block.
   static constexpr int NACC = NP == 1 ? 1 : 512 / BN;
-  static constexpr int TMEM_COLS = NACC * BN;
+  static constexpr int TMEM_COLS = NACC * BN <= 64 ? 64 : NACC * BN <= 128 ? 128 : NACC * BN <= 256 ? 256 : 512;   // power of two
 };
 
 // CL > 1: the CL CTAs of a cluster along grid.x compute the CL column tiles of the same 128-row tile.  They share the

@@ -29,7 +29,7 @@ struct b2s_lg {
   float *kn = nullptr, *cosb[2] = {nullptr, nullptr}, *sinb[2] = {nullptr, nullptr}, *x[2] = {nullptr, nullptr};
   float *qkv = nullptr, *ctx = nullptr, *msg = nullptr, *h1 = nullptr, *tok = nullptr, *sim = nullptr;
   float *rmax = nullptr, *rlog = nullptr, *cmax = nullptr, *clog = nullptr, *ls = nullptr, *max0 = nullptr;
-  int *ind[2] = {nullptr, nullptr}, *keep = nullptr, *srcmap = nullptr, *m0 = nullptr, *m1 = nullptr, *ctrl = nullptr;
+  int *ind[2] = {nullptr, nullptr}, *keep = nullptr, *srcmap = nullptr, *adapt = nullptr, *m0 = nullptr, *m1 = nullptr, *ctrl = nullptr;
   const float** wfinal_tab = nullptr; const float** bfinal_tab = nullptr; const float** wmatch_tab = nullptr;  // device tables [L]
   float* bmatch_tab = nullptr;
   int *prune_scratch[2] = {nullptr, nullptr};
@@ -83,6 +83,7 @@ static int lg_alloc_ws(b2s_lg* h, int cap) {
   B2S_TRY(h->wsarena.alloc(&h->max0, (size_t)cap));
   B2S_TRY(h->wsarena.alloc(&h->keep, R));
   B2S_TRY(h->wsarena.alloc(&h->srcmap, R));
+  B2S_TRY(h->wsarena.alloc(&h->adapt, (size_t)8 + 2 * LG_MAXBLK));
   B2S_TRY(h->wsarena.alloc(&h->m0, (size_t)cap));
   B2S_TRY(h->wsarena.alloc(&h->m1, (size_t)cap));
   B2S_TRY(h->wsarena.alloc(&h->ctrl, (size_t)LGC_INTS));
@@ -420,11 +421,37 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
     }
     if (i == L - 1 || (!do_stop && !do_prune)) continue;
     const LgLayer& l = h->L[i];
+    // upstream: scores > (1 - width_confidence) with a python double; undo the float rounding of the cfg
+    const float keep_thr = (float)(1.0 - std::round((double)h->cfg.width_conf * 1e6) / 1e6);
+    if (do_prune && cap <= 32 * LG_MAXBLK) {
+      // two launches: heads per 32-row block (keep masks, one atomic per CTA), then decision + placement + copy
+      const int nblk = cdiv(std::max(m, n), 32);
+      HeadBlkParams hp = {};
+      hp.x = h->x[cur]; hp.base[0] = 0; hp.base[1] = cap;
+      hp.wt = l.wtok; hp.bt = l.btok; hp.wm = l.wmatch; hp.bm = l.bmatch;
+      hp.thr = h->thr[i]; hp.keep_thr = keep_thr; hp.use_tok = do_stop;
+      hp.tok = h->tok; hp.ctrl = h->ctrl; hp.adapt = h->adapt; hp.layer = i;
+      launch_k(k_lg_heads_blk, dim3(nblk, 2), 256, 0, st, hp);
+      const int nxt = cur ^ 1;
+      GatherBlkParams gp = {};
+      gp.adapt = h->adapt; gp.ctrl = h->ctrl; gp.base[0] = 0; gp.base[1] = cap;
+      gp.layer = i; gp.num_points = m + n; gp.do_stop = do_stop ? 1 : 0; gp.pruning_min_kpts = h->cfg.pruning_min_kpts;
+      gp.nblk = nblk; gp.depth_conf = h->cfg.depth_conf;
+      gp.x_in = h->x[cur]; gp.x_out = h->x[nxt]; gp.cos_in = h->cosb[cur]; gp.cos_out = h->cosb[nxt];
+      gp.sin_in = h->sinb[cur]; gp.sin_out = h->sinb[nxt]; gp.ind_in = h->ind[cur]; gp.ind_out = h->ind[nxt];
+      gp.prune[0] = pr0; gp.prune[1] = pr1;
+      gp.xb_out = h->tc ? lgtc_xb(h->tc) : nullptr;
+      gp.xb_planes = h->tc ? lgtc_planes(h->tc) : 0; gp.xb_plane = (size_t)2 * cap * 256;
+      launch_k(k_lg_gather_blk, dim3(nblk, 2), 256, 0, st, gp);
+      h->launches += 2;
+      B2S_LAUNCH_CHECK();
+      continue;
+    }
     HeadParams hp = {};
     hp.x = h->x[cur]; hp.seg = {{0, cap}, {m, n}};
     hp.wt = l.wtok; hp.bt = l.btok; hp.wm = l.wmatch; hp.bm = l.bmatch;
-    hp.thr = h->thr[i]; // upstream: scores > (1 - width_confidence) with a python double; undo the float rounding of the cfg
-    hp.keep_thr = (float)(1.0 - std::round((double)h->cfg.width_conf * 1e6) / 1e6);
+    hp.thr = h->thr[i];
+    hp.keep_thr = keep_thr;
     hp.use_tok = do_stop; hp.use_match = do_prune;
     hp.tok = h->tok; hp.keep = h->keep; hp.ctrl = h->ctrl; hp.layer = i; hp.ls_pos = nullptr;
     dim3 hg(cdiv(std::max(m, n), 8), 2);

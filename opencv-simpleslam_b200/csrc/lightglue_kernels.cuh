@@ -369,6 +369,146 @@ __global__ void __launch_bounds__(1024) k_lg_prune_scan(ScanParams p) {
   if (threadIdx.x == 0) { p.ctrl[LGC_M + s] = carry; p.ctrl[LGC_CAN0 + s] = prune ? 1 : 0; }
 }
 
+// ---------------------------------------------------------------------------------------
+// Adaptive depth / width in two launches (pruning enabled): k_lg_heads_blk + k_lg_gather_blk replace
+// k_lg_heads + k_lg_prune_scan + k_lg_gather.  A CTA owns 32 consecutive rows of one image.
+//   heads : token / matchability heads of its rows -> 32-bit keep mask of the block, ONE atomic per CTA for the
+//           unconfident count, and a snapshot of the live state (active, m, n) for the next kernel
+//   gather: every CTA takes the (identical) early-exit decision from the final count, prefix-sums the block
+//           popcounts (<= 256 blocks: one warp) to place its rows, and copies its kept rows; one designated CTA
+//           per image publishes the new size.  The kernel never reads a ctrl word it writes (snapshot instead).
+// adapt: [0] active  [1] m  [2] n  [8 + s*LG_MAXBLK + b] keep mask of block b of image s
+// ---------------------------------------------------------------------------------------
+constexpr int LG_MAXBLK = 256;   // 32-row blocks per image (cap <= 8192)
+struct HeadBlkParams {
+  const float* x; int base[2];
+  const float* wt; float bt; const float* wm; float bm;
+  float thr; float keep_thr; int use_tok;
+  float* tok; int* ctrl; int* adapt; int layer;
+};
+
+__global__ void __launch_bounds__(256) k_lg_heads_blk(HeadBlkParams p) {
+  pdl_wait();
+  const int s = blockIdx.y, blk = blockIdx.x;
+  const bool active = lg_active(p.ctrl);
+  if (blk == 0 && s == 0 && threadIdx.x == 0) { p.adapt[0] = active ? 1 : 0; p.adapt[1] = p.ctrl[LGC_M]; p.adapt[2] = p.ctrl[LGC_N]; }
+  if (!active) return;
+  __shared__ unsigned s_mask;
+  __shared__ int s_unconf;
+  if (threadIdx.x == 0) { s_mask = 0u; s_unconf = 0; }
+  __syncthreads();
+  const int rows = p.ctrl[LGC_M + s];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4 wt0 = *reinterpret_cast<const float4*>(p.wt + lane * 4), wt1 = *reinterpret_cast<const float4*>(p.wt + 128 + lane * 4);
+  const float4 wm0 = *reinterpret_cast<const float4*>(p.wm + lane * 4), wm1 = *reinterpret_cast<const float4*>(p.wm + 128 + lane * 4);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int rb = warp * 4 + q, row = blk * 32 + rb;
+    if (row >= rows) break;                      // uniform per warp
+    const int r = p.base[s] + row;
+    const float* x = p.x + (size_t)r * 256;
+    const float4 a = *reinterpret_cast<const float4*>(x + lane * 4);
+    const float4 b = *reinterpret_cast<const float4*>(x + 128 + lane * 4);
+    float dt = 0.f;
+    if (p.use_tok) {
+      dt = a.x * wt0.x + a.y * wt0.y + a.z * wt0.z + a.w * wt0.w + b.x * wt1.x + b.y * wt1.y + b.z * wt1.z + b.w * wt1.w;
+      dt = warp_sum(dt);
+    }
+    float dm = a.x * wm0.x + a.y * wm0.y + a.z * wm0.z + a.w * wm0.w + b.x * wm1.x + b.y * wm1.y + b.z * wm1.z + b.w * wm1.w;
+    dm = warp_sum(dm);
+    if (lane == 0) {
+      bool keep = sigmoid_f(dm + p.bm) > p.keep_thr;
+      if (p.use_tok) {
+        const float t = sigmoid_f(dt + p.bt);
+        p.tok[r] = t;
+        if (t < p.thr) atomicAdd(&s_unconf, 1);
+        keep = keep || (t <= p.thr);
+      }
+      if (keep) atomicOr(&s_mask, 1u << rb);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    p.adapt[8 + s * LG_MAXBLK + blk] = (int)s_mask;
+    if (s_unconf) atomicAdd(&p.ctrl[LGC_UNCONF + p.layer], s_unconf);
+  }
+}
+
+struct GatherBlkParams {
+  const int* adapt; int* ctrl; int base[2];
+  int layer, num_points, do_stop, pruning_min_kpts, nblk; float depth_conf;
+  const float* x_in; float* x_out; const float* cos_in; float* cos_out; const float* sin_in; float* sin_out;
+  const int* ind_in; int* ind_out; int* prune[2];
+  __nv_bfloat16* xb_out; int xb_planes; size_t xb_plane;   // bf16 plane copy of x (tensor-core paths)
+};
+
+__global__ void __launch_bounds__(256) k_lg_gather_blk(GatherBlkParams p) {
+  pdl_wait();
+  if (!p.adapt[0]) return;
+  const int s = blockIdx.y, blk = blockIdx.x;
+  const bool lead = blk == 0 && s == 0 && threadIdx.x == 0;
+  if (p.do_stop) {   // upstream check_if_stop; every CTA takes the same decision from the same final count
+    const float ratio = 1.0f - (float)p.ctrl[LGC_UNCONF + p.layer] / (float)p.num_points;
+    if (ratio > p.depth_conf) { if (lead) p.ctrl[LGC_STOP] = 1; return; }
+  }
+  if (lead) p.ctrl[LGC_LAST] = p.layer + 1;
+  const int n = p.adapt[1 + s];
+  const bool prune = n > p.pruning_min_kpts;      // a side that is not eligible keeps every point
+  auto mask_of = [&](int b) -> unsigned {
+    const int left = n - b * 32;
+    if (left <= 0) return 0u;
+    const unsigned live = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+    return prune ? ((unsigned)p.adapt[8 + s * LG_MAXBLK + b] & live) : live;
+  };
+  __shared__ int s_before, s_total;
+  if (threadIdx.x < 32) {
+    int before = 0, total = 0;
+    for (int b = threadIdx.x; b < p.nblk; b += 32) {
+      const int c = __popc(mask_of(b));
+      total += c;
+      if (b < blk) before += c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); total += __shfl_xor_sync(0xffffffffu, total, o); }
+    if (threadIdx.x == 0) { s_before = before; s_total = total; }
+  }
+  __syncthreads();
+  if (blk == 0 && threadIdx.x == 0) { p.ctrl[LGC_M + s] = s_total; p.ctrl[LGC_CAN0 + s] = prune ? 1 : 0; }
+  const unsigned mask = mask_of(blk);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int rb = warp * 4 + q;
+    if (!((mask >> rb) & 1u)) continue;           // uniform per warp
+    const int src = p.base[s] + blk * 32 + rb;
+    const int dst = p.base[s] + s_before + __popc(mask & ((1u << rb) - 1u));
+    const float4* xi = reinterpret_cast<const float4*>(p.x_in + (size_t)src * 256);
+    float4* xo = reinterpret_cast<float4*>(p.x_out + (size_t)dst * 256);
+    const float4 a = xi[2 * lane], b = xi[2 * lane + 1];
+    xo[2 * lane] = a; xo[2 * lane + 1] = b;
+    if (p.xb_out) {
+      float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      for (int pl = 0; pl < p.xb_planes; ++pl) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162 hb = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          w[j] = *reinterpret_cast<const uint32_t*>(&hb);
+          f[2 * j] -= __uint_as_float(w[j] << 16); f[2 * j + 1] -= __uint_as_float(w[j] & 0xFFFF0000u);
+        }
+        *reinterpret_cast<uint4*>(p.xb_out + pl * p.xb_plane + (size_t)dst * 256 + lane * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    p.cos_out[(size_t)dst * 32 + lane] = p.cos_in[(size_t)src * 32 + lane];
+    p.sin_out[(size_t)dst * 32 + lane] = p.sin_in[(size_t)src * 32 + lane];
+    if (lane == 0) {
+      const int orig = p.ind_in[src];
+      p.ind_out[dst] = orig;
+      if (p.prune[s] && prune) p.prune[s][orig] += 1;
+    }
+  }
+}
+
 // gather the surviving rows into the other ping-pong buffers (layer i lives in buffer i & 1 when
 // pruning is enabled).  grid = (ceil(maxrows/8), 2), block 256 (warp per row).  Optionally also
 // writes the bf16 copy of the residual stream that the tensor-core path feeds to TMA.

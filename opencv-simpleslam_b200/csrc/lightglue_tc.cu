@@ -185,7 +185,7 @@ struct LgTensorCore {
 };
 
 static int make_linear(LgTensorCore* tc, const float* w_dev, const float* bias, int N, int K, TcLinear* out) {
-  out->N = N; out->K = K; out->bias = bias; out->BN = N <= 256 ? 64 : 128;
+  out->N = N; out->K = K; out->bias = bias; out->BN = N <= 256 ? 64 : (N % 128 == 0 && N != 768 ? 128 : 96);   // N = 768 (QKV): 8 x 32 tiles of 128 x 96 waste less of the second wave than 6 x 32 of 128 x 128
   const size_t n = (size_t)N * K;
   B2S_TRY(tc->warena.alloc(&out->w, n * tc->np));
   k_weight_planes<<<(unsigned)((n + 255) / 256), 256>>>(w_dev, out->w, N, K, tc->np);
@@ -233,12 +233,15 @@ template <int BN, int NP, int CL>
 static void gemm_attr_cl() {
   cudaFuncSetAttribute(k_gemm_tc<BN, NP, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGemmCfg<BN, NP>::SMEM);
 }
+// measured on B200 (tools/bench_gemm.py): sharing the A tile across a cluster does not shorten these GEMMs (their
+// mainloop is bound by shared-memory bandwidth - MMA operand reads + TMA writes - not by the L2 -> SM fill), so the
+// cluster variant is opt-in (B2S_CLUSTER=1)
 static bool gemm_cluster_enabled() {
-  static const bool on = [] { const char* e = std::getenv("B2S_NO_CLUSTER"); return !(e && e[0] == '1'); }();
+  static const bool on = [] { const char* e = std::getenv("B2S_CLUSTER"); return e && e[0] == '1'; }();
   return on;
 }
 static void tc_kernel_attrs() {
-  gemm_attr<64, 1>(); gemm_attr<128, 1>(); gemm_attr<64, 3>(); gemm_attr<128, 3>();
+  gemm_attr<64, 1>(); gemm_attr<128, 1>(); gemm_attr<64, 3>(); gemm_attr<128, 3>(); gemm_attr<96, 1>(); gemm_attr<96, 3>();
   gemm_attr_cl<64, 1, 4>(); gemm_attr_cl<128, 1, 4>(); gemm_attr_cl<128, 1, 2>();
   gemm_attr_cl<64, 3, 4>(); gemm_attr_cl<128, 3, 4>(); gemm_attr_cl<128, 3, 2>();
   cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
@@ -318,7 +321,10 @@ static int tc_gemm(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& a1, con
   };
   const CUtensorMap *c1 = a32(a1), *c2 = a32(a2);
   const int cl = (gemm_cluster_enabled() && c1 && c2) ? (grid.x % 4 == 0 ? 4 : (grid.x % 2 == 0 && w.BN == 128 ? 2 : 1)) : 1;
-  if (tc->np == 1) {
+  if (w.BN == 96) {
+    if (tc->np == 1) launch_k(k_gemm_tc<96, 1>, grid, TcGemmCfg<96, 1>::THREADS, TcGemmCfg<96, 1>::SMEM, st, a1, a2, w.map, p);
+    else launch_k(k_gemm_tc<96, 3>, grid, TcGemmCfg<96, 3>::THREADS, TcGemmCfg<96, 3>::SMEM, st, a1, a2, w.map, p);
+  } else if (tc->np == 1) {
     if (w.BN == 64) {
       if (cl == 4) launch_k_cluster(k_gemm_tc<64, 1, 4>, grid, TcGemmCfg<64, 1>::THREADS, TcGemmCfg<64, 1>::SMEM, st, 4, *c1, *c2, w.map, p);
       else launch_k(k_gemm_tc<64, 1>, grid, TcGemmCfg<64, 1>::THREADS, TcGemmCfg<64, 1>::SMEM, st, a1, a2, w.map, p);
@@ -548,7 +554,7 @@ extern "C" int b2s_bench_gemm_tc3(int M, int N, int K, int cl, int iters, float*
   const int np = 3;
   DeviceArena ar;
   const int Mp = cdiv(M, 128) * 128;
-  const int BN = N <= 256 ? 64 : 128;
+  const int BN = N <= 256 ? 64 : (N % 128 == 0 && N != 768 ? 128 : 96);
   __nv_bfloat16 *dA, *dW, *dO; float* dB; unsigned long long* dts;
   const size_t nA = (size_t)np * Mp * K, nW = (size_t)np * N * K, nO = (size_t)np * Mp * N;
   B2S_TRY(ar.alloc(&dA, nA)); B2S_TRY(ar.alloc(&dW, nW)); B2S_TRY(ar.alloc(&dO, nO)); B2S_TRY(ar.alloc(&dB, (size_t)N));
@@ -573,7 +579,8 @@ extern "C" int b2s_bench_gemm_tc3(int M, int N, int K, int cl, int iters, float*
   B2S_CUDA(cudaStreamCreate(&st));
   auto launch = [&](unsigned long long* ts) {
     TcGemmParams q = p; q.ts = ts;
-    if (BN == 64) {
+    if (BN == 96) launch_k(k_gemm_tc<96, 3>, grid, TcGemmCfg<96, 3>::THREADS, TcGemmCfg<96, 3>::SMEM, st, ma, ma, mw, q);
+    else if (BN == 64) {
       if (cl == 4) launch_k_cluster(k_gemm_tc<64, 3, 4>, grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, 4, ma32, ma32, mw, q);
       else launch_k(k_gemm_tc<64, 3>, grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, ma, ma, mw, q);
     } else {
