@@ -90,6 +90,8 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // lets the NEXT kernel start launching, pdl_wait() blocks until the PREVIOUS kernel has completed
 // and its memory is visible - it must precede the first access to any buffer another kernel writes
 // or reads (activations, workspaces, counters); constant weights may be read before it.
+// (Measured: an early pdl_trigger() in the small kernels makes the pair slower - parked CTAs of the next kernel take
+// issue slots from the running one - so only the tensor-core kernels, whose prologue is worth overlapping, trigger early.)
 #if defined(__CUDACC__)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

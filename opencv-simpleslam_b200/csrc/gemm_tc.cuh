@@ -38,6 +38,7 @@ struct TcGemmParams {
   const int* m_dev; int m_mult;     // nullable: live rows of segment 0 = *m_dev * m_mult (ALIKED keypoint count)
   int act;                          // 0 none, 1 SELU (after bias / residual)
   const float* residual; int ld_res; // nullable fp32 [rows, ld_res]: added after bias * alpha, before the activation
+  float* out_f32_t; int ld_f32_t;    // TC_EPI_F32, nullable: also write the transposed result out_f32_t[col * ld_f32_t + row]
   unsigned long long* ts;            // nullable profiling hook: per CTA 6 globaltimer stamps (b2s_bench_gemm_tc3)
 };
 
@@ -315,6 +316,15 @@ __global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __
           myrow[q ^ (lane & 7)] = make_uint4(__float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]), __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3]));
         __syncwarp();
         store_f32_tile(gc);
+        if (p.out_f32_t) {
+          // transposed copy (similarity^T for the column-wise statistics of the assignment): lane = row of the chunk,
+          // so one store instruction writes 32 consecutive floats of a transposed row
+          const int ncol = n_live - gc < 32 ? n_live - gc : 32;
+          if (lane < rows_q) {
+            for (int c = 0; c < ncol; ++c)
+              p.out_f32_t[(size_t)(gc + c) * p.ld_f32_t + qrow0 + lane] = sf[lane * 32 + ((((c >> 2) ^ (lane & 7)) << 2) | (c & 3))];
+          }
+        }
         __syncwarp();
         continue;
       }

@@ -27,7 +27,7 @@ struct b2s_lg {
   // workspace (rows = 2*cap; image0 at row 0, image1 at row cap)
   int cap = 0;
   float *kn = nullptr, *cosb[2] = {nullptr, nullptr}, *sinb[2] = {nullptr, nullptr}, *x[2] = {nullptr, nullptr};
-  float *qkv = nullptr, *ctx = nullptr, *msg = nullptr, *h1 = nullptr, *tok = nullptr, *sim = nullptr;
+  float *qkv = nullptr, *ctx = nullptr, *msg = nullptr, *h1 = nullptr, *tok = nullptr, *sim = nullptr, *simT = nullptr;
   float *rmax = nullptr, *rlog = nullptr, *cmax = nullptr, *clog = nullptr, *ls = nullptr, *max0 = nullptr;
   int *ind[2] = {nullptr, nullptr}, *keep = nullptr, *srcmap = nullptr, *adapt = nullptr, *m0 = nullptr, *m1 = nullptr, *ctrl = nullptr;
   const float** wfinal_tab = nullptr; const float** bfinal_tab = nullptr; const float** wmatch_tab = nullptr;  // device tables [L]
@@ -75,6 +75,7 @@ static int lg_alloc_ws(b2s_lg* h, int cap) {
   B2S_TRY(h->wsarena.alloc(&h->h1, R * 512));
   B2S_TRY(h->wsarena.alloc(&h->tok, R));
   B2S_TRY(h->wsarena.alloc(&h->sim, (size_t)cap * cap));
+  B2S_TRY(h->wsarena.alloc(&h->simT, (size_t)cap * cap));   // transposed similarity (tensor-core path)
   B2S_TRY(h->wsarena.alloc(&h->rmax, (size_t)cap));
   B2S_TRY(h->wsarena.alloc(&h->rlog, (size_t)cap));
   B2S_TRY(h->wsarena.alloc(&h->cmax, (size_t)cap));
@@ -500,7 +501,7 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
   }
   const int ld = cap;
   if (h->tc) {
-    B2S_TRY(lgtc_assignment(h->tc, st, h->x[0], do_prune ? h->x[1] : nullptr, cap, m, n, h->ctrl, h->sim, &h->launches));
+    B2S_TRY(lgtc_assignment(h->tc, st, h->x[0], do_prune ? h->x[1] : nullptr, cap, m, n, h->ctrl, h->sim, h->simT, &h->launches));
   } else {
     GemmParams g;
     g.A1 = md; g.lda1 = 256; g.K1 = 256; g.W = md + (size_t)cap * 256; g.ldw = 256; g.K = 256;
@@ -509,10 +510,19 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
     B2S_TRY(gemm_simt(g, st, &h->launches));
   }
   const int* ctrl = h->ctrl;
-  launch_k(k_lg_row_lse, cdiv(m, 8), 256, 0, st, h->sim, ld, ctrl, h->rmax, h->rlog);
-  launch_k(k_lg_col_lse, cdiv(n, 32), 1024, 0, st, h->sim, ld, ctrl, h->cmax, h->clog);
-  launch_k(k_lg_row_argmax, cdiv(m, 8), 256, 0, st, h->sim, ld, ctrl, h->rmax, h->rlog, h->cmax, h->clog, h->ls, h->ls + cap, h->max0, h->m0);
-  launch_k(k_lg_col_argmax, cdiv(n, 32), 1024, 0, st, h->sim, ld, ctrl, h->rmax, h->rlog, h->cmax, h->clog, h->ls, h->ls + cap, h->m1);
+  if (h->tc) {
+    // both directions per launch on sim / sim^T (written by the similarity GEMM's epilogue)
+    Lse2Params lp = {h->sim, h->simT, ld, ctrl, h->rmax, h->rlog, h->cmax, h->clog};
+    launch_k(k_lg_lse2, dim3(cdiv(std::max(m, n), 8), 2), 256, 0, st, lp);
+    Argmax2Params ap = {h->sim, h->simT, ld, ctrl, h->rmax, h->rlog, h->cmax, h->clog, h->ls, h->ls + cap, h->max0, h->m0, h->m1};
+    launch_k(k_lg_argmax2, dim3(cdiv(std::max(m, n), 8), 2), 256, 0, st, ap);
+    h->launches -= 2;
+  } else {
+    launch_k(k_lg_row_lse, cdiv(m, 8), 256, 0, st, h->sim, ld, ctrl, h->rmax, h->rlog);
+    launch_k(k_lg_col_lse, cdiv(n, 32), 1024, 0, st, h->sim, ld, ctrl, h->cmax, h->clog);
+    launch_k(k_lg_row_argmax, cdiv(m, 8), 256, 0, st, h->sim, ld, ctrl, h->rmax, h->rlog, h->cmax, h->clog, h->ls, h->ls + cap, h->max0, h->m0);
+    launch_k(k_lg_col_argmax, cdiv(n, 32), 1024, 0, st, h->sim, ld, ctrl, h->rmax, h->rlog, h->cmax, h->clog, h->ls, h->ls + cap, h->m1);
+  }
   FilterParams fp = {};
   fp.th = h->cfg.filter_thresh; fp.max0 = h->max0; fp.m0 = h->m0; fp.m1 = h->m1;
   fp.ctrl = h->ctrl; fp.cap = cap; fp.stop_layer = stop_layer;

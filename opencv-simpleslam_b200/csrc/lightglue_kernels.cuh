@@ -660,6 +660,82 @@ __global__ void __launch_bounds__(1024) k_lg_col_argmax(const float* sim, int ld
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// K14/K15 on the tensor-core path: the similarity GEMM also writes sim^T, so the column-wise statistics are row-wise
+// ones of the transposed matrix and both directions run in the same launch (blockIdx.y = direction), one warp per row,
+// 128-bit loads.  Same per-element arithmetic as the four kernels above.
+// ---------------------------------------------------------------------------------------
+struct Lse2Params { const float* sim; const float* simT; int ld; const int* ctrl; float* rmax; float* rlog; float* cmax; float* clog; };
+
+__global__ void __launch_bounds__(256) k_lg_lse2(Lse2Params p) {
+  pdl_wait();
+  const int d = blockIdx.y;
+  const int m = p.ctrl[LGC_M + d], n = p.ctrl[LGC_M + 1 - d];    // rows / columns in this direction
+  if (p.ctrl[LGC_M] <= 0 || p.ctrl[LGC_N] <= 0) return;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= m) return;
+  const int lane = threadIdx.x & 31;
+  const float* r = (d ? p.simT : p.sim) + (size_t)i * p.ld;
+  const int n4 = n & ~3;
+  float mx = -INFINITY;
+  for (int j = lane * 4; j < n4; j += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(r + j);
+    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  for (int j = n4 + lane; j < n; j += 32) mx = fmaxf(mx, r[j]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane * 4; j < n4; j += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(r + j);
+    sum += (expf(v.x - mx) + expf(v.y - mx)) + (expf(v.z - mx) + expf(v.w - mx));
+  }
+  for (int j = n4 + lane; j < n; j += 32) sum += expf(r[j] - mx);
+  sum = warp_sum(sum);
+  if (lane == 0) { (d ? p.cmax : p.rmax)[i] = mx; (d ? p.clog : p.rlog)[i] = logf(sum); }
+}
+
+struct Argmax2Params {
+  const float* sim; const float* simT; int ld; const int* ctrl;
+  const float* rmax; const float* rlog; const float* cmax; const float* clog; const float* ls0; const float* ls1;
+  float* max0; int* m0; int* m1;
+};
+
+__global__ void __launch_bounds__(256) k_lg_argmax2(Argmax2Params p) {
+  pdl_wait();
+  const int d = blockIdx.y;
+  const int m = p.ctrl[LGC_M + d], n = p.ctrl[LGC_M + 1 - d];
+  if (p.ctrl[LGC_M] <= 0 || p.ctrl[LGC_N] <= 0) return;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= m) return;
+  const int lane = threadIdx.x & 31;
+  const float* r = (d ? p.simT : p.sim) + (size_t)i * p.ld;
+  // direction 0: row i of image 0 against columns j of image 1; direction 1: the roles swap but assign_val keeps
+  // upstream's operand order (row statistics first)
+  const float* omax = d ? p.rmax : p.cmax; const float* olog = d ? p.rlog : p.clog; const float* ols = d ? p.ls0 : p.ls1;
+  const float smax = (d ? p.cmax : p.rmax)[i], slog = (d ? p.clog : p.rlog)[i], sls = (d ? p.ls1 : p.ls0)[i];
+  float best = -INFINITY; int bj = 0x7fffffff;
+  auto consider = [&](float sv, int j) {
+    const float v = d ? assign_val(sv, omax[j], olog[j], smax, slog, ols[j], sls) : assign_val(sv, smax, slog, omax[j], olog[j], sls, ols[j]);
+    if (v > best) { best = v; bj = j; }
+  };
+  const int n4 = n & ~3;
+  for (int j = lane * 4; j < n4; j += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(r + j);
+    consider(v.x, j); consider(v.y, j + 1); consider(v.z, j + 2); consider(v.w, j + 3);
+  }
+  for (int j = n4 + lane; j < n; j += 32) consider(r[j], j);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+    if (ob > best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+  }
+  if (lane == 0) {
+    if (d) p.m1[i] = bj == 0x7fffffff ? 0 : bj;
+    else { p.max0[i] = best; p.m0[i] = bj == 0x7fffffff ? 0 : bj; }
+  }
+}
+
 // K15c: upstream filter_matches + match list.  Single CTA of 1024 threads.
 struct FilterParams {
   int m, n; float th;                        // m, n are read from ctrl on the device

@@ -419,7 +419,7 @@ int lgtc_set_final(LgTensorCore* tc, const std::vector<const float*>& w, const s
 // x0 / x1: the two ping-pong residual buffers (x1 null when pruning is off); the last executed layer,
 // its buffer and the live sizes are read from ctrl on the device.
 int lgtc_assignment(LgTensorCore* tc, cudaStream_t st, const float* x0, const float* x1, int cap, int m, int n, const int* ctrl,
-                    float* sim, long long* launches) {
+                    float* sim, float* simT, long long* launches) {
   if (cap != tc->cap) { set_error("lgtc_assignment: workspace capacity mismatch"); return B2S_EINVAL; }
   const size_t plane = (size_t)2 * cap * 256;
   dim3 g(cdiv(std::max(m, n), 8), 2);
@@ -434,7 +434,7 @@ int lgtc_assignment(LgTensorCore* tc, cudaStream_t st, const float* x0, const fl
   p.K = 256; p.K1 = 256; p.N = n; p.bias = nullptr; p.ctrl = ctrl; p.ctrl_mode = 3;
   p.w_plane_rows = 2 * cap; p.w_row0 = cap;
   p.seg_base[0] = 0; p.seg_base[1] = 0; p.seg_rows[0] = m; p.seg_rows[1] = 0; p.tiles0 = cdiv(m, 128);
-  p.plane_rows = 2 * cap; p.epi = TC_EPI_F32; p.out_f32 = sim; p.ld_f32 = cap;
+  p.plane_rows = 2 * cap; p.epi = TC_EPI_F32; p.out_f32 = sim; p.ld_f32 = cap; p.out_f32_t = simT; p.ld_f32_t = cap;
   launch_k(k_gemm_tc<128, 3>, dim3(cdiv(n, 128), p.tiles0), TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, tc->m_md, tc->m_md, tc->m_md, p);
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
   if (launches) *launches += 3;

@@ -19,7 +19,7 @@ int lgtc_set_final(LgTensorCore* tc, const std::vector<const float*>& w, const s
 int lgtc_alloc_ws(LgTensorCore* tc, int cap);
 // assignment head: md = final_proj_last(x)/4 (both images), sim = md0 md1^T, always fp32-faithful (bf16x3)
 int lgtc_assignment(LgTensorCore* tc, cudaStream_t st, const float* x0, const float* x1, int cap, int m, int n, const int* ctrl,
-                    float* sim, long long* launches);
+                    float* sim, float* simT, long long* launches);
 // one full transformer layer (self + cross) in place on x [2*cap,256] fp32 master copy; m, n bound the
 // live counts (grid sizes), the live counts / early-exit flag come from the device state `ctrl`
 int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int layer, float* x, const float* cosb, const float* sinb, int cap,
