@@ -256,6 +256,8 @@ int b2s_test_attn_tc3(const float* q, const float* k, const float* v, int nq, in
 /* device-only timing of one self-block attention launch (2 problems x 4 heads, nq x nk), mean ms per launch */
 int b2s_bench_attn_tc(int nq, int nk, int iters, float* ms_out);
 int b2s_bench_attn_tc3(int nq, int nk, int iters, float* ms_out);
+/* same, plus SM-clock stamps of CTA (0,0,0) of one extra launch: trace_out [3 roles][64 tiles][8 events] (tools/trace_attn.py) */
+int b2s_trace_attn_tc3(int nq, int nk, int iters, float* ms_out, long long* trace_out);
 
 /* device-only timing of one bf16x3 layer-GEMM shape, `iters` launches back to back (PDL), clusters of `cl` CTAs sharing
  * the A tile (1 = none); ts_out (nullable) receives 6 globaltimer stamps (ns, relative) per CTA of one extra launch */

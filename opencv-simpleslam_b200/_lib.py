@@ -67,6 +67,7 @@ SIGNATURES = {
     "b2s_test_gemm_tc3": (C.c_int, [f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, f32p]),
     "b2s_test_attn_tc3": (C.c_int, [f32p, f32p, f32p, C.c_int, C.c_int, f32p]),
     "b2s_bench_attn_tc3": (C.c_int, [C.c_int, C.c_int, C.c_int, f32p]),
+    "b2s_trace_attn_tc3": (C.c_int, [C.c_int, C.c_int, C.c_int, f32p, vp]),
     "b2s_bench_gemm_tc3": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, vp, i32p]),
     "b2s_aliked_launch_count": (C.c_longlong, [vp]),
     "b2s_lg_launch_count": (C.c_longlong, [vp]),

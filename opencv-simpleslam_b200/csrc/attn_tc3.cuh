@@ -28,7 +28,8 @@ constexpr int A3_SLOT = A3_NP * A3_KPL;              // 24 KB: one V slot
 constexpr int A3_KSLOTS = 2, A3_KSLOT = A3_NP * A3_QPL;   // 48 KB: one K slot = a pair of key tiles
 constexpr int A3_SMEM = A3_NP * A3_QPL + A3_KSLOTS * A3_KSLOT + A3_SLOTS * A3_SLOT + 1024 + 256;
 constexpr int A3_THREADS = 384;
-static_assert(66 * 128 * 4 <= A3_KSLOTS * A3_KSLOT, "the final merge buffer aliases the K ring");
+static_assert(2 * 66 * 128 * 4 <= A3_KSLOTS * A3_KSLOT, "the final merge buffers alias the K ring");
+static_assert(8 * 2048 <= A3_SLOTS * A3_SLOT, "the output staging tiles alias the V ring");
 
 struct Attn3Params {
   AttnTcProb prob[2];
@@ -38,13 +39,16 @@ struct Attn3Params {
   __nv_bfloat16* out; int ldo; size_t out_plane;   // ctx planes [3][2*cap, 256] bf16
   const int* ctrl; int cross;
   unsigned long long* stats;       // nullable: stats[cross] += nq * nk of every live problem
+  int trace_cta;                   // CTA to trace: x | y << 8 | z << 16
+  long long* trace;                // nullable profiling hook (b2s_trace_attn_tc3): clock64 stamps of CTA (0,0,0), [role][tile][event]
 };
 
-// P chunk c (32 keys) of one row -> three planes in tensor memory (16 columns each); returns the partial row sum
+// P chunk c (32 keys) of one row -> three bf16 planes in REGISTERS (16 packed words each); returns the partial row sum.
+// The planes go to tensor memory later (a3_store_p_chunk), once the previous P V of the group has retired: everything
+// that does not depend on that MMA (exponentials, plane split) is done while it is still running.
 template <bool MASK>
-__device__ __forceinline__ float a3_write_p_chunk(const uint32_t (&v)[32], int c, uint32_t p_addr, int limit, float scale, float m_used) {
+__device__ __forceinline__ float a3_make_p_chunk(const uint32_t (&v)[32], int c, int limit, float scale, float m_used, uint32_t (&pk)[A3_NP][16]) {
   float sum0 = 0.f, sum1 = 0.f;
-  uint32_t pk[A3_NP][16];
 #pragma unroll
   for (int t = 0; t < 32; t += 2) {
     float p0 = ex2_approx(fmaf(__uint_as_float(v[t]), scale, -m_used));
@@ -59,9 +63,11 @@ __device__ __forceinline__ float a3_write_p_chunk(const uint32_t (&v)[32], int c
 #pragma unroll
     for (int pl = 0; pl < A3_NP; ++pl) pk[pl][t >> 1] = w[pl];
   }
+  return sum0 + sum1;
+}
+__device__ __forceinline__ void a3_store_p_chunk(const uint32_t (&pk)[A3_NP][16], int c, uint32_t p_addr) {
 #pragma unroll
   for (int pl = 0; pl < A3_NP; ++pl) tc::tmem_st16(p_addr + pl * 32 + c * 16, pk[pl]);
-  return sum0 + sum1;
 }
 
 __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constant__ CUtensorMap mapQ,
@@ -79,6 +85,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
   uint64_t* p_full = s_free + 2;               uint64_t* o_full = p_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
+  const long long t_entry = clock64();
   AttnTcProb pr = p.prob[blockIdx.z];
   const int q0 = blockIdx.x * A3_BQ;
   if (!p.ctrl && q0 >= pr.nq) return;                    // uniform per CTA (static sizes)
@@ -114,7 +121,11 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
   const int nt = live ? (pr.nk + A3_BK - 1) / A3_BK : 0;
   if (p.stats && live && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
     atomicAdd(&p.stats[p.cross ? 1 : 0], (unsigned long long)pr.nq * (unsigned long long)pr.nk);
-  const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 256;   // S[g] + 64 g, O[g] + 64 g, P[g] + 96 g
+  const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 256;
+  const bool tr = p.trace && (int)(blockIdx.x | (blockIdx.y << 8) | (blockIdx.z << 16)) == p.trace_cta;
+  auto stamp = [&](int role, int tile, int ev) { if (tr) p.trace[(role * 64 + tile) * 8 + ev] = clock64(); };
+  if (tr && threadIdx.x == 0) p.trace[(0 * 64 + 63) * 8 + 0] = t_entry;   // kernel entry
+  if (threadIdx.x == 0) stamp(0, 63, 1);                   // dependencies resolved, sizes known   // S[g] + 64 g, O[g] + 64 g, P[g] + 96 g
 
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -127,15 +138,22 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
 #pragma unroll
       for (int pl = 0; pl < A3_NP; ++pl)
         tc::tma_load_2d(sQ + pl * A3_QPL, &mapQ, q_full, p.qcol + h * 64, pl * p.plane_rows + pr.q_row + q0);
-      for (int j = 0; j < nt; ++j) {
-        if ((j & 1) == 0) {                                  // K: one 128-key tile per pair of key tiles
-          const int jp = j >> 1, kb = jp % A3_KSLOTS, kph = (jp / A3_KSLOTS) & 1;
-          tc::mbar_wait(&k_empty[kb], kph ^ 1);
-          tc::mbar_expect_tx(&k_full[kb], A3_KSLOT);
+      // K arrives as 128-key tiles, one per pair of key tiles, and is requested ONE PAIR AHEAD of the V tiles: its ring
+      // slot frees as soon as the score MMAs of pair jp - 1 retire, whereas a V slot only frees after the P V of three
+      // tiles earlier - issued in tile order, a K request would queue behind that wait and land too late for the next
+      // score pair (measured: ~1500 cycles of the S issuer waiting for K per pair).
+      auto load_k = [&](int jp) {
+        const int kb = jp % A3_KSLOTS, kph = (jp / A3_KSLOTS) & 1;
+        tc::mbar_wait(&k_empty[kb], kph ^ 1);
+        tc::mbar_expect_tx(&k_full[kb], A3_KSLOT);
 #pragma unroll
-          for (int pl = 0; pl < A3_NP; ++pl)
-            tc::tma_load_2d(sK + kb * A3_KSLOT + pl * A3_QPL, &mapQ, &k_full[kb], p.kcol + h * 64, pl * p.plane_rows + pr.k_row + j * A3_BK);
-        }
+        for (int pl = 0; pl < A3_NP; ++pl)
+          tc::tma_load_2d(sK + kb * A3_KSLOT + pl * A3_QPL, &mapQ, &k_full[kb], p.kcol + h * 64, pl * p.plane_rows + pr.k_row + jp * 2 * A3_BK);
+      };
+      const int npairs = (nt + 1) >> 1;
+      if (npairs > 0) load_k(0);
+      for (int j = 0; j < nt; ++j) {
+        if ((j & 1) == 0 && (j >> 1) + 1 < npairs) load_k((j >> 1) + 1);
         const int b = j % A3_SLOTS, ph = (j / A3_SLOTS) & 1;
         tc::mbar_wait(&v_empty[b], ph ^ 1);
         tc::mbar_expect_tx(&v_full[b], A3_SLOT);
@@ -148,12 +166,12 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
     if (tc::elect_one()) {
       using Terms = tc::PlaneTerms<A3_NP>;
       constexpr uint32_t idesc_s = tc::idesc_bf16(128, 128, 0, 0);   // S pair: A = Q (K-major), B = 128 keys (K-major)
-      constexpr uint32_t idesc_o = tc::idesc_bf16(128, 64, 0, 1);    // PV: A = P (tensor memory), B = V (MN-major)
       const uint32_t q_addr = tc::smem_u32(sQ);
       auto issue_s_pair = [&](int jp) {                              // tiles 2jp (-> S[0]) and 2jp + 1 (-> S[1])
         const int b = jp % A3_KSLOTS, ph = (jp / A3_KSLOTS) & 1;
         tc::mbar_wait(&k_full[b], ph);
         tc::tc_fence_after();
+        stamp(0, jp, 0);                                   // K pair landed, S pair issue starts
         const uint32_t k_addr = tc::smem_u32(sK + b * A3_KSLOT);
 #pragma unroll
         for (int t = 0; t < Terms::N; ++t)
@@ -166,11 +184,34 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
         tc::umma_commit(&s_full[0]);
         tc::umma_commit(&s_full[1]);
         tc::umma_commit(&k_empty[b]);
+        stamp(0, jp, 1);                                   // S pair issued
       };
-      auto issue_pv = [&](int j) {
+      tc::mbar_wait(q_full, 0);
+      issue_s_pair(0);
+      const int npairs = (nt + 1) >> 1;
+      for (int jp = 0; jp + 1 < npairs; ++jp) {
+        const int ph = jp & 1;                // both groups have their score tiles in registers: next pair can start
+        tc::mbar_wait(&s_free[0], ph);
+        tc::mbar_wait(&s_free[1], ph);
+        stamp(0, jp, 6);
+        issue_s_pair(jp + 1);
+      }
+    }
+  } else if (warp == 10) {
+    // ===== second MMA issuer: the P V products.  An issuing thread is blocked for about as long as its MMAs execute
+    //       and every commit / barrier round trip costs it a few hundred cycles, so with ONE issuer the tensor pipe idles
+    //       between the S pair and the two P V groups of a tile pair (measured: 3440 busy of 4735 cycles per pair).  The
+    //       score and the P V MMAs touch disjoint tensor-memory columns and are ordered by mbarriers only (s_free / p_full /
+    //       o_full), so they can be issued from two threads whose gaps overlap. =====
+    if (tc::elect_one()) {
+      using Terms = tc::PlaneTerms<A3_NP>;
+      constexpr uint32_t idesc_o = tc::idesc_bf16(128, 64, 0, 1);    // PV: A = P (tensor memory), B = V (MN-major)
+      for (int j = 0; j < nt; ++j) {
         const int b = j % A3_SLOTS, ph = (j / A3_SLOTS) & 1, g = j & 1;
+        tc::mbar_wait(&p_full[g], (j >> 1) & 1);      // P of tile j is in tensor memory
         tc::mbar_wait(&v_full[b], ph);
         tc::tc_fence_after();
+        stamp(0, j >> 1, 2 + 2 * (j & 1));
         const uint32_t v_addr = tc::smem_u32(sV + b * A3_SLOT);
 #pragma unroll
         for (int t = 0; t < Terms::N; ++t)
@@ -182,23 +223,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
           }
         tc::umma_commit(&o_full[g]);
         tc::umma_commit(&v_empty[b]);
-      };
-      tc::mbar_wait(q_full, 0);
-      issue_s_pair(0);
-      const int npairs = (nt + 1) >> 1;
-      for (int jp = 0; jp < npairs; ++jp) {
-        const int ph = jp & 1;
-        if (jp + 1 < npairs) {                // both groups have their score tiles in registers: next pair can start
-          tc::mbar_wait(&s_free[0], ph);
-          tc::mbar_wait(&s_free[1], ph);
-          issue_s_pair(jp + 1);
-        }
-        tc::mbar_wait(&p_full[0], ph);        // P of tile 2jp is in tensor memory
-        issue_pv(2 * jp);
-        if (2 * jp + 1 < nt) {
-          tc::mbar_wait(&p_full[1], ph);
-          issue_pv(2 * jp + 1);
-        }
+        stamp(0, j >> 1, 3 + 2 * (j & 1));
       }
     }
   } else if (warp < 8) {
@@ -228,6 +253,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
     for (int j = g; j < nt; j += 2, ++t) {
       tc::mbar_wait(&s_full[g], t & 1);
       tc::tc_fence_after();
+      if (quad == 0 && lane == 0) stamp(1 + g, t, 0);       // S tile complete (seen by the group)
       uint32_t s[2][32];
       tc::tmem_ld32(s_addr, s[0]); tc::tmem_ld32(s_addr + 32, s[1]);
       tc::tmem_ld_wait();
@@ -239,31 +265,44 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
       if (full) mx = fmaxf(atc_chunk_max<false>(s[0], 0, limit), atc_chunk_max<false>(s[1], 1, limit));
       else mx = fmaxf(atc_chunk_max<true>(s[0], 0, limit), atc_chunk_max<true>(s[1], 1, limit));
       const float mxs = mx * p.scale_log2e;
+      // reference maximum of this tile (lazy: raised only beyond 2^8) - decided before the exponentials
+      float corr = 1.f;
+      bool rescale = false;
       if (t == 0) {
         m_used = mxs;
-      } else {
-        // PV of the group's previous tile must have retired before P[g] is rewritten; collect its result
+      } else if (__any_sync(0xffffffffu, mxs > m_used + ATC_LAZY)) {
+        const float m_new = fmaxf(m_used, mxs);
+        corr = ex2_approx(m_used - m_new);                // 1 for rows whose reference did not move
+        m_used = m_new;
+        rescale = true;
+      }
+      uint32_t pk0[A3_NP][16], pk1[A3_NP][16];
+      float sum;
+      if (full) sum = a3_make_p_chunk<false>(s[0], 0, limit, p.scale_log2e, m_used, pk0) + a3_make_p_chunk<false>(s[1], 1, limit, p.scale_log2e, m_used, pk1);
+      else sum = a3_make_p_chunk<true>(s[0], 0, limit, p.scale_log2e, m_used, pk0) + a3_make_p_chunk<true>(s[1], 1, limit, p.scale_log2e, m_used, pk1);
+      if (t > 0) {
+        // PV of the group's previous tile must have retired before P[g] is rewritten; collect its result (it was
+        // computed against the previous reference maximum: add first, rescale afterwards)
+        if (quad == 0 && lane == 0) stamp(1 + g, t, 1);     // exponentials / planes done
         tc::mbar_wait(&o_full[g], (t - 1) & 1);
         tc::tc_fence_after();
+        if (quad == 0 && lane == 0) stamp(1 + g, t, 2);     // previous P V retired
         add_pv();
-        if (__any_sync(0xffffffffu, mxs > m_used + ATC_LAZY)) {   // lazy: raise the reference max only beyond 2^8
-          const float m_new = fmaxf(m_used, mxs);
-          const float corr = ex2_approx(m_used - m_new);  // 1 for rows whose reference did not move
-          l_run *= corr; m_used = m_new;
+        if (rescale) {
+          l_run *= corr;
 #pragma unroll
           for (int d = 0; d < A3_D; ++d) o[d] *= corr;
         }
       }
-      float sum;
-      if (full) sum = a3_write_p_chunk<false>(s[0], 0, p_addr, limit, p.scale_log2e, m_used) +
-                      a3_write_p_chunk<false>(s[1], 1, p_addr, limit, p.scale_log2e, m_used);
-      else sum = a3_write_p_chunk<true>(s[0], 0, p_addr, limit, p.scale_log2e, m_used) +
-                 a3_write_p_chunk<true>(s[1], 1, p_addr, limit, p.scale_log2e, m_used);
       l_run += sum;
+      a3_store_p_chunk(pk0, 0, p_addr);
+      a3_store_p_chunk(pk1, 1, p_addr);
       tc::tmem_st_wait();               // P is in tensor memory
       tc::tc_fence_before();            // order our tcgen05.ld / st before the MMAs that follow the arrive
       tc::mbar_arrive(&p_full[g]);
+      if (quad == 0 && lane == 0) stamp(1 + g, t, 3);       // P published
     }
+    if (quad == 0 && lane == 0) stamp(1 + g, 63, 0);        // key loop done
     // ---- the group's last PV ----
     if (t > 0) {
       tc::mbar_wait(&o_full[g], (t - 1) & 1);
@@ -273,40 +312,55 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
     const float m_run = m_used;
     tc::tc_fence_before();
     // ---- merge the two groups' partial softmax states (every MMA and every TMA load has completed) ----
-    float* mrg = reinterpret_cast<float*>(sK);            // [66][128] floats: O^T (64 rows), m, l
+    // Both groups park their state in shared memory ([d][row] floats, the K ring is idle), then group g produces output
+    // dims [32 g, 32 g + 32) of every row: merge, split into planes, and - as thread == row would make every store
+    // instruction touch 32 lines - write through a swizzled staging tile so that a store covers 8 rows x 64 B.
+    float* mrg = reinterpret_cast<float*>(sK) + g * (66 * 128);       // [66][128]: O^T (64 rows), m, l of group g
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (g == 1) {
 #pragma unroll
-      for (int d = 0; d < A3_D; ++d) mrg[d * 128 + r] = o[d];
-      mrg[64 * 128 + r] = m_run; mrg[65 * 128 + r] = l_run;
-    }
+    for (int d = 0; d < A3_D; ++d) mrg[d * 128 + r] = o[d];
+    mrg[64 * 128 + r] = m_run; mrg[65 * 128 + r] = l_run;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (g == 0 && q0 + r < pr.nq) {
-      const float m_b = mrg[64 * 128 + r], l_b = mrg[65 * 128 + r];
-      const float m = fmaxf(m_run, m_b);
-      const float ca = ex2_approx(m_run - m), cb = (m_b == -INFINITY) ? 0.f : ex2_approx(m_b - m);
-      const float inv = 1.f / (l_run * ca + l_b * cb);
+    {
+      const float* ma = reinterpret_cast<const float*>(sK);            // group 0's state
+      const float* mb = ma + 66 * 128;                                 // group 1's state
+      const float m_a = ma[64 * 128 + r], l_a = ma[65 * 128 + r], m_b = mb[64 * 128 + r], l_b = mb[65 * 128 + r];
+      const float m = fmaxf(m_a, m_b);
+      const float ca = ex2_approx(m_a - m), cb = (m_b == -INFINITY) ? 0.f : ex2_approx(m_b - m);
+      const float inv = 1.f / (l_a * ca + l_b * cb);
       const float fa = ca * inv, fb = cb * inv;
-      __nv_bfloat16* dst = p.out + (size_t)(pr.q_row + q0 + r) * p.ldo + h * 64;
+      float f[32];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        uint32_t w[A3_NP][4];
+      for (int e = 0; e < 32; ++e) { const int d = 32 * g + e; f[e] = ma[d * 128 + r] * fa + mb[d * 128 + r] * fb; }
+      uint32_t* sp = reinterpret_cast<uint32_t*>(sV) + warp * 512;     // staging tile of this warp: [32 rows][16 words]
+      const int rows_q = pr.nq - q0 - quad * 32;                       // live rows of this warp's quadrant
+      __nv_bfloat16* dst = p.out + (size_t)(pr.q_row + q0 + quad * 32) * p.ldo + h * 64 + 32 * g;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int d = 8 * q + 2 * e;
-          uint32_t pw[A3_NP];
-          tc::pack_planes2<A3_NP>(o[d] * fa + mrg[d * 128 + r] * fb, o[d + 1] * fa + mrg[(d + 1) * 128 + r] * fb, pw);
+      for (int pl = 0; pl < A3_NP; ++pl) {
+        uint32_t w[16];
 #pragma unroll
-          for (int pl = 0; pl < A3_NP; ++pl) w[pl][e] = pw[pl];
+        for (int j = 0; j < 16; ++j) {
+          w[j] = tc::pack_bf16x2(f[2 * j], f[2 * j + 1]);
+          if (pl + 1 < A3_NP) { f[2 * j] -= __uint_as_float(w[j] << 16); f[2 * j + 1] -= __uint_as_float(w[j] & 0xFFFF0000u); }
         }
+        uint4* prow = reinterpret_cast<uint4*>(sp + lane * 16);
 #pragma unroll
-        for (int pl = 0; pl < A3_NP; ++pl)
-          reinterpret_cast<uint4*>(dst + pl * p.out_plane)[q] = make_uint4(w[pl][0], w[pl][1], w[pl][2], w[pl][3]);
+        for (int j = 0; j < 4; ++j) prow[j ^ ((lane >> 1) & 3)] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int R = it * 8 + (lane >> 2), sl = lane & 3;
+          const uint4 v = reinterpret_cast<const uint4*>(sp + R * 16)[sl ^ ((R >> 1) & 3)];
+          if (R < rows_q) *reinterpret_cast<uint4*>(dst + pl * p.out_plane + (size_t)R * p.ldo + sl * 8) = v;
+        }
+        __syncwarp();
       }
     }
   }
+  if (threadIdx.x == 0) stamp(0, 63, 2);                   // output written (thread 0)
   tc::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(0, 63, 3);                   // CTA done
   if (warp == 10) tc::tmem_dealloc(tmem_base, 512);
 }
 

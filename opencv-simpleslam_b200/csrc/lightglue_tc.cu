@@ -617,7 +617,7 @@ extern "C" int b2s_bench_gemm_tc3(int M, int N, int K, int cl, int iters, float*
 
 // uploads q | k | v as [np][R, 768] planes and launches one attention (z problems); ctx planes come back summed
 static int run_attn(int np, const std::vector<__nv_bfloat16>& buf, int R, const AttnTcProb (&prob)[2], int nz, int maxq, int iters,
-                    float* ms_out, float* ctx, int nq_out) {
+                    float* ms_out, float* ctx, int nq_out, long long* trace_out = nullptr) {
   DeviceArena ar;
   __nv_bfloat16 *dq, *dctx;
   B2S_TRY(ar.alloc(&dq, buf.size())); B2S_TRY(ar.alloc(&dctx, (size_t)np * R * 256));
@@ -633,6 +633,8 @@ static int run_attn(int np, const std::vector<__nv_bfloat16>& buf, int R, const 
   Attn3Params a3 = {};
   a3.qcol = 0; a3.kcol = 256; a3.vcol = 512; a3.prob[0] = prob[0]; a3.prob[1] = prob[1]; a3.scale_log2e = sc; a3.out = dctx; a3.ldo = 256;
   a3.plane_rows = R; a3.out_plane = (size_t)R * 256;
+  long long* dtrace = nullptr;
+  if (trace_out) { B2S_TRY(ar.alloc(&dtrace, (size_t)3 * 64 * 8)); B2S_CUDA(cudaMemset(dtrace, 0, 3 * 64 * 8 * sizeof(long long))); }
   const dim3 grid(cdiv(maxq, 128), 4, nz);
   auto launch = [&]() {
     if (np == 1) k_attn_tc<<<grid, ATC_THREADS, ATC_SMEM>>>(mq, a1);
@@ -651,6 +653,13 @@ static int run_attn(int np, const std::vector<__nv_bfloat16>& buf, int R, const 
     B2S_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     *ms_out = ms / iters;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (trace_out && np == 3) {
+      a3.trace = dtrace; a3.trace_cta = trace_out[0] > 0 ? (int)trace_out[0] : 0;
+      launch();
+      B2S_LAUNCH_CHECK();
+      B2S_CUDA(cudaDeviceSynchronize());
+      B2S_CUDA(cudaMemcpy(trace_out, dtrace, 3 * 64 * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    }
     return 0;
   }
   launch();
@@ -689,7 +698,7 @@ extern "C" int b2s_test_attn_tc3(const float* q, const float* k, const float* v,
 
 // Device-only timing of the attention kernel on random data: one launch = what a LightGlue self
 // block issues (2 problems x 4 heads, nq queries x nk keys each).  ms_out = mean per launch.
-static int bench_attn(int nq, int nk, int iters, float* ms_out, int np) {
+static int bench_attn(int nq, int nk, int iters, float* ms_out, int np, long long* trace_out = nullptr) {
   if (nq <= 0 || nk <= 0 || iters <= 0 || !ms_out) { set_error("b2s_bench_attn_tc: bad argument"); return B2S_EINVAL; }
   const int cap = cdiv(std::max(nq, nk), 128) * 128;
   const int R = 2 * cap;
@@ -701,7 +710,9 @@ static int bench_attn(int nq, int nk, int iters, float* ms_out, int np) {
     buf[i] = __float2bfloat16_rn((((s >> 8) & 0xFFFF) / 32768.f - 1.f) * scale);
   }
   const AttnTcProb prob[2] = {{0, 0, nq, nk}, {cap, cap, nq, nk}};
-  return run_attn(np, buf, R, prob, 2, nq, iters, ms_out, nullptr, 0);
+  return run_attn(np, buf, R, prob, 2, nq, iters, ms_out, nullptr, 0, trace_out);
 }
 extern "C" int b2s_bench_attn_tc(int nq, int nk, int iters, float* ms_out) { return bench_attn(nq, nk, iters, ms_out, 1); }
 extern "C" int b2s_bench_attn_tc3(int nq, int nk, int iters, float* ms_out) { return bench_attn(nq, nk, iters, ms_out, 3); }
+// same + clock64 stamps of CTA (0,0,0) of one extra launch: trace_out [3 roles (MMA thread, softmax group 0 / 1)][64 tiles][8 events]
+extern "C" int b2s_trace_attn_tc3(int nq, int nk, int iters, float* ms_out, long long* trace_out) { return bench_attn(nq, nk, iters, ms_out, 3, trace_out); }
