@@ -169,7 +169,9 @@ def run_ours(args):
         de_buf = [torch.empty((NKP, 128), device=dev) for _ in range(NS)]
         n_host = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(NS)]
         counts = [0] * NS
-        s_ext, s_mat = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        # B2S_BENCH_PRIO=1: the matcher's stream gets the higher priority (its kernels leave 20 of the 148 SMs idle for the extractor)
+        prio = -1 if os.environ.get("B2S_BENCH_PRIO", "0") == "1" else 0
+        s_ext, s_mat = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev, priority=prio)
         ext_done = [torch.cuda.Event() for _ in range(NS)]
         mat_done = torch.cuda.Event()
 

@@ -412,11 +412,7 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
   }
   h->Hr = Hr; h->Wr = Wr; h->Hp = Hp; h->Wp = Wp;
   pp.out = h->img_pad; pp.resized = h->resized;
-  static const bool pre_old = [] { const char* e = std::getenv("B2S_PRE_OLD"); return e && e[0] == '1'; }();
-  if (!pre_old && fmt == B2S_IMG_BGR_U8_HWC && pp.do_resize && pp.do_blur && pp.ky == 3 && pp.kx == 3 && pp.scale_h <= PRE_T_MAXSCALE && pp.scale_w <= PRE_T_MAXSCALE)
-    launch_k(k_preprocess_tiled, dim3(cdiv(Wp, PRE_T_W), cdiv(Hp, PRE_T_H)), 256, 0, st, pp);
-  else
-    launch_k(k_preprocess, dim3(cdiv(Wp, 256), Hp), 256, 0, st, pp);
+  launch_k(k_preprocess, dim3(cdiv(Wp, 256), Hp), 256, 0, st, pp);
   ++h->launches; B2S_LAUNCH_CHECK();
 
   // ---- block1 (full res) and block2 (1/2 res) ----

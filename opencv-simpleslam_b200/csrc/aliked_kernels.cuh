@@ -116,78 +116,6 @@ __global__ void __launch_bounds__(256) k_preprocess(PreParams p) {
   }
 }
 
-// K0, tiled form for the common case (u8 BGR source, down-scale with a 3x3 blur, scale factors <= PRE_T_MAXSCALE):
-// a CTA produces a 64 x 8 tile of the padded output.  The source window of the tile is converted once (LUT), blurred
-// separably in shared memory with exactly pre_blur()'s operation order (row sums over j first, then the column sum
-// over i, fma chains from zero, reflect-101 borders), and every output pixel then interpolates four blurred values -
-// instead of re-deriving four 3x3 blurs from 16 byte loads per pixel and channel as k_preprocess does.
-constexpr int PRE_T_W = 64, PRE_T_H = 8, PRE_T_SW = 96, PRE_T_SH = 16;
-constexpr float PRE_T_MAXSCALE = 1.35f;     // window (64 * s + 4) x (8 * s + 4) must fit PRE_T_SW x PRE_T_SH
-
-__global__ void __launch_bounds__(256) k_preprocess_tiled(PreParams p) {
-  pdl_wait();
-  __shared__ float lut[256];
-  __shared__ float sa[3][PRE_T_SH][PRE_T_SW];     // source window, later the blurred window
-  __shared__ float sb[3][PRE_T_SH][PRE_T_SW];     // horizontal pass
-  const int tid = threadIdx.x;
-  lut[tid] = __fdiv_rn((float)tid, 255.0f);
-  const int xp0 = blockIdx.x * PRE_T_W, yp0 = blockIdx.y * PRE_T_H;
-  auto src_x0 = [&](int xp) { const int xr = min(max(xp - p.pad_l, 0), p.Wr - 1); float fx = p.scale_w * ((float)xr + 0.5f) - 0.5f; if (fx < 0.f) fx = 0.f; return (int)fx; };
-  auto src_y0 = [&](int yp) { const int yr = min(max(yp - p.pad_t, 0), p.Hr - 1); float fy = p.scale_h * ((float)yr + 0.5f) - 0.5f; if (fy < 0.f) fy = 0.f; return (int)fy; };
-  // unreflected source window [wy0, wy0 + wh) x [wx0, wx0 + ww): blurred values are needed on [y0min, y1max] x [x0min, x1max]
-  const int wx0 = src_x0(xp0) - 1, wy0 = src_y0(yp0) - 1;
-  const int ww = min(src_x0(min(xp0 + PRE_T_W - 1, p.Wp - 1)) + 1, p.W - 1) + 1 - wx0 + 1;
-  const int wh = min(src_y0(min(yp0 + PRE_T_H - 1, p.Hp - 1)) + 1, p.H - 1) + 1 - wy0 + 1;
-  __syncthreads();
-  const uint8_t* img = static_cast<const uint8_t*>(p.img);
-  for (int e = tid; e < wh * ww; e += 256) {
-    const int yy = e / ww, xx = e - yy * ww;
-    const uint8_t* px = img + (size_t)reflect_idx(wy0 + yy, p.H) * p.stride + reflect_idx(wx0 + xx, p.W) * 3;
-    sa[0][yy][xx] = lut[px[2]]; sa[1][yy][xx] = lut[px[1]]; sa[2][yy][xx] = lut[px[0]];      // RGB <- BGR
-  }
-  __syncthreads();
-  const float gx0 = p.gx[0], gx1 = p.gx[1], gx2 = p.gx[2], gy0 = p.gy[0], gy1 = p.gy[1], gy2 = p.gy[2];
-  for (int e = tid; e < 3 * wh * (ww - 2); e += 256) {          // row sums at window columns 1 .. ww - 2
-    const int c = e / (wh * (ww - 2)), r = e - c * wh * (ww - 2), yy = r / (ww - 2), xx = r - yy * (ww - 2) + 1;
-    float row = 0.f;
-    row = fmaf(gx0, sa[c][yy][xx - 1], row); row = fmaf(gx1, sa[c][yy][xx], row); row = fmaf(gx2, sa[c][yy][xx + 1], row);
-    sb[c][yy][xx] = row;
-  }
-  __syncthreads();
-  for (int e = tid; e < 3 * (wh - 2) * (ww - 2); e += 256) {    // column sums at window rows 1 .. wh - 2
-    const int c = e / ((wh - 2) * (ww - 2)), r = e - c * (wh - 2) * (ww - 2), yy = r / (ww - 2) + 1, xx = r - (yy - 1) * (ww - 2) + 1;
-    float acc = 0.f;
-    acc = fmaf(gy0, sb[c][yy - 1][xx], acc); acc = fmaf(gy1, sb[c][yy][xx], acc); acc = fmaf(gy2, sb[c][yy + 1][xx], acc);
-    sa[c][yy][xx] = acc;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int xp = xp0 + (tid & 63), yp = yp0 + (tid >> 6) + 4 * q;
-    if (xp >= p.Wp || yp >= p.Hp) continue;
-    const int yr = min(max(yp - p.pad_t, 0), p.Hr - 1);
-    const int xr = min(max(xp - p.pad_l, 0), p.Wr - 1);
-    float fy = p.scale_h * ((float)yr + 0.5f) - 0.5f; if (fy < 0.f) fy = 0.f;
-    float fx = p.scale_w * ((float)xr + 0.5f) - 0.5f; if (fx < 0.f) fx = 0.f;
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = y0 + (y0 < p.H - 1 ? 1 : 0), x1 = x0 + (x0 < p.W - 1 ? 1 : 0);
-    const float ly1 = fy - (float)y0, ly0 = 1.f - ly1, lx1 = fx - (float)x0, lx0 = 1.f - lx1;
-    float v[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float p00 = sa[c][y0 - wy0][x0 - wx0], p01 = sa[c][y0 - wy0][x1 - wx0];
-      const float p10 = sa[c][y1 - wy0][x0 - wx0], p11 = sa[c][y1 - wy0][x1 - wx0];
-      v[c] = ly0 * (lx0 * p00 + lx1 * p01) + ly1 * (lx0 * p10 + lx1 * p11);
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) p.out[((size_t)c * p.Hp + yp) * p.Wp + xp] = v[c];
-    if (p.resized && yp - p.pad_t == yr && xp - p.pad_l == xr) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) p.resized[((size_t)c * p.Hr + yr) * p.Wr + xr] = v[c];
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------
 // K1/K2: direct 3x3 conv (pad 1), planar CHW, BN folded into w/bias, optional 2x2 average
 // pooling fused into the input load, optional residual, SELU.
