@@ -299,7 +299,7 @@ int run_dcn_block(b2s_aliked* h, cudaStream_t st, const DcnBlockW& w, const floa
     g.bias = bias; g.residual = residual; g.ldr = N; g.act = act;
     return agemm(h, g, st);
   };
-  const int ppw = P >= 2048 ? 4 : 1;
+  const int ppw = P >= 2048 ? 2 : 1;   // pixels per warp: 2 keeps >= 2 CTAs per SM busy at 1/8 resolution (4 was one under-filled wave)
   DcnColParams cp = {};
   cp.H = Hh; cp.W = Ww; cp.clampv = clampv; cp.ppw = ppw;
   if (use_tc) { cp.col_pl = h->col3_pl; cp.plane = (size_t)P * 9 * CIN; } else cp.col_f32 = col;

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) k_preprocess(PreParams p) {
 // weights: [CIN][9][COUT]
 // ---------------------------------------------------------------------------------------
 template <int CIN, int COUT, bool POOL2>
-__global__ void __launch_bounds__(128 * (COUT / 16)) k_conv3x3(const float* __restrict__ in, int H, int W,
+__global__ void __launch_bounds__(128 * (COUT / 16), COUT == 16 ? 5 : 1) k_conv3x3(const float* __restrict__ in, int H, int W,
                                                                const float* __restrict__ w, const float* __restrict__ bias,
                                                                const float* __restrict__ residual, float* __restrict__ out,
                                                                int act, __nv_bfloat16* __restrict__ out_planes) {
@@ -1069,7 +1069,7 @@ __global__ void __launch_bounds__(256) k_sddh_patch(FeatSrc s, const float* __re
   store_planes1(d, plane, v.x); store_planes1(d + 32, plane, v.y); store_planes1(d + 64, plane, v.z); store_planes1(d + 96, plane, v.w);
 }
 
-__global__ void __launch_bounds__(256) k_sddh_sample(FeatSrc s, const float* __restrict__ kp_norm,
+__global__ void __launch_bounds__(256, 4) k_sddh_sample(FeatSrc s, const float* __restrict__ kp_norm,
                                                      const float* __restrict__ offs /*[n][M][2]*/, int M,
                                                      const int32_t* __restrict__ n_dev, __nv_bfloat16* __restrict__ S, size_t plane) {
   pdl_wait();

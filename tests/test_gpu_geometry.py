@@ -243,3 +243,53 @@ def test_reproject_and_match_map_updates_and_edge_cases():
     kps2[:200] = vis + rng.normal(0, 0.5, (200, 2)).astype(np.float32)
     with pytest.raises(RuntimeError):
         P.reproject_and_match_2d3d(wm2, K2, T2, kps2, des2, 1241, 376, radius_px=12.0)
+
+
+# ---- size-independent properties at the BASELINE sizes (2048 keypoints, 1241x376) ---------------------------------
+def test_ransac_properties_full_size(ransac):
+    """Permutation equivariance is not expected of a sampled estimator, but these are: determinism for a fixed seed,
+    invariance of the consensus under a common translation of both images' coordinates (Hartley normalisation), and
+    the mask always being the exact consensus set of the returned F."""
+    p1, p2, gt = G.two_view_scene(2048, 0.35, 0.2, 31)
+    F1, m1 = ransac.run_host(p1, p2, 1.0, seed=5)
+    F2, m2 = ransac.run_host(p1, p2, 1.0, seed=5)
+    assert np.array_equal(m1, m2) and np.array_equal(F1, F2)
+    F3, m3 = ransac.run_host(p1, p2, 1.0, seed=6)                      # another sample stream: a different, equally good model
+    assert abs(int(m3.sum()) - int(m1.sum())) <= 0.03 * m1.sum()
+    shift = np.float32([64.0, -32.0])
+    _, ms = ransac.run_host(p1 + shift, p2 + shift, 1.0, seed=5)       # exactly representable shift: same samples, same geometry
+    assert (ms == m1).mean() >= 0.95 and abs(int(ms.sum()) - int(m1.sum())) <= 0.03 * m1.sum()
+    err = G.fm_error(F1, p1, p2)
+    assert (err[m1.ravel() == 1] <= 1.0 + 1e-9).all() and (err[m1.ravel() == 0] > 1.0 - 1e-9).all()
+    # a looser threshold can only grow the consensus of the winning model's own mask
+    F4, m4 = ransac.run_host(p1, p2, 2.0, seed=5)
+    assert m4.sum() >= m1.sum()
+
+
+def test_remap_identity_and_shift_properties():
+    from b200slam import synth
+    from b200slam.geometry import FrameUndistorter
+    img = synth.frame(7, 376, 1241)
+    H, W = img.shape[:2]
+    xs, ys = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32))
+    assert np.array_equal(FrameUndistorter(xs, ys).remap(img), img)                       # identity maps reproduce the frame
+    out = FrameUndistorter(xs + 3.0, ys - 2.0).remap(img)                                 # integer shift = crop + zero border
+    assert np.array_equal(out[2:, :W - 3], img[:H - 2, 3:]) and not out[:2].any() and not out[:, W - 3:].any()
+    half = FrameUndistorter(xs + 0.5, ys).remap(img)                                      # half-pixel: rounded mean of neighbours
+    ref = ((img[:, :-1].astype(np.int32) + img[:, 1:].astype(np.int32) + 1) >> 1).astype(np.uint8)
+    assert np.array_equal(half[:, :W - 1], ref)
+
+
+def test_reproject_and_match_permutation_property():
+    """Relabelling the current frame's keypoints permutes the returned keypoint indices and nothing else."""
+    from b200slam import pnp_utils as P
+    from oracle import pnp as O
+    wm, K, Tcw, kps, des = O.tracking_scene(3000, 2048, 41)
+    a = P.reproject_and_match_2d3d(wm, K, Tcw, kps, des, 1241, 376, radius_px=12.0)
+    perm = np.random.default_rng(3).permutation(len(kps))
+    b = P.reproject_and_match_2d3d(wm, K, Tcw, kps[perm], des[perm], 1241, 376, radius_px=12.0)
+    assert len(a.mp_ids) > 500 and a.mp_ids == b.mp_ids
+    assert [int(perm[i]) for i in b.kp_indices] == a.kp_indices and np.array_equal(a.pts2d, b.pts2d) and np.array_equal(a.pts3d, b.pts3d)
+    # every assignment honours the reference's gates: inside the window, within the descriptor threshold, keypoints used once
+    uv, z = O.project_points(K, Tcw, a.pts3d.astype(np.float64))
+    assert (np.linalg.norm(uv - a.pts2d, axis=1) <= 12.0 + 1e-3).all() and len(set(a.kp_indices)) == len(a.kp_indices)
