@@ -432,7 +432,7 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
       hp.wt = l.wtok; hp.bt = l.btok; hp.wm = l.wmatch; hp.bm = l.bmatch;
       hp.thr = h->thr[i]; hp.keep_thr = keep_thr; hp.use_tok = do_stop;
       hp.tok = h->tok; hp.ctrl = h->ctrl; hp.adapt = h->adapt; hp.layer = i;
-      launch_k(k_lg_heads_blk, dim3(nblk, 2), 256, 0, st, hp);
+      launch_k(k_lg_heads_blk, dim3(nblk, 2), 1024, 0, st, hp);
       const int nxt = cur ^ 1;
       GatherBlkParams gp = {};
       gp.adapt = h->adapt; gp.ctrl = h->ctrl; gp.base[0] = 0; gp.base[1] = cap;
@@ -443,7 +443,7 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
       gp.prune[0] = pr0; gp.prune[1] = pr1;
       gp.xb_out = h->tc ? lgtc_xb(h->tc) : nullptr;
       gp.xb_planes = h->tc ? lgtc_planes(h->tc) : 0; gp.xb_plane = (size_t)2 * cap * 256;
-      launch_k(k_lg_gather_blk, dim3(nblk, 2), 256, 0, st, gp);
+      launch_k(k_lg_gather_blk, dim3(nblk, 2), 1024, 0, st, gp);
       h->launches += 2;
       B2S_LAUNCH_CHECK();
       continue;

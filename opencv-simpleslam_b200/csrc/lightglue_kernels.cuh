@@ -387,7 +387,7 @@ struct HeadBlkParams {
   float* tok; int* ctrl; int* adapt; int layer;
 };
 
-__global__ void __launch_bounds__(256) k_lg_heads_blk(HeadBlkParams p) {
+__global__ void __launch_bounds__(1024) k_lg_heads_blk(HeadBlkParams p) {   // 32 warps: one row per warp
   pdl_wait();
   const int s = blockIdx.y, blk = blockIdx.x;
   const bool active = lg_active(p.ctrl);
@@ -401,10 +401,9 @@ __global__ void __launch_bounds__(256) k_lg_heads_blk(HeadBlkParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4 wt0 = *reinterpret_cast<const float4*>(p.wt + lane * 4), wt1 = *reinterpret_cast<const float4*>(p.wt + 128 + lane * 4);
   const float4 wm0 = *reinterpret_cast<const float4*>(p.wm + lane * 4), wm1 = *reinterpret_cast<const float4*>(p.wm + 128 + lane * 4);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int rb = warp * 4 + q, row = blk * 32 + rb;
-    if (row >= rows) break;                      // uniform per warp
+  {
+    const int rb = warp, row = blk * 32 + rb;
+    if (row < rows) {                            // uniform per warp
     const int r = p.base[s] + row;
     const float* x = p.x + (size_t)r * 256;
     const float4 a = *reinterpret_cast<const float4*>(x + lane * 4);
@@ -426,6 +425,7 @@ __global__ void __launch_bounds__(256) k_lg_heads_blk(HeadBlkParams p) {
       }
       if (keep) atomicOr(&s_mask, 1u << rb);
     }
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -442,7 +442,7 @@ struct GatherBlkParams {
   __nv_bfloat16* xb_out; int xb_planes; size_t xb_plane;   // bf16 plane copy of x (tensor-core paths)
 };
 
-__global__ void __launch_bounds__(256) k_lg_gather_blk(GatherBlkParams p) {
+__global__ void __launch_bounds__(1024) k_lg_gather_blk(GatherBlkParams p) {   // 32 warps: one row per warp
   pdl_wait();
   if (!p.adapt[0]) return;
   const int s = blockIdx.y, blk = blockIdx.x;
@@ -476,10 +476,9 @@ __global__ void __launch_bounds__(256) k_lg_gather_blk(GatherBlkParams p) {
   if (blk == 0 && threadIdx.x == 0) { p.ctrl[LGC_M + s] = s_total; p.ctrl[LGC_CAN0 + s] = prune ? 1 : 0; }
   const unsigned mask = mask_of(blk);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int rb = warp * 4 + q;
-    if (!((mask >> rb) & 1u)) continue;           // uniform per warp
+  {
+    const int rb = warp;
+    if (!((mask >> rb) & 1u)) return;             // uniform per warp
     const int src = p.base[s] + blk * 32 + rb;
     const int dst = p.base[s] + s_before + __popc(mask & ((1u << rb) - 1u));
     const float4* xi = reinterpret_cast<const float4*>(p.x_in + (size_t)src * 256);
