@@ -8,7 +8,7 @@ import cv2
 import numpy as np
 import torch
 
-sys.path.insert(0, __file__.rsplit("/", 2)[0])
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from b200slam.geometry import FrameUndistorter, FundamentalRansac   # noqa: E402
 from b200slam import synth                                          # noqa: E402
 from oracle import geometry as G                                    # noqa: E402  (scene generator only)
@@ -70,7 +70,6 @@ def main():
 
 
 def bench_reproj():
-    sys.path.insert(0, "/root/repo")
     from b200slam import pnp_utils as P
     from oracle import pnp as O
     for n_points in (1500, 6000):

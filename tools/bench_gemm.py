@@ -5,7 +5,7 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, __file__.rsplit("/", 2)[0])
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from b200slam._lib import lib, check   # noqa: E402
 
 for (M, N, K, cl) in [(4096, 512, 256, 1), (4096, 512, 256, 4), (4096, 512, 512, 1), (4096, 512, 512, 4), (4096, 768, 256, 1),

@@ -4,7 +4,7 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, __file__.rsplit("/", 2)[0])
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from b200slam._lib import lib, check   # noqa: E402
 
 ms = C.c_float(0)
