@@ -160,8 +160,8 @@ class ReprojectionMatcher:
             self._create(max(self.max_points, int(2 ** np.ceil(np.log2(P)))), max(self.max_kps, int(2 ** np.ceil(np.log2(N)))))
         dev = torch.device("cuda", self.device_index)
         with torch.cuda.device(dev):
-            ids, pos, rows = self.mirror_of(world_map).sync(world_map)
             mir = self.mirror_of(world_map)
+            ids, pos, rows = mir.sync(world_map)
             Xw = torch.from_numpy(pos).to(dev, non_blocking=True)
             rows_d = torch.from_numpy(rows).to(dev, non_blocking=True)
             kps_d = torch.from_numpy(pts2d_cur).to(dev, non_blocking=True)
