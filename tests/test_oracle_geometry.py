@@ -117,3 +117,49 @@ def test_pnp_restatement_matches_reference_fixture():
         assert len(r.mp_ids) >= 100
         assert r.mp_ids == g[f"c{c}_mp_ids"].tolist() and r.kp_indices == g[f"c{c}_kp_indices"].tolist()
         assert np.array_equal(r.pts3d, g[f"c{c}_pts3d"]) and np.array_equal(r.pts2d, g[f"c{c}_pts2d"])
+
+
+def test_remap_restatement_random_shapes_against_cv2():
+    """Randomised pin of the fixed-point remap restatement: odd sizes, destination != source size, maps that leave the
+    image on every side, exact .5 / 1/32 sub-pixel positions (seeded, 40 cases)."""
+    rng = np.random.default_rng(1234)
+    for case in range(40):
+        sh, sw = int(rng.integers(2, 70)), int(rng.integers(2, 90))
+        dh, dw = int(rng.integers(1, 60)), int(rng.integers(1, 80))
+        src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        kind = case % 4
+        if kind == 0:      # arbitrary float positions, partly outside
+            mx = (rng.random((dh, dw), dtype=np.float32) * (sw + 8) - 4).astype(np.float32)
+            my = (rng.random((dh, dw), dtype=np.float32) * (sh + 8) - 4).astype(np.float32)
+        elif kind == 1:    # positions on the 1/32 grid (exact weights) and half-way between grid points (rounding of cvRound)
+            mx = (rng.integers(-64, 32 * sw + 64, (dh, dw)) / 32.0 + rng.choice([0.0, 1.0 / 64.0], (dh, dw))).astype(np.float32)
+            my = (rng.integers(-64, 32 * sh + 64, (dh, dw)) / 32.0 + rng.choice([0.0, 1.0 / 64.0], (dh, dw))).astype(np.float32)
+        elif kind == 2:    # affine warp
+            ys, xs = np.mgrid[0:dh, 0:dw].astype(np.float32)
+            a = rng.normal(0, 0.3, 4).astype(np.float32)
+            mx = (1 + a[0]) * xs + a[1] * ys + np.float32(rng.normal(0, 3)); my = a[2] * xs + (1 + a[3]) * ys + np.float32(rng.normal(0, 3))
+            mx, my = mx.astype(np.float32), my.astype(np.float32)
+        else:              # far outside / huge coordinates
+            mx = (rng.normal(0, 1e4, (dh, dw))).astype(np.float32); my = (rng.normal(0, 1e4, (dh, dw))).astype(np.float32)
+        want = cv2.remap(src, mx, my, cv2.INTER_LINEAR)
+        got = G.remap_bgr_u8(src, mx, my)
+        assert np.array_equal(want, got), f"case {case} kind {kind}: {(want != got).sum()} differing bytes"
+
+
+def test_map_descriptor_packing_rules():
+    """Host logic of the landmark mirror (pnp_utils.py:45-49, :112-123): last six observations, None entries skipped,
+    no usable descriptor when the newest one is None."""
+    from b200slam.pnp_utils import MapDescriptorMirror as M
+    d = [np.full(128, i, np.float32) for i in range(9)]
+    assert M._pack([]) == (0, None)
+    assert M._pack([(0, 0, d[0]), (1, 1, None)])[0] == 0
+    n, blk = M._pack([(i, i, d[i]) for i in range(9)])
+    assert n == 6 and [int(r[0]) for r in blk] == [3, 4, 5, 6, 7, 8]
+    obs = [(i, i, d[i]) for i in range(9)]; obs[5] = (5, 5, None)
+    n, blk = M._pack(obs)
+    assert n == 5 and [int(r[0]) for r in blk] == [3, 4, 6, 7, 8]
+    try:
+        M._pack([(0, 0, np.zeros(32, np.uint8))])
+        raise AssertionError("binary descriptors must be rejected")
+    except NotImplementedError:
+        pass
