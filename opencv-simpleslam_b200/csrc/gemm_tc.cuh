@@ -7,9 +7,10 @@
 // plane p of a weight lives K columns to the right ([N, NP*K]).
 // One 128 x BN output tile per CTA, BK = 64 (one 128-byte swizzle atom per row), TMA->smem ring
 // (a stage holds all NP planes of both operands), warp-specialised: warp 0 = TMA producer,
-// warp 1 = MMA issuer (one elected lane issues tcgen05.mma, accumulator in TMEM), warps 2..5 =
+// warp 1 = MMA issuer (one elected lane issues tcgen05.mma, accumulator in TMEM), warps 2..9 =
 // epilogue (tcgen05.ld: thread == accumulator row, so row-wise epilogues - rotary pairs, residual,
-// plane splitting - are thread-local).
+// plane splitting - are thread-local; two warps per TMEM lane quadrant alternate over the 32-column
+// chunks and write through a swizzled staging tile so that global stores are row-contiguous).
 // Row space: two segments (image0 / image1 of a pair) at fixed bases of a [2*cap, ld] buffer.
 #pragma once
 #include "tc_common.cuh"
