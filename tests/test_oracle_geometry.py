@@ -163,3 +163,20 @@ def test_map_descriptor_packing_rules():
         raise AssertionError("binary descriptors must be rejected")
     except NotImplementedError:
         pass
+
+
+def test_match_points_gather_equals_reference_list_comprehension():
+    """`_match_points` == the reference's `np.float32([kp[m.queryIdx].pt for m in matches])` (features_utils.py:191-192)
+    for cv2 lists and for the array-native containers."""
+    from b200slam import features_utils as fu
+    from b200slam.containers import DMatchArray, KeyPointArray
+    rng = np.random.default_rng(0)
+    p1 = (rng.random((50, 2)) * 500).astype(np.float32); p2 = (rng.random((60, 2)) * 500).astype(np.float32)
+    pairs = np.stack([rng.integers(0, 50, 30), rng.integers(0, 60, 30)], axis=1).astype(np.int32)
+    kp1 = [cv2.KeyPoint(float(x), float(y), 1) for x, y in p1]; kp2 = [cv2.KeyPoint(float(x), float(y), 1) for x, y in p2]
+    ms = [cv2.DMatch(int(i), int(j), 0.0) for i, j in pairs]
+    ref1 = np.float32([kp1[m.queryIdx].pt for m in ms]); ref2 = np.float32([kp2[m.trainIdx].pt for m in ms])
+    a1, a2 = fu._match_points(kp1, kp2, ms)
+    b1, b2 = fu._match_points(KeyPointArray(p1), KeyPointArray(p2), DMatchArray(pairs))
+    assert np.array_equal(a1, ref1) and np.array_equal(a2, ref2) and np.array_equal(b1, ref1) and np.array_equal(b2, ref2)
+    assert a1.dtype == np.float32 and a1.shape == (30, 2)
