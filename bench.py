@@ -96,8 +96,8 @@ def cpu_reference_arm(steps, warmup, n_pairs_per_step=1):
     from b200slam import weights, synth
     torch.set_num_threads(os.cpu_count() or 1)
     args = SimpleNamespace(use_lightglue=True, max_features=NKP, min_conf=0.7)
-    sa, src_a = weights.load_aliked_state()
-    sl, src_l = weights.load_lightglue_state()
+    sa, src_a = weights.load_aliked_state(allow_synthetic=True)
+    sl, src_l = weights.load_lightglue_state(allow_synthetic=True)
     det, mat = ofu.init_feature_pipeline(args, sa, sl)
     frames = [synth.frame(t, H, W) for t in range((warmup + steps) * n_pairs_per_step + 1)]
     prev = ofu.feature_extractor(args, frames[0], det)
@@ -146,8 +146,8 @@ def run_ours(args):
     from b200slam import features_utils as fu, synth, frontend, weights, _lib
 
     ns = SimpleNamespace(use_lightglue=True, max_features=NKP, min_conf=0.7, lg_precision=args.precision)
-    sa, src_a = weights.load_aliked_state()
-    sl, src_l = weights.load_lightglue_state()
+    sa, src_a = weights.load_aliked_state(allow_synthetic=True)
+    sl, src_l = weights.load_lightglue_state(allow_synthetic=True)
     det = frontend.ALIKED(max_num_keypoints=NKP, weights=sa, device=dev)
     mat = frontend.LightGlue(weights=sl, device=dev, precision=args.precision, max_kp=NKP)
 

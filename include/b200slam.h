@@ -41,9 +41,9 @@ enum {
  *   B2S_FP32      fp32-faithful on the tensor cores: every fp32 operand is carried as three bf16
  *                 planes and each contraction issues the six significant cross products into an fp32
  *                 TMEM accumulator (results agree with an fp32 FMA path to rounding level);
- *   B2S_BF16      operands rounded once to bf16 (fastest; >= 99 % match-set agreement);
- *   B2S_FP32_SIMT the same fp32 arithmetic on the CUDA cores (cross-check of the B2S_FP32 path). */
-enum { B2S_FP32 = 0, B2S_BF16 = 1, B2S_FP32_SIMT = 2 };
+ *   B2S_BF16      operands rounded once to bf16 (fastest; >= 99 % match-set agreement).
+ * The input projection and the assignment head are fp32-faithful in both modes. */
+enum { B2S_FP32 = 0, B2S_BF16 = 1 };
 enum { B2S_IMG_BGR_U8_HWC = 0, B2S_IMG_RGB_F32_CHW = 1 };
 
 typedef struct b2s_aliked b2s_aliked;
@@ -151,15 +151,33 @@ int b2s_lightglue_match_host(b2s_lg* h, const float* k0, const float* d0, int m,
                              int32_t* stop_layer, int32_t* matches0, int32_t* matches1,
                              float* ms0, float* ms1, int32_t* prune0, int32_t* prune1);
 
-/* Batched matching of P independent pairs (keyframe-window all-pairs, BASELINE config 3).
+/* Batched matching of P independent pairs: the keyframe-window all-pairs loops of the reference
+ * (`select_keyframe`, keyframe_utils.py:153; `triangulate_between_kfs_2view`, triangulation_utils.py:131 - BASELINE
+ * config 3) or the consecutive pairs of a frame stream.  The pair is a grid dimension of every kernel: ONE launch
+ * sequence serves up to b2s_lg_max_batch() pairs (larger batches are processed in such chunks), each pair with its own
+ * device-resident sizes, early-exit flag and pruning state; results are identical to P calls of b2s_lightglue_match
+ * with size0 = size1 = NULL.
  * Keypoints/descriptors of F frames are packed; frame f owns rows [cu[f], cu[f+1]).
  * pair p matches frame pair_i[p] against pair_j[p]; outputs for pair p start at row
  * p*stride of matches_dev/mscores_dev, counts in n_matches_dev[p]. Host arrays: cu,
- * pair_i, pair_j. */
+ * pair_i, pair_j.  _ex: counts (host, nullable) [F]: frame f owns rows [cu[f], cu[f] + counts[f]) - frames in fixed-size
+ * slots, as an all_gather of per-rank records leaves them; max_batch > 0 lowers the pairs per launch sequence;
+ * stop_layers_dev (nullable) [P]. */
 int b2s_lightglue_match_batch(b2s_lg* h, const float* kpts_dev, const float* desc_dev,
                               const int32_t* cu, int n_frames, const int32_t* pair_i,
                               const int32_t* pair_j, int n_pairs, void* stream, int stride,
                               int32_t* matches_dev, float* mscores_dev, int32_t* n_matches_dev);
+int b2s_lightglue_match_batch_ex(b2s_lg* h, const float* kpts_dev, const float* desc_dev,
+                                 const int32_t* cu, const int32_t* counts, int n_frames, const int32_t* pair_i,
+                                 const int32_t* pair_j, int n_pairs, void* stream, int stride, int max_batch,
+                                 int32_t* matches_dev, float* mscores_dev, int32_t* n_matches_dev,
+                                 int32_t* stop_layers_dev);
+int b2s_lg_max_batch(void);
+/* Device workspace of a matcher handle for `pairs` pairs per launch sequence of up to max_kp keypoints per image
+ * (bytes; about 110 MB per pair at 2048 keypoints in B2S_FP32), and the call that allocates it ahead of time (otherwise
+ * the workspace grows on demand, which synchronises the stream). */
+size_t b2s_lg_workspace_bytes(const b2s_lg_cfg* cfg, int max_kp, int pairs);
+int b2s_lg_reserve(b2s_lg* h, int max_kp, int pairs);
 
 /* ---------------------------------------------------------------------------------------------
  * Rows behind the matcher: epipolar outlier rejection and frame ingest.

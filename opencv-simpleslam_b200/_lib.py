@@ -28,8 +28,8 @@ class LgCfg(C.Structure):
                 ("pruning_min_kpts", C.c_int), ("precision", C.c_int), ("max_kp", C.c_int)]
 
 
-FP32, BF16, FP32_SIMT = 0, 1, 2
-PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp32_simt": FP32_SIMT}
+FP32, BF16 = 0, 1
+PRECISIONS = {"fp32": FP32, "bf16": BF16}
 IMG_BGR_U8_HWC, IMG_RGB_F32_CHW = 0, 1
 vp, i32p, f32p = C.c_void_p, C.c_void_p, C.c_void_p   # raw addresses (device or host)
 
@@ -55,6 +55,11 @@ SIGNATURES = {
                                            i32p, f32p, i32p, i32p, i32p, i32p, f32p, f32p, i32p, i32p]),
     "b2s_lightglue_match_batch": (C.c_int, [vp, f32p, f32p, i32p, C.c_int, i32p, i32p, C.c_int, vp, C.c_int,
                                             i32p, f32p, i32p]),
+    "b2s_lightglue_match_batch_ex": (C.c_int, [vp, f32p, f32p, i32p, i32p, C.c_int, i32p, i32p, C.c_int, vp, C.c_int, C.c_int,
+                                               i32p, f32p, i32p, i32p]),
+    "b2s_lg_max_batch": (C.c_int, []),
+    "b2s_lg_workspace_bytes": (C.c_size_t, [C.POINTER(LgCfg), C.c_int, C.c_int]),
+    "b2s_lg_reserve": (C.c_int, [vp, C.c_int, C.c_int]),
     "b2s_aliked_debug_get": (C.c_int, [vp, C.c_char_p, f32p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b2s_lg_set_debug": (C.c_int, [vp, C.c_int]),
     "b2s_lg_debug_get": (C.c_int, [vp, C.c_char_p, f32p, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -235,11 +235,11 @@ int tc_gemm(b2s_aliked* h, cudaStream_t st, const CUtensorMap& a, int plane_rows
   TcGemmParams p = {};
   p.residual = residual; p.ld_res = ldc;
   p.K = w.K; p.K1 = w.K; p.N = w.N; p.bias = bias; p.act = act;
-  p.seg_base[0] = 0; p.seg_rows[0] = rows_max; p.seg_base[1] = 0; p.seg_rows[1] = 0; p.tiles0 = cdiv(rows_max, 128);
+  p.seg_stride = 0; p.seg_rows = rows_max; p.tiles_per_seg = cdiv(rows_max, 128);
   p.plane_rows = plane_rows; p.m_dev = n_dev; p.m_mult = mult;
   if (out_f32) { p.epi = TC_EPI_F32; p.out_f32 = out_f32; p.ld_f32 = ldc; }
   else { p.epi = TC_EPI_BF16; p.out_bf16 = out_planes; p.ld_bf16 = ldc; p.out_plane = out_plane; }
-  launch_k(k_gemm_tc<64, 3>, dim3(cdiv(w.N, 64), p.tiles0), TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, a, a, w.map, p);
+  launch_k(k_gemm_tc<64, 3>, dim3(cdiv(w.N, 64), p.tiles_per_seg), TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, a, a, w.map, p);
   ++h->launches;
   B2S_LAUNCH_CHECK();
   return 0;

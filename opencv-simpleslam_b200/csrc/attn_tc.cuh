@@ -20,9 +20,12 @@
 
 namespace b2s {
 
-struct AttnTcProb { int q_row, k_row, nq, nk; };   // row bases inside the [2*cap, ld] bf16 buffer
+struct AttnTcProb { int q_row, k_row, nq, nk; };   // row bases inside the [segments * cap, ld] bf16 buffer
+// grid.z = problem.  With the LightGlue device state (`ctrl`, 32 ints per pair) problem z is SEGMENT z = 2 * pair + image
+// (lightglue_kernels.cuh): queries = segment z, keys = the same segment (self) or the pair's other image (cross), sizes
+// from the pair's state.  Without it (unit tests) the problems are the static prob[0..1].
 struct AttnTcParams {
-  AttnTcProb prob[2];
+  AttnTcProb prob[2]; int cap;
   int qcol, kcol, vcol;            // column offsets of Q / K / V (head h adds h*64)
   float scale_log2e;               // softmax scale * log2(e)
   __nv_bfloat16* out; int ldo;     // ctx [2*cap, 256] bf16, rows aligned with q_row
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) k_attn_tc(const __grid_constan
   uint64_t* p_full = s_free + 2;               uint64_t* o_full = p_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
-  AttnTcProb pr = p.prob[blockIdx.z];
+  AttnTcProb pr = p.prob[p.ctrl ? 0 : blockIdx.z];
   const int q0 = blockIdx.x * ATC_BQ;
   if (!p.ctrl && q0 >= pr.nq) return;                    // uniform per CTA (static sizes)
   const int h = blockIdx.y;
@@ -125,9 +128,12 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) k_attn_tc(const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();            // everything above overlaps the previous kernel's tail; Q/K/V are touched only below
   if (p.ctrl) {          // device-resident sizes (pruning / early exit)
-    const bool on = !p.ctrl[1] && p.ctrl[2] > 0 && p.ctrl[3] > 0;
-    pr.nq = on ? p.ctrl[2 + blockIdx.z] : 0;
-    pr.nk = p.ctrl[2 + (p.cross ? 1 - blockIdx.z : blockIdx.z)];
+    const int z = blockIdx.z, side = z & 1;
+    const int* c = p.ctrl + (z >> 1) * 32;
+    const bool on = !c[1] && c[2] > 0 && c[3] > 0;
+    pr.q_row = z * p.cap; pr.k_row = (p.cross ? z ^ 1 : z) * p.cap;
+    pr.nq = on ? c[2 + side] : 0;
+    pr.nk = c[2 + (p.cross ? 1 - side : side)];
   }
   const bool live = q0 < pr.nq;                          // uniform per CTA
   const int nt = live ? (pr.nk + ATC_BK - 1) / ATC_BK : 0;

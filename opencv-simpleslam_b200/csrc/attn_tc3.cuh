@@ -32,7 +32,7 @@ static_assert(2 * 66 * 128 * 4 <= A3_KSLOTS * A3_KSLOT, "the final merge buffers
 static_assert(8 * 2048 <= A3_SLOTS * A3_SLOT, "the output staging tiles alias the V ring");
 
 struct Attn3Params {
-  AttnTcProb prob[2];
+  AttnTcProb prob[2]; int cap;     // problems: see AttnTcParams
   int qcol, kcol, vcol;            // column offsets of Q / K / V (head h adds h*64)
   int plane_rows;                  // rows between operand planes in the q/k/v buffer
   float scale_log2e;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const long long t_entry = clock64();
-  AttnTcProb pr = p.prob[blockIdx.z];
+  AttnTcProb pr = p.prob[p.ctrl ? 0 : blockIdx.z];
   const int q0 = blockIdx.x * A3_BQ;
   if (!p.ctrl && q0 >= pr.nq) return;                    // uniform per CTA (static sizes)
   const int h = blockIdx.y;
@@ -113,9 +113,12 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
   if (p.ctrl) {          // device-resident sizes (pruning / early exit)
-    const bool on = !p.ctrl[1] && p.ctrl[2] > 0 && p.ctrl[3] > 0;
-    pr.nq = on ? p.ctrl[2 + blockIdx.z] : 0;
-    pr.nk = p.ctrl[2 + (p.cross ? 1 - blockIdx.z : blockIdx.z)];
+    const int z = blockIdx.z, side = z & 1;
+    const int* c = p.ctrl + (z >> 1) * 32;
+    const bool on = !c[1] && c[2] > 0 && c[3] > 0;
+    pr.q_row = z * p.cap; pr.k_row = (p.cross ? z ^ 1 : z) * p.cap;
+    pr.nq = on ? c[2 + side] : 0;
+    pr.nk = c[2 + (p.cross ? 1 - side : side)];
   }
   const bool live = q0 < pr.nq;                          // uniform per CTA
   const int nt = live ? (pr.nk + A3_BK - 1) / A3_BK : 0;

@@ -1,10 +1,7 @@
-// gemm_simt.cuh - fp32 FFMA GEMM with fused epilogues: the arithmetic-faithful ("fp32 path")
-// contraction used by LightGlue's Linear layers, ALIKED's DCN/SDDH im2col products and the
-// assignment similarity.   C[M,N] = epi( [A1 | A2][M,K] * W[N,K]^T )
-//   * A may be the K-concatenation of two row-major sources (avoids materialising
-//     torch.cat([x, msg], -1) of upstream SelfBlock/CrossBlock.ffn).
-//   * grid.z selects one of two row segments (image0 / image1 of a pair live at fixed bases
-//     so that point pruning can shrink each side independently).
+// gemm_simt.cuh - fp32 FFMA GEMM with fused epilogues for ALIKED's small contractions (block4's deformable-conv
+// im2col products, 1x1 aggregations) that are too small for a tensor-core tile.   C[M,N] = epi( [A1 | A2][M,K] * W[N,K]^T )
+//   * A may be the K-concatenation of two row-major sources.
+//   * grid.z selects one of two row segments.
 //   * the live row count can come from device memory (m_dev) so data-dependent sizes
 //     (number of detected keypoints) need no host sync.
 // Tile: BM x BN x 16, 256 threads, (BM/16)x(BN/16) register micro-tile split in two halves
@@ -44,33 +41,11 @@ struct GemmParams {
   // in a fixed order (no atomics -> bitwise reproducible) before applying the epilogue.
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;
   int splitk = 1;
-  // LightGlue device-resident control (lightglue_kernels.cuh, LGC_*): sizes / early exit without host syncs
-  //   lg_mode 1: transformer-layer GEMM - exit when stopped or a side is empty; seg_rows[z] = ctrl[2 + z]
-  //   lg_mode 2: assignment projection - seg_rows from ctrl, runs after a stop too; W / bias of layer
-  //              ctrl[6] from w_tab / b_tab; A1 := A1_alt when that layer lives in the odd buffer
-  //   lg_mode 3: similarity - M = ctrl[2], N = ctrl[3]
-  const int* lg_ctrl = nullptr; int lg_mode = 0;
-  const float* const* w_tab = nullptr; const float* const* b_tab = nullptr; const float* A1_alt = nullptr;
 };
 
 template <int BM, int BN>
 __global__ void __launch_bounds__(256, (BM >= 128 ? 2 : 3)) k_gemm_simt(GemmParams p) {
   pdl_wait();
-  if (p.lg_ctrl) {
-    const int* c = p.lg_ctrl;
-    if (c[2] <= 0 || c[3] <= 0) return;
-    if (p.lg_mode == 1) {
-      if (c[1]) return;
-      p.seg_rows[0] = c[2]; p.seg_rows[1] = c[3];
-    } else if (p.lg_mode == 2) {
-      p.seg_rows[0] = c[2]; p.seg_rows[1] = c[3];
-      const int last = c[6];
-      p.W = p.w_tab[last]; p.bias = p.b_tab[last];
-      if (p.A1_alt && (last & 1)) p.A1 = p.A1_alt;
-    } else {
-      p.M = c[2]; p.N = c[3];
-    }
-  }
   constexpr int BK = 16;
   constexpr int TM = BM / 16, TN = BN / 16;   // micro tile (8 or 4)
   constexpr int HM = TM / 2, HN = TN / 2;     // half tiles

@@ -11,18 +11,23 @@
 // epilogue (tcgen05.ld: thread == accumulator row, so row-wise epilogues - rotary pairs, residual,
 // plane splitting - are thread-local; two warps per TMEM lane quadrant alternate over the 32-column
 // chunks and write through a swizzled staging tile so that global stores are row-contiguous).
-// Row space: two segments (image0 / image1 of a pair) at fixed bases of a [2*cap, ld] buffer.
+// Row space: SEGMENTS of seg_stride rows (lightglue_kernels.cuh: segment 2p + s = image s of pair p of a batch); grid.y
+// enumerates (segment, 128-row tile) and the live rows of a segment come from the pair's device-resident state.
 #pragma once
 #include "tc_common.cuh"
 
 namespace b2s {
 
-enum TcEpi { TC_EPI_BF16 = 0, TC_EPI_ROTARY_BF16 = 1, TC_EPI_F32 = 2, TC_EPI_RESID_F32_BF16 = 3 };
+// epilogues: planes only | rotary + planes | fp32 only | in-place fp32 residual stream + planes | fp32 + planes
+enum TcEpi { TC_EPI_BF16 = 0, TC_EPI_ROTARY_BF16 = 1, TC_EPI_F32 = 2, TC_EPI_RESID_F32_BF16 = 3, TC_EPI_F32_BF16 = 4 };
+
+constexpr int TC_CTRL_INTS = 32;    // == LGC_INTS: ints of device-resident state per pair
 
 struct TcGemmParams {
   int K, K1, N;                     // K total, K1 = columns served by map A1 (K1 == K when single source)
-  int seg_base[2], seg_rows[2];     // row segments; tiles_m[z] = ceil(seg_rows[z]/128)
-  int tiles0;                       // number of M tiles in segment 0
+  int seg_stride;                   // rows between segment bases (0: a single segment)
+  int tiles_per_seg;                // grid.y = segments * tiles_per_seg
+  int seg_rows;                     // static live rows of every segment (used when neither ctrl nor m_dev is set)
   int plane_rows;                   // rows between consecutive operand planes of A1 / A2 (NP > 1)
   const float* bias;                // [N]
   int epi;
@@ -30,11 +35,15 @@ struct TcGemmParams {
   size_t out_plane;                         // elements between output planes
   float* out_f32; int ld_f32;               // TC_EPI_F32 (plain) / RESID (in-place residual stream)
   const float* rot_cos; const float* rot_sin; int rot_cols;   // [rows,32] tables
-  const int* ctrl;                  // LightGlue device state (nullable): live rows = ctrl[2 + seg]; exit when stopped
+  const int* ctrl;                  // LightGlue device state (nullable), TC_CTRL_INTS per pair: live rows of segment g =
+                                    //   ctrl[(g >> 1) * 32 + 2 + (g & 1)]; the pair's tiles exit when it has stopped
   int ctrl_mode;                    // 0/1 transformer layer (skipped after an early exit); 2 assignment head: runs after a stop
-                                    //   too, weight rows / bias of layer ctrl[6] (w_layer_rows apart); 3 similarity: M = ctrl[2],
-                                    //   N = ctrl[3], the B operand is an activation (planes w_plane_rows apart, first row w_row0)
+                                    //   too, weight rows / bias of layer ctrl[6] (w_layer_rows apart); 3 similarity of pair p =
+                                    //   grid segment p: A = segment 2p (M = ctrl[2]), B = the activation rows of segment 2p + 1
+                                    //   (N = ctrl[3], planes w_plane_rows apart), outputs out_pair_stride floats apart
   int w_layer_rows, w_plane_rows, w_row0;
+  size_t out_pair_stride;
+  int out_planes;                   // planes written by the bf16 epilogues (0 = NP; 1 lets a three-plane GEMM feed a bf16 layer)
   float alpha;                      // epilogue: (acc + bias) * alpha (0 means 1)
   const int* m_dev; int m_mult;     // nullable: live rows of segment 0 = *m_dev * m_mult (ALIKED keypoint count)
   int act;                          // 0 none, 1 SELU (after bias / residual)
@@ -102,9 +111,10 @@ __global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __
     if (p.ts) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.ts[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 6 + slot] = t; }
   };
   if (threadIdx.x == 0) stamp(0);                    // CTA start
-  const int seg = tile_m >= p.tiles0 ? 1 : 0;
-  const int row0 = p.seg_base[seg] + (tile_m - (seg ? p.tiles0 : 0)) * Cfg::BM;       // global row of the tile
-  int rows_live = p.seg_rows[seg] - (tile_m - (seg ? p.tiles0 : 0)) * Cfg::BM;        // live rows in this tile
+  const int gseg = tile_m / p.tiles_per_seg, tile_s = tile_m - gseg * p.tiles_per_seg;   // grid segment, tile inside it
+  const int seg = p.ctrl_mode == 3 ? 2 * gseg : gseg;                                  // row segment of the A operand
+  const int row0 = seg * p.seg_stride + tile_s * Cfg::BM;                              // global row of the tile
+  int rows_live = p.seg_rows - tile_s * Cfg::BM;                                      // live rows in this tile
   const int nkb = p.K / Cfg::BK;
 
   if (warp == 0 && lane == 0) {
@@ -131,20 +141,25 @@ __global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __
   pdl_wait();            // everything above overlaps the previous kernel's tail; operands are touched only below
   if (threadIdx.x == 0) stamp(1);                    // dependencies resolved
   int w_row = p.w_row0, n_live = p.N;
+  float* out_f32 = p.out_f32; float* out_f32_t = p.out_f32_t;
   if (p.ctrl) {          // device-resident sizes: pruning shrinks the segments, an early exit empties the layer
-    const bool sides = p.ctrl[2] > 0 && p.ctrl[3] > 0;
-    const bool on = sides && (p.ctrl_mode >= 2 || !p.ctrl[1]);
-    rows_live = on ? p.ctrl[2 + seg] - (tile_m - (seg ? p.tiles0 : 0)) * Cfg::BM : 0;
+    const int* c = p.ctrl + (seg >> 1) * TC_CTRL_INTS;
+    const bool sides = c[2] > 0 && c[3] > 0;
+    const bool on = sides && (p.ctrl_mode >= 2 || !c[1]);
+    rows_live = on ? c[2 + (seg & 1)] - tile_s * Cfg::BM : 0;
     if (p.ctrl_mode == 2) {
-      w_row += p.ctrl[6] * p.w_layer_rows;
+      w_row += c[6] * p.w_layer_rows;
       if (warp >= 2) {               // the bias depends on the layer: restage it (epilogue warps only)
         const int t = threadIdx.x - 64;
         if (t < BN) s_bias[t] = __ldg(p.bias + w_row + n0 + t);
         asm volatile("bar.sync 1, %0;" ::"n"(32 * Cfg::EPI_WARPS) : "memory");
       }
     } else if (p.ctrl_mode == 3) {
-      n_live = p.ctrl[3];
+      n_live = c[3];
       if (n0 >= n_live) rows_live = 0;
+      w_row = (seg + 1) * p.seg_stride;
+      out_f32 += gseg * p.out_pair_stride;
+      if (out_f32_t) out_f32_t += gseg * p.out_pair_stride;
     }
   }
   if (p.m_dev) rows_live = *p.m_dev * p.m_mult - tile_m * Cfg::BM;
@@ -228,16 +243,18 @@ __global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __
     float* sf = reinterpret_cast<float*>(stg);                      // fp32 tile [32 rows][32]
     uint32_t* sp = reinterpret_cast<uint32_t*>(stg);                // or one bf16 plane tile [32 rows][16 words]
     const int rows_q = rows_live - quad * 32;                       // live rows of this warp's quadrant
-    const size_t qrow0 = (size_t)row0 + quad * 32;
+    // output row of the quadrant: global row, except for the per-pair similarity matrices (row inside the pair's matrix)
+    const size_t qrow0 = (size_t)(p.ctrl_mode == 3 ? tile_s * Cfg::BM : row0) + quad * 32;
     uint4* myrow = reinterpret_cast<uint4*>(sf + lane * 32);
     auto store_f32_tile = [&](int gc) {
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int R = it * 4 + (lane >> 3), sl = lane & 7;
         const uint4 v = reinterpret_cast<const uint4*>(sf + R * 32)[sl ^ (R & 7)];
-        if (R < rows_q) *reinterpret_cast<uint4*>(p.out_f32 + (qrow0 + R) * p.ld_f32 + gc + sl * 4) = v;
+        if (R < rows_q) *reinterpret_cast<uint4*>(out_f32 + (qrow0 + R) * p.ld_f32 + gc + sl * 4) = v;
       }
     };
+    const int np_out = p.out_planes ? p.out_planes : NP;
 #pragma unroll 1
     for (int c0 = cgrp * 32; c0 < BN; c0 += 8 * Cfg::EPI_WARPS) {
       uint32_t v[32];
@@ -311,23 +328,23 @@ __global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __
           }
         }
       }
-      if (p.epi == TC_EPI_F32) {
+      if (p.epi == TC_EPI_F32 || p.epi == TC_EPI_F32_BF16) {
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           myrow[q ^ (lane & 7)] = make_uint4(__float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]), __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3]));
         __syncwarp();
         store_f32_tile(gc);
-        if (p.out_f32_t) {
+        if (out_f32_t) {
           // transposed copy (similarity^T for the column-wise statistics of the assignment): lane = row of the chunk,
           // so one store instruction writes 32 consecutive floats of a transposed row
           const int ncol = n_live - gc < 32 ? n_live - gc : 32;
           if (lane < rows_q) {
             for (int c = 0; c < ncol; ++c)
-              p.out_f32_t[(size_t)(gc + c) * p.ld_f32_t + qrow0 + lane] = sf[lane * 32 + ((((c >> 2) ^ (lane & 7)) << 2) | (c & 3))];
+              out_f32_t[(size_t)(gc + c) * p.ld_f32_t + qrow0 + lane] = sf[lane * 32 + ((((c >> 2) ^ (lane & 7)) << 2) | (c & 3))];
           }
         }
         __syncwarp();
-        continue;
+        if (p.epi == TC_EPI_F32) continue;
       }
       if (p.epi == TC_EPI_RESID_F32_BF16) {
         // x (fp32 residual stream, updated in place): row-contiguous load into the staging tile, add, write back
@@ -335,7 +352,7 @@ __global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __
         for (int it = 0; it < 8; ++it) {
           const int R = it * 4 + (lane >> 3), sl = lane & 7;
           uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (R < rows_q) v = *reinterpret_cast<const uint4*>(p.out_f32 + (qrow0 + R) * p.ld_f32 + gc + sl * 4);
+          if (R < rows_q) v = *reinterpret_cast<const uint4*>(out_f32 + (qrow0 + R) * p.ld_f32 + gc + sl * 4);
           reinterpret_cast<uint4*>(sf + R * 32)[sl ^ (R & 7)] = v;
         }
         __syncwarp();
@@ -353,6 +370,7 @@ __global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __
       // operand planes, one at a time: plane p = bf16(residual), residual -= plane p  (== tc::pack_planes2)
 #pragma unroll
       for (int pl = 0; pl < NP; ++pl) {
+        if (pl >= np_out) break;
         uint32_t w[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {

@@ -239,9 +239,12 @@ struct b2s_reproj {
   long long launches = 0;
 };
 
+// k_reproj_assign keeps one owner word per keypoint in shared memory (227 KB per CTA on sm_100)
+static constexpr int REPROJ_MAX_KPS = 49152;
+
 extern "C" int b2s_reproj_create(int device, int max_points, int max_kps, int cand_cap, b2s_reproj** out) {
-  if (!out || max_points < 1 || max_kps < 1 || cand_cap < 1 || cand_cap > REPROJ_MAXCAP || max_kps > 12000) {
-    set_error("b2s_reproj_create: bad arguments (cand_cap <= %d, max_kps <= 12000)", REPROJ_MAXCAP);
+  if (!out || max_points < 1 || max_kps < 1 || cand_cap < 1 || cand_cap > REPROJ_MAXCAP || max_kps > REPROJ_MAX_KPS) {
+    set_error("b2s_reproj_create: bad arguments (cand_cap <= %d, max_kps <= %d)", REPROJ_MAXCAP, REPROJ_MAX_KPS);
     return B2S_EINVAL;
   }
   int ndev = 0;

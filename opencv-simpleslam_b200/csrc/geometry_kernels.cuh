@@ -387,10 +387,12 @@ struct ReprojParams {
   int32_t* pos;              // [P] scratch of the assignment fixpoint
   float* uv;                 // [P,2] projections (float32 like the reference's uv_all), (-1,-1) behind the camera
   int32_t* out_kp;           // [P] assigned keypoint or -1
-  int32_t* flags;            // [0] != 0: some point had more than `cap` keypoints in its window
+  int32_t* flags;            // [0] != 0: a point whose candidate list was truncated to `cap` ran out of candidates (result unreliable)
 };
 
-constexpr int REPROJ_WARPS = 8, REPROJ_MAXCAP = 64;
+// A point keeps at most `cap` candidates: only keypoints that pass the descriptor gate (distance <= thr) are stored - the
+// others can never be chosen - and when more than `cap` pass, the `cap` nearest in descriptor distance survive.
+constexpr int REPROJ_WARPS = 8, REPROJ_MAXCAP = 256, REPROJ_TRUNC = 1 << 30;
 
 __global__ void __launch_bounds__(32 * REPROJ_WARPS) k_reproj_candidates(ReprojParams p) {
   pdl_wait();
@@ -416,6 +418,7 @@ __global__ void __launch_bounds__(32 * REPROJ_WARPS) k_reproj_candidates(ReprojP
   if (!live) { if (lane == 0) p.count[pt] = 0; return; }
   const float* mpd = p.mp_desc + (size_t)row * p.max_obs * 128;
   int cnt = 0;
+  bool truncated = false;
   for (int base = 0; base < p.N; base += 32) {
     const int i = base + lane;
     bool in = false;
@@ -435,24 +438,44 @@ __global__ void __launch_bounds__(32 * REPROJ_WARPS) k_reproj_candidates(ReprojP
         const float d = sqrtf(warp_sum(fmaf(e3, e3, fmaf(e2, e2, fmaf(e1, e1, e0 * e0)))));
         best = fminf(best, d);
       }
-      if (cnt < p.cap && lane == 0) { s_kp[warp][cnt] = j; s_d[warp][cnt] = best; }
-      ++cnt;
+      if (!((double)best <= p.thr)) continue;           // fails the descriptor gate: never assignable (uniform per warp)
+      if (cnt < p.cap) {
+        if (lane == 0) { s_kp[warp][cnt] = j; s_d[warp][cnt] = best; }
+        ++cnt;
+      } else {
+        // list full: the new candidate replaces the current worst (largest distance, then largest index) if it is better
+        truncated = true;
+        __syncwarp();
+        float wd = -1.f; int wq = -1, wk = -1;
+        for (int q = lane; q < p.cap; q += 32) {
+          const float dq = s_d[warp][q]; const int kq = s_kp[warp][q];
+          if (dq > wd || (dq == wd && kq > wk)) { wd = dq; wq = q; wk = kq; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float od = __shfl_xor_sync(0xffffffffu, wd, o);
+          const int oq = __shfl_xor_sync(0xffffffffu, wq, o), ok = __shfl_xor_sync(0xffffffffu, wk, o);
+          if (od > wd || (od == wd && ok > wk)) { wd = od; wq = oq; wk = ok; }
+        }
+        if (lane == 0 && (best < wd || (best == wd && j < wk))) { s_kp[warp][wq] = j; s_d[warp][wq] = best; }
+        __syncwarp();
+      }
     }
   }
   __syncwarp();
-  if (cnt > p.cap) { if (lane == 0) atomicOr(p.flags, 1); cnt = p.cap; }
-  // rank sort by (distance, keypoint index); the list is already ascending in the index
+  // rank sort by (distance, keypoint index)
   for (int e = lane; e < cnt; e += 32) {
     const float d = s_d[warp][e];
+    const int ke = s_kp[warp][e];
     int rank = 0;
     for (int q = 0; q < cnt; ++q) {
       const float dq = s_d[warp][q];
-      rank += (dq < d || (dq == d && q < e)) ? 1 : 0;
+      rank += (dq < d || (dq == d && s_kp[warp][q] < ke)) ? 1 : 0;
     }
-    p.cand_kp[(size_t)pt * p.cap + rank] = s_kp[warp][e];
+    p.cand_kp[(size_t)pt * p.cap + rank] = ke;
     p.cand_d[(size_t)pt * p.cap + rank] = d;
   }
-  if (lane == 0) p.count[pt] = cnt;
+  if (lane == 0) p.count[pt] = cnt | (truncated ? REPROJ_TRUNC : 0);
 }
 
 // one CTA; dynamic smem: owner[N]
@@ -468,12 +491,12 @@ __global__ void __launch_bounds__(1024) k_reproj_assign(ReprojParams p) {
     __syncthreads();
     for (int q = tid; q < p.P; q += 1024) {
       const int ps = p.pos[q];
-      if (ps < p.count[q] && (double)p.cand_d[(size_t)q * p.cap + ps] <= p.thr) atomicMin(&owner[p.cand_kp[(size_t)q * p.cap + ps]], q);
+      if (ps < (p.count[q] & (REPROJ_TRUNC - 1))) atomicMin(&owner[p.cand_kp[(size_t)q * p.cap + ps]], q);
     }
     __syncthreads();
     for (int q = tid; q < p.P; q += 1024) {
       const int ps = p.pos[q];
-      if (ps < p.count[q] && (double)p.cand_d[(size_t)q * p.cap + ps] <= p.thr && owner[p.cand_kp[(size_t)q * p.cap + ps]] != q) {
+      if (ps < (p.count[q] & (REPROJ_TRUNC - 1)) && owner[p.cand_kp[(size_t)q * p.cap + ps]] != q) {
         p.pos[q] = ps + 1;
         changed = 1;
       }
@@ -484,9 +507,10 @@ __global__ void __launch_bounds__(1024) k_reproj_assign(ReprojParams p) {
     if (!c) break;
   }
   for (int q = tid; q < p.P; q += 1024) {
-    const int ps = p.pos[q];
-    const bool ok = ps < p.count[q] && (double)p.cand_d[(size_t)q * p.cap + ps] <= p.thr;
+    const int ps = p.pos[q], cnt = p.count[q] & (REPROJ_TRUNC - 1);
+    const bool ok = ps < cnt;                    // every stored candidate passed the descriptor gate
     p.out_kp[q] = ok ? p.cand_kp[(size_t)q * p.cap + ps] : -1;
+    if (!ok && (p.count[q] & REPROJ_TRUNC)) atomicOr(p.flags, 1);   // lost all `cap` nearest candidates: the dropped ones might have matched
   }
 }
 #endif  // __CUDACC__

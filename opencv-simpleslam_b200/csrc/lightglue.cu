@@ -1,7 +1,9 @@
 // lightglue.cu - host orchestration of the LightGlue matcher behind b2s_lightglue_*.
 // Replaces `matcher({...})` at /root/reference/slam/core/features_utils.py:157-161 (the
 // arithmetic itself lives in the un-vendored `lightglue` package; spec: SURVEY.md A.3).
-#include "gemm_simt.cuh"
+// One launch sequence serves a BATCH of up to LG_MAXP independent pairs (keyframe-window all-pairs at
+// keyframe_utils.py:153 / triangulation_utils.py:131, or consecutive pairs of a stream): every kernel takes the pair
+// as a grid dimension, sizes and early-exit / pruning decisions live in per-pair device state.
 #include "lightglue_kernels.cuh"
 #include "lightglue_tc.cuh"
 
@@ -24,29 +26,27 @@ struct b2s_lg {
   float *in_w = nullptr, *in_b = nullptr, *wr = nullptr;
   std::vector<LgLayer> L;
   std::vector<float> thr;
-  // workspace (rows = 2*cap; image0 at row 0, image1 at row cap)
-  int cap = 0;
-  float *kn = nullptr, *cosb[2] = {nullptr, nullptr}, *sinb[2] = {nullptr, nullptr}, *x[2] = {nullptr, nullptr};
-  float *qkv = nullptr, *ctx = nullptr, *msg = nullptr, *h1 = nullptr, *tok = nullptr, *sim = nullptr, *simT = nullptr;
+  // workspace: segments of `cap` rows, segment 2p + s = image s of pair p; pcap pairs
+  int cap = 0, pcap = 0;
+  float *cosb[2] = {nullptr, nullptr}, *sinb[2] = {nullptr, nullptr}, *x[2] = {nullptr, nullptr};
+  float *sim = nullptr, *simT = nullptr;
   float *rmax = nullptr, *rlog = nullptr, *cmax = nullptr, *clog = nullptr, *ls = nullptr, *max0 = nullptr;
-  int *ind[2] = {nullptr, nullptr}, *keep = nullptr, *srcmap = nullptr, *adapt = nullptr, *m0 = nullptr, *m1 = nullptr, *ctrl = nullptr;
-  const float** wfinal_tab = nullptr; const float** bfinal_tab = nullptr; const float** wmatch_tab = nullptr;  // device tables [L]
-  float* bmatch_tab = nullptr;
-  int *prune_scratch[2] = {nullptr, nullptr};
+  int *ind[2] = {nullptr, nullptr}, *prune = nullptr, *adapt = nullptr, *m0 = nullptr, *m1 = nullptr, *ctrl = nullptr;
+  const float** wmatch_tab = nullptr; float* bmatch_tab = nullptr;   // device tables [L]
   int* h_ctrl = nullptr;  // pinned
   // host-API staging
   DeviceArena hostarena;
   int hcap = 0;
   float *hk[2] = {nullptr, nullptr}, *hd[2] = {nullptr, nullptr}, *hms[2] = {nullptr, nullptr}, *hmscores = nullptr;
   int32_t *hmatches = nullptr, *hnm = nullptr, *hm[2] = {nullptr, nullptr}, *hprune[2] = {nullptr, nullptr};
-  // debug
+  // debug (pair 0 of a batch)
   int debug = 0;
   float* dbg_layers = nullptr;  // [n_layers][2*cap][256]
   int dbg_m[16], dbg_n[16], dbg_nlayers = 0, dbg_simm = 0, dbg_simn = 0;
   long long launches = 0;
   KernelProf prof;
   unsigned long long* stats = nullptr;   // device: [0] sum nq*nk over self-attention problems, [1] over cross-attention problems
-  LgTensorCore* tc = nullptr;   // bf16 tcgen05 path (precision == B2S_BF16)
+  LgTensorCore* tc = nullptr;   // tcgen05 layers: bf16 operands (precision == B2S_BF16) or fp32 as three bf16 planes
 };
 
 static int upload_t(b2s_lg* h, const WeightBlob& wb, const std::string& name, size_t numel, float** out) {
@@ -56,43 +56,44 @@ static int upload_t(b2s_lg* h, const WeightBlob& wb, const std::string& name, si
   return h->warena.upload(out, v);
 }
 
-static int lg_alloc_ws(b2s_lg* h, int cap) {
+static size_t lg_ws_bytes(int np, int cap, int pcap, int n_layers, bool debug) {
+  const size_t R = (size_t)2 * pcap * cap, PC = (size_t)pcap * cap;
+  size_t b = 4 * (2 * (R * 32 * 2 + R * 256 + R) + R /*prune*/ + R /*ls*/ + 2 * PC * cap + 7 * PC + (size_t)pcap * (LG_ADAPT_INTS + LGC_INTS));
+  if (debug) b += 4 * (size_t)n_layers * 2 * cap * 256;
+  return b + lgtc_ws_bytes(np, cap, pcap);
+}
+
+static int lg_alloc_ws(b2s_lg* h, int cap, int pcap) {
   cap = (cap + 127) / 128 * 128;
+  pcap = std::max(1, std::min(pcap, LG_MAXP));
+  if (cap > 32 * LG_MAXBLK) { set_error("b2s_lightglue: %d keypoints per image exceed the supported %d", cap, 32 * LG_MAXBLK); return B2S_ESIZE; }
   h->wsarena.release();
-  h->cap = 0;
-  const size_t R = (size_t)2 * cap;
-  B2S_TRY(h->wsarena.alloc(&h->kn, R * 2));
+  h->cap = h->pcap = 0;
+  const size_t R = (size_t)2 * pcap * cap, PC = (size_t)pcap * cap;
   for (int i = 0; i < 2; ++i) {
     B2S_TRY(h->wsarena.alloc(&h->cosb[i], R * 32));
     B2S_TRY(h->wsarena.alloc(&h->sinb[i], R * 32));
     B2S_TRY(h->wsarena.alloc(&h->x[i], R * 256));
     B2S_TRY(h->wsarena.alloc(&h->ind[i], R));
-    B2S_TRY(h->wsarena.alloc(&h->prune_scratch[i], (size_t)cap));
   }
-  B2S_TRY(h->wsarena.alloc(&h->qkv, R * 768));
-  B2S_TRY(h->wsarena.alloc(&h->ctx, R * 256));
-  B2S_TRY(h->wsarena.alloc(&h->msg, R * 256));
-  B2S_TRY(h->wsarena.alloc(&h->h1, R * 512));
-  B2S_TRY(h->wsarena.alloc(&h->tok, R));
-  B2S_TRY(h->wsarena.alloc(&h->sim, (size_t)cap * cap));
-  B2S_TRY(h->wsarena.alloc(&h->simT, (size_t)cap * cap));   // transposed similarity (tensor-core path)
-  B2S_TRY(h->wsarena.alloc(&h->rmax, (size_t)cap));
-  B2S_TRY(h->wsarena.alloc(&h->rlog, (size_t)cap));
-  B2S_TRY(h->wsarena.alloc(&h->cmax, (size_t)cap));
-  B2S_TRY(h->wsarena.alloc(&h->clog, (size_t)cap));
+  B2S_TRY(h->wsarena.alloc(&h->prune, R));
+  B2S_TRY(h->wsarena.alloc(&h->sim, PC * cap));
+  B2S_TRY(h->wsarena.alloc(&h->simT, PC * cap));   // transposed similarity
+  B2S_TRY(h->wsarena.alloc(&h->rmax, PC));
+  B2S_TRY(h->wsarena.alloc(&h->rlog, PC));
+  B2S_TRY(h->wsarena.alloc(&h->cmax, PC));
+  B2S_TRY(h->wsarena.alloc(&h->clog, PC));
   B2S_TRY(h->wsarena.alloc(&h->ls, R));
-  B2S_TRY(h->wsarena.alloc(&h->max0, (size_t)cap));
-  B2S_TRY(h->wsarena.alloc(&h->keep, R));
-  B2S_TRY(h->wsarena.alloc(&h->srcmap, R));
-  B2S_TRY(h->wsarena.alloc(&h->adapt, (size_t)8 + 2 * LG_MAXBLK));
-  B2S_TRY(h->wsarena.alloc(&h->m0, (size_t)cap));
-  B2S_TRY(h->wsarena.alloc(&h->m1, (size_t)cap));
-  B2S_TRY(h->wsarena.alloc(&h->ctrl, (size_t)LGC_INTS));
+  B2S_TRY(h->wsarena.alloc(&h->max0, PC));
+  B2S_TRY(h->wsarena.alloc(&h->adapt, (size_t)pcap * LG_ADAPT_INTS));
+  B2S_TRY(h->wsarena.alloc(&h->m0, PC));
+  B2S_TRY(h->wsarena.alloc(&h->m1, PC));
+  B2S_TRY(h->wsarena.alloc(&h->ctrl, (size_t)pcap * LGC_INTS));
   h->dbg_layers = nullptr;
-  if (h->debug) B2S_TRY(h->wsarena.alloc(&h->dbg_layers, (size_t)h->cfg.n_layers * R * 256));
-  B2S_CUDA(cudaMemset(h->ctrl, 0, LGC_INTS * sizeof(int)));
-  if (h->tc) B2S_TRY(lgtc_alloc_ws(h->tc, cap));
-  h->cap = cap;
+  if (h->debug) B2S_TRY(h->wsarena.alloc(&h->dbg_layers, (size_t)h->cfg.n_layers * 2 * cap * 256));
+  B2S_CUDA(cudaMemset(h->ctrl, 0, (size_t)pcap * LGC_INTS * sizeof(int)));
+  B2S_TRY(lgtc_alloc_ws(h->tc, cap, pcap));
+  h->cap = cap; h->pcap = pcap;
   return 0;
 }
 
@@ -104,8 +105,8 @@ extern "C" void b2s_lg_default_cfg(b2s_lg_cfg* c) {
 
 extern "C" int b2s_lightglue_create(const b2s_lg_cfg* cfg, const void* weights, size_t nbytes, int device, b2s_lg** out) {
   if (!cfg || !weights || !out) { set_error("b2s_lightglue_create: null argument"); return B2S_EINVAL; }
-  if (cfg->precision != B2S_FP32 && cfg->precision != B2S_BF16 && cfg->precision != B2S_FP32_SIMT) {
-    set_error("b2s_lightglue_create: unknown precision %d", cfg->precision);
+  if (cfg->precision != B2S_FP32 && cfg->precision != B2S_BF16) {
+    set_error("b2s_lightglue_create: unknown precision %d (B2S_FP32 = fp32-faithful on tcgen05, B2S_BF16)", cfg->precision);
     return B2S_EINVAL;
   }
   if (cfg->dim != 256 || cfg->heads != 4 || cfg->in_dim != 128 || cfg->n_layers < 1 || cfg->n_layers > 16) {
@@ -193,29 +194,28 @@ extern "C" int b2s_lightglue_create(const b2s_lg_cfg* cfg, const void* weights, 
     h->thr.push_back((float)std::min(1.0, std::max(0.0, th)));
   }
   {
-    std::vector<const float*> wf, bf, wm; std::vector<float> bm;
-    for (const LgLayer& l : h->L) { wf.push_back(l.wfinal); bf.push_back(l.bfinal); wm.push_back(l.wmatch); bm.push_back(l.bmatch); }
-    if ((rc = h->warena.upload(&h->wfinal_tab, wf)) || (rc = h->warena.upload(&h->bfinal_tab, bf)) ||
-        (rc = h->warena.upload(&h->wmatch_tab, wm)) || (rc = h->warena.upload(&h->bmatch_tab, bm))) return fail(rc);
+    std::vector<const float*> wm; std::vector<float> bm;
+    for (const LgLayer& l : h->L) { wm.push_back(l.wmatch); bm.push_back(l.bmatch); }
+    if ((rc = h->warena.upload(&h->wmatch_tab, wm)) || (rc = h->warena.upload(&h->bmatch_tab, bm))) return fail(rc);
   }
   if ((rc = h->warena.alloc(&h->stats, (size_t)4))) return fail(rc);
   cudaMemset(h->stats, 0, 4 * sizeof(unsigned long long));
   if (cudaMallocHost((void**)&h->h_ctrl, LGC_INTS * sizeof(int)) != cudaSuccess) { set_error("cudaMallocHost failed"); return fail(B2S_ENOMEM); }
-  cudaFuncSetAttribute(k_attn_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-  if (cfg->precision != B2S_FP32_SIMT) {   // tensor-core paths: bf16 operands, or fp32 carried as three bf16 planes
-    if ((rc = lgtc_create(&h->tc, h->L.size(), cfg->precision == B2S_BF16 ? 1 : 3))) return fail(rc);
-    lgtc_set_prof(h->tc, &h->prof, h->stats);
-    for (size_t i = 0; i < h->L.size(); ++i) {
-      const LgLayer& l = h->L[i];
-      LgTcLayerSrc s = {l.wqkv, l.bqkv, l.wo, l.bo, l.w1, l.b1, l.lng, l.lnb, l.w2, l.b2,
-                        l.cwqkv, l.cbqkv, l.cwo, l.cbo, l.cw1, l.cb1, l.clng, l.clnb, l.cw2, l.cb2};
-      if ((rc = lgtc_set_layer(h->tc, (int)i, s))) return fail(rc);
-    }
+  // tensor-core layers: bf16 operands, or fp32 carried as three bf16 planes
+  if ((rc = lgtc_create(&h->tc, h->L.size(), cfg->precision == B2S_BF16 ? 1 : 3))) return fail(rc);
+  lgtc_set_prof(h->tc, &h->prof, h->stats);
+  for (size_t i = 0; i < h->L.size(); ++i) {
+    const LgLayer& l = h->L[i];
+    LgTcLayerSrc s = {l.wqkv, l.bqkv, l.wo, l.bo, l.w1, l.b1, l.lng, l.lnb, l.w2, l.b2,
+                      l.cwqkv, l.cbqkv, l.cwo, l.cbo, l.cw1, l.cb1, l.clng, l.clnb, l.cw2, l.cb2};
+    if ((rc = lgtc_set_layer(h->tc, (int)i, s))) return fail(rc);
+  }
+  {
     std::vector<const float*> wf, bf;
     for (const LgLayer& l : h->L) { wf.push_back(l.wfinal); bf.push_back(l.bfinal); }
-    if ((rc = lgtc_set_final(h->tc, wf, bf))) return fail(rc);
+    if ((rc = lgtc_set_final(h->tc, wf, bf)) || (rc = lgtc_set_input(h->tc, h->in_w, h->in_b))) return fail(rc);
   }
-  if ((rc = lg_alloc_ws(h, cfg->max_kp > 0 ? cfg->max_kp : 2048))) return fail(rc);
+  if ((rc = lg_alloc_ws(h, cfg->max_kp > 0 ? cfg->max_kp : 2048, 1))) return fail(rc);
   *out = h;
   return 0;
 }
@@ -258,279 +258,123 @@ extern "C" int b2s_lg_profile_read(b2s_lg* h, int cls, double* ms, long long* n)
 extern "C" int b2s_lg_set_debug(b2s_lg* h, int on) {
   if (!h) return B2S_EINVAL;
   B2S_CUDA(cudaSetDevice(h->device));
+  B2S_CUDA(cudaDeviceSynchronize());
   h->debug = on;
-  return lg_alloc_ws(h, h->cap);
+  return lg_alloc_ws(h, h->cap, h->pcap);
 }
 
-// one Linear over both images' live rows (m, n = upper bounds; live counts come from h->ctrl)
-static int lg_linear(b2s_lg* h, cudaStream_t st, const float* A1, int lda1, int K1, const float* A2, int lda2,
-                     const float* W, int K, int N, const float* bias, float* C, int ldc, int m, int n,
-                     const float* residual, int ldr, float alpha = 1.f) {
-  GemmParams g;
-  g.A1 = A1; g.lda1 = lda1; g.K1 = K1; g.A2 = A2; g.lda2 = lda2;
-  g.W = W; g.ldw = K; g.C = C; g.ldc = ldc; g.N = N; g.K = K;
-  g.nseg = 2; g.seg_base[0] = 0; g.seg_base[1] = h->cap; g.seg_rows[0] = m; g.seg_rows[1] = n;
-  g.bias = bias; g.alpha = alpha; g.residual = residual; g.ldr = ldr;
-  g.lg_ctrl = h->ctrl; g.lg_mode = 1;
-  return gemm_simt(g, st, &h->launches, &h->prof);
+extern "C" size_t b2s_lg_workspace_bytes(const b2s_lg_cfg* cfg, int max_kp, int pairs) {
+  if (!cfg || max_kp < 1 || pairs < 1) return 0;
+  return lg_ws_bytes(cfg->precision == B2S_BF16 ? 1 : 3, (max_kp + 127) / 128 * 128, std::min(pairs, LG_MAXP), cfg->n_layers, false);
 }
 
-static int lg_attention(b2s_lg* h, cudaStream_t st, AttnParams ap, int cross, int maxq) {
-  if (maxq <= 0) return 0;
-  ap.ctrl = h->ctrl; ap.cross = cross; ap.stats = h->prof.on ? h->stats : nullptr;
-  dim3 grid(cdiv(maxq, ATT_B), 4, 2);
-  h->prof.mark(PROF_ATTN, st);
-  launch_k(k_attn_fp32, grid, 256, ATT_SMEM, st, ap);
-  h->prof.mark(PROF_ATTN, st);
-  ++h->launches;
-  B2S_LAUNCH_CHECK();
-  return 0;
-}
+extern "C" int b2s_lg_max_batch(void) { return LG_MAXP; }
 
-static int lg_ffn(b2s_lg* h, cudaStream_t st, float* x, const float* msg, const float* w1, const float* b1,
-                  const float* lng, const float* lnb, const float* w2, const float* b2, int m, int n) {
-  // h1 = [x | msg] W1^T + b1 ; LN ; GELU ; x += h1 W2^T + b2
-  B2S_TRY(lg_linear(h, st, x, 256, 256, msg, 256, w1, 512, 512, b1, h->h1, 512, m, n, nullptr, 0));
-  RowSeg seg = {{0, h->cap}, {m, n}};
-  dim3 grid(cdiv(std::max(m, n), 8), 2);
-  launch_k(k_ln_gelu_512, grid, 256, 0, st, h->h1, seg, lng, lnb, (const int*)h->ctrl);
-  ++h->launches;
-  B2S_LAUNCH_CHECK();
-  return lg_linear(h, st, h->h1, 512, 512, nullptr, 0, w2, 512, 256, b2, x, 256, m, n, x, 256);
-}
-
-static int lg_layer_fp32(b2s_lg* h, cudaStream_t st, int li, int cur, int m, int n) {
-  const LgLayer& l = h->L[li];
-  float* x = h->x[cur];
-  const int cap = h->cap;
-  // ---- self block (shared weights, both images) ----
-  {
-    GemmParams g;
-    g.A1 = x; g.lda1 = 256; g.K1 = 256; g.W = l.wqkv; g.ldw = 256; g.C = h->qkv; g.ldc = 768; g.N = 768; g.K = 256;
-    g.nseg = 2; g.seg_base[0] = 0; g.seg_base[1] = cap; g.seg_rows[0] = m; g.seg_rows[1] = n;
-    g.bias = l.bqkv; g.rot_cols = 512; g.rot_cos = h->cosb[cur]; g.rot_sin = h->sinb[cur];
-    g.lg_ctrl = h->ctrl; g.lg_mode = 1;
-    B2S_TRY(gemm_simt(g, st, &h->launches, &h->prof));
-  }
-  AttnParams ap;
-  ap.ldq = ap.ldk = ap.ldv = 768; ap.ldo = 256; ap.scale = 0.125f;
-  ap.prob[0] = {h->qkv, h->qkv + 256, h->qkv + 512, h->ctx, m, m};
-  ap.prob[1] = {h->qkv + (size_t)cap * 768, h->qkv + (size_t)cap * 768 + 256, h->qkv + (size_t)cap * 768 + 512,
-                h->ctx + (size_t)cap * 256, n, n};
-  B2S_TRY(lg_attention(h, st, ap, 0, std::max(m, n)));
-  B2S_TRY(lg_linear(h, st, h->ctx, 256, 256, nullptr, 0, l.wo, 256, 256, l.bo, h->msg, 256, m, n, nullptr, 0));
-  B2S_TRY(lg_ffn(h, st, x, h->msg, l.w1, l.b1, l.lng, l.lnb, l.w2, l.b2, m, n));
-  // ---- cross block ----
-  B2S_TRY(lg_linear(h, st, x, 256, 256, nullptr, 0, l.cwqkv, 256, 512, l.cbqkv, h->qkv, 512, m, n, nullptr, 0));
-  ap.ldq = ap.ldk = ap.ldv = 512;
-  float* q0 = h->qkv; float* q1 = h->qkv + (size_t)cap * 512;
-  ap.prob[0] = {q0, q1, q1 + 256, h->ctx, m, n};
-  ap.prob[1] = {q1, q0, q0 + 256, h->ctx + (size_t)cap * 256, n, m};
-  B2S_TRY(lg_attention(h, st, ap, 1, std::max(m, n)));
-  B2S_TRY(lg_linear(h, st, h->ctx, 256, 256, nullptr, 0, l.cwo, 256, 256, l.cbo, h->msg, 256, m, n, nullptr, 0));
-  B2S_TRY(lg_ffn(h, st, x, h->msg, l.cw1, l.cb1, l.clng, l.clnb, l.cw2, l.cb2, m, n));
-  return 0;
-}
-
-static int fill_i32(b2s_lg* h, cudaStream_t st, int32_t* p, int n, int32_t v) {
-  if (!p || n <= 0) return 0;
-  launch_k(k_fill_i32, cdiv(n, 256), 256, 0, st, p, n, v);
-  ++h->launches;
-  B2S_LAUNCH_CHECK();
-  return 0;
-}
-static int fill_f32(b2s_lg* h, cudaStream_t st, float* p, int n, float v) {
-  if (!p || n <= 0) return 0;
-  launch_k(k_fill_f32, cdiv(n, 256), 256, 0, st, p, n, v);
-  ++h->launches;
-  B2S_LAUNCH_CHECK();
-  return 0;
-}
-
-// The whole match is enqueued without a single host synchronisation: the adaptive-depth exit test
-// and the adaptive-width pruning (upstream decides both on the host after every layer) are taken
-// on the device; kernels of layers behind an exit find the stop flag set and return at once.
-extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, int m, const float* k1,
-                                   const float* d1, int n, const float* size0, const float* size1, void* stream,
-                                   int32_t* matches, float* mscores, int32_t* n_matches, int32_t* stop_layer,
-                                   int32_t* matches0, int32_t* matches1, float* ms0, float* ms1,
-                                   int32_t* prune0, int32_t* prune1) {
-  if (!h || !matches || !mscores || !n_matches || m < 0 || n < 0) { set_error("b2s_lightglue_match: bad argument"); return B2S_EINVAL; }
+extern "C" int b2s_lg_reserve(b2s_lg* h, int max_kp, int pairs) {
+  if (!h || max_kp < 1 || pairs < 1) { set_error("b2s_lg_reserve: bad argument"); return B2S_EINVAL; }
   B2S_CUDA(cudaSetDevice(h->device));
-  cudaStream_t st = (cudaStream_t)stream;
+  const int cap = (max_kp + 127) / 128 * 128, pc = std::min(pairs, LG_MAXP);
+  if (cap <= h->cap && pc <= h->pcap) return 0;
+  B2S_CUDA(cudaDeviceSynchronize());
+  return lg_alloc_ws(h, std::max(cap, h->cap), std::max(pc, h->pcap));
+}
+
+// ---------------------------------------------------------------------------------------------
+// One launch sequence for np <= LG_MAXP pairs.  The whole batch is enqueued without a single host synchronisation: the
+// adaptive-depth exit test and the adaptive-width pruning (upstream decides both on the host after every layer) are
+// taken on the device per pair; kernels find a stopped pair's flag set and skip its tiles at once.
+// ---------------------------------------------------------------------------------------------
+static int lg_run(b2s_lg* h, cudaStream_t st, const LgBatchIn& in, const LgBatchOut& out, int np) {
   const int L = h->cfg.n_layers;
   const bool do_stop = h->cfg.depth_conf > 0.f;
   const bool do_prune = h->cfg.width_conf > 0.f;
-  // full-size outputs default to "unmatched"
-  B2S_TRY(fill_i32(h, st, matches0, m, -1));
-  B2S_TRY(fill_i32(h, st, matches1, n, -1));
-  B2S_TRY(fill_f32(h, st, ms0, m, 0.f));
-  B2S_TRY(fill_f32(h, st, ms1, n, 0.f));
-  if (!do_prune) {  // upstream: prune = n_layers everywhere when pruning is off
-    B2S_TRY(fill_i32(h, st, prune0, m, L));
-    B2S_TRY(fill_i32(h, st, prune1, n, L));
-  }
-  if (m == 0 || n == 0) {
-    B2S_CUDA(cudaMemsetAsync(n_matches, 0, sizeof(int32_t), st));
-    if (do_prune) { B2S_TRY(fill_i32(h, st, prune0, m, 1)); B2S_TRY(fill_i32(h, st, prune1, n, 1)); }
-    B2S_TRY(fill_i32(h, st, stop_layer, 1, 1));
-    return 0;
-  }
-  if (std::max(m, n) > h->cap) {
+  int maxm = 0, maxn = 0;
+  for (int p = 0; p < np; ++p) { maxm = std::max(maxm, in.pr[p].n[0]); maxn = std::max(maxn, in.pr[p].n[1]); }
+  const int maxrows = std::max(maxm, maxn);
+  if (maxrows > h->cap || np > h->pcap) {
     B2S_CUDA(cudaStreamSynchronize(st));
-    B2S_TRY(lg_alloc_ws(h, std::max(m, n)));
+    B2S_TRY(lg_alloc_ws(h, std::max(maxrows, h->cap), std::max(np, h->pcap)));
   }
-  const int cap = h->cap;
-  int* pr0 = do_prune ? (prune0 ? prune0 : h->prune_scratch[0]) : nullptr;
-  int* pr1 = do_prune ? (prune1 ? prune1 : h->prune_scratch[1]) : nullptr;
+  const int cap = h->cap, nseg = 2 * np;
+  const size_t plane_rows = (size_t)2 * h->pcap * cap;
   {
-    PosencParams pp;
-    pp.kp[0] = k0; pp.kp[1] = k1; pp.n[0] = m; pp.n[1] = n; pp.base[0] = 0; pp.base[1] = cap;
-    pp.has_size[0] = size0 != nullptr; pp.has_size[1] = size1 != nullptr;
-    pp.size[0][0] = size0 ? size0[0] : 0.f; pp.size[0][1] = size0 ? size0[1] : 0.f;
-    pp.size[1][0] = size1 ? size1[0] : 0.f; pp.size[1][1] = size1 ? size1[1] : 0.f;
-    pp.Wr = h->wr; pp.kn = h->kn; pp.cosb = h->cosb[0]; pp.sinb = h->sinb[0]; pp.ind = h->ind[0];
-    pp.prune[0] = pr0; pp.prune[1] = pr1;
+    PosencParams pp = {};
+    pp.in = in; pp.cap = cap; pp.Wr = h->wr; pp.cosb = h->cosb[0]; pp.sinb = h->sinb[0]; pp.ind = h->ind[0]; pp.prune = h->prune;
+    pp.din = lgtc_din(h->tc); pp.din_plane = plane_rows * 128;
     pp.ctrl = h->ctrl; pp.last_init = (do_stop || do_prune) ? 0 : L - 1;
-    launch_k(k_lg_posenc, dim3(cdiv(std::max(m, n), 64), 2), 256, 0, st, pp);
+    launch_k(k_lg_posenc, dim3(cdiv(std::max(maxrows, 1), 64), nseg), 256, 0, st, pp);
     ++h->launches;
     B2S_LAUNCH_CHECK();
   }
-  // input projection (two sources -> rows 0.. and cap..)
-  for (int s = 0; s < 2; ++s) {
-    GemmParams g;
-    g.A1 = s ? d1 : d0; g.lda1 = 128; g.K1 = 128; g.W = h->in_w; g.ldw = 128; g.K = 128; g.N = 256;
-    g.C = h->x[0] + (size_t)(s ? cap : 0) * 256; g.ldc = 256; g.M = s ? n : m; g.bias = h->in_b;
-    B2S_TRY(gemm_simt(g, st, &h->launches));
-  }
   h->dbg_nlayers = 0;
-  // with pruning enabled layer i lives in ping-pong buffer i & 1 (the gather after layer i moves the
-  // survivors across); without it everything stays in buffer 0
-  auto buf_of = [&](int i) { return do_prune ? (i & 1) : 0; };
-  for (int i = 0; i < L; ++i) {
-    const int cur = buf_of(i);
-    if (h->tc) B2S_TRY(lgtc_layer(h->tc, st, i, h->x[cur], h->cosb[cur], h->sinb[cur], cap, m, n, h->ctrl, i == 0, &h->launches));
-    else B2S_TRY(lg_layer_fp32(h, st, i, cur, m, n));
-    if (h->debug && h->dbg_layers) {   // debug only: snapshot the layer output and its live sizes (host sync)
-      B2S_CUDA(cudaMemcpyAsync(h->dbg_layers + (size_t)i * 2 * cap * 256, h->x[cur], (size_t)2 * cap * 256 * sizeof(float),
-                               cudaMemcpyDeviceToDevice, st));
-      B2S_CUDA(cudaMemcpyAsync(h->h_ctrl, h->ctrl, LGC_INTS * sizeof(int), cudaMemcpyDeviceToHost, st));
-      B2S_CUDA(cudaStreamSynchronize(st));
-      if (!h->h_ctrl[LGC_STOP] && h->h_ctrl[LGC_M] > 0 && h->h_ctrl[LGC_N] > 0) {
-        h->dbg_m[i] = h->h_ctrl[LGC_M]; h->dbg_n[i] = h->h_ctrl[LGC_N]; h->dbg_nlayers = i + 1;
-      }
-    }
-    if (i == L - 1 || (!do_stop && !do_prune)) continue;
-    const LgLayer& l = h->L[i];
+  if (maxm > 0 && maxn > 0) {
+    B2S_TRY(lgtc_input_proj(h->tc, st, h->x[0], nseg, maxrows, h->ctrl, &h->launches));
+    // with pruning enabled layer i lives in ping-pong buffer i & 1 (the gather after layer i moves the
+    // survivors across); without it everything stays in buffer 0
+    auto buf_of = [&](int i) { return do_prune ? (i & 1) : 0; };
     // upstream: scores > (1 - width_confidence) with a python double; undo the float rounding of the cfg
     const float keep_thr = (float)(1.0 - std::round((double)h->cfg.width_conf * 1e6) / 1e6);
-    if (do_prune && cap <= 32 * LG_MAXBLK) {
+    const int nblk = cdiv(maxrows, 32);
+    for (int i = 0; i < L; ++i) {
+      const int cur = buf_of(i);
+      B2S_TRY(lgtc_layer(h->tc, st, i, h->x[cur], h->cosb[cur], h->sinb[cur], nseg, maxrows, h->ctrl, &h->launches));
+      if (h->debug && h->dbg_layers) {   // debug only: snapshot pair 0's layer output and its live sizes (host sync)
+        B2S_CUDA(cudaMemcpyAsync(h->dbg_layers + (size_t)i * 2 * cap * 256, h->x[cur], (size_t)2 * cap * 256 * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st));
+        B2S_CUDA(cudaMemcpyAsync(h->h_ctrl, h->ctrl, LGC_INTS * sizeof(int), cudaMemcpyDeviceToHost, st));
+        B2S_CUDA(cudaStreamSynchronize(st));
+        if (!h->h_ctrl[LGC_STOP] && h->h_ctrl[LGC_M] > 0 && h->h_ctrl[LGC_N] > 0) {
+          h->dbg_m[i] = h->h_ctrl[LGC_M]; h->dbg_n[i] = h->h_ctrl[LGC_N]; h->dbg_nlayers = i + 1;
+        }
+      }
+      if (i == L - 1 || (!do_stop && !do_prune)) continue;
+      const LgLayer& l = h->L[i];
       // two launches: heads per 32-row block (keep masks, one atomic per CTA), then decision + placement + copy
-      const int nblk = cdiv(std::max(m, n), 32);
       HeadBlkParams hp = {};
-      hp.x = h->x[cur]; hp.base[0] = 0; hp.base[1] = cap;
+      hp.x = h->x[cur]; hp.cap = cap;
       hp.wt = l.wtok; hp.bt = l.btok; hp.wm = l.wmatch; hp.bm = l.bmatch;
-      hp.thr = h->thr[i]; hp.keep_thr = keep_thr; hp.use_tok = do_stop;
-      hp.tok = h->tok; hp.ctrl = h->ctrl; hp.adapt = h->adapt; hp.layer = i;
-      launch_k(k_lg_heads_blk, dim3(nblk, 2), 1024, 0, st, hp);
+      hp.thr = h->thr[i]; hp.keep_thr = keep_thr; hp.use_tok = do_stop; hp.use_match = do_prune;
+      hp.ctrl = h->ctrl; hp.adapt = h->adapt; hp.layer = i;
+      launch_k(k_lg_heads_blk, dim3(nblk, nseg), 1024, 0, st, hp);
       const int nxt = cur ^ 1;
       GatherBlkParams gp = {};
-      gp.adapt = h->adapt; gp.ctrl = h->ctrl; gp.base[0] = 0; gp.base[1] = cap;
-      gp.layer = i; gp.num_points = m + n; gp.do_stop = do_stop ? 1 : 0; gp.pruning_min_kpts = h->cfg.pruning_min_kpts;
+      gp.adapt = h->adapt; gp.ctrl = h->ctrl; gp.cap = cap;
+      gp.layer = i; gp.do_stop = do_stop ? 1 : 0; gp.do_prune = do_prune ? 1 : 0; gp.pruning_min_kpts = h->cfg.pruning_min_kpts;
       gp.nblk = nblk; gp.depth_conf = h->cfg.depth_conf;
       gp.x_in = h->x[cur]; gp.x_out = h->x[nxt]; gp.cos_in = h->cosb[cur]; gp.cos_out = h->cosb[nxt];
       gp.sin_in = h->sinb[cur]; gp.sin_out = h->sinb[nxt]; gp.ind_in = h->ind[cur]; gp.ind_out = h->ind[nxt];
-      gp.prune[0] = pr0; gp.prune[1] = pr1;
-      gp.xb_out = h->tc ? lgtc_xb(h->tc) : nullptr;
-      gp.xb_planes = h->tc ? lgtc_planes(h->tc) : 0; gp.xb_plane = (size_t)2 * cap * 256;
-      launch_k(k_lg_gather_blk, dim3(nblk, 2), 1024, 0, st, gp);
+      gp.prune = h->prune;
+      gp.xb_out = lgtc_xb(h->tc); gp.xb_planes = lgtc_planes(h->tc); gp.xb_plane = plane_rows * 256;
+      launch_k(k_lg_gather_blk, dim3(nblk, nseg), 1024, 0, st, gp);
       h->launches += 2;
       B2S_LAUNCH_CHECK();
-      continue;
     }
-    HeadParams hp = {};
-    hp.x = h->x[cur]; hp.seg = {{0, cap}, {m, n}};
-    hp.wt = l.wtok; hp.bt = l.btok; hp.wm = l.wmatch; hp.bm = l.bmatch;
-    hp.thr = h->thr[i];
-    hp.keep_thr = keep_thr;
-    hp.use_tok = do_stop; hp.use_match = do_prune;
-    hp.tok = h->tok; hp.keep = h->keep; hp.ctrl = h->ctrl; hp.layer = i; hp.ls_pos = nullptr;
-    dim3 hg(cdiv(std::max(m, n), 8), 2);
-    launch_k(k_lg_heads, hg, 256, 0, st, hp);
-    ScanParams sp;
-    sp.keep = h->keep; sp.srcmap = h->srcmap; sp.ctrl = h->ctrl; sp.base[0] = 0; sp.base[1] = cap;
-    sp.layer = i; sp.num_points = m + n; sp.do_stop = do_stop ? 1 : 0; sp.do_prune = do_prune ? 1 : 0;
-    sp.pruning_min_kpts = h->cfg.pruning_min_kpts; sp.depth_conf = h->cfg.depth_conf;
-    launch_k(k_lg_prune_scan, 2, 1024, 0, st, sp);
-    h->launches += 2;
-    B2S_LAUNCH_CHECK();
-    if (do_prune) {
-      const int nxt = cur ^ 1;
-      GatherParams gp;
-      gp.srcmap = h->srcmap; gp.ctrl = h->ctrl; gp.base[0] = 0; gp.base[1] = cap;
-      gp.x_in = h->x[cur]; gp.x_out = h->x[nxt]; gp.cos_in = h->cosb[cur]; gp.cos_out = h->cosb[nxt];
-      gp.sin_in = h->sinb[cur]; gp.sin_out = h->sinb[nxt]; gp.ind_in = h->ind[cur]; gp.ind_out = h->ind[nxt];
-      gp.prune[0] = pr0; gp.prune[1] = pr1;
-      gp.xb_out = h->tc ? lgtc_xb(h->tc) : nullptr;
-      gp.xb_planes = h->tc ? lgtc_planes(h->tc) : 0; gp.xb_plane = (size_t)2 * cap * 256;
-      launch_k(k_lg_gather, dim3(cdiv(std::max(m, n), 8), 2), 256, 0, st, gp);
+    // ---- assignment with the last executed layer's heads (K14/K15); that layer index, its buffer and the
+    //      live sizes are device-side values ----
+    {
+      FinalPrepParams fp = {};
+      fp.x = h->x[0]; fp.x_odd = do_prune ? h->x[1] : nullptr; fp.cap = cap; fp.ctrl = h->ctrl;
+      fp.wm_tab = h->wmatch_tab; fp.bm_tab = h->bmatch_tab; fp.tx = lgtc_tx(h->tc); fp.plane = plane_rows * 256; fp.ls = h->ls;
+      launch_k(k_lg_final_prep, dim3(cdiv(maxrows, 8), nseg), 256, 0, st, fp);
       ++h->launches;
       B2S_LAUNCH_CHECK();
     }
-  }
-  // ---- assignment with the last executed layer's heads (K14/K15); that layer index, its buffer and the
-  //      live sizes are device-side values ----
-  float* md = h->qkv;  // [2*cap, 256] (CUDA-core path)
-  if (!h->tc) {
-    GemmParams g;
-    g.A1 = h->x[0]; g.lda1 = 256; g.K1 = 256; g.A1_alt = do_prune ? h->x[1] : nullptr;
-    g.W = h->L[L - 1].wfinal; g.ldw = 256; g.K = 256; g.N = 256; g.bias = h->L[L - 1].bfinal; g.alpha = 0.25f;
-    g.C = md; g.ldc = 256;
-    g.nseg = 2; g.seg_base[0] = 0; g.seg_base[1] = cap; g.seg_rows[0] = m; g.seg_rows[1] = n;
-    g.lg_ctrl = h->ctrl; g.lg_mode = 2; g.w_tab = h->wfinal_tab; g.b_tab = h->bfinal_tab;
-    B2S_TRY(gemm_simt(g, st, &h->launches, &h->prof));
-  }
-  {
-    HeadParams hp = {};
-    hp.x = h->x[0]; hp.x_alt = do_prune ? h->x[1] : nullptr; hp.seg = {{0, cap}, {m, n}};
-    hp.wm_tab = h->wmatch_tab; hp.bm_tab = h->bmatch_tab; hp.ctrl = h->ctrl; hp.ls_pos = h->ls;
-    dim3 hg(cdiv(std::max(m, n), 8), 2);
-    launch_k(k_lg_heads, hg, 256, 0, st, hp);
-    ++h->launches;
+    B2S_TRY(lgtc_assignment(h->tc, st, np, maxm, maxn, h->ctrl, h->sim, h->simT, &h->launches));
+    AssignParams ap = {};
+    ap.sim = h->sim; ap.simT = h->simT; ap.ld = cap; ap.pair_stride = (size_t)cap * cap; ap.cap = cap; ap.ctrl = h->ctrl;
+    ap.rmax = h->rmax; ap.rlog = h->rlog; ap.cmax = h->cmax; ap.clog = h->clog; ap.ls = h->ls;
+    ap.max0 = h->max0; ap.m0 = h->m0; ap.m1 = h->m1;
+    launch_k(k_lg_lse2, dim3(cdiv(maxrows, 8), 2 * np), 256, 0, st, ap);
+    launch_k(k_lg_argmax2, dim3(cdiv(maxrows, 8), 2 * np), 256, 0, st, ap);
+    h->launches += 2;
     B2S_LAUNCH_CHECK();
   }
-  const int ld = cap;
-  if (h->tc) {
-    B2S_TRY(lgtc_assignment(h->tc, st, h->x[0], do_prune ? h->x[1] : nullptr, cap, m, n, h->ctrl, h->sim, h->simT, &h->launches));
-  } else {
-    GemmParams g;
-    g.A1 = md; g.lda1 = 256; g.K1 = 256; g.W = md + (size_t)cap * 256; g.ldw = 256; g.K = 256;
-    g.M = m; g.N = n; g.C = h->sim; g.ldc = ld;
-    g.lg_ctrl = h->ctrl; g.lg_mode = 3;
-    B2S_TRY(gemm_simt(g, st, &h->launches));
-  }
-  const int* ctrl = h->ctrl;
-  if (h->tc) {
-    // both directions per launch on sim / sim^T (written by the similarity GEMM's epilogue)
-    Lse2Params lp = {h->sim, h->simT, ld, ctrl, h->rmax, h->rlog, h->cmax, h->clog};
-    launch_k(k_lg_lse2, dim3(cdiv(std::max(m, n), 8), 2), 256, 0, st, lp);
-    Argmax2Params ap = {h->sim, h->simT, ld, ctrl, h->rmax, h->rlog, h->cmax, h->clog, h->ls, h->ls + cap, h->max0, h->m0, h->m1};
-    launch_k(k_lg_argmax2, dim3(cdiv(std::max(m, n), 8), 2), 256, 0, st, ap);
-    h->launches -= 2;
-  } else {
-    launch_k(k_lg_row_lse, cdiv(m, 8), 256, 0, st, h->sim, ld, ctrl, h->rmax, h->rlog);
-    launch_k(k_lg_col_lse, cdiv(n, 32), 1024, 0, st, h->sim, ld, ctrl, h->cmax, h->clog);
-    launch_k(k_lg_row_argmax, cdiv(m, 8), 256, 0, st, h->sim, ld, ctrl, h->rmax, h->rlog, h->cmax, h->clog, h->ls, h->ls + cap, h->max0, h->m0);
-    launch_k(k_lg_col_argmax, cdiv(n, 32), 1024, 0, st, h->sim, ld, ctrl, h->rmax, h->rlog, h->cmax, h->clog, h->ls, h->ls + cap, h->m1);
-  }
   FilterParams fp = {};
-  fp.th = h->cfg.filter_thresh; fp.max0 = h->max0; fp.m0 = h->m0; fp.m1 = h->m1;
-  fp.ctrl = h->ctrl; fp.cap = cap; fp.stop_layer = stop_layer;
-  fp.ind0 = h->ind[0]; fp.ind1 = h->ind[0] + cap; fp.ind_alt = do_prune ? h->ind[1] : nullptr;
-  fp.matches = matches; fp.mscores = mscores; fp.n_matches = n_matches;
-  fp.matches0 = matches0; fp.matches1 = matches1; fp.ms0 = ms0; fp.ms1 = ms1;
-  launch_k(k_lg_filter, 1, 1024, 0, st, fp);
-  h->launches += 5;
+  fp.out = out; fp.th = h->cfg.filter_thresh; fp.n_layers = L; fp.do_prune = do_prune ? 1 : 0;
+  fp.ctrl = h->ctrl; fp.cap = cap; fp.max0 = h->max0; fp.m0 = h->m0; fp.m1 = h->m1;
+  fp.ind = h->ind[0]; fp.ind_odd = do_prune ? h->ind[1] : nullptr; fp.prune = h->prune;
+  launch_k(k_lg_filter, np, 1024, 0, st, fp);
+  ++h->launches;
   B2S_LAUNCH_CHECK();
   if (h->debug) {
     B2S_CUDA(cudaMemcpyAsync(h->h_ctrl, h->ctrl, LGC_INTS * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -538,6 +382,24 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
     h->dbg_simm = h->h_ctrl[LGC_M]; h->dbg_simn = h->h_ctrl[LGC_N];
   }
   return 0;
+}
+
+extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, int m, const float* k1,
+                                   const float* d1, int n, const float* size0, const float* size1, void* stream,
+                                   int32_t* matches, float* mscores, int32_t* n_matches, int32_t* stop_layer,
+                                   int32_t* matches0, int32_t* matches1, float* ms0, float* ms1,
+                                   int32_t* prune0, int32_t* prune1) {
+  if (!h || !matches || !mscores || !n_matches || m < 0 || n < 0) { set_error("b2s_lightglue_match: bad argument"); return B2S_EINVAL; }
+  B2S_CUDA(cudaSetDevice(h->device));
+  LgBatchIn in = {};
+  LgBatchOut out = {};
+  LgPairIn& pi = in.pr[0];
+  pi.kp[0] = k0; pi.kp[1] = k1; pi.desc[0] = d0; pi.desc[1] = d1; pi.n[0] = m; pi.n[1] = n;
+  pi.has_size[0] = size0 != nullptr; pi.has_size[1] = size1 != nullptr;
+  if (size0) { pi.size[0][0] = size0[0]; pi.size[0][1] = size0[1]; }
+  if (size1) { pi.size[1][0] = size1[0]; pi.size[1][1] = size1[1]; }
+  out.pr[0] = {matches, mscores, n_matches, stop_layer, matches0, matches1, ms0, ms1, prune0, prune1, m, n};
+  return lg_run(h, (cudaStream_t)stream, in, out, 1);
 }
 
 static int lg_host_staging(b2s_lg* h, int need) {
@@ -598,22 +460,50 @@ extern "C" int b2s_lightglue_match_host(b2s_lg* h, const float* k0, const float*
   return 0;
 }
 
+// Batched matching: n_pairs pairs over packed varlen features, processed LG_MAXP pairs per launch sequence (the pair is a
+// grid dimension of every kernel).  max_batch (0 = LG_MAXP) lowers the number of pairs per sequence, e.g. to keep a
+// sequence's working set inside the 126 MB L2.
+extern "C" int b2s_lightglue_match_batch_ex(b2s_lg* h, const float* kpts, const float* desc, const int32_t* cu, const int32_t* counts,
+                                            int n_frames, const int32_t* pair_i, const int32_t* pair_j, int n_pairs,
+                                            void* stream, int stride, int max_batch, int32_t* matches, float* mscores,
+                                            int32_t* n_matches, int32_t* stop_layers) {
+  if (!h || !cu || !pair_i || !pair_j || n_pairs < 0 || !matches || !mscores || !n_matches) { set_error("b2s_lightglue_match_batch: bad argument"); return B2S_EINVAL; }
+  B2S_CUDA(cudaSetDevice(h->device));
+  const int B = max_batch > 0 ? std::min(max_batch, LG_MAXP) : LG_MAXP;
+  int maxkp = 1;
+  auto rows_of = [&](int f) { return counts ? counts[f] : cu[f + 1] - cu[f]; };   // counts: frames need not be packed back to back
+  for (int p = 0; p < n_pairs; ++p) {
+    const int a = pair_i[p], b = pair_j[p];
+    if (a < 0 || b < 0 || a >= n_frames || b >= n_frames) { set_error("pair %d out of range", p); return B2S_EINVAL; }
+    const int m = rows_of(a), n = rows_of(b);
+    if (m < 0 || n < 0) { set_error("cu is not ascending at pair %d", p); return B2S_EINVAL; }
+    if (std::min(m, n) > stride) { set_error("stride %d too small for pair %d", stride, p); return B2S_ESIZE; }
+    maxkp = std::max(maxkp, std::max(m, n));
+  }
+  B2S_TRY(b2s_lg_reserve(h, maxkp, std::min(B, std::max(n_pairs, 1))));
+  for (int p0 = 0; p0 < n_pairs; p0 += B) {
+    const int np = std::min(B, n_pairs - p0);
+    LgBatchIn in = {};
+    LgBatchOut out = {};
+    for (int q = 0; q < np; ++q) {
+      const int p = p0 + q, a = pair_i[p], b = pair_j[p];
+      LgPairIn& pi = in.pr[q];
+      pi.kp[0] = kpts + (size_t)cu[a] * 2; pi.desc[0] = desc + (size_t)cu[a] * 128; pi.n[0] = rows_of(a);
+      pi.kp[1] = kpts + (size_t)cu[b] * 2; pi.desc[1] = desc + (size_t)cu[b] * 128; pi.n[1] = rows_of(b);
+      out.pr[q] = {matches + (size_t)p * stride * 2, mscores + (size_t)p * stride, n_matches + p, stop_layers ? stop_layers + p : nullptr,
+                   nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pi.n[0], pi.n[1]};
+    }
+    B2S_TRY(lg_run(h, (cudaStream_t)stream, in, out, np));
+  }
+  return 0;
+}
+
 extern "C" int b2s_lightglue_match_batch(b2s_lg* h, const float* kpts, const float* desc, const int32_t* cu,
                                          int n_frames, const int32_t* pair_i, const int32_t* pair_j, int n_pairs,
                                          void* stream, int stride, int32_t* matches, float* mscores,
                                          int32_t* n_matches) {
-  if (!h || !cu || !pair_i || !pair_j || n_pairs < 0) { set_error("b2s_lightglue_match_batch: bad argument"); return B2S_EINVAL; }
-  for (int p = 0; p < n_pairs; ++p) {
-    const int a = pair_i[p], b = pair_j[p];
-    if (a < 0 || b < 0 || a >= n_frames || b >= n_frames) { set_error("pair %d out of range", p); return B2S_EINVAL; }
-    const int m = cu[a + 1] - cu[a], n = cu[b + 1] - cu[b];
-    if (std::min(m, n) > stride) { set_error("stride %d too small for pair %d", stride, p); return B2S_ESIZE; }
-    B2S_TRY(b2s_lightglue_match(h, kpts + (size_t)cu[a] * 2, desc + (size_t)cu[a] * 128, m, kpts + (size_t)cu[b] * 2,
-                                desc + (size_t)cu[b] * 128, n, nullptr, nullptr, stream,
-                                matches + (size_t)p * stride * 2, mscores + (size_t)p * stride, n_matches + p, nullptr,
-                                nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
-  }
-  return 0;
+  return b2s_lightglue_match_batch_ex(h, kpts, desc, cu, nullptr, n_frames, pair_i, pair_j, n_pairs, stream, stride, 0, matches, mscores,
+                                      n_matches, nullptr);
 }
 
 extern "C" int b2s_lg_debug_get(b2s_lg* h, const char* name, float* out, size_t cap_out, size_t* nout) {
@@ -624,7 +514,7 @@ extern "C" int b2s_lg_debug_get(b2s_lg* h, const char* name, float* out, size_t 
   const float* src = nullptr; size_t cnt = 0;
   std::vector<float> tmp;
   if (s.rfind("layer", 0) == 0 && h->dbg_layers) {
-    // "layer<i>_<side>" -> [rows,256]
+    // "layer<i>_<side>" -> [rows,256]  (pair 0)
     int li = 0, side = 0;
     if (sscanf(name, "layer%d_%d", &li, &side) != 2 || li < 0 || li >= h->dbg_nlayers || side < 0 || side > 1) {
       set_error("debug tensor %s not available", name); return B2S_EINVAL;
@@ -632,7 +522,7 @@ extern "C" int b2s_lg_debug_get(b2s_lg* h, const char* name, float* out, size_t 
     src = h->dbg_layers + ((size_t)li * 2 * h->cap + (side ? h->cap : 0)) * 256;
     cnt = (size_t)(side ? h->dbg_n[li] : h->dbg_m[li]) * 256;
   } else if (s == "sim") {
-    // compacted [m,n]
+    // compacted [m,n]  (pair 0)
     tmp.resize((size_t)h->dbg_simm * h->dbg_simn);
     if (!tmp.empty())
       B2S_CUDA(cudaMemcpy2D(tmp.data(), (size_t)h->dbg_simn * sizeof(float), h->sim, (size_t)h->cap * sizeof(float),

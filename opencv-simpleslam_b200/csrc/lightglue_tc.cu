@@ -73,56 +73,21 @@ int make_tmap_bf16_4d(CUtensorMap* out, const void* gptr, const uint64_t dims[4]
   return 0;
 }
 
-// ---- glue kernels -------------------------------------------------------------------------
-// store 8 consecutive values of one row as NP bf16 planes (plane p at y + p * plane)
-template <int NP>
-__device__ __forceinline__ void store_planes8(__nv_bfloat16* y, size_t plane, const float (&f)[8]) {
-  uint32_t w[NP][4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint32_t pw[NP];
-    tc::pack_planes2<NP>(f[2 * j], f[2 * j + 1], pw);
-#pragma unroll
-    for (int pl = 0; pl < NP; ++pl) w[pl][j] = pw[pl];
-  }
-#pragma unroll
-  for (int pl = 0; pl < NP; ++pl) *reinterpret_cast<uint4*>(y + pl * plane) = make_uint4(w[pl][0], w[pl][1], w[pl][2], w[pl][3]);
-}
-
-template <int NP>
-__global__ void __launch_bounds__(256) k_f32_to_bf16_rows(const float* __restrict__ x, const float* __restrict__ x_odd,
-                                                          __nv_bfloat16* __restrict__ y, int ld, size_t plane,
-                                                          int base0, int rows0, int base1, int rows1, const int* __restrict__ ctrl) {
-  pdl_wait();
-  if (ctrl) { rows0 = ctrl[2]; rows1 = ctrl[3]; }
-  if (x_odd && (ctrl[6] & 1)) x = x_odd;     // the last executed layer lives in the odd ping-pong buffer
-  // one warp per row of 256
-  const int s = blockIdx.y;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= (s ? rows1 : rows0)) return;
-  const int lane = threadIdx.x & 31;
-  const size_t off = (size_t)((s ? base1 : base0) + row) * ld + lane * 8;
-  const float4 a = *reinterpret_cast<const float4*>(x + off), b = *reinterpret_cast<const float4*>(x + off + 4);
-  const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  store_planes8<NP>(y + off, plane, f);
-}
-
-// LayerNorm(512) + GELU(erf): fp32 in -> NP bf16 planes out.  One warp per row.
+// ---- glue kernel --------------------------------------------------------------------------
+// LayerNorm(512) + GELU(erf): fp32 in -> NP bf16 planes out.  One warp per row, grid = (ceil(rows/8), segments); the live
+// rows of segment g come from the pair's device state ctrl[(g >> 1) * 32 + 2 + (g & 1)].
 template <int NP>
 __global__ void __launch_bounds__(256) k_ln_gelu_512_bf16(const float* __restrict__ h, __nv_bfloat16* __restrict__ y, size_t plane,
-                                                          int base0, int rows0, int base1, int rows1,
-                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          int cap, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const int* __restrict__ ctrl) {
   pdl_wait();
-  if (ctrl) {
-    if (ctrl[1] || ctrl[2] <= 0 || ctrl[3] <= 0) return;
-    rows0 = ctrl[2]; rows1 = ctrl[3];
-  }
-  const int s = blockIdx.y;
+  const int g = blockIdx.y;
+  const int* c = ctrl + (g >> 1) * TC_CTRL_INTS;
+  if (!(!c[1] && c[2] > 0 && c[3] > 0)) return;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= (s ? rows1 : rows0)) return;
+  if (row >= c[2 + (g & 1)]) return;
   const int lane = threadIdx.x & 31;
-  const size_t roff = (size_t)((s ? base1 : base0) + row) * 512;
+  const size_t roff = (size_t)(g * cap + row) * 512;
   float4 v[4];   // columns lane*8 + t*256 + {0..3} and +4: two chunks of 8 consecutive values per lane
   float sum = 0.f;
 #pragma unroll
@@ -134,22 +99,22 @@ __global__ void __launch_bounds__(256) k_ln_gelu_512_bf16(const float* __restric
   float sq = 0.f;
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    const float a = v[t].x - mean, b = v[t].y - mean, c = v[t].z - mean, d = v[t].w - mean;
-    sq += (a * a + b * b) + (c * c + d * d);
+    const float a = v[t].x - mean, b = v[t].y - mean, c2 = v[t].z - mean, d = v[t].w - mean;
+    sq += (a * a + b * b) + (c2 * c2 + d * d);
   }
   const float rstd = rsqrtf(warp_sum(sq) * (1.f / 512.f) + 1e-5f);
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
-    const int c = u * 256 + lane * 8;
+    const int col = u * 256 + lane * 8;
     float f[8];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const float4 g = *reinterpret_cast<const float4*>(gamma + c + e * 4), b = *reinterpret_cast<const float4*>(beta + c + e * 4);
+      const float4 gm = *reinterpret_cast<const float4*>(gamma + col + e * 4), b = *reinterpret_cast<const float4*>(beta + col + e * 4);
       const float4 x = v[2 * u + e];
-      f[4 * e] = gelu_erf_f((x.x - mean) * rstd * g.x + b.x); f[4 * e + 1] = gelu_erf_f((x.y - mean) * rstd * g.y + b.y);
-      f[4 * e + 2] = gelu_erf_f((x.z - mean) * rstd * g.z + b.z); f[4 * e + 3] = gelu_erf_f((x.w - mean) * rstd * g.w + b.w);
+      f[4 * e] = gelu_erf_f((x.x - mean) * rstd * gm.x + b.x); f[4 * e + 1] = gelu_erf_f((x.y - mean) * rstd * gm.y + b.y);
+      f[4 * e + 2] = gelu_erf_f((x.z - mean) * rstd * gm.z + b.z); f[4 * e + 3] = gelu_erf_f((x.w - mean) * rstd * gm.w + b.w);
     }
-    store_planes8<NP>(y + roff + c, plane, f);
+    store_planes8<NP>(y + roff + col, plane, f);
   }
 }
 
@@ -166,17 +131,19 @@ struct TcLayer {
 struct LgTensorCore {
   DeviceArena warena, wsarena;
   std::vector<TcLayer> L;
-  int np = 1;                      // operand planes: 1 = bf16, 3 = fp32 carried as bf16x3
-  int cap = 0;
-  // activation planes: [np][2*cap][C] bf16
+  int np = 1;                      // operand planes of the transformer layers: 1 = bf16, 3 = fp32 carried as bf16x3
+  int cap = 0, pcap = 0;           // rows per segment, pairs the workspace holds (segments = 2 * pcap)
+  // activation planes: [np][segments * cap][C] bf16
   __nv_bfloat16 *xb = nullptr, *qkvb = nullptr, *ctxb = nullptr, *h1b = nullptr;
   float* h1f = nullptr;
   CUtensorMap m_xb, m_ctxb, m_h1b, m_qkv768, m_qkv512;     // box {64, 128}: GEMM A operands, attention Q
   CUtensorMap m_kv768, m_kv512;                            // box {64, 64}: attention K / V tiles (np == 3)
   CUtensorMap m_xb32, m_ctxb32, m_h1b32;                   // box {64, 32}: A operands of the cluster-multicast GEMMs
-  // assignment head (always fp32-faithful, three planes): planes of the final x, of the projected descriptors md
-  __nv_bfloat16 *tx = nullptr, *md = nullptr;
-  CUtensorMap m_tx, m_md;
+  // always fp32-faithful (three planes) whatever the layer precision: the input projection (descriptor planes din) and the
+  // assignment head (planes tx of the final state, md of the projected descriptors) - scores decide the match set
+  __nv_bfloat16 *din = nullptr, *tx = nullptr, *md = nullptr;
+  CUtensorMap m_din, m_tx, m_md;
+  TcLinear win;                    // input_proj [256, 3*128]
   TcLinear wfinal;                 // all layers' final_proj stacked: [L*256, 3*256]
   float* bfinal = nullptr;         // [L*256]
   const int* ctrl = nullptr;       // LightGlue device state (sizes / early exit), set per match
@@ -184,13 +151,14 @@ struct LgTensorCore {
   unsigned long long* stats = nullptr;   // executed attention work counters (owned by the matcher handle)
 };
 
-static int make_linear(LgTensorCore* tc, const float* w_dev, const float* bias, int N, int K, TcLinear* out) {
+static int make_linear(LgTensorCore* tc, const float* w_dev, const float* bias, int N, int K, TcLinear* out, int np = 0) {
+  if (np == 0) np = tc->np;
   out->N = N; out->K = K; out->bias = bias; out->BN = N <= 256 ? 64 : (N % 128 == 0 && N != 768 ? 128 : 96);   // N = 768 (QKV): 8 x 32 tiles of 128 x 96 waste less of the second wave than 6 x 32 of 128 x 128
   const size_t n = (size_t)N * K;
-  B2S_TRY(tc->warena.alloc(&out->w, n * tc->np));
-  k_weight_planes<<<(unsigned)((n + 255) / 256), 256>>>(w_dev, out->w, N, K, tc->np);
+  B2S_TRY(tc->warena.alloc(&out->w, n * np));
+  k_weight_planes<<<(unsigned)((n + 255) / 256), 256>>>(w_dev, out->w, N, K, np);
   B2S_LAUNCH_CHECK();
-  return make_tmap_bf16_2d(&out->map, out->w, (uint64_t)tc->np * K, N, (uint64_t)tc->np * K * 2, 64, out->BN);
+  return make_tmap_bf16_2d(&out->map, out->w, (uint64_t)np * K, N, (uint64_t)np * K * 2, 64, out->BN);
 }
 
 // FFN first layer with the attention output projection folded in (exact in real arithmetic):
@@ -271,11 +239,22 @@ int lgtc_set_layer(LgTensorCore* tc, int li, const LgTcLayerSrc& s) {
   return 0;
 }
 
-int lgtc_alloc_ws(LgTensorCore* tc, int cap) {
+int lgtc_set_input(LgTensorCore* tc, const float* w, const float* b) {
+  B2S_TRY(make_linear(tc, w, b, 256, 128, &tc->win, 3));
+  B2S_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+size_t lgtc_ws_bytes(int np, int cap, int pcap) {
+  const size_t R = (size_t)2 * pcap * cap, P = (size_t)np;
+  return 2 * (P * R * (256 + 768 + 256 + 512) + 3 * R * (128 + 256 + 256)) + 4 * R * 512;
+}
+
+int lgtc_alloc_ws(LgTensorCore* tc, int cap, int pcap) {
   tc->wsarena.release();
-  tc->cap = 0;
-  if (cap % 128) { set_error("lgtc_alloc_ws: cap %d must be a multiple of 128", cap); return B2S_EINVAL; }
-  const size_t R = (size_t)2 * cap, P = (size_t)tc->np;
+  tc->cap = tc->pcap = 0;
+  if (cap % 128 || pcap < 1) { set_error("lgtc_alloc_ws: cap %d must be a multiple of 128, pairs %d >= 1", cap, pcap); return B2S_EINVAL; }
+  const size_t R = (size_t)2 * pcap * cap, P = (size_t)tc->np;
   B2S_TRY(tc->wsarena.alloc(&tc->xb, P * R * 256)); B2S_TRY(tc->wsarena.alloc(&tc->qkvb, P * R * 768));
   B2S_TRY(tc->wsarena.alloc(&tc->ctxb, P * R * 256));
   B2S_TRY(tc->wsarena.alloc(&tc->h1b, P * R * 512)); B2S_TRY(tc->wsarena.alloc(&tc->h1f, R * 512));
@@ -293,25 +272,28 @@ int lgtc_alloc_ws(LgTensorCore* tc, int cap) {
   B2S_TRY(make_tmap_bf16_2d(&tc->m_qkv512, tc->qkvb, 512, P * R, 1024, 64, 128));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_kv768, tc->qkvb, 768, P * R, 1536, 64, 64));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_kv512, tc->qkvb, 512, P * R, 1024, 64, 64));
+  B2S_TRY(tc->wsarena.alloc(&tc->din, 3 * R * 128));
   B2S_TRY(tc->wsarena.alloc(&tc->tx, 3 * R * 256)); B2S_TRY(tc->wsarena.alloc(&tc->md, 3 * R * 256));
+  B2S_CUDA(cudaMemset(tc->din, 0, 3 * R * 128 * 2));
   B2S_CUDA(cudaMemset(tc->tx, 0, 3 * R * 256 * 2)); B2S_CUDA(cudaMemset(tc->md, 0, 3 * R * 256 * 2));
+  B2S_TRY(make_tmap_bf16_2d(&tc->m_din, tc->din, 128, 3 * R, 256, 64, 128));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_tx, tc->tx, 256, 3 * R, 512, 64, 128));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_md, tc->md, 256, 3 * R, 512, 64, 128));
-  tc->cap = cap;
+  tc->cap = cap; tc->pcap = pcap;
   return 0;
 }
 
 void lgtc_destroy(LgTensorCore* tc) { delete tc; }
 void lgtc_set_prof(LgTensorCore* tc, KernelProf* prof, unsigned long long* stats) { tc->prof = prof; tc->stats = stats; }
 
+// One GEMM over all segments' live rows.  nseg segments, rows of every segment bounded by maxrows (grid size).
 static int tc_gemm(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& a1, const CUtensorMap& a2, int K1, const TcLinear& w,
-                   TcGemmParams p, int m, int n, long long* launches) {
+                   TcGemmParams p, int nseg, int maxrows, long long* launches) {
   p.K = w.K; p.K1 = K1; p.N = w.N; p.bias = w.bias; p.ctrl = tc->ctrl;
-  p.seg_base[0] = 0; p.seg_base[1] = tc->cap; p.seg_rows[0] = m; p.seg_rows[1] = n;
-  p.tiles0 = cdiv(m, 128);
-  p.plane_rows = 2 * tc->cap;
-  p.out_plane = (size_t)2 * tc->cap * p.ld_bf16;
-  const int tiles = p.tiles0 + cdiv(n, 128);
+  p.seg_stride = tc->cap; p.tiles_per_seg = cdiv(maxrows, 128); p.seg_rows = 0;
+  p.plane_rows = 2 * tc->pcap * tc->cap;
+  p.out_plane = (size_t)p.plane_rows * p.ld_bf16;
+  const int tiles = nseg * p.tiles_per_seg;
   if (tiles <= 0) return 0;
   dim3 grid(w.N / w.BN, tiles);
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
@@ -349,25 +331,24 @@ static int tc_gemm(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& a1, con
   return 0;
 }
 
-// one attention launch over the q/k/v planes in qkvb viewed with row length ld (768 self, 512 cross)
-static int tc_attention(LgTensorCore* tc, cudaStream_t st, int ld, const AttnTcProb (&prob)[2], int qcol, int kcol, int vcol, int cross,
+// one attention launch over the q/k/v planes in qkvb viewed with row length ld (768 self, 512 cross); problem = segment
+static int tc_attention(LgTensorCore* tc, cudaStream_t st, int ld, int nseg, int maxq, int qcol, int kcol, int vcol, int cross,
                         long long* launches) {
-  const int maxq = std::max(prob[0].nq, prob[1].nq);
-  if (maxq <= 0) return 0;
+  if (maxq <= 0 || nseg <= 0) return 0;
   const float scale_log2e = 0.125f * 1.4426950408889634f;
-  dim3 grid(cdiv(maxq, ATC_BQ), 4, 2);
+  dim3 grid(cdiv(maxq, ATC_BQ), 4, nseg);
   if (tc->prof) tc->prof->mark(PROF_ATTN, st);
   if (tc->np == 1) {
     AttnTcParams ap = {};
-    ap.prob[0] = prob[0]; ap.prob[1] = prob[1]; ap.qcol = qcol; ap.kcol = kcol; ap.vcol = vcol; ap.cross = cross;
+    ap.cap = tc->cap; ap.qcol = qcol; ap.kcol = kcol; ap.vcol = vcol; ap.cross = cross;
     ap.scale_log2e = scale_log2e; ap.out = tc->ctxb; ap.ldo = 256; ap.ctrl = tc->ctrl;
     ap.stats = (tc->prof && tc->prof->on) ? tc->stats : nullptr;
     launch_k(k_attn_tc, grid, ATC_THREADS, ATC_SMEM, st, ld == 768 ? tc->m_qkv768 : tc->m_qkv512, ap);
   } else {
     Attn3Params ap = {};
-    ap.prob[0] = prob[0]; ap.prob[1] = prob[1]; ap.qcol = qcol; ap.kcol = kcol; ap.vcol = vcol; ap.cross = cross;
-    ap.plane_rows = 2 * tc->cap;
-    ap.scale_log2e = scale_log2e; ap.out = tc->ctxb; ap.ldo = 256; ap.out_plane = (size_t)2 * tc->cap * 256; ap.ctrl = tc->ctrl;
+    ap.cap = tc->cap; ap.qcol = qcol; ap.kcol = kcol; ap.vcol = vcol; ap.cross = cross;
+    ap.plane_rows = 2 * tc->pcap * tc->cap;
+    ap.scale_log2e = scale_log2e; ap.out = tc->ctxb; ap.ldo = 256; ap.out_plane = (size_t)ap.plane_rows * 256; ap.ctrl = tc->ctrl;
     ap.stats = (tc->prof && tc->prof->on) ? tc->stats : nullptr;
     launch_k(k_attn_tc3, grid, A3_THREADS, A3_SMEM, st, ld == 768 ? tc->m_qkv768 : tc->m_qkv512,
              ld == 768 ? tc->m_kv768 : tc->m_kv512, ap);
@@ -379,19 +360,19 @@ static int tc_attention(LgTensorCore* tc, cudaStream_t st, int ld, const AttnTcP
 }
 
 static int tc_ffn(LgTensorCore* tc, cudaStream_t st, float* x, const TcLinear& w1, const float* lng, const float* lnb, const TcLinear& w2,
-                  int m, int n, long long* launches) {
+                  int nseg, int maxrows, long long* launches) {
   TcGemmParams p = {};
   p.epi = TC_EPI_F32; p.out_f32 = tc->h1f; p.ld_f32 = 512;
-  B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_ctxb, 256, w1, p, m, n, launches));          // [x | ctx] W1'^T + b1' (out_proj folded)
-  dim3 g(cdiv(std::max(m, n), 8), 2);
-  const size_t hplane = (size_t)2 * tc->cap * 512;
-  if (tc->np == 1) launch_k(k_ln_gelu_512_bf16<1>, g, 256, 0, st, tc->h1f, tc->h1b, hplane, 0, m, tc->cap, n, lng, lnb, tc->ctrl);
-  else launch_k(k_ln_gelu_512_bf16<3>, g, 256, 0, st, tc->h1f, tc->h1b, hplane, 0, m, tc->cap, n, lng, lnb, tc->ctrl);
+  B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_ctxb, 256, w1, p, nseg, maxrows, launches));          // [x | ctx] W1'^T + b1' (out_proj folded)
+  dim3 g(cdiv(maxrows, 8), nseg);
+  const size_t hplane = (size_t)2 * tc->pcap * tc->cap * 512;
+  if (tc->np == 1) launch_k(k_ln_gelu_512_bf16<1>, g, 256, 0, st, tc->h1f, tc->h1b, hplane, tc->cap, lng, lnb, tc->ctrl);
+  else launch_k(k_ln_gelu_512_bf16<3>, g, 256, 0, st, tc->h1f, tc->h1b, hplane, tc->cap, lng, lnb, tc->ctrl);
   if (launches) ++*launches;
   B2S_LAUNCH_CHECK();
   p = TcGemmParams();
   p.epi = TC_EPI_RESID_F32_BF16; p.out_f32 = x; p.ld_f32 = 256; p.out_bf16 = tc->xb; p.ld_bf16 = 256;
-  return tc_gemm(tc, st, tc->m_h1b, tc->m_h1b, 512, w2, p, m, n, launches);              // x += h W2^T + b2 ; xb = planes(x)
+  return tc_gemm(tc, st, tc->m_h1b, tc->m_h1b, 512, w2, p, nseg, maxrows, launches);              // x += h W2^T + b2 ; xb = planes(x)
 }
 
 // all layers' assignment projections (fp32 device pointers, [256,256] + [256] each) as one stacked bf16x3 weight
@@ -414,71 +395,74 @@ int lgtc_set_final(LgTensorCore* tc, const std::vector<const float*>& w, const s
   return make_tmap_bf16_2d(&o.map, o.w, 3 * 256, o.N, 3 * 256 * 2, 64, 64);
 }
 
+// Input projection on the tensor cores, always fp32-faithful: x = din W_in^T + b (din = descriptor planes written by
+// k_lg_posenc), fp32 residual stream + its operand planes (np of them) straight from the epilogue.
+int lgtc_input_proj(LgTensorCore* tc, cudaStream_t st, float* x, int nseg, int maxrows, const int* ctrl, long long* launches) {
+  tc->ctrl = ctrl;
+  TcGemmParams p = {};
+  p.K = 128; p.K1 = 128; p.N = 256; p.bias = tc->win.bias; p.ctrl = ctrl; p.ctrl_mode = 1;
+  p.seg_stride = tc->cap; p.tiles_per_seg = cdiv(maxrows, 128);
+  p.plane_rows = 2 * tc->pcap * tc->cap;
+  p.epi = TC_EPI_F32_BF16; p.out_f32 = x; p.ld_f32 = 256; p.out_bf16 = tc->xb; p.ld_bf16 = 256;
+  p.out_plane = (size_t)p.plane_rows * 256; p.out_planes = tc->np;
+  if (tc->prof) tc->prof->mark(PROF_GEMM, st);
+  launch_k(k_gemm_tc<64, 3>, dim3(4, nseg * p.tiles_per_seg), TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, tc->m_din, tc->m_din, tc->win.map, p);
+  if (tc->prof) tc->prof->mark(PROF_GEMM, st);
+  if (launches) ++*launches;
+  B2S_LAUNCH_CHECK();
+  return 0;
+}
+
 // Assignment head on the tensor cores (fp32 carried as bf16x3 whatever the layer precision):
-//   md = final_proj_last(x) / 256^(1/4) for both images, then sim = md0 md1^T  ([cap, cap] fp32, ld = cap).
-// x0 / x1: the two ping-pong residual buffers (x1 null when pruning is off); the last executed layer,
-// its buffer and the live sizes are read from ctrl on the device.
-int lgtc_assignment(LgTensorCore* tc, cudaStream_t st, const float* x0, const float* x1, int cap, int m, int n, const int* ctrl,
-                    float* sim, float* simT, long long* launches) {
-  if (cap != tc->cap) { set_error("lgtc_assignment: workspace capacity mismatch"); return B2S_EINVAL; }
-  const size_t plane = (size_t)2 * cap * 256;
-  dim3 g(cdiv(std::max(m, n), 8), 2);
-  launch_k(k_f32_to_bf16_rows<3>, g, 256, 0, st, x0, x1, tc->tx, 256, plane, 0, m, cap, n, ctrl);
+//   md = final_proj_last(x) / 256^(1/4) for both images (x planes tx written by k_lg_final_prep), then per pair
+//   sim = md0 md1^T  ([cap, cap] fp32, ld = cap) and its transpose.  The last executed layer and the live sizes are
+//   read from ctrl on the device.
+int lgtc_assignment(LgTensorCore* tc, cudaStream_t st, int npairs, int maxm, int maxn, const int* ctrl, float* sim, float* simT,
+                    long long* launches) {
+  const int cap = tc->cap;
+  const int plane_rows = 2 * tc->pcap * cap;
+  const size_t plane = (size_t)plane_rows * 256;
   TcGemmParams p = {};
   p.K = 256; p.K1 = 256; p.N = 256; p.bias = tc->bfinal; p.ctrl = ctrl; p.ctrl_mode = 2; p.w_layer_rows = 256; p.alpha = 0.25f;
-  p.seg_base[0] = 0; p.seg_base[1] = cap; p.seg_rows[0] = m; p.seg_rows[1] = n; p.tiles0 = cdiv(m, 128);
-  p.plane_rows = 2 * cap; p.epi = TC_EPI_BF16; p.out_bf16 = tc->md; p.ld_bf16 = 256; p.out_plane = plane;
+  p.seg_stride = cap; p.tiles_per_seg = cdiv(std::max(maxm, maxn), 128);
+  p.plane_rows = plane_rows; p.epi = TC_EPI_BF16; p.out_bf16 = tc->md; p.ld_bf16 = 256; p.out_plane = plane;
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
-  launch_k(k_gemm_tc<64, 3>, dim3(4, p.tiles0 + cdiv(n, 128)), TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, tc->m_tx, tc->m_tx, tc->wfinal.map, p);
+  launch_k(k_gemm_tc<64, 3>, dim3(4, 2 * npairs * p.tiles_per_seg), TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, tc->m_tx, tc->m_tx, tc->wfinal.map, p);
   p = TcGemmParams();
-  p.K = 256; p.K1 = 256; p.N = n; p.bias = nullptr; p.ctrl = ctrl; p.ctrl_mode = 3;
-  p.w_plane_rows = 2 * cap; p.w_row0 = cap;
-  p.seg_base[0] = 0; p.seg_base[1] = 0; p.seg_rows[0] = m; p.seg_rows[1] = 0; p.tiles0 = cdiv(m, 128);
-  p.plane_rows = 2 * cap; p.epi = TC_EPI_F32; p.out_f32 = sim; p.ld_f32 = cap; p.out_f32_t = simT; p.ld_f32_t = cap;
-  launch_k(k_gemm_tc<128, 3>, dim3(cdiv(n, 128), p.tiles0), TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, tc->m_md, tc->m_md, tc->m_md, p);
+  p.K = 256; p.K1 = 256; p.N = maxn; p.bias = nullptr; p.ctrl = ctrl; p.ctrl_mode = 3;
+  p.w_plane_rows = plane_rows; p.seg_stride = cap; p.tiles_per_seg = cdiv(maxm, 128);
+  p.plane_rows = plane_rows; p.epi = TC_EPI_F32; p.out_f32 = sim; p.ld_f32 = cap; p.out_f32_t = simT; p.ld_f32_t = cap;
+  p.out_pair_stride = (size_t)cap * cap;
+  launch_k(k_gemm_tc<128, 3>, dim3(cdiv(maxn, 128), npairs * p.tiles_per_seg), TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, tc->m_md, tc->m_md, tc->m_md, p);
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
-  if (launches) *launches += 3;
+  if (launches) *launches += 2;
   B2S_LAUNCH_CHECK();
   return 0;
 }
 
 __nv_bfloat16* lgtc_xb(LgTensorCore* tc) { return tc->xb; }
+__nv_bfloat16* lgtc_din(LgTensorCore* tc) { return tc->din; }
+__nv_bfloat16* lgtc_tx(LgTensorCore* tc) { return tc->tx; }
 int lgtc_planes(LgTensorCore* tc) { return tc->np; }
 
-// One transformer layer.  m, n are upper bounds of the live point counts (they size the grids); the
-// live counts and the early-exit flag are read from `ctrl` on the device.  `x` is the fp32 residual
-// stream of this layer; its bf16 plane copy xb is maintained by the FFN epilogues / the pruning gather
-// (derive_xb: re-derive it from x first - layer 0, right after the input projection).
-int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int li, float* x, const float* cosb, const float* sinb, int cap, int m, int n,
-               const int* ctrl, bool derive_xb, long long* launches) {
-  if (cap != tc->cap) { set_error("lgtc_layer: workspace capacity mismatch"); return B2S_EINVAL; }
+// One transformer layer over nseg segments (2 per pair).  maxrows bounds the live point counts (it sizes the grids); the
+// live counts and the early-exit flags are read from `ctrl` on the device.  `x` is the fp32 residual stream of this layer;
+// its bf16 plane copy xb is maintained by the producing epilogues (input projection, FFN) / the pruning gather.
+int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int li, float* x, const float* cosb, const float* sinb, int nseg, int maxrows,
+               const int* ctrl, long long* launches) {
   const TcLayer& l = tc->L[li];
   tc->ctrl = ctrl;
-  if (derive_xb) {
-    dim3 g(cdiv(std::max(m, n), 8), 2);
-    const size_t xplane = (size_t)2 * cap * 256;
-    if (tc->np == 1) launch_k(k_f32_to_bf16_rows<1>, g, 256, 0, st, x, (const float*)nullptr, tc->xb, 256, xplane, 0, m, cap, n, ctrl);
-    else launch_k(k_f32_to_bf16_rows<3>, g, 256, 0, st, x, (const float*)nullptr, tc->xb, 256, xplane, 0, m, cap, n, ctrl);
-    if (launches) ++*launches;
-    B2S_LAUNCH_CHECK();
-  }
   TcGemmParams p = {};
   // ---- self block ----
   p.epi = TC_EPI_ROTARY_BF16; p.out_bf16 = tc->qkvb; p.ld_bf16 = 768; p.rot_cos = cosb; p.rot_sin = sinb; p.rot_cols = 512;
-  B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_xb, 256, l.qkv, p, m, n, launches));
-  {
-    const AttnTcProb prob[2] = {{0, 0, m, m}, {cap, cap, n, n}};
-    B2S_TRY(tc_attention(tc, st, 768, prob, 0, 256, 512, 0, launches));
-  }
-  B2S_TRY(tc_ffn(tc, st, x, l.w1, l.lng, l.lnb, l.w2, m, n, launches));
+  B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_xb, 256, l.qkv, p, nseg, maxrows, launches));
+  B2S_TRY(tc_attention(tc, st, 768, nseg, maxrows, 0, 256, 512, 0, launches));
+  B2S_TRY(tc_ffn(tc, st, x, l.w1, l.lng, l.lnb, l.w2, nseg, maxrows, launches));
   // ---- cross block ----
   p = TcGemmParams(); p.epi = TC_EPI_BF16; p.out_bf16 = tc->qkvb; p.ld_bf16 = 512;
-  B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_xb, 256, l.cqkv, p, m, n, launches));
-  {
-    const AttnTcProb prob[2] = {{0, cap, m, n}, {cap, 0, n, m}};
-    B2S_TRY(tc_attention(tc, st, 512, prob, 0, 0, 256, 1, launches));
-  }
-  return tc_ffn(tc, st, x, l.cw1, l.clng, l.clnb, l.cw2, m, n, launches);
+  B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_xb, 256, l.cqkv, p, nseg, maxrows, launches));
+  B2S_TRY(tc_attention(tc, st, 512, nseg, maxrows, 0, 0, 256, 1, launches));
+  return tc_ffn(tc, st, x, l.cw1, l.clng, l.clnb, l.cw2, nseg, maxrows, launches);
 }
 
 }  // namespace b2s
@@ -524,8 +508,8 @@ static int test_gemm(const float* A, const float* W, const float* bias, int M, i
   tc_kernel_attrs();
   TcGemmParams p = {};
   p.K = K; p.K1 = K; p.N = N; p.bias = dB; p.epi = TC_EPI_F32; p.out_f32 = dC; p.ld_f32 = N; p.plane_rows = Mp;
-  p.seg_base[0] = 0; p.seg_rows[0] = M; p.seg_base[1] = 0; p.seg_rows[1] = 0; p.tiles0 = cdiv(M, 128);
-  dim3 grid(N / BN, p.tiles0);
+  p.seg_stride = 0; p.seg_rows = M; p.tiles_per_seg = cdiv(M, 128);
+  dim3 grid(N / BN, p.tiles_per_seg);
   if (np == 1) {
     if (BN == 64) k_gemm_tc<64, 1><<<grid, TcGemmCfg<64, 1>::THREADS, TcGemmCfg<64, 1>::SMEM>>>(ma, ma, mw, p);
     else k_gemm_tc<128, 1><<<grid, TcGemmCfg<128, 1>::THREADS, TcGemmCfg<128, 1>::SMEM>>>(ma, ma, mw, p);
@@ -574,7 +558,7 @@ extern "C" int b2s_bench_gemm_tc3(int M, int N, int K, int cl, int iters, float*
   tc_kernel_attrs();
   TcGemmParams p = {};
   p.K = K; p.K1 = K; p.N = N; p.bias = dB; p.epi = TC_EPI_BF16; p.out_bf16 = dO; p.ld_bf16 = N; p.out_plane = (size_t)Mp * N; p.plane_rows = Mp;
-  p.seg_base[0] = 0; p.seg_rows[0] = M; p.seg_base[1] = 0; p.seg_rows[1] = 0; p.tiles0 = Mp / 128;
+  p.seg_stride = 0; p.seg_rows = M; p.tiles_per_seg = Mp / 128;
   cudaStream_t st;
   B2S_CUDA(cudaStreamCreate(&st));
   auto launch = [&](unsigned long long* ts) {

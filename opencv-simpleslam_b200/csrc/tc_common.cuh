@@ -202,6 +202,24 @@ __device__ __forceinline__ void pack_planes2(float a, float b, uint32_t (&w)[NP]
     w[2] = pack_bf16x2(a, b);
   }
 }
+}  // namespace tc
+// store 8 consecutive values of one row as NP bf16 planes (plane p at y + p * plane)
+template <int NP>
+__device__ __forceinline__ void store_planes8(__nv_bfloat16* y, size_t plane, const float (&f)[8]) {
+  uint32_t w[NP][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t pw[NP];
+    tc::pack_planes2<NP>(f[2 * j], f[2 * j + 1], pw);
+#pragma unroll
+    for (int pl = 0; pl < NP; ++pl) w[pl][j] = pw[pl];
+  }
+#pragma unroll
+  for (int pl = 0; pl < NP; ++pl) *reinterpret_cast<uint4*>(y + pl * plane) = make_uint4(w[pl][0], w[pl][1], w[pl][2], w[pl][3]);
+}
+
+namespace tc {
+
 // operand-plane pairs (a_i, b_j) of the split product, smallest contributions first
 template <int NP> struct PlaneTerms {
   static constexpr int N = NP == 1 ? 1 : 6;

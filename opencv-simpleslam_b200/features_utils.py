@@ -11,9 +11,14 @@ Differences from the reference that are invisible to callers:
     cv2.KeyPoint_convert (no 2N device->host scalar syncs, features_utils.py:61-63);
   * matching is one C-ABI call on host buffers (b2s_lightglue_match_host);
   * the caller-side descriptor re-normalisation (features_utils.py:100) is fused into the extractor's last kernel.
+
+`filter_matches_ransac` is the reference's own body (cv2.findFundamentalMat: identical inlier sets); the parallel GPU
+estimator of libb200slam.so is opt-in (`args.gpu_ransac` at init_feature_pipeline, `set_gpu_ransac(True)` or
+B2S_GPU_RANSAC=1).  The OpenCV (ORB/SIFT) branch never touches the CUDA library: it is imported lazily.
 """
 from __future__ import annotations
 
+import os
 from itertools import repeat
 from typing import List
 
@@ -21,9 +26,25 @@ import cv2
 import numpy as np
 import torch
 
-from . import geometry as _geometry
 from .containers import DMatchArray, KeyPointArray
-from .frontend import ALIKED, LightGlue, rbd  # noqa: F401  (re-exported like the reference's imports)
+
+_GPU_RANSAC = os.environ.get("B2S_GPU_RANSAC", "0") == "1"
+
+
+def set_gpu_ransac(on: bool = True) -> None:
+    """Route `filter_matches_ransac` to the parallel GPU estimator (statistically equivalent consensus, not the same
+    sample sequence as cv2) instead of the reference's cv2.findFundamentalMat call."""
+    global _GPU_RANSAC
+    _GPU_RANSAC = bool(on)
+
+
+def __getattr__(name):
+    # `from lightglue import LightGlue, ALIKED` / `from lightglue.utils import rbd` of the reference (features_utils.py:8-9),
+    # resolved lazily so that ORB/SIFT-only users never load the CUDA library
+    if name in ("ALIKED", "LightGlue", "rbd"):
+        from . import frontend
+        return getattr(frontend, name)
+    raise AttributeError(name)
 
 
 # --------------------------------------------------------------------------- #
@@ -31,12 +52,24 @@ from .frontend import ALIKED, LightGlue, rbd  # noqa: F401  (re-exported like th
 # --------------------------------------------------------------------------- #
 def init_feature_pipeline(args):
     """Instantiate detector & matcher according to CLI arguments. Returns (detector, matcher)."""
+    if getattr(args, "gpu_ransac", None) is not None:
+        set_gpu_ransac(bool(args.gpu_ransac))
     if args.use_lightglue:
         if not torch.cuda.is_available():
             raise RuntimeError("b200slam: the LightGlue branch needs a CUDA device (no CPU fallback)")
-        detector = ALIKED(max_num_keypoints=int(getattr(args, "max_features", 4000))).eval().to("cuda")
-        matcher = LightGlue(features="aliked",
-                            precision=str(getattr(args, "lg_precision", "fp32"))).eval().to("cuda")
+        from . import weights as _weights
+        from .frontend import ALIKED, LightGlue
+        # real checkpoints (the reference's torch.hub cache, or args.aliked_weights / args.lightglue_weights); seeded
+        # synthetic weights only on explicit opt-in (args.synthetic_weights or B2S_SYNTHETIC_WEIGHTS=1)
+        synth_ok = bool(getattr(args, "synthetic_weights", False)) or None
+        sa, _ = _weights.load_aliked_state(path=getattr(args, "aliked_weights", None), allow_synthetic=synth_ok)
+        sl, _ = _weights.load_lightglue_state(path=getattr(args, "lightglue_weights", None), allow_synthetic=synth_ok)
+        detector = ALIKED(max_num_keypoints=int(getattr(args, "max_features", 4000)), weights=sa).eval().to("cuda")
+        kw = {}
+        if getattr(args, "lg_pruning_min_kpts", None) is not None:
+            kw["pruning_threshold"] = int(args.lg_pruning_min_kpts)
+        matcher = LightGlue(features="aliked", weights=sl,
+                            precision=str(getattr(args, "lg_precision", "fp32")), **kw).eval().to("cuda")
     else:
         detector = _get_opencv_detector(args.detector, max_features=int(getattr(args, "max_features", 6000)))
         matcher = _get_opencv_matcher(args.matcher, args.detector)
@@ -142,14 +175,7 @@ def _match_points(kp1, kp2, matches):
     return _kps_to_array(kp1)[qi], _kps_to_array(kp2)[ti]
 
 
-def filter_matches_ransac(kp1, kp2, matches, thresh=1.0):
-    """Drop outliers with a fundamental-matrix RANSAC (features_utils.py:185-200).  The reference's
-    `cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC, thresh, 0.99)` is replaced by the parallel 7-point RANSAC of
-    libb200slam.so (geometry.FundamentalRansac: 2048 samples scored at once, same error measure and threshold)."""
-    if len(matches) < 8:
-        return matches
-    pts1, pts2 = _match_points(kp1, kp2, matches)
-    _, mask = _geometry.find_fundamental_mat(pts1, pts2, thresh)
+def _apply_inlier_mask(matches, mask):
     if isinstance(matches, DMatchArray):
         return DMatchArray(matches.pairs[:0]) if mask is None else matches[mask.ravel().astype(bool)]
     if mask is None:
@@ -158,18 +184,35 @@ def filter_matches_ransac(kp1, kp2, matches, thresh=1.0):
     return [m for m, ok in zip(matches, mask) if ok]
 
 
+def filter_matches_ransac(kp1, kp2, matches, thresh=1.0):
+    """Drop outliers with a fundamental-matrix RANSAC (features_utils.py:185-200).  Default: the reference's own call,
+    `cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC, thresh, 0.99)` - the surviving matches are IDENTICAL to the
+    reference's on the same inputs (cv2's sampler is a fixed-seed private RNG stream that only cv2 reproduces).
+    Opt-in (`set_gpu_ransac`, `args.gpu_ransac`, B2S_GPU_RANSAC=1): the parallel 7-point RANSAC of libb200slam.so."""
+    if _GPU_RANSAC:
+        return filter_matches_ransac_gpu(kp1, kp2, matches, thresh)
+    return filter_matches_ransac_cv2(kp1, kp2, matches, thresh)
+
+
 def filter_matches_ransac_cv2(kp1, kp2, matches, thresh=1.0):
-    """The reference's own body (cv2.findFundamentalMat on the host) - kept for side-by-side comparisons in tests / tools."""
+    """The reference's body verbatim in behaviour: < 8 matches pass through, else cv2's FM_RANSAC inlier mask."""
     if len(matches) < 8:
         return matches
     pts1, pts2 = _match_points(kp1, kp2, matches)
     _, mask = cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC, thresh, 0.99)
-    if isinstance(matches, DMatchArray):
-        return DMatchArray(matches.pairs[:0]) if mask is None else matches[mask.ravel().astype(bool)]
-    if mask is None:
-        return []
-    mask = mask.ravel().astype(bool)
-    return [m for m, ok in zip(matches, mask) if ok]
+    return _apply_inlier_mask(matches, mask)
+
+
+def filter_matches_ransac_gpu(kp1, kp2, matches, thresh=1.0):
+    """Same contract on the GPU (geometry.FundamentalRansac: 2048 minimal samples solved and scored at once, OpenCV's
+    error measure and threshold).  Consensus sizes match cv2's statistically (tests/test_gpu_geometry.py), the inlier set is
+    not bit-identical to cv2's because the sample sequence differs."""
+    if len(matches) < 8:
+        return matches
+    from . import geometry as _geometry
+    pts1, pts2 = _match_points(kp1, kp2, matches)
+    _, mask = _geometry.find_fundamental_mat(pts1, pts2, thresh)
+    return _apply_inlier_mask(matches, mask)
 
 
 # --------------------------------------------------------------------------- #
@@ -193,6 +236,7 @@ def _convert_lightglue_to_opencv(kp0, kp1, matches):
 
 
 def _lightglue_detect_and_match(img1, img2, extractor, matcher):
+    from .frontend import rbd
     f0, f1 = extractor.extract_bgr(img1), extractor.extract_bgr(img2)
     matches = rbd(matcher({"image0": f0, "image1": f1}))   # with image_size, no min_conf (as the reference)
     f0, f1 = rbd(f0), rbd(f1)

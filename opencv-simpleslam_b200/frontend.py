@@ -303,6 +303,55 @@ class LightGlue(_Module):
 
     forward = __call__
 
+    # -- batched matching: the pair is a grid dimension of every kernel (b2s_lightglue_match_batch_ex) ----------
+    @property
+    def max_batch(self) -> int:
+        return int(lib.b2s_lg_max_batch())
+
+    def reserve(self, max_kp: int, pairs: int = 1):
+        """Allocate the workspace for `pairs` pairs per launch sequence up front (it otherwise grows on demand)."""
+        check(lib.b2s_lg_reserve(self._handle, int(max_kp), int(pairs)), "b2s_lg_reserve")
+        return self
+
+    def match_batch_packed(self, kpts, desc, cu, pair_i, pair_j, stride=None, max_batch=0, out=None, counts=None):
+        """Packed varlen form: kpts [T,2] / desc [T,128] CUDA f32 hold the features of F frames, frame f = rows
+        [cu[f], cu[f+1]) - or [cu[f], cu[f] + counts[f]) when `counts` is given (frames in fixed-size slots) - with
+        cu, counts, pair_i, pair_j host int arrays.  Enqueues on the current stream without host
+        synchronisation and returns device tensors {'matches' [P,stride,2] i32, 'scores' [P,stride] f32, 'n' [P] i32,
+        'stop' [P] i32}; rows >= n[p] of pair p are undefined.  Results equal P single `match_device` calls."""
+        cu = np.ascontiguousarray(cu, np.int32); pair_i = np.ascontiguousarray(pair_i, np.int32); pair_j = np.ascontiguousarray(pair_j, np.int32)
+        P = len(pair_i)
+        dev = self.device
+        if counts is not None:
+            counts = np.ascontiguousarray(counts, np.int32)
+        n_frames = len(counts) if counts is not None else len(cu) - 1
+        if stride is None:
+            cnt = counts if counts is not None else np.diff(cu)
+            stride = int(max(1, np.minimum(cnt[pair_i], cnt[pair_j]).max())) if P else 1
+        if out is None:
+            out = {"matches": torch.empty((max(P, 1), stride, 2), dtype=torch.int32, device=dev),
+                   "scores": torch.empty((max(P, 1), stride), dtype=torch.float32, device=dev),
+                   "n": torch.zeros((max(P, 1),), dtype=torch.int32, device=dev),
+                   "stop": torch.zeros((max(P, 1),), dtype=torch.int32, device=dev)}
+        st = torch.cuda.current_stream(dev).cuda_stream
+        check(lib.b2s_lightglue_match_batch_ex(self._handle, kpts.data_ptr(), desc.data_ptr(), cu.ctypes.data,
+                                               counts.ctypes.data if counts is not None else None, n_frames,
+                                               pair_i.ctypes.data, pair_j.ctypes.data, P, st, int(stride), int(max_batch),
+                                               out["matches"].data_ptr(), out["scores"].data_ptr(), out["n"].data_ptr(),
+                                               out["stop"].data_ptr()), "b2s_lightglue_match_batch")
+        return out
+
+    def match_batch_device(self, kpts_list, desc_list, pairs, stride=None, max_batch=0):
+        """kpts_list[f] [n_f,2], desc_list[f] [n_f,128] CUDA f32; pairs = [(i, j), ...] frame indices."""
+        with torch.cuda.device(self.device):
+            cu = np.cumsum([0] + [int(k.shape[0]) for k in kpts_list]).astype(np.int32)
+            kp = torch.cat([k.reshape(-1, 2) for k in kpts_list]).contiguous() if len(kpts_list) else torch.empty((0, 2), device=self.device)
+            de = torch.cat([d.reshape(-1, 128) for d in desc_list]).contiguous() if len(desc_list) else torch.empty((0, 128), device=self.device)
+            pi = np.asarray([p[0] for p in pairs], np.int32); pj = np.asarray([p[1] for p in pairs], np.int32)
+            out = self.match_batch_packed(kp, de, cu, pi, pj, stride, max_batch)
+            out["_keepalive"] = (kp, de)       # the packed inputs must outlive the enqueued kernels
+            return out
+
     def match_host(self, k0, d0, k1, d1, size0=None, size1=None, full=False):
         """One C-ABI call with host (numpy f32) buffers: b2s_lightglue_match_host."""
         k0 = np.ascontiguousarray(k0, np.float32); k1 = np.ascontiguousarray(k1, np.float32)
@@ -328,6 +377,12 @@ class LightGlue(_Module):
 
     def profile(self, on=True):
         check(lib.b2s_lg_profile(self._handle, 1 if on else 0), "b2s_lg_profile")
+
+    def workspace_bytes(self, max_kp: int, pairs: int = 1) -> int:
+        cfg = _lib.LgCfg()
+        lib.b2s_lg_default_cfg(C.byref(cfg))
+        cfg.n_layers, cfg.precision = self.n_layers, _lib.PRECISIONS[self.precision]
+        return int(lib.b2s_lg_workspace_bytes(C.byref(cfg), int(max_kp), int(pairs)))
 
     def profile_read(self, cls: int):
         """(summed kernel ms, launches) of class 0 = attention, 1 = GEMM since the last read."""

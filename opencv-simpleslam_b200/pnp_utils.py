@@ -21,7 +21,9 @@ from .features_utils import _kps_to_array
 from .geometry import _device_index
 
 MAX_OBS = 6            # the reference checks the last six observations (pnp_utils.py:112)
-CAND_CAP = 64
+CAND_CAP = 64          # candidates kept per landmark (only keypoints passing the descriptor gate are stored, nearest first)
+CAND_CAP_MAX = 256     # library limit (REPROJ_MAXCAP): used for the one retry when a truncated list ran dry
+MAX_KPS_LIB = 49152    # library limit on keypoints per frame (REPROJ_MAX_KPS)
 
 
 @dataclass
@@ -118,24 +120,29 @@ class MapDescriptorMirror:
 class ReprojectionMatcher:
     """b2s_reproj_* handle + per-map descriptor mirrors."""
 
-    def __init__(self, device=None, max_points: int = 8192, max_kps: int = 4096):
+    def __init__(self, device=None, max_points: int = 8192, max_kps: int = 4096, cand_cap: int = CAND_CAP):
         self.device_index = _device_index(device)
-        self._handle, self.max_points, self.max_kps = None, 0, 0
+        self._handle, self.max_points, self.max_kps, self.cand_cap = None, 0, 0, int(cand_cap)
+        self._wide = None                      # lazily created twin with CAND_CAP_MAX candidates per landmark
         self._create(max_points, max_kps)
         self._mirrors = weakref.WeakKeyDictionary()
 
     def _create(self, max_points, max_kps):
-        if self._handle:
-            lib.b2s_reproj_destroy(self._handle)
+        if max_kps > MAX_KPS_LIB:
+            raise ValueError(f"reproject_and_match_2d3d: {max_kps} keypoints exceed the library limit {MAX_KPS_LIB}")
         h = C.c_void_p()
-        check(lib.b2s_reproj_create(self.device_index, int(max_points), int(max_kps), CAND_CAP, C.byref(h)), "b2s_reproj_create")
-        self._handle, self.max_points, self.max_kps = h, int(max_points), int(max_kps)
+        # create the new handle first: if that fails the old one stays valid (and is destroyed exactly once)
+        check(lib.b2s_reproj_create(self.device_index, int(max_points), int(max_kps), self.cand_cap, C.byref(h)), "b2s_reproj_create")
+        old, self._handle = self._handle, h
+        self.max_points, self.max_kps = int(max_points), int(max_kps)
+        if old:
+            lib.b2s_reproj_destroy(old)
 
     def __del__(self):
         try:
-            if getattr(self, "_handle", None):
-                lib.b2s_reproj_destroy(self._handle)
-                self._handle = None
+            h, self._handle = getattr(self, "_handle", None), None
+            if h:
+                lib.b2s_reproj_destroy(h)
         except Exception:
             pass
 
@@ -157,7 +164,8 @@ class ReprojectionMatcher:
         if des.shape != (N, 128):
             raise ValueError(f"expected float descriptors [N,128] matching the keypoints, got {des.shape}")
         if P > self.max_points or N > self.max_kps:
-            self._create(max(self.max_points, int(2 ** np.ceil(np.log2(P)))), max(self.max_kps, int(2 ** np.ceil(np.log2(N)))))
+            grow = lambda need, lim: min(int(2 ** np.ceil(np.log2(need))), lim) if lim else int(2 ** np.ceil(np.log2(need)))   # noqa: E731
+            self._create(max(self.max_points, grow(P, 0)), max(self.max_kps, max(grow(N, MAX_KPS_LIB), min(N, MAX_KPS_LIB))))
         dev = torch.device("cuda", self.device_index)
         with torch.cuda.device(dev):
             mir = self.mirror_of(world_map)
@@ -177,7 +185,15 @@ class ReprojectionMatcher:
                                        flags.data_ptr()), "b2s_reproj_match")
             res = torch.cat([out, flags]).cpu().numpy()
         if res[-1] & 1:
-            raise RuntimeError(f"reproject_and_match_2d3d: a search window held more than {CAND_CAP} keypoints (radius_px={radius_px})")
+            # a landmark had more than cand_cap keypoints passing the descriptor gate AND lost all of the kept (nearest)
+            # ones to earlier landmarks: rerun once with the library's widest candidate list before giving up
+            if self.cand_cap < CAND_CAP_MAX:
+                if self._wide is None:
+                    self._wide = ReprojectionMatcher(self.device_index, self.max_points, self.max_kps, CAND_CAP_MAX)
+                    self._wide._mirrors = self._mirrors
+                return self._wide.match(world_map, K, Tcw_pred, kps_cur, des_cur, img_w, img_h, radius_px, max_l2)
+            raise RuntimeError(f"reproject_and_match_2d3d: a landmark exhausted {self.cand_cap} descriptor-gated candidates "
+                               f"(radius_px={radius_px}, max_l2={max_l2})")
         kp_of = res[:P]
         sel = np.flatnonzero(kp_of >= 0)
         if len(sel) == 0:

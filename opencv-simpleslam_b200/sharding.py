@@ -1,8 +1,8 @@
 """Work sharding across GPUs.  Frames and frame pairs are independent units, so
 the data path needs no collective: every rank works on its own contiguous chunk of the stream
 (plus one halo frame it re-extracts itself) or on its own slice of the keyframe-window pairs.
-Only the optional gather of per-frame features for cross-GPU window pairs communicates
-(`gather_window_features`, one all_gather of (count, kpts, desc) records)."""
+Only the gather of per-frame features for cross-GPU window pairs communicates
+(`gather_window_records`: one all_gather_into_tensor of a flat (kpts | desc | count) record buffer)."""
 from __future__ import annotations
 
 from typing import List, Tuple
@@ -35,20 +35,49 @@ def frames_of_rank(n_keyframes: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_keyframes, world))
 
 
-def gather_window_features(kpts: torch.Tensor, desc: torch.Tensor, counts: torch.Tensor, group=None):
-    """all_gather of this rank's extracted keyframes so every rank can match any window pair.
-    kpts [F_local, max_kp, 2], desc [F_local, max_kp, 128], counts [F_local] (int32), same
-    F_local on every rank (pad with count 0).  Returns lists indexed by source rank.
-    NCCL on GPUs (NVLink/NVSwitch), gloo in the CPU tests."""
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    out_k = [torch.empty_like(kpts) for _ in range(world)]
-    out_d = [torch.empty_like(desc) for _ in range(world)]
-    out_c = [torch.empty_like(counts) for _ in range(world)]
-    dist.all_gather(out_k, kpts.contiguous(), group=group)
-    dist.all_gather(out_d, desc.contiguous(), group=group)
-    dist.all_gather(out_c, counts.contiguous(), group=group)
-    return out_k, out_d, out_c
+class WindowRecord:
+    """This rank's keyframe records as ONE flat f32 buffer, so that sharing a window is a single collective:
+    [ keypoints slots*max_kp*2 | descriptors slots*max_kp*128 | counts slots ]   (counts stored as exact floats)."""
+
+    def __init__(self, slots: int, max_kp: int, device):
+        self.slots, self.max_kp = int(slots), int(max_kp)
+        self.nk, self.nd = self.slots * self.max_kp * 2, self.slots * self.max_kp * 128
+        self.flat = torch.zeros(self.nk + self.nd + self.slots, dtype=torch.float32, device=device)
+
+    @property
+    def kpts(self):
+        return self.flat[:self.nk].view(self.slots, self.max_kp, 2)
+
+    @property
+    def desc(self):
+        return self.flat[self.nk:self.nk + self.nd].view(self.slots, self.max_kp, 128)
+
+    @property
+    def counts(self):
+        return self.flat[self.nk + self.nd:]
+
+    def put(self, slot: int, kpts: torch.Tensor, desc: torch.Tensor, n: torch.Tensor):
+        """Device-side copy of one extraction (handle-owned buffers [max_kp, .], count on the device): no host sync."""
+        self.kpts[slot].copy_(kpts[:self.max_kp]); self.desc[slot].copy_(desc[:self.max_kp])
+        self.counts[slot:slot + 1].copy_(n.to(torch.float32))
+
+
+def gather_window_records(rec: WindowRecord, world: int, group=None):
+    """ONE `all_gather_into_tensor` of the flat records (17 MB for 16 keyframes of 2048 points; NCCL on GPUs, gloo in the
+    CPU tests), then the slot-major views every rank matches from:
+      kpts [world*slots*max_kp, 2], desc [world*slots*max_kp, 128] (frame of rank r, slot s at row (r*slots+s)*max_kp),
+      counts int32 [world*slots]."""
+    if world > 1:
+        import torch.distributed as dist
+        flat = torch.empty(world * rec.flat.numel(), dtype=torch.float32, device=rec.flat.device)
+        dist.all_gather_into_tensor(flat, rec.flat, group=group)      # rank r's record at [r*L, (r+1)*L)
+        out = flat.view(world, rec.flat.numel())
+    else:
+        out = rec.flat[None]
+    kp = out[:, :rec.nk].reshape(world * rec.slots * rec.max_kp, 2)                      # per-rank sections -> one array
+    de = out[:, rec.nk:rec.nk + rec.nd].reshape(world * rec.slots * rec.max_kp, 128)
+    cnt = out[:, rec.nk + rec.nd:].reshape(world * rec.slots).round().to(torch.int32)
+    return kp.contiguous(), de.contiguous(), cnt
 
 
 def global_frame_table(n_keyframes: int, world: int):

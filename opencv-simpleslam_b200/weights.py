@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import math
 import os
+import warnings
 import struct
 from collections import OrderedDict
 
@@ -142,19 +143,46 @@ def _rename_legacy_lightglue(sd):
     return out
 
 
-def load_aliked_state(model_name="aliked-n16", seed=0):
-    """(state_dict, source) - the real checkpoint if it is on disk, else synthetic."""
-    path = os.path.join(CKPT_DIR, f"{model_name}.pth")
-    if os.path.exists(path):
-        return torch.load(path, map_location="cpu"), path
+class MissingCheckpointError(FileNotFoundError):
+    pass
+
+
+def _synthetic_allowed(allow_synthetic) -> bool:
+    """Explicit opt-in only: the argument wins, else B2S_SYNTHETIC_WEIGHTS=1 (benchmarks / tests on boxes without the
+    checkpoints).  The reference always runs real weights (torch.hub download), so silently matching with random
+    weights would quietly degrade a SLAM run instead of failing."""
+    if allow_synthetic is not None:
+        return bool(allow_synthetic)
+    return os.environ.get("B2S_SYNTHETIC_WEIGHTS", "0") == "1"
+
+
+def _missing(what, tried):
+    return MissingCheckpointError(
+        f"b200slam: no {what} checkpoint found (tried {', '.join(tried)}). Put the upstream file there, pass its path "
+        "(args.aliked_weights / args.lightglue_weights or weights=...), or opt in to seeded synthetic weights with "
+        "args.synthetic_weights=True / B2S_SYNTHETIC_WEIGHTS=1 (benchmarks and tests only: matches are meaningless).")
+
+
+def load_aliked_state(model_name="aliked-n16", seed=0, path=None, allow_synthetic=None):
+    """(state_dict, source): `path` if given, else the reference's torch.hub cache; synthetic only on opt-in."""
+    tried = [path] if path else [os.path.join(CKPT_DIR, f"{model_name}.pth")]
+    for p in tried:
+        if os.path.exists(p):
+            return torch.load(p, map_location="cpu"), p
+    if path or not _synthetic_allowed(allow_synthetic):
+        raise _missing(f"ALIKED ({model_name})", tried)
+    warnings.warn(f"b200slam: ALIKED runs on SYNTHETIC weights (seed={seed}); keypoints are not meaningful", stacklevel=2)
     return synthetic_aliked_state(model_name, seed), f"synthetic(seed={seed})"
 
 
-def load_lightglue_state(seed=0, **kw):
-    for fn in ("aliked_lightglue_v0-1_arxiv.pth", "aliked_lightglue.pth"):
-        path = os.path.join(CKPT_DIR, fn)
-        if os.path.exists(path):
-            return _rename_legacy_lightglue(torch.load(path, map_location="cpu")), path
+def load_lightglue_state(seed=0, path=None, allow_synthetic=None, **kw):
+    tried = [path] if path else [os.path.join(CKPT_DIR, fn) for fn in ("aliked_lightglue_v0-1_arxiv.pth", "aliked_lightglue.pth")]
+    for p in tried:
+        if os.path.exists(p):
+            return _rename_legacy_lightglue(torch.load(p, map_location="cpu")), p
+    if path or not _synthetic_allowed(allow_synthetic):
+        raise _missing("LightGlue (aliked)", tried)
+    warnings.warn(f"b200slam: LightGlue runs on SYNTHETIC weights (seed={seed}); matches are not meaningful", stacklevel=2)
     return synthetic_lightglue_state(seed, **kw), f"synthetic(seed={seed})"
 
 

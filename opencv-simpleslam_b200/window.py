@@ -1,41 +1,47 @@
 """Keyframe-window all-pairs matching across GPUs (BASELINE config 3): every rank extracts the
-keyframes f with f mod world == rank, ONE all_gather (NCCL over NVLink/NVSwitch; gloo in CPU tests) shares the
-(count, keypoints, descriptors) records, then rank r matches the window pairs p with p mod world == r.  The reference
-runs this window through `select_keyframe` / `triangulate_between_kfs_2view` one pair at a time on one device
+keyframes f with f mod world == rank, ONE packed all_gather (NCCL over NVLink/NVSwitch; gloo in CPU tests) shares the
+(keypoints, descriptors, count) records, then rank r matches the window pairs p with p mod world == r in batched launch
+sequences (the pair is a grid dimension of every matcher kernel).  The reference runs this window through
+`select_keyframe` / `triangulate_between_kfs_2view` one pair at a time on one device
 (slam/core/keyframe_utils.py:153-154, triangulation_utils.py:131-132)."""
 from __future__ import annotations
 
 from typing import Dict, List, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib, sharding
 
 
-def match_keyframe_window(frames: List[torch.Tensor], det, mat, H: int, W: int, rank: int = 0, world: int = 1, group=None
-                          ) -> Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor]]:
+def match_keyframe_window(frames: List[torch.Tensor], det, mat, H: int, W: int, rank: int = 0, world: int = 1, group=None,
+                          max_batch: int = 0, timing: dict | None = None
+                          ) -> Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
     """frames: u8 BGR HWC CUDA tensors of ALL keyframes of the window (each rank only touches its own).
-    Returns {(i, j): (matches int32 [K,2], scores f32 [K])} for the pairs this rank owns; tensors stay on the device."""
+    Returns {(i, j): (matches int32 [stride,2], scores f32 [stride], n int32 [])} for the pairs this rank owns; tensors
+    stay on the device (rows >= n are undefined).  timing (optional dict) receives CUDA events around the gather."""
     dev = det.device
     n_kf, max_kp = len(frames), det.n_limit
     mine = sharding.frames_of_rank(n_kf, rank, world)
-    slots = -(-n_kf // world)                               # same F_local on every rank (padded with count 0)
-    kp = torch.zeros((slots, max_kp, 2), device=dev)
-    de = torch.zeros((slots, max_kp, 128), device=dev)
-    cnt = torch.zeros((slots,), dtype=torch.int32, device=dev)
+    slots = -(-n_kf // world)                               # same number of slots on every rank (padded with count 0)
+    rec = sharding.WindowRecord(slots, max_kp, dev)
     for s, f in enumerate(mine):
         k, d, _, n = det.extract_device(frames[f], _lib.IMG_BGR_U8_HWC, H, W, 3 * W)
-        kp[s].copy_(k); de[s].copy_(d); cnt[s:s + 1].copy_(n)
-    if world > 1:
-        gk, gd, gc = sharding.gather_window_features(kp, de, cnt, group)
-    else:
-        gk, gd, gc = [kp], [de], [cnt]
-    counts = torch.stack(gc).cpu()                          # one small D2H: the counts size the matcher launches
+        rec.put(s, k, d, n)
+    if timing is not None:
+        timing["gather_start"] = torch.cuda.Event(enable_timing=True); timing["gather_end"] = torch.cuda.Event(enable_timing=True)
+        timing["gather_start"].record()
+    kp_all, de_all, counts = sharding.gather_window_records(rec, world, group)   # [world*slots*max_kp, 2|128], [world*slots]
+    if timing is not None:
+        timing["gather_end"].record()
+    counts_h = counts.cpu().numpy().astype(np.int32)        # one small D2H: the counts size the matcher launches
     table = sharding.global_frame_table(n_kf, world)
-    out = {}
-    for (i, j) in sharding.shard_pairs(sharding.window_pairs(n_kf), rank, world):
-        (ri, si), (rj, sj) = table[i], table[j]
-        m, n = int(counts[ri, si]), int(counts[rj, sj])
-        r = mat.match_device(gk[ri][si, :m], gd[ri][si, :m], gk[rj][sj, :n], gd[rj][sj, :n], full=False)
-        out[(i, j)] = (r["matches"], r["scores"], r["n"])
-    return out
+    slot_of = lambda f: table[f][0] * slots + table[f][1]   # noqa: E731
+    my_pairs = sharding.shard_pairs(sharding.window_pairs(n_kf), rank, world)
+    if not my_pairs:
+        return {}
+    offs = (np.arange(world * slots, dtype=np.int64) * max_kp).astype(np.int32)
+    pi = np.asarray([slot_of(i) for i, _ in my_pairs], np.int32)
+    pj = np.asarray([slot_of(j) for _, j in my_pairs], np.int32)
+    r = mat.match_batch_packed(kp_all, de_all, offs, pi, pj, stride=max_kp, max_batch=max_batch, counts=counts_h)
+    return {pair: (r["matches"][p], r["scores"][p], r["n"][p]) for p, pair in enumerate(my_pairs)}

@@ -42,13 +42,17 @@ def _worker(rank, world, port, ret):
         g = torch.Generator().manual_seed(0)
         all_k = torch.rand(n_kf, max_kp, 2, generator=g); all_d = torch.rand(n_kf, max_kp, 128, generator=g)
         all_c = torch.randint(1, max_kp, (n_kf,), generator=g, dtype=torch.int32)
-        k, d, c = all_k[mine], all_d[mine], all_c[mine]
-        gk, gd, gc = sharding.gather_window_features(k, d, c)
+        slots = -(-n_kf // world)
+        rec = sharding.WindowRecord(slots, max_kp, "cpu")
+        for s, f in enumerate(mine):
+            rec.put(s, all_k[f], all_d[f], all_c[f:f + 1])
+        gk, gd, gc = sharding.gather_window_records(rec, world)       # ONE all_gather_into_tensor of the flat record
         table = sharding.global_frame_table(n_kf, world)
-        ok = True
+        ok = gk.shape == (world * slots * max_kp, 2) and gd.shape == (world * slots * max_kp, 128) and gc.dtype == torch.int32
         for f in range(n_kf):
             owner, slot = table[f]
-            ok &= torch.equal(gk[owner][slot], all_k[f]) and torch.equal(gd[owner][slot], all_d[f]) and int(gc[owner][slot]) == int(all_c[f])
+            row = (owner * slots + slot) * max_kp
+            ok &= torch.equal(gk[row:row + max_kp], all_k[f]) and torch.equal(gd[row:row + max_kp], all_d[f]) and int(gc[owner * slots + slot]) == int(all_c[f])
         pairs = sharding.shard_pairs(sharding.window_pairs(n_kf), rank, world)
         cnt = torch.tensor([len(pairs)])
         dist.all_reduce(cnt)

@@ -94,13 +94,13 @@ def test_ransac_edge_cases(ransac):
     from b200slam import features_utils as fu
     kps = [cv2.KeyPoint(float(3 * i), float(i % 11), 1) for i in range(30)]
     ms = [cv2.DMatch(i, i, 0.0) for i in range(30)]
-    assert fu.filter_matches_ransac(kps, kps, ms[:7], 1.0) == ms[:7]          # < 8: unchanged (reference :188-189)
+    assert fu.filter_matches_ransac_gpu(kps, kps, ms[:7], 1.0) == ms[:7]          # < 8: unchanged (reference :188-189)
     assert ransac.run_host(np.zeros((5, 2), np.float32), np.zeros((5, 2), np.float32)) == (None, None)
     # every correspondence identical -> every sample degenerate -> no model -> reference returns [] (mask is None)
     same = [cv2.KeyPoint(5.0, 5.0, 1)] * 30
-    assert fu.filter_matches_ransac(same, same, ms, 1.0) == []
+    assert fu.filter_matches_ransac_gpu(same, same, ms, 1.0) == []
     # pure translation of a planar grid is consistent with many F: whatever is returned must satisfy its own mask
-    out = fu.filter_matches_ransac(kps, kps, ms, 1.0)
+    out = fu.filter_matches_ransac_gpu(kps, kps, ms, 1.0)
     assert isinstance(out, list) and all(isinstance(m, cv2.DMatch) for m in out)
     # growth beyond the handle's capacity
     p1, p2, _ = G.two_view_scene(5000, 0.1, 0.1, 12)
@@ -108,21 +108,44 @@ def test_ransac_edge_cases(ransac):
     assert mask.sum() >= 0.85 * 4500 and ransac.max_points >= 5000
 
 
-def test_filter_matches_ransac_drop_in(ransac):
-    """Same signature / return type as the reference; array-native containers keep their type."""
+def test_filter_matches_ransac_default_is_reference_identical():
+    """a11: the default `filter_matches_ransac` is the reference's body (features_utils.py:185-200): on the same inputs the
+    surviving matches are IDENTICAL to `cv2.findFundamentalMat(pts1, pts2, FM_RANSAC, thresh, 0.99)`'s mask, scene by scene."""
+    from b200slam import features_utils as fu
+    from b200slam.containers import DMatchArray, KeyPointArray
+    for seed, (n, out_frac, noise, thresh) in enumerate([(600, 0.3, 0.15, 1.0), (1300, 0.2, 0.3, 2.5), (2048, 0.1, 0.1, 1.0), (90, 0.4, 0.5, 3.0)]):
+        p1, p2, _ = G.two_view_scene(n, out_frac, noise, 40 + seed)
+        kp1 = [cv2.KeyPoint(float(x), float(y), 1) for x, y in p1]
+        kp2 = [cv2.KeyPoint(float(x), float(y), 1) for x, y in p2]
+        ms = [cv2.DMatch(i, i, 0.0) for i in range(n)]
+        _, mask = cv2.findFundamentalMat(np.float32([kp1[m.queryIdx].pt for m in ms]), np.float32([kp2[m.trainIdx].pt for m in ms]),
+                                         cv2.FM_RANSAC, thresh, 0.99)
+        want = [m.queryIdx for m, ok in zip(ms, mask.ravel().astype(bool)) if ok]
+        got = fu.filter_matches_ransac(kp1, kp2, ms, thresh)
+        assert [m.queryIdx for m in got] == want and 8 <= len(want) < n
+        got_a = fu.filter_matches_ransac(KeyPointArray(p1), KeyPointArray(p2), DMatchArray(np.stack([np.arange(n)] * 2, 1)), thresh)
+        assert isinstance(got_a, DMatchArray) and got_a.queryIdx.tolist() == want
+
+
+def test_filter_matches_ransac_gpu_opt_in(ransac):
+    """The GPU estimator (opt-in): same signature / return type; consensus statistically equal to cv2's."""
     from b200slam import features_utils as fu
     from b200slam.containers import DMatchArray, KeyPointArray
     p1, p2, gt = G.two_view_scene(600, 0.3, 0.15, 21)
     kp1 = [cv2.KeyPoint(float(x), float(y), 1) for x, y in p1]
     kp2 = [cv2.KeyPoint(float(x), float(y), 1) for x, y in p2]
     ms = [cv2.DMatch(i, i, 0.0) for i in range(600)]
-    out = fu.filter_matches_ransac(kp1, kp2, ms, 1.0)
-    ref = fu.filter_matches_ransac_cv2(kp1, kp2, ms, 1.0)
+    fu.set_gpu_ransac(True)
+    try:
+        out = fu.filter_matches_ransac(kp1, kp2, ms, 1.0)
+    finally:
+        fu.set_gpu_ransac(False)
+    ref = fu.filter_matches_ransac(kp1, kp2, ms, 1.0)
     assert isinstance(out, list) and isinstance(out[0], cv2.DMatch)
     so, sr = {m.queryIdx for m in out}, {m.queryIdx for m in ref}
     assert len(so) >= 0.98 * len(sr) and len(so & sr) / len(so | sr) >= 0.9
     assert np.mean([gt[i] for i in so]) >= 0.97
-    out_a = fu.filter_matches_ransac(KeyPointArray(p1), KeyPointArray(p2), DMatchArray(np.stack([np.arange(600)] * 2, 1)), 1.0)
+    out_a = fu.filter_matches_ransac_gpu(KeyPointArray(p1), KeyPointArray(p2), DMatchArray(np.stack([np.arange(600)] * 2, 1)), 1.0)
     assert isinstance(out_a, DMatchArray) and set(out_a.queryIdx.tolist()) == so
 
 
@@ -235,14 +258,24 @@ def test_reproject_and_match_map_updates_and_edge_cases():
     # camera looking away: nothing projects into the image
     Tb = Tcw.copy(); Tb[:3, :3] = Tcw[:3, :3] @ np.diag([-1.0, 1.0, -1.0]); Tb[:3, 3] = [0, 0, -200.0]
     assert P.reproject_and_match_2d3d(wm, K, Tb, kps, des, 1241, 376).mp_ids == O.reproject_and_match_2d3d(wm, K, Tb, kps, des, 1241, 376).mp_ids
-    # a window holding more keypoints than the candidate capacity is reported, not silently truncated
+    # a dense cluster: 200 keypoints inside one landmark's search window (more than the 64 candidate slots).  Only
+    # keypoints that pass the descriptor gate are stored, so the reference's result is reproduced - no error, no limit
+    # on --proj_radius (the reference has none, pnp_utils.py:268-295)
     wm2, K2, T2, kps2, des2 = O.tracking_scene(300, 512, 5)
     usable = [p for p in wm2.points.values() if p.observations and p.observations[-1][2] is not None]
     uv, _ = O.project_points(K2, T2, np.asarray([p.position for p in usable]))
     vis = uv[(uv[:, 0] > 50) & (uv[:, 0] < 1100) & (uv[:, 1] > 50) & (uv[:, 1] < 300)][0]
     kps2[:200] = vis + rng.normal(0, 0.5, (200, 2)).astype(np.float32)
-    with pytest.raises(RuntimeError):
-        P.reproject_and_match_2d3d(wm2, K2, T2, kps2, des2, 1241, 376, radius_px=12.0)
+    for radius in (12.0, 40.0):
+        c2 = P.reproject_and_match_2d3d(wm2, K2, T2, kps2, des2, 1241, 376, radius_px=radius)
+        o3 = O.reproject_and_match_2d3d(wm2, K2, T2, kps2, des2, 1241, 376, radius_px=radius)
+        assert c2.mp_ids == o3.mp_ids and c2.kp_indices == o3.kp_indices and len(o3.mp_ids) > 50
+    # ... and when more than 64 keypoints of a window DO pass the gate (identical descriptors) and a landmark loses all of
+    # them to earlier landmarks, the matcher retries with the widest candidate list instead of failing
+    des3 = des2.copy(); des3[:200] = des3[0]
+    c3 = P.reproject_and_match_2d3d(wm2, K2, T2, kps2, des3, 1241, 376, radius_px=12.0, max_l2=2.5)
+    o4 = O.reproject_and_match_2d3d(wm2, K2, T2, kps2, des3, 1241, 376, radius_px=12.0, max_l2=2.5)
+    assert c3.mp_ids == o4.mp_ids and c3.kp_indices == o4.kp_indices
 
 
 # ---- size-independent properties at the BASELINE sizes (2048 keypoints, 1241x376) ---------------------------------

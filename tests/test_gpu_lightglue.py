@@ -27,7 +27,7 @@ CASES = {
 def _models(wkw, mkw, n_layers=9):
     from b200slam import frontend
     sd = weights.synthetic_lightglue_state(seed=0, n_layers=n_layers, **wkw)
-    ora = oracle.LightGlue(n_layers=n_layers, **{k: v for k, v in mkw.items() if k != "precision"}).eval()
+    ora = oracle.LightGlue(n_layers=n_layers, **{k: v for k, v in mkw.items() if k not in ("precision", "max_kp")}).eval()
     ora.load_state_dict(sd, strict=False)
     return ora, frontend.LightGlue(weights=sd, **mkw)
 
@@ -60,16 +60,99 @@ def test_match_parity_through_c_abi(name):
         assert ro["prune0"][0].min() < ro["stop"], "pruning must actually happen in this case"
 
 
-@pytest.mark.parametrize("name", ["headline_2048", "adaptive_prune_and_stop"])
-def test_simt_cross_check_path(name):
-    """precision='fp32_simt' (CUDA-core fp32, the cross-check of the tensor-core fp32 path) meets the same bar."""
-    m, n, wkw, mkw = CASES[name]
-    ora, mat = _models(wkw, dict(mkw, precision="fp32_simt"))
-    k0, d0, k1, d1, _ = noisy_copy_pair(m, n, seed=1)
+def test_config4_matcher_4096_full_depth_vs_oracle():
+    """BASELINE config 4's matcher: 4096 x 4096 keypoints, depth_confidence = width_confidence = -1 (all 9 layers, no
+    pruning), fp32 path against the CPU oracle: identical match index pairs, scores within 1e-3 relative."""
+    mkw = dict(depth_confidence=-1, width_confidence=-1)
+    ora, mat = _models({}, dict(mkw, max_kp=4096))
+    k0, d0, k1, d1, _ = noisy_copy_pair(4096, 4096, seed=7)
+    k0 = k0 * torch.tensor([1920.0 / 1241.0, 1080.0 / 376.0]); k1 = k1 * torch.tensor([1920.0 / 1241.0, 1080.0 / 376.0])
     ro = _oracle_run(ora, k0, d0, k1, d1)
     rg = mat.match_host(k0.numpy(), d0.numpy(), k1.numpy(), d1.numpy(), full=True)
-    assert np.array_equal(rg["matches"], ro["matches"][0].numpy()) and rg["stop"] == ro["stop"]
-    assert rel_err(rg["scores"], ro["scores"][0].numpy()) < 1e-3
+    mo = ro["matches"][0].numpy()
+    assert len(mo) > 500 and rg["stop"] == ro["stop"] == 9
+    assert np.array_equal(rg["matches"], mo), f"match pairs differ: {len(match_set(mo) ^ match_set(rg['matches']))} of {len(mo)}"
+    assert rel_err(rg["scores"], ro["scores"][0].numpy()) < 1e-3          # tolerance: 1e-3 relative
+    assert np.array_equal(rg["matches0"], ro["matches0"][0].numpy()) and np.array_equal(rg["matches1"], ro["matches1"][0].numpy())
+    assert (rg["prune0"] == 9).all() and (rg["prune1"] == 9).all()
+
+
+def _window_feats(n_kf, lo, hi, seed=100):
+    g = torch.Generator().manual_seed(seed)
+    base = noisy_copy_pair(hi, hi, seed=seed)
+    feats = []
+    for f in range(n_kf):
+        n = int(torch.randint(lo, hi + 1, (1,), generator=g))
+        sel = torch.randperm(hi, generator=g)[:n]
+        d = torch.nn.functional.normalize(base[1][sel] + 0.03 * torch.randn(n, 128, generator=g), dim=1)
+        k = base[0][sel] + 2.0 * f + torch.randn(n, 2, generator=g)
+        feats.append((k.contiguous(), d.contiguous()))
+    return feats
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_batched_window_equals_single_pair_calls(precision):
+    """BASELINE config 3 shape: 16 keyframes, all 120 pairs in batched launch sequences (the pair is a grid dimension of
+    every kernel) == 120 single-pair calls, bit for bit (matches, scores, counts, executed layers), ragged sizes, with
+    weights that make pairs prune and exit at different layers."""
+    from b200slam import frontend, sharding
+    sd = weights.synthetic_lightglue_state(seed=0, **ADAPT)
+    mat = frontend.LightGlue(weights=sd, precision=precision, filter_threshold=1e-6, max_kp=640)
+    feats = [(k.cuda(), d.cuda()) for k, d in _window_feats(16, 380, 640)]
+    pairs = sharding.window_pairs(16)
+    single = {}
+    for (i, j) in pairs:
+        r = mat.match_device(feats[i][0], feats[i][1], feats[j][0], feats[j][1], full=False)
+        torch.cuda.synchronize()
+        n = int(r["n"])
+        single[(i, j)] = (r["matches"][:n].cpu().numpy(), r["scores"][:n].cpu().numpy(), int(r["stop"]))
+    stops = {v[2] for v in single.values()}
+    assert len(stops) > 1, f"the pairs must not all stop at the same layer ({stops})"
+    for max_batch in (0, 5):
+        out = mat.match_batch_device([f[0] for f in feats], [f[1] for f in feats], pairs, max_batch=max_batch)
+        torch.cuda.synchronize()
+        nb, mb, sb, stb = out["n"].cpu().numpy(), out["matches"].cpu().numpy(), out["scores"].cpu().numpy(), out["stop"].cpu().numpy()
+        for p, key in enumerate(pairs):
+            ms, ss, st = single[key]
+            assert nb[p] == len(ms) and stb[p] == st, (key, nb[p], len(ms), stb[p], st)
+            assert np.array_equal(mb[p, :nb[p]], ms) and np.array_equal(sb[p, :nb[p]], ss), key
+    assert sum(len(v[0]) for v in single.values()) > 120 * 10, "vacuous"
+
+
+def test_batch_vs_oracle_headline_size():
+    """A batch of 3 pairs at 2048 keypoints against the CPU oracle pair by pair: identical match index pairs."""
+    ora, mat = _models({}, dict(max_kp=2048))
+    feats = _window_feats(3, 1800, 2048, seed=5)
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    out = mat.match_batch_device([f[0].cuda() for f in feats], [f[1].cuda() for f in feats], pairs)
+    torch.cuda.synchronize()
+    for p, (i, j) in enumerate(pairs):
+        ro = _oracle_run(ora, feats[i][0], feats[i][1], feats[j][0], feats[j][1])
+        n = int(out["n"][p])
+        assert len(ro["matches"][0]) > 50
+        assert np.array_equal(out["matches"][p, :n].cpu().numpy(), ro["matches"][0].numpy()), (i, j)
+        assert rel_err(out["scores"][p, :n].cpu().numpy(), ro["scores"][0].numpy()) < 1e-3
+        assert int(out["stop"][p]) == ro["stop"]
+
+
+def test_batch_edge_cases():
+    """Empty frames inside a batch, a single pair, more pairs than one launch sequence holds."""
+    ora, mat = _models({}, {})
+    feats = _window_feats(4, 60, 130, seed=9)
+    feats.append((torch.zeros(0, 2), torch.zeros(0, 128)))
+    kl, dl = [f[0].cuda() for f in feats], [f[1].cuda() for f in feats]
+    pairs = [(0, 4), (4, 1), (0, 1), (2, 3)] + [(a, b) for a in range(4) for b in range(4) if a != b] * 2
+    assert len(pairs) > mat.max_batch
+    out = mat.match_batch_device(kl, dl, pairs)
+    torch.cuda.synchronize()
+    n = out["n"].cpu().numpy()
+    assert n[0] == 0 and n[1] == 0
+    for p, (i, j) in enumerate(pairs):
+        if 4 in (i, j):
+            continue
+        ro = _oracle_run(ora, feats[i][0], feats[i][1], feats[j][0], feats[j][1])
+        assert np.array_equal(out["matches"][p, :n[p]].cpu().numpy(), ro["matches"][0].numpy()), (p, i, j)
+    assert mat.workspace_bytes(2048, 4) > mat.workspace_bytes(2048, 1) > 50e6
 
 
 def test_layer_taps_and_similarity():

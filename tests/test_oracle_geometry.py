@@ -97,8 +97,16 @@ def test_geometry_handles_fail_loudly_without_a_device():
     kps = [cv2.KeyPoint(float(i), float(i % 7), 1) for i in range(20)]
     ms = [cv2.DMatch(i, i, 0.0) for i in range(20)]
     assert fu.filter_matches_ransac(kps, kps, ms[:5], 1.0) == ms[:5]      # < 8 matches: returned unchanged (reference :188-189)
+    # default = the reference's own cv2 body: works without a GPU (ORB/SIFT-only users) ...
+    p1, p2, _ = G.two_view_scene(200, 0.2, 0.2, 3)
+    kpa = [cv2.KeyPoint(float(x), float(y), 1) for x, y in p1]; kpb = [cv2.KeyPoint(float(x), float(y), 1) for x, y in p2]
+    msa = [cv2.DMatch(i, i, 0.0) for i in range(200)]
+    out = fu.filter_matches_ransac(kpa, kpb, msa, 1.0)
+    _, mask = cv2.findFundamentalMat(p1.astype(np.float32), p2.astype(np.float32), cv2.FM_RANSAC, 1.0, 0.99)
+    assert [m.queryIdx for m in out] == np.flatnonzero(mask.ravel()).tolist() and 8 <= len(out) < 200
+    # ... the GPU estimator is opt-in and has no CPU fallback
     try:
-        fu.filter_matches_ransac(kps, kps, ms, 1.0)
+        fu.filter_matches_ransac_gpu(kps, kps, ms, 1.0)
         raise AssertionError("expected a RuntimeError without CUDA")
     except RuntimeError as e:
         assert "no CPU fallback" in str(e)

@@ -15,7 +15,7 @@ if world > 1:
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=dev)
 H, W, NKP, NKF = 376, 1241, 2048, 16
-sa, _ = weights.load_aliked_state(); sl, _ = weights.load_lightglue_state()
+sa, _ = weights.load_aliked_state(allow_synthetic=True); sl, _ = weights.load_lightglue_state(allow_synthetic=True)
 det = frontend.ALIKED(max_num_keypoints=NKP, weights=sa, device=dev)
 mat = frontend.LightGlue(weights=sl, device=dev, precision=args.precision, max_kp=NKP)
 frames = [torch.from_numpy(synth.frame(8 * t, H, W)).to(dev) for t in range(NKF)]     # keyframes t = 0, 8, ..., 120

@@ -8,7 +8,7 @@ from b200slam import _lib, weights, frontend, synth
 H, W, NKP = 376, 1241, 2048
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 dev = torch.device("cuda", 0)
-sa, _ = weights.load_aliked_state()
+sa, _ = weights.load_aliked_state(allow_synthetic=True)
 det = frontend.ALIKED(max_num_keypoints=NKP, weights=sa, device=dev)
 frames = [torch.from_numpy(synth.frame(t, H, W)).to(dev) for t in range(n)]
 for f in frames:

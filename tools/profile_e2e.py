@@ -9,7 +9,7 @@ from b200slam import features_utils as fu, synth, frontend, weights
 H, W, NKP = 376, 1241, 2048
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 ns = SimpleNamespace(use_lightglue=True, max_features=NKP, min_conf=0.7, lg_precision=prec)
-sa, _ = weights.load_aliked_state(); sl, _ = weights.load_lightglue_state()
+sa, _ = weights.load_aliked_state(allow_synthetic=True); sl, _ = weights.load_lightglue_state(allow_synthetic=True)
 det = frontend.ALIKED(max_num_keypoints=NKP, weights=sa, device="cuda:0")
 mat = frontend.LightGlue(weights=sl, device="cuda:0", precision=prec, max_kp=NKP)
 frames = [synth.frame(t, H, W) for t in range(12)]

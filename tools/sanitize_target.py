@@ -1,0 +1,69 @@
+"""Small workloads for compute-sanitizer (run under gpurun): exercises every hand-written mbarrier / TMEM / TMA
+pipeline at sizes the sanitizer finishes in minutes.
+  python tools/sanitize_target.py [gemm|attn|conv|match|batch|all]"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from b200slam import _lib, frontend, synth, weights  # noqa: E402
+from helpers import noisy_copy_pair  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+lib, check = _lib.lib, _lib.check
+g = torch.Generator().manual_seed(0)
+
+
+def gemm():
+    for fn in ("b2s_test_gemm_tc", "b2s_test_gemm_tc3"):
+        for (M, N, K) in [(200, 256, 256), (333, 512, 512), (130, 768, 256)]:
+            A = torch.randn(M, K, generator=g); W = torch.randn(N, K, generator=g) / K ** 0.5; b = torch.randn(N, generator=g)
+            out = np.empty((M, N), np.float32)
+            check(getattr(lib, fn)(A.numpy().ctypes.data, W.numpy().ctypes.data, b.numpy().ctypes.data, M, N, K, out.ctypes.data), fn)
+            ref = (A.double() @ W.double().T + b.double()).numpy()
+            print(fn, M, N, K, "rel err", float(np.abs(out - ref).max() / np.abs(ref).max()))
+
+
+def attn():
+    for fn in ("b2s_test_attn_tc", "b2s_test_attn_tc3"):
+        for (nq, nk) in [(130, 200), (300, 390)]:
+            q = torch.randn(nq, 256, generator=g); k = torch.randn(nk, 256, generator=g); v = torch.randn(nk, 256, generator=g)
+            out = np.empty((nq, 256), np.float32)
+            check(getattr(lib, fn)(q.numpy().ctypes.data, k.numpy().ctypes.data, v.numpy().ctypes.data, nq, nk, out.ctypes.data), fn)
+            print(fn, nq, nk, "finite", bool(np.isfinite(out).all()))
+
+
+def conv_and_match(batch=False):
+    Hh, Ww, nkp = 120, 160, 256
+    det = frontend.ALIKED(max_num_keypoints=nkp, weights=weights.synthetic_aliked_state(), device="cuda:0")
+    f0, f1 = det.extract_bgr(synth.frame(0, Hh, Ww)), det.extract_bgr(synth.frame(1, Hh, Ww))
+    print("extract", f0["keypoints"].shape[1], f1["keypoints"].shape[1])
+    for prec in ("fp32", "bf16"):
+        mat = frontend.LightGlue(weights=weights.synthetic_lightglue_state(token_bias=1.4, token_gain=6.0, match_bias=-5.0, match_gain=4.0),
+                                 device="cuda:0", precision=prec, max_kp=512)
+        r = mat({"image0": f0, "image1": f1})
+        k0, d0, k1, d1, _ = noisy_copy_pair(300, 280, seed=1)
+        r2 = mat.match_host(k0.numpy(), d0.numpy(), k1.numpy(), d1.numpy(), full=True)
+        print(prec, "matches", len(r["matches"][0]), len(r2["matches"]), "stop", r2["stop"])
+        if batch and hasattr(mat, "match_batch_device"):
+            feats = [noisy_copy_pair(200 + 40 * i, 200 + 40 * i, seed=20 + i)[:2] for i in range(3)]
+            out = mat.match_batch_device([f[0].cuda() for f in feats], [f[1].cuda() for f in feats], [(0, 1), (0, 2), (1, 2)])
+            torch.cuda.synchronize()
+            print(prec, "batch", [int(v) for v in out["n"].cpu()])
+
+
+if what in ("gemm", "all"):
+    gemm()
+if what in ("attn", "all"):
+    attn()
+if what in ("match", "conv", "all"):
+    conv_and_match(batch=False)
+if what in ("batch",):
+    conv_and_match(batch=True)
+torch.cuda.synchronize()
+print("sanitize target done:", what)
