@@ -161,14 +161,17 @@ int b2s_lightglue_match_host(b2s_lg* h, const float* k0, const float* d0, int m,
  * pair p matches frame pair_i[p] against pair_j[p]; outputs for pair p start at row
  * p*stride of matches_dev/mscores_dev, counts in n_matches_dev[p]. Host arrays: cu,
  * pair_i, pair_j.  _ex: counts (host, nullable) [F]: frame f owns rows [cu[f], cu[f] + counts[f]) - frames in fixed-size
- * slots, as an all_gather of per-rank records leaves them; max_batch > 0 lowers the pairs per launch sequence;
- * stop_layers_dev (nullable) [P]. */
+ * slots, as an all_gather of per-rank records leaves them; counts_dev (DEVICE, nullable) [F]: the true count of frame f is
+ * min(host count, counts_dev[f]) read on the device - the extractor's n_out_dev goes straight in and a frame stream never
+ * waits for a count to reach the host (the host count is then just the slot capacity); max_batch > 0 lowers the pairs
+ * per launch sequence; stop_layers_dev (nullable) [P]. */
 int b2s_lightglue_match_batch(b2s_lg* h, const float* kpts_dev, const float* desc_dev,
                               const int32_t* cu, int n_frames, const int32_t* pair_i,
                               const int32_t* pair_j, int n_pairs, void* stream, int stride,
                               int32_t* matches_dev, float* mscores_dev, int32_t* n_matches_dev);
 int b2s_lightglue_match_batch_ex(b2s_lg* h, const float* kpts_dev, const float* desc_dev,
-                                 const int32_t* cu, const int32_t* counts, int n_frames, const int32_t* pair_i,
+                                 const int32_t* cu, const int32_t* counts, const int32_t* counts_dev, int n_frames,
+                                 const int32_t* pair_i,
                                  const int32_t* pair_j, int n_pairs, void* stream, int stride, int max_batch,
                                  int32_t* matches_dev, float* mscores_dev, int32_t* n_matches_dev,
                                  int32_t* stop_layers_dev);

@@ -55,7 +55,7 @@ SIGNATURES = {
                                            i32p, f32p, i32p, i32p, i32p, i32p, f32p, f32p, i32p, i32p]),
     "b2s_lightglue_match_batch": (C.c_int, [vp, f32p, f32p, i32p, C.c_int, i32p, i32p, C.c_int, vp, C.c_int,
                                             i32p, f32p, i32p]),
-    "b2s_lightglue_match_batch_ex": (C.c_int, [vp, f32p, f32p, i32p, i32p, C.c_int, i32p, i32p, C.c_int, vp, C.c_int, C.c_int,
+    "b2s_lightglue_match_batch_ex": (C.c_int, [vp, f32p, f32p, i32p, i32p, i32p, C.c_int, i32p, i32p, C.c_int, vp, C.c_int, C.c_int,
                                                i32p, f32p, i32p, i32p]),
     "b2s_lg_max_batch": (C.c_int, []),
     "b2s_lg_workspace_bytes": (C.c_size_t, [C.POINTER(LgCfg), C.c_int, C.c_int]),

@@ -394,7 +394,7 @@ extern "C" int b2s_lightglue_match(b2s_lg* h, const float* k0, const float* d0, 
   LgBatchIn in = {};
   LgBatchOut out = {};
   LgPairIn& pi = in.pr[0];
-  pi.kp[0] = k0; pi.kp[1] = k1; pi.desc[0] = d0; pi.desc[1] = d1; pi.n[0] = m; pi.n[1] = n;
+  pi.kp[0] = k0; pi.kp[1] = k1; pi.desc[0] = d0; pi.desc[1] = d1; pi.n[0] = m; pi.n[1] = n; pi.n_dev[0] = pi.n_dev[1] = nullptr;
   pi.has_size[0] = size0 != nullptr; pi.has_size[1] = size1 != nullptr;
   if (size0) { pi.size[0][0] = size0[0]; pi.size[0][1] = size0[1]; }
   if (size1) { pi.size[1][0] = size1[0]; pi.size[1][1] = size1[1]; }
@@ -464,7 +464,7 @@ extern "C" int b2s_lightglue_match_host(b2s_lg* h, const float* k0, const float*
 // grid dimension of every kernel).  max_batch (0 = LG_MAXP) lowers the number of pairs per sequence, e.g. to keep a
 // sequence's working set inside the 126 MB L2.
 extern "C" int b2s_lightglue_match_batch_ex(b2s_lg* h, const float* kpts, const float* desc, const int32_t* cu, const int32_t* counts,
-                                            int n_frames, const int32_t* pair_i, const int32_t* pair_j, int n_pairs,
+                                            const int32_t* counts_dev, int n_frames, const int32_t* pair_i, const int32_t* pair_j, int n_pairs,
                                             void* stream, int stride, int max_batch, int32_t* matches, float* mscores,
                                             int32_t* n_matches, int32_t* stop_layers) {
   if (!h || !cu || !pair_i || !pair_j || n_pairs < 0 || !matches || !mscores || !n_matches) { set_error("b2s_lightglue_match_batch: bad argument"); return B2S_EINVAL; }
@@ -490,6 +490,7 @@ extern "C" int b2s_lightglue_match_batch_ex(b2s_lg* h, const float* kpts, const 
       LgPairIn& pi = in.pr[q];
       pi.kp[0] = kpts + (size_t)cu[a] * 2; pi.desc[0] = desc + (size_t)cu[a] * 128; pi.n[0] = rows_of(a);
       pi.kp[1] = kpts + (size_t)cu[b] * 2; pi.desc[1] = desc + (size_t)cu[b] * 128; pi.n[1] = rows_of(b);
+      if (counts_dev) { pi.n_dev[0] = counts_dev + a; pi.n_dev[1] = counts_dev + b; }
       out.pr[q] = {matches + (size_t)p * stride * 2, mscores + (size_t)p * stride, n_matches + p, stop_layers ? stop_layers + p : nullptr,
                    nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pi.n[0], pi.n[1]};
     }
@@ -502,7 +503,7 @@ extern "C" int b2s_lightglue_match_batch(b2s_lg* h, const float* kpts, const flo
                                          int n_frames, const int32_t* pair_i, const int32_t* pair_j, int n_pairs,
                                          void* stream, int stride, int32_t* matches, float* mscores,
                                          int32_t* n_matches) {
-  return b2s_lightglue_match_batch_ex(h, kpts, desc, cu, nullptr, n_frames, pair_i, pair_j, n_pairs, stream, stride, 0, matches, mscores,
+  return b2s_lightglue_match_batch_ex(h, kpts, desc, cu, nullptr, nullptr, n_frames, pair_i, pair_j, n_pairs, stream, stride, 0, matches, mscores,
                                       n_matches, nullptr);
 }
 

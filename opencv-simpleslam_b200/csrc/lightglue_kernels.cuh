@@ -14,8 +14,8 @@ namespace b2s {
 // Device-resident matcher state, LGC_INTS ints PER PAIR: adaptive depth / width decisions never visit the host.
 //   [LGC_STOP] early-exit flag (sticky)   [LGC_M],[LGC_N] live points of image 0 / 1
 //   [LGC_CAN0],[LGC_CAN1] this layer's prune-eligibility per side   [LGC_LAST] last executed layer
-//   [LGC_NPTS] original m + n   [LGC_UNCONF + i] #(token confidence < thr_i) after layer i
-enum { LGC_STOP = 1, LGC_M = 2, LGC_N = 3, LGC_CAN0 = 4, LGC_CAN1 = 5, LGC_LAST = 6, LGC_NPTS = 7, LGC_UNCONF = 8, LGC_INTS = 32 };
+//   [LGC_NPTS] original m + n   [LGC_UNCONF + i] #(token confidence < thr_i) after layer i (i < 16)   [LGC_M0],[LGC_N0] original m, n
+enum { LGC_STOP = 1, LGC_M = 2, LGC_N = 3, LGC_CAN0 = 4, LGC_CAN1 = 5, LGC_LAST = 6, LGC_NPTS = 7, LGC_UNCONF = 8, LGC_M0 = 24, LGC_N0 = 25, LGC_INTS = 32 };
 __device__ __forceinline__ bool lg_active(const int* c) { return !c[LGC_STOP] && c[LGC_M] > 0 && c[LGC_N] > 0; }
 
 constexpr int LG_MAXP = 16;      // pairs per launch sequence (larger batches are chunked)
@@ -23,12 +23,14 @@ constexpr int LG_MAXBLK = 256;   // 32-row blocks per image (cap <= 8192)
 constexpr int LG_ADAPT_INTS = 8 + 2 * LG_MAXBLK;
 
 // per-pair inputs / outputs, passed BY VALUE to the first / last kernel of a batch (no host staging buffer to recycle)
-struct LgPairIn { const float* kp[2]; const float* desc[2]; int n[2]; int has_size[2]; float size[2][2]; };
+// n[s]: point count of image s, or - when n_dev[s] is set - an upper bound of the device-resident count *n_dev[s] (the
+// extractor's n_out): a frame stream then never waits for a count to reach the host
+struct LgPairIn { const float* kp[2]; const float* desc[2]; const int* n_dev[2]; int n[2]; int has_size[2]; float size[2][2]; };
 struct LgBatchIn { LgPairIn pr[LG_MAXP]; };
 struct LgPairOut {
   int32_t* matches; float* mscores; int32_t* n_matches; int32_t* stop_layer;     // compact list (required), executed layers (nullable)
   int32_t* matches0; int32_t* matches1; float* ms0; float* ms1; int32_t* prune0; int32_t* prune1;   // full-size, nullable
-  int m, n;                                                                      // original counts
+  int m, n;                                                                      // original counts (upper bounds with LgPairIn::n_dev)
 };
 struct LgBatchOut { LgPairOut pr[LG_MAXP]; };
 
@@ -53,11 +55,13 @@ __global__ void __launch_bounds__(256) k_lg_posenc(PosencParams p) {
   pdl_wait();
   const int g = blockIdx.y, pair = g >> 1, s = g & 1;   // blockIdx.x = chunk of 64 points (every CTA re-derives the extent)
   const LgPairIn& in = p.in.pr[pair];
-  const int n = in.n[s];
+  const int n0 = in.n_dev[0] ? max(0, min(in.n[0], *in.n_dev[0])) : in.n[0];
+  const int n1 = in.n_dev[1] ? max(0, min(in.n[1], *in.n_dev[1])) : in.n[1];
+  const int n = s ? n1 : n0;
   const float* kp = in.kp[s];
   if (blockIdx.x == 0 && s == 0 && threadIdx.x < LGC_INTS) {
     const int t = threadIdx.x;
-    p.ctrl[pair * LGC_INTS + t] = t == LGC_M ? in.n[0] : t == LGC_N ? in.n[1] : t == LGC_LAST ? p.last_init : t == LGC_NPTS ? in.n[0] + in.n[1] : 0;
+    p.ctrl[pair * LGC_INTS + t] = (t == LGC_M || t == LGC_M0) ? n0 : (t == LGC_N || t == LGC_N0) ? n1 : t == LGC_LAST ? p.last_init : t == LGC_NPTS ? n0 + n1 : 0;
   }
   if (blockIdx.x * 64 >= n) return;
   __shared__ float red[4][8];
@@ -382,14 +386,15 @@ __global__ void __launch_bounds__(1024) k_lg_filter(FilterParams p) {
   const LgPairOut& o = p.out.pr[pair];
   const int* c = p.ctrl + pair * LGC_INTS;
   const int tid = threadIdx.x;
-  const bool empty_in = o.m <= 0 || o.n <= 0;
+  const int om = c[LGC_M0], on = c[LGC_N0];        // original counts (<= o.m, o.n)
+  const bool empty_in = om <= 0 || on <= 0;
   // ---- defaults over the original points ----
-  for (int i = tid; i < o.m; i += 1024) {
+  for (int i = tid; i < om; i += 1024) {
     if (o.matches0) o.matches0[i] = -1;
     if (o.ms0) o.ms0[i] = 0.f;
     if (o.prune0) o.prune0[i] = !p.do_prune ? p.n_layers : (empty_in ? 1 : p.prune[(size_t)(2 * pair) * p.cap + i]);
   }
-  for (int j = tid; j < o.n; j += 1024) {
+  for (int j = tid; j < on; j += 1024) {
     if (o.matches1) o.matches1[j] = -1;
     if (o.ms1) o.ms1[j] = 0.f;
     if (o.prune1) o.prune1[j] = !p.do_prune ? p.n_layers : (empty_in ? 1 : p.prune[(size_t)(2 * pair + 1) * p.cap + j]);

@@ -6,6 +6,7 @@
 #include "attn_tc.cuh"
 #include "attn_tc3.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tcp.cuh"
 
 #include <algorithm>
 #include <vector>
@@ -208,8 +209,28 @@ static bool gemm_cluster_enabled() {
   static const bool on = [] { const char* e = std::getenv("B2S_CLUSTER"); return e && e[0] == '1'; }();
   return on;
 }
+template <int BN, int NP>
+static void gemmp_attr() {
+  cudaFuncSetAttribute(k_gemm_tcp<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcpGemmCfg<BN, NP>::SMEM);
+}
+// persistent tile-scheduler GEMM (gemm_tcp.cuh) unless B2S_GEMM_PERSIST=0 (A/B measurements against the one-tile-per-CTA kernel)
+static bool gemm_persistent() {
+  static const bool on = [] { const char* e = std::getenv("B2S_GEMM_PERSIST"); return !(e && e[0] == '0'); }();
+  return on;
+}
+static int sm_count() {
+  static const int n = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v > 0 ? v : 148; }();
+  return n;
+}
+// launch of the persistent kernel: grid = min(tiles, SMs), every CTA walks tiles blockIdx.x, + gridDim.x, ...
+template <int BN, int NP>
+static void launch_gemm_p(cudaStream_t st, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const TcGemmParams& p, int m_tiles) {
+  const int total = m_tiles * ((p.N + BN - 1) / BN);
+  launch_k(k_gemm_tcp<BN, NP>, dim3(std::min(total, sm_count())), TcpGemmCfg<BN, NP>::THREADS, TcpGemmCfg<BN, NP>::SMEM, st, a1, a2, w, p, m_tiles);
+}
 static void tc_kernel_attrs() {
   gemm_attr<64, 1>(); gemm_attr<128, 1>(); gemm_attr<64, 3>(); gemm_attr<128, 3>(); gemm_attr<96, 1>(); gemm_attr<96, 3>();
+  gemmp_attr<64, 1>(); gemmp_attr<128, 1>(); gemmp_attr<64, 3>(); gemmp_attr<128, 3>(); gemmp_attr<96, 1>(); gemmp_attr<96, 3>();
   gemm_attr_cl<64, 1, 4>(); gemm_attr_cl<128, 1, 4>(); gemm_attr_cl<128, 1, 2>();
   gemm_attr_cl<64, 3, 4>(); gemm_attr_cl<128, 3, 4>(); gemm_attr_cl<128, 3, 2>();
   cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
@@ -303,7 +324,17 @@ static int tc_gemm(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& a1, con
   };
   const CUtensorMap *c1 = a32(a1), *c2 = a32(a2);
   const int cl = (gemm_cluster_enabled() && c1 && c2) ? (grid.x % 4 == 0 ? 4 : (grid.x % 2 == 0 && w.BN == 128 ? 2 : 1)) : 1;
-  if (w.BN == 96) {
+  if (gemm_persistent()) {
+    if (tc->np == 1) {
+      if (w.BN == 64) launch_gemm_p<64, 1>(st, a1, a2, w.map, p, tiles);
+      else if (w.BN == 96) launch_gemm_p<96, 1>(st, a1, a2, w.map, p, tiles);
+      else launch_gemm_p<128, 1>(st, a1, a2, w.map, p, tiles);
+    } else {
+      if (w.BN == 64) launch_gemm_p<64, 3>(st, a1, a2, w.map, p, tiles);
+      else if (w.BN == 96) launch_gemm_p<96, 3>(st, a1, a2, w.map, p, tiles);
+      else launch_gemm_p<128, 3>(st, a1, a2, w.map, p, tiles);
+    }
+  } else if (w.BN == 96) {
     if (tc->np == 1) launch_k(k_gemm_tc<96, 1>, grid, TcGemmCfg<96, 1>::THREADS, TcGemmCfg<96, 1>::SMEM, st, a1, a2, w.map, p);
     else launch_k(k_gemm_tc<96, 3>, grid, TcGemmCfg<96, 3>::THREADS, TcGemmCfg<96, 3>::SMEM, st, a1, a2, w.map, p);
   } else if (tc->np == 1) {
@@ -406,7 +437,8 @@ int lgtc_input_proj(LgTensorCore* tc, cudaStream_t st, float* x, int nseg, int m
   p.epi = TC_EPI_F32_BF16; p.out_f32 = x; p.ld_f32 = 256; p.out_bf16 = tc->xb; p.ld_bf16 = 256;
   p.out_plane = (size_t)p.plane_rows * 256; p.out_planes = tc->np;
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
-  launch_k(k_gemm_tc<64, 3>, dim3(4, nseg * p.tiles_per_seg), TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, tc->m_din, tc->m_din, tc->win.map, p);
+  if (gemm_persistent()) launch_gemm_p<64, 3>(st, tc->m_din, tc->m_din, tc->win.map, p, nseg * p.tiles_per_seg);
+  else launch_k(k_gemm_tc<64, 3>, dim3(4, nseg * p.tiles_per_seg), TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, tc->m_din, tc->m_din, tc->win.map, p);
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
   if (launches) ++*launches;
   B2S_LAUNCH_CHECK();
@@ -427,13 +459,15 @@ int lgtc_assignment(LgTensorCore* tc, cudaStream_t st, int npairs, int maxm, int
   p.seg_stride = cap; p.tiles_per_seg = cdiv(std::max(maxm, maxn), 128);
   p.plane_rows = plane_rows; p.epi = TC_EPI_BF16; p.out_bf16 = tc->md; p.ld_bf16 = 256; p.out_plane = plane;
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
-  launch_k(k_gemm_tc<64, 3>, dim3(4, 2 * npairs * p.tiles_per_seg), TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, tc->m_tx, tc->m_tx, tc->wfinal.map, p);
+  if (gemm_persistent()) launch_gemm_p<64, 3>(st, tc->m_tx, tc->m_tx, tc->wfinal.map, p, 2 * npairs * p.tiles_per_seg);
+  else launch_k(k_gemm_tc<64, 3>, dim3(4, 2 * npairs * p.tiles_per_seg), TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, tc->m_tx, tc->m_tx, tc->wfinal.map, p);
   p = TcGemmParams();
   p.K = 256; p.K1 = 256; p.N = maxn; p.bias = nullptr; p.ctrl = ctrl; p.ctrl_mode = 3;
   p.w_plane_rows = plane_rows; p.seg_stride = cap; p.tiles_per_seg = cdiv(maxm, 128);
   p.plane_rows = plane_rows; p.epi = TC_EPI_F32; p.out_f32 = sim; p.ld_f32 = cap; p.out_f32_t = simT; p.ld_f32_t = cap;
   p.out_pair_stride = (size_t)cap * cap;
-  launch_k(k_gemm_tc<128, 3>, dim3(cdiv(maxn, 128), npairs * p.tiles_per_seg), TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, tc->m_md, tc->m_md, tc->m_md, p);
+  if (gemm_persistent()) launch_gemm_p<128, 3>(st, tc->m_md, tc->m_md, tc->m_md, p, npairs * p.tiles_per_seg);
+  else launch_k(k_gemm_tc<128, 3>, dim3(cdiv(maxn, 128), npairs * p.tiles_per_seg), TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, tc->m_md, tc->m_md, tc->m_md, p);
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
   if (launches) *launches += 2;
   B2S_LAUNCH_CHECK();
@@ -510,7 +544,11 @@ static int test_gemm(const float* A, const float* W, const float* bias, int M, i
   p.K = K; p.K1 = K; p.N = N; p.bias = dB; p.epi = TC_EPI_F32; p.out_f32 = dC; p.ld_f32 = N; p.plane_rows = Mp;
   p.seg_stride = 0; p.seg_rows = M; p.tiles_per_seg = cdiv(M, 128);
   dim3 grid(N / BN, p.tiles_per_seg);
-  if (np == 1) {
+  if (gemm_persistent()) {
+    cudaStream_t st = 0;
+    if (np == 1) { if (BN == 64) launch_gemm_p<64, 1>(st, ma, ma, mw, p, p.tiles_per_seg); else launch_gemm_p<128, 1>(st, ma, ma, mw, p, p.tiles_per_seg); }
+    else { if (BN == 64) launch_gemm_p<64, 3>(st, ma, ma, mw, p, p.tiles_per_seg); else launch_gemm_p<128, 3>(st, ma, ma, mw, p, p.tiles_per_seg); }
+  } else if (np == 1) {
     if (BN == 64) k_gemm_tc<64, 1><<<grid, TcGemmCfg<64, 1>::THREADS, TcGemmCfg<64, 1>::SMEM>>>(ma, ma, mw, p);
     else k_gemm_tc<128, 1><<<grid, TcGemmCfg<128, 1>::THREADS, TcGemmCfg<128, 1>::SMEM>>>(ma, ma, mw, p);
   } else {
@@ -563,7 +601,11 @@ extern "C" int b2s_bench_gemm_tc3(int M, int N, int K, int cl, int iters, float*
   B2S_CUDA(cudaStreamCreate(&st));
   auto launch = [&](unsigned long long* ts) {
     TcGemmParams q = p; q.ts = ts;
-    if (BN == 96) launch_k(k_gemm_tc<96, 3>, grid, TcGemmCfg<96, 3>::THREADS, TcGemmCfg<96, 3>::SMEM, st, ma, ma, mw, q);
+    if (cl == 0) {          // persistent tile-scheduler kernel
+      if (BN == 96) launch_gemm_p<96, 3>(st, ma, ma, mw, q, Mp / 128);
+      else if (BN == 64) launch_gemm_p<64, 3>(st, ma, ma, mw, q, Mp / 128);
+      else launch_gemm_p<128, 3>(st, ma, ma, mw, q, Mp / 128);
+    } else if (BN == 96) launch_k(k_gemm_tc<96, 3>, grid, TcGemmCfg<96, 3>::THREADS, TcGemmCfg<96, 3>::SMEM, st, ma, ma, mw, q);
     else if (BN == 64) {
       if (cl == 4) launch_k_cluster(k_gemm_tc<64, 3, 4>, grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, 4, ma32, ma32, mw, q);
       else launch_k(k_gemm_tc<64, 3>, grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, ma, ma, mw, q);

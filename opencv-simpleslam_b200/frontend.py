@@ -313,10 +313,12 @@ class LightGlue(_Module):
         check(lib.b2s_lg_reserve(self._handle, int(max_kp), int(pairs)), "b2s_lg_reserve")
         return self
 
-    def match_batch_packed(self, kpts, desc, cu, pair_i, pair_j, stride=None, max_batch=0, out=None, counts=None):
+    def match_batch_packed(self, kpts, desc, cu, pair_i, pair_j, stride=None, max_batch=0, out=None, counts=None, counts_dev=None):
         """Packed varlen form: kpts [T,2] / desc [T,128] CUDA f32 hold the features of F frames, frame f = rows
         [cu[f], cu[f+1]) - or [cu[f], cu[f] + counts[f]) when `counts` is given (frames in fixed-size slots) - with
-        cu, counts, pair_i, pair_j host int arrays.  Enqueues on the current stream without host
+        cu, counts, pair_i, pair_j host int arrays.  counts_dev (CUDA int32 [F], optional): the true count of frame f is
+        min(counts[f], counts_dev[f]) read on the device (the extractor's device-resident n goes straight in; `counts` is then
+        just the slot capacity and nothing waits for a count on the host).  Enqueues on the current stream without host
         synchronisation and returns device tensors {'matches' [P,stride,2] i32, 'scores' [P,stride] f32, 'n' [P] i32,
         'stop' [P] i32}; rows >= n[p] of pair p are undefined.  Results equal P single `match_device` calls."""
         cu = np.ascontiguousarray(cu, np.int32); pair_i = np.ascontiguousarray(pair_i, np.int32); pair_j = np.ascontiguousarray(pair_j, np.int32)
@@ -335,7 +337,8 @@ class LightGlue(_Module):
                    "stop": torch.zeros((max(P, 1),), dtype=torch.int32, device=dev)}
         st = torch.cuda.current_stream(dev).cuda_stream
         check(lib.b2s_lightglue_match_batch_ex(self._handle, kpts.data_ptr(), desc.data_ptr(), cu.ctypes.data,
-                                               counts.ctypes.data if counts is not None else None, n_frames,
+                                               counts.ctypes.data if counts is not None else None,
+                                               counts_dev.data_ptr() if counts_dev is not None else None, n_frames,
                                                pair_i.ctypes.data, pair_j.ctypes.data, P, st, int(stride), int(max_batch),
                                                out["matches"].data_ptr(), out["scores"].data_ptr(), out["n"].data_ptr(),
                                                out["stop"].data_ptr()), "b2s_lightglue_match_batch")

@@ -34,7 +34,6 @@ def match_keyframe_window(frames: List[torch.Tensor], det, mat, H: int, W: int, 
     kp_all, de_all, counts = sharding.gather_window_records(rec, world, group)   # [world*slots*max_kp, 2|128], [world*slots]
     if timing is not None:
         timing["gather_end"].record()
-    counts_h = counts.cpu().numpy().astype(np.int32)        # one small D2H: the counts size the matcher launches
     table = sharding.global_frame_table(n_kf, world)
     slot_of = lambda f: table[f][0] * slots + table[f][1]   # noqa: E731
     my_pairs = sharding.shard_pairs(sharding.window_pairs(n_kf), rank, world)
@@ -43,5 +42,7 @@ def match_keyframe_window(frames: List[torch.Tensor], det, mat, H: int, W: int, 
     offs = (np.arange(world * slots, dtype=np.int64) * max_kp).astype(np.int32)
     pi = np.asarray([slot_of(i) for i, _ in my_pairs], np.int32)
     pj = np.asarray([slot_of(j) for _, j in my_pairs], np.int32)
-    r = mat.match_batch_packed(kp_all, de_all, offs, pi, pj, stride=max_kp, max_batch=max_batch, counts=counts_h)
+    # the keypoint counts stay on the device (counts_dev): the host passes the slot capacity and never waits for them
+    r = mat.match_batch_packed(kp_all, de_all, offs, pi, pj, stride=max_kp, max_batch=max_batch,
+                               counts=np.full(world * slots, max_kp, np.int32), counts_dev=counts)
     return {pair: (r["matches"][p], r["scores"][p], r["n"][p]) for p, pair in enumerate(my_pairs)}
