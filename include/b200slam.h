@@ -100,6 +100,14 @@ int b2s_aliked_extract(b2s_aliked* h, const void* img_dev, int img_format, int H
                        int row_stride, void* stream, float* kpts_dev, float* desc_dev,
                        float* scores_dev, int32_t* n_out_dev);
 
+/* Batched extraction of B same-shape frames (imgs_dev: HOST array of B device image pointers).  The frames are spread
+ * over n_lanes (<= 8; 0 = 4) internal extractor lanes - own workspace and stream each - that run concurrently; `stream`
+ * forks into the lanes and joins them, nothing synchronises with the host.  Outputs are slabs:
+ * kpts_dev [B, max_kp, 2], desc_dev [B, max_kp, 128], scores_dev (nullable) [B, max_kp], n_out_dev [B]. */
+int b2s_aliked_extract_batch(b2s_aliked* h, const void* const* imgs_dev, int B, int img_format, int H, int W,
+                             int row_stride, int n_lanes, void* stream, float* kpts_dev, float* desc_dev,
+                             float* scores_dev, int32_t* n_out_dev);
+
 /* same, host buffers; copies in/out, synchronises, returns the count in *n_out. */
 int b2s_aliked_extract_host(b2s_aliked* h, const void* img_host, int img_format, int H, int W,
                             int row_stride, float* kpts_host, float* desc_host,
@@ -119,6 +127,11 @@ int b2s_aliked_extract_host_begin(b2s_aliked* h, const void* img_host, int img_f
                                   int row_stride, float desc_renorm_eps);
 int b2s_aliked_extract_host_keypoints(b2s_aliked* h, float* kpts_host, int32_t* n_out);
 int b2s_aliked_extract_host_finish(b2s_aliked* h, float* desc_host, float* scores_host);
+
+/* Device-side copy of the last *_host extraction's n keypoints / descriptors (exactly what the caller received) into
+ * caller-owned device buffers: a host-API caller can keep a frame's features on the GPU and skip their re-upload when the
+ * frame is matched next (the drop-in's feature cache, opencv-simpleslam_b200/features_utils.py). */
+int b2s_aliked_copy_last_features(b2s_aliked* h, float* kpts_dst_dev, float* desc_dst_dev, int n, void* stream);
 
 int b2s_lightglue_create(const b2s_lg_cfg* cfg, const void* weights, size_t nbytes, int device,
                          b2s_lg** out);

@@ -42,11 +42,13 @@ SIGNATURES = {
     "b2s_aliked_create": (C.c_int, [C.POINTER(AlikedCfg), vp, C.c_size_t, C.c_int, C.POINTER(vp)]),
     "b2s_aliked_destroy": (None, [vp]),
     "b2s_aliked_extract": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, f32p, f32p, f32p, i32p]),
+    "b2s_aliked_extract_batch": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, f32p, f32p, f32p, i32p]),
     "b2s_aliked_extract_host": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, i32p]),
     "b2s_aliked_extract_host_ex": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, i32p, C.c_float]),
     "b2s_aliked_extract_host_begin": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
     "b2s_aliked_extract_host_keypoints": (C.c_int, [vp, f32p, i32p]),
     "b2s_aliked_extract_host_finish": (C.c_int, [vp, f32p, f32p]),
+    "b2s_aliked_copy_last_features": (C.c_int, [vp, f32p, f32p, C.c_int, vp]),
     "b2s_lightglue_create": (C.c_int, [C.POINTER(LgCfg), vp, C.c_size_t, C.c_int, C.POINTER(vp)]),
     "b2s_lg_destroy": (None, [vp]),
     "b2s_lightglue_match": (C.c_int, [vp, f32p, f32p, C.c_int, f32p, f32p, C.c_int, f32p, f32p, vp,

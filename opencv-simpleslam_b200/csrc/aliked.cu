@@ -61,6 +61,17 @@ struct b2s_aliked {
   float desc_renorm_eps = 0.f;                           // set per call by b2s_aliked_extract_host_ex
   // split host API (begin / keypoints / finish): pinned staging for the early keypoint copy
   float* pin_kp = nullptr; int32_t* pin_n = nullptr; cudaEvent_t ev_kp = nullptr; bool early_kp = false; bool pending = false;  b2s_remap* undist = nullptr;                           // optional ingest stage (b2s_aliked_set_undistort); borrowed
+  // batched extraction (b2s_aliked_extract_batch): extra LANES = complete extractors (own workspace, own stream) created
+  // lazily from a copy of the weight blob; frame i of a batch runs on lane i mod n_lanes, the lanes run concurrently
+  // CUDA-graph replay of one extraction (batched path): the ~60 launches of a frame are captured once per frame shape
+  // over fixed staging buffers (image in, keypoints / descriptors / scores / count out) and replayed with one launch
+  DeviceArena grarena;
+  cudaGraphExec_t gexec = nullptr; int g_fmt = -1, g_H = 0, g_W = 0, g_stride = 0; float g_eps = 0.f; bool g_failed = false;
+  uint8_t* g_img = nullptr; size_t g_img_bytes = 0; float *g_kp = nullptr, *g_desc = nullptr, *g_sc = nullptr; int32_t* g_n = nullptr;
+  long long g_launches = 0;
+  float* thr0 = nullptr;                                 // device copy of cfg.det_thresh (source of the per-call reset of thr)
+  std::vector<uint8_t> blob;
+  std::vector<b2s_aliked*> lanes; std::vector<cudaStream_t> lane_st; std::vector<cudaEvent_t> lane_ev; cudaEvent_t ev_fork = nullptr;
 };
 
 extern "C" void b2s_aliked_default_cfg(b2s_aliked_cfg* c) {
@@ -348,6 +359,11 @@ extern "C" int b2s_aliked_create(const b2s_aliked_cfg* cfg, const void* weights,
   cudaFuncSetAttribute(k_conv3x3_tc<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<32, 32>::SMEM);
   int rc = load_weights(h, wb);
   if (rc) { delete h; return rc; }
+  h->blob.assign(static_cast<const uint8_t*>(weights), static_cast<const uint8_t*>(weights) + nbytes);
+  {
+    std::vector<float> t0(1, h->cfg.det_thresh);
+    if ((rc = h->warena.upload(&h->thr0, t0))) { delete h; return rc; }
+  }
   *out = h;
   return 0;
 }
@@ -355,13 +371,23 @@ extern "C" int b2s_aliked_create(const b2s_aliked_cfg* cfg, const void* weights,
 extern "C" void b2s_aliked_destroy(b2s_aliked* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
+  for (b2s_aliked* l : h->lanes) b2s_aliked_destroy(l);
+  for (cudaStream_t s : h->lane_st) cudaStreamDestroy(s);
+  for (cudaEvent_t e : h->lane_ev) cudaEventDestroy(e);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->pin_kp) cudaFreeHost(h->pin_kp);
   if (h->pin_n) cudaFreeHost(h->pin_n);
   if (h->ev_kp) cudaEventDestroy(h->ev_kp);
   delete h;
 }
 
-extern "C" long long b2s_aliked_launch_count(const b2s_aliked* h) { return h ? h->launches : 0; }
+extern "C" long long b2s_aliked_launch_count(const b2s_aliked* h) {
+  if (!h) return 0;
+  long long n = h->launches;
+  for (const b2s_aliked* l : h->lanes) n += l->launches;
+  return n;
+}
 
 extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H, int W, int row_stride, void* stream,
                                   float* kpts, float* desc, float* scores, int32_t* n_out) {
@@ -496,7 +522,7 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
   // ---- DKD ----
   {
     B2S_CUDA(cudaMemsetAsync(h->dk, 0, 8 * sizeof(int), st));
-    B2S_CUDA(cudaMemcpyAsync(h->thr, &h->cfg.det_thresh, sizeof(float), cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(h->thr, h->thr0, sizeof(float), cudaMemcpyDeviceToDevice, st));   // device source: capturable in a CUDA graph
     launch_k(k_dkd_nms, dim3(cdiv(Wr, NMS_T), cdiv(Hr, NMS_T)), 256, 0, st, h->score, Hr, Wr, h->nms, h->thr, h->dk, h->cand_idx, h->cand_sc, h->cand_cap);
     launch_k(k_dkd_fallback, 1, 1024, 0, st, h->score, h->nms, Hr * Wr, h->thr, h->dk, h->cand_idx, h->cand_sc, h->cand_cap);
     launch_k(k_dkd_select, 1, 1024, 0, st, h->cand_sc, h->cand_idx, h->cand_cap, h->n_limit, h->dk);
@@ -533,6 +559,100 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
     B2S_TRY(tc_gemm(h, st, h->m_F, K, h->tc_agg, nullptr, 0, K, n_out, 1, h->descraw, 128, nullptr, 0));
     launch_k(k_desc_normalize, cdiv(K, 8), 256, 0, st, h->descraw, n_out, desc, h->desc_renorm_eps);
     ++h->launches; B2S_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// One extraction as a CUDA-graph replay: image -> staging, graph (all kernels of b2s_aliked_extract over the staging
+// buffers), results -> the caller's buffers.  Falls back to the eager launch sequence if capture is not possible.
+static int aliked_extract_graphed(b2s_aliked* h, const void* img, int fmt, int H, int W, int row_stride, cudaStream_t st,
+                                  float* kpts, float* desc, float* scores, int32_t* n_out) {
+  static const bool off = [] { const char* e = std::getenv("B2S_ALIKED_GRAPH"); return e && e[0] == '0'; }();
+  if (off || h->g_failed) return b2s_aliked_extract(h, img, fmt, H, W, row_stride, st, kpts, desc, scores, n_out);
+  const size_t bytes = fmt == B2S_IMG_BGR_U8_HWC ? (size_t)(row_stride > 0 ? row_stride : 3 * W) * H : (size_t)3 * H * W * sizeof(float);
+  if (!h->gexec || h->g_fmt != fmt || h->g_H != H || h->g_W != W || h->g_stride != row_stride || h->g_eps != h->desc_renorm_eps) {
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    if (bytes > h->g_img_bytes || !h->g_kp) {
+      B2S_CUDA(cudaStreamSynchronize(st));
+      h->grarena.release();
+      h->g_img_bytes = 0;
+      B2S_TRY(h->grarena.alloc(&h->g_img, bytes));
+      B2S_TRY(h->grarena.alloc(&h->g_kp, (size_t)h->n_limit * 2));
+      B2S_TRY(h->grarena.alloc(&h->g_desc, (size_t)h->n_limit * 128));
+      B2S_TRY(h->grarena.alloc(&h->g_sc, (size_t)h->n_limit));
+      B2S_TRY(h->grarena.alloc(&h->g_n, (size_t)1));
+      h->g_img_bytes = bytes;
+    }
+    // eager warm-up call: sizes the workspace and the tensor maps (both synchronise / allocate: not capturable)
+    B2S_CUDA(cudaMemcpyAsync(h->g_img, img, bytes, cudaMemcpyDeviceToDevice, st));
+    B2S_TRY(b2s_aliked_extract(h, h->g_img, fmt, H, W, row_stride, st, h->g_kp, h->g_desc, h->g_sc, h->g_n));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    const long long l0 = h->launches;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    int rc = 0;
+    if (e == cudaSuccess) {
+      rc = b2s_aliked_extract(h, h->g_img, fmt, H, W, row_stride, st, h->g_kp, h->g_desc, h->g_sc, h->g_n);
+      e = cudaStreamEndCapture(st, &graph);
+    }
+    if (e == cudaSuccess && rc == 0 && graph) e = cudaGraphInstantiate(&h->gexec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess || rc != 0 || !h->gexec) {
+      cudaGetLastError();
+      h->gexec = nullptr; h->g_failed = true;          // this driver cannot capture the sequence: stay eager
+      return b2s_aliked_extract(h, img, fmt, H, W, row_stride, st, kpts, desc, scores, n_out);
+    }
+    h->g_launches = h->launches - l0; h->launches = l0;
+    h->g_fmt = fmt; h->g_H = H; h->g_W = W; h->g_stride = row_stride; h->g_eps = h->desc_renorm_eps;
+  }
+  B2S_CUDA(cudaMemcpyAsync(h->g_img, img, bytes, cudaMemcpyDeviceToDevice, st));
+  B2S_CUDA(cudaGraphLaunch(h->gexec, st));
+  h->launches += h->g_launches;
+  const size_t nl = (size_t)h->n_limit;
+  B2S_CUDA(cudaMemcpyAsync(kpts, h->g_kp, nl * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(desc, h->g_desc, nl * 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (scores) B2S_CUDA(cudaMemcpyAsync(scores, h->g_sc, nl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  B2S_CUDA(cudaMemcpyAsync(n_out, h->g_n, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// Batched extraction of B same-shape frames.  The extractor's ~60 kernels per frame are small (a 320 x 1024 frame does
+// not fill 148 SMs) and latency bound, so the frames of a batch are spread over n_lanes complete extractors (own
+// workspace, own stream) that run CONCURRENTLY: `stream` forks into the lane streams and joins them again, nothing
+// synchronises with the host.  Each lane replays its extraction as a CUDA graph (one launch per frame instead of ~60:
+// the host could not issue the launches of four concurrent lanes fast enough).  Outputs are [B, max_kp, .] slabs;
+// n_out_dev [B].
+extern "C" int b2s_aliked_extract_batch(b2s_aliked* h, const void* const* imgs_dev, int B, int fmt, int H, int W, int row_stride,
+                                        int n_lanes, void* stream, float* kpts, float* desc, float* scores, int32_t* n_out) {
+  if (!h || !imgs_dev || B < 0 || !kpts || !desc || !n_out) { set_error("b2s_aliked_extract_batch: bad argument"); return B2S_EINVAL; }
+  if (B == 0) return 0;
+  B2S_CUDA(cudaSetDevice(h->device));
+  const int want = std::max(1, std::min(std::min(n_lanes > 0 ? n_lanes : 4, B), 8));
+  while ((int)h->lanes.size() < want - 1) {      // lane 0 is this handle on the caller's stream
+    b2s_aliked* l = nullptr;
+    B2S_TRY(b2s_aliked_create(&h->cfg, h->blob.data(), h->blob.size(), h->device, &l));
+    l->desc_renorm_eps = h->desc_renorm_eps;
+    h->lanes.push_back(l);
+    cudaStream_t s; cudaEvent_t e;
+    B2S_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    B2S_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->lane_st.push_back(s); h->lane_ev.push_back(e);
+  }
+  if (!h->ev_fork) B2S_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nl = (size_t)h->n_limit;
+  B2S_CUDA(cudaEventRecord(h->ev_fork, st));
+  for (int l = 1; l < want; ++l) B2S_CUDA(cudaStreamWaitEvent(h->lane_st[l - 1], h->ev_fork, 0));
+  for (int i = 0; i < B; ++i) {
+    const int l = i % want;
+    b2s_aliked* lane = l == 0 ? h : h->lanes[l - 1];
+    lane->desc_renorm_eps = h->desc_renorm_eps;
+    B2S_TRY(aliked_extract_graphed(lane, imgs_dev[i], fmt, H, W, row_stride, l == 0 ? st : h->lane_st[l - 1], kpts + i * nl * 2,
+                                   desc + i * nl * 128, scores ? scores + i * nl : nullptr, n_out + i));
+  }
+  for (int l = 1; l < want; ++l) {
+    B2S_CUDA(cudaEventRecord(h->lane_ev[l - 1], h->lane_st[l - 1]));
+    B2S_CUDA(cudaStreamWaitEvent(st, h->lane_ev[l - 1], 0));
   }
   return 0;
 }
@@ -628,6 +748,19 @@ extern "C" int b2s_aliked_extract_host_finish(b2s_aliked* h, float* desc, float*
     if (scores) B2S_CUDA(cudaMemcpyAsync(scores, h->hscores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
   B2S_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// Device-side copy of the LAST host extraction's results (n rows; valid until the next extraction on this handle) into
+// caller-owned device buffers, enqueued on `stream`: lets a host-API caller keep the features it has just received on
+// the GPU too, so that a following match of the same frame needs no re-upload (features_utils feature cache).
+extern "C" int b2s_aliked_copy_last_features(b2s_aliked* h, float* kpts_dst_dev, float* desc_dst_dev, int n, void* stream) {
+  if (!h || !kpts_dst_dev || !desc_dst_dev || n < 0 || n > h->n_limit || !h->hkp) { set_error("b2s_aliked_copy_last_features: bad argument or no host extraction yet"); return B2S_EINVAL; }
+  if (h->pending) { set_error("b2s_aliked_copy_last_features: an extraction is pending"); return B2S_EINVAL; }
+  B2S_CUDA(cudaSetDevice(h->device));
+  if (n == 0) return 0;
+  B2S_CUDA(cudaMemcpyAsync(kpts_dst_dev, h->hkp, (size_t)n * 2 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  B2S_CUDA(cudaMemcpyAsync(desc_dst_dev, h->hdesc, (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
 

@@ -85,11 +85,9 @@ struct TcGemmCfg {
   static constexpr int TMEM_COLS = NACC * BN <= 64 ? 64 : NACC * BN <= 128 ? 128 : NACC * BN <= 256 ? 256 : 512;   // power of two
 };
 
-// CL > 1: the CL CTAs of a cluster along grid.x compute the CL column tiles of the same 128-row tile.  They share the
-// A operand: every CTA loads 128/CL rows of each A plane (tensor maps with 32-row boxes) and multicasts them into the
-// same smem offset of all CL CTAs, so the L2 -> SM operand traffic per CTA drops from A + W to A/CL + W.  A stage is
-// released to the producers of ALL CTAs (multicast tcgen05.commit, empty barriers count CL arrivals).
-template <int BN, int NP, int CL = 1>
+// (A cluster-multicast variant sharing the A tile between the column tiles of a row tile was measured in round 1 - no
+// gain: the main loop is bound by shared-memory bandwidth, not by the L2 -> SM fill - and removed.)
+template <int BN, int NP>
 __global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __grid_constant__ CUtensorMap mapA1,
                                                  const __grid_constant__ CUtensorMap mapA2,
                                                  const __grid_constant__ CUtensorMap mapW, TcGemmParams p) {
@@ -121,7 +119,7 @@ __global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __
     tc::tma_prefetch_desc(&mapA1); tc::tma_prefetch_desc(&mapA2); tc::tma_prefetch_desc(&mapW);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], CL); }
+    for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
     tc::mbar_init(tmem_full, 1);
     tc::fence_barrier_init();
   }
@@ -132,12 +130,9 @@ __global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __
   }
   pdl_trigger();
   tc::tc_fence_before();
-  if (CL > 1) tc::cluster_sync();      // every CTA's barriers exist before a peer's multicast can signal them
-  else __syncthreads();
+  __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t crank = CL > 1 ? tc::cluster_ctarank() : 0;
-  constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1);
   pdl_wait();            // everything above overlaps the previous kernel's tail; operands are touched only below
   if (threadIdx.x == 0) stamp(1);                    // dependencies resolved
   int w_row = p.w_row0, n_live = p.N;
@@ -177,25 +172,11 @@ __global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __
         const int k0 = kb * Cfg::BK;
 #pragma unroll
         for (int pl = 0; pl < NP; ++pl) {
-          if (CL > 1) {
-            // this CTA's share of the A tile: rows [crank * 128/CL, +128/CL), in 32-row boxes, to every CTA of the cluster
-#pragma unroll
-            for (int q = 0; q < 4 / CL; ++q) {
-              const int r = (int)crank * (128 / CL) + q * 32;
-              uint8_t* dst = st + pl * Cfg::A_BYTES + r * 128;
-              if (k0 < p.K1) tc::tma_load_2d_mc(dst, &mapA1, &full[s], k0, row0 + r + pl * p.plane_rows, cmask);
-              else tc::tma_load_2d_mc(dst, &mapA2, &full[s], k0 - p.K1, row0 + r + pl * p.plane_rows, cmask);
-            }
-          } else if (k0 < p.K1) tc::tma_load_2d(st + pl * Cfg::A_BYTES, &mapA1, &full[s], k0, row0 + pl * p.plane_rows);
+          if (k0 < p.K1) tc::tma_load_2d(st + pl * Cfg::A_BYTES, &mapA1, &full[s], k0, row0 + pl * p.plane_rows);
           else tc::tma_load_2d(st + pl * Cfg::A_BYTES, &mapA2, &full[s], k0 - p.K1, row0 + pl * p.plane_rows);
           if (p.w_plane_rows) tc::tma_load_2d(st + NP * Cfg::A_BYTES + pl * Cfg::B_BYTES, &mapW, &full[s], k0, w_row + n0 + pl * p.w_plane_rows);
           else tc::tma_load_2d(st + NP * Cfg::A_BYTES + pl * Cfg::B_BYTES, &mapW, &full[s], pl * p.K + k0, w_row + n0);
         }
-      }
-      if (CL > 1) {
-        // tail: do not exit while a peer may still read the rows this CTA multicast or signal this CTA's barriers -
-        // wait until every CTA of the cluster has released the last stages
-        for (int kb = nkb > Cfg::STAGES ? nkb - Cfg::STAGES : 0; kb < nkb; ++kb) tc::mbar_wait(&empty[kb % Cfg::STAGES], (kb / Cfg::STAGES) & 1);
       }
     }
   } else if (warp == 1) {
@@ -220,8 +201,7 @@ __global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __
             used |= 1u << acc;
           }
         }
-        if (CL > 1) tc::umma_commit_mc(&empty[s], cmask);   // frees the stage in every CTA of the cluster when these MMAs retire
-        else tc::umma_commit(&empty[s]);
+        tc::umma_commit(&empty[s]);                          // frees the stage when these MMAs retire
         if (kb == nkb - 1) tc::umma_commit(tmem_full);
       }
     }

@@ -522,6 +522,13 @@ extern "C" int b2s_lg_debug_get(b2s_lg* h, const char* name, float* out, size_t 
     }
     src = h->dbg_layers + ((size_t)li * 2 * h->cap + (side ? h->cap : 0)) * 256;
     cnt = (size_t)(side ? h->dbg_n[li] : h->dbg_m[li]) * 256;
+  } else if (s == "ctrl") {
+    // pair 0's device state after the last match (debug mode): LGC_* ints as floats - decision-margin reports read the
+    // per-layer unconfident counts (exit-ratio margins) from it
+    tmp.assign(h->h_ctrl, h->h_ctrl + LGC_INTS);
+    *nout = tmp.size();
+    std::memcpy(out, tmp.data(), std::min(cap_out, tmp.size()) * sizeof(float));
+    return 0;
   } else if (s == "sim") {
     // compacted [m,n]  (pair 0)
     tmp.resize((size_t)h->dbg_simm * h->dbg_simn);

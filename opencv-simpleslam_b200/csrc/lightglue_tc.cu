@@ -139,7 +139,6 @@ struct LgTensorCore {
   float* h1f = nullptr;
   CUtensorMap m_xb, m_ctxb, m_h1b, m_qkv768, m_qkv512;     // box {64, 128}: GEMM A operands, attention Q
   CUtensorMap m_kv768, m_kv512;                            // box {64, 64}: attention K / V tiles (np == 3)
-  CUtensorMap m_xb32, m_ctxb32, m_h1b32;                   // box {64, 32}: A operands of the cluster-multicast GEMMs
   // always fp32-faithful (three planes) whatever the layer precision: the input projection (descriptor planes din) and the
   // assignment head (planes tx of the final state, md of the projected descriptors) - scores decide the match set
   __nv_bfloat16 *din = nullptr, *tx = nullptr, *md = nullptr;
@@ -198,17 +197,6 @@ template <int BN, int NP>
 static void gemm_attr() {
   cudaFuncSetAttribute(k_gemm_tc<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGemmCfg<BN, NP>::SMEM);
 }
-template <int BN, int NP, int CL>
-static void gemm_attr_cl() {
-  cudaFuncSetAttribute(k_gemm_tc<BN, NP, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGemmCfg<BN, NP>::SMEM);
-}
-// measured on B200 (tools/bench_gemm.py): sharing the A tile across a cluster does not shorten these GEMMs (their
-// mainloop is bound by shared-memory bandwidth - MMA operand reads + TMA writes - not by the L2 -> SM fill), so the
-// cluster variant is opt-in (B2S_CLUSTER=1)
-static bool gemm_cluster_enabled() {
-  static const bool on = [] { const char* e = std::getenv("B2S_CLUSTER"); return e && e[0] == '1'; }();
-  return on;
-}
 template <int BN, int NP>
 static void gemmp_attr() {
   cudaFuncSetAttribute(k_gemm_tcp<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcpGemmCfg<BN, NP>::SMEM);
@@ -231,8 +219,6 @@ static void launch_gemm_p(cudaStream_t st, const CUtensorMap& a1, const CUtensor
 static void tc_kernel_attrs() {
   gemm_attr<64, 1>(); gemm_attr<128, 1>(); gemm_attr<64, 3>(); gemm_attr<128, 3>(); gemm_attr<96, 1>(); gemm_attr<96, 3>();
   gemmp_attr<64, 1>(); gemmp_attr<128, 1>(); gemmp_attr<64, 3>(); gemmp_attr<128, 3>(); gemmp_attr<96, 1>(); gemmp_attr<96, 3>();
-  gemm_attr_cl<64, 1, 4>(); gemm_attr_cl<128, 1, 4>(); gemm_attr_cl<128, 1, 2>();
-  gemm_attr_cl<64, 3, 4>(); gemm_attr_cl<128, 3, 4>(); gemm_attr_cl<128, 3, 2>();
   cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
   cudaFuncSetAttribute(k_attn_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM);
 }
@@ -286,9 +272,6 @@ int lgtc_alloc_ws(LgTensorCore* tc, int cap, int pcap) {
   B2S_TRY(make_tmap_bf16_2d(&tc->m_xb, tc->xb, 256, P * R, 512, 64, 128));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_ctxb, tc->ctxb, 256, P * R, 512, 64, 128));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_h1b, tc->h1b, 512, P * R, 1024, 64, 128));
-  B2S_TRY(make_tmap_bf16_2d(&tc->m_xb32, tc->xb, 256, P * R, 512, 64, 32));
-  B2S_TRY(make_tmap_bf16_2d(&tc->m_ctxb32, tc->ctxb, 256, P * R, 512, 64, 32));
-  B2S_TRY(make_tmap_bf16_2d(&tc->m_h1b32, tc->h1b, 512, P * R, 1024, 64, 32));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_qkv768, tc->qkvb, 768, P * R, 1536, 64, 128));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_qkv512, tc->qkvb, 512, P * R, 1024, 64, 128));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_kv768, tc->qkvb, 768, P * R, 1536, 64, 64));
@@ -318,12 +301,6 @@ static int tc_gemm(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& a1, con
   if (tiles <= 0) return 0;
   dim3 grid(w.N / w.BN, tiles);
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
-  // cluster-multicast variant: the column tiles of a row tile share the A operand (32-row-box views of the same buffers)
-  auto a32 = [&](const CUtensorMap& m) -> const CUtensorMap* {
-    return &m == &tc->m_xb ? &tc->m_xb32 : &m == &tc->m_ctxb ? &tc->m_ctxb32 : &m == &tc->m_h1b ? &tc->m_h1b32 : nullptr;
-  };
-  const CUtensorMap *c1 = a32(a1), *c2 = a32(a2);
-  const int cl = (gemm_cluster_enabled() && c1 && c2) ? (grid.x % 4 == 0 ? 4 : (grid.x % 2 == 0 && w.BN == 128 ? 2 : 1)) : 1;
   if (gemm_persistent()) {
     if (tc->np == 1) {
       if (w.BN == 64) launch_gemm_p<64, 1>(st, a1, a2, w.map, p, tiles);
@@ -334,27 +311,14 @@ static int tc_gemm(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& a1, con
       else if (w.BN == 96) launch_gemm_p<96, 3>(st, a1, a2, w.map, p, tiles);
       else launch_gemm_p<128, 3>(st, a1, a2, w.map, p, tiles);
     }
-  } else if (w.BN == 96) {
-    if (tc->np == 1) launch_k(k_gemm_tc<96, 1>, grid, TcGemmCfg<96, 1>::THREADS, TcGemmCfg<96, 1>::SMEM, st, a1, a2, w.map, p);
-    else launch_k(k_gemm_tc<96, 3>, grid, TcGemmCfg<96, 3>::THREADS, TcGemmCfg<96, 3>::SMEM, st, a1, a2, w.map, p);
-  } else if (tc->np == 1) {
-    if (w.BN == 64) {
-      if (cl == 4) launch_k_cluster(k_gemm_tc<64, 1, 4>, grid, TcGemmCfg<64, 1>::THREADS, TcGemmCfg<64, 1>::SMEM, st, 4, *c1, *c2, w.map, p);
-      else launch_k(k_gemm_tc<64, 1>, grid, TcGemmCfg<64, 1>::THREADS, TcGemmCfg<64, 1>::SMEM, st, a1, a2, w.map, p);
-    } else {
-      if (cl == 4) launch_k_cluster(k_gemm_tc<128, 1, 4>, grid, TcGemmCfg<128, 1>::THREADS, TcGemmCfg<128, 1>::SMEM, st, 4, *c1, *c2, w.map, p);
-      else if (cl == 2) launch_k_cluster(k_gemm_tc<128, 1, 2>, grid, TcGemmCfg<128, 1>::THREADS, TcGemmCfg<128, 1>::SMEM, st, 2, *c1, *c2, w.map, p);
-      else launch_k(k_gemm_tc<128, 1>, grid, TcGemmCfg<128, 1>::THREADS, TcGemmCfg<128, 1>::SMEM, st, a1, a2, w.map, p);
-    }
+  } else if (tc->np == 1) {     // one tile per CTA (A/B measurements)
+    if (w.BN == 64) launch_k(k_gemm_tc<64, 1>, grid, TcGemmCfg<64, 1>::THREADS, TcGemmCfg<64, 1>::SMEM, st, a1, a2, w.map, p);
+    else if (w.BN == 96) launch_k(k_gemm_tc<96, 1>, grid, TcGemmCfg<96, 1>::THREADS, TcGemmCfg<96, 1>::SMEM, st, a1, a2, w.map, p);
+    else launch_k(k_gemm_tc<128, 1>, grid, TcGemmCfg<128, 1>::THREADS, TcGemmCfg<128, 1>::SMEM, st, a1, a2, w.map, p);
   } else {
-    if (w.BN == 64) {
-      if (cl == 4) launch_k_cluster(k_gemm_tc<64, 3, 4>, grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, 4, *c1, *c2, w.map, p);
-      else launch_k(k_gemm_tc<64, 3>, grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, a1, a2, w.map, p);
-    } else {
-      if (cl == 4) launch_k_cluster(k_gemm_tc<128, 3, 4>, grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, 4, *c1, *c2, w.map, p);
-      else if (cl == 2) launch_k_cluster(k_gemm_tc<128, 3, 2>, grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, 2, *c1, *c2, w.map, p);
-      else launch_k(k_gemm_tc<128, 3>, grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, a1, a2, w.map, p);
-    }
+    if (w.BN == 64) launch_k(k_gemm_tc<64, 3>, grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, a1, a2, w.map, p);
+    else if (w.BN == 96) launch_k(k_gemm_tc<96, 3>, grid, TcGemmCfg<96, 3>::THREADS, TcGemmCfg<96, 3>::SMEM, st, a1, a2, w.map, p);
+    else launch_k(k_gemm_tc<128, 3>, grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, a1, a2, w.map, p);
   }
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
   if (launches) ++*launches;
@@ -589,9 +553,8 @@ extern "C" int b2s_bench_gemm_tc3(int M, int N, int K, int cl, int iters, float*
   const dim3 grid(N / BN, Mp / 128);
   const size_t ncta = (size_t)grid.x * grid.y;
   B2S_TRY(ar.alloc(&dts, ncta * 6));
-  CUtensorMap ma, ma32, mw;
+  CUtensorMap ma, mw;
   B2S_TRY(make_tmap_bf16_2d(&ma, dA, K, (uint64_t)np * Mp, (uint64_t)K * 2, 64, 128));
-  B2S_TRY(make_tmap_bf16_2d(&ma32, dA, K, (uint64_t)np * Mp, (uint64_t)K * 2, 64, 32));
   B2S_TRY(make_tmap_bf16_2d(&mw, dW, (uint64_t)np * K, N, (uint64_t)np * K * 2, 64, BN));
   tc_kernel_attrs();
   TcGemmParams p = {};
@@ -606,14 +569,8 @@ extern "C" int b2s_bench_gemm_tc3(int M, int N, int K, int cl, int iters, float*
       else if (BN == 64) launch_gemm_p<64, 3>(st, ma, ma, mw, q, Mp / 128);
       else launch_gemm_p<128, 3>(st, ma, ma, mw, q, Mp / 128);
     } else if (BN == 96) launch_k(k_gemm_tc<96, 3>, grid, TcGemmCfg<96, 3>::THREADS, TcGemmCfg<96, 3>::SMEM, st, ma, ma, mw, q);
-    else if (BN == 64) {
-      if (cl == 4) launch_k_cluster(k_gemm_tc<64, 3, 4>, grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, 4, ma32, ma32, mw, q);
-      else launch_k(k_gemm_tc<64, 3>, grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, ma, ma, mw, q);
-    } else {
-      if (cl == 4) launch_k_cluster(k_gemm_tc<128, 3, 4>, grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, 4, ma32, ma32, mw, q);
-      else if (cl == 2) launch_k_cluster(k_gemm_tc<128, 3, 2>, grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, 2, ma32, ma32, mw, q);
-      else launch_k(k_gemm_tc<128, 3>, grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, ma, ma, mw, q);
-    }
+    else if (BN == 64) launch_k(k_gemm_tc<64, 3>, grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, ma, ma, mw, q);
+    else launch_k(k_gemm_tc<128, 3>, grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, ma, ma, mw, q);
   };
   cudaEvent_t e0, e1;
   B2S_CUDA(cudaEventCreate(&e0)); B2S_CUDA(cudaEventCreate(&e1));

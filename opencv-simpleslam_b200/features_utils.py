@@ -38,6 +38,62 @@ def set_gpu_ransac(on: bool = True) -> None:
     _GPU_RANSAC = bool(on)
 
 
+class _FeatureCache:
+    """Device-side copies of the last few extractions, keyed by the descriptor array handed to the caller.  The reference's
+    callers extract a frame and match it one call later (main_revamped.py:283,319-325): `feature_matcher` then finds both
+    frames' features still on the GPU and skips the 2 x 1.06 MB re-upload and the KeyPoint-list -> array conversion.
+    A hit requires the SAME ndarray object (weak reference) with unchanged contents (a strided sample of values is
+    compared) and a keypoint list of the same length whose sampled points agree; anything else falls back to the upload."""
+    KEEP = 4
+
+    def __init__(self):
+        self.entries = []
+
+    @staticmethod
+    def _sample(des):
+        n = len(des)
+        return des[:: max(1, n // 16), ::16].copy() if n else des[:0].copy()
+
+    def put(self, det, kp_arr, kps, des):
+        import weakref
+        n = len(des)
+        if n == 0:
+            return
+        try:
+            kp_dev, de_dev = det.last_features_device(n)
+            ref = weakref.ref(des)
+        except Exception:
+            return
+        self.entries.append({"ref": ref, "ptr": des.ctypes.data, "shape": des.shape, "stamp": self._sample(des), "kp_arr": kp_arr,
+                             "kps_id": id(kps), "kp_dev": kp_dev, "de_dev": de_dev, "dev": det.device})
+        del self.entries[:-self.KEEP]
+
+    def get(self, kps, des, device):
+        if not isinstance(des, np.ndarray):
+            return None
+        for e in reversed(self.entries):
+            if e["ref"]() is des and e["ptr"] == des.ctypes.data and e["shape"] == des.shape and e["dev"] == device:
+                n = len(des)
+                if len(kps) != n or not np.array_equal(self._sample(des), e["stamp"]):
+                    return None
+                ka = e["kp_arr"]
+                if isinstance(kps, KeyPointArray):
+                    ok = kps.pts is ka or np.array_equal(kps.pts[[0, n // 2, n - 1]], ka[[0, n // 2, n - 1]])
+                else:
+                    ok = all(kps[i].pt == (float(ka[i, 0]), float(ka[i, 1])) for i in (0, n // 2, n - 1))
+                return (e["kp_dev"], e["de_dev"]) if ok else None
+        return None
+
+
+_feature_cache = _FeatureCache()
+_last_h2d = 0
+
+
+def last_match_h2d_bytes() -> int:
+    """Bytes the last `feature_matcher` call uploaded (0 when both frames' features were still on the GPU)."""
+    return _last_h2d
+
+
 def __getattr__(name):
     # `from lightglue import LightGlue, ALIKED` / `from lightglue.utils import rbd` of the reference (features_utils.py:8-9),
     # resolved lazily so that ORB/SIFT-only users never load the CUDA library
@@ -138,7 +194,14 @@ def feature_extractor(args, img: np.ndarray, detector):
         # features_utils.py:100  des0 /= (||des0||_2 + 1e-8) runs on the device, fused into the descriptor normalisation
         # and the cv2.KeyPoint list is built while the descriptor head is still running on the GPU
         make = KeyPointArray if getattr(args, "array_native", False) else _convert_lg_kps_to_opencv   # opt-in: SURVEY 8f f2
-        kp0, des0, _ = detector.extract_host_split(img, make, desc_renorm_eps=1e-8)
+        seen = {}
+
+        def on_kp(k):
+            seen["kp"] = k.copy()
+            return make(k)
+        kp0, des0, _ = detector.extract_host_split(img, on_kp, desc_renorm_eps=1e-8)
+        if not getattr(args, "no_feature_cache", False):
+            _feature_cache.put(detector, seen["kp"], kp0, des0)
         return kp0, des0
     kp0, des0 = detector.detectAndCompute(img, None)
     if des0 is None:
@@ -152,10 +215,17 @@ def feature_matcher(args, kp0, kp1, des0, des1, matcher):
             or len(kp0) == 0 or len(kp1) == 0 or len(des0) == 0 or len(des1) == 0):
         return []
     if args.use_lightglue:
+        global _last_h2d
         d0 = des0.detach().cpu().numpy() if isinstance(des0, torch.Tensor) else des0
         d1 = des1.detach().cpu().numpy() if isinstance(des1, torch.Tensor) else des1
+        # frames extracted a call or two ago are still on the GPU (feature cache): no re-upload, no list -> array conversion
+        c0 = _feature_cache.get(kp0, d0, matcher.device)
+        c1 = _feature_cache.get(kp1, d1, matcher.device)
+        k0a, d0a = c0 if c0 is not None else (_kps_to_array(kp0), d0)
+        k1a, d1a = c1 if c1 is not None else (_kps_to_array(kp1), d1)
         # no image_size: upstream then normalises by the keypoint extent (features_utils.py:158-161)
-        raw = matcher.match_host(_kps_to_array(kp0), d0, _kps_to_array(kp1), d1)
+        raw = matcher.match_mixed(k0a, d0a, k1a, d1a)
+        _last_h2d = raw["h2d_bytes"]
         thr = float(getattr(args, "min_conf", 0.7))
         keep = raw["scores"] > np.float32(thr)
         if getattr(args, "array_native", False):

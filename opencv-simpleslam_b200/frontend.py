@@ -128,6 +128,21 @@ class ALIKED(_Module):
                                      self._desc.data_ptr(), self._sc.data_ptr(), self._n.data_ptr()), "b2s_aliked_extract")
         return self._kp, self._desc, self._sc, self._n
 
+    def extract_batch_device(self, imgs, fmt: int, H: int, W: int, row_stride: int = 0, lanes: int = 0, out=None):
+        """B same-shape CUDA images -> slabs (kpts [B,max_kp,2], desc [B,max_kp,128], scores [B,max_kp], n int32 [B]) on the
+        device (b2s_aliked_extract_batch): the frames run concurrently on `lanes` internal extractor lanes forked from /
+        joined into the current stream; no host synchronisation.  `out` = (kpts, desc, scores, n) slabs to fill."""
+        B = len(imgs)
+        dev = self.device
+        if out is None:
+            out = (torch.empty((B, self.n_limit, 2), dtype=torch.float32, device=dev), torch.empty((B, self.n_limit, 128), dtype=torch.float32, device=dev),
+                   torch.empty((B, self.n_limit), dtype=torch.float32, device=dev), torch.zeros((B,), dtype=torch.int32, device=dev))
+        ptrs = (C.c_void_p * max(B, 1))(*[t.data_ptr() for t in imgs])
+        st = torch.cuda.current_stream(dev).cuda_stream
+        check(lib.b2s_aliked_extract_batch(self._handle, ptrs, B, fmt, H, W, row_stride, int(lanes), st, out[0].data_ptr(), out[1].data_ptr(),
+                                           out[2].data_ptr() if out[2] is not None else None, out[3].data_ptr()), "b2s_aliked_extract_batch")
+        return out
+
     def _finish(self, H, W):
         self._n_host.copy_(self._n, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
@@ -200,6 +215,15 @@ class ALIKED(_Module):
             sc = np.empty((max(n.value, 1),), np.float32)
             check(lib.b2s_aliked_extract_host_finish(self._handle, de.ctypes.data, sc.ctypes.data), "b2s_aliked_extract_host_finish")
         return res, de[:n.value], sc[:n.value]
+
+    def last_features_device(self, n: int):
+        """CUDA copies (kpts [n,2], desc [n,128]) of what the last extract_host* call returned (b2s_aliked_copy_last_features)."""
+        with torch.cuda.device(self.device):
+            kp = torch.empty((n, 2), dtype=torch.float32, device=self.device)
+            de = torch.empty((n, 128), dtype=torch.float32, device=self.device)
+            check(lib.b2s_aliked_copy_last_features(self._handle, kp.data_ptr(), de.data_ptr(), int(n),
+                                                    torch.cuda.current_stream(self.device).cuda_stream), "b2s_aliked_copy_last_features")
+        return kp, de
 
     def debug(self, name: str) -> np.ndarray:
         n = C.c_size_t(0)
@@ -354,6 +378,43 @@ class LightGlue(_Module):
             out = self.match_batch_packed(kp, de, cu, pi, pj, stride, max_batch)
             out["_keepalive"] = (kp, de)       # the packed inputs must outlive the enqueued kernels
             return out
+
+    def match_mixed(self, k0, d0, k1, d1):
+        """The drop-in's matching call: each side is either host numpy (k [m,2], d [m,128] f32: uploaded) or CUDA tensors
+        already on this device (a frame whose features the feature cache kept on the GPU: no upload).  One packed D2H of
+        (count, executed layers, matches, scores) through pinned memory, one synchronisation.  Returns
+        {'matches' int32 [K,2], 'scores' f32 [K], 'stop', 'h2d_bytes'}."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            h2d = 0
+            ts = []
+            for a in (k0, d0, k1, d1):
+                if isinstance(a, torch.Tensor):
+                    ts.append(a)
+                else:
+                    a = np.ascontiguousarray(a, np.float32)
+                    h2d += a.nbytes
+                    ts.append(torch.from_numpy(a).to(dev, non_blocking=True))
+            k0, d0, k1, d1 = ts
+            m, n = int(k0.shape[0]), int(k1.shape[0])
+            cap = max(min(m, n), 1)
+            if getattr(self, "_mx_cap", 0) < cap:
+                self._mx_cap = max(cap, 2048)
+                self._mx_dev = torch.zeros(4 + 3 * self._mx_cap, dtype=torch.int32, device=dev)     # n, stop, -, - | matches | scores
+                self._mx_pin = torch.zeros(4 + 3 * self._mx_cap, dtype=torch.int32).pin_memory()
+            o, c = self._mx_dev, self._mx_cap
+            base = o.data_ptr()
+            st = torch.cuda.current_stream(dev)
+            check(lib.b2s_lightglue_match(self._handle, k0.data_ptr(), d0.data_ptr(), m, k1.data_ptr(), d1.data_ptr(), n, None, None,
+                                          st.cuda_stream, base + 16, base + 16 + 8 * c, base, base + 4, None, None, None, None, None, None),
+                  "b2s_lightglue_match")
+            self._mx_pin.copy_(o, non_blocking=True)
+            st.synchronize()
+            hp = self._mx_pin.numpy()
+            nm, stop = int(hp[0]), int(hp[1])
+            matches = hp[4: 4 + 2 * nm].reshape(nm, 2).copy()
+            scores = hp[4 + 2 * c: 4 + 2 * c + nm].view(np.float32).copy()
+            return {"matches": matches, "scores": scores, "stop": stop, "h2d_bytes": h2d}
 
     def match_host(self, k0, d0, k1, d1, size0=None, size1=None, full=False):
         """One C-ABI call with host (numpy f32) buffers: b2s_lightglue_match_host."""

@@ -110,6 +110,27 @@ def test_untruncated_raster_order():
     assert rel_err(de[common], fo["descriptors"][0].numpy()[idx[common]]) < 1e-3
 
 
+def test_extract_batch_equals_per_frame_extraction():
+    """b2s_aliked_extract_batch (frames spread over concurrent extractor lanes, forked from / joined into the caller's
+    stream) gives bit for bit what per-frame b2s_aliked_extract calls give."""
+    from b200slam import _lib
+    _, det = _pair(max_kp=700)
+    Hh, Ww = 240, 320
+    imgs = [torch.from_numpy(synth.frame(40 + t, Hh, Ww)).cuda() for t in range(7)]
+    ref = []
+    for im in imgs:
+        kp, de, sc, n = det.extract_device(im, _lib.IMG_BGR_U8_HWC, Hh, Ww, 3 * Ww)
+        torch.cuda.synchronize()
+        k = int(n)
+        ref.append((kp[:k].clone(), de[:k].clone(), sc[:k].clone()))
+    for lanes in (1, 3, 4):
+        kp, de, sc, n = det.extract_batch_device(imgs, _lib.IMG_BGR_U8_HWC, Hh, Ww, 3 * Ww, lanes=lanes)
+        torch.cuda.synchronize()
+        for i, (rk, rd, rs) in enumerate(ref):
+            k = int(n[i])
+            assert k == len(rk) and torch.equal(kp[i, :k], rk) and torch.equal(de[i, :k], rd) and torch.equal(sc[i, :k], rs), (lanes, i)
+
+
 def test_degenerate_images_do_not_crash():
     _, det = _pair(max_kp=256)
     for img in (np.zeros((64, 48, 3), np.uint8), np.full((100, 333, 3), 255, np.uint8)):

@@ -117,6 +117,29 @@ def test_reference_self_consistency_fixture(pipelines):
     assert all(0 <= m.queryIdx < len(kp1m) and 0 <= m.trainIdx < len(kp2m) for m in mm + md)
 
 
+def test_feature_cache_path_equals_upload_path(pipelines):
+    """feature_matcher finds the features of frames extracted just before still on the GPU (features_utils._FeatureCache):
+    no upload, same matches as the plain host-buffer call; a modified descriptor array or keypoint list is a miss."""
+    args, fu, ofu, det, mat = pipelines[:5]
+    i0, i1 = synth.frame(50, 376, 1241), synth.frame(51, 376, 1241)
+    g0, g1 = fu.feature_extractor(args, i0, det), fu.feature_extractor(args, i1, det)
+    m_cached = fu.feature_matcher(args, g0[0], g1[0], g0[1], g1[1], mat)
+    assert fu.last_match_h2d_bytes() == 0
+    ref = mat.match_host(fu._kps_to_array(g0[0]), g0[1], fu._kps_to_array(g1[0]), g1[1])
+    keep = ref["scores"] > np.float32(0.7)
+    assert [(m.queryIdx, m.trainIdx) for m in m_cached] == [tuple(r) for r in ref["matches"][keep].tolist()] and len(m_cached) > 100
+    # copies of the same values are different objects: upload path, same result
+    m_copy = fu.feature_matcher(args, list(g0[0]), g1[0], g0[1].copy(), g1[1], mat)
+    assert fu.last_match_h2d_bytes() == len(g0[0]) * 130 * 4
+    assert [(m.queryIdx, m.trainIdx) for m in m_copy] == [(m.queryIdx, m.trainIdx) for m in m_cached]
+    # in-place modification of a cached array is detected (contents sample) -> upload of the modified values
+    g1[1][:] = g1[1][::-1].copy()
+    m_mod = fu.feature_matcher(args, g0[0], g1[0], g0[1], g1[1], mat)
+    assert fu.last_match_h2d_bytes() == len(g1[0]) * 130 * 4
+    ref2 = mat.match_host(fu._kps_to_array(g0[0]), g0[1], fu._kps_to_array(g1[0]), g1[1])
+    assert [(m.queryIdx, m.trainIdx) for m in m_mod] == [tuple(r) for r in ref2["matches"][ref2["scores"] > np.float32(0.7)].tolist()]
+
+
 def test_empty_input_guards(pipelines):
     args, fu, mat = pipelines[0], pipelines[1], pipelines[4]
     kp = [cv2.KeyPoint(1.0, 2.0, 1)]; de = np.zeros((1, 128), np.float32)
