@@ -304,6 +304,7 @@ def run_ours(args):
     ncpu = os.cpu_count() or 1
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
         # one process per GPU on a shared host: keep each rank on its own slice of the cores (the e2e leg is host bound)
         per = max(1, ncpu // world)
@@ -450,7 +451,7 @@ def run_ours(args):
         "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.precision != "bf16" else "bf16", "data": "synthetic",
         "config": workload_config(src_a, src_l),
-        "run": {"pairs_per_step": P, "batch": f"{P} frames per batched extraction ({args.lanes or 4} concurrent lanes), {P} pairs per batched matcher launch sequence",
+        "run": {"pairs_per_step": P, "batch": f"{P} frames per batched extraction ({args.lanes or 4} concurrent CUDA-graph lanes), {P} pairs per batched matcher launch sequence",
                 "l2": "flushed before every step (256 MiB write on the extraction stream, inside the timed region)",
                 "pipeline": "2 CUDA streams: extraction of step s+1 overlaps the matching of step s; keypoint counts stay on the device (no host sync in the timed region)",
                 "mean_matches_per_pair": mean_matches, "stop_layers_last_step": stops, "precision": args.precision,
@@ -516,7 +517,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("B2S_PRECISION", "fp32"), choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("B2S_BENCH_BATCH", "8")), help="pairs per step = per batched launch sequence")
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("B2S_BENCH_LANES", "4")), help="concurrent extractor lanes")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("B2S_BENCH_LANES", "8")), help="concurrent extractor lanes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the bf16 / adaptive side measurements")
     ap.add_argument("--no-window", action="store_true", help="skip the config-3 keyframe-window sub-record")

@@ -4,6 +4,7 @@
 #include "aliked_kernels.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tcp.cuh"
 #include "conv_tc.cuh"
 
 #include <algorithm>
@@ -250,7 +251,14 @@ int tc_gemm(b2s_aliked* h, cudaStream_t st, const CUtensorMap& a, int plane_rows
   p.plane_rows = plane_rows; p.m_dev = n_dev; p.m_mult = mult;
   if (out_f32) { p.epi = TC_EPI_F32; p.out_f32 = out_f32; p.ld_f32 = ldc; }
   else { p.epi = TC_EPI_BF16; p.out_bf16 = out_planes; p.ld_bf16 = ldc; p.out_plane = out_plane; }
-  launch_k(k_gemm_tc<64, 3>, dim3(cdiv(w.N, 64), p.tiles_per_seg), TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, a, a, w.map, p);
+  const int total = cdiv(w.N, 64) * p.tiles_per_seg;
+  if (total >= 2 * 148) {
+    // many tiles (SDDH sf_conv: 32768 sample rows): the persistent tile scheduler overlaps every tile's epilogue (this
+    // K = 128 GEMM is all epilogue) with the next tile's main loop
+    launch_k(k_gemm_tcp<64, 3>, dim3(148), TcpGemmCfg<64, 3>::THREADS, TcpGemmCfg<64, 3>::SMEM, st, a, a, w.map, p, p.tiles_per_seg);
+  } else {
+    launch_k(k_gemm_tc<64, 3>, dim3(cdiv(w.N, 64), p.tiles_per_seg), TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, a, a, w.map, p);
+  }
   ++h->launches;
   B2S_LAUNCH_CHECK();
   return 0;
@@ -352,6 +360,7 @@ extern "C" int b2s_aliked_create(const b2s_aliked_cfg* cfg, const void* weights,
   h->M = cfg->model == 1 ? 32 : 16;
   h->n_limit = cfg->max_kp > 0 ? cfg->max_kp : 20000;
   cudaFuncSetAttribute(k_gemm_tc<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGemmCfg<64, 3>::SMEM);
+  cudaFuncSetAttribute(k_gemm_tcp<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcpGemmCfg<64, 3>::SMEM);
   cudaFuncSetAttribute(k_dcn_offcol<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 18 * 9 * 64 * (int)sizeof(float));
   cudaFuncSetAttribute(k_dcn_offcol<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 18 * 9 * 128 * (int)sizeof(float));
   cudaFuncSetAttribute(k_conv3x3_tc<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<16, 16>::SMEM);

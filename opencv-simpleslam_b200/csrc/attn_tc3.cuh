@@ -39,6 +39,7 @@ struct Attn3Params {
   __nv_bfloat16* out; int ldo; size_t out_plane;   // ctx planes [3][2*cap, 256] bf16
   const int* ctrl; int cross;
   unsigned long long* stats;       // nullable: stats[cross] += nq * nk of every live problem
+  int pv_issuers;                  // 1: one thread issues every P V product; 2: one thread per softmax group
   int trace_cta;                   // CTA to trace: x | y << 8 | z << 16
   long long* trace;                // nullable profiling hook (b2s_trace_attn_tc3): clock64 stamps of CTA (0,0,0), [role][tile][event]
 };
@@ -170,9 +171,11 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
       using Terms = tc::PlaneTerms<A3_NP>;
       constexpr uint32_t idesc_s = tc::idesc_bf16(128, 128, 0, 0);   // S pair: A = Q (K-major), B = 128 keys (K-major)
       const uint32_t q_addr = tc::smem_u32(sQ);
-      auto issue_s_pair = [&](int jp) {                              // tiles 2jp (-> S[0]) and 2jp + 1 (-> S[1])
-        const int b = jp % A3_KSLOTS, ph = (jp / A3_KSLOTS) & 1;
-        tc::mbar_wait(&k_full[b], ph);
+      // (the barrier that completes LAST is waited on last: a wait on an already-complete mbarrier still costs ~100
+      //  cycles, which must not sit between the late event and the first MMA)
+      auto wait_k = [&](int jp) { tc::mbar_wait(&k_full[jp % A3_KSLOTS], (jp / A3_KSLOTS) & 1); };
+      auto issue_s_pair = [&](int jp) {                              // tiles 2jp (-> S[0]) and 2jp + 1 (-> S[1]); K pair jp has landed
+        const int b = jp % A3_KSLOTS;
         tc::tc_fence_after();
         stamp(0, jp, 0);                                   // K pair landed, S pair issue starts
         const uint32_t k_addr = tc::smem_u32(sK + b * A3_KSLOT);
@@ -190,29 +193,35 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
         stamp(0, jp, 1);                                   // S pair issued
       };
       tc::mbar_wait(q_full, 0);
+      wait_k(0);
       issue_s_pair(0);
       const int npairs = (nt + 1) >> 1;
       for (int jp = 0; jp + 1 < npairs; ++jp) {
         const int ph = jp & 1;                // both groups have their score tiles in registers: next pair can start
+        wait_k(jp + 1);                       // landed long ago (requested one pair ahead)
         tc::mbar_wait(&s_free[0], ph);
         tc::mbar_wait(&s_free[1], ph);
         stamp(0, jp, 6);
         issue_s_pair(jp + 1);
       }
     }
-  } else if (warp == 10) {
-    // ===== second MMA issuer: the P V products.  An issuing thread is blocked for about as long as its MMAs execute
+  } else if (warp == 10 || (warp == 11 && p.pv_issuers == 2)) {
+    // ===== second (and third) MMA issuer: the P V products.  An issuing thread is blocked for about as long as its MMAs execute
     //       and every commit / barrier round trip costs it a few hundred cycles, so with ONE issuer the tensor pipe idles
     //       between the S pair and the two P V groups of a tile pair (measured: 3440 busy of 4735 cycles per pair).  The
     //       score and the P V MMAs touch disjoint tensor-memory columns and are ordered by mbarriers only (s_free / p_full /
-    //       o_full), so they can be issued from two threads whose gaps overlap. =====
+    //       o_full), so they can be issued from two threads whose gaps overlap.  With pv_issuers == 2 the two softmax
+    //       groups' P V products come from two threads as well (warp 10: even key tiles, warp 11: odd ones): every
+    //       issue batch pays ~450 cycles of barrier round trips before its first MMA (trace: P published -> P V start),
+    //       and the pipe idles whenever all issuers are in that phase at once. =====
     if (tc::elect_one()) {
       using Terms = tc::PlaneTerms<A3_NP>;
       constexpr uint32_t idesc_o = tc::idesc_bf16(128, 64, 0, 1);    // PV: A = P (tensor memory), B = V (MN-major)
-      for (int j = 0; j < nt; ++j) {
+      const int jstep = p.pv_issuers == 2 ? 2 : 1;
+      for (int j = (p.pv_issuers == 2 ? warp - 10 : 0); j < nt; j += jstep) {
         const int b = j % A3_SLOTS, ph = (j / A3_SLOTS) & 1, g = j & 1;
-        tc::mbar_wait(&p_full[g], (j >> 1) & 1);      // P of tile j is in tensor memory
-        tc::mbar_wait(&v_full[b], ph);
+        tc::mbar_wait(&v_full[b], ph);                // V tile j landed (early)
+        tc::mbar_wait(&p_full[g], (j >> 1) & 1);      // P of tile j is in tensor memory (the late event: waited on last)
         tc::tc_fence_after();
         stamp(0, j >> 1, 2 + 2 * (j & 1));
         const uint32_t v_addr = tc::smem_u32(sV + b * A3_SLOT);

@@ -216,6 +216,11 @@ static void launch_gemm_p(cudaStream_t st, const CUtensorMap& a1, const CUtensor
   const int total = m_tiles * ((p.N + BN - 1) / BN);
   launch_k(k_gemm_tcp<BN, NP>, dim3(std::min(total, sm_count())), TcpGemmCfg<BN, NP>::THREADS, TcpGemmCfg<BN, NP>::SMEM, st, a1, a2, w, p, m_tiles);
 }
+// P V products of the fp32 attention kernel issued by one thread per softmax group (2) or by a single thread (1)
+static int attn_pv_issuers() {
+  static const int n = [] { const char* e = std::getenv("B2S_ATTN_PV_ISSUERS"); return (e && e[0] == '1') ? 1 : 2; }();
+  return n;
+}
 static void tc_kernel_attrs() {
   gemm_attr<64, 1>(); gemm_attr<128, 1>(); gemm_attr<64, 3>(); gemm_attr<128, 3>(); gemm_attr<96, 1>(); gemm_attr<96, 3>();
   gemmp_attr<64, 1>(); gemmp_attr<128, 1>(); gemmp_attr<64, 3>(); gemmp_attr<128, 3>(); gemmp_attr<96, 1>(); gemmp_attr<96, 3>();
@@ -341,6 +346,7 @@ static int tc_attention(LgTensorCore* tc, cudaStream_t st, int ld, int nseg, int
     launch_k(k_attn_tc, grid, ATC_THREADS, ATC_SMEM, st, ld == 768 ? tc->m_qkv768 : tc->m_qkv512, ap);
   } else {
     Attn3Params ap = {};
+    ap.pv_issuers = attn_pv_issuers();
     ap.cap = tc->cap; ap.qcol = qcol; ap.kcol = kcol; ap.vcol = vcol; ap.cross = cross;
     ap.plane_rows = 2 * tc->pcap * tc->cap;
     ap.scale_log2e = scale_log2e; ap.out = tc->ctxb; ap.ldo = 256; ap.out_plane = (size_t)ap.plane_rows * 256; ap.ctrl = tc->ctrl;
@@ -615,7 +621,7 @@ static int run_attn(int np, const std::vector<__nv_bfloat16>& buf, int R, const 
   a1.qcol = 0; a1.kcol = 256; a1.vcol = 512; a1.prob[0] = prob[0]; a1.prob[1] = prob[1]; a1.scale_log2e = sc; a1.out = dctx; a1.ldo = 256;
   Attn3Params a3 = {};
   a3.qcol = 0; a3.kcol = 256; a3.vcol = 512; a3.prob[0] = prob[0]; a3.prob[1] = prob[1]; a3.scale_log2e = sc; a3.out = dctx; a3.ldo = 256;
-  a3.plane_rows = R; a3.out_plane = (size_t)R * 256;
+  a3.plane_rows = R; a3.out_plane = (size_t)R * 256; a3.pv_issuers = attn_pv_issuers();
   long long* dtrace = nullptr;
   if (trace_out) { B2S_TRY(ar.alloc(&dtrace, (size_t)3 * 64 * 8)); B2S_CUDA(cudaMemset(dtrace, 0, 3 * 64 * 8 * sizeof(long long))); }
   const dim3 grid(cdiv(maxq, 128), 4, nz);
