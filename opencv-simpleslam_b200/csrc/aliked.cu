@@ -577,7 +577,9 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
 static int aliked_extract_graphed(b2s_aliked* h, const void* img, int fmt, int H, int W, int row_stride, cudaStream_t st,
                                   float* kpts, float* desc, float* scores, int32_t* n_out) {
   static const bool off = [] { const char* e = std::getenv("B2S_ALIKED_GRAPH"); return e && e[0] == '0'; }();
-  if (off || h->g_failed) return b2s_aliked_extract(h, img, fmt, H, W, row_stride, st, kpts, desc, scores, n_out);
+  // the legacy default stream cannot be captured: lane 0 of a caller that works on it stays on the eager launch sequence
+  const bool legacy = st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread;
+  if (off || legacy || h->g_failed) return b2s_aliked_extract(h, img, fmt, H, W, row_stride, st, kpts, desc, scores, n_out);
   const size_t bytes = fmt == B2S_IMG_BGR_U8_HWC ? (size_t)(row_stride > 0 ? row_stride : 3 * W) * H : (size_t)3 * H * W * sizeof(float);
   if (!h->gexec || h->g_fmt != fmt || h->g_H != H || h->g_W != W || h->g_stride != row_stride || h->g_eps != h->desc_renorm_eps) {
     if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }

@@ -307,14 +307,17 @@ static int tc_gemm(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& a1, con
   dim3 grid(w.N / w.BN, tiles);
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
   if (gemm_persistent()) {
+    // (128-wide tiles for the N = 256 / 768 GEMMs of a large batch were measured: no gain over the 64 / 96-wide defaults)
+    const int BN = w.BN;
+    const CUtensorMap& wm = w.map;
     if (tc->np == 1) {
-      if (w.BN == 64) launch_gemm_p<64, 1>(st, a1, a2, w.map, p, tiles);
-      else if (w.BN == 96) launch_gemm_p<96, 1>(st, a1, a2, w.map, p, tiles);
-      else launch_gemm_p<128, 1>(st, a1, a2, w.map, p, tiles);
+      if (BN == 64) launch_gemm_p<64, 1>(st, a1, a2, wm, p, tiles);
+      else if (BN == 96) launch_gemm_p<96, 1>(st, a1, a2, wm, p, tiles);
+      else launch_gemm_p<128, 1>(st, a1, a2, wm, p, tiles);
     } else {
-      if (w.BN == 64) launch_gemm_p<64, 3>(st, a1, a2, w.map, p, tiles);
-      else if (w.BN == 96) launch_gemm_p<96, 3>(st, a1, a2, w.map, p, tiles);
-      else launch_gemm_p<128, 3>(st, a1, a2, w.map, p, tiles);
+      if (BN == 64) launch_gemm_p<64, 3>(st, a1, a2, wm, p, tiles);
+      else if (BN == 96) launch_gemm_p<96, 3>(st, a1, a2, wm, p, tiles);
+      else launch_gemm_p<128, 3>(st, a1, a2, wm, p, tiles);
     }
   } else if (tc->np == 1) {     // one tile per CTA (A/B measurements)
     if (w.BN == 64) launch_k(k_gemm_tc<64, 1>, grid, TcGemmCfg<64, 1>::THREADS, TcGemmCfg<64, 1>::SMEM, st, a1, a2, w.map, p);

@@ -139,6 +139,7 @@ class ALIKED(_Module):
                    torch.empty((B, self.n_limit), dtype=torch.float32, device=dev), torch.zeros((B,), dtype=torch.int32, device=dev))
         ptrs = (C.c_void_p * max(B, 1))(*[t.data_ptr() for t in imgs])
         st = torch.cuda.current_stream(dev).cuda_stream
+        assert out[0].is_contiguous() and out[1].is_contiguous() and out[3].is_contiguous()
         check(lib.b2s_aliked_extract_batch(self._handle, ptrs, B, fmt, H, W, row_stride, int(lanes), st, out[0].data_ptr(), out[1].data_ptr(),
                                            out[2].data_ptr() if out[2] is not None else None, out[3].data_ptr()), "b2s_aliked_extract_batch")
         return out

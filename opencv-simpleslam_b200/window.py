@@ -15,7 +15,7 @@ from . import _lib, sharding
 
 
 def match_keyframe_window(frames: List[torch.Tensor], det, mat, H: int, W: int, rank: int = 0, world: int = 1, group=None,
-                          max_batch: int = 0, timing: dict | None = None
+                          max_batch: int = 0, timing: dict | None = None, lanes: int = 8
                           ) -> Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
     """frames: u8 BGR HWC CUDA tensors of ALL keyframes of the window (each rank only touches its own).
     Returns {(i, j): (matches int32 [stride,2], scores f32 [stride], n int32 [])} for the pairs this rank owns; tensors
@@ -25,9 +25,12 @@ def match_keyframe_window(frames: List[torch.Tensor], det, mat, H: int, W: int, 
     mine = sharding.frames_of_rank(n_kf, rank, world)
     slots = -(-n_kf // world)                               # same number of slots on every rank (padded with count 0)
     rec = sharding.WindowRecord(slots, max_kp, dev)
-    for s, f in enumerate(mine):
-        k, d, _, n = det.extract_device(frames[f], _lib.IMG_BGR_U8_HWC, H, W, 3 * W)
-        rec.put(s, k, d, n)
+    if mine:
+        # this rank's keyframes in ONE batched extraction (concurrent extractor lanes) straight into the record buffer
+        cnt = torch.zeros((len(mine),), dtype=torch.int32, device=dev)
+        det.extract_batch_device([frames[f] for f in mine], _lib.IMG_BGR_U8_HWC, H, W, 3 * W, lanes=lanes,
+                                 out=(rec.kpts[:len(mine)], rec.desc[:len(mine)], None, cnt))
+        rec.counts[:len(mine)].copy_(cnt)                      # int32 -> exact float32
     if timing is not None:
         timing["gather_start"] = torch.cuda.Event(enable_timing=True); timing["gather_end"] = torch.cuda.Event(enable_timing=True)
         timing["gather_start"].record()

@@ -45,16 +45,21 @@ def conv_and_match(batch=False):
     print("extract", f0["keypoints"].shape[1], f1["keypoints"].shape[1])
     for prec in ("fp32", "bf16"):
         mat = frontend.LightGlue(weights=weights.synthetic_lightglue_state(token_bias=1.4, token_gain=6.0, match_bias=-5.0, match_gain=4.0),
-                                 device="cuda:0", precision=prec, max_kp=512)
+                                 device="cuda:0", precision=prec, max_kp=512, filter_threshold=1e-6)
         r = mat({"image0": f0, "image1": f1})
         k0, d0, k1, d1, _ = noisy_copy_pair(300, 280, seed=1)
         r2 = mat.match_host(k0.numpy(), d0.numpy(), k1.numpy(), d1.numpy(), full=True)
         print(prec, "matches", len(r["matches"][0]), len(r2["matches"]), "stop", r2["stop"])
-        if batch and hasattr(mat, "match_batch_device"):
+        if batch:
             feats = [noisy_copy_pair(200 + 40 * i, 200 + 40 * i, seed=20 + i)[:2] for i in range(3)]
-            out = mat.match_batch_device([f[0].cuda() for f in feats], [f[1].cuda() for f in feats], [(0, 1), (0, 2), (1, 2)])
+            out = mat.match_batch_device([f[0].cuda() for f in feats], [f[1].cuda() for f in feats], [(0, 1), (0, 2), (1, 2), (2, 0)])
             torch.cuda.synchronize()
-            print(prec, "batch", [int(v) for v in out["n"].cpu()])
+            print(prec, "batch", [int(v) for v in out["n"].cpu()], "stop", [int(v) for v in out["stop"].cpu()])
+    if batch:
+        imgs = [torch.from_numpy(synth.frame(t, Hh, Ww)).cuda() for t in range(3)]
+        kp, de, sc, n = det.extract_batch_device(imgs, _lib.IMG_BGR_U8_HWC, Hh, Ww, 3 * Ww, lanes=2)
+        torch.cuda.synchronize()
+        print("extract_batch", n.cpu().tolist())
 
 
 if what in ("gemm", "all"):
