@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - ALIKED+LightGlue frame-pairs/sec on synthetic KITTI-shaped frames (BASELINE.json).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16] [--batch P]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|fp32x3|bf16] [--batch P]
 
 Unit of work (BASELINE config 2): one frame-pair of the steady-state stream = 1 ALIKED extraction (frame t) + 1 LightGlue
 match (t-1, t), 1241x376, 2048 kp.  A "step" is P = --batch consecutive pairs: P frames go through ONE batched extraction
@@ -246,6 +246,11 @@ class Stream:
         torch.cuda.synchronize()
         wall = time.perf_counter() - wall0
         launches = self.det.launches + matcher.launches - l0
+        # precision fp32 = fp16x2 operand planes: a batch that left the fp16 range would report n = LG_RANGE (-2) and need
+        # the bf16x3 re-run - that must not happen silently inside a timed region
+        bad = sum(int((o["n"] < 0).sum()) for o in self.outs if o is not None)
+        if bad:
+            raise RuntimeError(f"{bad} pairs of the timed region left the fp16 operand range (LG_RANGE): re-run with --precision fp32x3")
         return e0.elapsed_time(e1), launches, res["n"].cpu().tolist(), res["stop"].cpu().tolist(), wall
 
 
@@ -438,7 +443,7 @@ def run_ours(args):
     gemm_s = kp_["gemm_ms"] * 1e-3
     alg = 1024.0 * kp_["self_w"] + 768.0 * kp_["cross_w"]
     executed = 1024.0 * (kp_["self_w"] + kp_["cross_w"])
-    issue_mult = {"fp32": 6, "bf16": 1}[args.precision]
+    issue_mult = {"fp32": 3, "fp32x3": 6, "bf16": 1}[args.precision]
     achieved = alg / attn_s / 1e12 if attn_s > 0 else None
     gemm_ach = kp_["gemm_alg"] / gemm_s / 1e12 if gemm_s > 0 else None
     ncu = {}
@@ -455,7 +460,9 @@ def run_ours(args):
                 "l2": "flushed before every step (256 MiB write on the extraction stream, inside the timed region)",
                 "pipeline": "2 CUDA streams: extraction of step s+1 overlaps the matching of step s; keypoint counts stay on the device (no host sync in the timed region)",
                 "mean_matches_per_pair": mean_matches, "stop_layers_last_step": stops, "precision": args.precision,
-                "arithmetic": {"fp32": "fp32-faithful on tcgen05: operands as three bf16 planes, six cross products, fp32 accumulate",
+                "arithmetic": {"fp32": "fp32-faithful on tcgen05: operands as two fp16 planes (x = h0 + 2^-11 h1), three cross products, fp32 accumulate; "
+                                       "device-side fp16 range check, flagged batches re-run on bf16x3 planes",
+                               "fp32x3": "fp32-faithful on tcgen05: operands as three bf16 planes, six cross products, fp32 accumulate",
                                "bf16": "bf16 operands on tcgen05, fp32 accumulate"}[args.precision],
                 "launches_per_pair": launches / (K * P)},
         "gpu_launches": int(launches),
@@ -464,7 +471,8 @@ def run_ours(args):
                 "api": "features_utils.feature_extractor + feature_matcher, one pair per call (host numpy in, cv2 lists out)",
                 "matches_last_pair": e2e_matches},
         "roofline": {"bound": "tensor",
-                     "kernel": {"fp32": "k_attn_tc3 (fp32 on bf16x3 planes, tcgen05)", "bf16": "k_attn_tc (bf16, tcgen05)"}[args.precision],
+                     "kernel": {"fp32": "k_attn_tc3<2> (fp32 on fp16x2 planes, tcgen05)", "fp32x3": "k_attn_tc3<3> (fp32 on bf16x3 planes, tcgen05)",
+                                "bf16": "k_attn_tc (bf16, tcgen05)"}[args.precision],
                      "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                      "frac": (achieved / tensor_peak) if achieved else None,
                      "traffic": ncu.get("dram_bytes_per_launch"),
@@ -515,7 +523,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("B2S_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("B2S_PRECISION", "fp32"), choices=["fp32", "fp32x3", "bf16"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("B2S_BENCH_BATCH", "8")), help="pairs per step = per batched launch sequence")
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("B2S_BENCH_LANES", "8")), help="concurrent extractor lanes")
     ap.add_argument("--no-cpu-baseline", action="store_true")

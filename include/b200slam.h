@@ -37,13 +37,19 @@ enum {
   B2S_ESIZE = -5     /* input larger than the handle supports */
 };
 
-/* Arithmetic of the LightGlue transformer layers.
- *   B2S_FP32      fp32-faithful on the tensor cores: every fp32 operand is carried as three bf16
- *                 planes and each contraction issues the six significant cross products into an fp32
- *                 TMEM accumulator (results agree with an fp32 FMA path to rounding level);
+/* Arithmetic of the LightGlue matcher.
+ *   B2S_FP32      fp32-faithful on the tensor cores, fast form: every fp32 operand is carried as TWO fp16 planes
+ *                 x = h0 + 2^-11 h1 (22 significant bits at any magnitude) and each contraction issues the three
+ *                 significant cross products into fp32 TMEM accumulators (operand error below the fp32 rounding noise
+ *                 of the accumulation; identical match sets vs an fp32 reference in every parity test).  fp16 limits
+ *                 the operand range to |x| < 65504: every producer checks it on the device, and a launch sequence
+ *                 that left the range is re-run on the B2S_FP32X3 engine (b2s_lg_fallback; the host entry points do
+ *                 so themselves, device entry points report n_matches = B2S_LG_RANGE);
+ *   B2S_FP32X3    fp32-faithful, any range: three bf16 planes, six cross products (twice the tensor-core work);
  *   B2S_BF16      operands rounded once to bf16 (fastest; >= 99 % match-set agreement).
- * The input projection and the assignment head are fp32-faithful in both modes. */
-enum { B2S_FP32 = 0, B2S_BF16 = 1 };
+ * The input projection and the assignment head are fp32-faithful in every mode. */
+enum { B2S_FP32 = 0, B2S_BF16 = 1, B2S_FP32X3 = 2 };
+enum { B2S_LG_RANGE = -2 };   /* n_matches of a pair whose launch sequence left the fp16 operand range (B2S_FP32) */
 enum { B2S_IMG_BGR_U8_HWC = 0, B2S_IMG_RGB_F32_CHW = 1 };
 
 typedef struct b2s_aliked b2s_aliked;
@@ -194,6 +200,11 @@ int b2s_lg_max_batch(void);
  * the workspace grows on demand, which synchronises the stream). */
 size_t b2s_lg_workspace_bytes(const b2s_lg_cfg* cfg, int max_kp, int pairs);
 int b2s_lg_reserve(b2s_lg* h, int max_kp, int pairs);
+/* B2S_FP32: the B2S_FP32X3 matcher that re-runs pairs reported as B2S_LG_RANGE (created on first use; *out = NULL for the
+ * other precisions), how often it was asked for, and the operand planes of a handle (1 bf16, 2 fp16x2, 3 bf16x3). */
+int b2s_lg_fallback(b2s_lg* h, b2s_lg** out);
+long long b2s_lg_range_fallbacks(const b2s_lg* h);
+int b2s_lg_planes(const b2s_lg* h);
 
 /* ---------------------------------------------------------------------------------------------
  * Rows behind the matcher: epipolar outlier rejection and frame ingest.
@@ -296,6 +307,12 @@ int b2s_trace_attn_tc3(int nq, int nk, int iters, float* ms_out, long long* trac
 /* device-only timing of one bf16x3 layer-GEMM shape, `iters` launches back to back (PDL), clusters of `cl` CTAs sharing
  * the A tile (1 = none); ts_out (nullable) receives 6 globaltimer stamps (ns, relative) per CTA of one extra launch */
 int b2s_bench_gemm_tc3(int M, int N, int K, int cl, int iters, float* ms_out, long long* ts_out, int* n_cta_out);
+/* the same unit-test / timing entry points for the fp16x2 operand scheme of B2S_FP32 */
+int b2s_test_gemm_h2(const float* A, const float* W, const float* bias, int M, int N, int K, float* C);
+int b2s_test_attn_h2(const float* q, const float* k, const float* v, int nq, int nk, float* ctx);
+int b2s_bench_attn_h2(int nq, int nk, int iters, float* ms_out);
+int b2s_trace_attn_h2(int nq, int nk, int iters, float* ms_out, long long* trace_out);
+int b2s_bench_gemm_h2(int M, int N, int K, int cl, int iters, float* ms_out, long long* ts_out, int* n_cta_out);
 
 /* Number of CUDA kernels this library launched on behalf of the handle so far. */
 long long b2s_aliked_launch_count(const b2s_aliked* h);

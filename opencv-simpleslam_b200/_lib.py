@@ -28,8 +28,9 @@ class LgCfg(C.Structure):
                 ("pruning_min_kpts", C.c_int), ("precision", C.c_int), ("max_kp", C.c_int)]
 
 
-FP32, BF16 = 0, 1
-PRECISIONS = {"fp32": FP32, "bf16": BF16}
+FP32, BF16, FP32X3 = 0, 1, 2
+PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp32x3": FP32X3}
+LG_RANGE = -2   # n_matches of a pair whose launch sequence left the fp16 operand range (B2S_FP32)
 IMG_BGR_U8_HWC, IMG_RGB_F32_CHW = 0, 1
 vp, i32p, f32p = C.c_void_p, C.c_void_p, C.c_void_p   # raw addresses (device or host)
 
@@ -62,6 +63,14 @@ SIGNATURES = {
     "b2s_lg_max_batch": (C.c_int, []),
     "b2s_lg_workspace_bytes": (C.c_size_t, [C.POINTER(LgCfg), C.c_int, C.c_int]),
     "b2s_lg_reserve": (C.c_int, [vp, C.c_int, C.c_int]),
+    "b2s_lg_fallback": (C.c_int, [vp, C.POINTER(vp)]),
+    "b2s_lg_range_fallbacks": (C.c_longlong, [vp]),
+    "b2s_lg_planes": (C.c_int, [vp]),
+    "b2s_test_gemm_h2": (C.c_int, [f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, f32p]),
+    "b2s_test_attn_h2": (C.c_int, [f32p, f32p, f32p, C.c_int, C.c_int, f32p]),
+    "b2s_bench_attn_h2": (C.c_int, [C.c_int, C.c_int, C.c_int, f32p]),
+    "b2s_trace_attn_h2": (C.c_int, [C.c_int, C.c_int, C.c_int, f32p, vp]),
+    "b2s_bench_gemm_h2": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, vp, i32p]),
     "b2s_aliked_debug_get": (C.c_int, [vp, C.c_char_p, f32p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b2s_lg_set_debug": (C.c_int, [vp, C.c_int]),
     "b2s_lg_debug_get": (C.c_int, [vp, C.c_char_p, f32p, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -21,15 +21,23 @@
 
 namespace b2s {
 
-constexpr int A3_BQ = 128, A3_BK = 64, A3_D = 64, A3_NP = 3, A3_SLOTS = 3;
-constexpr int A3_QPL = A3_BQ * A3_D * 2;             // 16 KB: one Q plane  [128 x 64] bf16
-constexpr int A3_KPL = A3_BK * A3_D * 2;             //  8 KB: one K / V plane [64 x 64] bf16
-constexpr int A3_SLOT = A3_NP * A3_KPL;              // 24 KB: one V slot
-constexpr int A3_KSLOTS = 2, A3_KSLOT = A3_NP * A3_QPL;   // 48 KB: one K slot = a pair of key tiles
-constexpr int A3_SMEM = A3_NP * A3_QPL + A3_KSLOTS * A3_KSLOT + A3_SLOTS * A3_SLOT + 1024 + 256;
+constexpr int A3_BQ = 128, A3_BK = 64, A3_D = 64, A3_SLOTS = 3;
+constexpr int A3_QPL = A3_BQ * A3_D * 2;             // 16 KB: one Q plane  [128 x 64] 16-bit
+constexpr int A3_KPL = A3_BK * A3_D * 2;             //  8 KB: one K / V plane [64 x 64] 16-bit
 constexpr int A3_THREADS = 384;
-static_assert(2 * 66 * 128 * 4 <= A3_KSLOTS * A3_KSLOT, "the final merge buffers alias the K ring");
-static_assert(8 * 2048 <= A3_SLOTS * A3_SLOT, "the output staging tiles alias the V ring");
+// NP = 3: fp32 as three bf16 planes (six products per contraction); NP = 2: two fp16 planes in the attention operand
+// format of tc_common.cuh (three products; q, k, v prescaled by 16, P by 2^7 - the lazy softmax reference lets P reach 2^8).
+template <int NP>
+struct A3Cfg {
+  static constexpr int SLOT = NP * A3_KPL;             // one V slot
+  static constexpr int KSLOTS = NP == 3 ? 2 : 3;       // K slots = pairs of key tiles
+  static constexpr int KSLOT = NP * A3_QPL;
+  static constexpr int SMEM = NP * A3_QPL + KSLOTS * KSLOT + A3_SLOTS * SLOT + 1024 + 256;
+  static constexpr int PCOLS = NP * 32;                // tensor-memory columns of one group's P planes
+  static_assert(2 * 66 * 128 * 4 <= KSLOTS * KSLOT, "the final merge buffers alias the K ring");
+  static_assert(8 * 2048 <= A3_SLOTS * SLOT, "the output staging tiles alias the V ring");
+};
+constexpr float A3_P_PRESCALE = 128.f;               // NP = 2: P is stored as 2^7 P
 
 struct Attn3Params {
   AttnTcProb prob[2]; int cap;     // problems: see AttnTcParams
@@ -42,13 +50,15 @@ struct Attn3Params {
   int pv_issuers;                  // 1: one thread issues every P V product; 2: one thread per softmax group
   int trace_cta;                   // CTA to trace: x | y << 8 | z << 16
   long long* trace;                // nullable profiling hook (b2s_trace_attn_tc3): clock64 stamps of CTA (0,0,0), [role][tile][event]
+  int* range_flag;                 // NP == 2, nullable: set to 1 when an output value leaves the fp16 range
+  float out_scale;                 // NP == 2: 1 / (q-k-v prescale * P prescale) applied to the normalised output (0 means 1)
 };
 
 // P chunk c (32 keys) of one row -> three bf16 planes in REGISTERS (16 packed words each); returns the partial row sum.
 // The planes go to tensor memory later (a3_store_p_chunk), once the previous P V of the group has retired: everything
 // that does not depend on that MMA (exponentials, plane split) is done while it is still running.
-template <bool MASK>
-__device__ __forceinline__ float a3_make_p_chunk(const uint32_t (&v)[32], int c, int limit, float scale, float m_used, uint32_t (&pk)[A3_NP][16]) {
+template <bool MASK, int NP>
+__device__ __forceinline__ float a3_make_p_chunk(const uint32_t (&v)[32], int c, int limit, float scale, float m_used, uint32_t (&pk)[NP][16]) {
   float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
   for (int t = 0; t < 32; t += 2) {
@@ -59,20 +69,25 @@ __device__ __forceinline__ float a3_make_p_chunk(const uint32_t (&v)[32], int c,
       if (c * 32 + t + 1 >= limit) p1 = 0.f;
     }
     sum0 += p0; sum1 += p1;
-    uint32_t w[A3_NP];
-    tc::pack_planes2<A3_NP>(p0, p1, w);
+    uint32_t w[NP];
+    if (NP == 2) tc::pack_h2_attn(p0, p1, A3_P_PRESCALE, w[0], w[NP - 1]);
+    else tc::pack_planes2<NP>(p0, p1, w);
 #pragma unroll
-    for (int pl = 0; pl < A3_NP; ++pl) pk[pl][t >> 1] = w[pl];
+    for (int pl = 0; pl < NP; ++pl) pk[pl][t >> 1] = w[pl];
   }
   return sum0 + sum1;
 }
-__device__ __forceinline__ void a3_store_p_chunk(const uint32_t (&pk)[A3_NP][16], int c, uint32_t p_addr) {
+template <int NP>
+__device__ __forceinline__ void a3_store_p_chunk(const uint32_t (&pk)[NP][16], int c, uint32_t p_addr) {
 #pragma unroll
-  for (int pl = 0; pl < A3_NP; ++pl) tc::tmem_st16(p_addr + pl * 32 + c * 16, pk[pl]);
+  for (int pl = 0; pl < NP; ++pl) tc::tmem_st16(p_addr + pl * 32 + c * 16, pk[pl]);
 }
 
+template <int NP>
 __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constant__ CUtensorMap mapQ,
                                                             const __grid_constant__ CUtensorMap mapKV, Attn3Params p) {
+  using Cfg = A3Cfg<NP>;
+  constexpr int A3_NP = NP, A3_SLOT = Cfg::SLOT, A3_KSLOTS = Cfg::KSLOTS, A3_KSLOT = Cfg::KSLOT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                               // [3 planes]
@@ -169,7 +184,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
   } else if (warp == 9) {
     if (tc::elect_one()) {
       using Terms = tc::PlaneTerms<A3_NP>;
-      constexpr uint32_t idesc_s = tc::idesc_bf16(128, 128, 0, 0);   // S pair: A = Q (K-major), B = 128 keys (K-major)
+      constexpr uint32_t idesc_s = tc::idesc_planes<NP>(128, 128, 0, 0);   // S pair: A = Q (K-major), B = 128 keys (K-major)
       const uint32_t q_addr = tc::smem_u32(sQ);
       // (the barrier that completes LAST is waited on last: a wait on an already-complete mbarrier still costs ~100
       //  cycles, which must not sit between the late event and the first MMA)
@@ -216,7 +231,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
     //       and the pipe idles whenever all issuers are in that phase at once. =====
     if (tc::elect_one()) {
       using Terms = tc::PlaneTerms<A3_NP>;
-      constexpr uint32_t idesc_o = tc::idesc_bf16(128, 64, 0, 1);    // PV: A = P (tensor memory), B = V (MN-major)
+      constexpr uint32_t idesc_o = tc::idesc_planes<NP>(128, 64, 0, 1);    // PV: A = P (tensor memory), B = V (MN-major)
       const int jstep = p.pv_issuers == 2 ? 2 : 1;
       for (int j = (p.pv_issuers == 2 ? warp - 10 : 0); j < nt; j += jstep) {
         const int b = j % A3_SLOTS, ph = (j / A3_SLOTS) & 1, g = j & 1;
@@ -231,7 +246,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
           for (int kk = 0; kk < A3_BK / 16; ++kk) {
             // P plane: 32 columns (64 keys), 16 keys = 8 columns; V plane: [64 keys x 64 d] MN-major, 16 keys = 2048 B
             const uint64_t bd = tc::smem_desc_sw128(v_addr + Terms::b(t) * A3_KPL + kk * 2048, 16, 1024);
-            tc::umma_bf16_ts(tO + g * 64, tP + g * 96 + Terms::a(t) * 32 + kk * 8, bd, idesc_o, (t | kk) ? 1u : 0u);   // fresh per tile
+            tc::umma_bf16_ts(tO + g * 64, tP + g * Cfg::PCOLS + Terms::a(t) * 32 + kk * 8, bd, idesc_o, (t | kk) ? 1u : 0u);   // fresh per tile
           }
         tc::umma_commit(&o_full[g]);
         tc::umma_commit(&v_empty[b]);
@@ -249,7 +264,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
     float o[A3_D];                                        // running output (fp32 registers)
 #pragma unroll
     for (int d = 0; d < A3_D; ++d) o[d] = 0.f;
-    const uint32_t s_addr = tS + g * 64 + lane_addr, o_addr = tO + g * 64 + lane_addr, p_addr = tP + g * 96 + lane_addr;
+    const uint32_t s_addr = tS + g * 64 + lane_addr, o_addr = tO + g * 64 + lane_addr, p_addr = tP + g * Cfg::PCOLS + lane_addr;
     // o += the P V result of one tile sitting in TMEM (exact fp32 adds)
     auto add_pv = [&]() {
 #pragma unroll
@@ -290,8 +305,8 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
       }
       uint32_t pk0[A3_NP][16], pk1[A3_NP][16];
       float sum;
-      if (full) sum = a3_make_p_chunk<false>(s[0], 0, limit, p.scale_log2e, m_used, pk0) + a3_make_p_chunk<false>(s[1], 1, limit, p.scale_log2e, m_used, pk1);
-      else sum = a3_make_p_chunk<true>(s[0], 0, limit, p.scale_log2e, m_used, pk0) + a3_make_p_chunk<true>(s[1], 1, limit, p.scale_log2e, m_used, pk1);
+      if (full) sum = a3_make_p_chunk<false, NP>(s[0], 0, limit, p.scale_log2e, m_used, pk0) + a3_make_p_chunk<false, NP>(s[1], 1, limit, p.scale_log2e, m_used, pk1);
+      else sum = a3_make_p_chunk<true, NP>(s[0], 0, limit, p.scale_log2e, m_used, pk0) + a3_make_p_chunk<true, NP>(s[1], 1, limit, p.scale_log2e, m_used, pk1);
       if (t > 0) {
         // PV of the group's previous tile must have retired before P[g] is rewritten; collect its result (it was
         // computed against the previous reference maximum: add first, rescale afterwards)
@@ -307,8 +322,8 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
         }
       }
       l_run += sum;
-      a3_store_p_chunk(pk0, 0, p_addr);
-      a3_store_p_chunk(pk1, 1, p_addr);
+      a3_store_p_chunk<NP>(pk0, 0, p_addr);
+      a3_store_p_chunk<NP>(pk1, 1, p_addr);
       tc::tmem_st_wait();               // P is in tensor memory
       tc::tc_fence_before();            // order our tcgen05.ld / st before the MMAs that follow the arrive
       tc::mbar_arrive(&p_full[g]);
@@ -339,7 +354,8 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
       const float m_a = ma[64 * 128 + r], l_a = ma[65 * 128 + r], m_b = mb[64 * 128 + r], l_b = mb[65 * 128 + r];
       const float m = fmaxf(m_a, m_b);
       const float ca = ex2_approx(m_a - m), cb = (m_b == -INFINITY) ? 0.f : ex2_approx(m_b - m);
-      const float inv = 1.f / (l_a * ca + l_b * cb);
+      float inv = 1.f / (l_a * ca + l_b * cb);
+      if (NP == 2 && p.out_scale != 0.f) inv *= p.out_scale;          // power of two: undoes the operand prescales exactly
       const float fa = ca * inv, fb = cb * inv;
       float f[32];
 #pragma unroll
@@ -347,13 +363,26 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
       uint32_t* sp = reinterpret_cast<uint32_t*>(sV) + warp * 512;     // staging tile of this warp: [32 rows][16 words]
       const int rows_q = pr.nq - q0 - quad * 32;                       // live rows of this warp's quadrant
       __nv_bfloat16* dst = p.out + (size_t)(pr.q_row + q0 + quad * 32) * p.ldo + h * 64 + 32 * g;
+      uint32_t h1w[NP == 2 ? 16 : 1];
 #pragma unroll
       for (int pl = 0; pl < A3_NP; ++pl) {
         uint32_t w[16];
+        if (NP == 2) {
+          if (pl == 0) {
+            uint32_t ov = 0u;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          w[j] = tc::pack_bf16x2(f[2 * j], f[2 * j + 1]);
-          if (pl + 1 < A3_NP) { f[2 * j] -= __uint_as_float(w[j] << 16); f[2 * j + 1] -= __uint_as_float(w[j] & 0xFFFF0000u); }
+            for (int j = 0; j < 16; ++j) { tc::pack_h2(f[2 * j], f[2 * j + 1], w[j], h1w[j]); ov |= tc::h2_ovf(w[j]); }
+            if (ov && lane < rows_q && p.range_flag) *p.range_flag = 1;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = h1w[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            w[j] = tc::pack_bf16x2(f[2 * j], f[2 * j + 1]);
+            if (pl + 1 < A3_NP) { f[2 * j] -= __uint_as_float(w[j] << 16); f[2 * j + 1] -= __uint_as_float(w[j] & 0xFFFF0000u); }
+          }
         }
         uint4* prow = reinterpret_cast<uint4*>(sp + lane * 16);
 #pragma unroll

@@ -50,14 +50,26 @@ struct TcGemmParams {
   const float* residual; int ld_res; // nullable fp32 [rows, ld_res]: added after bias * alpha, before the activation
   float* out_f32_t; int ld_f32_t;    // TC_EPI_F32, nullable: also write the transposed result out_f32_t[col * ld_f32_t + row]
   unsigned long long* ts;            // nullable profiling hook: per CTA 6 globaltimer stamps (b2s_bench_gemm_tc3)
+  int attn_fmt;                      // NP == 2: output planes in the attention operand format (tc_common.cuh) instead of the GEMM one
+  int* range_flag;                   // NP == 2, nullable: set to 1 when an output value leaves the fp16 range
 };
 
-// fp32 weight [N,K] -> np bf16 planes side by side: out[n][p*K + k]
-static __global__ void k_weight_planes(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int N, int K, int np) {
+// fp32 weight [N,K] -> np operand planes side by side: out[n][p*K + k] (np = 2: fp16 pair, scaled residual; *bad is set
+// when a weight is outside the fp16 range)
+static __global__ void k_weight_planes(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int N, int K, int np, int* bad = nullptr) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)N * K) return;
   const int n = (int)(i / K), k = (int)(i % K);
   float r = w[i];
+  if (np == 2) {
+    const __half h0 = __float2half_rn(r);
+    const __half h1 = __float2half_rn((r - __half2float(h0)) * tc::H2_RS);
+    __half* o = reinterpret_cast<__half*>(out);
+    o[(size_t)n * 2 * K + k] = h0;
+    o[(size_t)n * 2 * K + K + k] = h1;
+    if (bad && !(fabsf(r) <= 65504.f)) *bad = 1;
+    return;
+  }
   for (int p = 0; p < np; ++p) {
     const __nv_bfloat16 b = __float2bfloat16_rn(r);
     out[(size_t)n * np * K + (size_t)p * K + k] = b;
@@ -182,7 +194,7 @@ __global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (tc::elect_one()) {
-      constexpr uint32_t idesc = tc::idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t idesc = tc::idesc_planes<NP>(128, BN, 0, 0);
       uint32_t used = 0;                                  // accumulators already written (first MMA overwrites)
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % Cfg::STAGES, ph = (kb / Cfg::STAGES) & 1;
@@ -262,7 +274,7 @@ __global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __
         tc::tmem_ld32(taddr, v);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) f[j] = NP == 2 ? fmaf(__uint_as_float(v[j]), Terms::CORR, f[j]) : f[j] + __uint_as_float(v[j]);
       }
       const int gc = n0 + c0;
       if (gc >= p.N) continue;                       // uniform per warp
@@ -347,15 +359,33 @@ __global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __
         store_f32_tile(gc);
         __syncwarp();
       }
-      // operand planes, one at a time: plane p = bf16(residual), residual -= plane p  (== tc::pack_planes2)
+      // operand planes, one at a time: plane p = bf16(residual), residual -= plane p  (== tc::pack_planes2);
+      // NP == 2: the two fp16 planes (GEMM or attention operand format), with the range check
+      uint32_t h1w[NP == 2 ? 16 : 1];
 #pragma unroll
       for (int pl = 0; pl < NP; ++pl) {
         if (pl >= np_out) break;
         uint32_t w[16];
+        if (NP == 2) {
+          if (pl == 0) {
+            uint32_t ov = 0u;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          w[j] = tc::pack_bf16x2(f[2 * j], f[2 * j + 1]);
-          if (pl + 1 < NP) { f[2 * j] -= __uint_as_float(w[j] << 16); f[2 * j + 1] -= __uint_as_float(w[j] & 0xFFFF0000u); }
+            for (int j = 0; j < 16; ++j) {
+              if (p.attn_fmt) tc::pack_h2_attn(f[2 * j], f[2 * j + 1], tc::H2_ATTN_PRESCALE, w[j], h1w[j]);
+              else tc::pack_h2(f[2 * j], f[2 * j + 1], w[j], h1w[j]);
+              ov |= tc::h2_ovf(w[j]);
+            }
+            if (ov && live && p.range_flag) *p.range_flag = 1;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = h1w[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            w[j] = tc::pack_bf16x2(f[2 * j], f[2 * j + 1]);
+            if (pl + 1 < NP) { f[2 * j] -= __uint_as_float(w[j] << 16); f[2 * j + 1] -= __uint_as_float(w[j] & 0xFFFF0000u); }
+          }
         }
         uint4* prow = reinterpret_cast<uint4*>(sp + lane * 16);
 #pragma unroll

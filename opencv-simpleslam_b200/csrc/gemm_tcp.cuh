@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
   } else if (warp == 1) {
     // ===== MMA issuer: tile lt accumulates into TMEM buffer lt & 1 while the epilogue drains the other one =====
     if (tc::elect_one()) {
-      constexpr uint32_t idesc = tc::idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t idesc = tc::idesc_planes<NP>(128, BN, 0, 0);
       int it = 0, lt = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         const TcpTile ti = tcp_tile(p, t, n_tiles, BN);
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
           tc::tmem_ld32(taddr, v);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) f[j] = NP == 2 ? fmaf(__uint_as_float(v[j]), Terms::CORR, f[j]) : f[j] + __uint_as_float(v[j]);
         }
         if (c0 + 8 * Cfg::EPI_WARPS >= BN) {
           // that was this warp's last read of the buffer: hand it back to the MMA issuer before the stores
@@ -317,15 +317,33 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
           store_f32_tile(gc);
           __syncwarp();
         }
-        // operand planes, one at a time: plane p = bf16(residual), residual -= plane p  (== tc::pack_planes2)
+        // operand planes, one at a time: plane p = bf16(residual), residual -= plane p  (== tc::pack_planes2);
+        // NP == 2: the two fp16 planes (GEMM or attention operand format), with the range check
+        uint32_t h1w[NP == 2 ? 16 : 1];
 #pragma unroll
         for (int pl = 0; pl < NP; ++pl) {
           if (pl >= np_out) break;
           uint32_t w[16];
+          if (NP == 2) {
+            if (pl == 0) {
+              uint32_t ov = 0u;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            w[j] = tc::pack_bf16x2(f[2 * j], f[2 * j + 1]);
-            if (pl + 1 < NP) { f[2 * j] -= __uint_as_float(w[j] << 16); f[2 * j + 1] -= __uint_as_float(w[j] & 0xFFFF0000u); }
+              for (int j = 0; j < 16; ++j) {
+                if (p.attn_fmt) tc::pack_h2_attn(f[2 * j], f[2 * j + 1], tc::H2_ATTN_PRESCALE, w[j], h1w[j]);
+                else tc::pack_h2(f[2 * j], f[2 * j + 1], w[j], h1w[j]);
+                ov |= tc::h2_ovf(w[j]);
+              }
+              if (ov && live && p.range_flag) *p.range_flag = 1;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) w[j] = h1w[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              w[j] = tc::pack_bf16x2(f[2 * j], f[2 * j + 1]);
+              if (pl + 1 < NP) { f[2 * j] -= __uint_as_float(w[j] << 16); f[2 * j + 1] -= __uint_as_float(w[j] & 0xFFFF0000u); }
+            }
           }
           uint4* prow = reinterpret_cast<uint4*>(sp + lane * 16);
 #pragma unroll

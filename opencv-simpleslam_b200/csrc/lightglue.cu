@@ -46,8 +46,14 @@ struct b2s_lg {
   long long launches = 0;
   KernelProf prof;
   unsigned long long* stats = nullptr;   // device: [0] sum nq*nk over self-attention problems, [1] over cross-attention problems
-  LgTensorCore* tc = nullptr;   // tcgen05 layers: bf16 operands (precision == B2S_BF16) or fp32 as three bf16 planes
+  LgTensorCore* tc = nullptr;   // tcgen05 layers: bf16 operands (B2S_BF16), fp32 as two fp16 planes (B2S_FP32) or as three bf16 planes (B2S_FP32X3)
+  int planes = 3;               // operand planes of tc: 1, 2 or 3
+  // B2S_FP32 only: the weight blob and, created on the first range overflow, a B2S_FP32X3 matcher that re-runs flagged batches
+  std::vector<uint8_t> blob;
+  b2s_lg* fallback = nullptr;
+  long long range_fallbacks = 0;
 };
+static int planes_of(int precision) { return precision == B2S_BF16 ? 1 : precision == B2S_FP32 ? 2 : 3; }
 
 static int upload_t(b2s_lg* h, const WeightBlob& wb, const std::string& name, size_t numel, float** out) {
   const TensorView* t = wb.get(name, numel);
@@ -105,8 +111,8 @@ extern "C" void b2s_lg_default_cfg(b2s_lg_cfg* c) {
 
 extern "C" int b2s_lightglue_create(const b2s_lg_cfg* cfg, const void* weights, size_t nbytes, int device, b2s_lg** out) {
   if (!cfg || !weights || !out) { set_error("b2s_lightglue_create: null argument"); return B2S_EINVAL; }
-  if (cfg->precision != B2S_FP32 && cfg->precision != B2S_BF16) {
-    set_error("b2s_lightglue_create: unknown precision %d (B2S_FP32 = fp32-faithful on tcgen05, B2S_BF16)", cfg->precision);
+  if (cfg->precision != B2S_FP32 && cfg->precision != B2S_BF16 && cfg->precision != B2S_FP32X3) {
+    set_error("b2s_lightglue_create: unknown precision %d (B2S_FP32 / B2S_FP32X3 = fp32-faithful on tcgen05, B2S_BF16)", cfg->precision);
     return B2S_EINVAL;
   }
   if (cfg->dim != 256 || cfg->heads != 4 || cfg->in_dim != 128 || cfg->n_layers < 1 || cfg->n_layers > 16) {
@@ -201,19 +207,36 @@ extern "C" int b2s_lightglue_create(const b2s_lg_cfg* cfg, const void* weights, 
   if ((rc = h->warena.alloc(&h->stats, (size_t)4))) return fail(rc);
   cudaMemset(h->stats, 0, 4 * sizeof(unsigned long long));
   if (cudaMallocHost((void**)&h->h_ctrl, LGC_INTS * sizeof(int)) != cudaSuccess) { set_error("cudaMallocHost failed"); return fail(B2S_ENOMEM); }
-  // tensor-core layers: bf16 operands, or fp32 carried as three bf16 planes
-  if ((rc = lgtc_create(&h->tc, h->L.size(), cfg->precision == B2S_BF16 ? 1 : 3))) return fail(rc);
-  lgtc_set_prof(h->tc, &h->prof, h->stats);
-  for (size_t i = 0; i < h->L.size(); ++i) {
-    const LgLayer& l = h->L[i];
-    LgTcLayerSrc s = {l.wqkv, l.bqkv, l.wo, l.bo, l.w1, l.b1, l.lng, l.lnb, l.w2, l.b2,
-                      l.cwqkv, l.cbqkv, l.cwo, l.cbo, l.cw1, l.cb1, l.clng, l.clnb, l.cw2, l.cb2};
-    if ((rc = lgtc_set_layer(h->tc, (int)i, s))) return fail(rc);
-  }
-  {
+  // tensor-core layers: bf16 operands, fp32 carried as two fp16 planes, or as three bf16 planes
+  auto build_tc = [&](int planes) -> int {
+    int r = 0;
+    if ((r = lgtc_create(&h->tc, h->L.size(), planes))) return r;
+    h->planes = planes;
+    lgtc_set_prof(h->tc, &h->prof, h->stats);
+    for (size_t i = 0; i < h->L.size(); ++i) {
+      const LgLayer& l = h->L[i];
+      LgTcLayerSrc s = {l.wqkv, l.bqkv, l.wo, l.bo, l.w1, l.b1, l.lng, l.lnb, l.w2, l.b2,
+                        l.cwqkv, l.cbqkv, l.cwo, l.cbo, l.cw1, l.cb1, l.clng, l.clnb, l.cw2, l.cb2};
+      if ((r = lgtc_set_layer(h->tc, (int)i, s))) return r;
+    }
     std::vector<const float*> wf, bf;
     for (const LgLayer& l : h->L) { wf.push_back(l.wfinal); bf.push_back(l.bfinal); }
-    if ((rc = lgtc_set_final(h->tc, wf, bf)) || (rc = lgtc_set_input(h->tc, h->in_w, h->in_b))) return fail(rc);
+    if ((r = lgtc_set_final(h->tc, wf, bf)) || (r = lgtc_set_input(h->tc, h->in_w, h->in_b))) return r;
+    return 0;
+  };
+  if ((rc = build_tc(planes_of(cfg->precision)))) return fail(rc);
+  if (h->planes == 2) {
+    // a weight outside the fp16 range (never seen with real checkpoints) rules the fp16x2 engine out for this model
+    int bad = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(&bad, lgtc_range_flag(h->tc), sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+      set_error("b2s_lightglue_create: weight range check failed"); return fail(B2S_ECUDA);
+    }
+    if (bad) {
+      lgtc_destroy(h->tc); h->tc = nullptr;
+      if ((rc = build_tc(3))) return fail(rc);
+    } else {
+      h->blob.assign((const uint8_t*)weights, (const uint8_t*)weights + nbytes);
+    }
   }
   if ((rc = lg_alloc_ws(h, cfg->max_kp > 0 ? cfg->max_kp : 2048, 1))) return fail(rc);
   *out = h;
@@ -224,9 +247,28 @@ extern "C" void b2s_lg_destroy(b2s_lg* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+  if (h->fallback) b2s_lg_destroy(h->fallback);
   if (h->tc) lgtc_destroy(h->tc);
   delete h;
 }
+
+// B2S_FP32 matcher: the bf16x3 matcher that re-runs launch sequences whose values left the fp16 range (created on first
+// use from the retained weight blob); *out = nullptr when this matcher needs none (B2S_BF16 / B2S_FP32X3).
+extern "C" int b2s_lg_fallback(b2s_lg* h, b2s_lg** out) {
+  if (!h || !out) { set_error("b2s_lg_fallback: null argument"); return B2S_EINVAL; }
+  *out = nullptr;
+  if (h->planes != 2) return 0;
+  if (!h->fallback) {
+    b2s_lg_cfg c = h->cfg;
+    c.precision = B2S_FP32X3; c.max_kp = std::max(h->cap, 128);
+    B2S_TRY(b2s_lightglue_create(&c, h->blob.data(), h->blob.size(), h->device, &h->fallback));
+  }
+  ++h->range_fallbacks;
+  *out = h->fallback;
+  return 0;
+}
+extern "C" long long b2s_lg_range_fallbacks(const b2s_lg* h) { return h ? h->range_fallbacks : 0; }
+extern "C" int b2s_lg_planes(const b2s_lg* h) { return h ? h->planes : 0; }
 
 extern "C" long long b2s_lg_launch_count(const b2s_lg* h) { return h ? h->launches : 0; }
 
@@ -265,7 +307,7 @@ extern "C" int b2s_lg_set_debug(b2s_lg* h, int on) {
 
 extern "C" size_t b2s_lg_workspace_bytes(const b2s_lg_cfg* cfg, int max_kp, int pairs) {
   if (!cfg || max_kp < 1 || pairs < 1) return 0;
-  return lg_ws_bytes(cfg->precision == B2S_BF16 ? 1 : 3, (max_kp + 127) / 128 * 128, std::min(pairs, LG_MAXP), cfg->n_layers, false);
+  return lg_ws_bytes(planes_of(cfg->precision), (max_kp + 127) / 128 * 128, std::min(pairs, LG_MAXP), cfg->n_layers, false);
 }
 
 extern "C" int b2s_lg_max_batch(void) { return LG_MAXP; }
@@ -301,6 +343,7 @@ static int lg_run(b2s_lg* h, cudaStream_t st, const LgBatchIn& in, const LgBatch
     PosencParams pp = {};
     pp.in = in; pp.cap = cap; pp.Wr = h->wr; pp.cosb = h->cosb[0]; pp.sinb = h->sinb[0]; pp.ind = h->ind[0]; pp.prune = h->prune;
     pp.din = lgtc_din(h->tc); pp.din_plane = plane_rows * 128;
+    pp.din_planes = lgtc_faithful_planes(h->tc); pp.range_flag = lgtc_range_flag(h->tc);
     pp.ctrl = h->ctrl; pp.last_init = (do_stop || do_prune) ? 0 : L - 1;
     launch_k(k_lg_posenc, dim3(cdiv(std::max(maxrows, 1), 64), nseg), 256, 0, st, pp);
     ++h->launches;
@@ -344,7 +387,7 @@ static int lg_run(b2s_lg* h, cudaStream_t st, const LgBatchIn& in, const LgBatch
       gp.x_in = h->x[cur]; gp.x_out = h->x[nxt]; gp.cos_in = h->cosb[cur]; gp.cos_out = h->cosb[nxt];
       gp.sin_in = h->sinb[cur]; gp.sin_out = h->sinb[nxt]; gp.ind_in = h->ind[cur]; gp.ind_out = h->ind[nxt];
       gp.prune = h->prune;
-      gp.xb_out = lgtc_xb(h->tc); gp.xb_planes = lgtc_planes(h->tc); gp.xb_plane = plane_rows * 256;
+      gp.xb_out = lgtc_xb(h->tc); gp.xb_planes = lgtc_planes(h->tc); gp.xb_plane = plane_rows * 256; gp.range_flag = lgtc_range_flag(h->tc);
       launch_k(k_lg_gather_blk, dim3(nblk, nseg), 1024, 0, st, gp);
       h->launches += 2;
       B2S_LAUNCH_CHECK();
@@ -355,6 +398,7 @@ static int lg_run(b2s_lg* h, cudaStream_t st, const LgBatchIn& in, const LgBatch
       FinalPrepParams fp = {};
       fp.x = h->x[0]; fp.x_odd = do_prune ? h->x[1] : nullptr; fp.cap = cap; fp.ctrl = h->ctrl;
       fp.wm_tab = h->wmatch_tab; fp.bm_tab = h->bmatch_tab; fp.tx = lgtc_tx(h->tc); fp.plane = plane_rows * 256; fp.ls = h->ls;
+      fp.tx_planes = lgtc_faithful_planes(h->tc); fp.range_flag = lgtc_range_flag(h->tc);
       launch_k(k_lg_final_prep, dim3(cdiv(maxrows, 8), nseg), 256, 0, st, fp);
       ++h->launches;
       B2S_LAUNCH_CHECK();
@@ -373,6 +417,7 @@ static int lg_run(b2s_lg* h, cudaStream_t st, const LgBatchIn& in, const LgBatch
   fp.out = out; fp.th = h->cfg.filter_thresh; fp.n_layers = L; fp.do_prune = do_prune ? 1 : 0;
   fp.ctrl = h->ctrl; fp.cap = cap; fp.max0 = h->max0; fp.m0 = h->m0; fp.m1 = h->m1;
   fp.ind = h->ind[0]; fp.ind_odd = do_prune ? h->ind[1] : nullptr; fp.prune = h->prune;
+  fp.range_flag = h->planes == 2 ? lgtc_range_flag(h->tc) : nullptr;
   launch_k(k_lg_filter, np, 1024, 0, st, fp);
   ++h->launches;
   B2S_LAUNCH_CHECK();
@@ -444,6 +489,13 @@ extern "C" int b2s_lightglue_match_host(b2s_lg* h, const float* k0, const float*
   B2S_CUDA(cudaMemcpyAsync(h->h_ctrl, h->hnm, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));   // pinned: n_matches, stop
   B2S_CUDA(cudaStreamSynchronize(st));
   const int32_t nm = h->h_ctrl[0];
+  if (nm == B2S_LG_RANGE) {     // fp16x2 engine: a value left the fp16 range - the bf16x3 engine takes this pair
+    b2s_lg* fb = nullptr;
+    B2S_TRY(b2s_lg_fallback(h, &fb));
+    if (!fb) { set_error("b2s_lightglue_match_host: range overflow without a fallback engine"); return B2S_ECUDA; }
+    return b2s_lightglue_match_host(fb, k0, d0, m, k1, d1, n, size0, size1, matches, mscores, n_matches, stop_layer, matches0, matches1,
+                                    ms0, ms1, prune0, prune1);
+  }
   *n_matches = nm;
   if (stop_layer) *stop_layer = h->h_ctrl[1];
   if (nm > 0) {

@@ -47,7 +47,8 @@ struct PosencParams {
   float* cosb; float* sinb;  // [rows,32]
   int* ind;                  // [rows]  identity index map
   int* prune;                // [rows]  per-point prune counters (by original index) -> 1
-  __nv_bfloat16* din; size_t din_plane;   // [3][rows,128] descriptor planes
+  __nv_bfloat16* din; size_t din_plane;   // [din_planes][rows,128] descriptor planes
+  int din_planes; int* range_flag;        // 3: bf16x3; 2: fp16x2 (out-of-range values raise *range_flag)
   int* ctrl; int last_init;  // device state, reset here (last_init = L-1 when depth/width adaptivity is off)
 };
 
@@ -103,12 +104,22 @@ __global__ void __launch_bounds__(256) k_lg_posenc(PosencParams p) {
     p.cosb[(size_t)r * 32 + lane] = cosf(pr);
     p.sinb[(size_t)r * 32 + lane] = sinf(pr);
     const float4 d = *reinterpret_cast<const float4*>(desc + (size_t)i * 128 + lane * 4);
-    uint32_t wa[3], wb[3];
-    tc::pack_planes2<3>(d.x, d.y, wa);
-    tc::pack_planes2<3>(d.z, d.w, wb);
+    if (p.din_planes == 2) {
+      uint32_t wa[2], wb[2];
+      tc::pack_planes2<2>(d.x, d.y, wa);
+      tc::pack_planes2<2>(d.z, d.w, wb);
 #pragma unroll
-    for (int pl = 0; pl < 3; ++pl)
-      *reinterpret_cast<uint2*>(p.din + pl * p.din_plane + (size_t)r * 128 + lane * 4) = make_uint2(wa[pl], wb[pl]);
+      for (int pl = 0; pl < 2; ++pl)
+        *reinterpret_cast<uint2*>(p.din + pl * p.din_plane + (size_t)r * 128 + lane * 4) = make_uint2(wa[pl], wb[pl]);
+      if ((tc::h2_ovf(wa[0]) | tc::h2_ovf(wb[0])) && p.range_flag) *p.range_flag = 1;
+    } else {
+      uint32_t wa[3], wb[3];
+      tc::pack_planes2<3>(d.x, d.y, wa);
+      tc::pack_planes2<3>(d.z, d.w, wb);
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl)
+        *reinterpret_cast<uint2*>(p.din + pl * p.din_plane + (size_t)r * 128 + lane * 4) = make_uint2(wa[pl], wb[pl]);
+    }
   }
 }
 
@@ -184,7 +195,8 @@ struct GatherBlkParams {
   int layer, do_stop, do_prune, pruning_min_kpts, nblk; float depth_conf;
   const float* x_in; float* x_out; const float* cos_in; float* cos_out; const float* sin_in; float* sin_out;
   const int* ind_in; int* ind_out; int* prune;             // prune [rows] by original index
-  __nv_bfloat16* xb_out; int xb_planes; size_t xb_plane;   // bf16 plane copy of x (operand of the next layer's GEMMs)
+  __nv_bfloat16* xb_out; int xb_planes; size_t xb_plane;   // operand-plane copy of x (next layer's GEMMs): 1 / 3 bf16 planes, 2 fp16 planes
+  int* range_flag;                                         // xb_planes == 2: raised by an out-of-range value
 };
 
 __global__ void __launch_bounds__(1024) k_lg_gather_blk(GatherBlkParams p) {   // 32 warps: one row per warp
@@ -235,6 +247,7 @@ __global__ void __launch_bounds__(1024) k_lg_gather_blk(GatherBlkParams p) {   /
   {
     const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     if (p.xb_planes == 1) store_planes8<1>(p.xb_out + (size_t)dst * 256 + lane * 8, p.xb_plane, f);
+    else if (p.xb_planes == 2) { if (store_planes8<2>(p.xb_out + (size_t)dst * 256 + lane * 8, p.xb_plane, f) && p.range_flag) *p.range_flag = 1; }
     else store_planes8<3>(p.xb_out + (size_t)dst * 256 + lane * 8, p.xb_plane, f);
   }
   p.cos_out[(size_t)dst * 32 + lane] = p.cos_in[(size_t)src * 32 + lane];
@@ -256,8 +269,9 @@ struct FinalPrepParams {
   const float* x; const float* x_odd;     // x_odd nullable (no pruning)
   int cap; const int* ctrl;
   const float* const* wm_tab; const float* bm_tab;   // matchability heads per layer
-  __nv_bfloat16* tx; size_t plane;        // [3][rows,256]
+  __nv_bfloat16* tx; size_t plane;        // [tx_planes][rows,256]
   float* ls;                              // [rows]
+  int tx_planes; int* range_flag;         // 3: bf16x3; 2: fp16x2 (+ range check)
 };
 
 __global__ void __launch_bounds__(256) k_lg_final_prep(FinalPrepParams p) {
@@ -274,7 +288,8 @@ __global__ void __launch_bounds__(256) k_lg_final_prep(FinalPrepParams p) {
   const size_t r = (size_t)(g * p.cap + row);
   const float4 a = *reinterpret_cast<const float4*>(xsrc + r * 256 + lane * 8), b = *reinterpret_cast<const float4*>(xsrc + r * 256 + lane * 8 + 4);
   const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  store_planes8<3>(p.tx + r * 256 + lane * 8, p.plane, f);
+  if (p.tx_planes == 2) { if (store_planes8<2>(p.tx + r * 256 + lane * 8, p.plane, f) && p.range_flag) *p.range_flag = 1; }
+  else store_planes8<3>(p.tx + r * 256 + lane * 8, p.plane, f);
   const float4 w0 = *reinterpret_cast<const float4*>(wm + lane * 8), w1 = *reinterpret_cast<const float4*>(wm + lane * 8 + 4);
   float dm = a.x * w0.x + a.y * w0.y + a.z * w0.z + a.w * w0.w + b.x * w1.x + b.y * w1.y + b.z * w1.z + b.w * w1.w;
   dm = warp_sum(dm);
@@ -378,6 +393,7 @@ struct FilterParams {
   const float* max0; const int* m0; const int* m1;   // [pairs, cap]
   const int* ind; const int* ind_odd;                // [rows] pruned index -> original index; ind_odd (nullable): odd ping-pong buffer
   const int* prune;                                  // [rows] prune counters by original index
+  int* range_flag;   // nullable: [0] sticky "a value left the fp16 range during this launch sequence", [1] CTA arrival counter
 };
 
 __global__ void __launch_bounds__(1024) k_lg_filter(FilterParams p) {
@@ -386,6 +402,21 @@ __global__ void __launch_bounds__(1024) k_lg_filter(FilterParams p) {
   const LgPairOut& o = p.out.pr[pair];
   const int* c = p.ctrl + pair * LGC_INTS;
   const int tid = threadIdx.x;
+  // fp16x2 path: a value left the fp16 range somewhere in this launch sequence -> every pair of it reports
+  // n_matches = B2S_LG_RANGE (the host re-runs the batch on the bf16x3 engine).  The last CTA to read the flag clears it.
+  __shared__ int s_range;
+  if (p.range_flag) {
+    if (tid == 0) {
+      s_range = *reinterpret_cast<volatile int*>(p.range_flag);
+      __threadfence();
+      if (atomicAdd(p.range_flag + 1, 1) == (int)gridDim.x - 1) { p.range_flag[0] = 0; p.range_flag[1] = 0; }
+    }
+    __syncthreads();
+    if (s_range) {
+      if (tid == 0) { *o.n_matches = -2; if (o.stop_layer) *o.stop_layer = 0; }
+      return;
+    }
+  }
   const int om = c[LGC_M0], on = c[LGC_N0];        // original counts (<= o.m, o.n)
   const bool empty_in = om <= 0 || on <= 0;
   // ---- defaults over the original points ----

@@ -80,7 +80,7 @@ int make_tmap_bf16_4d(CUtensorMap* out, const void* gptr, const uint64_t dims[4]
 template <int NP>
 __global__ void __launch_bounds__(256) k_ln_gelu_512_bf16(const float* __restrict__ h, __nv_bfloat16* __restrict__ y, size_t plane,
                                                           int cap, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          const int* __restrict__ ctrl) {
+                                                          const int* __restrict__ ctrl, int* range_flag) {
   pdl_wait();
   const int g = blockIdx.y;
   const int* c = ctrl + (g >> 1) * TC_CTRL_INTS;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) k_ln_gelu_512_bf16(const float* __restric
       f[4 * e] = gelu_erf_f((x.x - mean) * rstd * gm.x + b.x); f[4 * e + 1] = gelu_erf_f((x.y - mean) * rstd * gm.y + b.y);
       f[4 * e + 2] = gelu_erf_f((x.z - mean) * rstd * gm.z + b.z); f[4 * e + 3] = gelu_erf_f((x.w - mean) * rstd * gm.w + b.w);
     }
-    store_planes8<NP>(y + roff + col, plane, f);
+    if (store_planes8<NP>(y + roff + col, plane, f) && range_flag) *range_flag = 1;
   }
 }
 
@@ -132,7 +132,9 @@ struct TcLayer {
 struct LgTensorCore {
   DeviceArena warena, wsarena;
   std::vector<TcLayer> L;
-  int np = 1;                      // operand planes of the transformer layers: 1 = bf16, 3 = fp32 carried as bf16x3
+  int np = 1;                      // operand planes of the transformer layers: 1 = bf16, 3 = fp32 carried as bf16x3, 2 = fp32 as fp16x2
+  int npf = 3;                     // operand planes of the always-fp32-faithful parts (input projection, assignment head): 3, or 2 with np == 2
+  int* range_flag = nullptr;       // np == 2: sticky device flag, raised by any producer whose value leaves the fp16 range
   int cap = 0, pcap = 0;           // rows per segment, pairs the workspace holds (segments = 2 * pcap)
   // activation planes: [np][segments * cap][C] bf16
   __nv_bfloat16 *xb = nullptr, *qkvb = nullptr, *ctxb = nullptr, *h1b = nullptr;
@@ -156,7 +158,7 @@ static int make_linear(LgTensorCore* tc, const float* w_dev, const float* bias, 
   out->N = N; out->K = K; out->bias = bias; out->BN = N <= 256 ? 64 : (N % 128 == 0 && N != 768 ? 128 : 96);   // N = 768 (QKV): 8 x 32 tiles of 128 x 96 waste less of the second wave than 6 x 32 of 128 x 128
   const size_t n = (size_t)N * K;
   B2S_TRY(tc->warena.alloc(&out->w, n * np));
-  k_weight_planes<<<(unsigned)((n + 255) / 256), 256>>>(w_dev, out->w, N, K, np);
+  k_weight_planes<<<(unsigned)((n + 255) / 256), 256>>>(w_dev, out->w, N, K, np, tc->range_flag);
   B2S_LAUNCH_CHECK();
   return make_tmap_bf16_2d(&out->map, out->w, (uint64_t)np * K, N, (uint64_t)np * K * 2, 64, out->BN);
 }
@@ -223,15 +225,37 @@ static int attn_pv_issuers() {
 }
 static void tc_kernel_attrs() {
   gemm_attr<64, 1>(); gemm_attr<128, 1>(); gemm_attr<64, 3>(); gemm_attr<128, 3>(); gemm_attr<96, 1>(); gemm_attr<96, 3>();
+  gemm_attr<64, 2>(); gemm_attr<128, 2>(); gemm_attr<96, 2>();
   gemmp_attr<64, 1>(); gemmp_attr<128, 1>(); gemmp_attr<64, 3>(); gemmp_attr<128, 3>(); gemmp_attr<96, 1>(); gemmp_attr<96, 3>();
+  gemmp_attr<64, 2>(); gemmp_attr<128, 2>(); gemmp_attr<96, 2>();
   cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
-  cudaFuncSetAttribute(k_attn_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM);
+  cudaFuncSetAttribute(k_attn_tc3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Cfg<3>::SMEM);
+  cudaFuncSetAttribute(k_attn_tc3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Cfg<2>::SMEM);
+}
+// one GEMM launch, persistent or one tile per CTA, dispatched on (tile width, operand planes)
+template <int BN, int NP>
+static void launch_gemm_any(cudaStream_t st, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const TcGemmParams& p, int m_tiles) {
+  if (gemm_persistent()) launch_gemm_p<BN, NP>(st, a1, a2, w, p, m_tiles);
+  else launch_k(k_gemm_tc<BN, NP>, dim3(cdiv(p.N, BN), m_tiles), TcGemmCfg<BN, NP>::THREADS, TcGemmCfg<BN, NP>::SMEM, st, a1, a2, w, p);
+}
+template <int NP>
+static void launch_gemm_bn(int BN, cudaStream_t st, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const TcGemmParams& p, int m_tiles) {
+  if (BN == 64) launch_gemm_any<64, NP>(st, a1, a2, w, p, m_tiles);
+  else if (BN == 96) launch_gemm_any<96, NP>(st, a1, a2, w, p, m_tiles);
+  else launch_gemm_any<128, NP>(st, a1, a2, w, p, m_tiles);
+}
+static void launch_gemm(int np, int BN, cudaStream_t st, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const TcGemmParams& p, int m_tiles) {
+  if (np == 1) launch_gemm_bn<1>(BN, st, a1, a2, w, p, m_tiles);
+  else if (np == 2) launch_gemm_bn<2>(BN, st, a1, a2, w, p, m_tiles);
+  else launch_gemm_bn<3>(BN, st, a1, a2, w, p, m_tiles);
 }
 
 int lgtc_create(LgTensorCore** out, size_t n_layers, int planes) {
-  if (planes != 1 && planes != 3) { set_error("lgtc_create: planes must be 1 or 3"); return B2S_EINVAL; }
+  if (planes < 1 || planes > 3) { set_error("lgtc_create: planes must be 1, 2 or 3"); return B2S_EINVAL; }
   LgTensorCore* tc = new LgTensorCore();
   tc->np = planes;
+  tc->npf = planes == 2 ? 2 : 3;
+  if (tc->warena.alloc(&tc->range_flag, 2) || cudaMemset(tc->range_flag, 0, 2 * sizeof(int)) != cudaSuccess) { delete tc; return B2S_ENOMEM; }
   tc->L.resize(n_layers);
   tc_kernel_attrs();
   *out = tc;
@@ -252,14 +276,14 @@ int lgtc_set_layer(LgTensorCore* tc, int li, const LgTcLayerSrc& s) {
 }
 
 int lgtc_set_input(LgTensorCore* tc, const float* w, const float* b) {
-  B2S_TRY(make_linear(tc, w, b, 256, 128, &tc->win, 3));
+  B2S_TRY(make_linear(tc, w, b, 256, 128, &tc->win, tc->npf));
   B2S_CUDA(cudaDeviceSynchronize());
   return 0;
 }
 
 size_t lgtc_ws_bytes(int np, int cap, int pcap) {
-  const size_t R = (size_t)2 * pcap * cap, P = (size_t)np;
-  return 2 * (P * R * (256 + 768 + 256 + 512) + 3 * R * (128 + 256 + 256)) + 4 * R * 512;
+  const size_t R = (size_t)2 * pcap * cap, P = (size_t)np, F = np == 2 ? 2 : 3;
+  return 2 * (P * R * (256 + 768 + 256 + 512) + F * R * (128 + 256 + 256)) + 4 * R * 512;
 }
 
 int lgtc_alloc_ws(LgTensorCore* tc, int cap, int pcap) {
@@ -281,13 +305,14 @@ int lgtc_alloc_ws(LgTensorCore* tc, int cap, int pcap) {
   B2S_TRY(make_tmap_bf16_2d(&tc->m_qkv512, tc->qkvb, 512, P * R, 1024, 64, 128));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_kv768, tc->qkvb, 768, P * R, 1536, 64, 64));
   B2S_TRY(make_tmap_bf16_2d(&tc->m_kv512, tc->qkvb, 512, P * R, 1024, 64, 64));
-  B2S_TRY(tc->wsarena.alloc(&tc->din, 3 * R * 128));
-  B2S_TRY(tc->wsarena.alloc(&tc->tx, 3 * R * 256)); B2S_TRY(tc->wsarena.alloc(&tc->md, 3 * R * 256));
-  B2S_CUDA(cudaMemset(tc->din, 0, 3 * R * 128 * 2));
-  B2S_CUDA(cudaMemset(tc->tx, 0, 3 * R * 256 * 2)); B2S_CUDA(cudaMemset(tc->md, 0, 3 * R * 256 * 2));
-  B2S_TRY(make_tmap_bf16_2d(&tc->m_din, tc->din, 128, 3 * R, 256, 64, 128));
-  B2S_TRY(make_tmap_bf16_2d(&tc->m_tx, tc->tx, 256, 3 * R, 512, 64, 128));
-  B2S_TRY(make_tmap_bf16_2d(&tc->m_md, tc->md, 256, 3 * R, 512, 64, 128));
+  const size_t F = (size_t)tc->npf;
+  B2S_TRY(tc->wsarena.alloc(&tc->din, F * R * 128));
+  B2S_TRY(tc->wsarena.alloc(&tc->tx, F * R * 256)); B2S_TRY(tc->wsarena.alloc(&tc->md, F * R * 256));
+  B2S_CUDA(cudaMemset(tc->din, 0, F * R * 128 * 2));
+  B2S_CUDA(cudaMemset(tc->tx, 0, F * R * 256 * 2)); B2S_CUDA(cudaMemset(tc->md, 0, F * R * 256 * 2));
+  B2S_TRY(make_tmap_bf16_2d(&tc->m_din, tc->din, 128, F * R, 256, 64, 128));
+  B2S_TRY(make_tmap_bf16_2d(&tc->m_tx, tc->tx, 256, F * R, 512, 64, 128));
+  B2S_TRY(make_tmap_bf16_2d(&tc->m_md, tc->md, 256, F * R, 512, 64, 128));
   tc->cap = cap; tc->pcap = pcap;
   return 0;
 }
@@ -304,30 +329,10 @@ static int tc_gemm(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& a1, con
   p.out_plane = (size_t)p.plane_rows * p.ld_bf16;
   const int tiles = nseg * p.tiles_per_seg;
   if (tiles <= 0) return 0;
-  dim3 grid(w.N / w.BN, tiles);
+  p.range_flag = tc->range_flag;
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
-  if (gemm_persistent()) {
-    // (128-wide tiles for the N = 256 / 768 GEMMs of a large batch were measured: no gain over the 64 / 96-wide defaults)
-    const int BN = w.BN;
-    const CUtensorMap& wm = w.map;
-    if (tc->np == 1) {
-      if (BN == 64) launch_gemm_p<64, 1>(st, a1, a2, wm, p, tiles);
-      else if (BN == 96) launch_gemm_p<96, 1>(st, a1, a2, wm, p, tiles);
-      else launch_gemm_p<128, 1>(st, a1, a2, wm, p, tiles);
-    } else {
-      if (BN == 64) launch_gemm_p<64, 3>(st, a1, a2, wm, p, tiles);
-      else if (BN == 96) launch_gemm_p<96, 3>(st, a1, a2, wm, p, tiles);
-      else launch_gemm_p<128, 3>(st, a1, a2, wm, p, tiles);
-    }
-  } else if (tc->np == 1) {     // one tile per CTA (A/B measurements)
-    if (w.BN == 64) launch_k(k_gemm_tc<64, 1>, grid, TcGemmCfg<64, 1>::THREADS, TcGemmCfg<64, 1>::SMEM, st, a1, a2, w.map, p);
-    else if (w.BN == 96) launch_k(k_gemm_tc<96, 1>, grid, TcGemmCfg<96, 1>::THREADS, TcGemmCfg<96, 1>::SMEM, st, a1, a2, w.map, p);
-    else launch_k(k_gemm_tc<128, 1>, grid, TcGemmCfg<128, 1>::THREADS, TcGemmCfg<128, 1>::SMEM, st, a1, a2, w.map, p);
-  } else {
-    if (w.BN == 64) launch_k(k_gemm_tc<64, 3>, grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, a1, a2, w.map, p);
-    else if (w.BN == 96) launch_k(k_gemm_tc<96, 3>, grid, TcGemmCfg<96, 3>::THREADS, TcGemmCfg<96, 3>::SMEM, st, a1, a2, w.map, p);
-    else launch_k(k_gemm_tc<128, 3>, grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, a1, a2, w.map, p);
-  }
+  // (128-wide tiles for the N = 256 / 768 GEMMs of a large batch were measured: no gain over the 64 / 96-wide defaults)
+  launch_gemm(tc->np, w.BN, st, a1, a2, w.map, p, tiles);
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
   if (launches) ++*launches;
   B2S_LAUNCH_CHECK();
@@ -354,8 +359,17 @@ static int tc_attention(LgTensorCore* tc, cudaStream_t st, int ld, int nseg, int
     ap.plane_rows = 2 * tc->pcap * tc->cap;
     ap.scale_log2e = scale_log2e; ap.out = tc->ctxb; ap.ldo = 256; ap.out_plane = (size_t)ap.plane_rows * 256; ap.ctrl = tc->ctrl;
     ap.stats = (tc->prof && tc->prof->on) ? tc->stats : nullptr;
-    launch_k(k_attn_tc3, grid, A3_THREADS, A3_SMEM, st, ld == 768 ? tc->m_qkv768 : tc->m_qkv512,
-             ld == 768 ? tc->m_kv768 : tc->m_kv512, ap);
+    if (tc->np == 2) {
+      // q, k, v arrive prescaled by 16 (S is 256 x too large), P is stored as 2^7 P: O = 2^11 x the true numerator
+      ap.scale_log2e = scale_log2e / (tc::H2_ATTN_PRESCALE * tc::H2_ATTN_PRESCALE);
+      ap.out_scale = 1.f / (tc::H2_ATTN_PRESCALE * A3_P_PRESCALE);
+      ap.range_flag = tc->range_flag;
+      launch_k(k_attn_tc3<2>, grid, A3_THREADS, A3Cfg<2>::SMEM, st, ld == 768 ? tc->m_qkv768 : tc->m_qkv512,
+               ld == 768 ? tc->m_kv768 : tc->m_kv512, ap);
+    } else {
+      launch_k(k_attn_tc3<3>, grid, A3_THREADS, A3Cfg<3>::SMEM, st, ld == 768 ? tc->m_qkv768 : tc->m_qkv512,
+               ld == 768 ? tc->m_kv768 : tc->m_kv512, ap);
+    }
   }
   if (tc->prof) tc->prof->mark(PROF_ATTN, st);
   if (launches) ++*launches;
@@ -370,8 +384,9 @@ static int tc_ffn(LgTensorCore* tc, cudaStream_t st, float* x, const TcLinear& w
   B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_ctxb, 256, w1, p, nseg, maxrows, launches));          // [x | ctx] W1'^T + b1' (out_proj folded)
   dim3 g(cdiv(maxrows, 8), nseg);
   const size_t hplane = (size_t)2 * tc->pcap * tc->cap * 512;
-  if (tc->np == 1) launch_k(k_ln_gelu_512_bf16<1>, g, 256, 0, st, tc->h1f, tc->h1b, hplane, tc->cap, lng, lnb, tc->ctrl);
-  else launch_k(k_ln_gelu_512_bf16<3>, g, 256, 0, st, tc->h1f, tc->h1b, hplane, tc->cap, lng, lnb, tc->ctrl);
+  if (tc->np == 1) launch_k(k_ln_gelu_512_bf16<1>, g, 256, 0, st, tc->h1f, tc->h1b, hplane, tc->cap, lng, lnb, tc->ctrl, tc->range_flag);
+  else if (tc->np == 2) launch_k(k_ln_gelu_512_bf16<2>, g, 256, 0, st, tc->h1f, tc->h1b, hplane, tc->cap, lng, lnb, tc->ctrl, tc->range_flag);
+  else launch_k(k_ln_gelu_512_bf16<3>, g, 256, 0, st, tc->h1f, tc->h1b, hplane, tc->cap, lng, lnb, tc->ctrl, tc->range_flag);
   if (launches) ++*launches;
   B2S_LAUNCH_CHECK();
   p = TcGemmParams();
@@ -392,11 +407,12 @@ int lgtc_set_final(LgTensorCore* tc, const std::vector<const float*>& w, const s
   TcLinear& o = tc->wfinal;
   o.N = (int)L * 256; o.K = 256; o.bias = ball; o.BN = 64;
   const size_t n = L * 256 * 256;
-  B2S_TRY(tc->warena.alloc(&o.w, 3 * n));
-  k_weight_planes<<<(unsigned)((n + 255) / 256), 256>>>(wall, o.w, o.N, 256, 3);
+  const int F = tc->npf;
+  B2S_TRY(tc->warena.alloc(&o.w, F * n));
+  k_weight_planes<<<(unsigned)((n + 255) / 256), 256>>>(wall, o.w, o.N, 256, F, tc->range_flag);
   B2S_LAUNCH_CHECK();
   B2S_CUDA(cudaDeviceSynchronize());
-  return make_tmap_bf16_2d(&o.map, o.w, 3 * 256, o.N, 3 * 256 * 2, 64, 64);
+  return make_tmap_bf16_2d(&o.map, o.w, (uint64_t)F * 256, o.N, (uint64_t)F * 256 * 2, 64, 64);
 }
 
 // Input projection on the tensor cores, always fp32-faithful: x = din W_in^T + b (din = descriptor planes written by
@@ -408,10 +424,9 @@ int lgtc_input_proj(LgTensorCore* tc, cudaStream_t st, float* x, int nseg, int m
   p.seg_stride = tc->cap; p.tiles_per_seg = cdiv(maxrows, 128);
   p.plane_rows = 2 * tc->pcap * tc->cap;
   p.epi = TC_EPI_F32_BF16; p.out_f32 = x; p.ld_f32 = 256; p.out_bf16 = tc->xb; p.ld_bf16 = 256;
-  p.out_plane = (size_t)p.plane_rows * 256; p.out_planes = tc->np;
+  p.out_plane = (size_t)p.plane_rows * 256; p.out_planes = tc->np; p.range_flag = tc->range_flag;
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
-  if (gemm_persistent()) launch_gemm_p<64, 3>(st, tc->m_din, tc->m_din, tc->win.map, p, nseg * p.tiles_per_seg);
-  else launch_k(k_gemm_tc<64, 3>, dim3(4, nseg * p.tiles_per_seg), TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, tc->m_din, tc->m_din, tc->win.map, p);
+  launch_gemm(tc->npf, 64, st, tc->m_din, tc->m_din, tc->win.map, p, nseg * p.tiles_per_seg);
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
   if (launches) ++*launches;
   B2S_LAUNCH_CHECK();
@@ -431,16 +446,15 @@ int lgtc_assignment(LgTensorCore* tc, cudaStream_t st, int npairs, int maxm, int
   p.K = 256; p.K1 = 256; p.N = 256; p.bias = tc->bfinal; p.ctrl = ctrl; p.ctrl_mode = 2; p.w_layer_rows = 256; p.alpha = 0.25f;
   p.seg_stride = cap; p.tiles_per_seg = cdiv(std::max(maxm, maxn), 128);
   p.plane_rows = plane_rows; p.epi = TC_EPI_BF16; p.out_bf16 = tc->md; p.ld_bf16 = 256; p.out_plane = plane;
+  p.range_flag = tc->range_flag;
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
-  if (gemm_persistent()) launch_gemm_p<64, 3>(st, tc->m_tx, tc->m_tx, tc->wfinal.map, p, 2 * npairs * p.tiles_per_seg);
-  else launch_k(k_gemm_tc<64, 3>, dim3(4, 2 * npairs * p.tiles_per_seg), TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM, st, tc->m_tx, tc->m_tx, tc->wfinal.map, p);
+  launch_gemm(tc->npf, 64, st, tc->m_tx, tc->m_tx, tc->wfinal.map, p, 2 * npairs * p.tiles_per_seg);
   p = TcGemmParams();
   p.K = 256; p.K1 = 256; p.N = maxn; p.bias = nullptr; p.ctrl = ctrl; p.ctrl_mode = 3;
   p.w_plane_rows = plane_rows; p.seg_stride = cap; p.tiles_per_seg = cdiv(maxm, 128);
   p.plane_rows = plane_rows; p.epi = TC_EPI_F32; p.out_f32 = sim; p.ld_f32 = cap; p.out_f32_t = simT; p.ld_f32_t = cap;
   p.out_pair_stride = (size_t)cap * cap;
-  if (gemm_persistent()) launch_gemm_p<128, 3>(st, tc->m_md, tc->m_md, tc->m_md, p, npairs * p.tiles_per_seg);
-  else launch_k(k_gemm_tc<128, 3>, dim3(cdiv(maxn, 128), npairs * p.tiles_per_seg), TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM, st, tc->m_md, tc->m_md, tc->m_md, p);
+  launch_gemm(tc->npf, 128, st, tc->m_md, tc->m_md, tc->m_md, p, npairs * p.tiles_per_seg);
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
   if (launches) *launches += 2;
   B2S_LAUNCH_CHECK();
@@ -451,6 +465,8 @@ __nv_bfloat16* lgtc_xb(LgTensorCore* tc) { return tc->xb; }
 __nv_bfloat16* lgtc_din(LgTensorCore* tc) { return tc->din; }
 __nv_bfloat16* lgtc_tx(LgTensorCore* tc) { return tc->tx; }
 int lgtc_planes(LgTensorCore* tc) { return tc->np; }
+int lgtc_faithful_planes(LgTensorCore* tc) { return tc->npf; }
+int* lgtc_range_flag(LgTensorCore* tc) { return tc->range_flag; }
 
 // One transformer layer over nseg segments (2 per pair).  maxrows bounds the live point counts (it sizes the grids); the
 // live counts and the early-exit flags are read from `ctrl` on the device.  `x` is the fp32 residual stream of this layer;
@@ -461,12 +477,12 @@ int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int li, float* x, const float*
   tc->ctrl = ctrl;
   TcGemmParams p = {};
   // ---- self block ----
-  p.epi = TC_EPI_ROTARY_BF16; p.out_bf16 = tc->qkvb; p.ld_bf16 = 768; p.rot_cos = cosb; p.rot_sin = sinb; p.rot_cols = 512;
+  p.epi = TC_EPI_ROTARY_BF16; p.out_bf16 = tc->qkvb; p.ld_bf16 = 768; p.rot_cos = cosb; p.rot_sin = sinb; p.rot_cols = 512; p.attn_fmt = 1;
   B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_xb, 256, l.qkv, p, nseg, maxrows, launches));
   B2S_TRY(tc_attention(tc, st, 768, nseg, maxrows, 0, 256, 512, 0, launches));
   B2S_TRY(tc_ffn(tc, st, x, l.w1, l.lng, l.lnb, l.w2, nseg, maxrows, launches));
   // ---- cross block ----
-  p = TcGemmParams(); p.epi = TC_EPI_BF16; p.out_bf16 = tc->qkvb; p.ld_bf16 = 512;
+  p = TcGemmParams(); p.epi = TC_EPI_BF16; p.out_bf16 = tc->qkvb; p.ld_bf16 = 512; p.attn_fmt = 1;
   B2S_TRY(tc_gemm(tc, st, tc->m_xb, tc->m_xb, 256, l.cqkv, p, nseg, maxrows, launches));
   B2S_TRY(tc_attention(tc, st, 512, nseg, maxrows, 0, 0, 256, 1, launches));
   return tc_ffn(tc, st, x, l.cw1, l.clng, l.clnb, l.cw2, nseg, maxrows, launches);
@@ -477,12 +493,22 @@ int lgtc_layer(LgTensorCore* tc, cudaStream_t st, int li, float* x, const float*
 // ---- unit-test entry points (host buffers) --------------------------------------------------
 using namespace b2s;
 
-// host fp32 [rows, cols] -> np bf16 planes [np][rows_pad, cols] (zero padded)
-static std::vector<__nv_bfloat16> to_planes(const float* x, size_t rows, size_t cols, size_t rows_pad, int np) {
+// host fp32 [rows, cols] -> np operand planes [np][rows_pad, cols] (zero padded).  np = 2: fp16 pair, GEMM format
+// (scaled residual) or - attn_fmt - attention format (prescaled by 16, unscaled residual)
+static std::vector<__nv_bfloat16> to_planes(const float* x, size_t rows, size_t cols, size_t rows_pad, int np, bool attn_fmt = false) {
   std::vector<__nv_bfloat16> v((size_t)np * rows_pad * cols, __float2bfloat16_rn(0.f));
+  __half* hv = reinterpret_cast<__half*>(v.data());
   for (size_t i = 0; i < rows; ++i)
     for (size_t c = 0; c < cols; ++c) {
       float r = x[i * cols + c];
+      if (np == 2) {
+        if (attn_fmt) r *= tc::H2_ATTN_PRESCALE;
+        const __half h0 = __float2half_rn(r);
+        const float res = r - __half2float(h0);
+        hv[i * cols + c] = h0;
+        hv[(rows_pad + i) * cols + c] = __float2half_rn(attn_fmt ? res : res * tc::H2_RS);
+        continue;
+      }
       for (int p = 0; p < np; ++p) {
         const __nv_bfloat16 b = __float2bfloat16_rn(r);
         v[((size_t)p * rows_pad + i) * cols + c] = b;
@@ -516,18 +542,7 @@ static int test_gemm(const float* A, const float* W, const float* bias, int M, i
   TcGemmParams p = {};
   p.K = K; p.K1 = K; p.N = N; p.bias = dB; p.epi = TC_EPI_F32; p.out_f32 = dC; p.ld_f32 = N; p.plane_rows = Mp;
   p.seg_stride = 0; p.seg_rows = M; p.tiles_per_seg = cdiv(M, 128);
-  dim3 grid(N / BN, p.tiles_per_seg);
-  if (gemm_persistent()) {
-    cudaStream_t st = 0;
-    if (np == 1) { if (BN == 64) launch_gemm_p<64, 1>(st, ma, ma, mw, p, p.tiles_per_seg); else launch_gemm_p<128, 1>(st, ma, ma, mw, p, p.tiles_per_seg); }
-    else { if (BN == 64) launch_gemm_p<64, 3>(st, ma, ma, mw, p, p.tiles_per_seg); else launch_gemm_p<128, 3>(st, ma, ma, mw, p, p.tiles_per_seg); }
-  } else if (np == 1) {
-    if (BN == 64) k_gemm_tc<64, 1><<<grid, TcGemmCfg<64, 1>::THREADS, TcGemmCfg<64, 1>::SMEM>>>(ma, ma, mw, p);
-    else k_gemm_tc<128, 1><<<grid, TcGemmCfg<128, 1>::THREADS, TcGemmCfg<128, 1>::SMEM>>>(ma, ma, mw, p);
-  } else {
-    if (BN == 64) k_gemm_tc<64, 3><<<grid, TcGemmCfg<64, 3>::THREADS, TcGemmCfg<64, 3>::SMEM>>>(ma, ma, mw, p);
-    else k_gemm_tc<128, 3><<<grid, TcGemmCfg<128, 3>::THREADS, TcGemmCfg<128, 3>::SMEM>>>(ma, ma, mw, p);
-  }
+  launch_gemm(np, BN, 0, ma, ma, mw, p, p.tiles_per_seg);
   B2S_LAUNCH_CHECK();
   B2S_CUDA(cudaDeviceSynchronize());
   B2S_CUDA(cudaMemcpy(C, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
@@ -539,14 +554,16 @@ extern "C" int b2s_test_gemm_tc(const float* A, const float* W, const float* bia
 extern "C" int b2s_test_gemm_tc3(const float* A, const float* W, const float* bias, int M, int N, int K, float* C) {
   return test_gemm(A, W, bias, M, N, K, C, 3);
 }
+extern "C" int b2s_test_gemm_h2(const float* A, const float* W, const float* bias, int M, int N, int K, float* C) {
+  return test_gemm(A, W, bias, M, N, K, C, 2);
+}
 
 // Device-only timing of one layer GEMM shape (bf16x3 planes in, planes out like the QKV / FFN epilogues), `iters` launches
 // back to back on one stream with programmatic dependent launch, optionally as clusters of `cl` CTAs sharing A.
 // ts_out (nullable, host, [tiles*6]): globaltimer stamps of the last launch's CTAs relative to its earliest CTA start:
 // start, dependencies resolved, first stage landed, accumulators complete, epilogue done, end (ns).
-extern "C" int b2s_bench_gemm_tc3(int M, int N, int K, int cl, int iters, float* ms_out, long long* ts_out, int* n_cta_out) {
-  if (M <= 0 || N % 64 || K % 64 || iters <= 0 || !ms_out) { set_error("b2s_bench_gemm_tc3: bad argument"); return B2S_EINVAL; }
-  const int np = 3;
+static int bench_gemm(int np, int M, int N, int K, int cl, int iters, float* ms_out, long long* ts_out, int* n_cta_out) {
+  if (M <= 0 || N % 64 || K % 64 || iters <= 0 || !ms_out) { set_error("b2s_bench_gemm: bad argument"); return B2S_EINVAL; }
   DeviceArena ar;
   const int Mp = cdiv(M, 128) * 128;
   const int BN = N <= 256 ? 64 : (N % 128 == 0 && N != 768 ? 128 : 96);
@@ -555,7 +572,11 @@ extern "C" int b2s_bench_gemm_tc3(int M, int N, int K, int cl, int iters, float*
   B2S_TRY(ar.alloc(&dA, nA)); B2S_TRY(ar.alloc(&dW, nW)); B2S_TRY(ar.alloc(&dO, nO)); B2S_TRY(ar.alloc(&dB, (size_t)N));
   std::vector<__nv_bfloat16> h(std::max(nA, nW));
   uint32_t sd = 777u;
-  for (size_t i = 0; i < h.size(); ++i) { sd = sd * 1664525u + 1013904223u; h[i] = __float2bfloat16_rn(((sd >> 8) & 0xFFFF) / 32768.f - 1.f); }
+  for (size_t i = 0; i < h.size(); ++i) {
+    sd = sd * 1664525u + 1013904223u;
+    const float v = ((sd >> 8) & 0xFFFF) / 32768.f - 1.f;
+    if (np == 2) reinterpret_cast<__half*>(h.data())[i] = __float2half_rn(v); else h[i] = __float2bfloat16_rn(v);
+  }
   B2S_CUDA(cudaMemcpy(dA, h.data(), nA * 2, cudaMemcpyHostToDevice));
   B2S_CUDA(cudaMemcpy(dW, h.data(), nW * 2, cudaMemcpyHostToDevice));
   B2S_CUDA(cudaMemset(dB, 0, (size_t)N * 4));
@@ -573,7 +594,12 @@ extern "C" int b2s_bench_gemm_tc3(int M, int N, int K, int cl, int iters, float*
   B2S_CUDA(cudaStreamCreate(&st));
   auto launch = [&](unsigned long long* ts) {
     TcGemmParams q = p; q.ts = ts;
-    if (cl == 0) {          // persistent tile-scheduler kernel
+    if (np == 2) {
+      if (cl == 0) { if (BN == 96) launch_gemm_p<96, 2>(st, ma, ma, mw, q, Mp / 128); else if (BN == 64) launch_gemm_p<64, 2>(st, ma, ma, mw, q, Mp / 128); else launch_gemm_p<128, 2>(st, ma, ma, mw, q, Mp / 128); }
+      else if (BN == 96) launch_k(k_gemm_tc<96, 2>, grid, TcGemmCfg<96, 2>::THREADS, TcGemmCfg<96, 2>::SMEM, st, ma, ma, mw, q);
+      else if (BN == 64) launch_k(k_gemm_tc<64, 2>, grid, TcGemmCfg<64, 2>::THREADS, TcGemmCfg<64, 2>::SMEM, st, ma, ma, mw, q);
+      else launch_k(k_gemm_tc<128, 2>, grid, TcGemmCfg<128, 2>::THREADS, TcGemmCfg<128, 2>::SMEM, st, ma, ma, mw, q);
+    } else if (cl == 0) {          // persistent tile-scheduler kernel
       if (BN == 96) launch_gemm_p<96, 3>(st, ma, ma, mw, q, Mp / 128);
       else if (BN == 64) launch_gemm_p<64, 3>(st, ma, ma, mw, q, Mp / 128);
       else launch_gemm_p<128, 3>(st, ma, ma, mw, q, Mp / 128);
@@ -607,6 +633,13 @@ extern "C" int b2s_bench_gemm_tc3(int M, int N, int K, int cl, int iters, float*
   return 0;
 }
 
+extern "C" int b2s_bench_gemm_tc3(int M, int N, int K, int cl, int iters, float* ms_out, long long* ts_out, int* n_cta_out) {
+  return bench_gemm(3, M, N, K, cl, iters, ms_out, ts_out, n_cta_out);
+}
+extern "C" int b2s_bench_gemm_h2(int M, int N, int K, int cl, int iters, float* ms_out, long long* ts_out, int* n_cta_out) {
+  return bench_gemm(2, M, N, K, cl, iters, ms_out, ts_out, n_cta_out);
+}
+
 // uploads q | k | v as [np][R, 768] planes and launches one attention (z problems); ctx planes come back summed
 static int run_attn(int np, const std::vector<__nv_bfloat16>& buf, int R, const AttnTcProb (&prob)[2], int nz, int maxq, int iters,
                     float* ms_out, float* ctx, int nq_out, long long* trace_out = nullptr) {
@@ -625,12 +658,14 @@ static int run_attn(int np, const std::vector<__nv_bfloat16>& buf, int R, const 
   Attn3Params a3 = {};
   a3.qcol = 0; a3.kcol = 256; a3.vcol = 512; a3.prob[0] = prob[0]; a3.prob[1] = prob[1]; a3.scale_log2e = sc; a3.out = dctx; a3.ldo = 256;
   a3.plane_rows = R; a3.out_plane = (size_t)R * 256; a3.pv_issuers = attn_pv_issuers();
+  if (np == 2) { a3.scale_log2e = sc / (tc::H2_ATTN_PRESCALE * tc::H2_ATTN_PRESCALE); a3.out_scale = 1.f / (tc::H2_ATTN_PRESCALE * A3_P_PRESCALE); }
   long long* dtrace = nullptr;
   if (trace_out) { B2S_TRY(ar.alloc(&dtrace, (size_t)3 * 64 * 8)); B2S_CUDA(cudaMemset(dtrace, 0, 3 * 64 * 8 * sizeof(long long))); }
   const dim3 grid(cdiv(maxq, 128), 4, nz);
   auto launch = [&]() {
     if (np == 1) k_attn_tc<<<grid, ATC_THREADS, ATC_SMEM>>>(mq, a1);
-    else k_attn_tc3<<<grid, A3_THREADS, A3_SMEM>>>(mq, mkv, a3);
+    else if (np == 2) k_attn_tc3<2><<<grid, A3_THREADS, A3Cfg<2>::SMEM>>>(mq, mkv, a3);
+    else k_attn_tc3<3><<<grid, A3_THREADS, A3Cfg<3>::SMEM>>>(mq, mkv, a3);
   };
   if (iters > 0) {
     cudaEvent_t e0, e1;
@@ -645,7 +680,7 @@ static int run_attn(int np, const std::vector<__nv_bfloat16>& buf, int R, const 
     B2S_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     *ms_out = ms / iters;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (trace_out && np == 3) {
+    if (trace_out && np != 1) {
       a3.trace = dtrace; a3.trace_cta = trace_out[0] > 0 ? (int)trace_out[0] : 0;
       launch();
       B2S_LAUNCH_CHECK();
@@ -661,7 +696,12 @@ static int run_attn(int np, const std::vector<__nv_bfloat16>& buf, int R, const 
   B2S_CUDA(cudaMemcpy(out.data(), dctx, out.size() * 2, cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < (size_t)nq_out * 256; ++i) {
     float acc = 0.f;
-    for (int p = np - 1; p >= 0; --p) acc += __bfloat162float(out[(size_t)p * R * 256 + i]);
+    if (np == 2) {
+      const __half* ho = reinterpret_cast<const __half*>(out.data());
+      acc = __half2float(ho[i]) + __half2float(ho[(size_t)R * 256 + i]) * tc::H2_IRS;
+    } else {
+      for (int p = np - 1; p >= 0; --p) acc += __bfloat162float(out[(size_t)p * R * 256 + i]);
+    }
     ctx[i] = acc;
   }
   return 0;
@@ -677,7 +717,7 @@ static int test_attn(const float* q, const float* k, const float* v, int nq, int
     std::memcpy(&f[(size_t)i * 768 + 256], k + (size_t)i * 256, 256 * 4);
     std::memcpy(&f[(size_t)i * 768 + 512], v + (size_t)i * 256, 256 * 4);
   }
-  std::vector<__nv_bfloat16> buf = to_planes(f.data(), R, 768, R, np);
+  std::vector<__nv_bfloat16> buf = to_planes(f.data(), R, 768, R, np, true);
   const AttnTcProb prob[2] = {{0, 0, nq, nk}, {0, 0, 0, 0}};
   return run_attn(np, buf, R, prob, 1, nq, 0, nullptr, ctx, nq);
 }
@@ -686,6 +726,9 @@ extern "C" int b2s_test_attn_tc(const float* q, const float* k, const float* v, 
 }
 extern "C" int b2s_test_attn_tc3(const float* q, const float* k, const float* v, int nq, int nk, float* ctx) {
   return test_attn(q, k, v, nq, nk, ctx, 3);
+}
+extern "C" int b2s_test_attn_h2(const float* q, const float* k, const float* v, int nq, int nk, float* ctx) {
+  return test_attn(q, k, v, nq, nk, ctx, 2);
 }
 
 // Device-only timing of the attention kernel on random data: one launch = what a LightGlue self
@@ -698,13 +741,20 @@ static int bench_attn(int nq, int nk, int iters, float* ms_out, int np, long lon
   uint32_t s = 12345u;
   for (size_t i = 0; i < buf.size(); ++i) {
     s = s * 1664525u + 1013904223u;
+    const float v = ((s >> 8) & 0xFFFF) / 32768.f - 1.f;
+    if (np == 2) {          // plane 0: 16 x values in [-1, 1); plane 1: residuals (2^-11 of that)
+      reinterpret_cast<__half*>(buf.data())[i] = __float2half_rn(i < (size_t)R * 768 ? 16.f * v : 16.f * v / 2048);
+      continue;
+    }
     const float scale = i < (size_t)R * 768 ? 1.f : (i < (size_t)2 * R * 768 ? 1.f / 256 : 1.f / 65536);   // lower planes are small
-    buf[i] = __float2bfloat16_rn((((s >> 8) & 0xFFFF) / 32768.f - 1.f) * scale);
+    buf[i] = __float2bfloat16_rn(v * scale);
   }
   const AttnTcProb prob[2] = {{0, 0, nq, nk}, {cap, cap, nq, nk}};
   return run_attn(np, buf, R, prob, 2, nq, iters, ms_out, nullptr, 0, trace_out);
 }
 extern "C" int b2s_bench_attn_tc(int nq, int nk, int iters, float* ms_out) { return bench_attn(nq, nk, iters, ms_out, 1); }
 extern "C" int b2s_bench_attn_tc3(int nq, int nk, int iters, float* ms_out) { return bench_attn(nq, nk, iters, ms_out, 3); }
+extern "C" int b2s_bench_attn_h2(int nq, int nk, int iters, float* ms_out) { return bench_attn(nq, nk, iters, ms_out, 2); }
+extern "C" int b2s_trace_attn_h2(int nq, int nk, int iters, float* ms_out, long long* trace_out) { return bench_attn(nq, nk, iters, ms_out, 2, trace_out); }
 // same + clock64 stamps of CTA (0,0,0) of one extra launch: trace_out [3 roles (MMA thread, softmax group 0 / 1)][64 tiles][8 events]
 extern "C" int b2s_trace_attn_tc3(int nq, int nk, int iters, float* ms_out, long long* trace_out) { return bench_attn(nq, nk, iters, ms_out, 3, trace_out); }

@@ -1,5 +1,6 @@
-// lightglue_tc.cuh - tcgen05/TMEM path of the LightGlue layers (interface): bf16 operands (planes = 1)
-// or fp32 carried as three bf16 planes (planes = 3, fp32-faithful).  Everything is batched over row SEGMENTS
+// lightglue_tc.cuh - tcgen05/TMEM path of the LightGlue layers (interface): bf16 operands (planes = 1),
+// fp32 carried as three bf16 planes (planes = 3, fp32-faithful, any range) or as two fp16 planes (planes = 2,
+// fp32-faithful at half the tensor-core work, values must stay inside the fp16 range - checked on the device).  Everything is batched over row SEGMENTS
 // (lightglue_kernels.cuh): segment 2p + s = image s of pair p, `cap` rows apart.
 #pragma once
 #include <cuda_bf16.h>
@@ -33,6 +34,8 @@ __nv_bfloat16* lgtc_xb(LgTensorCore* tc);    // bf16 plane copy of the residual 
 __nv_bfloat16* lgtc_din(LgTensorCore* tc);   // [3][rows,128] descriptor planes (written by k_lg_posenc)
 __nv_bfloat16* lgtc_tx(LgTensorCore* tc);    // [3][rows,256] planes of the final state (written by k_lg_final_prep)
 int lgtc_planes(LgTensorCore* tc);
+int lgtc_faithful_planes(LgTensorCore* tc);   // planes of din / tx / md: 3, or 2 on the fp16x2 path
+int* lgtc_range_flag(LgTensorCore* tc);       // device [2]: sticky fp16 range flag, arrival counter (k_lg_filter)
 void lgtc_destroy(LgTensorCore* tc);
 void lgtc_set_prof(LgTensorCore* tc, KernelProf* prof, unsigned long long* stats);
 

@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace b2s {
@@ -180,6 +181,16 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, 
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with fp16 A/B (format code 0)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// instruction descriptor of the operand-plane scheme NP (1, 3: bf16 planes; 2: fp16 planes)
+template <int NP>
+__host__ __device__ constexpr uint32_t idesc_planes(int M, int N, int a_mn_major, int b_mn_major) {
+  return NP == 2 ? idesc_f16(M, N, a_mn_major, b_mn_major) : idesc_bf16(M, N, a_mn_major, b_mn_major);
+}
 
 // ---- fp32 carried as bf16 planes --------------------------------------------------------------
 // x = a0 + a1 + a2 exactly up to 24 significant bits (each a_i a bf16, a_{i+1} = bf16(residual)):
@@ -190,8 +201,42 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+// ---- fp32 carried as TWO fp16 planes ("h2", NP == 2) --------------------------------------------
+// x = h0 + h1 * 2^-11 with h0 = fp16(x) and h1 = fp16((x - h0) * 2^11): 22 significant bits whatever the magnitude
+// of x (the scaled residual is as far from the fp16 subnormal range as x itself), and a product x*w needs only the
+// THREE cross terms h0*w0 (main) and h0*w1 + h1*w0 (corrections, accumulated separately and weighted 2^-11 by the
+// epilogue; the dropped h1*w1 is 2^-22 of the product) - half the tensor-core work of the bf16x3 scheme at an
+// operand error (2^-23 rms) that stays below the fp32 rounding noise of the accumulation itself.  The price is
+// fp16's exponent range: |x| must stay below 65504.  Every producer of h2 planes therefore checks the packed words
+// for infinities (h2_ovf) and raises a sticky device flag; the matcher re-runs a flagged batch on the bf16x3 path.
+// Attention operands (q, k, v, P: a contraction there has ONE accumulator) use the unscaled variant
+// h1 = fp16(s*x - h0), h0 = fp16(s*x) with a fixed power-of-two prescale s (H2_ATTN_PRESCALE; P: 2^14, P <= 1).
+constexpr float H2_RS = 2048.f;                 // residual scale 2^11
+constexpr float H2_IRS = 1.f / 2048.f;
+constexpr float H2_ATTN_PRESCALE = 16.f;        // q, k, v are stored as 16 x
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+// nonzero iff one of the two fp16 halves of w is +-inf or nan
+__device__ __forceinline__ uint32_t h2_ovf(uint32_t w) { return ((w & 0x7FFF7FFFu) + 0x04000400u) & 0x80008000u; }
+// GEMM operand format (scaled residual)
+__device__ __forceinline__ void pack_h2(float a, float b, uint32_t& w0, uint32_t& w1) {
+  w0 = pack_f16x2(a, b);
+  const float2 f = unpack_f16x2(w0);
+  w1 = pack_f16x2((a - f.x) * H2_RS, (b - f.y) * H2_RS);
+}
+// attention operand format (prescaled by s, unscaled residual)
+__device__ __forceinline__ void pack_h2_attn(float a, float b, float s, uint32_t& w0, uint32_t& w1) {
+  a *= s; b *= s;
+  w0 = pack_f16x2(a, b);
+  const float2 f = unpack_f16x2(w0);
+  w1 = pack_f16x2(a - f.x, b - f.y);
+}
 template <int NP>
 __device__ __forceinline__ void pack_planes2(float a, float b, uint32_t (&w)[NP]) {
+  if (NP == 2) { pack_h2(a, b, w[0], w[NP - 1]); return; }
   w[0] = pack_bf16x2(a, b);
   if (NP > 1) {
     a -= __uint_as_float(w[0] << 16); b -= __uint_as_float(w[0] & 0xFFFF0000u);
@@ -203,9 +248,10 @@ __device__ __forceinline__ void pack_planes2(float a, float b, uint32_t (&w)[NP]
   }
 }
 }  // namespace tc
-// store 8 consecutive values of one row as NP bf16 planes (plane p at y + p * plane)
+// store 8 consecutive values of one row as NP operand planes (plane p at y + p * plane); NP == 2: returns nonzero when a
+// value left the fp16 range (the caller raises the matcher's range flag)
 template <int NP>
-__device__ __forceinline__ void store_planes8(__nv_bfloat16* y, size_t plane, const float (&f)[8]) {
+__device__ __forceinline__ uint32_t store_planes8(__nv_bfloat16* y, size_t plane, const float (&f)[8]) {
   uint32_t w[NP][4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -216,16 +262,20 @@ __device__ __forceinline__ void store_planes8(__nv_bfloat16* y, size_t plane, co
   }
 #pragma unroll
   for (int pl = 0; pl < NP; ++pl) *reinterpret_cast<uint4*>(y + pl * plane) = make_uint4(w[pl][0], w[pl][1], w[pl][2], w[pl][3]);
+  if (NP != 2) return 0u;
+  return tc::h2_ovf(w[0][0]) | tc::h2_ovf(w[0][1]) | tc::h2_ovf(w[0][2]) | tc::h2_ovf(w[0][3]);
 }
 
 namespace tc {
 
 // operand-plane pairs (a_i, b_j) of the split product, smallest contributions first
 template <int NP> struct PlaneTerms {
-  static constexpr int N = NP == 1 ? 1 : 6;
-  // NP == 3: (2,0) (1,1) (0,2) (1,0) (0,1) (0,0)
-  __host__ __device__ static constexpr int a(int t) { return NP == 1 ? 0 : (t == 0 ? 2 : (t == 1 || t == 3) ? 1 : 0); }
-  __host__ __device__ static constexpr int b(int t) { return NP == 1 ? 0 : (t == 2 ? 2 : (t == 1 || t == 4) ? 1 : 0); }
+  static constexpr int N = NP == 1 ? 1 : NP == 2 ? 3 : 6;
+  // NP == 3: (2,0) (1,1) (0,2) (1,0) (0,1) (0,0)      NP == 2: (1,0) (0,1) (0,0)
+  __host__ __device__ static constexpr int a(int t) { return NP == 1 ? 0 : NP == 2 ? (t == 0 ? 1 : 0) : (t == 0 ? 2 : (t == 1 || t == 3) ? 1 : 0); }
+  __host__ __device__ static constexpr int b(int t) { return NP == 1 ? 0 : NP == 2 ? (t == 1 ? 1 : 0) : (t == 2 ? 2 : (t == 1 || t == 4) ? 1 : 0); }
+  // weight of the correction accumulator (every term but the last) in the epilogue's sum
+  static constexpr float CORR = NP == 2 ? 1.f / 2048.f : 1.f;
 };
 
 }  // namespace tc

@@ -273,9 +273,29 @@ class LightGlue(_Module):
         self._param = torch.empty(1, device=dev)
 
     def _destroy(self):
+        self._fb = None
         if getattr(self, "_handle", None):
             lib.b2s_lg_destroy(self._handle)
             self._handle = None
+
+    # -- precision="fp32" runs on fp16x2 operand planes (include/b200slam.h); a launch sequence in which a value left the
+    #    fp16 range reports n = LG_RANGE for its pairs and is re-run on the bf16x3 engine (any range, twice the MMA work)
+    def fallback(self):
+        """The precision='fp32x3' matcher with the same weights and settings (created on first use)."""
+        if getattr(self, "_fb", None) is None:
+            fb = object.__new__(LightGlue)
+            fb.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ("_handle", "_fb", "_param", "_mx_cap", "_mx_dev", "_mx_pin")})
+            fb.precision = "fp32x3"
+            fb._handle = None
+            fb._create(self.device)
+            self._fb = fb
+        self.range_fallbacks = getattr(self, "range_fallbacks", 0) + 1
+        return self._fb
+
+    @property
+    def planes(self) -> int:
+        """Operand planes of the engine actually in use: 1 bf16, 2 fp16x2, 3 bf16x3."""
+        return int(lib.b2s_lg_planes(self._handle))
 
     def match_device(self, k0, d0, k1, d1, size0=None, size1=None, full=True):
         """CUDA f32 tensors k [m,2], d [m,128]; enqueues on the current stream WITHOUT any host
@@ -321,6 +341,8 @@ class LightGlue(_Module):
             r = self.match_device(k0[0], e0[0], k1[0], e1[0], sz[0], sz[1], full=True)
             torch.cuda.current_stream(self.device).synchronize()
             nm = int(r["n"].item())
+            if nm == _lib.LG_RANGE:
+                return self.fallback()(data)
             return {"matches0": r["matches0"].long()[None], "matches1": r["matches1"].long()[None],
                     "matching_scores0": r["matching_scores0"][None], "matching_scores1": r["matching_scores1"][None],
                     "stop": int(r["stop"].item()), "matches": [r["matches"][:nm].long()], "scores": [r["scores"][:nm]],
@@ -369,6 +391,20 @@ class LightGlue(_Module):
                                                out["stop"].data_ptr()), "b2s_lightglue_match_batch")
         return out
 
+    def resolve_range(self, out, kpts, desc, cu, pair_i, pair_j, max_batch=0, counts=None, counts_dev=None) -> int:
+        """Synchronises and re-runs, on the bf16x3 engine, the pairs of a `match_batch_packed` result that report
+        n == LG_RANGE (precision='fp32' only; same arguments as that call).  Returns how many pairs were re-run."""
+        n = out["n"].cpu().numpy()
+        bad = np.nonzero(n[: len(pair_i)] == _lib.LG_RANGE)[0]
+        if len(bad) == 0:
+            return 0
+        pi = np.ascontiguousarray(np.asarray(pair_i, np.int32)[bad]); pj = np.ascontiguousarray(np.asarray(pair_j, np.int32)[bad])
+        r = self.fallback().match_batch_packed(kpts, desc, cu, pi, pj, int(out["matches"].shape[1]), max_batch, None, counts, counts_dev)
+        idx = torch.as_tensor(bad, device=self.device, dtype=torch.long)
+        for k in ("matches", "scores", "n", "stop"):
+            out[k][idx] = r[k][: len(bad)]
+        return int(len(bad))
+
     def match_batch_device(self, kpts_list, desc_list, pairs, stride=None, max_batch=0):
         """kpts_list[f] [n_f,2], desc_list[f] [n_f,128] CUDA f32; pairs = [(i, j), ...] frame indices."""
         with torch.cuda.device(self.device):
@@ -378,6 +414,8 @@ class LightGlue(_Module):
             pi = np.asarray([p[0] for p in pairs], np.int32); pj = np.asarray([p[1] for p in pairs], np.int32)
             out = self.match_batch_packed(kp, de, cu, pi, pj, stride, max_batch)
             out["_keepalive"] = (kp, de)       # the packed inputs must outlive the enqueued kernels
+            if self.precision == "fp32":
+                self.resolve_range(out, kp, de, cu, pi, pj, max_batch)
             return out
 
     def match_mixed(self, k0, d0, k1, d1):
@@ -413,6 +451,10 @@ class LightGlue(_Module):
             st.synchronize()
             hp = self._mx_pin.numpy()
             nm, stop = int(hp[0]), int(hp[1])
+            if nm == _lib.LG_RANGE:
+                r = self.fallback().match_mixed(k0, d0, k1, d1)
+                r["h2d_bytes"] += h2d
+                return r
             matches = hp[4: 4 + 2 * nm].reshape(nm, 2).copy()
             scores = hp[4 + 2 * c: 4 + 2 * c + nm].view(np.float32).copy()
             return {"matches": matches, "scores": scores, "stop": stop, "h2d_bytes": h2d}

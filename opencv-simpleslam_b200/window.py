@@ -15,11 +15,13 @@ from . import _lib, sharding
 
 
 def match_keyframe_window(frames: List[torch.Tensor], det, mat, H: int, W: int, rank: int = 0, world: int = 1, group=None,
-                          max_batch: int = 0, timing: dict | None = None, lanes: int = 8
+                          max_batch: int = 0, timing: dict | None = None, lanes: int = 8, check_range: bool = True
                           ) -> Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
     """frames: u8 BGR HWC CUDA tensors of ALL keyframes of the window (each rank only touches its own).
     Returns {(i, j): (matches int32 [stride,2], scores f32 [stride], n int32 [])} for the pairs this rank owns; tensors
-    stay on the device (rows >= n are undefined).  timing (optional dict) receives CUDA events around the gather."""
+    stay on the device (rows >= n are undefined).  timing (optional dict) receives CUDA events around the gather.
+    check_range (precision='fp32' matcher only): read the match counts back once and re-run pairs that left the fp16
+    operand range on the bf16x3 engine (LightGlue.resolve_range); False leaves n = LG_RANGE for the caller to handle."""
     dev = det.device
     n_kf, max_kp = len(frames), det.n_limit
     mine = sharding.frames_of_rank(n_kf, rank, world)
@@ -46,6 +48,8 @@ def match_keyframe_window(frames: List[torch.Tensor], det, mat, H: int, W: int, 
     pi = np.asarray([slot_of(i) for i, _ in my_pairs], np.int32)
     pj = np.asarray([slot_of(j) for _, j in my_pairs], np.int32)
     # the keypoint counts stay on the device (counts_dev): the host passes the slot capacity and never waits for them
-    r = mat.match_batch_packed(kp_all, de_all, offs, pi, pj, stride=max_kp, max_batch=max_batch,
-                               counts=np.full(world * slots, max_kp, np.int32), counts_dev=counts)
+    caps = np.full(world * slots, max_kp, np.int32)
+    r = mat.match_batch_packed(kp_all, de_all, offs, pi, pj, stride=max_kp, max_batch=max_batch, counts=caps, counts_dev=counts)
+    if check_range and mat.precision == "fp32":
+        mat.resolve_range(r, kp_all, de_all, offs, pi, pj, max_batch, caps, counts)
     return {pair: (r["matches"][p], r["scores"][p], r["n"][p]) for p, pair in enumerate(my_pairs)}
