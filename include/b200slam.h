@@ -113,6 +113,9 @@ int b2s_aliked_extract(b2s_aliked* h, const void* img_dev, int img_format, int H
 int b2s_aliked_extract_batch(b2s_aliked* h, const void* const* imgs_dev, int B, int img_format, int H, int W,
                              int row_stride, int n_lanes, void* stream, float* kpts_dev, float* desc_dev,
                              float* scores_dev, int32_t* n_out_dev);
+/* eps > 0: b2s_aliked_extract_batch also applies `des /= (||des||_2 + eps)` (features_utils.py:100, eps = 1e-8) on the
+ * device, as b2s_aliked_extract_host_ex does for single frames; 0 (default) switches it off. */
+int b2s_aliked_set_batch_renorm(b2s_aliked* h, float eps);
 
 /* same, host buffers; copies in/out, synchronises, returns the count in *n_out. */
 int b2s_aliked_extract_host(b2s_aliked* h, const void* img_host, int img_format, int H, int W,

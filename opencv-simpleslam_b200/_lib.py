@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200slam.so")
+LIB_PATH = os.environ.get("B2S_LIB_PATH") or os.path.join(_HERE, "libb200slam.so")   # B2S_LIB_PATH: A/B builds of the library (development)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -44,6 +44,7 @@ SIGNATURES = {
     "b2s_aliked_destroy": (None, [vp]),
     "b2s_aliked_extract": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, f32p, f32p, f32p, i32p]),
     "b2s_aliked_extract_batch": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, f32p, f32p, f32p, i32p]),
+    "b2s_aliked_set_batch_renorm": (C.c_int, [vp, C.c_float]),
     "b2s_aliked_extract_host": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, i32p]),
     "b2s_aliked_extract_host_ex": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, i32p, C.c_float]),
     "b2s_aliked_extract_host_begin": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),

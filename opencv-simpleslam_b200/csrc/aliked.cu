@@ -60,6 +60,7 @@ struct b2s_aliked {
   float *hkp = nullptr, *hdesc = nullptr, *hscores = nullptr; int32_t* hn = nullptr;
   long long launches = 0;
   float desc_renorm_eps = 0.f;                           // set per call by b2s_aliked_extract_host_ex
+  float batch_renorm_eps = 0.f;                          // b2s_aliked_set_batch_renorm: what b2s_aliked_extract_batch applies
   // split host API (begin / keypoints / finish): pinned staging for the early keypoint copy
   float* pin_kp = nullptr; int32_t* pin_n = nullptr; cudaEvent_t ev_kp = nullptr; bool early_kp = false; bool pending = false;  b2s_remap* undist = nullptr;                           // optional ingest stage (b2s_aliked_set_undistort); borrowed
   // batched extraction (b2s_aliked_extract_batch): extra LANES = complete extractors (own workspace, own stream) created
@@ -657,9 +658,11 @@ extern "C" int b2s_aliked_extract_batch(b2s_aliked* h, const void* const* imgs_d
   for (int i = 0; i < B; ++i) {
     const int l = i % want;
     b2s_aliked* lane = l == 0 ? h : h->lanes[l - 1];
-    lane->desc_renorm_eps = h->desc_renorm_eps;
-    B2S_TRY(aliked_extract_graphed(lane, imgs_dev[i], fmt, H, W, row_stride, l == 0 ? st : h->lane_st[l - 1], kpts + i * nl * 2,
-                                   desc + i * nl * 128, scores ? scores + i * nl : nullptr, n_out + i));
+    lane->desc_renorm_eps = h->batch_renorm_eps;
+    const int rc = aliked_extract_graphed(lane, imgs_dev[i], fmt, H, W, row_stride, l == 0 ? st : h->lane_st[l - 1], kpts + i * nl * 2,
+                                          desc + i * nl * 128, scores ? scores + i * nl : nullptr, n_out + i);
+    lane->desc_renorm_eps = 0.f;
+    B2S_TRY(rc);
   }
   for (int l = 1; l < want; ++l) {
     B2S_CUDA(cudaEventRecord(h->lane_ev[l - 1], h->lane_st[l - 1]));
@@ -670,6 +673,14 @@ extern "C" int b2s_aliked_extract_batch(b2s_aliked* h, const void* const* imgs_d
 
 extern "C" int b2s_aliked_extract_host_ex(b2s_aliked* h, const void* img, int fmt, int H, int W, int row_stride,
                                           float* kpts, float* desc, float* scores, int32_t* n_out, float desc_renorm_eps);
+
+// eps > 0: b2s_aliked_extract_batch also applies the reference caller's `des /= (||des||_2 + eps)` (features_utils.py:100,
+// eps = 1e-8) in its last kernel, like b2s_aliked_extract_host_ex does for single frames; 0 (default) switches it off
+extern "C" int b2s_aliked_set_batch_renorm(b2s_aliked* h, float eps) {
+  if (!h || !(eps >= 0.f)) { set_error("b2s_aliked_set_batch_renorm: bad argument"); return B2S_EINVAL; }
+  h->batch_renorm_eps = eps;
+  return 0;
+}
 
 static int aliked_host_staging(b2s_aliked* h, size_t bytes) {
   if (bytes > h->himg_bytes || !h->hkp) {

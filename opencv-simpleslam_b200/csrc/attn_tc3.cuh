@@ -15,7 +15,8 @@
 //  * the score MMAs are issued for PAIRS of key tiles (N = 128: tile 2i for group 0 and 2i+1 for group 1 land
 //    in adjacent TMEM columns), which halves the re-reads of Q from shared memory; K therefore arrives as
 //    128-key tiles (2-slot ring, 3 planes x 16 KB), V as 64-key tiles (3-slot ring, 3 planes x 8 KB).
-// TMEM (512 columns allocated): S[g] 64 | O[g] 64 | P[g] 3 x 32, g = 0, 1.   grid = (ceil(max nq/128), heads, nprob).
+// TMEM (512 columns allocated): S[buffer][g] 64 | O[g] 64 | P[g] NP x 32, g = 0, 1 (one score buffer with NP = 3, two with
+// NP = 2, see A3Cfg).   grid = (ceil(max nq/128), heads, nprob).
 #pragma once
 #include "attn_tc.cuh"
 
@@ -34,10 +35,16 @@ struct A3Cfg {
   static constexpr int KSLOT = NP * A3_QPL;
   static constexpr int SMEM = NP * A3_QPL + KSLOTS * KSLOT + A3_SLOTS * SLOT + 1024 + 256;
   static constexpr int PCOLS = NP * 32;                // tensor-memory columns of one group's P planes
+  // score buffers in tensor memory: S[buffer][group] 64 columns each.  NP = 2 leaves room for TWO buffers (2 x 128 S + 128 O
+  // + 128 P = 512 columns): the score pair of key tiles (2i + 2, 2i + 3) is issued while the softmax groups still work on
+  // pair i, so no group ever waits for its scores (NP = 3: 128 S + 128 O + 192 P, one buffer)
+  // (measured with NP = 2, 2048 x 2048: two buffers + staggered groups 29.4 us per launch vs 29.8 with one - the softmax
+  //  groups, not the score MMAs, set the period - so one buffer is used)
+  static constexpr int SBUF = 1;
   static_assert(2 * 66 * 128 * 4 <= KSLOTS * KSLOT, "the final merge buffers alias the K ring");
   static_assert(8 * 2048 <= A3_SLOTS * SLOT, "the output staging tiles alias the V ring");
 };
-constexpr float A3_P_PRESCALE = 128.f;               // NP = 2: P is stored as 2^7 P
+constexpr float A3_P_PRESCALE = 128.f, A3_P_PRESCALE_LOG2 = 7.f;   // NP = 2: P is stored as 2^7 P (the exponent gets + 7: no multiply)
 
 struct Attn3Params {
   AttnTcProb prob[2]; int cap;     // problems: see AttnTcParams
@@ -51,7 +58,7 @@ struct Attn3Params {
   int trace_cta;                   // CTA to trace: x | y << 8 | z << 16
   long long* trace;                // nullable profiling hook (b2s_trace_attn_tc3): clock64 stamps of CTA (0,0,0), [role][tile][event]
   int* range_flag;                 // NP == 2, nullable: set to 1 when an output value leaves the fp16 range
-  float out_scale;                 // NP == 2: 1 / (q-k-v prescale * P prescale) applied to the normalised output (0 means 1)
+  float out_scale;                 // NP == 2: 1 / (v prescale) applied to the normalised output (0 means 1); P and l carry the same 2^7
 };
 
 // P chunk c (32 keys) of one row -> three bf16 planes in REGISTERS (16 packed words each); returns the partial row sum.
@@ -70,7 +77,7 @@ __device__ __forceinline__ float a3_make_p_chunk(const uint32_t (&v)[32], int c,
     }
     sum0 += p0; sum1 += p1;
     uint32_t w[NP];
-    if (NP == 2) tc::pack_h2_attn(p0, p1, A3_P_PRESCALE, w[0], w[NP - 1]);
+    if (NP == 2) tc::pack_h2_raw(p0, p1, w[0], w[NP - 1]);     // the caller folded the 2^7 prescale into m_used
     else tc::pack_planes2<NP>(p0, p1, w);
 #pragma unroll
     for (int pl = 0; pl < NP; ++pl) pk[pl][t >> 1] = w[pl];
@@ -97,8 +104,8 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;                 uint64_t* k_empty = k_full + A3_SLOTS;
   uint64_t* v_full = k_empty + A3_SLOTS;       uint64_t* v_empty = v_full + A3_SLOTS;
-  uint64_t* s_full = v_empty + A3_SLOTS;       uint64_t* s_free = s_full + 2;
-  uint64_t* p_full = s_free + 2;               uint64_t* o_full = p_full + 2;
+  uint64_t* s_full = v_empty + A3_SLOTS;       uint64_t* s_free = s_full + 4;      // [buffer][group]
+  uint64_t* p_full = s_free + 4;               uint64_t* o_full = p_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const long long t_entry = clock64();
@@ -115,10 +122,8 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
       tc::mbar_init(&k_full[b], 1); tc::mbar_init(&k_empty[b], 1);
       tc::mbar_init(&v_full[b], 1); tc::mbar_init(&v_empty[b], 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      tc::mbar_init(&s_full[b], 1); tc::mbar_init(&s_free[b], 128);
-      tc::mbar_init(&p_full[b], 128); tc::mbar_init(&o_full[b], 1);
-    }
+    for (int b = 0; b < 4; ++b) { tc::mbar_init(&s_full[b], 1); tc::mbar_init(&s_free[b], 128); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&p_full[b], 128); tc::mbar_init(&o_full[b], 1); }
     tc::fence_barrier_init();
   }
   if (warp == 10) tc::tmem_alloc(tmem_slot, 512);
@@ -140,7 +145,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
   const int nt = live ? (pr.nk + A3_BK - 1) / A3_BK : 0;
   if (p.stats && live && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
     atomicAdd(&p.stats[p.cross ? 1 : 0], (unsigned long long)pr.nq * (unsigned long long)pr.nk);
-  const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 256;
+  const uint32_t tS = tmem_base, tO = tmem_base + Cfg::SBUF * 128, tP = tO + 128;
   const bool tr = p.trace && (int)(blockIdx.x | (blockIdx.y << 8) | (blockIdx.z << 16)) == p.trace_cta;
   auto stamp = [&](int role, int tile, int ev) { if (tr) p.trace[(role * 64 + tile) * 8 + ev] = clock64(); };
   if (tr && threadIdx.x == 0) p.trace[(0 * 64 + 63) * 8 + 0] = t_entry;   // kernel entry
@@ -170,9 +175,10 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
           tc::tma_load_2d(sK + kb * A3_KSLOT + pl * A3_QPL, &mapQ, &k_full[kb], p.kcol + h * 64, pl * p.plane_rows + pr.k_row + jp * 2 * A3_BK);
       };
       const int npairs = (nt + 1) >> 1;
-      if (npairs > 0) load_k(0);
+      constexpr int KAHEAD = Cfg::SBUF;                    // pairs requested ahead of the V tiles (<= A3_KSLOTS - 1)
+      for (int jp = 0; jp < KAHEAD && jp < npairs; ++jp) load_k(jp);
       for (int j = 0; j < nt; ++j) {
-        if ((j & 1) == 0 && (j >> 1) + 1 < npairs) load_k((j >> 1) + 1);
+        if ((j & 1) == 0 && (j >> 1) + KAHEAD < npairs) load_k((j >> 1) + KAHEAD);
         const int b = j % A3_SLOTS, ph = (j / A3_SLOTS) & 1;
         tc::mbar_wait(&v_empty[b], ph ^ 1);
         tc::mbar_expect_tx(&v_full[b], A3_SLOT);
@@ -189,8 +195,8 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
       // (the barrier that completes LAST is waited on last: a wait on an already-complete mbarrier still costs ~100
       //  cycles, which must not sit between the late event and the first MMA)
       auto wait_k = [&](int jp) { tc::mbar_wait(&k_full[jp % A3_KSLOTS], (jp / A3_KSLOTS) & 1); };
-      auto issue_s_pair = [&](int jp) {                              // tiles 2jp (-> S[0]) and 2jp + 1 (-> S[1]); K pair jp has landed
-        const int b = jp % A3_KSLOTS;
+      auto issue_s_pair = [&](int jp) {                              // tiles 2jp (-> S[.][0]) and 2jp + 1 (-> S[.][1]); K pair jp has landed
+        const int b = jp % A3_KSLOTS, sb = jp % Cfg::SBUF;
         tc::tc_fence_after();
         stamp(0, jp, 0);                                   // K pair landed, S pair issue starts
         const uint32_t k_addr = tc::smem_u32(sK + b * A3_KSLOT);
@@ -200,24 +206,24 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
           for (int k = 0; k < A3_D / 16; ++k) {
             const uint64_t ad = tc::smem_desc_sw128(q_addr + Terms::a(t) * A3_QPL + k * 32, 16, 1024);
             const uint64_t bd = tc::smem_desc_sw128(k_addr + Terms::b(t) * A3_QPL + k * 32, 16, 1024);
-            tc::umma_bf16(tS, ad, bd, idesc_s, (t | k) ? 1u : 0u);
+            tc::umma_bf16(tS + sb * 128, ad, bd, idesc_s, (t | k) ? 1u : 0u);
           }
-        tc::umma_commit(&s_full[0]);
-        tc::umma_commit(&s_full[1]);
+        tc::umma_commit(&s_full[2 * sb]);
+        tc::umma_commit(&s_full[2 * sb + 1]);
         tc::umma_commit(&k_empty[b]);
         stamp(0, jp, 1);                                   // S pair issued
       };
       tc::mbar_wait(q_full, 0);
-      wait_k(0);
-      issue_s_pair(0);
       const int npairs = (nt + 1) >> 1;
-      for (int jp = 0; jp + 1 < npairs; ++jp) {
-        const int ph = jp & 1;                // both groups have their score tiles in registers: next pair can start
-        wait_k(jp + 1);                       // landed long ago (requested one pair ahead)
-        tc::mbar_wait(&s_free[0], ph);
-        tc::mbar_wait(&s_free[1], ph);
-        stamp(0, jp, 6);
-        issue_s_pair(jp + 1);
+      for (int jp = 0; jp < npairs; ++jp) {
+        wait_k(jp);                           // landed long ago (requested ahead)
+        if (jp >= Cfg::SBUF) {                // both groups have the previous tiles of this score buffer in registers
+          const int sb = jp % Cfg::SBUF, ph = (jp / Cfg::SBUF - 1) & 1;
+          tc::mbar_wait(&s_free[2 * sb], ph);
+          tc::mbar_wait(&s_free[2 * sb + 1], ph);
+          stamp(0, jp - 1, 6);
+        }
+        issue_s_pair(jp);
       }
     }
   } else if (warp == 10 || (warp == 11 && p.pv_issuers == 2)) {
@@ -264,7 +270,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
     float o[A3_D];                                        // running output (fp32 registers)
 #pragma unroll
     for (int d = 0; d < A3_D; ++d) o[d] = 0.f;
-    const uint32_t s_addr = tS + g * 64 + lane_addr, o_addr = tO + g * 64 + lane_addr, p_addr = tP + g * Cfg::PCOLS + lane_addr;
+    const uint32_t s_base = tS + g * 64 + lane_addr, o_addr = tO + g * 64 + lane_addr, p_addr = tP + g * Cfg::PCOLS + lane_addr;
     // o += the P V result of one tile sitting in TMEM (exact fp32 adds)
     auto add_pv = [&]() {
 #pragma unroll
@@ -278,14 +284,16 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
     };
     int t = 0;                                            // index among this group's tiles
     for (int j = g; j < nt; j += 2, ++t) {
-      tc::mbar_wait(&s_full[g], t & 1);
+      const int sb = t % Cfg::SBUF;                        // score buffer of pair t
+      tc::mbar_wait(&s_full[2 * sb + g], (t / Cfg::SBUF) & 1);
       tc::tc_fence_after();
       if (quad == 0 && lane == 0) stamp(1 + g, t, 0);       // S tile complete (seen by the group)
       uint32_t s[2][32];
+      const uint32_t s_addr = s_base + sb * 128;
       tc::tmem_ld32(s_addr, s[0]); tc::tmem_ld32(s_addr + 32, s[1]);
       tc::tmem_ld_wait();
       tc::tc_fence_before();
-      tc::mbar_arrive(&s_free[g]);                        // S[g] is in registers: next QK^T of this group may overwrite it
+      tc::mbar_arrive(&s_free[2 * sb + g]);               // S[sb][g] is in registers: a later QK^T of this group may overwrite it
       const int limit = pr.nk - j * A3_BK;
       const bool full = limit >= A3_BK;
       float mx;
@@ -305,8 +313,10 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
       }
       uint32_t pk0[A3_NP][16], pk1[A3_NP][16];
       float sum;
-      if (full) sum = a3_make_p_chunk<false, NP>(s[0], 0, limit, p.scale_log2e, m_used, pk0) + a3_make_p_chunk<false, NP>(s[1], 1, limit, p.scale_log2e, m_used, pk1);
-      else sum = a3_make_p_chunk<true, NP>(s[0], 0, limit, p.scale_log2e, m_used, pk0) + a3_make_p_chunk<true, NP>(s[1], 1, limit, p.scale_log2e, m_used, pk1);
+      // NP == 2: P and its row sum are 2^7 too large (exponent offset); the final normalisation O / l cancels it
+      const float m_eff = NP == 2 ? m_used - A3_P_PRESCALE_LOG2 : m_used;
+      if (full) sum = a3_make_p_chunk<false, NP>(s[0], 0, limit, p.scale_log2e, m_eff, pk0) + a3_make_p_chunk<false, NP>(s[1], 1, limit, p.scale_log2e, m_eff, pk1);
+      else sum = a3_make_p_chunk<true, NP>(s[0], 0, limit, p.scale_log2e, m_eff, pk0) + a3_make_p_chunk<true, NP>(s[1], 1, limit, p.scale_log2e, m_eff, pk1);
       if (t > 0) {
         // PV of the group's previous tile must have retired before P[g] is rewritten; collect its result (it was
         // computed against the previous reference maximum: add first, rescale afterwards)

@@ -20,7 +20,10 @@ struct TcpGemmCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;       // one plane
   static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
-  static constexpr int EPI_WARPS = 8;
+#ifndef B2S_TCP_EPI_WARPS_WIDE
+#define B2S_TCP_EPI_WARPS_WIDE 8
+#endif
+  static constexpr int EPI_WARPS = (BN == 64 || NP == 3) ? 8 : B2S_TCP_EPI_WARPS_WIDE;    // <= 4 * BN / 32: every epilogue warp must own a chunk
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int STG_BYTES = EPI_WARPS * 4096;                       // per-warp output staging tiles
   static constexpr int BUDGET = 227 * 1024 - STG_BYTES - 1024 /*align*/ - 256 /*barriers*/;
@@ -85,6 +88,10 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // profiling hook (b2s_bench_gemm_*, ts != nullptr): SM-clock stamps of CTA 0, [role][local tile < 16][event < 4];
+  // role 0 producer, 1 MMA issuer, 2 / 3 epilogue warps 2 / 6
+  const bool tr = p.ts && blockIdx.x == 0;
+  auto stamp = [&](int role, int lt, int ev) { if (tr && lt < 16) p.ts[(role * 16 + lt) * 4 + ev] = (unsigned long long)clock64(); };
   const int n_tiles = (p.N + BN - 1) / BN;
   const int total = m_tiles * n_tiles;
   const int nkb = p.K / Cfg::BK;
@@ -108,13 +115,15 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
   if (warp == 0) {
     // ===== TMA producer: the operand ring runs across tiles =====
     if (tc::elect_one()) {
-      int it = 0;
+      int it = 0, ltp = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         const TcpTile ti = tcp_tile(p, t, n_tiles, BN);
         if (ti.rows_live <= 0) continue;
+        stamp(0, ltp, 0);                                    // producer: first request of the tile ...
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
           tc::mbar_wait(&empty[s], ph ^ 1);
+          if (kb == nkb - 1) stamp(0, ltp++, 1);             // ... its last stage slot became free
           tc::mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
           uint8_t* st = smem + s * Cfg::STAGE_BYTES;
           const int k0 = kb * Cfg::BK;
@@ -137,14 +146,17 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
         const TcpTile ti = tcp_tile(p, t, n_tiles, BN);
         if (ti.rows_live <= 0) continue;
         const int ab = lt & 1, aph = (lt >> 1) & 1;
+        stamp(1, lt, 0);                                    // MMA: tile start
         tc::mbar_wait(&tmem_empty[ab], aph ^ 1);            // the epilogue has drained this buffer (two tiles ago)
         tc::tc_fence_after();
+        stamp(1, lt, 1);                                    // accumulator buffer free
         const uint32_t acc_base = tmem_base + ab * Cfg::ACC_COLS;
         uint32_t used = 0;                                  // accumulators already written (first MMA overwrites)
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % Cfg::STAGES, ph = (it / Cfg::STAGES) & 1;
           tc::mbar_wait(&full[s], ph);
           tc::tc_fence_after();
+          if (kb == 0) stamp(1, lt, 2);                     // first operand stage of the tile landed
           const uint32_t a0 = tc::smem_u32(smem + s * Cfg::STAGE_BYTES), b0 = a0 + NP * Cfg::A_BYTES;
 #pragma unroll
           for (int tm = 0; tm < Terms::N; ++tm) {
@@ -160,6 +172,7 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
           tc::umma_commit(&empty[s]);                       // frees the stage when these MMAs retire
         }
         tc::umma_commit(&tmem_full[ab]);                    // accumulators of this tile complete
+        stamp(1, lt, 3);                                    // all MMAs of the tile issued
         ++lt;
       }
     }
@@ -196,8 +209,10 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
           if (R < rows_q) *reinterpret_cast<uint4*>(out_f32 + (qrow0 + R) * p.ld_f32 + gc + sl * 4) = v;
         }
       };
+      if (lane == 0 && (warp == 2 || warp == 6)) stamp(warp == 2 ? 2 : 3, lt, 0);   // epilogue: waiting for the accumulators
       tc::mbar_wait(&tmem_full[ab], aph);
       tc::tc_fence_after();
+      if (lane == 0 && (warp == 2 || warp == 6)) stamp(warp == 2 ? 2 : 3, lt, 1);   // accumulators complete
       const uint32_t acc_base = tmem_base + ab * Cfg::ACC_COLS;
 #pragma unroll 1
       for (int c0 = cgrp * 32; c0 < BN; c0 += 8 * Cfg::EPI_WARPS) {
@@ -233,6 +248,7 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
           tc::tc_fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&tmem_empty[ab]);
+          if (lane == 0 && (warp == 2 || warp == 6)) stamp(warp == 2 ? 2 : 3, lt, 2);   // buffer handed back
         }
         const int gc = ti.n0 + c0;
         if (gc >= p.N) continue;                       // uniform per warp
@@ -358,6 +374,7 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
           __syncwarp();
         }
       }
+      if (lane == 0 && (warp == 2 || warp == 6)) stamp(warp == 2 ? 2 : 3, lt, 3);     // stores of the tile issued
       ++lt;
     }
   }

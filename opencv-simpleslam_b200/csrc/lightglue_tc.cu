@@ -360,9 +360,9 @@ static int tc_attention(LgTensorCore* tc, cudaStream_t st, int ld, int nseg, int
     ap.scale_log2e = scale_log2e; ap.out = tc->ctxb; ap.ldo = 256; ap.out_plane = (size_t)ap.plane_rows * 256; ap.ctrl = tc->ctrl;
     ap.stats = (tc->prof && tc->prof->on) ? tc->stats : nullptr;
     if (tc->np == 2) {
-      // q, k, v arrive prescaled by 16 (S is 256 x too large), P is stored as 2^7 P: O = 2^11 x the true numerator
+      // q, k, v arrive prescaled by 16 (S is 256 x too large); P and the row sums are 2^7 x too large alike: O / l = 16 x the result
       ap.scale_log2e = scale_log2e / (tc::H2_ATTN_PRESCALE * tc::H2_ATTN_PRESCALE);
-      ap.out_scale = 1.f / (tc::H2_ATTN_PRESCALE * A3_P_PRESCALE);
+      ap.out_scale = 1.f / tc::H2_ATTN_PRESCALE;
       ap.range_flag = tc->range_flag;
       launch_k(k_attn_tc3<2>, grid, A3_THREADS, A3Cfg<2>::SMEM, st, ld == 768 ? tc->m_qkv768 : tc->m_qkv512,
                ld == 768 ? tc->m_kv768 : tc->m_kv512, ap);
@@ -618,7 +618,13 @@ static int bench_gemm(int np, int M, int N, int K, int cl, int iters, float* ms_
   float ms = 0.f;
   B2S_CUDA(cudaEventElapsedTime(&ms, e0, e1));
   *ms_out = ms / iters;
-  if (ts_out) {
+  if (ts_out && cl == 0) {      // persistent kernel: raw SM-clock stamps of CTA 0, [4 roles][16 tiles][4 events] (gemm_tcp.cuh)
+    B2S_CUDA(cudaMemsetAsync(dts, 0, ncta * 6 * sizeof(unsigned long long), st));
+    launch(dts);
+    B2S_LAUNCH_CHECK();
+    B2S_CUDA(cudaStreamSynchronize(st));
+    B2S_CUDA(cudaMemcpy(ts_out, dts, std::min<size_t>(ncta * 6, 256) * 8, cudaMemcpyDeviceToHost));
+  } else if (ts_out) {
     for (int i = 0; i < 4; ++i) launch(i == 3 ? dts : nullptr);
     B2S_LAUNCH_CHECK();
     B2S_CUDA(cudaStreamSynchronize(st));
@@ -658,7 +664,7 @@ static int run_attn(int np, const std::vector<__nv_bfloat16>& buf, int R, const 
   Attn3Params a3 = {};
   a3.qcol = 0; a3.kcol = 256; a3.vcol = 512; a3.prob[0] = prob[0]; a3.prob[1] = prob[1]; a3.scale_log2e = sc; a3.out = dctx; a3.ldo = 256;
   a3.plane_rows = R; a3.out_plane = (size_t)R * 256; a3.pv_issuers = attn_pv_issuers();
-  if (np == 2) { a3.scale_log2e = sc / (tc::H2_ATTN_PRESCALE * tc::H2_ATTN_PRESCALE); a3.out_scale = 1.f / (tc::H2_ATTN_PRESCALE * A3_P_PRESCALE); }
+  if (np == 2) { a3.scale_log2e = sc / (tc::H2_ATTN_PRESCALE * tc::H2_ATTN_PRESCALE); a3.out_scale = 1.f / tc::H2_ATTN_PRESCALE; }
   long long* dtrace = nullptr;
   if (trace_out) { B2S_TRY(ar.alloc(&dtrace, (size_t)3 * 64 * 8)); B2S_CUDA(cudaMemset(dtrace, 0, 3 * 64 * 8 * sizeof(long long))); }
   const dim3 grid(cdiv(maxq, 128), 4, nz);

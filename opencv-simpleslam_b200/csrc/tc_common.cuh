@@ -221,19 +221,28 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
 __device__ __forceinline__ float2 unpack_f16x2(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
 // nonzero iff one of the two fp16 halves of w is +-inf or nan
 __device__ __forceinline__ uint32_t h2_ovf(uint32_t w) { return ((w & 0x7FFF7FFFu) + 0x04000400u) & 0x80008000u; }
+// (a - lo(w), b - hi(w)) for a packed fp16 pair w: two mixed-precision adds (FHADD with a negated .H0 / .H1 operand) - no
+// unpacking; exact when w = fp16x2(a, b)
+__device__ __forceinline__ void sub_f16x2(float a, float b, uint32_t w, float& ra, float& rb) {
+  asm("{\n\t.reg .b16 lo, hi;\n\t.reg .b32 nw;\n\tneg.f16x2 nw, %2;\n\tmov.b32 {lo, hi}, nw;\n\t"
+      "add.rn.f32.f16 %0, lo, %3;\n\tadd.rn.f32.f16 %1, hi, %4;\n\t}" : "=f"(ra), "=f"(rb) : "r"(w), "f"(a), "f"(b));
+}
 // GEMM operand format (scaled residual)
 __device__ __forceinline__ void pack_h2(float a, float b, uint32_t& w0, uint32_t& w1) {
   w0 = pack_f16x2(a, b);
-  const float2 f = unpack_f16x2(w0);
-  w1 = pack_f16x2((a - f.x) * H2_RS, (b - f.y) * H2_RS);
+  float ra, rb;
+  sub_f16x2(a, b, w0, ra, rb);
+  w1 = pack_f16x2(ra * H2_RS, rb * H2_RS);
+}
+// attention operand format (unscaled residual) of values that already carry their prescale
+__device__ __forceinline__ void pack_h2_raw(float a, float b, uint32_t& w0, uint32_t& w1) {
+  w0 = pack_f16x2(a, b);
+  float ra, rb;
+  sub_f16x2(a, b, w0, ra, rb);
+  w1 = pack_f16x2(ra, rb);
 }
 // attention operand format (prescaled by s, unscaled residual)
-__device__ __forceinline__ void pack_h2_attn(float a, float b, float s, uint32_t& w0, uint32_t& w1) {
-  a *= s; b *= s;
-  w0 = pack_f16x2(a, b);
-  const float2 f = unpack_f16x2(w0);
-  w1 = pack_f16x2(a - f.x, b - f.y);
-}
+__device__ __forceinline__ void pack_h2_attn(float a, float b, float s, uint32_t& w0, uint32_t& w1) { pack_h2_raw(a * s, b * s, w0, w1); }
 template <int NP>
 __device__ __forceinline__ void pack_planes2(float a, float b, uint32_t (&w)[NP]) {
   if (NP == 2) { pack_h2(a, b, w[0], w[NP - 1]); return; }

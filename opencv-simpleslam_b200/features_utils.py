@@ -100,6 +100,9 @@ def __getattr__(name):
     if name in ("ALIKED", "LightGlue", "rbd"):
         from . import frontend
         return getattr(frontend, name)
+    if name in ("FramePairStream", "match_sequence"):      # sequence form of feature_extractor + feature_matcher (stream.py)
+        from . import stream
+        return getattr(stream, name)
     raise AttributeError(name)
 
 

@@ -206,3 +206,36 @@ def test_array_native_path_equals_list_path(pipelines):
     assert [(m.queryIdx, m.trainIdx) for m in ml] == [(m.queryIdx, m.trainIdx) for m in mn]
     il, inn = fu.filter_matches_ransac(l0[0], l1[0], ml, 2.5), fu.filter_matches_ransac(n0[0], n1[0], mn, 2.5)
     assert [m.queryIdx for m in il] == inn.queryIdx.tolist()      # cv2 RANSAC on the same points: same survivors
+
+
+@pytest.mark.parametrize("batch,n_frames", [(4, 11), (8, 8), (3, 1)])
+def test_frame_pair_stream_equals_per_call_api(pipelines, batch, n_frames):
+    """features_utils.FramePairStream (pinned staging, batched extraction + batched matching, copies on a second stream,
+    host conversion overlapped with the next chunk) yields exactly what feature_extractor + feature_matcher return
+    frame by frame: same keypoints, bit-identical descriptors, same DMatch lists - across chunk boundaries, with a
+    ragged last chunk and with a single frame."""
+    args, fu, ofu, det, mat = pipelines[:5]
+    frames = [synth.frame(40 + t, 376, 1241) for t in range(n_frames)]
+    ref = []
+    prev = None
+    for f in frames:
+        cur = fu.feature_extractor(args, f, det)
+        m = None if prev is None else fu.feature_matcher(args, prev[0], cur[0], prev[1], cur[1], mat)
+        ref.append((cur[0], cur[1], m))
+        prev = cur
+    stream = fu.FramePairStream(args, det, mat, batch=batch)
+    got = list(stream.run(iter(frames)))
+    assert len(got) == n_frames
+    for t, ((rk, rd, rm), (gk, gd, gm)) in enumerate(zip(ref, got)):
+        assert isinstance(gk, list) and (not gk or isinstance(gk[0], cv2.KeyPoint))
+        assert [k.pt for k in gk] == [k.pt for k in rk], f"keypoints of frame {t}"
+        assert gd.dtype == np.float32 and np.array_equal(gd, rd), f"descriptors of frame {t}"
+        if t == 0:
+            assert gm is None
+        else:
+            assert [(m.queryIdx, m.trainIdx, m.imgIdx, m.distance) for m in gm] == [(m.queryIdx, m.trainIdx, m.imgIdx, m.distance) for m in rm], f"matches of pair {t}"
+            assert len(gm) > 20
+    assert stream.h2d_bytes == n_frames * 376 * 1241 * 3 and stream.d2h_bytes > 0
+    # the per-call API still works afterwards (the batch re-normalisation switch is restored)
+    again = fu.feature_extractor(args, frames[0], det)
+    assert np.array_equal(again[1], ref[0][1])

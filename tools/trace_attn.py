@@ -1,4 +1,4 @@
-"""Timeline of one CTA of the fp32 (bf16x3) attention kernel from SM-clock stamps (b2s_trace_attn_tc3)."""
+"""Timeline of one CTA of the fp32 attention kernel from SM-clock stamps: python tools/trace_attn.py [h2|x3] (fp16x2 planes, default, or bf16x3)."""
 import ctypes as C
 import sys
 
@@ -7,15 +7,16 @@ import numpy as np
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from b200slam._lib import lib, check   # noqa: E402
 
+trace_fn = lib.b2s_trace_attn_tc3 if (len(sys.argv) > 1 and sys.argv[1] == "x3") else lib.b2s_trace_attn_h2
 ms = C.c_float(0)
 for cta in ((0, 0, 0), (15, 3, 1), (7, 2, 0)):       # whole-CTA phases of a few CTAs (tr[0,0,0] carries the CTA to trace)
     tr = np.zeros((3, 64, 8), np.int64)
     tr[0, 0, 0] = cta[0] | (cta[1] << 8) | (cta[2] << 16)
-    check(lib.b2s_trace_attn_tc3(2048, 2048, 20, C.addressof(ms), tr.ctypes.data), "trace_attn")
+    check(trace_fn(2048, 2048, 20, C.addressof(ms), tr.ctypes.data), "trace_attn")
     e = tr[0, 63]
     print(f"CTA {cta}: launch {ms.value * 1e3:.1f} us | entry -> deps {e[1] - e[0]} clk | deps -> key loop done {tr[1, 63, 0] - e[1]} | loop done -> output written {e[2] - tr[1, 63, 0]} | total {e[3] - e[0]} clk")
 tr = np.zeros((3, 64, 8), np.int64)
-check(lib.b2s_trace_attn_tc3(2048, 2048, 50, C.addressof(ms), tr.ctypes.data), "trace_attn")
+check(trace_fn(2048, 2048, 50, C.addressof(ms), tr.ctypes.data), "trace_attn")
 tr[0, 63] = 0; tr[1, 63] = 0; tr[2, 63] = 0
 t0 = tr[tr > 0].min()
 rel = np.where(tr > 0, tr - t0, -1)
