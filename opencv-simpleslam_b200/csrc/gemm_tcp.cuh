@@ -26,9 +26,10 @@ struct TcpGemmCfg {
   static constexpr int EPI_WARPS = (BN == 64 || NP == 3) ? 8 : B2S_TCP_EPI_WARPS_WIDE;    // <= 4 * BN / 32: every epilogue warp must own a chunk
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int STG_BYTES = EPI_WARPS * 4096;                       // per-warp output staging tiles
-  static constexpr int BUDGET = 227 * 1024 - STG_BYTES - 1024 /*align*/ - 256 /*barriers*/;
+  static constexpr int BIAS_FLOATS = 32 * EPI_WARPS;                       // one 32-float bias chunk per epilogue warp
+  static constexpr int BUDGET = 227 * 1024 - STG_BYTES - 1024 /*align*/ - 256 /*barriers*/ - BIAS_FLOATS * 4;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 4 ? 4 : BUDGET / STAGE_BYTES;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 1024 + 256;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 1024 + 256 + BIAS_FLOATS * 4;
   static constexpr int ACC_COLS = 256;                                     // columns of one accumulator buffer
   // fp32 path: TWO accumulators whatever the tile width - correction terms / main a0*w0 term.  An output element's
   // accumulation sequence (and therefore its bits) then does not depend on BN, and the epilogue drains 2 instead of
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
   uint64_t* tmem_full = bars + 2 * Cfg::STAGES;   // [2]       MMA -> epilogue
   uint64_t* tmem_empty = tmem_full + 2;           // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(stg_base + Cfg::STG_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // profiling hook (b2s_bench_gemm_*, ts != nullptr): SM-clock stamps of CTA 0, [role][local tile < 16][event < 4];
@@ -210,6 +212,17 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
         }
       };
       if (lane == 0 && (warp == 2 || warp == 6)) stamp(warp == 2 ? 2 : 3, lt, 0);   // epilogue: waiting for the accumulators
+      // the bias of this warp's chunks (lane = column) is requested before the wait for the accumulators: eight broadcast
+      // __ldg per chunk inside the thread == row epilogue were measured at 11 % of the K = 256 GEMMs
+      float breg[(BN + 8 * Cfg::EPI_WARPS - 1) / (8 * Cfg::EPI_WARPS)];
+      if (p.bias) {
+        const float* bsrc = p.bias + ti.w_row * (p.ctrl_mode == 2 ? 1 : 0) + ti.n0 + lane;
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(breg) / sizeof(float)); ++k) {
+          const int c0 = cgrp * 32 + k * 8 * Cfg::EPI_WARPS;
+          breg[k] = (c0 < BN && ti.n0 + c0 < p.N) ? __ldg(bsrc + c0) : 0.f;
+        }
+      }
       tc::mbar_wait(&tmem_full[ab], aph);
       tc::tc_fence_after();
       if (lane == 0 && (warp == 2 || warp == 6)) stamp(warp == 2 ? 2 : 3, lt, 1);   // accumulators complete
@@ -253,12 +266,18 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
         const int gc = ti.n0 + c0;
         if (gc >= p.N) continue;                       // uniform per warp
         if (p.bias) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + ti.w_row * (p.ctrl_mode == 2 ? 1 : 0) + gc);
+          float* sb = s_bias + (warp - 2) * 32;
+          constexpr int NB = (int)(sizeof(breg) / sizeof(float));
+          static_assert(NB <= 2, "an epilogue warp owns at most two chunks");
+          sb[lane] = (NB > 1 && c0 >= 8 * Cfg::EPI_WARPS) ? breg[NB - 1] : breg[0];
+          __syncwarp();
+          const float4* b4 = reinterpret_cast<const float4*>(sb);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 bv = __ldg(b4 + q);
+            const float4 bv = b4[q];
             f[4 * q] += bv.x; f[4 * q + 1] += bv.y; f[4 * q + 2] += bv.z; f[4 * q + 3] += bv.w;
           }
+          __syncwarp();
         }
         if (p.alpha != 0.f) {
 #pragma unroll

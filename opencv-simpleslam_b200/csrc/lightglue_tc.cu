@@ -153,9 +153,9 @@ struct LgTensorCore {
   unsigned long long* stats = nullptr;   // executed attention work counters (owned by the matcher handle)
 };
 
-static int make_linear(LgTensorCore* tc, const float* w_dev, const float* bias, int N, int K, TcLinear* out, int np = 0) {
+static int make_linear(LgTensorCore* tc, const float* w_dev, const float* bias, int N, int K, TcLinear* out, int np = 0, int bn = 0) {
   if (np == 0) np = tc->np;
-  out->N = N; out->K = K; out->bias = bias; out->BN = N <= 256 ? 64 : (N % 128 == 0 && N != 768 ? 128 : 96);   // N = 768 (QKV): 8 x 32 tiles of 128 x 96 waste less of the second wave than 6 x 32 of 128 x 128
+  out->N = N; out->K = K; out->bias = bias; out->BN = bn ? bn : N <= 256 ? 64 : (N % 128 == 0 && N != 768 ? 128 : 96);   // N = 768 (QKV): 8 x 32 tiles of 128 x 96 waste less of the second wave than 6 x 32 of 128 x 128
   const size_t n = (size_t)N * K;
   B2S_TRY(tc->warena.alloc(&out->w, n * np));
   k_weight_planes<<<(unsigned)((n + 255) / 256), 256>>>(w_dev, out->w, N, K, np, tc->range_flag);
@@ -266,10 +266,14 @@ int lgtc_set_layer(LgTensorCore* tc, int li, const LgTcLayerSrc& s) {
   TcLayer& l = tc->L[li];
   B2S_TRY(make_linear(tc, s.wqkv, s.bqkv, 768, 256, &l.qkv));
   B2S_TRY(make_folded_ffn1(tc, s.w1, s.b1, s.wo, s.bo, &l.w1));
-  B2S_TRY(make_linear(tc, s.w2, s.b2, 256, 512, &l.w2));
+  // FFN second layer (N = 256, K = 512): 128-wide tiles on the fp16x2 path (an M128 x N64 MMA reads 192 B of operands per
+  // clock from shared memory, N128 128 B: measured 1.051 -> 1.037 ms per pair), 64-wide otherwise (B2S_FFN2_BN overrides)
+  static const int ffn2_env = [] { const char* e = std::getenv("B2S_FFN2_BN"); const int v = e ? std::atoi(e) : 0; return (v == 128 || v == 64) ? v : 0; }();
+  const int ffn2_bn = ffn2_env ? ffn2_env : (tc->np == 2 ? 128 : 64);
+  B2S_TRY(make_linear(tc, s.w2, s.b2, 256, 512, &l.w2, 0, ffn2_bn));
   B2S_TRY(make_linear(tc, s.cwqkv, s.cbqkv, 512, 256, &l.cqkv));
   B2S_TRY(make_folded_ffn1(tc, s.cw1, s.cb1, s.cwo, s.cbo, &l.cw1));
-  B2S_TRY(make_linear(tc, s.cw2, s.cb2, 256, 512, &l.cw2));
+  B2S_TRY(make_linear(tc, s.cw2, s.cb2, 256, 512, &l.cw2, 0, ffn2_bn));
   l.lng = s.lng; l.lnb = s.lnb; l.clng = s.clng; l.clnb = s.clnb;
   B2S_CUDA(cudaDeviceSynchronize());
   return 0;
