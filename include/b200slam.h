@@ -233,6 +233,20 @@ int b2s_fm_ransac(b2s_fm* h, const float* pts1_dev, const float* pts2_dev, const
 /* host buffers; copies in/out on the handle's own stream and synchronises */
 int b2s_fm_ransac_host(b2s_fm* h, const float* pts1, const float* pts2, int n, float thresh, int n_hyp,
                        uint64_t seed, uint8_t* mask, double* F, int32_t* n_inliers, int32_t* model_index);
+/* cv2-IDENTICAL form: the same mask and the same F (to rounding) as `cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC,
+ * thresh, confidence)` (features_utils.py:195-196) for n >= 15 - below that OpenCV silently runs LMedS, whose winner for
+ * n <= 13 is decided by the rounding noise of near-zero residuals and is left to cv2 itself by the Python drop-in.
+ * OpenCV's loop (calib3d ptsetreg.cpp RANSACPointSetRegistrator::run) is reproduced, not approximated: the host draws
+ * the subsets of all max_iters iterations from cv::RNG((uint64)-1) (getSubset + haveCollinearPoints - the stream does not
+ * depend on the models), the device solves every subset with fundam.cpp's run7Point (including the null-space basis
+ * OpenCV's SVD returns, which fixes the order of the up-to-three models) and counts inliers with computeError's float32
+ * errors, and the host replays the strictly-greater update and RANSACUpdateNumIters over the counts; a last kernel
+ * writes the winner's mask.  max_iters <= the handle's max_hypotheses (cv2's default is 1000).
+ *   mask [n] u8, F [9] f64 row-major (F[8] = 1), n_inliers; info4 = { winning iteration, model within it (-1: no
+ *   model - cv2 returns None), final iteration bound, subsets drawn }.  Restated in oracle/cv_ransac.py (pinned against
+ *   cv2), tests/test_gpu_geometry.py compares with cv2.findFundamentalMat directly. */
+int b2s_fm_cv_ransac_host(b2s_fm* h, const float* pts1, const float* pts2, int n, double thresh, double confidence,
+                          int max_iters, uint8_t* mask, double* F, int32_t* n_inliers, int32_t* info4);
 /* test hook: candidate models (pixel coordinates, [3][9]), their number and consensus counts of one sample */
 int b2s_fm_debug_models(b2s_fm* h, int hyp, double* models27, int32_t* n_models, int32_t* counts3);
 long long b2s_fm_launch_count(const b2s_fm* h);

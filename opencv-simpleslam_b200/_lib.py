@@ -92,6 +92,7 @@ SIGNATURES = {
     "b2s_fm_destroy": (None, [vp]),
     "b2s_fm_ransac": (C.c_int, [vp, f32p, f32p, i32p, C.c_int, C.c_float, C.c_int, C.c_uint64, vp, vp, vp, i32p]),
     "b2s_fm_ransac_host": (C.c_int, [vp, f32p, f32p, C.c_int, C.c_float, C.c_int, C.c_uint64, vp, vp, i32p, i32p]),
+    "b2s_fm_cv_ransac_host": (C.c_int, [vp, f32p, f32p, C.c_int, C.c_double, C.c_double, C.c_int, vp, vp, i32p, i32p]),
     "b2s_fm_debug_models": (C.c_int, [vp, C.c_int, vp, i32p, i32p]),
     "b2s_fm_launch_count": (C.c_longlong, [vp]),
     "b2s_remap_create": (C.c_int, [C.c_int, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),

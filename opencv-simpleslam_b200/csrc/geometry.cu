@@ -3,6 +3,8 @@
 // the undistortion maps, /root/reference/slam/monocular/main_revamped.py:313-324).
 #include "geometry_kernels.cuh"
 
+#include <algorithm>
+#include <cfloat>
 #include <cmath>
 
 using namespace b2s;
@@ -14,9 +16,84 @@ struct b2s_fm {
   // host API staging (device copies of the caller's host arrays + pinned result block)
   float *d_pts1 = nullptr, *d_pts2 = nullptr; uint8_t* d_mask = nullptr; double* d_F = nullptr; int32_t* d_res = nullptr;
   uint8_t* h_pin = nullptr;    // pinned: [max_pts] mask | 9 doubles | 2 int32
+  int32_t* d_subsets = nullptr;   // cv2-identical path: [max_hyp][7] sample indices
+  uint8_t* h_cv = nullptr;        // pinned: pts1 | pts2 ([max_pts][2] f32 each) | subsets [max_hyp][7] | counts [max_hyp][3] | nmodels [max_hyp]
+  unsigned sign1 = 0, sign2 = 0;  // completion vectors of OpenCV's SVD (see k_fmcv_models)
   cudaStream_t stream = nullptr;
   long long launches = 0;
 };
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// cv2-identical RANSAC, host part: OpenCV's sample stream and the sequential bookkeeping of its loop
+// (modules/calib3d/src/ptsetreg.cpp, fundam.cpp; restated in oracle/cv_ransac.py and pinned there against cv2 itself)
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct CvRng {   // cv::RNG: multiply-with-carry
+  uint64_t state;
+  explicit CvRng(uint64_t s) : state(s ? s : 0xffffffffull) {}
+  unsigned next() { state = (uint64_t)(unsigned)state * 4164903690u + (unsigned)(state >> 32); return (unsigned)state; }
+  int uniform(int a, int b) { return a == b ? a : (int)(next() % (unsigned)(b - a) + a); }
+};
+
+// JacobiSVDImpl_ completes Vt with vectors whose components are +-1/m, sign = (rng.next() & 256) of RNG(0x12345678)
+void fmcv_signs(unsigned* s1, unsigned* s2) {
+  CvRng rng(0x12345678ull);
+  unsigned a = 0, b = 0;
+  for (int k = 0; k < 9; ++k) a |= (rng.next() & 256u) ? 1u << k : 0u;
+  for (int k = 0; k < 9; ++k) b |= (rng.next() & 256u) ? 1u << k : 0u;
+  *s1 = a; *s2 = b;
+}
+
+// fundam.cpp haveCollinearPoints on the 7 sampled points (only the last one is tested; float32 differences)
+bool fmcv_collinear(const float* pts, const int* idx) {
+  const int i = 6;
+  const float xi = pts[2 * idx[i]], yi = pts[2 * idx[i] + 1];
+  for (int j = 0; j < i; ++j) {
+    const double dx1 = pts[2 * idx[j]] - xi, dy1 = pts[2 * idx[j] + 1] - yi;
+    for (int k = 0; k < j; ++k) {
+      const double dx2 = pts[2 * idx[k]] - xi, dy2 = pts[2 * idx[k] + 1] - yi;
+      if (std::fabs(dx2 * dy1 - dy2 * dx1) <= (double)FLT_EPSILON * (std::fabs(dx1) + std::fabs(dy1) + std::fabs(dx2) + std::fabs(dy2))) return true;
+    }
+  }
+  return false;
+}
+
+// every iteration's subset (getSubset with 10000 attempts); returns how many were drawn before getSubset failed
+int fmcv_subsets(const float* pts1, const float* pts2, int n, int max_iters, int32_t* out) {
+  CvRng rng((uint64_t)-1);
+  for (int it = 0; it < max_iters; ++it) {
+    int* idx = out + 7 * it;
+    bool found = false;
+    for (int attempt = 0; attempt < 10000 && !found; ++attempt) {
+      for (int i = 0; i < 7; ++i) {
+        int c;
+        for (;;) {
+          c = rng.uniform(0, n);
+          bool dup = false;
+          for (int j = 0; j < i; ++j) dup |= idx[j] == c;
+          if (!dup) break;
+        }
+        idx[i] = c;
+      }
+      found = !fmcv_collinear(pts1, idx) && !fmcv_collinear(pts2, idx);
+    }
+    if (!found) return it;
+  }
+  return max_iters;
+}
+
+int fmcv_update_num_iters(double p, double ep, int model_points, int max_iters) {
+  p = std::max(p, 0.); p = std::min(p, 1.);
+  ep = std::max(ep, 0.); ep = std::min(ep, 1.);
+  double num = std::max(1. - p, DBL_MIN);
+  double denom = 1. - std::pow(1. - ep, model_points);
+  if (denom < DBL_MIN) return 0;
+  num = std::log(num);
+  denom = std::log(denom);
+  return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : (int)std::lrint(num / denom);
+}
+}  // namespace
 
 extern "C" int b2s_fm_create(int device, int max_points, int max_hypotheses, b2s_fm** out) {
   if (!out || max_points < 8 || max_hypotheses < 1) { set_error("b2s_fm_create: bad arguments"); return B2S_EINVAL; }
@@ -41,9 +118,12 @@ extern "C" int b2s_fm_create(int device, int max_points, int max_hypotheses, b2s
   A(h->arena.alloc(&h->d_mask, (size_t)max_points));
   A(h->arena.alloc(&h->d_F, 9));
   A(h->arena.alloc(&h->d_res, 2));
+  A(h->arena.alloc(&h->d_subsets, (size_t)max_hypotheses * 7));
   if (rc == 0 && cudaMallocHost((void**)&h->h_pin, (size_t)max_points + 128) != cudaSuccess) { set_error("b2s_fm_create: pinned alloc failed"); rc = B2S_ENOMEM; }
+  if (rc == 0 && cudaMallocHost((void**)&h->h_cv, (size_t)max_points * 16 + (size_t)max_hypotheses * 11 * sizeof(int32_t)) != cudaSuccess) { set_error("b2s_fm_create: pinned alloc failed"); rc = B2S_ENOMEM; }
+  fmcv_signs(&h->sign1, &h->sign2);
   if (rc == 0 && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("b2s_fm_create: stream"); rc = B2S_ECUDA; }
-  if (rc != 0) { if (h->h_pin) cudaFreeHost(h->h_pin); delete h; return rc; }
+  if (rc != 0) { if (h->h_pin) cudaFreeHost(h->h_pin); if (h->h_cv) cudaFreeHost(h->h_cv); delete h; return rc; }
   *out = h;
   return 0;
 }
@@ -53,6 +133,7 @@ extern "C" void b2s_fm_destroy(b2s_fm* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->h_pin) cudaFreeHost(h->h_pin);
+  if (h->h_cv) cudaFreeHost(h->h_cv);
   delete h;
 }
 
@@ -100,6 +181,76 @@ extern "C" int b2s_fm_ransac_host(b2s_fm* h, const float* pts1, const float* pts
   if (F) std::memcpy(F, hF, 9 * sizeof(double));
   if (n_inliers) *n_inliers = hres[0];
   if (model_index) *model_index = hres[1];
+  return 0;
+}
+
+
+// cv2.findFundamentalMat(pts1, pts2, FM_RANSAC, thresh, confidence[, max_iters]) for n >= 15: same mask, same F
+extern "C" int b2s_fm_cv_ransac_host(b2s_fm* h, const float* pts1, const float* pts2, int n, double thresh, double confidence,
+                                     int max_iters, uint8_t* mask, double* F, int32_t* n_inliers, int32_t* info4) {
+  if (!h || !pts1 || !pts2 || !mask) { set_error("b2s_fm_cv_ransac_host: null argument"); return B2S_EINVAL; }
+  if (n < 15) { set_error("b2s_fm_cv_ransac_host: OpenCV runs RANSAC from 15 correspondences on (LMedS below), got %d", n); return B2S_EINVAL; }
+  if (max_iters < 1) max_iters = 1;
+  if (n > h->max_pts || max_iters > h->max_hyp) { set_error("b2s_fm_cv_ransac_host: n=%d / max_iters=%d exceed the handle (%d / %d)", n, max_iters, h->max_pts, h->max_hyp); return B2S_ESIZE; }
+  if (thresh <= 0) thresh = 3;
+  if (confidence < DBL_EPSILON || confidence > 1 - DBL_EPSILON) confidence = 0.99;
+  B2S_CUDA(cudaSetDevice(h->device));
+  float* hp1 = reinterpret_cast<float*>(h->h_cv);
+  float* hp2 = hp1 + (size_t)h->max_pts * 2;
+  int32_t* hsub = reinterpret_cast<int32_t*>(hp2 + (size_t)h->max_pts * 2);
+  int32_t* hcnt = hsub + (size_t)h->max_hyp * 7;
+  int32_t* hnm = hcnt + (size_t)h->max_hyp * 3;
+  std::memcpy(hp1, pts1, (size_t)n * 8);
+  std::memcpy(hp2, pts2, (size_t)n * 8);
+  B2S_CUDA(cudaMemcpyAsync(h->d_pts1, hp1, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  B2S_CUDA(cudaMemcpyAsync(h->d_pts2, hp2, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  const int n_sub = fmcv_subsets(pts1, pts2, n, max_iters, hsub);    // overlaps the point upload
+  if (n_inliers) *n_inliers = 0;
+  if (info4) { info4[0] = -1; info4[1] = -1; info4[2] = max_iters; info4[3] = n_sub; }
+  if (n_sub == 0) {            // getSubset failed in iteration 0: cv2 returns no model
+    B2S_CUDA(cudaStreamSynchronize(h->stream));
+    std::memset(mask, 0, (size_t)n);
+    return 0;
+  }
+  B2S_CUDA(cudaMemcpyAsync(h->d_subsets, hsub, (size_t)n_sub * 7 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  FmCvParams p = {};
+  p.m1 = h->d_pts1; p.m2 = h->d_pts2; p.n = n; p.n_sub = n_sub; p.subsets = h->d_subsets; p.sign1 = h->sign1; p.sign2 = h->sign2;
+  p.thresh2 = (float)(thresh * thresh);
+  p.models = h->models; p.nmodels = h->nmodels; p.counts = h->counts; p.mask = h->d_mask; p.F = h->d_F;
+  launch_k(k_fmcv_models, dim3(cdiv(n_sub, 32)), dim3(32), 0, h->stream, p);
+  launch_k(k_fmcv_count, dim3(n_sub), dim3(128), 0, h->stream, p);
+  h->launches += 2;
+  B2S_CUDA(cudaMemcpyAsync(hcnt, h->counts, (size_t)n_sub * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  B2S_CUDA(cudaStreamSynchronize(h->stream));
+  B2S_LAUNCH_CHECK();
+  (void)hnm;
+  // RANSACPointSetRegistrator::run, the sequential part
+  int niters = max_iters, max_good = 0, win_it = -1, win_k = -1;
+  for (int it = 0; it < niters && it < n_sub; ++it) {
+    for (int k = 0; k < 3; ++k) {
+      const int good = hcnt[3 * it + k];
+      if (good < 0) break;
+      if (good > std::max(max_good, 6)) {
+        max_good = good; win_it = it; win_k = k;
+        niters = fmcv_update_num_iters(confidence, (double)(n - good) / n, 7, niters);
+      }
+    }
+  }
+  if (info4) { info4[0] = win_it; info4[1] = win_k; info4[2] = niters; }
+  if (max_good <= 0) { std::memset(mask, 0, (size_t)n); return 0; }
+  p.winner = win_it * 3 + win_k;
+  launch_k(k_fmcv_mask, dim3(cdiv(n, 256)), dim3(256), 0, h->stream, p);
+  h->launches += 1;
+  uint8_t* pm = h->h_pin;
+  const size_t off = ((size_t)h->max_pts + 15) & ~(size_t)15;
+  double* hF = reinterpret_cast<double*>(pm + off);
+  B2S_CUDA(cudaMemcpyAsync(pm, h->d_mask, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  B2S_CUDA(cudaMemcpyAsync(hF, h->d_F, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  B2S_CUDA(cudaStreamSynchronize(h->stream));
+  B2S_LAUNCH_CHECK();
+  std::memcpy(mask, pm, (size_t)n);
+  if (F) std::memcpy(F, hF, 9 * sizeof(double));
+  if (n_inliers) *n_inliers = max_good;
   return 0;
 }
 

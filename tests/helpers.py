@@ -1,4 +1,6 @@
 """Shared test inputs (seeded, regenerated - never read from /root/reference)."""
+import os
+
 import numpy as np
 import torch
 
@@ -75,3 +77,16 @@ def aliked_decision_margins(score_gpu, score_ora, n_limit, thr=0.2):
     gap = float(srt[n_limit - 1] - srt[n_limit]) if (n_limit > 0 and len(srt) > n_limit) else None
     return {"n_diff": len(out), "max_margin": max([m for _, m in out], default=0.0), "margins": out,
             "min_thr_margin": float(np.abs(cand - thr).min()) if len(cand) else None, "kth_gap": gap}
+
+
+FM_CV_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fm_cv.npz")
+
+
+def fm_cv_golden_cases():
+    """(case, pts1, pts2, thresh, F, mask [n,1]) of the cv2-generated fixtures (tests/golden/make_golden_fm_cv.py)."""
+    z = np.load(FM_CV_GOLD)
+    c = 0
+    while f"c{c}_cfg" in z:
+        n = int(z[f"c{c}_cfg"][0])
+        yield c, z[f"c{c}_pts1"], z[f"c{c}_pts2"], float(z[f"c{c}_cfg"][4]), z[f"c{c}_F"], np.unpackbits(z[f"c{c}_mask"])[:n].reshape(-1, 1)
+        c += 1

@@ -326,3 +326,67 @@ def test_reproject_and_match_permutation_property():
     # every assignment honours the reference's gates: inside the window, within the descriptor threshold, keypoints used once
     uv, z = O.project_points(K, Tcw, a.pts3d.astype(np.float64))
     assert (np.linalg.norm(uv - a.pts2d, axis=1) <= 12.0 + 1e-3).all() and len(set(a.kp_indices)) == len(a.kp_indices)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# f1 / a11: OpenCV's RANSAC reproduced on the GPU (b2s_fm_cv_ransac_host) - identical to cv2, not statistically close
+# ---------------------------------------------------------------------------------------------------------------
+def _cv_scenes():
+    sizes = [20, 60, 150, 300, 700, 1300, 2048, 15, 33, 500, 4000, 97]
+    for seed in range(36):
+        n = sizes[seed % len(sizes)]
+        yield seed, n, [0.1, 0.3, 0.5, 0.2, 0.6, 0.8][seed % 6], [0.2, 0.5, 1.0][seed % 3], [1.0, 1.0, 3.0, 0.5, 2.5][seed % 5]
+
+
+def test_fm_cv_ransac_is_identical_to_cv2(ransac):
+    """Mask equality and F to 1e-8 against `cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC, thresh, 0.99)` - the reference's
+    exact call (features_utils.py:195-196) - on 36 seeded scenes (15 ... 4000 matches, 10 ... 80 % outliers)."""
+    for seed, n, of, noise, thresh in _cv_scenes():
+        p1, p2, _ = G.two_view_scene(n, of, noise, seed=500 + seed)
+        Fc, mc = cv2.findFundamentalMat(p1, p2, cv2.FM_RANSAC, thresh, 0.99)
+        Fg, mg = ransac.run_cv(p1, p2, thresh, 0.99)
+        assert mg is not None and np.array_equal(mc, mg), (seed, n, int(mc.sum()), None if mg is None else int(mg.sum()), ransac.last_info)
+        assert np.abs(Fc - Fg).max() <= 1e-8 * np.abs(Fc).max(), (seed, n)
+        assert ransac.last_count == int(mc.sum())
+
+
+def test_fm_cv_ransac_golden_fixtures(ransac):
+    """The committed masks / F were produced by cv2 (tests/golden/make_golden_fm_cv.py); incl. an integer grid with
+    duplicated points (getSubset redraws, checkSubset rejections) and 4000 correspondences."""
+    from helpers import fm_cv_golden_cases
+    for c, p1, p2, thresh, F, mask in fm_cv_golden_cases():
+        Fg, mg = ransac.run_cv(p1, p2, thresh, 0.99)
+        assert np.array_equal(mask, mg), c
+        assert np.abs(F - Fg).max() <= 1e-8 * np.abs(F).max(), c
+
+
+def test_fm_cv_ransac_matches_restatement_bookkeeping(ransac):
+    """Winning iteration / model / final iteration bound equal the restatement's (oracle/cv_ransac.py)."""
+    from oracle import cv_ransac as R
+    for seed in (1, 2, 3):
+        p1, p2, _ = G.two_view_scene(400, 0.5, 0.5, seed=700 + seed)
+        _, mg = ransac.run_cv(p1, p2, 1.0, 0.99)
+        _, mo, info = R.ransac_run(*R._prep(p1, p2), 1.0)
+        assert np.array_equal(mg.ravel(), mo) and ransac.last_info[:3] == (info["winner"][0], info["winner"][1], info["niters"])
+
+
+def test_filter_matches_ransac_gpu_cv2_mode_is_reference_identical():
+    """`filter_matches_ransac` in "gpu_cv2" mode keeps exactly the matches the reference keeps (lists and array-native
+    containers); fewer than 15 matches are OpenCV's LMedS branch and go to cv2; fewer than 8 pass through."""
+    from b200slam import features_utils as fu
+    from b200slam.containers import DMatchArray, KeyPointArray
+    fu.set_ransac_mode("gpu_cv2")
+    try:
+        for seed, (n, out_frac, noise, thresh) in enumerate([(600, 0.3, 0.15, 1.0), (1300, 0.2, 0.3, 2.5), (2048, 0.1, 0.1, 1.0),
+                                                             (90, 0.4, 0.5, 3.0), (12, 0.2, 0.3, 1.0), (7, 0.0, 0.1, 1.0)]):
+            p1, p2, _ = G.two_view_scene(n, out_frac, noise, 40 + seed)
+            kp1 = [cv2.KeyPoint(float(x), float(y), 1) for x, y in p1]
+            kp2 = [cv2.KeyPoint(float(x), float(y), 1) for x, y in p2]
+            ms = [cv2.DMatch(i, i, 0.0) for i in range(n)]
+            want = [m.queryIdx for m in fu.filter_matches_ransac_cv2(kp1, kp2, ms, thresh)]
+            got = fu.filter_matches_ransac(kp1, kp2, ms, thresh)
+            assert [m.queryIdx for m in got] == want
+            got_a = fu.filter_matches_ransac(KeyPointArray(p1), KeyPointArray(p2), DMatchArray(np.stack([np.arange(n)] * 2, 1)), thresh)
+            assert isinstance(got_a, DMatchArray) and got_a.queryIdx.tolist() == want
+    finally:
+        fu.set_ransac_mode("cv2")
