@@ -23,7 +23,10 @@ struct TcpGemmCfg {
 #ifndef B2S_TCP_EPI_WARPS_WIDE
 #define B2S_TCP_EPI_WARPS_WIDE 8
 #endif
-  static constexpr int EPI_WARPS = (BN == 64 || NP == 3) ? 8 : B2S_TCP_EPI_WARPS_WIDE;    // <= 4 * BN / 32: every epilogue warp must own a chunk
+#ifndef B2S_TCP_EPI_WARPS_96
+#define B2S_TCP_EPI_WARPS_96 B2S_TCP_EPI_WARPS_WIDE
+#endif
+  static constexpr int EPI_WARPS = (BN == 64 || NP == 3) ? 8 : (BN == 96 ? B2S_TCP_EPI_WARPS_96 : B2S_TCP_EPI_WARPS_WIDE);    // <= 4 * BN / 32: every epilogue warp must own a chunk
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int STG_BYTES = EPI_WARPS * 4096;                       // per-warp output staging tiles
   static constexpr int BIAS_FLOATS = 32 * EPI_WARPS;                       // one 32-float bias chunk per epilogue warp
@@ -36,6 +39,15 @@ struct TcpGemmCfg {
   // 256 / BN accumulators: measured 1.50 -> 1.45 ms per match at 8 pairs, GEMM error vs float64 3e-7 (K = 256) / 5e-7
   // (K = 512) of the output scale - still below torch's own fp32 matmul (6e-7) - and every parity test unchanged.
   static constexpr int NACC = NP == 1 ? 1 : 2;
+  // fp16x2 path: the a0*w0 and a0*w1 products of a k-step as ONE MMA with the two weight planes (adjacent in the stage)
+  // as a 2*BN-row B operand -> [main | correction] accumulator columns, then a1*w0 into the correction columns.  The A
+  // plane a0 is read from shared memory once instead of twice per k-step (the SS-form main loop is bound by shared-memory
+  // bandwidth: operand reads + TMA writes).
+#ifndef B2S_TCP_STACK
+#define B2S_TCP_STACK 1
+#endif
+  static constexpr bool STACK = NP == 2 && B2S_TCP_STACK != 0;
+  static constexpr int MAIN_COL = STACK ? 0 : BN, CORR_COL = STACK ? BN : 0;   // accumulator columns inside a buffer (NACC == 2)
   static_assert(STAGES >= 2, "need a double-buffered operand ring");
   static_assert(NACC * BN <= ACC_COLS, "accumulators of one tile must fit one TMEM buffer");
 };
@@ -160,15 +172,32 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
           tc::tc_fence_after();
           if (kb == 0) stamp(1, lt, 2);                     // first operand stage of the tile landed
           const uint32_t a0 = tc::smem_u32(smem + s * Cfg::STAGE_BYTES), b0 = a0 + NP * Cfg::A_BYTES;
+          if constexpr (Cfg::STACK) {
+            constexpr uint32_t idesc2 = tc::idesc_planes<NP>(128, 2 * BN, 0, 0);
 #pragma unroll
-          for (int tm = 0; tm < Terms::N; ++tm) {
-            const int acc = (Cfg::NACC == 1) ? 0 : (tm == Terms::N - 1 ? 1 + kb % (Cfg::NACC - 1) : 0);
+            for (int k = 0; k < Cfg::BK / 16; ++k) {      // a0 * [w0 ; w1] -> [main | correction]
+              const uint64_t ad = tc::smem_desc_sw128(a0 + k * 32, 16, 1024);
+              const uint64_t bd = tc::smem_desc_sw128(b0 + k * 32, 16, 1024);
+              tc::umma_bf16(acc_base, ad, bd, idesc2, used);
+              used = 1u;
+            }
 #pragma unroll
-            for (int k = 0; k < Cfg::BK / 16; ++k) {
-              const uint64_t ad = tc::smem_desc_sw128(a0 + Terms::a(tm) * Cfg::A_BYTES + k * 32, 16, 1024);
-              const uint64_t bd = tc::smem_desc_sw128(b0 + Terms::b(tm) * Cfg::B_BYTES + k * 32, 16, 1024);
-              tc::umma_bf16(acc_base + acc * BN, ad, bd, idesc, (used >> acc) & 1u);
-              used |= 1u << acc;
+            for (int k = 0; k < Cfg::BK / 16; ++k) {      // a1 * w0 -> correction
+              const uint64_t ad = tc::smem_desc_sw128(a0 + Cfg::A_BYTES + k * 32, 16, 1024);
+              const uint64_t bd = tc::smem_desc_sw128(b0 + k * 32, 16, 1024);
+              tc::umma_bf16(acc_base + BN, ad, bd, idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int tm = 0; tm < Terms::N; ++tm) {
+              const int acc = (Cfg::NACC == 1) ? 0 : (tm == Terms::N - 1 ? 1 + kb % (Cfg::NACC - 1) : 0);
+#pragma unroll
+              for (int k = 0; k < Cfg::BK / 16; ++k) {
+                const uint64_t ad = tc::smem_desc_sw128(a0 + Terms::a(tm) * Cfg::A_BYTES + k * 32, 16, 1024);
+                const uint64_t bd = tc::smem_desc_sw128(b0 + Terms::b(tm) * Cfg::B_BYTES + k * 32, 16, 1024);
+                tc::umma_bf16(acc_base + acc * BN, ad, bd, idesc, (used >> acc) & 1u);
+                used |= 1u << acc;
+              }
             }
           }
           tc::umma_commit(&empty[s]);                       // frees the stage when these MMAs retire
@@ -240,7 +269,7 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
         } else {
           // main-term accumulators first (1 .. n_main), the correction accumulator last
           const int n_main = nkb < Cfg::NACC - 1 ? nkb : Cfg::NACC - 1;
-          tc::tmem_ld32(taddr + BN, v);
+          tc::tmem_ld32(taddr + Cfg::MAIN_COL, v);
           tc::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -251,7 +280,7 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
           }
-          tc::tmem_ld32(taddr, v);
+          tc::tmem_ld32(taddr + Cfg::CORR_COL, v);
           tc::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = NP == 2 ? fmaf(__uint_as_float(v[j]), Terms::CORR, f[j]) : f[j] + __uint_as_float(v[j]);

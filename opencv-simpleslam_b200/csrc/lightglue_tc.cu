@@ -264,7 +264,8 @@ int lgtc_create(LgTensorCore** out, size_t n_layers, int planes) {
 
 int lgtc_set_layer(LgTensorCore* tc, int li, const LgTcLayerSrc& s) {
   TcLayer& l = tc->L[li];
-  B2S_TRY(make_linear(tc, s.wqkv, s.bqkv, 768, 256, &l.qkv));
+  static const int qkv_env = [] { const char* e = std::getenv("B2S_QKV_BN"); const int v = e ? std::atoi(e) : 0; return (v == 128 || v == 96) ? v : 0; }();
+  B2S_TRY(make_linear(tc, s.wqkv, s.bqkv, 768, 256, &l.qkv, 0, qkv_env));
   B2S_TRY(make_folded_ffn1(tc, s.w1, s.b1, s.wo, s.bo, &l.w1));
   // FFN second layer (N = 256, K = 512): 128-wide tiles on the fp16x2 path (an M128 x N64 MMA reads 192 B of operands per
   // clock from shared memory, N128 128 B: measured 1.051 -> 1.037 ms per pair), 64-wide otherwise (B2S_FFN2_BN overrides)
