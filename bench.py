@@ -374,12 +374,37 @@ def run_ours(args):
     # ---- e2e through the drop-in API with host buffers, one pair per call like the reference's callers ----------
     e2e_pairs = max(4, min(K * P, 24))
     e2e_sets = {}
+    ransac_leg = []
     prev = fu.feature_extractor(ns, frames_np[0], det)
     for t in range(1, 4):   # warm-up; rank 0 keeps these pairs' match sets for the parity check (frames 0..3 = the CPU leg's)
         cur = fu.feature_extractor(ns, frames_np[t % len(frames_np)], det)
         ms = fu.feature_matcher(ns, prev[0], cur[0], prev[1], cur[1], mat)
         e2e_sets[t] = _pos_pairs(prev[0], cur[0], ms)
+        if rank == 0:
+            ransac_leg.append((prev[0], cur[0], ms))
         prev = cur
+    # ---- the stage right behind the matcher: filter_matches_ransac, reference body (cv2) vs OpenCV's RANSAC
+    #      reproduced on the GPU (b2s_fm_cv_ransac_host) on the matches just produced ----------
+    ransac = None
+    if rank == 0 and ransac_leg:
+        fu.filter_matches_ransac_gpu_cv2(*ransac_leg[0], 1.0)       # handle creation
+        t_cv = t_gpu = 0.0
+        same = True
+        sizes = []
+        for kpa, kpb, mm in ransac_leg:
+            ta = time.perf_counter()
+            keep_cv = fu.filter_matches_ransac_cv2(kpa, kpb, mm, 1.0)
+            tb = time.perf_counter()
+            keep_gpu = fu.filter_matches_ransac_gpu_cv2(kpa, kpb, mm, 1.0)
+            tc = time.perf_counter()
+            t_cv += tb - ta; t_gpu += tc - tb
+            same &= [(m.queryIdx, m.trainIdx) for m in keep_cv] == [(m.queryIdx, m.trainIdx) for m in keep_gpu]
+            sizes.append((len(mm), len(keep_cv)))
+        ransac = {"pairs": len(ransac_leg), "matches_in_out": sizes, "identical_to_cv2": bool(same),
+                  "cv2_ms_per_call": 1e3 * t_cv / len(ransac_leg), "gpu_cv2_ms_per_call": 1e3 * t_gpu / len(ransac_leg),
+                  "what": "features_utils.filter_matches_ransac(kp1, kp2, matches, 1.0) on the per-call leg's first pairs: the reference's "
+                          "cv2.findFundamentalMat call vs b2s_fm_cv_ransac_host (host lists in, surviving cv2.DMatch list out, "
+                          "wall clock incl. the Python point gathering)"}
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -536,6 +561,8 @@ def run_ours(args):
         out["adaptive_leg"] = adaptive
     if win:
         out["config3_window"] = win
+    if ransac:
+        out["ransac_filter"] = ransac
     if world == 1 and not args.no_cpu_baseline:
         keep = {}
         v, ms_cpu, meta, _ = cpu_reference_arm(steps=2, warmup=1, keep=keep)

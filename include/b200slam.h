@@ -237,8 +237,9 @@ int b2s_fm_ransac_host(b2s_fm* h, const float* pts1, const float* pts2, int n, f
  * thresh, confidence)` (features_utils.py:195-196) for n >= 15 - below that OpenCV silently runs LMedS, whose winner for
  * n <= 13 is decided by the rounding noise of near-zero residuals and is left to cv2 itself by the Python drop-in.
  * OpenCV's loop (calib3d ptsetreg.cpp RANSACPointSetRegistrator::run) is reproduced, not approximated: the host draws
- * the subsets of all max_iters iterations from cv::RNG((uint64)-1) (getSubset + haveCollinearPoints - the stream does not
- * depend on the models), the device solves every subset with fundam.cpp's run7Point (including the null-space basis
+ * the iterations' subsets from cv::RNG((uint64)-1) ahead of the models (getSubset + haveCollinearPoints - the stream does
+ * not depend on them; waves of 64 / 256 / the rest, so a high inlier ratio stops after the first wave), the device solves
+ * every subset of a wave with fundam.cpp's run7Point (including the null-space basis
  * OpenCV's SVD returns, which fixes the order of the up-to-three models) and counts inliers with computeError's float32
  * errors, and the host replays the strictly-greater update and RANSACUpdateNumIters over the counts; a last kernel
  * writes the winner's mask.  max_iters <= the handle's max_hypotheses (cv2's default is 1000).

@@ -59,10 +59,10 @@ bool fmcv_collinear(const float* pts, const int* idx) {
   return false;
 }
 
-// every iteration's subset (getSubset with 10000 attempts); returns how many were drawn before getSubset failed
-int fmcv_subsets(const float* pts1, const float* pts2, int n, int max_iters, int32_t* out) {
-  CvRng rng((uint64_t)-1);
-  for (int it = 0; it < max_iters; ++it) {
+// the subsets of the next `count` iterations of the loop (getSubset with 10000 attempts), continuing the call's RNG
+// stream; returns how many were drawn before getSubset failed
+int fmcv_subsets(CvRng& rng, const float* pts1, const float* pts2, int n, int count, int32_t* out) {
+  for (int it = 0; it < count; ++it) {
     int* idx = out + 7 * it;
     bool found = false;
     for (int attempt = 0; attempt < 10000 && !found; ++attempt) {
@@ -80,7 +80,7 @@ int fmcv_subsets(const float* pts1, const float* pts2, int n, int max_iters, int
     }
     if (!found) return it;
   }
-  return max_iters;
+  return count;
 }
 
 int fmcv_update_num_iters(double p, double ep, int model_points, int max_iters) {
@@ -204,41 +204,57 @@ extern "C" int b2s_fm_cv_ransac_host(b2s_fm* h, const float* pts1, const float* 
   std::memcpy(hp2, pts2, (size_t)n * 8);
   B2S_CUDA(cudaMemcpyAsync(h->d_pts1, hp1, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
   B2S_CUDA(cudaMemcpyAsync(h->d_pts2, hp2, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
-  const int n_sub = fmcv_subsets(pts1, pts2, n, max_iters, hsub);    // overlaps the point upload
   if (n_inliers) *n_inliers = 0;
-  if (info4) { info4[0] = -1; info4[1] = -1; info4[2] = max_iters; info4[3] = n_sub; }
-  if (n_sub == 0) {            // getSubset failed in iteration 0: cv2 returns no model
+  if (info4) { info4[0] = -1; info4[1] = -1; info4[2] = max_iters; info4[3] = 0; }
+  FmCvParams p = {};
+  p.m1 = h->d_pts1; p.m2 = h->d_pts2; p.n = n; p.sign1 = h->sign1; p.sign2 = h->sign2;
+  p.thresh2 = (float)(thresh * thresh);
+  p.mask = h->d_mask; p.F = h->d_F;
+  // RANSACPointSetRegistrator::run in WAVES of iterations (64, 256, the rest): with a high inlier ratio the adaptive
+  // bound drops to a handful of iterations after the first good model and the later waves are never drawn or solved.
+  // The subsets of a wave are drawn on the host while the previous copies / kernels are in flight.
+  CvRng rng((uint64_t)-1);
+  int niters = max_iters, max_good = 0, win_it = -1, win_k = -1, drawn = 0;
+  bool exhausted = false;
+  const int wave_end[3] = {std::min(64, max_iters), std::min(320, max_iters), max_iters};
+  for (int w = 0; w < 3 && drawn < niters && !exhausted; ++w) {
+    const int lo = drawn, want = std::min(wave_end[w], niters) - lo;
+    if (want <= 0) continue;
+    const int got = fmcv_subsets(rng, pts1, pts2, n, want, hsub + (size_t)lo * 7);
+    exhausted = got < want;
+    drawn += got;
+    if (got == 0) break;
+    B2S_CUDA(cudaMemcpyAsync(h->d_subsets + (size_t)lo * 7, hsub + (size_t)lo * 7, (size_t)got * 7 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    p.n_sub = got; p.subsets = h->d_subsets + (size_t)lo * 7;
+    p.models = h->models + (size_t)lo * 27; p.nmodels = h->nmodels + lo; p.counts = h->counts + (size_t)lo * 3;
+    launch_k(k_fmcv_models, dim3(cdiv(got, 32)), dim3(32), 0, h->stream, p);
+    launch_k(k_fmcv_count, dim3(got), dim3(128), 0, h->stream, p);
+    h->launches += 2;
+    B2S_CUDA(cudaMemcpyAsync(hcnt + (size_t)lo * 3, h->counts + (size_t)lo * 3, (size_t)got * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    B2S_CUDA(cudaStreamSynchronize(h->stream));
+    B2S_LAUNCH_CHECK();
+    // the sequential part of the loop over this wave's counts
+    for (int it = lo; it < lo + got && it < niters; ++it) {
+      for (int k = 0; k < 3; ++k) {
+        const int good = hcnt[3 * it + k];
+        if (good < 0) break;
+        if (good > std::max(max_good, 6)) {
+          max_good = good; win_it = it; win_k = k;
+          niters = fmcv_update_num_iters(confidence, (double)(n - good) / n, 7, niters);
+        }
+      }
+    }
+  }
+  (void)hnm;
+  if (info4) info4[3] = drawn;
+  if (drawn == 0) {            // getSubset failed in iteration 0: cv2 returns no model
     B2S_CUDA(cudaStreamSynchronize(h->stream));
     std::memset(mask, 0, (size_t)n);
     return 0;
   }
-  B2S_CUDA(cudaMemcpyAsync(h->d_subsets, hsub, (size_t)n_sub * 7 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-  FmCvParams p = {};
-  p.m1 = h->d_pts1; p.m2 = h->d_pts2; p.n = n; p.n_sub = n_sub; p.subsets = h->d_subsets; p.sign1 = h->sign1; p.sign2 = h->sign2;
-  p.thresh2 = (float)(thresh * thresh);
-  p.models = h->models; p.nmodels = h->nmodels; p.counts = h->counts; p.mask = h->d_mask; p.F = h->d_F;
-  launch_k(k_fmcv_models, dim3(cdiv(n_sub, 32)), dim3(32), 0, h->stream, p);
-  launch_k(k_fmcv_count, dim3(n_sub), dim3(128), 0, h->stream, p);
-  h->launches += 2;
-  B2S_CUDA(cudaMemcpyAsync(hcnt, h->counts, (size_t)n_sub * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-  B2S_CUDA(cudaStreamSynchronize(h->stream));
-  B2S_LAUNCH_CHECK();
-  (void)hnm;
-  // RANSACPointSetRegistrator::run, the sequential part
-  int niters = max_iters, max_good = 0, win_it = -1, win_k = -1;
-  for (int it = 0; it < niters && it < n_sub; ++it) {
-    for (int k = 0; k < 3; ++k) {
-      const int good = hcnt[3 * it + k];
-      if (good < 0) break;
-      if (good > std::max(max_good, 6)) {
-        max_good = good; win_it = it; win_k = k;
-        niters = fmcv_update_num_iters(confidence, (double)(n - good) / n, 7, niters);
-      }
-    }
-  }
   if (info4) { info4[0] = win_it; info4[1] = win_k; info4[2] = niters; }
   if (max_good <= 0) { std::memset(mask, 0, (size_t)n); return 0; }
-  p.winner = win_it * 3 + win_k;
+  p.winner = win_it * 3 + win_k; p.models = h->models;
   launch_k(k_fmcv_mask, dim3(cdiv(n, 256)), dim3(256), 0, h->stream, p);
   h->launches += 1;
   uint8_t* pm = h->h_pin;

@@ -25,11 +25,11 @@ def timeit(fn, iters=20):
     return e0.elapsed_time(e1) / iters, (time.perf_counter() - t0) * 1e3 / iters
 ms, wall = timeit(lambda: det.extract_device(frames[1], _lib.IMG_BGR_U8_HWC, H, W, 3 * W))
 print(f"ALIKED extract: {ms:.3f} ms/frame (wall {wall:.3f})  kp={len(feats[1][0])}")
-precs = sys.argv[1].split(",") if len(sys.argv) > 1 else ["bf16", "fp32", "fp32_simt"]
+precs = sys.argv[1].split(",") if len(sys.argv) > 1 else ["bf16", "fp32", "fp32x3"]
 for prec in [p for p in precs if p != "none"]:
     for dc, wc, tag in ((0.95, 0.99, "adaptive"), (-1, -1, "full-depth")):
         mat = frontend.LightGlue(weights=sl, device=dev, precision=prec, max_kp=NKP, depth_confidence=dc, width_confidence=wc)
         r = mat.match_device(feats[0][0], feats[0][1], feats[1][0], feats[1][1], full=False)
         torch.cuda.synchronize()
-        ms, wall = timeit(lambda: mat.match_device(feats[0][0], feats[0][1], feats[1][0], feats[1][1], full=False), 10 if prec == "fp32_simt" else 20)
+        ms, wall = timeit(lambda: mat.match_device(feats[0][0], feats[0][1], feats[1][0], feats[1][1], full=False), 20)
         print(f"LightGlue {prec} {tag}: {ms:.3f} ms/pair (wall {wall:.3f}) matches={int(r['n'].item())} stop={int(r['stop'].item())}")
