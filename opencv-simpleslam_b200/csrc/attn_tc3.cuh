@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_attn_tc3(const __grid_constan
   using Cfg = A3Cfg<NP>;
   constexpr int A3_NP = NP, A3_SLOT = Cfg::SLOT, A3_KSLOTS = Cfg::KSLOTS, A3_KSLOT = Cfg::KSLOT;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned by pointer ARITHMETIC on the __shared__ array: an integer round trip would make every staging access a generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                               // [3 planes]
   uint8_t* sK = sQ + A3_NP * A3_QPL;                // ring [A3_KSLOTS][3 planes][128 keys]; reused for the final merge
   uint8_t* sV = sK + A3_KSLOTS * A3_KSLOT;          // ring [A3_SLOTS][3 planes][64 keys]

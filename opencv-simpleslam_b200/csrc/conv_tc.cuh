@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(192) k_conv3x3_tc(const __grid_constant__ CUte
   using Cfg = ConvTcCfg<CIN, COUT>;
   using Terms = tc::PlaneTerms<3>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  // aligned by pointer ARITHMETIC on the __shared__ array: an integer round trip would make every staging access a generic LD / ST
+  uint8_t* smem = smem_raw + ((128u - (tc::smem_u32(smem_raw) & 127u)) & 127u);
   uint8_t* sA = smem;                                       // [3 planes][NCH][R+2][130][8]
   uint8_t* sW = sA + 3 * Cfg::A_PLANE;                      // [3 planes][9*NCH][COUT][8]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 3 * Cfg::W_PLANE);

@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(TcGemmCfg<BN, NP>::THREADS) k_gemm_tc(const __
   using Cfg = TcGemmCfg<BN, NP>;
   using Terms = tc::PlaneTerms<NP>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned by pointer ARITHMETIC on the __shared__ array: an integer round trip would make every staging access a generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   // stage s: A planes at s*STAGE_BYTES + p*A_BYTES, W planes behind them
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* full = bars;                 // [STAGES]

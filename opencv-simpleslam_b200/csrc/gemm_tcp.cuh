@@ -15,7 +15,11 @@
 
 namespace b2s {
 
-template <int BN, int NP>
+// EW = 16: the PLANES-ONLY variant for the K = 256 layer GEMMs (QKV with rotary, cross QK / V), whose tile period is set by
+// the epilogue (main loop 3.5-5 k cycles, 8 epilogue warps with two 32 x 32 chunks each 7 k): sixteen epilogue warps own one
+// chunk each (four resident warps per scheduler hide the tcgen05.ld / staging / store latencies), 2 KB of staging per
+// warp, no fp32 output / residual / activation paths (the launcher only selects it for TC_EPI_BF16 / TC_EPI_ROTARY_BF16).
+template <int BN, int NP, int EW = 0>
 struct TcpGemmCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;       // one plane
@@ -26,9 +30,12 @@ struct TcpGemmCfg {
 #ifndef B2S_TCP_EPI_WARPS_96
 #define B2S_TCP_EPI_WARPS_96 B2S_TCP_EPI_WARPS_WIDE
 #endif
-  static constexpr int EPI_WARPS = (BN == 64 || NP == 3) ? 8 : (BN == 96 ? B2S_TCP_EPI_WARPS_96 : B2S_TCP_EPI_WARPS_WIDE);    // <= 4 * BN / 32: every epilogue warp must own a chunk
+  static constexpr int EPI_WARPS = EW ? EW : (BN == 64 || NP == 3) ? 8 : (BN == 96 ? B2S_TCP_EPI_WARPS_96 : B2S_TCP_EPI_WARPS_WIDE);    // <= 4 * BN / 32: every epilogue warp must own a chunk
+  static constexpr bool PLANES_ONLY = EW == 16;
+  static_assert(EW == 0 || (EW == 16 && BN == 128 && NP == 2), "the 16-warp epilogue is the fp16x2, 128-wide, planes-only variant");
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
-  static constexpr int STG_BYTES = EPI_WARPS * 4096;                       // per-warp output staging tiles
+  static constexpr int STG_WARP = PLANES_ONLY ? 2048 : 4096;               // staging tile of one epilogue warp (fp32 32 x 32, or one plane 32 x 32 x 2 B)
+  static constexpr int STG_BYTES = EPI_WARPS * STG_WARP;
   static constexpr int BIAS_FLOATS = 32 * EPI_WARPS;                       // one 32-float bias chunk per epilogue warp
   static constexpr int BUDGET = 227 * 1024 - STG_BYTES - 1024 /*align*/ - 256 /*barriers*/ - BIAS_FLOATS * 4;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 4 ? 4 : BUDGET / STAGE_BYTES;
@@ -43,6 +50,9 @@ struct TcpGemmCfg {
   // as a 2*BN-row B operand -> [main | correction] accumulator columns, then a1*w0 into the correction columns.  The A
   // plane a0 is read from shared memory once instead of twice per k-step (the SS-form main loop is bound by shared-memory
   // bandwidth: operand reads + TMA writes).
+#ifndef B2S_TCP_DIRECT_STORE
+#define B2S_TCP_DIRECT_STORE 0
+#endif
 #ifndef B2S_TCP_STACK
 #define B2S_TCP_STACK 1
 #endif
@@ -83,14 +93,16 @@ __device__ __forceinline__ TcpTile tcp_tile(const TcGemmParams& p, int t, int n_
   return ti;
 }
 
-template <int BN, int NP>
-__global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(const __grid_constant__ CUtensorMap mapA1,
+template <int BN, int NP, int EW = 0>
+__global__ void __launch_bounds__(TcpGemmCfg<BN, NP, EW>::THREADS, 1) k_gemm_tcp(const __grid_constant__ CUtensorMap mapA1,
                                                      const __grid_constant__ CUtensorMap mapA2,
                                                      const __grid_constant__ CUtensorMap mapW, TcGemmParams p, int m_tiles) {
-  using Cfg = TcpGemmCfg<BN, NP>;
+  using Cfg = TcpGemmCfg<BN, NP, EW>;
+  constexpr bool PO = Cfg::PLANES_ONLY;
   using Terms = tc::PlaneTerms<NP>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned by pointer ARITHMETIC on the __shared__ array: an integer round trip would make every staging access a generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   // stage s: A planes at s*STAGE_BYTES + p*A_BYTES, W planes behind them; then the staging tiles, then the barriers
   uint8_t* stg_base = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + Cfg::STG_BYTES);
@@ -215,7 +227,7 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
     // Output staging: thread == row makes each store instruction touch 32 different lines and the LSU serialises them;
     // instead a warp parks its 32 x 32 chunk in shared memory (16-byte slots XOR-swizzled by row: conflict-free both
     // ways) and writes it back row-contiguously (4 rows x 128 B or 8 rows x 64 B per instruction).
-    uint8_t* stg = stg_base + (warp - 2) * 4096;
+    uint8_t* stg = stg_base + (warp - 2) * Cfg::STG_WARP;
     float* sf = reinterpret_cast<float*>(stg);                      // fp32 tile [32 rows][32]
     uint32_t* sp = reinterpret_cast<uint32_t*>(stg);                // or one bf16 plane tile [32 rows][16 words]
     uint4* myrow = reinterpret_cast<uint4*>(sf + lane * 32);
@@ -252,6 +264,20 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
           breg[k] = (c0 < BN && ti.n0 + c0 < p.N) ? __ldg(bsrc + c0) : 0.f;
         }
       }
+      // TC_EPI_RESID_F32_BF16: the fp32 residual stream x of this warp's chunk (row-contiguous, staged like the outputs) is
+      // requested before the accumulators are waited for, the next chunk's while the current one is packed and stored -
+      // the loads sat at the head of the epilogue's dependency chain (ncu source page: 60 % of the FFN2 launch's stall
+      // samples on the eight stores that park x in the staging tile)
+      uint4 xp[8];
+      auto load_x = [&](int gc) {
+#pragma unroll
+        for (int i8 = 0; i8 < 8; ++i8) {
+          const int R = i8 * 4 + (lane >> 3), sl = lane & 7;
+          xp[i8] = make_uint4(0u, 0u, 0u, 0u);
+          if (R < rows_q) xp[i8] = *reinterpret_cast<const uint4*>(out_f32 + (qrow0 + R) * p.ld_f32 + gc + sl * 4);
+        }
+      };
+      if (!PO && p.epi == TC_EPI_RESID_F32_BF16 && ti.n0 + cgrp * 32 < p.N) load_x(ti.n0 + cgrp * 32);
       tc::mbar_wait(&tmem_full[ab], aph);
       tc::tc_fence_after();
       if (lane == 0 && (warp == 2 || warp == 6)) stamp(warp == 2 ? 2 : 3, lt, 1);   // accumulators complete
@@ -308,11 +334,11 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
           }
           __syncwarp();
         }
-        if (p.alpha != 0.f) {
+        if (!PO && p.alpha != 0.f) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
         }
-        if (p.residual && live) {
+        if (!PO && p.residual && live) {
           const float4* rs = reinterpret_cast<const float4*>(p.residual + grow * p.ld_res + gc);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -320,7 +346,7 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
             f[4 * q] += rv.x; f[4 * q + 1] += rv.y; f[4 * q + 2] += rv.z; f[4 * q + 3] += rv.w;
           }
         }
-        if (p.act == 1) {
+        if (!PO && p.act == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = selu_f(f[j]);
         }
@@ -342,7 +368,7 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
             }
           }
         }
-        if (p.epi == TC_EPI_F32 || p.epi == TC_EPI_F32_BF16) {
+        if (!PO && (p.epi == TC_EPI_F32 || p.epi == TC_EPI_F32_BF16)) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             myrow[q ^ (lane & 7)] = make_uint4(__float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]), __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3]));
@@ -360,14 +386,16 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
           __syncwarp();
           if (p.epi == TC_EPI_F32) continue;
         }
-        if (p.epi == TC_EPI_RESID_F32_BF16) {
+        if (!PO && p.epi == TC_EPI_RESID_F32_BF16) {
           // x (fp32 residual stream, updated in place): row-contiguous load into the staging tile, add, write back
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8) {
             const int R = i8 * 4 + (lane >> 3), sl = lane & 7;
-            uint4 xv = make_uint4(0u, 0u, 0u, 0u);
-            if (R < rows_q) xv = *reinterpret_cast<const uint4*>(out_f32 + (qrow0 + R) * p.ld_f32 + gc + sl * 4);
-            reinterpret_cast<uint4*>(sf + R * 32)[sl ^ (R & 7)] = xv;
+            reinterpret_cast<uint4*>(sf + R * 32)[sl ^ (R & 7)] = xp[i8];
+          }
+          {
+            const int c1 = c0 + 8 * Cfg::EPI_WARPS;
+            if (c1 < BN && ti.n0 + c1 < p.N) load_x(ti.n0 + c1);      // next chunk of this warp, in flight behind this one
           }
           __syncwarp();
 #pragma unroll
@@ -409,6 +437,16 @@ __global__ void __launch_bounds__(TcpGemmCfg<BN, NP>::THREADS, 1) k_gemm_tcp(con
               if (pl + 1 < NP) { f[2 * j] -= __uint_as_float(w[j] << 16); f[2 * j + 1] -= __uint_as_float(w[j] & 0xFFFF0000u); }
             }
           }
+#if B2S_TCP_DIRECT_STORE
+          // planes straight from registers: a thread owns 64 contiguous bytes of its row (no shared-memory round trip -
+          // the staging tile competes with the MMA operand reads and the TMA writes for shared-memory bandwidth)
+          if (lane < rows_q) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pl * p.out_plane + (qrow0 + lane) * p.ld_bf16 + gc);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          }
+          continue;
+#endif
           uint4* prow = reinterpret_cast<uint4*>(sp + lane * 16);
 #pragma unroll
           for (int j = 0; j < 4; ++j) prow[j ^ ((lane >> 1) & 3)] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);

@@ -228,6 +228,7 @@ static void tc_kernel_attrs() {
   gemm_attr<64, 2>(); gemm_attr<128, 2>(); gemm_attr<96, 2>();
   gemmp_attr<64, 1>(); gemmp_attr<128, 1>(); gemmp_attr<64, 3>(); gemmp_attr<128, 3>(); gemmp_attr<96, 1>(); gemmp_attr<96, 3>();
   gemmp_attr<64, 2>(); gemmp_attr<128, 2>(); gemmp_attr<96, 2>();
+  cudaFuncSetAttribute(k_gemm_tcp<128, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcpGemmCfg<128, 2, 16>::SMEM);
   cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
   cudaFuncSetAttribute(k_attn_tc3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Cfg<3>::SMEM);
   cudaFuncSetAttribute(k_attn_tc3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3Cfg<2>::SMEM);
@@ -238,6 +239,14 @@ static void launch_gemm_any(cudaStream_t st, const CUtensorMap& a1, const CUtens
   if (gemm_persistent()) launch_gemm_p<BN, NP>(st, a1, a2, w, p, m_tiles);
   else launch_k(k_gemm_tc<BN, NP>, dim3(cdiv(p.N, BN), m_tiles), TcGemmCfg<BN, NP>::THREADS, TcGemmCfg<BN, NP>::SMEM, st, a1, a2, w, p);
 }
+// the 16-epilogue-warp planes-only kernel (gemm_tcp.cuh) for fp16x2 GEMMs whose epilogue emits operand planes only
+static bool gemm_epi16() {
+  static const bool on = [] { const char* e = std::getenv("B2S_GEMM_EPI16"); return !(e && e[0] == '0'); }();
+  return on;
+}
+static bool planes_only(const TcGemmParams& p) {
+  return (p.epi == TC_EPI_BF16 || p.epi == TC_EPI_ROTARY_BF16) && p.alpha == 0.f && !p.residual && p.act == 0 && !p.out_f32 && !p.out_f32_t && !p.ts;
+}
 template <int NP>
 static void launch_gemm_bn(int BN, cudaStream_t st, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const TcGemmParams& p, int m_tiles) {
   if (BN == 64) launch_gemm_any<64, NP>(st, a1, a2, w, p, m_tiles);
@@ -245,6 +254,11 @@ static void launch_gemm_bn(int BN, cudaStream_t st, const CUtensorMap& a1, const
   else launch_gemm_any<128, NP>(st, a1, a2, w, p, m_tiles);
 }
 static void launch_gemm(int np, int BN, cudaStream_t st, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w, const TcGemmParams& p, int m_tiles) {
+  if (np == 2 && BN == 128 && gemm_persistent() && gemm_epi16() && planes_only(p)) {
+    const int total = m_tiles * ((p.N + 127) / 128);
+    launch_k(k_gemm_tcp<128, 2, 16>, dim3(std::min(total, sm_count())), TcpGemmCfg<128, 2, 16>::THREADS, TcpGemmCfg<128, 2, 16>::SMEM, st, a1, a2, w, p, m_tiles);
+    return;
+  }
   if (np == 1) launch_gemm_bn<1>(BN, st, a1, a2, w, p, m_tiles);
   else if (np == 2) launch_gemm_bn<2>(BN, st, a1, a2, w, p, m_tiles);
   else launch_gemm_bn<3>(BN, st, a1, a2, w, p, m_tiles);
@@ -265,7 +279,8 @@ int lgtc_create(LgTensorCore** out, size_t n_layers, int planes) {
 int lgtc_set_layer(LgTensorCore* tc, int li, const LgTcLayerSrc& s) {
   TcLayer& l = tc->L[li];
   static const int qkv_env = [] { const char* e = std::getenv("B2S_QKV_BN"); const int v = e ? std::atoi(e) : 0; return (v == 128 || v == 96) ? v : 0; }();
-  B2S_TRY(make_linear(tc, s.wqkv, s.bqkv, 768, 256, &l.qkv, 0, qkv_env));
+  // N = 768 on the fp16x2 path: 128-wide tiles so that the 16-warp planes-only epilogue applies (B2S_QKV_BN overrides)
+  B2S_TRY(make_linear(tc, s.wqkv, s.bqkv, 768, 256, &l.qkv, 0, qkv_env ? qkv_env : (tc->np == 2 && gemm_epi16() ? 128 : 0)));
   B2S_TRY(make_folded_ffn1(tc, s.w1, s.b1, s.wo, s.bo, &l.w1));
   // FFN second layer (N = 256, K = 512): 128-wide tiles on the fp16x2 path (an M128 x N64 MMA reads 192 B of operands per
   // clock from shared memory, N128 128 B: measured 1.051 -> 1.037 ms per pair), 64-wide otherwise (B2S_FFN2_BN overrides)
