@@ -1,6 +1,6 @@
 """Small workloads for compute-sanitizer (run under gpurun): exercises every hand-written mbarrier / TMEM / TMA
 pipeline at sizes the sanitizer finishes in minutes.
-  python tools/sanitize_target.py [gemm|attn|conv|match|batch|all]"""
+  python tools/sanitize_target.py [gemm|attn|conv|match|batch|geom|all]"""
 import ctypes as C
 import os
 import sys
@@ -20,7 +20,7 @@ g = torch.Generator().manual_seed(0)
 
 
 def gemm():
-    for fn in ("b2s_test_gemm_tc", "b2s_test_gemm_tc3"):
+    for fn in ("b2s_test_gemm_tc", "b2s_test_gemm_tc3", "b2s_test_gemm_h2"):
         for (M, N, K) in [(200, 256, 256), (333, 512, 512), (130, 768, 256)]:
             A = torch.randn(M, K, generator=g); W = torch.randn(N, K, generator=g) / K ** 0.5; b = torch.randn(N, generator=g)
             out = np.empty((M, N), np.float32)
@@ -30,7 +30,7 @@ def gemm():
 
 
 def attn():
-    for fn in ("b2s_test_attn_tc", "b2s_test_attn_tc3"):
+    for fn in ("b2s_test_attn_tc", "b2s_test_attn_tc3", "b2s_test_attn_h2"):
         for (nq, nk) in [(130, 200), (300, 390)]:
             q = torch.randn(nq, 256, generator=g); k = torch.randn(nk, 256, generator=g); v = torch.randn(nk, 256, generator=g)
             out = np.empty((nq, 256), np.float32)
@@ -62,6 +62,19 @@ def conv_and_match(batch=False):
         print("extract_batch", n.cpu().tolist())
 
 
+def geom():
+    from b200slam.geometry import FundamentalRansac
+    rng = np.random.default_rng(0)
+    r = FundamentalRansac(max_points=1024, n_hyp=1024)
+    p1 = rng.uniform(0, 600, (300, 2)).astype(np.float32)
+    p2 = (p1 + rng.normal(0, 1.5, p1.shape) + np.array([12.0, 1.0])).astype(np.float32)
+    F, mask = r.run_cv(p1, p2, 1.0, 0.99)
+    F2, mask2 = r.run_host(p1, p2, 1.0)
+    print("fm cv inliers", r.last_count, "info", r.last_info, "parallel", int(mask2.sum()))
+
+
+if what in ("geom", "all"):
+    geom()
 if what in ("gemm", "all"):
     gemm()
 if what in ("attn", "all"):
