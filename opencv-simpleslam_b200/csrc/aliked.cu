@@ -526,7 +526,7 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
     ScoreParams sp;
     sp.s8 = h->s8; sp.Hp = Hp; sp.Wp = Wp; sp.w2 = h->sh2; sp.w4 = h->sh4; sp.w6 = h->sh6;
     sp.score = h->score; sp.Hr = Hr; sp.Wr = Wr; sp.pad_t = pp.pad_t; sp.pad_l = pp.pad_l;
-    launch_k(k_aliked_score, dim3(cdiv(Wp, 32), cdiv(Hp, 8)), 256, 0, st, sp);
+    launch_k(k_aliked_score, dim3(cdiv(Wp, 32), cdiv(Hp, SCORE_TH)), 256, 0, st, sp);
     h->launches += 3; B2S_LAUNCH_CHECK();
   }
   // ---- DKD ----

@@ -122,6 +122,10 @@ __global__ void __launch_bounds__(256) k_preprocess(PreParams p) {
 // block = (16, 8, COUT/16): thread -> 2x2 pixels x 16 output channels; tile 32 x 16 pixels.
 // weights: [CIN][9][COUT]
 // ---------------------------------------------------------------------------------------
+// SELU as a CALL: k_conv3x3's epilogue applies it to 64 values per thread, and 64 inlined expm1f bodies made the kernel
+// 11.7 k instructions (28 % of its stall samples were instruction-fetch stalls, profiles/r2f_stall_top_lines_aliked.txt)
+__device__ __noinline__ float selu_call(float x) { return selu_f(x); }
+
 template <int CIN, int COUT, bool POOL2>
 __global__ void __launch_bounds__(128 * (COUT / 16), COUT == 16 ? 5 : 1) k_conv3x3(const float* __restrict__ in, int H, int W,
                                                                const float* __restrict__ w, const float* __restrict__ bias,
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(128 * (COUT / 16), COUT == 16 ? 5 : 1) k_conv3
 #pragma unroll
         for (int o = 0; o < 16; ++o) {
           v[o] = acc[py * 2 + px][o] + bias[tz * 16 + o];
-          if (act == 1) v[o] = selu_f(v[o]);
+          if (act == 1) v[o] = selu_call(v[o]);
         }
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(128 * (COUT / 16), COUT == 16 ? 5 : 1) k_conv3
         float v = acc[py * 2 + px][o] + bias[co];
         const size_t idx = ((size_t)co * H + gy) * W + gx;
         if (residual) v += residual[idx];
-        if (act == 1) v = selu_f(v);
+        if (act == 1) v = selu_call(v);
         out[idx] = v;
       }
     }
@@ -659,19 +663,21 @@ __global__ void __launch_bounds__(256) k_aliked_featmap(FeatSrc s, float* __rest
 // ---------------------------------------------------------------------------------------
 // K5b: score-head tail: conv3x3(8->4)+SELU, conv3x3(4->4)+SELU, conv3x3(4->1), sigmoid, all
 // zero-padded at the PADDED image border; writes the unpadded score map [Hr][Wr].
-// tile 32x8, halo 3, block 256.  w2 [4][8][9], w4 [4][4][9], w6 [4][9].
+// tile 32x16, halo 3, block 256.  w2 [4][8][9], w4 [4][4][9], w6 [4][9].
 // ---------------------------------------------------------------------------------------
 struct ScoreParams {
   const float* s8; int Hp, Wp; const float* w2; const float* w4; const float* w6;
   float* score; int Hr, Wr, pad_t, pad_l;
 };
 
+constexpr int SCORE_TH = 16;
 __global__ void __launch_bounds__(256) k_aliked_score(ScoreParams p) {
   pdl_wait();
-  constexpr int TW = 32, TH = 8;
+  constexpr int TW = 32, TH = SCORE_TH;     // 32 x 16 outputs per CTA: 1.6 x halo overhead on the first layer instead of 2.1 x at TH = 8
   __shared__ float t0[8][TH + 6][TW + 6];
   __shared__ float t1[4][TH + 4][TW + 4];
-  __shared__ float t2[4][TH + 2][TW + 2];
+  float (*t2)[TH + 2][TW + 2] = reinterpret_cast<float (*)[TH + 2][TW + 2]>(&t0[0][0][0]);   // second layer's output reuses the input tile (dead by then)
+  static_assert(4 * (TH + 2) * (TW + 2) <= 8 * (TH + 6) * (TW + 6), "t2 must fit inside t0");
   __shared__ float w2[4 * 8 * 9], w4[4 * 4 * 9], w6[4 * 9];
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
@@ -720,8 +726,8 @@ __global__ void __launch_bounds__(256) k_aliked_score(ScoreParams p) {
     for (int o = 0; o < 4; ++o) t2[o][r][q] = in ? selu_f(a[o]) : 0.f;
   }
   __syncthreads();
-  {
-    const int r = tid / TW, q = tid % TW;
+  for (int e = tid; e < TH * TW; e += 256) {
+    const int r = e / TW, q = e % TW;
     const int gy = y0 + r, gx = x0 + q;
     const int yu = gy - p.pad_t, xu = gx - p.pad_l;
     if (gy < p.Hp && gx < p.Wp && yu >= 0 && yu < p.Hr && xu >= 0 && xu < p.Wr) {
