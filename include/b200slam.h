@@ -34,7 +34,8 @@ enum {
   B2S_ECUDA = -2,    /* CUDA runtime error (message has the cudaError string) */
   B2S_ENOMEM = -3,
   B2S_ENODEV = -4,   /* no usable sm_100 device */
-  B2S_ESIZE = -5     /* input larger than the handle supports */
+  B2S_ESIZE = -5,    /* input larger than the handle supports */
+  B2S_ERANGE = -6    /* ALIKED: an activation left the fp16 range of the two-plane convolutions (re-create with B2S_ALIKED_CONV_NP=3) */
 };
 
 /* Arithmetic of the LightGlue matcher.

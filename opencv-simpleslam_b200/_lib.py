@@ -31,6 +31,9 @@ class LgCfg(C.Structure):
 FP32, BF16, FP32X3 = 0, 1, 2
 PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp32x3": FP32X3}
 LG_RANGE = -2   # n_matches of a pair whose launch sequence left the fp16 operand range (B2S_FP32)
+ALIKED_RANGE = -2   # keypoint count of a frame whose fp16x2 convolutions left the fp16 range (device-resident APIs)
+ALIKED_RANGE_MSG = ("b200slam: an ALIKED activation left the fp16 range of the two-plane convolutions; "
+                    "re-create the extractor with B2S_ALIKED_CONV_NP=3 (three bf16 planes)")
 IMG_BGR_U8_HWC, IMG_RGB_F32_CHW = 0, 1
 vp, i32p, f32p = C.c_void_p, C.c_void_p, C.c_void_p   # raw addresses (device or host)
 

@@ -13,6 +13,12 @@
 
 using namespace b2s;
 
+// output rows per CTA of block2.conv2 on the fp16x2 path (B2S_CONV22_R at build time for A/B measurements)
+#ifndef B2S_CONV22_R
+#define B2S_CONV22_R 5
+#endif
+static constexpr int CONV22_R = B2S_CONV22_R;
+
 struct TcWeight {     // fp32 weight [N][K] as three bf16 planes [N][3K] + tensor map (box {64, 64})
   __nv_bfloat16* w = nullptr; CUtensorMap map; int N = 0, K = 0;
 };
@@ -37,7 +43,9 @@ struct b2s_aliked {
   float *sh0, *sh2, *sh4, *sh6;                         // score head
   float *so0_w, *so0_b, *so2_w, *so2_b, *sf_w, *aggT;   // desc head
   TcWeight tc_so0, tc_sf, tc_agg;                       // desc-head contractions on the tensor cores (fp32 as bf16x3)
-  __nv_bfloat16 *b1c2_pl, *b2c1_pl, *b2c2_pl;           // conv weights as bf16x3 chunk planes (conv_tc.cuh)
+  __nv_bfloat16 *b1c2_pl, *b2c1_pl, *b2c2_pl;           // conv weights as chunk planes (conv_tc.cuh): conv_np planes
+  int conv_np = 2;                                       // operand planes of the implicit-GEMM convolutions: 2 (fp16 pair, range-checked) or 3 (bf16)
+  int* range_flag = nullptr;                             // device flag: an activation left the fp16 range (conv_np == 2)
   __nv_bfloat16 *t1a_pl, *x1p_pl, *t2a_pl;              // activations as chunk planes: block1.conv1 out, pool2(x1), block2.conv1 out
   CUtensorMap m_t1a, m_x1p, m_t2a; int mapHp = 0, mapWp = 0;
   __nv_bfloat16* col3_pl;                               // block3 deformable im2col as bf16x3 planes [3][P3][<= 576]
@@ -193,12 +201,20 @@ int load_weights(b2s_aliked* h, const WeightBlob& wb) {
       const int nch = cin / 8;
       const size_t plane = (size_t)9 * cin * cout;
       std::vector<__nv_bfloat16> o(3 * plane);
+      uint16_t* o16 = reinterpret_cast<uint16_t*>(o.data());
       for (int tap = 0; tap < 9; ++tap)
         for (int cc = 0; cc < nch; ++cc)
           for (int co = 0; co < cout; ++co)
             for (int j = 0; j < 8; ++j) {
               float r = t->data[((size_t)co * cin + cc * 8 + j) * 9 + tap] * b.scale[co];
               const size_t idx = (((size_t)tap * nch + cc) * cout + co) * 8 + j;
+              if (h->conv_np == 2) {           // fp16 pair: h0 = fp16(w), h1 = fp16((w - h0) * 2^11)  (tc::pack_h2)
+                const __half h0 = __float2half_rn(r);
+                const __half h1 = __float2half_rn((r - __half2float(h0)) * 2048.f);
+                o16[idx] = *reinterpret_cast<const uint16_t*>(&h0);
+                o16[plane + idx] = *reinterpret_cast<const uint16_t*>(&h1);
+                continue;
+              }
               for (int pl = 0; pl < 3; ++pl) {
                 const __nv_bfloat16 q = __float2bfloat16_rn(r);
                 o[pl * plane + idx] = q;
@@ -364,9 +380,20 @@ extern "C" int b2s_aliked_create(const b2s_aliked_cfg* cfg, const void* weights,
   cudaFuncSetAttribute(k_gemm_tcp<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcpGemmCfg<64, 3>::SMEM);
   cudaFuncSetAttribute(k_dcn_offcol<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 18 * 9 * 64 * (int)sizeof(float));
   cudaFuncSetAttribute(k_dcn_offcol<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 18 * 9 * 128 * (int)sizeof(float));
-  cudaFuncSetAttribute(k_conv3x3_tc<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<16, 16>::SMEM);
-  cudaFuncSetAttribute(k_conv3x3_tc<16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<16, 32>::SMEM);
-  cudaFuncSetAttribute(k_conv3x3_tc<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<32, 32>::SMEM);
+  cudaFuncSetAttribute(k_conv3x3_tc<16, 16, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<16, 16, 3, 4>::SMEM);
+  cudaFuncSetAttribute(k_conv3x3_tc<16, 32, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<16, 32, 3, 4>::SMEM);
+  cudaFuncSetAttribute(k_conv3x3_tc<32, 32, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<32, 32, 3, 4>::SMEM);
+  cudaFuncSetAttribute(k_conv3x3_tc<16, 16, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<16, 16, 2, 4>::SMEM);
+  cudaFuncSetAttribute(k_conv3x3_tc<16, 32, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<16, 32, 2, 4>::SMEM);
+  cudaFuncSetAttribute(k_conv3x3_tc<32, 32, 2, CONV22_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<32, 32, 2, CONV22_R>::SMEM);
+  {
+    // implicit-GEMM convolutions on two fp16 planes (default) or three bf16 planes (B2S_ALIKED_CONV_NP=3: for weights whose
+    // activations leave the fp16 range - an extraction that does reports B2S_ALIKED_RANGE keypoints and the host raises)
+    const char* e = std::getenv("B2S_ALIKED_CONV_NP");
+    h->conv_np = (e && e[0] == '3') ? 3 : 2;
+    std::vector<int> z(1, 0);
+    if (int r0 = h->warena.upload(&h->range_flag, z)) { delete h; return r0; }
+  }
   int rc = load_weights(h, wb);
   if (rc) { delete h; return rc; }
   h->blob.assign(static_cast<const uint8_t*>(weights), static_cast<const uint8_t*>(weights) + nbytes);
@@ -447,7 +474,7 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
     B2S_TRY(alloc_ws(h, Hp, Wp));
   }
   h->Hr = Hr; h->Wr = Wr; h->Hp = Hp; h->Wp = Wp;
-  pp.out = h->img_pad; pp.resized = h->resized;
+  pp.out = h->img_pad; pp.resized = h->resized; pp.range_flag = h->range_flag;
   launch_k(k_preprocess, dim3(cdiv(Wp, 256), Hp), 256, 0, st, pp);
   ++h->launches; B2S_LAUNCH_CHECK();
 
@@ -457,15 +484,15 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
   // epilogue (planes for block2.conv1) and into the 1x1 downsample.
   const int H2 = Hp / 2, W2 = Wp / 2;
   if (h->mapHp != Hp || h->mapWp != Wp) {
-    auto mk = [&](CUtensorMap* m, const __nv_bfloat16* ptr, int Hh, int Ww, int nch) -> int {
-      const uint64_t dims[4] = {8, (uint64_t)Ww, (uint64_t)Hh, (uint64_t)3 * nch};
+    auto mk = [&](CUtensorMap* m, const __nv_bfloat16* ptr, int Hh, int Ww, int nch, int rows) -> int {
+      const uint64_t dims[4] = {8, (uint64_t)Ww, (uint64_t)Hh, (uint64_t)h->conv_np * nch};
       const uint64_t str[3] = {16, (uint64_t)Ww * 16, (uint64_t)Hh * Ww * 16};
-      const uint32_t box[4] = {8, 130, 6, (uint32_t)nch};
+      const uint32_t box[4] = {8, 130, (uint32_t)rows + 2, (uint32_t)nch};
       return make_tmap_bf16_4d(m, ptr, dims, str, box);
     };
-    B2S_TRY(mk(&h->m_t1a, h->t1a_pl, Hp, Wp, 2));
-    B2S_TRY(mk(&h->m_x1p, h->x1p_pl, H2, W2, 2));
-    B2S_TRY(mk(&h->m_t2a, h->t2a_pl, H2, W2, 4));
+    B2S_TRY(mk(&h->m_t1a, h->t1a_pl, Hp, Wp, 2, 4));
+    B2S_TRY(mk(&h->m_x1p, h->x1p_pl, H2, W2, 2, 4));
+    B2S_TRY(mk(&h->m_t2a, h->t2a_pl, H2, W2, 4, h->conv_np == 2 ? CONV22_R : 4));
     const uint64_t P3 = (uint64_t)(H2 / 4) * (W2 / 4);
     B2S_TRY(make_tmap_bf16_2d(&h->m_col3a, h->col3_pl, 288, 3 * P3, 288 * 2, 64, 128));
     B2S_TRY(make_tmap_bf16_2d(&h->m_col3b, h->col3_pl, 576, 3 * P3, 576 * 2, 64, 128));
@@ -473,17 +500,22 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
   }
   {
     dim3 g(cdiv(Wp, 32), cdiv(Hp, 16));
-    launch_k(k_conv3x3<3, 16, false>, g, dim3(16, 8, 1), 0, st, h->img_pad, Hp, Wp, h->b1c1_w, h->b1c1_b, nullptr, (float*)nullptr, 1, h->t1a_pl);
+    launch_k(k_conv3x3<3, 16, false>, g, dim3(16, 8, 1), 0, st, h->img_pad, Hp, Wp, h->b1c1_w, h->b1c1_b, nullptr, (float*)nullptr, 1, h->t1a_pl,
+             h->conv_np, h->range_flag);
+    const bool h2 = h->conv_np == 2;
     ConvTcParams cp = {};
-    cp.H = Hp; cp.W = Wp; cp.wplanes = h->b1c2_pl; cp.bias = h->b1c2_b; cp.out_chw = h->x1; cp.out_pooled = h->x1p_pl;
-    launch_k(k_conv3x3_tc<16, 16>, dim3(cdiv(Wp, 128), cdiv(Hp, 4)), 192, ConvTcCfg<16, 16>::SMEM, st, h->m_t1a, cp);
+    cp.H = Hp; cp.W = Wp; cp.wplanes = h->b1c2_pl; cp.bias = h->b1c2_b; cp.out_chw = h->x1; cp.out_pooled = h->x1p_pl; cp.range_flag = h->range_flag;
+    if (h2) launch_k(k_conv3x3_tc<16, 16, 2, 4>, dim3(cdiv(Wp, 128), cdiv(Hp, 4)), 192, ConvTcCfg<16, 16, 2, 4>::SMEM, st, h->m_t1a, cp);
+    else launch_k(k_conv3x3_tc<16, 16, 3, 4>, dim3(cdiv(Wp, 128), cdiv(Hp, 4)), 192, ConvTcCfg<16, 16, 3, 4>::SMEM, st, h->m_t1a, cp);
     launch_k(k_pool2_conv1x1<16, 32>, cdiv(H2 * W2, 64), 256, 0, st, h->x1, H2, W2, h->b2ds_w, h->b2ds_b, h->r2);
     cp = ConvTcParams();
-    cp.H = H2; cp.W = W2; cp.wplanes = h->b2c1_pl; cp.bias = h->b2c1_b; cp.out_planes = h->t2a_pl;
-    launch_k(k_conv3x3_tc<16, 32>, dim3(cdiv(W2, 128), cdiv(H2, 4)), 192, ConvTcCfg<16, 32>::SMEM, st, h->m_x1p, cp);
+    cp.H = H2; cp.W = W2; cp.wplanes = h->b2c1_pl; cp.bias = h->b2c1_b; cp.out_planes = h->t2a_pl; cp.range_flag = h->range_flag;
+    if (h2) launch_k(k_conv3x3_tc<16, 32, 2, 4>, dim3(cdiv(W2, 128), cdiv(H2, 4)), 192, ConvTcCfg<16, 32, 2, 4>::SMEM, st, h->m_x1p, cp);
+    else launch_k(k_conv3x3_tc<16, 32, 3, 4>, dim3(cdiv(W2, 128), cdiv(H2, 4)), 192, ConvTcCfg<16, 32, 3, 4>::SMEM, st, h->m_x1p, cp);
     cp = ConvTcParams();
     cp.H = H2; cp.W = W2; cp.wplanes = h->b2c2_pl; cp.bias = h->b2c2_b; cp.residual = h->r2; cp.out_chw = h->x2;
-    launch_k(k_conv3x3_tc<32, 32>, dim3(cdiv(W2, 128), cdiv(H2, 4)), 192, ConvTcCfg<32, 32>::SMEM, st, h->m_t2a, cp);
+    if (h2) launch_k(k_conv3x3_tc<32, 32, 2, CONV22_R>, dim3(cdiv(W2, 128), cdiv(H2, CONV22_R)), 192, ConvTcCfg<32, 32, 2, CONV22_R>::SMEM, st, h->m_t2a, cp);
+    else launch_k(k_conv3x3_tc<32, 32, 3, 4>, dim3(cdiv(W2, 128), cdiv(H2, 4)), 192, ConvTcCfg<32, 32, 3, 4>::SMEM, st, h->m_t2a, cp);
     h->launches += 5; B2S_LAUNCH_CHECK();
   }
   // ---- block3 (1/8) and block4 (1/32): DCN via im2col + GEMM, HWC ----
@@ -540,7 +572,7 @@ extern "C" int b2s_aliked_extract(b2s_aliked* h, const void* img, int fmt, int H
     RefineParams rp;
     rp.dk = h->dk; rp.sel_idx = h->sel_idx; rp.sel_sc = h->sel_sc; rp.score = h->score; rp.H = Hr; rp.W = Wr;
     rp.scale_x = (float)((double)Wr / (double)W); rp.scale_y = (float)((double)Hr / (double)H);
-    rp.kp_norm = h->kp_norm; rp.kp_out = kpts; rp.disp = h->disp; rp.sampled = h->sampled; rp.n_out = n_out;
+    rp.kp_norm = h->kp_norm; rp.kp_out = kpts; rp.disp = h->disp; rp.sampled = h->sampled; rp.n_out = n_out; rp.range_flag = h->conv_np == 2 ? h->range_flag : nullptr;
     launch_k(k_dkd_refine, cdiv(h->n_limit, RF_KP), 256, 0, st, rp);
     h->launches += 5; B2S_LAUNCH_CHECK();
     // upstream puts DKD's 2nd return value (dispersity) under "keypoint_scores" 
@@ -705,6 +737,14 @@ extern "C" int b2s_aliked_set_undistort(b2s_aliked* h, b2s_remap* r) {
   return 0;
 }
 
+
+// n_out of an extraction whose two-plane (fp16) convolutions saw an activation beyond the fp16 range (k_dkd_refine)
+static constexpr int32_t ALIKED_RANGE = -2;
+static int aliked_range_error() {
+  set_error("b2s_aliked: an activation left the fp16 range of the fp16x2 convolutions - re-create the extractor with B2S_ALIKED_CONV_NP=3 (three bf16 planes)");
+  return B2S_ERANGE;
+}
+
 // host-API ingest: the uploaded frame goes through the attached cv2.remap stage (u8 BGR only) before K0
 static int aliked_ingest(b2s_aliked* h, int fmt, int* H, int* W, int* row_stride, cudaStream_t st, const void** img_dev) {
   *img_dev = h->himg;
@@ -753,7 +793,8 @@ extern "C" int b2s_aliked_extract_host_keypoints(b2s_aliked* h, float* kpts, int
   B2S_CUDA(cudaSetDevice(h->device));
   B2S_CUDA(cudaEventSynchronize(h->ev_kp));
   const int32_t n = *h->pin_n;
-  *n_out = n;
+  *n_out = n > 0 ? n : 0;
+  if (n == ALIKED_RANGE) return aliked_range_error();
   if (n > 0) std::memcpy(kpts, h->pin_kp, (size_t)n * 2 * sizeof(float));
   return 0;
 }
@@ -808,7 +849,8 @@ extern "C" int b2s_aliked_extract_host_ex(b2s_aliked* h, const void* img, int fm
   int32_t n = 0;
   B2S_CUDA(cudaMemcpyAsync(&n, h->hn, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   B2S_CUDA(cudaStreamSynchronize(st));
-  *n_out = n;
+  *n_out = n > 0 ? n : 0;
+  if (n == ALIKED_RANGE) return aliked_range_error();
   if (n > 0) {
     B2S_CUDA(cudaMemcpyAsync(kpts, h->hkp, (size_t)n * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
     B2S_CUDA(cudaMemcpyAsync(desc, h->hdesc, (size_t)n * 128 * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace b2s {
 
@@ -20,6 +21,7 @@ struct PreParams {
   float scale_h, scale_w;
   float* out;
   float* resized;   // optional tap: [3][Hr][Wr]
+  int* range_flag;  // nullable: the extraction's fp16-range flag, cleared here (first kernel of an extraction)
 };
 
 __shared__ float pre_lut[256];   // u8 -> float(u8)/255 (filled by k_preprocess; replaces 100+ divisions per pixel)
@@ -52,6 +54,7 @@ __device__ __forceinline__ float pre_blur(const PreParams& p, int c, int y, int 
 
 __global__ void __launch_bounds__(256) k_preprocess(PreParams p) {
   pdl_wait();
+  if (p.range_flag && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.range_flag = 0;
   pre_lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);   // blockDim.x == 256
   __syncthreads();
   const int xp = blockIdx.x * blockDim.x + threadIdx.x;
@@ -130,7 +133,7 @@ template <int CIN, int COUT, bool POOL2>
 __global__ void __launch_bounds__(128 * (COUT / 16), COUT == 16 ? 5 : 1) k_conv3x3(const float* __restrict__ in, int H, int W,
                                                                const float* __restrict__ w, const float* __restrict__ bias,
                                                                const float* __restrict__ residual, float* __restrict__ out,
-                                                               int act, __nv_bfloat16* __restrict__ out_planes) {
+                                                               int act, __nv_bfloat16* __restrict__ out_planes, int np, int* range_flag) {
   pdl_wait();
   constexpr int CC = CIN < 8 ? CIN : 8;
   constexpr int TH = 16, TW = 32, RS = TW + 4;
@@ -217,6 +220,15 @@ __global__ void __launch_bounds__(128 * (COUT / 16), COUT == 16 ? 5 : 1) k_conv3
           float r[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) r[j] = v[8 * ch + j];
+          if (np == 2) {                     // two fp16 planes (scaled residual), range-checked
+            uint32_t w0[4], w1[4], ov = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { tc::pack_h2(r[2 * j], r[2 * j + 1], w0[j], w1[j]); ov |= tc::h2_ovf(w0[j]); }
+            *reinterpret_cast<uint4*>(d) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+            *reinterpret_cast<uint4*>(d + plane) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+            if (ov && range_flag) *range_flag = 1;
+            continue;
+          }
 #pragma unroll
           for (int pl = 0; pl < 3; ++pl) {
             uint32_t w[4];
@@ -961,13 +973,16 @@ struct RefineParams {
   float* kp_out;               // [K,2] original-image pixels
   float* disp; float* sampled; // [K]
   int32_t* n_out;
+  const int* range_flag;       // nullable: fp16-range flag of the convolutions (all of them ran before this kernel)
 };
 
 constexpr int RF_KP = 32;     // keypoints per CTA: 8 threads rank one keypoint, one of them refines it
 __global__ void __launch_bounds__(256) k_dkd_refine(RefineParams p) {
   pdl_wait();
   const int K = p.dk[4];
-  if (blockIdx.x == 0 && threadIdx.x == 0) *p.n_out = K;
+  // a frame whose activations left the fp16 range of the two-plane convolutions reports ALIKED_RANGE keypoints (every
+  // later kernel then skips it): the host raises instead of returning features computed from saturated planes
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.n_out = (p.range_flag && *p.range_flag) ? -2 : K;
   if (blockIdx.x * RF_KP >= K) return;                 // uniform per CTA
   __shared__ int t_idx[1024];
   __shared__ float t_sc[1024];

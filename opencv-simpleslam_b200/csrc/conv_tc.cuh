@@ -1,5 +1,6 @@
 // conv_tc.cuh - 3x3 convolution (pad 1) as an implicit GEMM on tcgen05/TMEM, fp32-faithful (operands
-// carried as three bf16 planes, six cross products, tc_common.cuh).  ALIKED block1.conv2, block2.conv1/2.
+// carried as NP planes, tc_common.cuh: NP = 2 two fp16 planes / three cross products with a device-side range
+// check - the default; NP = 3 three bf16 planes / six cross products).  ALIKED block1.conv2, block2.conv1/2.
 //
 // Activations live in HBM as "chunk planes": [plane p][8-channel chunk c][H][W][8] bf16, i.e. one pixel of
 // one chunk is 16 bytes and pixels of a row are contiguous.  A CTA produces R output rows x 128 pixels:
@@ -18,16 +19,19 @@
 
 namespace b2s {
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, int NP = 3, int R_ = 4>
 struct ConvTcCfg {
-  static constexpr int R = 4, TW = 128, PW = TW + 2;
+  static constexpr int R = R_, TW = 128, PW = TW + 2;      // R output rows per CTA (5 on the fp16x2 path of <32,32>: 128 CTAs = one wave at half resolution)
   static constexpr int NCH = CIN / 8;
   static constexpr int RS = PW * 16;                       // bytes of one input row of one chunk
   static constexpr int CS = (R + 2) * RS;                  // chunk stride
   static constexpr int A_PLANE = NCH * CS;
   static constexpr int W_PLANE = 9 * CIN * COUT * 2;
-  static constexpr int TMEM_COLS = R * 2 * COUT < 32 ? 32 : R * 2 * COUT;   // 128 (COUT 16) / 256 (COUT 32): powers of two
-  static constexpr int SMEM = 3 * A_PLANE + 3 * W_PLANE + 128 /*align*/ + 128 /*barriers*/ + COUT * 4;
+  static constexpr int ACC = R * 2 * COUT;                 // accumulator columns: (main, correction) per output row
+  static constexpr int TMEM_COLS = ACC <= 32 ? 32 : ACC <= 64 ? 64 : ACC <= 128 ? 128 : ACC <= 256 ? 256 : 512;
+  static_assert(ACC <= 512, "accumulators exceed the tensor memory");
+  static constexpr int SMEM = NP * A_PLANE + NP * W_PLANE + 128 /*align*/ + 128 /*barriers*/ + COUT * 4;
+  static_assert(SMEM <= 227 * 1024, "tile does not fit the shared memory");
   static constexpr int THREADS = 192;                      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 };
 
@@ -39,31 +43,37 @@ struct ConvTcParams {
   float* out_chw;                   // fp32 CHW [COUT][H][W] (nullable)
   __nv_bfloat16* out_planes;        // chunk planes [3][COUT/8][H][W][8] (nullable)
   __nv_bfloat16* out_pooled;        // chunk planes of the 2x2 average [3][COUT/8][H/2][W/2][8] (nullable)
+  int* range_flag;                  // NP == 2: set to 1 when a value written as fp16 planes leaves the fp16 range
 };
 
-// 8 channels of one pixel -> three planes (16 bytes each) at d + p * plane
-__device__ __forceinline__ void conv_store_planes8(__nv_bfloat16* d, size_t plane, const float* f) {
-  uint32_t w[3][4];
+// 8 channels of one pixel -> NP planes (16 bytes each) at d + p * plane; NP == 2: returns nonzero when a value overflowed fp16
+template <int NP>
+__device__ __forceinline__ uint32_t conv_store_planes8(__nv_bfloat16* d, size_t plane, const float* f) {
+  uint32_t w[NP][4];
+  uint32_t ov = 0u;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    uint32_t pw[3];
-    tc::pack_planes2<3>(f[2 * j], f[2 * j + 1], pw);
-    w[0][j] = pw[0]; w[1][j] = pw[1]; w[2][j] = pw[2];
+    uint32_t pw[NP];
+    tc::pack_planes2<NP>(f[2 * j], f[2 * j + 1], pw);
+#pragma unroll
+    for (int pl = 0; pl < NP; ++pl) w[pl][j] = pw[pl];
+    if (NP == 2) ov |= tc::h2_ovf(pw[0]);
   }
 #pragma unroll
-  for (int pl = 0; pl < 3; ++pl) *reinterpret_cast<uint4*>(d + pl * plane) = make_uint4(w[pl][0], w[pl][1], w[pl][2], w[pl][3]);
+  for (int pl = 0; pl < NP; ++pl) *reinterpret_cast<uint4*>(d + pl * plane) = make_uint4(w[pl][0], w[pl][1], w[pl][2], w[pl][3]);
+  return ov;
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, int NP = 3, int R_ = 4>
 __global__ void __launch_bounds__(192) k_conv3x3_tc(const __grid_constant__ CUtensorMap mapIn, ConvTcParams p) {
-  using Cfg = ConvTcCfg<CIN, COUT>;
-  using Terms = tc::PlaneTerms<3>;
+  using Cfg = ConvTcCfg<CIN, COUT, NP, R_>;
+  using Terms = tc::PlaneTerms<NP>;
   extern __shared__ uint8_t smem_raw[];
   // aligned by pointer ARITHMETIC on the __shared__ array: an integer round trip would make every staging access a generic LD / ST
   uint8_t* smem = smem_raw + ((128u - (tc::smem_u32(smem_raw) & 127u)) & 127u);
-  uint8_t* sA = smem;                                       // [3 planes][NCH][R+2][130][8]
-  uint8_t* sW = sA + 3 * Cfg::A_PLANE;                      // [3 planes][9*NCH][COUT][8]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 3 * Cfg::W_PLANE);
+  uint8_t* sA = smem;                                       // [NP planes][NCH][R+2][130][8]
+  uint8_t* sW = sA + NP * Cfg::A_PLANE;                     // [NP planes][9*NCH][COUT][8]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + NP * Cfg::W_PLANE);
   uint64_t* w_full = bars;
   uint64_t* in_full = bars + 1;
   uint64_t* row_full = bars + 2;                            // [R]
@@ -89,16 +99,16 @@ __global__ void __launch_bounds__(192) k_conv3x3_tc(const __grid_constant__ CUte
 
   if (warp == 0) {
     if (tc::elect_one()) {
-      tc::mbar_expect_tx(w_full, 3 * Cfg::W_PLANE);          // constant weights: before the dependency wait
-      tc::bulk_load(sW, p.wplanes, 3 * Cfg::W_PLANE, w_full);
+      tc::mbar_expect_tx(w_full, NP * Cfg::W_PLANE);         // constant weights: before the dependency wait
+      tc::bulk_load(sW, p.wplanes, NP * Cfg::W_PLANE, w_full);
       pdl_wait();                                             // the input map is written by the previous kernel
-      tc::mbar_expect_tx(in_full, 3 * Cfg::A_PLANE);
+      tc::mbar_expect_tx(in_full, NP * Cfg::A_PLANE);
 #pragma unroll
-      for (int pl = 0; pl < 3; ++pl) tc::tma_load_4d(sA + pl * Cfg::A_PLANE, &mapIn, in_full, 0, x0 - 1, y0 - 1, pl * Cfg::NCH);
+      for (int pl = 0; pl < NP; ++pl) tc::tma_load_4d(sA + pl * Cfg::A_PLANE, &mapIn, in_full, 0, x0 - 1, y0 - 1, pl * Cfg::NCH);
     }
   } else if (warp == 1) {
     if (tc::elect_one()) {
-      constexpr uint32_t idesc = tc::idesc_bf16(128, COUT, 0, 0);
+      constexpr uint32_t idesc = tc::idesc_planes<NP>(128, COUT, 0, 0);
       const uint32_t a_base = tc::smem_u32(sA), w_base = tc::smem_u32(sW);
       tc::mbar_wait(w_full, 0);
       tc::mbar_wait(in_full, 0);
@@ -134,6 +144,7 @@ __global__ void __launch_bounds__(192) k_conv3x3_tc(const __grid_constant__ CUte
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const size_t HW = (size_t)p.H * p.W;
     float prev[COUT];                                         // previous (even) row, kept for the 2x2 pooling
+    uint32_t ovf = 0u;
 #pragma unroll 1
     for (int r = 0; r < Cfg::R; ++r) {
       tc::mbar_wait(&row_full[r], 0);
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(192) k_conv3x3_tc(const __grid_constant__ CUte
                      : "r"(tmem_base + lane_addr + r * 2 * COUT + COUT + c0) : "memory");
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[c0 + j] = (__uint_as_float(a[j]) + __uint_as_float(b[j])) + s_bias[c0 + j];
+        for (int j = 0; j < 16; ++j) f[c0 + j] = (NP == 2 ? fmaf(__uint_as_float(b[j]), Terms::CORR, __uint_as_float(a[j])) : __uint_as_float(a[j]) + __uint_as_float(b[j])) + s_bias[c0 + j];
       }
       const int gy = y0 + r;
       const bool inside = gy < p.H && gx < p.W;
@@ -171,7 +182,7 @@ __global__ void __launch_bounds__(192) k_conv3x3_tc(const __grid_constant__ CUte
         if (p.out_planes) {
 #pragma unroll
           for (int ch = 0; ch < COUT / 8; ++ch)
-            conv_store_planes8(p.out_planes + ((size_t)ch * HW + pix) * 8, (size_t)(COUT / 8) * HW * 8, f + 8 * ch);
+            ovf |= conv_store_planes8<NP>(p.out_planes + ((size_t)ch * HW + pix) * 8, (size_t)(COUT / 8) * HW * 8, f + 8 * ch);
         }
       }
       if (p.out_pooled) {                                     // uniform branch; all lanes shuffle
@@ -192,11 +203,12 @@ __global__ void __launch_bounds__(192) k_conv3x3_tc(const __grid_constant__ CUte
             const size_t HW2 = (size_t)H2 * W2, qpix = (size_t)qy * W2 + qx;
 #pragma unroll
             for (int ch = 0; ch < COUT / 8; ++ch)
-              conv_store_planes8(p.out_pooled + ((size_t)ch * HW2 + qpix) * 8, (size_t)(COUT / 8) * HW2 * 8, q + 8 * ch);
+              ovf |= conv_store_planes8<NP>(p.out_pooled + ((size_t)ch * HW2 + qpix) * 8, (size_t)(COUT / 8) * HW2 * 8, q + 8 * ch);
           }
         }
       }
     }
+    if (NP == 2 && ovf && p.range_flag) *p.range_flag = 1;
   }
   tc::tc_fence_before();
   __syncthreads();

@@ -148,6 +148,8 @@ class ALIKED(_Module):
         self._n_host.copy_(self._n, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         n = int(self._n_host[0])
+        if n == _lib.ALIKED_RANGE:
+            raise _lib.B2SError(_lib.ALIKED_RANGE_MSG)
         return {"keypoints": self._kp[:n].clone()[None], "descriptors": self._desc[:n].clone()[None],
                 "keypoint_scores": self._sc[:n].clone()[None],
                 "image_size": torch.tensor([[float(W), float(H)]], device=self.device)}

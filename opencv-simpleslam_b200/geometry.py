@@ -35,13 +35,14 @@ class FundamentalRansac:
 
     def __init__(self, device=None, max_points: int = 4096, n_hyp: int = DEFAULT_HYPOTHESES, seed: int = 0):
         self.device_index, self.n_hyp, self.seed = _device_index(device), int(n_hyp), int(seed)
+        self.max_hyp = max(self.n_hyp, 1000)       # handle capacity: the parallel estimator's samples / cv2's default maxIters
         self._handle, self.max_points = None, 0
         self._create(max(int(max_points), 8))
 
     def _create(self, max_points: int):
         self._destroy()
         h = C.c_void_p()
-        check(lib.b2s_fm_create(self.device_index, max_points, self.n_hyp, C.byref(h)), "b2s_fm_create")
+        check(lib.b2s_fm_create(self.device_index, max_points, self.max_hyp, C.byref(h)), "b2s_fm_create")
         self._handle, self.max_points = h, max_points
 
     def _destroy(self):
@@ -90,8 +91,8 @@ class FundamentalRansac:
             raise ValueError("pts1 and pts2 must have the same length")
         if n < 15:
             raise ValueError("run_cv covers OpenCV's RANSAC branch (n >= 15); below that cv2 runs LMedS")
-        if n > self.max_points or max_iters > self.n_hyp:
-            self.n_hyp = max(self.n_hyp, int(max_iters))
+        if n > self.max_points or max_iters > self.max_hyp:
+            self.max_hyp = max(self.max_hyp, int(max_iters))
             self._create(int(2 ** np.ceil(np.log2(max(n, self.max_points)))))
         mask = np.empty((n,), np.uint8)
         F = np.empty((9,), np.float64)

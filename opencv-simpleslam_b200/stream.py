@@ -154,6 +154,8 @@ class FramePairStream:
         out = []
         for i in range(nb):
             n = int(cn[i])
+            if n == _lib.ALIKED_RANGE:
+                raise _lib.B2SError(_lib.ALIKED_RANGE_MSG)
             kp_arr = kp_np[i, :n].copy()
             des = de_np[i, :n].copy()
             kps = KeyPointArray(kp_arr) if self.array_native else fu._convert_lg_kps_to_opencv(kp_arr)

@@ -52,4 +52,6 @@ def match_keyframe_window(frames: List[torch.Tensor], det, mat, H: int, W: int, 
     r = mat.match_batch_packed(kp_all, de_all, offs, pi, pj, stride=max_kp, max_batch=max_batch, counts=caps, counts_dev=counts)
     if check_range and mat.precision == "fp32":
         mat.resolve_range(r, kp_all, de_all, offs, pi, pj, max_batch, caps, counts)
+    if check_range and bool((counts < 0).any().item()):      # a keyframe's fp16x2 convolutions left the fp16 range (any rank)
+        raise _lib.B2SError(_lib.ALIKED_RANGE_MSG)
     return {pair: (r["matches"][p], r["scores"][p], r["n"][p]) for p, pair in enumerate(my_pairs)}

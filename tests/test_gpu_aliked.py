@@ -138,3 +138,32 @@ def test_degenerate_images_do_not_crash():
         assert len(kp) <= 256 and np.isfinite(kp).all() and np.isfinite(de).all()
     with pytest.raises(Exception):
         det.extract_host(np.zeros((4, 4, 3), np.uint8))     # too small: error code, not a crash
+
+
+def test_fp16x2_convolutions_agree_with_bf16x3_and_report_range_overflow(aliked_state, monkeypatch):
+    """block1.conv2 / block2.conv1 / block2.conv2 run on two fp16 planes by default (three cross products), on three
+    bf16 planes with B2S_ALIKED_CONV_NP=3: same keypoints, descriptors within fp32 rounding.  Activations beyond the
+    fp16 range must not produce features: the extraction raises and names the switch."""
+    from b200slam import _lib, frontend
+    img = synth.frame(5, 240, 320)
+    det2 = frontend.ALIKED(max_num_keypoints=512, weights=aliked_state, device="cuda:0")
+    monkeypatch.setenv("B2S_ALIKED_CONV_NP", "3")
+    det3 = frontend.ALIKED(max_num_keypoints=512, weights=aliked_state, device="cuda:0")
+    monkeypatch.delenv("B2S_ALIKED_CONV_NP")
+    f2, f3 = det2.extract_bgr(img), det3.extract_bgr(img)
+    k2, k3 = f2["keypoints"][0].cpu().numpy(), f3["keypoints"][0].cpu().numpy()
+    s2, s3 = set(map(tuple, np.rint(k2 * 8).astype(int).tolist())), set(map(tuple, np.rint(k3 * 8).astype(int).tolist()))
+    assert len(s2 & s3) >= 0.99 * len(s3) and len(s3) > 100
+    x2a, x2b = det2.debug("x2"), det3.debug("x2")
+    assert rel_err(x2a, x2b) < 2e-6
+    # blow the first layer up: |activation| ~ 1e7 > 65504
+    big = {k: (v * 1e7 if k == "block1.conv1.weight" else v) for k, v in aliked_state.items()}
+    bad = frontend.ALIKED(max_num_keypoints=512, weights=big, device="cuda:0")
+    with pytest.raises(_lib.B2SError, match="B2S_ALIKED_CONV_NP=3"):
+        bad.extract_bgr(img)
+    with pytest.raises(_lib.B2SError, match="B2S_ALIKED_CONV_NP=3"):
+        bad.extract_host(img)
+    monkeypatch.setenv("B2S_ALIKED_CONV_NP", "3")
+    ok = frontend.ALIKED(max_num_keypoints=512, weights=big, device="cuda:0")
+    monkeypatch.delenv("B2S_ALIKED_CONV_NP")
+    ok.extract_bgr(img)        # three bf16 planes keep fp32's exponent range: no error
