@@ -4,7 +4,7 @@
 # launch list, sanitizer over the tensor-core entry points / match / batch / geometry.
 set -x
 mkdir -p gpurun_out
-T=r2f
+T=r2g
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${T}_smi.txt
 python -m pytest tests -m gpu -q > gpurun_out/${T}_pytest_gpu.log 2>&1; tail -2 gpurun_out/${T}_pytest_gpu.log
 python bench.py > gpurun_out/${T}_bench_fp32.json 2> gpurun_out/${T}_bench_fp32.err
