@@ -150,7 +150,9 @@ def find_fundamental_mat(pts1, pts2, thresh: float = 1.0):
 def find_fundamental_mat_cv(pts1, pts2, thresh: float = 3.0, confidence: float = 0.99):
     """`cv2.findFundamentalMat(pts1, pts2, cv2.FM_RANSAC, thresh, confidence)` with identical results: OpenCV's RANSAC
     (n >= 15) on the GPU, the degenerate small cases (n < 15: OpenCV's LMedS branch, whose winner for n <= 13 is decided
-    by the rounding noise of its own arithmetic; n == 7; n < 7) by cv2 itself."""
+    by the rounding noise of its own arithmetic; n == 7; n < 7) by cv2 itself.  One documented difference: when no valid
+    7-point sample exists (all points collinear / identical) cv2 returns F = None together with an UNINITIALISED mask
+    array; this function returns (None, None), i.e. `filter_matches_ransac` keeps no match."""
     pts1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
     if len(pts1) < 15:
         import cv2

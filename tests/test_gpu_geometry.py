@@ -388,5 +388,9 @@ def test_filter_matches_ransac_gpu_cv2_mode_is_reference_identical():
             assert [m.queryIdx for m in got] == want
             got_a = fu.filter_matches_ransac(KeyPointArray(p1), KeyPointArray(p2), DMatchArray(np.stack([np.arange(n)] * 2, 1)), thresh)
             assert isinstance(got_a, DMatchArray) and got_a.queryIdx.tolist() == want
+        # degenerate input (no valid 7-point sample): cv2 returns F = None with an UNINITIALISED mask, which the reference then
+        # reads; the GPU path returns no model and filter_matches_ransac keeps nothing (features_utils.py:197-198's branch)
+        same = [cv2.KeyPoint(10.0, 20.0, 1)] * 30
+        assert fu.filter_matches_ransac(same, same, [cv2.DMatch(i, i, 0.0) for i in range(30)], 1.0) == []
     finally:
         fu.set_ransac_mode("cv2")
