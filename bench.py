@@ -422,7 +422,7 @@ def run_ours(args):
 
     # ---- e2e through the SEQUENCE form of the same API (features_utils.FramePairStream): host frames in, cv2 lists out,
     #      chunks of P frames, H2D / D2H through pinned buffers on a copy stream inside the timed region ----------
-    seq_pairs = max(2 * P, min(K * P, 64))
+    seq_pairs = max(2 * P, min(4 * K * P, 256))     # a recorded sequence is long: pipeline fill / drain (one chunk each) must not dominate
     seq_frames = [frames_np[t % len(frames_np)] for t in range(seq_pairs + 1)]
     fps = fu.FramePairStream(ns, det, mat, batch=P, lanes=args.lanes)
     for _ in fps.run(seq_frames[: 2 * P + 1]):     # warm-up: allocations, graph capture of the lanes with the fused re-normalisation
