@@ -139,3 +139,37 @@ def test_oracle_against_committed_golden():
     assert match_set(r["matches"][0]) == match_set(z["matches"])
     np.testing.assert_allclose(r["scores"][0].numpy(), z["scores"], atol=1e-3)
     assert len(z["matches"]) >= meta["min_matches"]
+
+
+def test_preprocess_blur_and_resize_against_opencv():
+    """Independent pin of the kornia-style anti-aliased resize restated in oracle/preprocess.py (upstream
+    ImagePreprocessor: gaussian_blur2d with a reflect border, then bilinear interpolation with half-pixel centres):
+    OpenCV implements the same two operations (cv2.GaussianBlur with BORDER_REFLECT_101 and an explicit sigma;
+    cv2.resize INTER_LINEAR) - same kernel formula, same border rule, same sampling grid."""
+    import cv2
+    import torch.nn.functional as F
+    from oracle import preprocess as P
+    rng = np.random.default_rng(0)
+    for (h, w) in [(376, 1241), (480, 640), (1080, 1920)]:
+        img = rng.random((h, w, 3), dtype=np.float32)
+        t = torch.from_numpy(img).permute(2, 0, 1)[None]
+        hn, wn = P.resized_shape(h, w, 1024)
+        bp = P.blur_params(h, w, hn, wn)
+        if bp is not None:
+            ky, kx, sy, sx = bp
+            mine = P.gaussian_blur2d(t, ky, kx, sy, sx)[0].permute(1, 2, 0).numpy()
+            theirs = cv2.GaussianBlur(img, (kx, ky), sigmaX=sx, sigmaY=sy, borderType=cv2.BORDER_REFLECT_101)
+            assert np.abs(mine - theirs).max() < 2e-6, (h, w)
+            # the 1-D kernel itself
+            assert np.allclose(P.gaussian_kernel1d(kx, sx).numpy(), cv2.getGaussianKernel(kx, sx, cv2.CV_32F).ravel(), atol=1e-7)
+            src = theirs
+        else:
+            src = img
+        # bilinear, half-pixel centres (F.interpolate align_corners=False == cv2.INTER_LINEAR) on the SAME blurred input
+        mine = F.interpolate(torch.from_numpy(src).permute(2, 0, 1)[None], size=(hn, wn), mode="bilinear", align_corners=None)[0].permute(1, 2, 0).numpy()
+        theirs = cv2.resize(src, (wn, hn), interpolation=cv2.INTER_LINEAR)
+        assert np.abs(mine - theirs).max() < 1e-4, (h, w)      # float32 source coordinates differ by ~1e-5 px between the two; white noise turns that into ~2e-5.  A half-pixel or align_corners mix-up would be ~1e-1
+        # and the composed function the oracle uses
+        full, scales = P.resize_long_side(t, 1024)
+        assert np.abs(full[0].permute(1, 2, 0).numpy() - theirs).max() < 1e-4
+        assert np.allclose(scales.numpy(), [wn / w, hn / h])
