@@ -192,6 +192,19 @@ def test_keyframe_window_all_pairs_single_gpu(pipelines):
     for (i, j), (m, s, n) in res.items():
         ref = mat.match_host(feats[i][0], feats[i][1], feats[j][0], feats[j][1])
         assert np.array_equal(m[: int(n)].cpu().numpy(), ref["matches"])
+    # and against the ORACLE (not only the GPU's own single-pair path): the window's raw matches of two pairs, filtered like
+    # feature_matcher does (score > min_conf), equal the oracle adapter's match sets by keypoint position
+    odet, omat = pipelines[5], pipelines[6]
+    of = [ofu.feature_extractor(args, f, odet) for f in frames_np]
+    pos = lambda pt: tuple(np.rint(np.asarray(pt) * 8).astype(int))   # noqa: E731
+    for (i, j) in [(0, 1), (2, 3)]:
+        m, sc, n = res[(i, j)]
+        mm, ss = m[: int(n)].cpu().numpy(), sc[: int(n)].cpu().numpy()
+        keep = ss > np.float32(args.min_conf)
+        sg = {(pos(feats[i][0][a]), pos(feats[j][0][b])) for a, b in mm[keep]}
+        mo = ofu.feature_matcher(args, of[i][0], of[j][0], of[i][1], of[j][1], omat)
+        so = {(pos(of[i][0][q.queryIdx].pt), pos(of[j][0][q.trainIdx].pt)) for q in mo}
+        assert len(so) > 20 and sg == so, f"window pair {(i, j)}: {len(sg ^ so)} of {len(so)} differ from the oracle"
 
 
 def test_array_native_path_equals_list_path(pipelines):
