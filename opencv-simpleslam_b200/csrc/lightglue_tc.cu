@@ -123,6 +123,8 @@ __global__ void __launch_bounds__(256) k_ln_gelu_512_bf16(const float* __restric
 struct TcLinear {            // bf16 weight planes [N, NP*K] + their tensor map (box {64, BN})
   __nv_bfloat16* w = nullptr; const float* bias = nullptr; int N = 0, K = 0, BN = 0;
   CUtensorMap map;
+  CUtensorMap map64;         // BN == 128 only: box {64, 64} for launches whose 128-wide tiles would leave half of the SMs idle
+  bool has64 = false;
 };
 struct TcLayer {
   TcLinear qkv, w1, w2, cqkv, cw1, cw2;
@@ -160,6 +162,10 @@ static int make_linear(LgTensorCore* tc, const float* w_dev, const float* bias, 
   B2S_TRY(tc->warena.alloc(&out->w, n * np));
   k_weight_planes<<<(unsigned)((n + 255) / 256), 256>>>(w_dev, out->w, N, K, np, tc->range_flag);
   B2S_LAUNCH_CHECK();
+  if (out->BN == 128 && N % 64 == 0) {
+    B2S_TRY(make_tmap_bf16_2d(&out->map64, out->w, (uint64_t)np * K, N, (uint64_t)np * K * 2, 64, 64));
+    out->has64 = true;
+  }
   return make_tmap_bf16_2d(&out->map, out->w, (uint64_t)np * K, N, (uint64_t)np * K * 2, 64, out->BN);
 }
 
@@ -351,8 +357,13 @@ static int tc_gemm(LgTensorCore* tc, cudaStream_t st, const CUtensorMap& a1, con
   if (tiles <= 0) return 0;
   p.range_flag = tc->range_flag;
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
-  // (128-wide tiles for the N = 256 / 768 GEMMs of a large batch were measured: no gain over the 64 / 96-wide defaults)
-  launch_gemm(tc->np, w.BN, st, a1, a2, w.map, p, tiles);
+  // a single pair (32 row tiles): 128-wide tiles of an N = 256 GEMM are 64 CTAs on 148 SMs - 64-wide ones fill them.  An
+  // output element's accumulation sequence does not depend on the tile width, so the result bits are the same.
+  // More generally: with T 128-wide tiles on S SMs the busiest CTA works ceil(T / S) tiles, with 64-wide ones ceil(2 T / S) half
+  // tiles - take the narrow ones when that is less and the launch is small (a large batch is bound by per-tile efficiency).
+  const int t128 = tiles * cdiv(w.N, 128), sms = sm_count();
+  if (w.BN == 128 && w.has64 && t128 < 2 * sms && cdiv(2 * t128, sms) < 2 * cdiv(t128, sms)) launch_gemm(tc->np, 64, st, a1, a2, w.map64, p, tiles);
+  else launch_gemm(tc->np, w.BN, st, a1, a2, w.map, p, tiles);
   if (tc->prof) tc->prof->mark(PROF_GEMM, st);
   if (launches) ++*launches;
   B2S_LAUNCH_CHECK();
