@@ -366,9 +366,16 @@ __global__ void __launch_bounds__(256) k_lg_argmax2(AssignParams p) {
     if (v > best) { best = v; bj = j; }
   };
   const int n4 = n & ~3;
+  // the other side's statistics are contiguous in j: three 128-bit loads per four scores instead of twelve scalar ones
+  auto consider4 = [&](float sv, float om, float ol, float os, int j) {
+    const float v = d ? assign_val(sv, om, ol, smax, slog, os, sls) : assign_val(sv, smax, slog, om, ol, sls, os);
+    if (v > best) { best = v; bj = j; }
+  };
   for (int j = lane * 4; j < n4; j += 128) {
     const float4 v = *reinterpret_cast<const float4*>(r + j);
-    consider(v.x, j); consider(v.y, j + 1); consider(v.z, j + 2); consider(v.w, j + 3);
+    const float4 om = *reinterpret_cast<const float4*>(omax + j), ol = *reinterpret_cast<const float4*>(olog + j), os = *reinterpret_cast<const float4*>(ols + j);
+    consider4(v.x, om.x, ol.x, os.x, j); consider4(v.y, om.y, ol.y, os.y, j + 1);
+    consider4(v.z, om.z, ol.z, os.z, j + 2); consider4(v.w, om.w, ol.w, os.w, j + 3);
   }
   for (int j = n4 + lane; j < n; j += 32) consider(r[j], j);
 #pragma unroll
